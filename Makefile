@@ -1,0 +1,45 @@
+# Build of the B200 path-tracing core, the C++ host library, the offlinerender driver and the CPU oracle.
+#   make            -> product libraries + driver
+#   make oracle     -> oracle/_build/liboracle.so (test infrastructure)
+# All artefacts are git-ignored but travel to the GPU box with the gpurun snapshot.
+
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       := $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
+LIBDIR    := vviewer_b200/_lib
+ORCDIR    := oracle/_build
+
+NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --use_fast_math=false \
+             -Xcompiler -fPIC,-fvisibility=hidden,-O3 -Xptxas -v -Iinclude
+CXXFLAGS  := -O2 -std=c++17 -fPIC -fvisibility=hidden -Wall -Wno-unused-variable -Wno-unused-function -Iinclude
+
+CUDA_SRCS := $(wildcard vviewer_b200/csrc/*.cu)
+CUDA_HDRS := $(wildcard vviewer_b200/csrc/*.cuh) include/ptc.h
+HOST_SRCS := vviewer_b200/host/vengine.cpp vviewer_b200/host/io_image.cpp vviewer_b200/host/io_obj.cpp \
+             vviewer_b200/host/scenes.cpp vviewer_b200/host/capi.cpp
+HOST_HDRS := $(wildcard vviewer_b200/host/*.hpp) include/ptc.h include/vengine_host.h
+
+all: $(LIBDIR)/libptc_cuda.so $(LIBDIR)/libvengine_host.so $(LIBDIR)/offlinerender
+
+$(LIBDIR)/libptc_cuda.so: $(CUDA_SRCS) $(CUDA_HDRS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ vviewer_b200/csrc/ptc_cuda.cu -lcudart
+
+$(LIBDIR)/libvengine_host.so: $(HOST_SRCS) $(HOST_HDRS)
+	@mkdir -p $(LIBDIR)
+	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOST_SRCS) -lz -ldl
+
+$(LIBDIR)/offlinerender: vviewer_b200/bin/offlinerender/main.cpp $(LIBDIR)/libvengine_host.so
+	$(CXX) $(CXXFLAGS) -o $@ vviewer_b200/bin/offlinerender/main.cpp $(HOST_SRCS) -lz -ldl
+
+oracle: $(ORCDIR)/liboracle.so
+
+# -ffp-contract=off: the world-space flatten and the LBVH reference build must round exactly like the
+# device kernels, which use explicit __fmul_rn/__fadd_rn
+$(ORCDIR)/liboracle.so: oracle/oracle.cpp oracle/omath.hpp oracle/bsdf.hpp oracle/accel.hpp include/ptc.h
+	@mkdir -p $(ORCDIR)
+	$(CXX) -O3 -std=c++17 -fPIC -fvisibility=hidden -ffp-contract=off -fopenmp -Wall -Iinclude -shared -o $@ oracle/oracle.cpp
+
+clean:
+	rm -rf $(LIBDIR) $(ORCDIR)
+
+.PHONY: all oracle clean

@@ -1,0 +1,245 @@
+/*
+ * ptc.h — C-ABI of the B200 path-tracing core ("ptc").
+ *
+ * This is the drop-in boundary for vengine's offline GPU path-tracing render path.
+ * It replaces, for that path only, what the reference reaches through
+ *   class RendererPathTracing            (src/lib/vengine/core/Renderer.hpp:11-39)
+ *   VulkanRendererPathTracing::render()  (src/lib/vengine/vulkan/renderers/VulkanRendererPathTracing.cpp:121-226, 791-901)
+ *   vkCmdTraceRaysKHR + pt shaders          (VulkanRendererPathTracing.cpp:848-855, src/lib/vengine/shaders/pt/)
+ *   driver BLAS/TLAS build               (src/lib/vengine/vulkan/resources/VulkanAccelerationStructure.cpp:137,258)
+ *
+ * Rules of the boundary: extern "C", plain pointers and sizes, caller-owned host memory that is
+ * copied during the call, 0 = success / non-zero = error (text through ptc_last_error), no
+ * exceptions, no CUDA / Vulkan / torch types.  Two libraries export exactly this surface:
+ *   vviewer_b200/_lib/libptc_cuda.so   the product (hand-written sm_100a CUDA, no CPU fallback)
+ *   oracle/_build/liboracle.so         the CPU restatement used ONLY by tests / smoke / bench cpu_baseline
+ *
+ * All matrices are column-major float[16] (glm layout), like the reference's UBOs.
+ */
+#ifndef PTC_H
+#define PTC_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PTC_API __attribute__((visibility("default")))
+#else
+#define PTC_API
+#endif
+
+/* ---------------------------------------------------------------- POD records */
+
+/* Vertex, 17 floats = 68 B, scalar layout.  Reference: src/lib/vengine/core/Mesh.hpp:15-40,
+ * src/lib/vengine/shaders/include/structs.glsl:4-12 */
+typedef struct ptc_vertex {
+    float position[3];
+    float uv[2];
+    float normal[3];
+    float color[3];
+    float tangent[3];
+    float bitangent[3];
+} ptc_vertex;
+
+/* One mesh = a range of the shared vertex / index pools (replaces the per-mesh device addresses of
+ * InstanceData, src/lib/vengine/core/Instances.hpp:17-35). Indices are relative to first_vertex. */
+typedef struct ptc_mesh {
+    uint32_t first_index;  /* offset into indices[] (in uint32 units, multiple of 3) */
+    uint32_t tri_count;
+    uint32_t first_vertex; /* offset into vertices[] */
+    uint32_t vertex_count;
+} ptc_mesh;
+
+/* InstanceData, 128 B. Reference: src/lib/vengine/core/Instances.hpp:17-35, structs.glsl:26-38.
+ * id = (object id, front-facing volume material | -1, back-facing volume material | -1, 0) as floats. */
+typedef struct ptc_instance {
+    float model[16];
+    float id[4];
+    uint32_t material_index;
+    uint32_t mesh_index; /* replaces vertexAddress/indexAddress */
+    uint32_t num_triangles;
+    uint32_t pad[9];
+} ptc_instance;
+
+/* MaterialData, 128 B. Reference: src/lib/vengine/vulkan/common/VulkanStructs.hpp:51-63, structs.glsl:41-52.
+ * Volume materials alias: albedo.rgb = sigma_a, metallic_roughness_ao.rgb = sigma_s, emissive[0] = g. */
+typedef struct ptc_material {
+    float albedo[4];                /* rgb albedo, a alpha */
+    float metallic_roughness_ao[4]; /* r metallic, g roughness, b ao, a transparent flag */
+    float emissive[4];              /* rgb colour, a intensity */
+    uint32_t tex1[4];               /* albedo, metallic, roughness, ao texture index */
+    uint32_t tex2[4];               /* emissive, normal, brdf-lut (unused), alpha texture index */
+    float uv_tiling[4];             /* u, v, material type (ptc_material_type), unused */
+    uint32_t pad1[4];
+    uint32_t pad2[4];
+} ptc_material;
+
+enum ptc_material_type { PTC_MATERIAL_PBR_STANDARD = 0, PTC_MATERIAL_SKYBOX = 1, PTC_MATERIAL_LAMBERT = 2, PTC_MATERIAL_VOLUME = 3 };
+
+/* LightData 64 B / LightInstance 64 B. Reference: VulkanStructs.hpp:65-71, Instances.hpp:39-44,
+ * packing src/lib/vengine/vulkan/VulkanInstances.cpp:73-108. */
+typedef struct ptc_light_data {
+    float color[4]; /* rgb, a intensity */
+    uint32_t type[4];
+    uint32_t pad1[4];
+    uint32_t pad2[4];
+} ptc_light_data;
+
+typedef struct ptc_light_instance {
+    uint32_t info[4];   /* r LightData index, g InstanceData index, b unused, a type 0 point / 1 directional / 2 mesh */
+    float position[4];  /* point: world pos; directional: model * (0,0,1,0) (unnormalised); mesh: row 0 of model */
+    float position1[4]; /* mesh: row 1 */
+    float position2[4]; /* mesh: row 2 */
+} ptc_light_instance;
+
+/* 8-bit texture, rows stored in memory order (row 0 is sampled at v = 0). Sampling is bilinear, REPEAT,
+ * LOD 0 (ray-tracing stages have no derivatives), sRGB decode before filtering when srgb != 0.
+ * Reference: src/lib/vengine/vulkan/resources/VulkanTexture.cpp:219-232, VulkanUtils.cpp:535-554. */
+typedef struct ptc_texture {
+    uint32_t width, height;
+    uint32_t channels; /* 1 or 4 */
+    uint32_t srgb;
+    const uint8_t *data;
+} ptc_texture;
+
+/* Equirectangular RGBA32F environment, rows in memory order (row 0 sampled at v = 0, i.e. the image
+ * as loaded with the reference's vertical flip, src/lib/vengine/core/Image.cpp:39-40).  The backend
+ * resamples it into a cubemap with face size min(width/4, 1080) like
+ * VulkanRendererSkybox::createCubemap (VulkanRendererSkybox.cpp:98-135). May be NULL. */
+typedef struct ptc_env {
+    const float *equirect_rgba;
+    uint32_t width, height;
+} ptc_env;
+
+typedef struct ptc_scene_desc {
+    const ptc_vertex *vertices;
+    uint64_t n_vertices;
+    const uint32_t *indices;
+    uint64_t n_indices;
+    const ptc_mesh *meshes;
+    uint32_t n_meshes;
+    const ptc_instance *instances;
+    uint32_t n_instances;
+    const ptc_material *materials;
+    uint32_t n_materials;
+    const ptc_light_data *light_data;
+    uint32_t n_light_data;
+    const ptc_light_instance *light_instances; /* ComponentLight objects first, then mesh lights */
+    uint32_t n_light_instances;
+    const ptc_texture *textures;
+    uint32_t n_textures;
+    ptc_env env;
+} ptc_scene_desc;
+
+/* SceneData, 304 B. Reference: src/lib/vengine/core/Scene.hpp:27-35, structs.glsl:15-23. */
+typedef struct ptc_scene_data {
+    float view[16];
+    float view_inverse[16];
+    float projection[16];
+    float projection_inverse[16];
+    float exposure[4];   /* r exposure, g environment intensity, b lens radius, a focal distance */
+    float background[4]; /* rgb colour, a environment type 0 solid / 1 HDRI / 2 solid + HDRI lighting */
+    float volumes[4];    /* r camera volume material | -1, g znear, b zfar */
+} ptc_scene_data;
+
+enum ptc_camera_type { PTC_CAMERA_PERSPECTIVE = 0, PTC_CAMERA_ORTHOGRAPHIC = 1 };
+enum ptc_split_mode { PTC_SPLIT_NONE = 0, PTC_SPLIT_TILE = 1, PTC_SPLIT_SAMPLE = 2 };
+
+/* Render settings = RendererPathTracing::RenderInfo (Renderer.hpp:14-28) + PathTracingData
+ * (VulkanRendererPathTracing.hpp:57-61) + the multi-GPU partition of this rank. */
+typedef struct ptc_render_params {
+    ptc_scene_data scene;
+    uint32_t samples;    /* total samples per pixel; batches = samples / batch_size (remainder dropped, T7) */
+    uint32_t batch_size;
+    uint32_t depth;
+    uint32_t width, height;
+    uint32_t camera_type; /* ptc_camera_type; orthographic = true parallel rays (documented deviation T10) */
+    float ortho_width, ortho_height;
+    /* partition: this context renders only its share; the sum over ranks is the full image */
+    uint32_t split_mode; /* ptc_split_mode */
+    uint32_t rank, world;
+    uint32_t tile_size;  /* tile edge in pixels for PTC_SPLIT_TILE (0 = 32) */
+    uint32_t flags;      /* PTC_FLAG_* */
+    uint32_t reserved[7];
+} ptc_render_params;
+
+#define PTC_FLAG_WORLD_ORIGIN_PROBE_PDF 1u /* use the world-space ray origin in the probe-ray pdf instead of reproducing rayNEE.rahit.glsl:122 */
+
+typedef struct ptc_stats {
+    uint64_t segments;    /* iterations of the raygen depth loop (raygen.rgen.glsl:100-124) */
+    uint64_t path_rays;   /* closest-hit traces */
+    uint64_t shadow_rays; /* shadow chains started (lightSampling.glsl:108-144) */
+    uint64_t shadow_hops;
+    uint64_t probe_rays;  /* probe chains started (next_event_estimation.glsl) */
+    uint64_t probe_hops;
+    double render_ms;     /* wall time of the last ptc_render* call (device time for the CUDA backend) */
+    double trace_ms;      /* time inside the closest-hit traversal kernel (CUDA events), 0 for the oracle */
+    double shade_ms;
+    double shadow_ms;
+    double build_ms;      /* last ptc_build_accel */
+    uint64_t trace_launches;
+    uint64_t kernel_launches; /* all kernels launched by the last render */
+    uint64_t n_triangles;     /* world-space triangles in the acceleration structure */
+    uint64_t n_bvh_nodes;
+    uint64_t scene_bytes;     /* device bytes held by scene + accel */
+    uint64_t reserved[4];
+} ptc_stats;
+
+typedef struct ptc_ctx ptc_ctx;
+
+/* ---------------------------------------------------------------- lifecycle */
+PTC_API int ptc_create(ptc_ctx **out, const int *device_ids, int n_devices);
+PTC_API void ptc_destroy(ptc_ctx *ctx);
+PTC_API const char *ptc_last_error(const ptc_ctx *ctx);
+PTC_API const char *ptc_backend_name(void); /* "cuda-sm_100a" or "cpu-oracle" */
+
+/* ---------------------------------------------------------------- scene */
+/* replaces VulkanScene::updateFrame + VulkanMaterials::updateBuffers + VulkanTextures::updateTextures
+ * (VulkanRendererPathTracing.cpp:202-205) */
+PTC_API int ptc_upload_scene(ptc_ctx *ctx, const ptc_scene_desc *scene);
+/* replaces the driver BLAS/TLAS builds: on-device LBVH over world-space triangles */
+PTC_API int ptc_build_accel(ptc_ctx *ctx);
+
+/* ---------------------------------------------------------------- render */
+/* replaces render(VkDescriptorSet) batch loop + readback (VulkanRendererPathTracing.cpp:791-956).
+ * Outputs: width*height*4 floats each, row-major, top-left origin, alpha = 1; any may be NULL. Blocking. */
+PTC_API int ptc_render(ptc_ctx *ctx, const ptc_render_params *params, float *radiance_rgba, float *albedo_rgba,
+                       float *normal_rgba);
+/* same, but the three outputs are DEVICE pointers on the context's device (for the NCCL reduce). The
+ * oracle returns an error. */
+PTC_API int ptc_render_device(ptc_ctx *ctx, const ptc_render_params *params, void *d_radiance_rgba, void *d_albedo_rgba,
+                              void *d_normal_rgba);
+PTC_API float ptc_progress(const ptc_ctx *ctx); /* RendererPathTracing::renderProgress */
+PTC_API int ptc_get_stats(ptc_ctx *ctx, ptc_stats *out);
+
+/* ---------------------------------------------------------------- parity hooks */
+/* rays: n x 8 floats (origin xyz, tmin, direction xyz, tmax). Outputs per ray: instance (-1 on miss),
+ * primitive id within the instance's mesh, t, barycentric u, v. */
+PTC_API int ptc_trace_closest(ptc_ctx *ctx, const float *rays, int n, int *inst, int *prim, float *t, float *u, float *v);
+
+/* LBVH structure dump for the bit-exact build check. Arrays are caller-allocated:
+ * morton[n] (sorted 64-bit keys), order[n] (sorted -> world triangle id), parent/left/right for the 2n-1 nodes
+ * (internal nodes 0..n-2, leaves n-1..2n-2; children encoded the same way), aabb[(2n-1)*6].
+ * Pass NULL to skip an array. Returns the triangle count through n_out. */
+PTC_API int ptc_get_lbvh(ptc_ctx *ctx, uint64_t *n_out, uint64_t *morton, uint32_t *order, int32_t *parent, int32_t *left,
+                         int32_t *right, float *aabb);
+
+/* BSDF parity hooks (src/lib/vengine/shaders/include/brdfs/pbrStandard.glsl:92-165).  Per item:
+ * params = albedo rgb, metallic, roughness (5 floats); wi, wo local frame (y = normal).
+ * eval: out_f[3], out_pdf[1].   sample: u[3] = (u0, u1, lobe pick) -> out_wi[3], out_f[3], out_pdf[1]. */
+PTC_API int ptc_bsdf_eval(ptc_ctx *ctx, int n, const float *params, const float *wi, const float *wo, float *out_f,
+                          float *out_pdf);
+PTC_API int ptc_bsdf_sample(ptc_ctx *ctx, int n, const float *params, const float *wo, const float *u, float *out_wi,
+                            float *out_f, float *out_pdf);
+
+/* Environment lookup parity hook: n directions (xyz) -> rgb of the backend's cubemap at LOD 0. */
+PTC_API int ptc_env_lookup(ptc_ctx *ctx, int n, const float *dirs, float *out_rgb);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTC_H */

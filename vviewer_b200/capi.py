@@ -1,0 +1,413 @@
+"""ctypes bindings for the two C interfaces of this repository.
+
+* ``include/ptc.h``           — the drop-in boundary (libptc_cuda.so; the oracle exports the same surface)
+* ``include/vengine_host.h``  — C view of the C++ host library (scene model + RendererPathTracing)
+
+Nothing here computes anything: it only declares structures / prototypes and loads shared libraries.
+The product library is ``vviewer_b200/_lib/libptc_cuda.so``; loading it fails loudly when it is missing
+(there is no CPU fallback).  The oracle library is loaded only by tests, smoke() and bench.py's CPU legs
+through :func:`load_oracle`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_DIR = os.path.join(ROOT, "vviewer_b200", "_lib")
+CUDA_LIB = os.path.join(LIB_DIR, "libptc_cuda.so")
+HOST_LIB = os.path.join(LIB_DIR, "libvengine_host.so")
+ORACLE_LIB = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+
+f32 = C.c_float
+u32 = C.c_uint32
+u64 = C.c_uint64
+
+
+class ptc_vertex(C.Structure):
+    _fields_ = [("position", f32 * 3), ("uv", f32 * 2), ("normal", f32 * 3), ("color", f32 * 3), ("tangent", f32 * 3),
+                ("bitangent", f32 * 3)]
+
+
+class ptc_mesh(C.Structure):
+    _fields_ = [("first_index", u32), ("tri_count", u32), ("first_vertex", u32), ("vertex_count", u32)]
+
+
+class ptc_instance(C.Structure):
+    _fields_ = [("model", f32 * 16), ("id", f32 * 4), ("material_index", u32), ("mesh_index", u32), ("num_triangles", u32),
+                ("pad", u32 * 9)]
+
+
+class ptc_material(C.Structure):
+    _fields_ = [("albedo", f32 * 4), ("metallic_roughness_ao", f32 * 4), ("emissive", f32 * 4), ("tex1", u32 * 4),
+                ("tex2", u32 * 4), ("uv_tiling", f32 * 4), ("pad1", u32 * 4), ("pad2", u32 * 4)]
+
+
+class ptc_light_data(C.Structure):
+    _fields_ = [("color", f32 * 4), ("type", u32 * 4), ("pad1", u32 * 4), ("pad2", u32 * 4)]
+
+
+class ptc_light_instance(C.Structure):
+    _fields_ = [("info", u32 * 4), ("position", f32 * 4), ("position1", f32 * 4), ("position2", f32 * 4)]
+
+
+class ptc_texture(C.Structure):
+    _fields_ = [("width", u32), ("height", u32), ("channels", u32), ("srgb", u32), ("data", C.POINTER(C.c_uint8))]
+
+
+class ptc_env(C.Structure):
+    _fields_ = [("equirect_rgba", C.POINTER(f32)), ("width", u32), ("height", u32)]
+
+
+class ptc_scene_desc(C.Structure):
+    _fields_ = [("vertices", C.POINTER(ptc_vertex)), ("n_vertices", u64), ("indices", C.POINTER(u32)), ("n_indices", u64),
+                ("meshes", C.POINTER(ptc_mesh)), ("n_meshes", u32), ("instances", C.POINTER(ptc_instance)), ("n_instances", u32),
+                ("materials", C.POINTER(ptc_material)), ("n_materials", u32), ("light_data", C.POINTER(ptc_light_data)),
+                ("n_light_data", u32), ("light_instances", C.POINTER(ptc_light_instance)), ("n_light_instances", u32),
+                ("textures", C.POINTER(ptc_texture)), ("n_textures", u32), ("env", ptc_env)]
+
+
+class ptc_scene_data(C.Structure):
+    _fields_ = [("view", f32 * 16), ("view_inverse", f32 * 16), ("projection", f32 * 16), ("projection_inverse", f32 * 16),
+                ("exposure", f32 * 4), ("background", f32 * 4), ("volumes", f32 * 4)]
+
+
+class ptc_render_params(C.Structure):
+    _fields_ = [("scene", ptc_scene_data), ("samples", u32), ("batch_size", u32), ("depth", u32), ("width", u32), ("height", u32),
+                ("camera_type", u32), ("ortho_width", f32), ("ortho_height", f32), ("split_mode", u32), ("rank", u32), ("world", u32),
+                ("tile_size", u32), ("flags", u32), ("reserved", u32 * 7)]
+
+
+class ptc_stats(C.Structure):
+    _fields_ = [("segments", u64), ("path_rays", u64), ("shadow_rays", u64), ("shadow_hops", u64), ("probe_rays", u64),
+                ("probe_hops", u64), ("render_ms", C.c_double), ("trace_ms", C.c_double), ("shade_ms", C.c_double),
+                ("shadow_ms", C.c_double), ("build_ms", C.c_double), ("trace_launches", u64), ("kernel_launches", u64),
+                ("n_triangles", u64), ("n_bvh_nodes", u64), ("scene_bytes", u64), ("reserved", u64 * 4)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+PTC_SPLIT_NONE, PTC_SPLIT_TILE, PTC_SPLIT_SAMPLE = 0, 1, 2
+PTC_FLAG_WORLD_ORIGIN_PROBE_PDF = 1
+
+# every symbol include/ptc.h declares
+PTC_SYMBOLS = ["ptc_create", "ptc_destroy", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_build_accel", "ptc_render",
+               "ptc_render_device", "ptc_progress", "ptc_get_stats", "ptc_trace_closest", "ptc_get_lbvh", "ptc_bsdf_eval",
+               "ptc_bsdf_sample", "ptc_env_lookup"]
+VH_SYMBOLS = ["vh_engine_create", "vh_engine_destroy", "vh_backend_ok", "vh_last_error", "vh_scene_list", "vh_build_scene",
+              "vh_set_render_info", "vh_get_render_info", "vh_scene_desc", "vh_render_params", "vh_render_to_memory", "vh_render",
+              "vh_get_stats", "vh_read_hdr", "vh_write_hdr"]
+
+_fp = C.POINTER(f32)
+_ip = C.POINTER(C.c_int)
+
+
+def _declare_ptc(lib):
+    vp = C.c_void_p
+    lib.ptc_create.argtypes = [C.POINTER(vp), _ip, C.c_int]
+    lib.ptc_create.restype = C.c_int
+    lib.ptc_destroy.argtypes = [vp]
+    lib.ptc_destroy.restype = None
+    lib.ptc_last_error.argtypes = [vp]
+    lib.ptc_last_error.restype = C.c_char_p
+    lib.ptc_backend_name.argtypes = []
+    lib.ptc_backend_name.restype = C.c_char_p
+    lib.ptc_upload_scene.argtypes = [vp, C.POINTER(ptc_scene_desc)]
+    lib.ptc_upload_scene.restype = C.c_int
+    lib.ptc_build_accel.argtypes = [vp]
+    lib.ptc_build_accel.restype = C.c_int
+    lib.ptc_render.argtypes = [vp, C.POINTER(ptc_render_params), vp, vp, vp]
+    lib.ptc_render.restype = C.c_int
+    lib.ptc_render_device.argtypes = [vp, C.POINTER(ptc_render_params), vp, vp, vp]
+    lib.ptc_render_device.restype = C.c_int
+    lib.ptc_progress.argtypes = [vp]
+    lib.ptc_progress.restype = f32
+    lib.ptc_get_stats.argtypes = [vp, C.POINTER(ptc_stats)]
+    lib.ptc_get_stats.restype = C.c_int
+    lib.ptc_trace_closest.argtypes = [vp, vp, C.c_int, vp, vp, vp, vp, vp]
+    lib.ptc_trace_closest.restype = C.c_int
+    lib.ptc_get_lbvh.argtypes = [vp, C.POINTER(u64), vp, vp, vp, vp, vp, vp]
+    lib.ptc_get_lbvh.restype = C.c_int
+    lib.ptc_bsdf_eval.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
+    lib.ptc_bsdf_eval.restype = C.c_int
+    lib.ptc_bsdf_sample.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
+    lib.ptc_bsdf_sample.restype = C.c_int
+    lib.ptc_env_lookup.argtypes = [vp, C.c_int, vp, vp]
+    lib.ptc_env_lookup.restype = C.c_int
+    return lib
+
+
+def _declare_vh(lib):
+    vp = C.c_void_p
+    lib.vh_engine_create.argtypes = [C.c_char_p, C.c_char_p]
+    lib.vh_engine_create.restype = vp
+    lib.vh_engine_destroy.argtypes = [vp]
+    lib.vh_engine_destroy.restype = None
+    lib.vh_backend_ok.argtypes = [vp]
+    lib.vh_backend_ok.restype = C.c_int
+    lib.vh_last_error.argtypes = [vp]
+    lib.vh_last_error.restype = C.c_char_p
+    lib.vh_scene_list.argtypes = []
+    lib.vh_scene_list.restype = C.c_char_p
+    lib.vh_build_scene.argtypes = [vp, C.c_char_p, C.c_int, f32, C.c_int]
+    lib.vh_build_scene.restype = C.c_int
+    lib.vh_set_render_info.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.vh_set_render_info.restype = None
+    lib.vh_get_render_info.argtypes = [vp, _ip, _ip, _ip, _ip, _ip]
+    lib.vh_get_render_info.restype = None
+    lib.vh_scene_desc.argtypes = [vp]
+    lib.vh_scene_desc.restype = C.POINTER(ptc_scene_desc)
+    lib.vh_render_params.argtypes = [vp, C.POINTER(ptc_render_params)]
+    lib.vh_render_params.restype = C.c_int
+    lib.vh_render_to_memory.argtypes = [vp, vp, vp, vp]
+    lib.vh_render_to_memory.restype = C.c_int
+    lib.vh_render.argtypes = [vp, C.c_char_p]
+    lib.vh_render.restype = C.c_int
+    lib.vh_get_stats.argtypes = [vp, C.POINTER(ptc_stats)]
+    lib.vh_get_stats.restype = C.c_int
+    lib.vh_read_hdr.argtypes = [C.c_char_p, _ip, _ip, vp]
+    lib.vh_read_hdr.restype = C.c_int
+    lib.vh_write_hdr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, vp]
+    lib.vh_write_hdr.restype = C.c_int
+    return lib
+
+
+def load_ptc(path):
+    if not os.path.exists(path):
+        raise RuntimeError("path-tracing backend library not found: %s (run `make` / __graft_entry__.build())" % path)
+    return _declare_ptc(C.CDLL(path, mode=C.RTLD_LOCAL))
+
+
+_cuda = None
+_host = None
+_oracle = None
+
+
+def load_cuda():
+    """The product: hand-written sm_100a CUDA behind include/ptc.h. Raises if the library is absent."""
+    global _cuda
+    if _cuda is None:
+        _cuda = load_ptc(CUDA_LIB)
+    return _cuda
+
+
+def load_oracle():
+    """CPU restatement of the reference. TEST INFRASTRUCTURE: tests, smoke() and bench CPU legs only."""
+    global _oracle
+    if _oracle is None:
+        _oracle = load_ptc(ORACLE_LIB)
+    return _oracle
+
+
+def load_host():
+    global _host
+    if _host is None:
+        if not os.path.exists(HOST_LIB):
+            raise RuntimeError("host library not found: %s (run `make`)" % HOST_LIB)
+        _host = _declare_vh(C.CDLL(HOST_LIB, mode=C.RTLD_LOCAL))
+    return _host
+
+
+def np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """RAII wrapper of a ptc_ctx of one backend library."""
+
+    def __init__(self, lib, device=None):
+        self.lib = lib
+        self.ctx = C.c_void_p()
+        if device is None:
+            rc = lib.ptc_create(C.byref(self.ctx), None, 0)
+        else:
+            d = (C.c_int * 1)(int(device))
+            rc = lib.ptc_create(C.byref(self.ctx), d, 1)
+        if rc != 0 or not self.ctx:
+            msg = lib.ptc_last_error(self.ctx).decode() if self.ctx else "no context"
+            raise RuntimeError("ptc_create failed (%s): %s" % (lib.ptc_backend_name().decode(), msg))
+
+    def close(self):
+        if self.ctx:
+            self.lib.ptc_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError("%s failed: %s" % (what, self.lib.ptc_last_error(self.ctx).decode()))
+
+    def upload_scene(self, desc_ptr):
+        self._check(self.lib.ptc_upload_scene(self.ctx, desc_ptr), "ptc_upload_scene")
+
+    def build_accel(self):
+        self._check(self.lib.ptc_build_accel(self.ctx), "ptc_build_accel")
+
+    def render(self, params, want_aovs=True):
+        n = params.width * params.height * 4
+        rad = np.zeros(n, np.float32)
+        alb = np.zeros(n, np.float32) if want_aovs else None
+        nrm = np.zeros(n, np.float32) if want_aovs else None
+        self._check(self.lib.ptc_render(self.ctx, C.byref(params), np_ptr(rad), np_ptr(alb) if want_aovs else None,
+                                        np_ptr(nrm) if want_aovs else None), "ptc_render")
+        shape = (params.height, params.width, 4)
+        if want_aovs:
+            return rad.reshape(shape), alb.reshape(shape), nrm.reshape(shape)
+        return rad.reshape(shape)
+
+    def render_device(self, params, d_rad, d_alb, d_nrm):
+        self._check(self.lib.ptc_render_device(self.ctx, C.byref(params), C.c_void_p(d_rad), C.c_void_p(d_alb) if d_alb else None,
+                                               C.c_void_p(d_nrm) if d_nrm else None), "ptc_render_device")
+
+    def stats(self):
+        s = ptc_stats()
+        self._check(self.lib.ptc_get_stats(self.ctx, C.byref(s)), "ptc_get_stats")
+        return s.as_dict()
+
+    def trace_closest(self, rays):
+        rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+        n = rays.shape[0]
+        inst = np.zeros(n, np.int32)
+        prim = np.zeros(n, np.int32)
+        t = np.zeros(n, np.float32)
+        u = np.zeros(n, np.float32)
+        v = np.zeros(n, np.float32)
+        self._check(self.lib.ptc_trace_closest(self.ctx, np_ptr(rays), n, np_ptr(inst), np_ptr(prim), np_ptr(t), np_ptr(u), np_ptr(v)),
+                    "ptc_trace_closest")
+        return inst, prim, t, u, v
+
+    def get_lbvh(self):
+        n = u64(0)
+        self._check(self.lib.ptc_get_lbvh(self.ctx, C.byref(n), None, None, None, None, None, None), "ptc_get_lbvh")
+        n = int(n.value)
+        nn = max(2 * n - 1, 0)
+        out = dict(n=n, morton=np.zeros(n, np.uint64), order=np.zeros(n, np.uint32), parent=np.zeros(nn, np.int32),
+                   left=np.zeros(nn, np.int32), right=np.zeros(nn, np.int32), aabb=np.zeros((nn, 6), np.float32))
+        if n:
+            k = u64(0)
+            self._check(self.lib.ptc_get_lbvh(self.ctx, C.byref(k), np_ptr(out["morton"]), np_ptr(out["order"]), np_ptr(out["parent"]),
+                                              np_ptr(out["left"]), np_ptr(out["right"]), np_ptr(out["aabb"])), "ptc_get_lbvh")
+        return out
+
+    def bsdf_eval(self, params, wi, wo):
+        params = np.ascontiguousarray(params, np.float32)
+        wi = np.ascontiguousarray(wi, np.float32)
+        wo = np.ascontiguousarray(wo, np.float32)
+        n = params.shape[0]
+        f = np.zeros((n, 3), np.float32)
+        pdf = np.zeros(n, np.float32)
+        self._check(self.lib.ptc_bsdf_eval(self.ctx, n, np_ptr(params), np_ptr(wi), np_ptr(wo), np_ptr(f), np_ptr(pdf)), "ptc_bsdf_eval")
+        return f, pdf
+
+    def bsdf_sample(self, params, wo, u):
+        params = np.ascontiguousarray(params, np.float32)
+        wo = np.ascontiguousarray(wo, np.float32)
+        u = np.ascontiguousarray(u, np.float32)
+        n = params.shape[0]
+        wi = np.zeros((n, 3), np.float32)
+        f = np.zeros((n, 3), np.float32)
+        pdf = np.zeros(n, np.float32)
+        self._check(self.lib.ptc_bsdf_sample(self.ctx, n, np_ptr(params), np_ptr(wo), np_ptr(u), np_ptr(wi), np_ptr(f), np_ptr(pdf)),
+                    "ptc_bsdf_sample")
+        return wi, f, pdf
+
+    def env_lookup(self, dirs):
+        dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        out = np.zeros_like(dirs)
+        self._check(self.lib.ptc_env_lookup(self.ctx, dirs.shape[0], np_ptr(dirs), np_ptr(out)), "ptc_env_lookup")
+        return out
+
+
+class HostEngine:
+    """The C++ vengine host library: scene recipes, flattening, RendererPathTracing."""
+
+    def __init__(self, backend_lib=None, asset_root=None):
+        self.lib = load_host()
+        b = (backend_lib or CUDA_LIB).encode()
+        a = (asset_root or ROOT).encode()
+        self.h = C.c_void_p(self.lib.vh_engine_create(b, a))
+
+    def close(self):
+        if self.h:
+            self.lib.vh_engine_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def backend_ok(self):
+        return bool(self.lib.vh_backend_ok(self.h))
+
+    def last_error(self):
+        return self.lib.vh_last_error(self.h).decode()
+
+    def scene_list(self):
+        return self.lib.vh_scene_list().decode().split(",")
+
+    def build_scene(self, name, texture_size=0, scale=0.0, camera=0):
+        rc = self.lib.vh_build_scene(self.h, name.encode(), int(texture_size), float(scale), int(camera))
+        if rc != 0:
+            raise RuntimeError("unknown scene recipe %r" % name)
+
+    def set_render_info(self, width=0, height=0, samples=0, batch_size=0, depth=0):
+        self.lib.vh_set_render_info(self.h, width, height, samples, batch_size, depth)
+
+    def render_info(self):
+        v = [C.c_int() for _ in range(5)]
+        self.lib.vh_get_render_info(self.h, *[C.byref(x) for x in v])
+        return dict(zip(["width", "height", "samples", "batch_size", "depth"], [x.value for x in v]))
+
+    def scene_desc(self):
+        return self.lib.vh_scene_desc(self.h)
+
+    def render_params(self):
+        p = ptc_render_params()
+        self.lib.vh_render_params(self.h, C.byref(p))
+        return p
+
+    def render_to_memory(self):
+        ri = self.render_info()
+        n = ri["width"] * ri["height"] * 4
+        rad, alb, nrm = (np.zeros(n, np.float32) for _ in range(3))
+        rc = self.lib.vh_render_to_memory(self.h, np_ptr(rad), np_ptr(alb), np_ptr(nrm))
+        if rc != 0:
+            raise RuntimeError("RendererPathTracing::render failed: %s" % self.last_error())
+        shape = (ri["height"], ri["width"], 4)
+        return rad.reshape(shape), alb.reshape(shape), nrm.reshape(shape)
+
+    def render(self, filename):
+        rc = self.lib.vh_render(self.h, filename.encode())
+        if rc != 0:
+            raise RuntimeError("RendererPathTracing::render failed: %s" % self.last_error())
+
+    def stats(self):
+        s = ptc_stats()
+        self.lib.vh_get_stats(self.h, C.byref(s))
+        return s.as_dict()
+
+
+def read_hdr(path):
+    lib = load_host()
+    w, h = C.c_int(), C.c_int()
+    if lib.vh_read_hdr(path.encode(), C.byref(w), C.byref(h), None) != 0:
+        raise RuntimeError("cannot read %s" % path)
+    out = np.zeros((h.value, w.value, 4), np.float32)
+    lib.vh_read_hdr(path.encode(), C.byref(w), C.byref(h), np_ptr(out))
+    return out
+
+
+def write_hdr(path, img):
+    lib = load_host()
+    img = np.ascontiguousarray(img, np.float32)
+    h, w, c = img.shape
+    if lib.vh_write_hdr(path.encode(), w, h, c, np_ptr(img)) != 0:
+        raise RuntimeError("cannot write %s" % path)

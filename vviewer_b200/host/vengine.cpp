@@ -1,0 +1,608 @@
+/*
+ * Host-side scene model: implementation. See vengine.hpp for the reference files each part mirrors.
+ */
+#include "vengine.hpp"
+
+#include <dlfcn.h>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+
+namespace vengine {
+
+uint32_t Entity::s_nextId = 1;
+
+/* ====================================================================== textures */
+static ImageU8 solidImage(uint8_t r, uint8_t g, uint8_t b, uint8_t a) {
+    ImageU8 im;
+    im.width = im.height = 1;
+    im.channels = 4;
+    im.data = {r, g, b, a};
+    return im;
+}
+
+Textures::Textures() {
+    /* VulkanTextures::createBaseTextures (VulkanTextures.cpp:71-76): slots 0, 1, 2; core/Image.hpp:56-85 */
+    createTexture("white", solidImage(255, 255, 255, 255), ColorSpace::LINEAR);
+    createTexture("whiteColor", solidImage(255, 255, 255, 255), ColorSpace::sRGB);
+    createTexture("normalmapdefault", solidImage(0x80, 0x80, 0xFF, 0xFF), ColorSpace::LINEAR);
+}
+
+Texture *Textures::createTexture(const std::string &name, const ImageU8 &image, ColorSpace colorSpace) {
+    if (m_map.has(name)) return m_map.get(name);
+    auto t = std::make_unique<Texture>();
+    t->name = name;
+    t->image = image;
+    t->colorSpace = colorSpace;
+    t->bindlessResourceIndex = (uint32_t)m_textures.size();
+    Texture *raw = t.get();
+    m_textures.push_back(std::move(t));
+    return m_map.add(name, raw);
+}
+
+Texture *Textures::createTexture(const AssetInfo &info, ColorSpace colorSpace) {
+    if (m_map.has(info.name)) return m_map.get(info.name);
+    ImageU8 im;
+    /* every 8-bit texture is loaded vertically flipped because the HDR loader leaves
+     * stbi_set_flip_vertically_on_load(true) set globally (core/Image.cpp:39; SURVEY trap T11) */
+    if (!loadImageU8(info.filepath, im, true)) {
+        std::fprintf(stderr, "Textures::createTexture(): unable to load %s\n", info.filepath.c_str());
+        return nullptr;
+    }
+    return createTexture(info.name, im, colorSpace);
+}
+
+/* ====================================================================== materials */
+ptc_material &Material::block() { return m_materials.blocks()[m_index]; }
+const ptc_material &Material::block() const { return m_materials.blocks()[m_index]; }
+
+static bool isBlack3(vec3 c, float eps) { return std::fabs(c.x) <= eps && std::fabs(c.y) <= eps && std::fabs(c.z) <= eps; }
+
+MaterialPBRStandard::MaterialPBRStandard(const AssetInfo &info, Materials &materials, MaterialIndex index) : Material(info, materials, index) {
+    ptc_material &b = block();
+    std::memset(&b, 0, sizeof(b));
+    b.uv_tiling[2] = (float)MaterialType::MATERIAL_PBR_STANDARD;
+    albedo() = vec4(1, 1, 1, 1);
+    metallic() = 0;
+    roughness() = 1;
+    ao() = 1;
+    emissive() = vec4(0, 0, 0, 1);
+    uTiling() = 1;
+    vTiling() = 1;
+    Textures &tx = materials.textures();
+    setAlbedoTexture(tx.get("whiteColor"));
+    setMetallicTexture(tx.get("white"));
+    setRoughnessTexture(tx.get("white"));
+    setAOTexture(tx.get("white"));
+    setEmissiveTexture(tx.get("whiteColor"));
+    setNormalTexture(tx.get("normalmapdefault"));
+    setAlphaTexture(tx.get("white"));
+}
+bool MaterialPBRStandard::isEmissive() const {
+    return (block().emissive[3] > std::numeric_limits<float>::epsilon()) && !isBlack3(emissiveColor(), 0.01f);
+}
+
+MaterialLambert::MaterialLambert(const AssetInfo &info, Materials &materials, MaterialIndex index) : Material(info, materials, index) {
+    ptc_material &b = block();
+    std::memset(&b, 0, sizeof(b));
+    b.uv_tiling[2] = (float)MaterialType::MATERIAL_LAMBERT;
+    albedo() = vec4(1, 1, 1, 1);
+    ao() = 1;
+    emissive() = vec4(0, 0, 0, 1);
+    uTiling() = 1;
+    vTiling() = 1;
+    Textures &tx = materials.textures();
+    setAlbedoTexture(tx.get("whiteColor"));
+    setAOTexture(tx.get("white"));
+    setEmissiveTexture(tx.get("whiteColor"));
+    setNormalTexture(tx.get("normalmapdefault"));
+    setAlphaTexture(tx.get("white"));
+}
+bool MaterialLambert::isEmissive() const {
+    return (block().emissive[3] > std::numeric_limits<float>::epsilon()) && !isBlack3(emissiveColor(), 0.01f);
+}
+
+MaterialVolume::MaterialVolume(const AssetInfo &info, Materials &materials, MaterialIndex index) : Material(info, materials, index) {
+    ptc_material &b = block();
+    std::memset(&b, 0, sizeof(b));
+    b.uv_tiling[2] = (float)MaterialType::MATERIAL_VOLUME;
+    sigmaS() = vec4(0.2f);
+    sigmaA() = vec4(0.01f);
+    g() = 0.0f;
+}
+
+Material *Materials::createMaterial(const AssetInfo &info, MaterialType type) {
+    switch (type) {
+        case MaterialType::MATERIAL_PBR_STANDARD: return createMaterial<MaterialPBRStandard>(info);
+        case MaterialType::MATERIAL_LAMBERT: return createMaterial<MaterialLambert>(info);
+        case MaterialType::MATERIAL_VOLUME: return createMaterial<MaterialVolume>(info);
+        default: return nullptr;
+    }
+}
+
+/* ====================================================================== transform */
+void Transform::setRotation(vec3 forward, vec3 up) {
+    vec3 newZ = vm::normalize(-forward);
+    vec3 newY = vm::normalize(up);
+    vec3 newX = vm::normalize(vm::cross(newY, newZ));
+    newY = vm::normalize(vm::cross(newZ, newX));
+    mat4 r(1.0f);
+    r[0][0] = newX.x; r[0][1] = newX.y; r[0][2] = newX.z;
+    r[1][0] = newY.x; r[1][1] = newY.y; r[1][2] = newY.z;
+    r[2][0] = newZ.x; r[2][1] = newZ.y; r[2][2] = newZ.z;
+    setRotation(vm::quat_cast(r));
+}
+
+/* ====================================================================== scene */
+SceneObject *Scene::addSceneObject(const std::string &name, SceneObject *parent, Transform transform) {
+    m_objects.push_back(std::make_unique<SceneObject>(name));
+    SceneObject *o = m_objects.back().get();
+    o->setLocalTransform(transform);
+    if (parent == nullptr)
+        m_sceneGraph.push_back(o);
+    else
+        parent->addChild(o);
+    return o;
+}
+
+void Scene::clear() {
+    m_sceneGraph.clear();
+    m_objects.clear();
+    m_instances.invalidate();
+}
+
+void Scene::update() {
+    for (SceneObject *root : m_sceneGraph) root->update(nullptr);
+    m_instances.invalidate();
+    m_instances.build();
+}
+
+static void flatRec(SceneObject *o, SceneObjectVector &out) {
+    out.push_back(o);
+    for (SceneObject *c : o->children()) flatRec(c, out);
+}
+SceneObjectVector Scene::getSceneObjectsFlat() const {
+    SceneObjectVector v;
+    for (SceneObject *r : m_sceneGraph) flatRec(r, v);
+    return v;
+}
+
+Light *Scene::createLight(const AssetInfo &info, LightType type, vec4 color) {
+    ptc_light_data ld{};
+    ld.color[0] = color.x; ld.color[1] = color.y; ld.color[2] = color.z; ld.color[3] = color.w;
+    ld.type[0] = (uint32_t)type;
+    if (m_lightData.size() >= 1024) return nullptr;
+    m_lightData.reserve(1024); /* Light holds a reference into the table */
+    m_lightData.push_back(ld);
+    m_lights.push_back(std::make_unique<Light>(info, type, m_lightData, (LightIndex)(m_lightData.size() - 1)));
+    return m_lights.back().get();
+}
+
+ptc_scene_data Scene::getSceneData() const {
+    ptc_scene_data sd{};
+    mat4 view = m_camera->viewMatrix();
+    mat4 viewInv = m_camera->viewMatrixInverse();
+    std::memcpy(sd.view, view.data(), 64);
+    std::memcpy(sd.view_inverse, viewInv.data(), 64);
+    sd.exposure[0] = m_exposure;
+    sd.exposure[1] = m_environmentIntensity;
+    sd.exposure[2] = m_camera->lensRadius();
+    sd.exposure[3] = m_camera->focalDistance();
+    sd.background[0] = m_backgroundColor.x;
+    sd.background[1] = m_backgroundColor.y;
+    sd.background[2] = m_backgroundColor.z;
+    sd.background[3] = (float)m_environmentType;
+    sd.volumes[0] = -1;
+    sd.volumes[1] = m_camera->znear();
+    sd.volumes[2] = m_camera->zfar();
+    sd.volumes[3] = 0;
+    return sd;
+}
+
+/* ====================================================================== instances (core/Instances.cpp) */
+void InstancesManager::invalidate() {
+    m_instancesOpaque.clear();
+    m_transparent.clear();
+    m_lights.clear();
+    m_meshLights.clear();
+    m_volumes.clear();
+    m_order.clear();
+}
+
+void InstancesManager::build() {
+    /* fillSceneObjectVectors, Instances.cpp:100-143 */
+    for (SceneObject *so : m_scene->getSceneObjectsFlat()) {
+        if (!so->isActive()) continue;
+        if (so->has<ComponentMesh>()) {
+            Mesh *mesh = so->get<ComponentMesh>().mesh();
+            if (so->has<ComponentMaterial>() && mesh != nullptr) {
+                Material *material = so->get<ComponentMaterial>().material();
+                if (material == nullptr) continue;
+                if (material->isEmissive()) m_meshLights.push_back(so);
+                if (!material->isTransparent()) {
+                    bool found = false;
+                    for (auto &g : m_instancesOpaque)
+                        if (g.first == mesh) {
+                            g.second.push_back(so);
+                            found = true;
+                            break;
+                        }
+                    if (!found) m_instancesOpaque.push_back({mesh, SceneObjectVector{so}});
+                } else {
+                    m_transparent.push_back(so);
+                }
+            }
+        }
+        if (so->has<ComponentLight>()) {
+            if (so->get<ComponentLight>().light() != nullptr) m_lights.push_back(so);
+        }
+        if (so->has<ComponentVolume>()) {
+            ComponentVolume &v = so->get<ComponentVolume>();
+            if (v.frontFacing() != nullptr || v.backFacing() != nullptr) m_volumes.push_back(so);
+        }
+    }
+    /* buildInstanceDataFromScratch, Instances.cpp:145-181: opaque groups, transparent, lights */
+    for (auto &g : m_instancesOpaque)
+        for (SceneObject *so : g.second) m_order.push_back(so);
+    for (SceneObject *so : m_transparent) m_order.push_back(so);
+    for (SceneObject *so : m_lights) m_order.push_back(so);
+}
+
+/* ====================================================================== engine */
+static std::string dirOf(const std::string &p) {
+    size_t k = p.find_last_of('/');
+    return k == std::string::npos ? "." : p.substr(0, k);
+}
+static std::string selfDir() {
+    Dl_info info;
+    if (dladdr((void *)&selfDir, &info) && info.dli_fname) return dirOf(info.dli_fname);
+    return ".";
+}
+
+Engine::Engine(const std::string &name, const std::string &backendLib, const std::string &assetRoot)
+    : m_name(name), m_backendLib(backendLib), m_assetRoot(assetRoot) {
+    if (m_backendLib.empty()) m_backendLib = selfDir() + "/libptc_cuda.so";
+    if (m_assetRoot.empty()) {
+        const char *env = std::getenv("VVIEWER_ASSETS");
+        m_assetRoot = env ? env : (selfDir() + "/../..");
+    }
+    m_textures = std::make_unique<Textures>();
+    m_materials = std::make_unique<Materials>(*m_textures);
+    m_scene = std::make_unique<Scene>(*this);
+    m_renderer = std::make_unique<Renderer>(std::make_unique<CudaRendererPathTracing>(*this, m_backendLib));
+}
+Engine::~Engine() {}
+
+std::string Engine::assetPath(const std::string &rel) const {
+    if (!rel.empty() && rel[0] == '/') return rel;
+    return m_assetRoot + "/" + rel;
+}
+
+void Engine::initResources() {
+    /* initDefaultData, VulkanEngine.cpp:331-391 */
+    auto *defaultMaterial = m_materials->createMaterial<MaterialPBRStandard>(AssetInfo("defaultMaterial", AssetSource::ENGINE));
+    defaultMaterial->albedo() = vec4(0.8f, 0.8f, 0.8f, 1);
+    defaultMaterial->metallic() = 0.5f;
+    defaultMaterial->roughness() = 0.5f;
+    defaultMaterial->ao() = 1.0f;
+    defaultMaterial->emissive() = vec4(0, 0, 0, 1);
+    auto *defaultEmissive = m_materials->createMaterial<MaterialPBRStandard>(AssetInfo("defaultEmissive", AssetSource::ENGINE));
+    defaultEmissive->albedo() = vec4(1, 1, 1, 1);
+    defaultEmissive->emissive() = vec4(1, 1, 1, 1);
+    auto *defaultVolume = m_materials->createMaterial<MaterialVolume>(AssetInfo("defaultVolume", AssetSource::ENGINE));
+    defaultVolume->sigmaS() = vec4(0.01f, 0.01f, 0.01f, 1);
+    defaultVolume->sigmaA() = vec4(0.01f, 0.01f, 0.01f, 1);
+    defaultVolume->g() = 0.0f;
+
+    m_lightsMap.add("defaultPointLight", m_scene->createLight(AssetInfo("defaultPointLight", AssetSource::ENGINE), LightType::POINT_LIGHT, vec4(1, 1, 1, 1)));
+    m_lightsMap.add("defaultDirectionalLightSun",
+                    m_scene->createLight(AssetInfo("defaultDirectionalLightSun", AssetSource::ENGINE), LightType::DIRECTIONAL_LIGHT, vec4(1, 0.9f, 0.8f, 1)));
+    m_lightsMap.add("defaultDirectionalLightMoon",
+                    m_scene->createLight(AssetInfo("defaultDirectionalLightMoon", AssetSource::ENGINE), LightType::DIRECTIONAL_LIGHT, vec4(0.31f, 0.4f, 0.52f, 1)));
+
+    importModel(AssetInfo("assets/models/uvsphere.obj", AssetSource::ENGINE), false);
+    importModel(AssetInfo("assets/models/plane.obj", AssetSource::ENGINE), false);
+    importModel(AssetInfo("assets/models/cube.obj", AssetSource::ENGINE), false);
+
+    m_scene->skyboxMaterial() = importEnvironmentMap(AssetInfo("assets/HDR/harbor.hdr", AssetSource::ENGINE));
+}
+
+Model3D *Engine::addModel(std::unique_ptr<Model3D> model) {
+    Model3D *raw = model.get();
+    for (auto &m : raw->meshes) {
+        m->poolIndex = (uint32_t)m_meshPool.size();
+        m_meshPool.push_back(m.get());
+    }
+    m_ownedModels.push_back(std::move(model));
+    m_models.add(raw->name, raw);
+    return raw;
+}
+
+Model3D *Engine::importModel(const AssetInfo &info, bool) {
+    if (m_models.has(info.name)) return m_models.get(info.name);
+    auto model = std::make_unique<Model3D>();
+    model->name = info.name;
+    std::string err;
+    if (!loadOBJ(assetPath(info.filepath), *model, &err)) {
+        std::fprintf(stderr, "Engine::importModel(): %s\n", err.c_str());
+        return nullptr;
+    }
+    return addModel(std::move(model));
+}
+
+EnvironmentMap *Engine::importEnvironmentMap(const AssetInfo &info) {
+    for (auto &e : m_envMaps)
+        if (e->name == info.name) return e.get();
+    auto env = std::make_unique<EnvironmentMap>();
+    env->name = info.name;
+    if (!loadImageHDR(assetPath(info.filepath), env->equirect, true)) {
+        std::fprintf(stderr, "Engine::importEnvironmentMap(): unable to load %s\n", info.filepath.c_str());
+        return nullptr;
+    }
+    m_envMaps.push_back(std::move(env));
+    return m_envMaps.back().get();
+}
+
+void Engine::flatten(FlatScene &out) {
+    out = FlatScene();
+    /* geometry pools: only meshes that are instanced */
+    std::unordered_map<Mesh *, uint32_t> meshSlot;
+    InstancesManager &im = m_scene->instancesManager();
+    auto slotOf = [&](Mesh *mesh) -> uint32_t {
+        auto it = meshSlot.find(mesh);
+        if (it != meshSlot.end()) return it->second;
+        ptc_mesh pm{};
+        pm.first_index = (uint32_t)out.indices.size();
+        pm.tri_count = mesh->nTriangles();
+        pm.first_vertex = (uint32_t)out.vertices.size();
+        pm.vertex_count = (uint32_t)mesh->vertices.size();
+        out.vertices.insert(out.vertices.end(), mesh->vertices.begin(), mesh->vertices.end());
+        out.indices.insert(out.indices.end(), mesh->indices.begin(), mesh->indices.begin() + (size_t)pm.tri_count * 3);
+        uint32_t s = (uint32_t)out.meshes.size();
+        out.meshes.push_back(pm);
+        meshSlot[mesh] = s;
+        return s;
+    };
+    std::unordered_map<SceneObject *, uint32_t> instanceSlot;
+    /* initInstanceData, Instances.cpp:76-98 + VulkanInstances.cpp:117-130. Light-only objects own an
+     * InstanceData slot in the reference as well but carry no geometry; they are skipped here because
+     * nothing on the path-tracing path reads them. */
+    for (SceneObject *so : im.instanceOrder()) {
+        if (!so->has<ComponentMesh>() || !so->has<ComponentMaterial>()) continue;
+        Mesh *mesh = so->get<ComponentMesh>().mesh();
+        Material *mat = so->get<ComponentMaterial>().material();
+        if (!mesh || !mat) continue;
+        ptc_instance inst{};
+        std::memcpy(inst.model, so->modelMatrix().data(), 64);
+        inst.id[0] = (float)so->getID();
+        inst.id[1] = -1;
+        inst.id[2] = -1;
+        inst.id[3] = 0;
+        inst.material_index = mat->materialIndex();
+        if (so->has<ComponentVolume>()) {
+            ComponentVolume &v = so->get<ComponentVolume>();
+            if (v.frontFacing()) inst.id[1] = (float)v.frontFacing()->materialIndex();
+            if (v.backFacing()) inst.id[2] = (float)v.backFacing()->materialIndex();
+        }
+        inst.mesh_index = slotOf(mesh);
+        inst.num_triangles = mesh->nTriangles();
+        instanceSlot[so] = (uint32_t)out.instances.size();
+        out.instances.push_back(inst);
+    }
+    out.materials = m_materials->blocks();
+    out.lightData = m_scene->lightData();
+    /* VulkanInstancesManager::build, VulkanInstances.cpp:66-109 */
+    for (SceneObject *so : im.lights()) {
+        Light *light = so->get<ComponentLight>().light();
+        ptc_light_instance li{};
+        li.info[0] = light->lightIndex();
+        li.info[1] = 0;
+        li.info[3] = (uint32_t)light->type();
+        if (light->type() == LightType::POINT_LIGHT) {
+            vec3 p = so->worldPosition();
+            li.position[0] = p.x; li.position[1] = p.y; li.position[2] = p.z;
+        } else if (light->type() == LightType::DIRECTIONAL_LIGHT) {
+            vec4 d = so->modelMatrix() * vec4(0, 0, 1, 0);
+            li.position[0] = d.x; li.position[1] = d.y; li.position[2] = d.z;
+        }
+        li.position[3] = so->get<ComponentLight>().castShadows() ? 1.0f : 0.0f;
+        out.lightInstances.push_back(li);
+    }
+    for (SceneObject *so : im.meshLights()) {
+        auto it = instanceSlot.find(so);
+        if (it == instanceSlot.end()) continue;
+        ptc_light_instance li{};
+        li.info[1] = it->second;
+        li.info[3] = (uint32_t)LightType::MESH_LIGHT;
+        const mat4 &m = so->modelMatrix();
+        for (int c = 0; c < 4; c++) {
+            li.position[c] = m[c][0];
+            li.position1[c] = m[c][1];
+            li.position2[c] = m[c][2];
+        }
+        out.lightInstances.push_back(li);
+    }
+    for (auto &t : m_textures->all()) {
+        ptc_texture pt{};
+        pt.width = (uint32_t)t->image.width;
+        pt.height = (uint32_t)t->image.height;
+        pt.channels = (uint32_t)t->image.channels;
+        pt.srgb = t->colorSpace == ColorSpace::sRGB ? 1u : 0u;
+        pt.data = t->image.data.data();
+        out.textures.push_back(pt);
+    }
+    ptc_scene_desc &d = out.desc;
+    d.vertices = out.vertices.data();
+    d.n_vertices = out.vertices.size();
+    d.indices = out.indices.data();
+    d.n_indices = out.indices.size();
+    d.meshes = out.meshes.data();
+    d.n_meshes = (uint32_t)out.meshes.size();
+    d.instances = out.instances.data();
+    d.n_instances = (uint32_t)out.instances.size();
+    d.materials = out.materials.data();
+    d.n_materials = (uint32_t)out.materials.size();
+    d.light_data = out.lightData.data();
+    d.n_light_data = (uint32_t)out.lightData.size();
+    d.light_instances = out.lightInstances.data();
+    d.n_light_instances = (uint32_t)out.lightInstances.size();
+    d.textures = out.textures.data();
+    d.n_textures = (uint32_t)out.textures.size();
+    EnvironmentMap *env = m_scene->skyboxMaterial();
+    if (env && !env->equirect.data.empty()) {
+        d.env.equirect_rgba = env->equirect.data.data();
+        d.env.width = (uint32_t)env->equirect.width;
+        d.env.height = (uint32_t)env->equirect.height;
+    }
+}
+
+/* ====================================================================== renderer */
+bool PtcBackend::load(const std::string &libPath, std::string *err) {
+    path = libPath;
+    handle = dlopen(libPath.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!handle) {
+        if (err) *err = std::string("cannot load path-tracing backend '") + libPath + "': " + dlerror();
+        return false;
+    }
+#define PTC_SYM(field, sym)                                                      \
+    field = reinterpret_cast<decltype(field)>(dlsym(handle, #sym));              \
+    if (!field) {                                                                \
+        if (err) *err = std::string("backend is missing symbol ") + #sym;        \
+        return false;                                                            \
+    }
+    PTC_SYM(create, ptc_create)
+    PTC_SYM(destroy, ptc_destroy)
+    PTC_SYM(last_error, ptc_last_error)
+    PTC_SYM(backend_name, ptc_backend_name)
+    PTC_SYM(upload_scene, ptc_upload_scene)
+    PTC_SYM(build_accel, ptc_build_accel)
+    PTC_SYM(render, ptc_render)
+    PTC_SYM(progress, ptc_progress)
+    PTC_SYM(get_stats, ptc_get_stats)
+#undef PTC_SYM
+    return true;
+}
+
+CudaRendererPathTracing::CudaRendererPathTracing(Engine &engine, const std::string &backendLib) : m_engine(engine) {
+    /* like VulkanRendererPathTracing::initResources (…PathTracing.cpp:45-91) a failure leaves
+     * isRayTracingEnabled() == false; render() then reports the error and returns */
+    if (!m_backend.load(backendLib, &m_error)) {
+        std::fprintf(stderr, "CudaRendererPathTracing: %s\n", m_error.c_str());
+        return;
+    }
+    if (m_backend.create(&m_ctx, nullptr, 0) != 0 || !m_ctx) {
+        m_error = std::string("ptc_create failed: ") + (m_ctx ? m_backend.last_error(m_ctx) : "no context");
+        std::fprintf(stderr, "CudaRendererPathTracing: %s\n", m_error.c_str());
+        return;
+    }
+    m_isInitialized = true;
+}
+
+CudaRendererPathTracing::~CudaRendererPathTracing() {
+    if (m_ctx) m_backend.destroy(m_ctx);
+}
+
+float CudaRendererPathTracing::renderProgress() { return (m_ctx && m_isInitialized) ? m_backend.progress(m_ctx) : 0.0f; }
+
+ptc_render_params CudaRendererPathTracing::makeRenderParams() {
+    /* VulkanRendererPathTracing::render, …PathTracing.cpp:143-199 */
+    Scene &scene = m_engine.scene();
+    auto camera = scene.camera();
+    ptc_render_params rp{};
+    rp.scene = scene.getSceneData();
+    uint32_t width = renderInfo().width, height = renderInfo().height;
+    mat4 proj(1.0f);
+    if (camera->type() == CameraType::PERSPECTIVE) {
+        auto pc = std::static_pointer_cast<PerspectiveCamera>(camera);
+        proj = vm::perspective(vm::radians(pc->fov()), static_cast<float>(width) / height, camera->znear(), camera->zfar());
+        rp.camera_type = PTC_CAMERA_PERSPECTIVE;
+    } else {
+        /* trap T10: the reference builds glm::ortho in pixel units and still shoots rays from the eye
+         * point; we render a true orthographic view of orthoWidth x orthoWidth / aspect */
+        auto oc = std::static_pointer_cast<OrthographicCamera>(camera);
+        float ow = oc->orthoWidth(), oh = ow / (static_cast<float>(width) / height);
+        proj = vm::ortho(-ow / 2, ow / 2, -oh / 2, oh / 2, camera->znear(), camera->zfar());
+        rp.camera_type = PTC_CAMERA_ORTHOGRAPHIC;
+        rp.ortho_width = ow;
+        rp.ortho_height = oh;
+    }
+    proj[1][1] *= -1;
+    mat4 projInv = vm::inverse(proj);
+    std::memcpy(rp.scene.projection, proj.data(), 64);
+    std::memcpy(rp.scene.projection_inverse, projInv.data(), 64);
+    rp.scene.volumes[0] = -1;
+    if (camera->volume() != nullptr) {
+        if (camera->volume()->type() != MaterialType::MATERIAL_VOLUME)
+            std::fprintf(stderr, "The material set for the render camera's volume is not a volume material\n");
+        else
+            rp.scene.volumes[0] = static_cast<float>(camera->volume()->materialIndex());
+    }
+    rp.samples = renderInfo().samples;
+    rp.batch_size = renderInfo().batchSize;
+    rp.depth = renderInfo().depth;
+    rp.width = width;
+    rp.height = height;
+    rp.split_mode = PTC_SPLIT_NONE;
+    rp.rank = 0;
+    rp.world = 1;
+    return rp;
+}
+
+bool CudaRendererPathTracing::renderToMemory(std::vector<float> &radiance, std::vector<float> &albedo, std::vector<float> &normal) {
+    if (!m_isInitialized) {
+        std::fprintf(stderr, "CudaRendererPathTracing::render(): backend not initialised: %s\n", m_error.c_str());
+        return false;
+    }
+    if (m_renderInProgress) return false;
+    Scene &scene = m_engine.scene();
+    if (scene.getSceneObjectsFlat().empty()) {
+        std::fprintf(stderr, "Trying to render an empty scene\n");
+        return false;
+    }
+    m_renderInProgress = true;
+    bool ok = false;
+    do {
+        FlatScene flat;
+        m_engine.flatten(flat);
+        ptc_render_params rp = makeRenderParams();
+        if (m_backend.upload_scene(m_ctx, &flat.desc) != 0) break;
+        if (m_backend.build_accel(m_ctx) != 0) break;
+        size_t n = (size_t)rp.width * rp.height * 4;
+        radiance.assign(n, 0.0f);
+        albedo.assign(n, 0.0f);
+        normal.assign(n, 0.0f);
+        if (m_backend.render(m_ctx, &rp, radiance.data(), albedo.data(), normal.data()) != 0) break;
+        m_backend.get_stats(m_ctx, &m_stats);
+        ok = true;
+    } while (false);
+    if (!ok) {
+        m_error = m_backend.last_error(m_ctx);
+        std::fprintf(stderr, "CudaRendererPathTracing::render(): %s\n", m_error.c_str());
+    }
+    m_renderInProgress = false;
+    return ok;
+}
+
+void CudaRendererPathTracing::render() {
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<float> radiance, albedo, normal;
+    if (!renderToMemory(radiance, albedo, normal)) return;
+    /* storeToDisk, …PathTracing.cpp:958-1027 (OIDN is out of scope: denoise == true writes the
+     * un-denoised radiance and, with writeAllFiles, the _radiance AOV) */
+    const RenderInfo &ri = renderInfo();
+    const uint32_t channels = 4;
+    if (ri.writeAllFiles) {
+        writeToDisk(albedo, ri.filename + "_albedo", FileType::HDR, ri.width, ri.height, channels);
+        writeToDisk(normal, ri.filename + "_normal", FileType::HDR, ri.width, ri.height, channels);
+        if (ri.denoise) writeToDisk(radiance, ri.filename + "_radiance", FileType::HDR, ri.width, ri.height, channels);
+    }
+    if (ri.fileType == FileType::PNG && ri.exposure != 0.0f) applyExposure(radiance, ri.exposure, channels);
+    writeToDisk(radiance, ri.filename, ri.fileType, ri.width, ri.height, channels);
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::string ext = (ri.fileType == FileType::PNG) ? "png" : "hdr";
+    std::printf("Scene rendered: %s.%s in: %dms\n", ri.filename.c_str(), ext.c_str(), (int)ms);
+}
+
+}  // namespace vengine
