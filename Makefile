@@ -8,7 +8,7 @@ CXX       := $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
 LIBDIR    := vviewer_b200/_lib
 ORCDIR    := oracle/_build
 
-NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --use_fast_math=false \
+NVCCFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
              -Xcompiler -fPIC,-fvisibility=hidden,-O3 -Xptxas -v -Iinclude
 CXXFLAGS  := -O2 -std=c++17 -fPIC -fvisibility=hidden -Wall -Wno-unused-variable -Wno-unused-function -Iinclude
 

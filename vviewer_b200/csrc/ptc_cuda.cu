@@ -1,0 +1,710 @@
+/*
+ * libptc_cuda.so — the product: include/ptc.h implemented with hand-written sm_100a CUDA.
+ * No CPU fallback exists; every entry point fails loudly when CUDA is unavailable.
+ *
+ * Host side of the hot path = what VulkanRendererPathTracing::render() does below the scene model
+ * (src/lib/vengine/vulkan/renderers/VulkanRendererPathTracing.cpp:121-226, 791-956): upload scene records,
+ * (re)build the acceleration structure, loop over batches, read the three RGBA32F targets back.
+ */
+#include "common.cuh"
+#include "bsdf.cuh"
+#include "lbvh.cuh"
+#include "traverse.cuh"
+#include "wavefront.cuh"
+
+#include <atomic>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+struct TextureSlot {
+    cudaArray_t array = nullptr;
+    cudaTextureObject_t tex = 0;
+};
+
+}  // namespace
+
+struct ptc_ctx {
+    int device = 0;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    int smCount = 148;
+
+    /* scene */
+    DBuf<ptc_vertex> vertices;
+    DBuf<uint32_t> indices;
+    DBuf<DInstance> instances;
+    DBuf<ptc_material> materials;
+    DBuf<ptc_light_data> lightData;
+    DBuf<ptc_light_instance> lightInstances;
+    DBuf<cudaTextureObject_t> texTable;
+    std::vector<TextureSlot> textures;
+    cudaArray_t cubeArray = nullptr;
+    cudaTextureObject_t cubeTex = 0;
+    uint32_t cubeN = 0;
+    uint32_t nInstances = 0, nMaterials = 0, nLightInstances = 0, nTextures = 0, nWorldTris = 0;
+    bool anyEmissive = false, anyTransparent = false, anyVolumeChange = false;
+    bool sceneUploaded = false, accelBuilt = false;
+    lbvh::Build accel;
+
+    /* render state */
+    DBuf<float4> accR, accA, accN;
+    DBuf<float4> wOrgRng, wDirFlags, wBeta, wRadiance, wHit, wAovA, wAovN, wShOrg, wShDir, wShContrib, wPrBeta;
+    DBuf<uint32_t> wQueue0, wQueue1, wQShadow, wQProbe, wCounters, pixmap;
+    DBuf<unsigned long long> wStats;
+    size_t waveCapacity = 0;
+    cudaEvent_t evA = nullptr, evB = nullptr;
+
+    std::atomic<float> progress{0.0f};
+    ptc_stats stats{};
+
+    void freeTextures() {
+        for (auto &t : textures) {
+            if (t.tex) cudaDestroyTextureObject(t.tex);
+            if (t.array) cudaFreeArray(t.array);
+        }
+        textures.clear();
+        if (cubeTex) cudaDestroyTextureObject(cubeTex);
+        if (cubeArray) cudaFreeArray(cubeArray);
+        cubeTex = 0;
+        cubeArray = nullptr;
+        cubeN = 0;
+    }
+    ~ptc_ctx() {
+        cudaSetDevice(device);
+        freeTextures();
+        if (evA) cudaEventDestroy(evA);
+        if (evB) cudaEventDestroy(evB);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+int fail(ptc_ctx *c, const std::string &msg) {
+    if (c) c->err = msg;
+    return 1;
+}
+
+/* 3x3 inverse of the upper-left block of a column-major 4x4; row-major output */
+void inverse3(const float *M, float *out) {
+    float a = M[0], b = M[4], c = M[8];
+    float d = M[1], e = M[5], f = M[9];
+    float g = M[2], h = M[6], i = M[10];
+    float co00 = e * i - f * h, co01 = -(d * i - f * g), co02 = d * h - e * g;
+    float det = a * co00 + b * co01 + c * co02;
+    float id = 1.0f / det;
+    out[0] = co00 * id;
+    out[1] = -(b * i - c * h) * id;
+    out[2] = (b * f - c * e) * id;
+    out[3] = co01 * id;
+    out[4] = (a * i - c * g) * id;
+    out[5] = -(a * f - c * d) * id;
+    out[6] = co02 * id;
+    out[7] = -(a * h - b * g) * id;
+    out[8] = (a * e - b * d) * id;
+}
+
+DScene makeDScene(ptc_ctx *c) {
+    DScene s{};
+    s.vertices = c->vertices.p;
+    s.indices = c->indices.p;
+    s.instances = c->instances.p;
+    s.materials = c->materials.p;
+    s.lightData = c->lightData.p;
+    s.lightInstances = c->lightInstances.p;
+    s.textures = c->texTable.p;
+    s.cubemap = c->cubeTex;
+    s.nInstances = c->nInstances;
+    s.nMaterials = c->nMaterials;
+    s.nLightInstances = c->nLightInstances;
+    s.nTextures = c->nTextures;
+    s.hasCubemap = c->cubeTex ? 1u : 0u;
+    s.bvhNodes = c->accel.nodes.p;
+    s.tris = c->accel.trisSorted.p;
+    s.nTris = c->accelBuilt ? c->accel.n : 0u;
+    s.rootIsLeaf = c->accel.n == 1 ? 1 : 0;
+    s.anyEmissive = c->anyEmissive ? 1u : 0u;
+    s.anyTransparent = c->anyTransparent ? 1u : 0u;
+    s.anyVolume = c->anyVolumeChange ? 1u : 0u;
+    return s;
+}
+
+void createTexture2D(ptc_ctx *c, const ptc_texture &in, TextureSlot &slot) {
+    /* every texture becomes RGBA8 (an R8 source reads back as (r, 0, 0, 1) like VK_FORMAT_R8_UNORM) */
+    std::vector<uint8_t> rgba((size_t)in.width * in.height * 4);
+    for (size_t p = 0; p < (size_t)in.width * in.height; p++) {
+        uint8_t px[4] = {0, 0, 0, 255};
+        for (uint32_t k = 0; k < in.channels && k < 4; k++) px[k] = in.data[p * in.channels + k];
+        std::memcpy(&rgba[p * 4], px, 4);
+    }
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+    CUDA_TRY(cudaMallocArray(&slot.array, &fmt, in.width, in.height));
+    CUDA_TRY(cudaMemcpy2DToArray(slot.array, 0, 0, rgba.data(), (size_t)in.width * 4, (size_t)in.width * 4, in.height, cudaMemcpyHostToDevice));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = slot.array;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap; /* REPEAT */
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    td.sRGB = in.srgb ? 1 : 0; /* VK_FORMAT_R8G8B8A8_SRGB: decode before filtering */
+    CUDA_TRY(cudaCreateTextureObject(&slot.tex, &rd, &td, nullptr));
+}
+
+void createCubemap(ptc_ctx *c, const ptc_env &env) {
+    if (!env.equirect_rgba || !env.width || !env.height) return;
+    const uint32_t N = std::max(1u, std::min(env.width / 4u, 1080u)); /* VulkanRendererSkybox.cpp:100 */
+    /* equirect as a float4 texture: linear, REPEAT, like the reference's sampler for the HDR image */
+    cudaArray_t eqArray = nullptr;
+    cudaTextureObject_t eqTex = 0;
+    cudaChannelFormatDesc f4 = cudaCreateChannelDesc<float4>();
+    CUDA_TRY(cudaMallocArray(&eqArray, &f4, env.width, env.height));
+    CUDA_TRY(cudaMemcpy2DToArray(eqArray, 0, 0, env.equirect_rgba, (size_t)env.width * 16, (size_t)env.width * 16, env.height, cudaMemcpyHostToDevice));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = eqArray;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    CUDA_TRY(cudaCreateTextureObject(&eqTex, &rd, &td, nullptr));
+
+    DBuf<float4> faces;
+    faces.alloc((size_t)6 * N * N);
+    dim3 block(16, 16, 1), grid((N + 15) / 16, (N + 15) / 16, 6);
+    wf::k_equirect_to_cube<<<grid, block, 0, c->stream>>>(eqTex, N, faces.p);
+    CUDA_TRY(cudaGetLastError());
+
+    CUDA_TRY(cudaMalloc3DArray(&c->cubeArray, &f4, make_cudaExtent(N, N, 6), cudaArrayCubemap));
+    cudaMemcpy3DParms cp{};
+    cp.srcPtr = make_cudaPitchedPtr(faces.p, (size_t)N * 16, N, N);
+    cp.dstArray = c->cubeArray;
+    cp.extent = make_cudaExtent(N, N, 6);
+    cp.kind = cudaMemcpyDeviceToDevice;
+    CUDA_TRY(cudaMemcpy3DAsync(&cp, c->stream));
+    cudaResourceDesc crd{};
+    crd.resType = cudaResourceTypeArray;
+    crd.res.array.array = c->cubeArray;
+    cudaTextureDesc ctd{};
+    ctd.addressMode[0] = ctd.addressMode[1] = ctd.addressMode[2] = cudaAddressModeClamp;
+    ctd.filterMode = cudaFilterModeLinear;
+    ctd.readMode = cudaReadModeElementType;
+    ctd.normalizedCoords = 1;
+    ctd.seamlessCubemap = 1;
+    CUDA_TRY(cudaCreateTextureObject(&c->cubeTex, &crd, &ctd, nullptr));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaDestroyTextureObject(eqTex);
+    cudaFreeArray(eqArray);
+    c->cubeN = N;
+}
+
+void ensureWave(ptc_ctx *c, size_t slots, uint32_t depth) {
+    if (slots > c->waveCapacity) {
+        c->wOrgRng.alloc(slots);
+        c->wDirFlags.alloc(slots);
+        c->wBeta.alloc(slots);
+        c->wRadiance.alloc(slots);
+        c->wHit.alloc(slots);
+        c->wAovA.alloc(slots);
+        c->wAovN.alloc(slots);
+        c->wShOrg.alloc(slots);
+        c->wShDir.alloc(slots);
+        c->wShContrib.alloc(slots);
+        c->wPrBeta.alloc(slots);
+        c->wQueue0.alloc(slots);
+        c->wQueue1.alloc(slots);
+        c->wQShadow.alloc(slots);
+        c->wQProbe.alloc(slots);
+        c->waveCapacity = slots;
+    }
+    c->wCounters.alloc((size_t)(depth + 2) * wf::CNT_STRIDE);
+    c->wStats.alloc(wf::ST_COUNT);
+}
+
+wf::Wave makeWave(ptc_ctx *c) {
+    wf::Wave w{};
+    w.orgRng = c->wOrgRng.p;
+    w.dirFlags = c->wDirFlags.p;
+    w.beta = c->wBeta.p;
+    w.radiance = c->wRadiance.p;
+    w.hit = c->wHit.p;
+    w.aovAlbedo = c->wAovA.p;
+    w.aovNormal = c->wAovN.p;
+    w.shOrgTmax = c->wShOrg.p;
+    w.shDirVol = c->wShDir.p;
+    w.shContrib = c->wShContrib.p;
+    w.prBetaPdf = c->wPrBeta.p;
+    w.queue[0] = c->wQueue0.p;
+    w.queue[1] = c->wQueue1.p;
+    w.qShadow = c->wQShadow.p;
+    w.qProbe = c->wQProbe.p;
+    w.counters = c->wCounters.p;
+    w.stats = c->wStats.p;
+    return w;
+}
+
+int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, float4 *dN) {
+    const uint32_t W = rp->width, H = rp->height;
+    const uint32_t batches = rp->samples / rp->batch_size; /* VulkanRendererPathTracing.cpp:798-799 (T7) */
+    const uint32_t totalSamples = batches * rp->batch_size;
+    const uint32_t world = rp->world ? rp->world : 1u;
+    const uint32_t tile = rp->tile_size ? rp->tile_size : 32u;
+    const size_t nPix = (size_t)W * H;
+    cudaStream_t s = c->stream;
+
+    /* pixel set of this rank */
+    uint32_t nPixLocal = (uint32_t)nPix;
+    const uint32_t *pixmapPtr = nullptr;
+    if (rp->split_mode == PTC_SPLIT_TILE && world > 1) {
+        std::vector<uint32_t> pm;
+        pm.reserve(nPix / world + 1024);
+        const uint32_t tilesX = (W + tile - 1) / tile;
+        for (uint32_t y = 0; y < H; y++)
+            for (uint32_t x = 0; x < W; x++)
+                if (((y / tile) * tilesX + (x / tile)) % world == rp->rank) pm.push_back(y * W + x);
+        nPixLocal = (uint32_t)pm.size();
+        c->pixmap.upload(pm.data(), pm.size(), s);
+        CUDA_TRY(cudaStreamSynchronize(s));
+        pixmapPtr = c->pixmap.p;
+    }
+
+    /* explicit clear (the reference relies on fresh device memory being zero, trap T8) */
+    CUDA_TRY(cudaMemsetAsync(dR, 0, nPix * sizeof(float4), s));
+    CUDA_TRY(cudaMemsetAsync(dA, 0, nPix * sizeof(float4), s));
+    CUDA_TRY(cudaMemsetAsync(dN, 0, nPix * sizeof(float4), s));
+
+    /* samples of one batch run concurrently; very large batches are cut into chunks that fit the wave */
+    const size_t maxSlots = (size_t)1 << 26;
+    uint32_t chunkSamples = rp->batch_size;
+    if (nPixLocal > 0) chunkSamples = (uint32_t)std::max<size_t>(1, std::min<size_t>(rp->batch_size, maxSlots / nPixLocal));
+    ensureWave(c, (size_t)chunkSamples * std::max(1u, nPixLocal), rp->depth);
+    wf::Wave w = makeWave(c);
+    CUDA_TRY(cudaMemsetAsync(c->wStats.p, 0, wf::ST_COUNT * sizeof(unsigned long long), s));
+
+    wf::RenderConst rc{};
+    rc.sd = rp->scene;
+    rc.width = W;
+    rc.height = H;
+    rc.depth = rp->depth;
+    rc.totalSamples = totalSamples;
+    rc.cameraType = rp->camera_type;
+    rc.orthoW = rp->ortho_width;
+    rc.orthoH = rp->ortho_height;
+    rc.totalLights = c->nLightInstances;
+    rc.flags = rp->flags;
+    rc.nPixLocal = nPixLocal;
+    rc.pixmap = pixmapPtr;
+    DScene sc = makeDScene(c);
+
+    const int gridTrace = c->smCount * 8;  /* persistent: 8 blocks of 128 threads per SM */
+    const int gridShade = c->smCount * 8;
+    uint64_t launches = 0, traceLaunches = 0;
+    double traceMs = 0, shadeMs = 0, shadowMs = 0;
+    const bool timeKernels = std::getenv("PTC_TIME_KERNELS") != nullptr;
+    auto timed = [&](double &acc, auto &&launch) {
+        if (timeKernels) CUDA_TRY(cudaEventRecord(c->evA, s));
+        launch();
+        if (timeKernels) {
+            CUDA_TRY(cudaEventRecord(c->evB, s));
+            CUDA_TRY(cudaEventSynchronize(c->evB));
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, c->evA, c->evB));
+            acc += ms;
+        }
+    };
+
+    cudaEvent_t evStart, evStop;
+    CUDA_TRY(cudaEventCreate(&evStart));
+    CUDA_TRY(cudaEventCreate(&evStop));
+    CUDA_TRY(cudaEventRecord(evStart, s));
+    uint32_t myBatches = 0, doneBatches = 0;
+    for (uint32_t b = 0; b < batches; b++)
+        if (!(rp->split_mode == PTC_SPLIT_SAMPLE && world > 1 && (b % world) != rp->rank)) myBatches++;
+
+    if (nPixLocal > 0) {
+        for (uint32_t b = 0; b < batches; b++) {
+            if (rp->split_mode == PTC_SPLIT_SAMPLE && world > 1 && (b % world) != rp->rank) continue;
+            for (uint32_t s0 = 0; s0 < rp->batch_size; s0 += chunkSamples) {
+                const uint32_t ns = std::min(chunkSamples, rp->batch_size - s0);
+                const uint32_t nSlots = ns * nPixLocal;
+                CUDA_TRY(cudaMemsetAsync(c->wCounters.p, 0, (size_t)(rp->depth + 2) * wf::CNT_STRIDE * sizeof(uint32_t), s));
+                wf::k_raygen<<<(nSlots + 255) / 256, 256, 0, s>>>(w, rc, nSlots, b * rp->batch_size + s0);
+                launches++;
+                for (uint32_t d = 0; d < rp->depth; d++) {
+                    timed(traceMs, [&] { wf::k_extend<<<gridTrace, TRV_BLOCK, 0, s>>>(w, sc, d); });
+                    timed(shadeMs, [&] { wf::k_shade<<<gridShade, 128, 0, s>>>(w, sc, rc, d); });
+                    launches += 2;
+                    traceLaunches++;
+                    if (rc.totalLights > 0) {
+                        timed(shadowMs, [&] { wf::k_shadow<<<gridTrace, TRV_BLOCK, 0, s>>>(w, sc, rc, d); });
+                        launches++;
+                    }
+                    if (c->anyEmissive) {
+                        timed(shadowMs, [&] { wf::k_probe<<<gridTrace, TRV_BLOCK, 0, s>>>(w, sc, rc, d); });
+                        launches++;
+                    }
+                }
+                wf::k_collect_stats<<<1, 32, 0, s>>>(w, rp->depth);
+                wf::k_accumulate<<<(nPixLocal + 255) / 256, 256, 0, s>>>(w, rc, ns, dR, dA, dN);
+                launches += 2;
+            }
+            doneBatches++;
+            CUDA_TRY(cudaGetLastError());
+            /* renderProgress(): batches complete when the stream reaches this point; keep the queue short
+             * enough that the number is meaningful without stalling the device */
+            if ((doneBatches & 3u) == 0u) {
+                CUDA_TRY(cudaStreamSynchronize(s));
+                c->progress = (float)doneBatches / (float)myBatches;
+            }
+        }
+    }
+    /* alpha = 1 everywhere, including pixels owned by other ranks when this image is the reduce root's term */
+    CUDA_TRY(cudaEventRecord(evStop, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, evStart, evStop));
+    cudaEventDestroy(evStart);
+    cudaEventDestroy(evStop);
+
+    unsigned long long hs[wf::ST_COUNT];
+    CUDA_TRY(cudaMemcpy(hs, c->wStats.p, sizeof(hs), cudaMemcpyDeviceToHost));
+    c->stats.segments = hs[wf::ST_SEGMENTS];
+    c->stats.path_rays = hs[wf::ST_SEGMENTS];
+    c->stats.shadow_rays = hs[wf::ST_SHADOW_RAYS];
+    c->stats.shadow_hops = hs[wf::ST_SHADOW_HOPS];
+    c->stats.probe_rays = hs[wf::ST_PROBE_RAYS];
+    c->stats.probe_hops = hs[wf::ST_PROBE_HOPS];
+    c->stats.render_ms = ms;
+    c->stats.trace_ms = traceMs;
+    c->stats.shade_ms = shadeMs;
+    c->stats.shadow_ms = shadowMs;
+    c->stats.trace_launches = traceLaunches;
+    c->stats.kernel_launches = launches;
+    c->progress = 1.0f;
+    return 0;
+}
+
+__global__ void k_fill_alpha(float4 *a, float4 *b, float4 *cc, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    a[i].w = 1.0f;
+    b[i].w = 1.0f;
+    cc[i].w = 1.0f;
+}
+
+}  // namespace
+
+/* ====================================================================== C-ABI */
+#define PTC_GUARD_BEGIN try {
+#define PTC_GUARD_END(ctx)                          \
+    }                                               \
+    catch (const CudaError &e) {                    \
+        return fail(ctx, e.msg);                    \
+    }                                               \
+    catch (const std::exception &e) {               \
+        return fail(ctx, e.what());                 \
+    }
+
+extern "C" {
+
+PTC_API const char *ptc_backend_name(void) { return "cuda-sm_100a"; }
+
+PTC_API int ptc_create(ptc_ctx **out, const int *device_ids, int n_devices) {
+    if (!out) return 1;
+    *out = nullptr;
+    ptc_ctx *c = new ptc_ctx();
+    *out = c; /* returned even on failure so that ptc_last_error can explain */
+    PTC_GUARD_BEGIN
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(c, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    c->device = (device_ids && n_devices > 0) ? device_ids[0] : 0;
+    if (!(device_ids && n_devices > 0)) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) == cudaSuccess) c->device = cur;
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major != 10) return fail(c, std::string("device '") + prop.name + "' is not sm_100; this build targets B200 only");
+    c->smCount = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&c->evA));
+    CUDA_TRY(cudaEventCreate(&c->evB));
+    return 0;
+    PTC_GUARD_END(c)
+}
+
+PTC_API void ptc_destroy(ptc_ctx *ctx) { delete ctx; }
+PTC_API const char *ptc_last_error(const ptc_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
+    if (!c || !sd) return fail(c, "null argument");
+    if (!c->stream) return fail(c, "context has no CUDA device");
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    c->sceneUploaded = false;
+    c->accelBuilt = false;
+    c->vertices.upload(sd->vertices, sd->n_vertices, s);
+    c->indices.upload(sd->indices, sd->n_indices, s);
+    c->materials.upload(sd->materials, sd->n_materials, s);
+    c->lightData.upload(sd->light_data, sd->n_light_data, s);
+    c->lightInstances.upload(sd->light_instances, sd->n_light_instances, s);
+    c->nMaterials = sd->n_materials;
+    c->nLightInstances = sd->n_light_instances;
+    c->nInstances = sd->n_instances;
+
+    std::vector<DInstance> inst(sd->n_instances);
+    uint64_t tri = 0;
+    c->anyEmissive = c->anyTransparent = c->anyVolumeChange = false;
+    for (uint32_t i = 0; i < sd->n_instances; i++) {
+        const ptc_instance &in = sd->instances[i];
+        if (in.mesh_index >= sd->n_meshes) return fail(c, "instance mesh index out of range");
+        if (in.material_index >= sd->n_materials) return fail(c, "instance material index out of range");
+        const ptc_mesh &m = sd->meshes[in.mesh_index];
+        DInstance &d = inst[i];
+        const float *M = in.model;
+        for (int r = 0; r < 3; r++)
+            for (int col = 0; col < 4; col++) d.m[r * 4 + col] = M[col * 4 + r];
+        inverse3(M, d.nrm);
+        /* world->object = [A^-1 | -A^-1 t] */
+        for (int r = 0; r < 3; r++) {
+            for (int col = 0; col < 3; col++) d.w2o[r * 4 + col] = d.nrm[r * 3 + col];
+            d.w2o[r * 4 + 3] = -(d.nrm[r * 3 + 0] * M[12] + d.nrm[r * 3 + 1] * M[13] + d.nrm[r * 3 + 2] * M[14]);
+        }
+        d.volFront = in.id[1];
+        d.volBack = in.id[2];
+        d.material = in.material_index;
+        d.firstIndex = m.first_index;
+        d.firstVertex = m.first_vertex;
+        d.numTriangles = in.num_triangles;
+        d.firstWorldTri = (uint32_t)tri;
+        d.pad = 0;
+        tri += m.tri_count;
+        const ptc_material &mat = sd->materials[in.material_index];
+        const float ei = mat.emissive[3];
+        if (std::fabs(ei * mat.emissive[0]) > 0.05f || std::fabs(ei * mat.emissive[1]) > 0.05f || std::fabs(ei * mat.emissive[2]) > 0.05f)
+            c->anyEmissive = true;
+        if (mat.metallic_roughness_ao[3] > 0.0f) c->anyTransparent = true;
+        if (in.id[1] != in.id[2]) c->anyVolumeChange = true;
+    }
+    if (tri >= 0x7fffffffull) return fail(c, "more than 2^31 world triangles");
+    c->nWorldTris = (uint32_t)tri;
+    c->instances.upload(inst.data(), inst.size(), s);
+
+    c->freeTextures();
+    c->textures.resize(sd->n_textures);
+    std::vector<cudaTextureObject_t> table(sd->n_textures);
+    for (uint32_t t = 0; t < sd->n_textures; t++) {
+        const ptc_texture &in = sd->textures[t];
+        if (in.channels != 1 && in.channels != 4) return fail(c, "texture channels must be 1 or 4");
+        createTexture2D(c, in, c->textures[t]);
+        table[t] = c->textures[t].tex;
+    }
+    c->nTextures = sd->n_textures;
+    c->texTable.upload(table.data(), table.size(), s);
+    createCubemap(c, sd->env);
+    CUDA_TRY(cudaStreamSynchronize(s));
+    c->sceneUploaded = true;
+    return 0;
+    PTC_GUARD_END(c)
+}
+
+PTC_API int ptc_build_accel(ptc_ctx *c) {
+    if (!c) return 1;
+    if (!c->sceneUploaded) return fail(c, "ptc_upload_scene has not been called");
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->evA, c->stream));
+    c->accel.run(c->vertices.p, c->indices.p, c->instances.p, c->nInstances, c->nWorldTris, c->stream);
+    CUDA_TRY(cudaEventRecord(c->evB, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->evA, c->evB));
+    c->accelBuilt = true;
+    c->stats.build_ms = ms;
+    c->stats.n_triangles = c->nWorldTris;
+    c->stats.n_bvh_nodes = c->nWorldTris ? 2ull * c->nWorldTris - 1 : 0;
+    c->stats.scene_bytes = c->accel.bytes() + c->vertices.bytes() + c->indices.bytes() + c->instances.bytes() + c->materials.bytes();
+    return 0;
+    PTC_GUARD_END(c)
+}
+
+static int renderChecked(ptc_ctx *c, const ptc_render_params *rp) {
+    if (!c || !rp) return fail(c, "null argument");
+    if (!c->accelBuilt) return fail(c, "ptc_build_accel has not been called");
+    if (rp->batch_size == 0 || rp->width == 0 || rp->height == 0 || rp->depth == 0) return fail(c, "bad render params");
+    if (rp->depth > 255) return fail(c, "depth must be <= 255");
+    if ((uint64_t)rp->width * rp->height >= 0x7fffffffull) return fail(c, "image too large");
+    return 0;
+}
+
+PTC_API int ptc_render_device(ptc_ctx *c, const ptc_render_params *rp, void *dR, void *dA, void *dN) {
+    if (int rcode = renderChecked(c, rp)) return rcode;
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t nPix = (size_t)rp->width * rp->height;
+    float4 *r = (float4 *)dR, *a = (float4 *)dA, *n = (float4 *)dN;
+    if (!r) { c->accR.alloc(nPix); r = c->accR.p; }
+    if (!a) { c->accA.alloc(nPix); a = c->accA.p; }
+    if (!n) { c->accN.alloc(nPix); n = c->accN.p; }
+    int rcode = renderImpl(c, rp, r, a, n);
+    if (rcode) return rcode;
+    if (rp->split_mode == PTC_SPLIT_NONE || rp->rank == 0) {
+        k_fill_alpha<<<(unsigned)((nPix + 255) / 256), 256, 0, c->stream>>>(r, a, n, nPix);
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+    PTC_GUARD_END(c)
+}
+
+PTC_API int ptc_render(ptc_ctx *c, const ptc_render_params *rp, float *radiance, float *albedo, float *normal) {
+    if (int rcode = renderChecked(c, rp)) return rcode;
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t nPix = (size_t)rp->width * rp->height;
+    c->accR.alloc(nPix);
+    c->accA.alloc(nPix);
+    c->accN.alloc(nPix);
+    int rcode = renderImpl(c, rp, c->accR.p, c->accA.p, c->accN.p);
+    if (rcode) return rcode;
+    k_fill_alpha<<<(unsigned)((nPix + 255) / 256), 256, 0, c->stream>>>(c->accR.p, c->accA.p, c->accN.p, nPix);
+    /* readback like getRenderTargetData x3 (…PathTracing.cpp:890-893) */
+    if (radiance) CUDA_TRY(cudaMemcpyAsync(radiance, c->accR.p, nPix * 16, cudaMemcpyDeviceToHost, c->stream));
+    if (albedo) CUDA_TRY(cudaMemcpyAsync(albedo, c->accA.p, nPix * 16, cudaMemcpyDeviceToHost, c->stream));
+    if (normal) CUDA_TRY(cudaMemcpyAsync(normal, c->accN.p, nPix * 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+    PTC_GUARD_END(c)
+}
+
+PTC_API float ptc_progress(const ptc_ctx *c) { return c ? c->progress.load() : 0.0f; }
+PTC_API int ptc_get_stats(ptc_ctx *c, ptc_stats *out) {
+    if (!c || !out) return 1;
+    *out = c->stats;
+    return 0;
+}
+
+PTC_API int ptc_trace_closest(ptc_ctx *c, const float *rays, int n, int *inst, int *prim, float *t, float *u, float *v) {
+    if (!c || !rays) return fail(c, "null argument");
+    if (!c->accelBuilt) return fail(c, "ptc_build_accel has not been called");
+    if (n <= 0) return 0;
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    DBuf<float> dRays, dT, dU, dV;
+    DBuf<int> dInst, dPrim;
+    dRays.upload(rays, (size_t)n * 8, s);
+    dT.alloc(n); dU.alloc(n); dV.alloc(n); dInst.alloc(n); dPrim.alloc(n);
+    DScene sc = makeDScene(c);
+    wf::k_trace_closest<<<(n + TRV_BLOCK - 1) / TRV_BLOCK, TRV_BLOCK, 0, s>>>(sc, dRays.p, n, dInst.p, dPrim.p, dT.p, dU.p, dV.p);
+    CUDA_TRY(cudaGetLastError());
+    if (inst) CUDA_TRY(cudaMemcpyAsync(inst, dInst.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (prim) CUDA_TRY(cudaMemcpyAsync(prim, dPrim.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (t) CUDA_TRY(cudaMemcpyAsync(t, dT.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (u) CUDA_TRY(cudaMemcpyAsync(u, dU.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    if (v) CUDA_TRY(cudaMemcpyAsync(v, dV.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+    PTC_GUARD_END(c)
+}
+
+PTC_API int ptc_get_lbvh(ptc_ctx *c, uint64_t *n_out, uint64_t *morton, uint32_t *order, int32_t *parent, int32_t *left, int32_t *right,
+                         float *aabb) {
+    if (!c) return 1;
+    if (!c->accelBuilt) return fail(c, "ptc_build_accel has not been called");
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    const lbvh::Build &B = c->accel;
+    const size_t n = B.n;
+    if (n_out) *n_out = n;
+    if (n == 0) return 0;
+    const size_t nn = 2 * n - 1;
+    if (morton) CUDA_TRY(cudaMemcpy(morton, B.keysSorted.p, n * 8, cudaMemcpyDeviceToHost));
+    if (order) CUDA_TRY(cudaMemcpy(order, B.order.p, n * 4, cudaMemcpyDeviceToHost));
+    if (parent) CUDA_TRY(cudaMemcpy(parent, B.parent.p, nn * 4, cudaMemcpyDeviceToHost));
+    if (left) CUDA_TRY(cudaMemcpy(left, B.left.p, nn * 4, cudaMemcpyDeviceToHost));
+    if (right) CUDA_TRY(cudaMemcpy(right, B.right.p, nn * 4, cudaMemcpyDeviceToHost));
+    if (aabb) {
+        std::vector<float4> lo(nn), hi(nn);
+        CUDA_TRY(cudaMemcpy(lo.data(), B.nodeLo.p, nn * 16, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(hi.data(), B.nodeHi.p, nn * 16, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < nn; i++) {
+            aabb[i * 6 + 0] = lo[i].x; aabb[i * 6 + 1] = lo[i].y; aabb[i * 6 + 2] = lo[i].z;
+            aabb[i * 6 + 3] = hi[i].x; aabb[i * 6 + 4] = hi[i].y; aabb[i * 6 + 5] = hi[i].z;
+        }
+    }
+    return 0;
+    PTC_GUARD_END(c)
+}
+
+PTC_API int ptc_bsdf_eval(ptc_ctx *c, int n, const float *params, const float *wi, const float *wo, float *out_f, float *out_pdf) {
+    if (!c || !c->stream) return fail(c, "context has no CUDA device");
+    if (n <= 0) return 0;
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    DBuf<float> dP, dWi, dWo, dF, dPdf;
+    dP.upload(params, (size_t)n * 5, s);
+    dWi.upload(wi, (size_t)n * 3, s);
+    dWo.upload(wo, (size_t)n * 3, s);
+    dF.alloc((size_t)n * 3);
+    dPdf.alloc(n);
+    wf::k_bsdf_eval<<<(n + 255) / 256, 256, 0, s>>>(n, dP.p, dWi.p, dWo.p, dF.p, dPdf.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_f, dF.p, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_pdf, dPdf.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+    PTC_GUARD_END(c)
+}
+
+PTC_API int ptc_bsdf_sample(ptc_ctx *c, int n, const float *params, const float *wo, const float *u, float *out_wi, float *out_f,
+                            float *out_pdf) {
+    if (!c || !c->stream) return fail(c, "context has no CUDA device");
+    if (n <= 0) return 0;
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    DBuf<float> dP, dWo, dU, dWi, dF, dPdf;
+    dP.upload(params, (size_t)n * 5, s);
+    dWo.upload(wo, (size_t)n * 3, s);
+    dU.upload(u, (size_t)n * 3, s);
+    dWi.alloc((size_t)n * 3);
+    dF.alloc((size_t)n * 3);
+    dPdf.alloc(n);
+    wf::k_bsdf_sample<<<(n + 255) / 256, 256, 0, s>>>(n, dP.p, dWo.p, dU.p, dWi.p, dF.p, dPdf.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_wi, dWi.p, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_f, dF.p, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_pdf, dPdf.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+    PTC_GUARD_END(c)
+}
+
+PTC_API int ptc_env_lookup(ptc_ctx *c, int n, const float *dirs, float *out_rgb) {
+    if (!c || !c->stream) return fail(c, "context has no CUDA device");
+    if (n <= 0) return 0;
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    DBuf<float> dD, dO;
+    dD.upload(dirs, (size_t)n * 3, s);
+    dO.alloc((size_t)n * 3);
+    DScene sc = makeDScene(c);
+    wf::k_env_lookup<<<(n + 255) / 256, 256, 0, s>>>(sc, n, dD.p, dO.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_rgb, dO.p, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+    PTC_GUARD_END(c)
+}
+
+} /* extern "C" */

@@ -1,0 +1,864 @@
+/*
+ * Wavefront path-tracing pipeline: raygen -> [extend -> shade -> shadow -> probe] x depth -> accumulate.
+ * Replaces the Vulkan ray-tracing pipeline of the reference (paths under src/lib/vengine/shaders/pt/):
+ *   k_raygen      raygen.rgen.glsl:24-98        camera ray, thin lens, path state init
+ *   k_extend      traceRayEXT at raygen.rgen.glsl:110 (closest hit, sbt offset 0)
+ *   k_shade       rayPrimaryLambert.rchit / rayPrimaryPBRStandard.rchit / rayPrimary.rmiss incl.
+ *                 process_volume_hit.glsl, lightSampling.glsl:1-106 (sampling part), russian_roulette.glsl
+ *   k_shadow      lightSampling.glsl:108-144 + raySecondary.rahit/.rchit/.rmiss (shadow chain)
+ *   k_probe       next_event_estimation.glsl + rayNEE.rahit/.rchit/.rmiss (BSDF-sample emissive probe)
+ *   k_accumulate  raygen.rgen.glsl:126-144
+ * Path state is SoA in HBM, one slot per (sample, pixel) of the batch; queues hold slot ids and are compacted
+ * with ballot/popc warp-aggregated atomics.  Kernels are persistent grid-stride loops that read their work
+ * count from device memory, so a whole batch runs without a single host synchronisation.
+ */
+#pragma once
+#include "common.cuh"
+#include "bsdf.cuh"
+#include "traverse.cuh"
+
+namespace wf {
+
+/* flags word of a path */
+#define PF_DEPTH_MASK 0xffu
+#define PF_SURFACE 0x100u /* surfaceDepth > 0 */
+#define PF_INVOL 0x200u   /* insideVolume */
+#define PF_VOL_SHIFT 16
+
+enum { CNT_ACTIVE = 0, CNT_SHADOW = 1, CNT_PROBE = 2, CNT_STRIDE = 4 };
+enum { ST_SEGMENTS = 0, ST_SHADOW_RAYS, ST_SHADOW_HOPS, ST_PROBE_RAYS, ST_PROBE_HOPS, ST_COUNT };
+
+struct Wave {
+    float4 *orgRng;    /* origin.xyz, rng state */
+    float4 *dirFlags;  /* direction.xyz, flags */
+    float4 *beta;      /* throughput.xyz */
+    float4 *radiance;  /* rgb */
+    float4 *hit;       /* t, u, v, triangle position (int bits, -1 = miss) */
+    float4 *aovAlbedo; /* first-hit albedo */
+    float4 *aovNormal; /* first-hit normal * 0.5 + 0.5 */
+    float4 *shOrgTmax; /* shadow request: origin.xyz, tmax */
+    float4 *shDirVol;  /* direction.xyz, volume state (flags bits) */
+    float4 *shContrib; /* unshadowed contribution rgb */
+    float4 *prBetaPdf; /* probe request: beta before roulette .xyz, sampling pdf */
+    uint32_t *queue[2];
+    uint32_t *qShadow, *qProbe;
+    uint32_t *counters; /* [depth + 1][CNT_STRIDE] */
+    unsigned long long *stats;
+};
+
+struct RenderConst {
+    ptc_scene_data sd;
+    uint32_t width, height, depth, totalSamples;
+    uint32_t cameraType;
+    float orthoW, orthoH;
+    uint32_t totalLights;
+    uint32_t flags;
+    uint32_t nPixLocal;      /* pixels rendered by this rank */
+    const uint32_t *pixmap;  /* local pixel -> global pixel, or nullptr = identity */
+};
+
+PTC_D uint32_t laneId() { return threadIdx.x & 31u; }
+
+/* ballot/popc compaction: every lane of the warp must call this */
+PTC_D void queuePush(uint32_t *__restrict__ queue, uint32_t *__restrict__ counter, bool pred, uint32_t value) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0u) return;
+    const int leader = __ffs(m) - 1;
+    uint32_t base = 0;
+    if ((int)laneId() == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) queue[base + __popc(m & ((1u << laneId()) - 1u))] = value;
+}
+PTC_D void statAdd(unsigned long long *stat, uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (laneId() == 0 && v) atomicAdd(stat, (unsigned long long)v);
+}
+
+PTC_D float3 mulPoint(const float *m /*3x4 row-major*/, float3 p) {
+    return f3(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7], m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
+}
+PTC_D float3 mulNormal(const float *a /*3x3 row-major inverse*/, float3 n) { /* a^T * n */
+    return f3(a[0] * n.x + a[3] * n.y + a[6] * n.z, a[1] * n.x + a[4] * n.y + a[7] * n.z, a[2] * n.x + a[5] * n.y + a[8] * n.z);
+}
+PTC_D float3 ld3(const float *p) { return f3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
+
+PTC_D float4 texFetch(const DScene &sc, uint32_t idx, float u, float v) {
+    if (idx >= sc.nTextures) return make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    return tex2D<float4>(sc.textures[idx], u, v);
+}
+PTC_D float3 envFetch(const DScene &sc, float3 d) {
+    if (!sc.hasCubemap) return f3(0.0f);
+    float4 c = texCubemap<float4>(sc.cubemap, d.x, d.y, d.z);
+    return f3(c);
+}
+
+/* ------------------------------------------------------------------ geometry of a hit (process_hit.glsl + construct_frame.glsl) */
+struct Surf {
+    const DInstance *inst;
+    const ptc_material *mat;
+    float3 p0, p1, p2; /* object-space positions */
+    float2 uv;
+    float3 pos, n, t; /* world position, unnormalised->normalised world normal / tangent */
+};
+PTC_D void loadSurf(const DScene &sc, int32_t triPos, float u, float v, bool wantFrame, Surf &s) {
+    const float4 a = __ldg(&sc.tris[3 * (size_t)triPos + 0]);
+    const float4 b = __ldg(&sc.tris[3 * (size_t)triPos + 1]);
+    const uint32_t instIdx = __float_as_uint(a.w), prim = __float_as_uint(b.w);
+    const DInstance *I = &sc.instances[instIdx];
+    s.inst = I;
+    s.mat = &sc.materials[I->material];
+    const uint32_t *ind = sc.indices + I->firstIndex + 3 * (size_t)prim;
+    const ptc_vertex *V0 = &sc.vertices[I->firstVertex + __ldg(ind + 0)];
+    const ptc_vertex *V1 = &sc.vertices[I->firstVertex + __ldg(ind + 1)];
+    const ptc_vertex *V2 = &sc.vertices[I->firstVertex + __ldg(ind + 2)];
+    const float w0 = 1.0f - u - v, w1 = u, w2 = v;
+    s.p0 = ld3(V0->position);
+    s.p1 = ld3(V1->position);
+    s.p2 = ld3(V2->position);
+    s.uv = make_float2(__ldg(&V0->uv[0]) * w0 + __ldg(&V1->uv[0]) * w1 + __ldg(&V2->uv[0]) * w2,
+                       __ldg(&V0->uv[1]) * w0 + __ldg(&V1->uv[1]) * w1 + __ldg(&V2->uv[1]) * w2);
+    float3 lp = s.p0 * w0 + s.p1 * w1 + s.p2 * w2;
+    s.pos = mulPoint(I->m, lp);
+    float3 ln = ld3(V0->normal) * w0 + ld3(V1->normal) * w1 + ld3(V2->normal) * w2;
+    s.n = normalize(mulNormal(I->nrm, ln));
+    if (wantFrame) {
+        float3 lt = ld3(V0->tangent) * w0 + ld3(V1->tangent) * w1 + ld3(V2->tangent) * w2;
+        s.t = normalize(mulNormal(I->nrm, lt));
+    }
+}
+
+/* ------------------------------------------------------------------ volumes */
+struct Medium {
+    float3 sigma_s, sigma_t;
+    float g;
+};
+PTC_D Medium loadMedium(const DScene &sc, uint32_t idx) { /* process_volume_hit.glsl:3-8 */
+    const ptc_material *m = &sc.materials[idx];
+    float3 sa = ld3(m->albedo);
+    float3 ss = fmax3(ld3(m->metallic_roughness_ao), f3(PT_EPSILON));
+    Medium md;
+    md.sigma_s = ss;
+    md.sigma_t = sa + ss;
+    md.g = __ldg(&m->emissive[0]);
+    return md;
+}
+PTC_D float3 transmittance(const DScene &sc, uint32_t volIdx, float vtstart, float vtend) { /* process_volume_transmittance.glsl */
+    Medium md = loadMedium(sc, volIdx);
+    float dist = fmaxf(vtend - vtstart, PT_EPSILON);
+    return exp3(-(md.sigma_t * dist));
+}
+PTC_D void volumeChange(const DInstance *I, bool flipped, uint32_t &flags) { /* rchit :74-90 */
+    flags &= ~(PF_INVOL | 0xffff0000u);
+    float nv = flipped ? I->volFront : I->volBack;
+    if (nv != -1.0f) flags |= PF_INVOL | ((uint32_t)nv << PF_VOL_SHIFT);
+}
+
+/* ------------------------------------------------------------------ light sampling (lightSampling.glsl:1-106) */
+struct LightSample {
+    float3 dir, radiance;
+    float pdf, tmax;
+    bool delta;
+};
+PTC_D LightSample sampleLight(const DScene &sc, const RenderConst &rc, uint32_t &rng, float3 origin) {
+    LightSample ls;
+    ls.delta = true;
+    ls.radiance = f3(0.0f);
+    ls.pdf = 1.0f;
+    ls.dir = f3(0.0f, 1.0f, 0.0f);
+    ls.tmax = 10000.0f;
+    const uint32_t totalLights = rc.totalLights;
+    if (totalLights == 0u) return ls;
+    const float pick = 1.0f / (float)totalLights;
+    uint32_t li = min((uint32_t)(rnd(rng) * (float)totalLights), totalLights - 1u);
+    const ptc_light_instance *L = &sc.lightInstances[li];
+    const uint32_t type = __ldg(&L->info[3]);
+    if (type == 0u) { /* point */
+        const ptc_light_data *ld = &sc.lightData[__ldg(&L->info[0])];
+        float3 lp = ld3(L->position);
+        float3 d = lp - origin;
+        ls.tmax = length(d);
+        ls.dir = d / ls.tmax;
+        float dist = length(origin - lp);
+        ls.radiance = ld3(ld->color) * (1.0f / (dist * dist)) * __ldg(&ld->color[3]);
+        ls.pdf = pick;
+    } else if (type == 1u) { /* directional; direction left unnormalised (trap T4) */
+        const ptc_light_data *ld = &sc.lightData[__ldg(&L->info[0])];
+        ls.dir = -ld3(L->position);
+        ls.tmax = rc.sd.volumes[2];
+        ls.radiance = ld3(ld->color) * __ldg(&ld->color[3]);
+        ls.pdf = pick;
+    } else if (type == 2u) { /* mesh light */
+        const DInstance *I = &sc.instances[__ldg(&L->info[1])];
+        const ptc_material *mat = &sc.materials[I->material];
+        const uint32_t nt = I->numTriangles;
+        uint32_t tri = min((uint32_t)(rnd(rng) * (float)nt), nt - 1u);
+        const float u0 = rnd(rng), u1 = rnd(rng);
+        float2 bc = sampleTriangle(u0, u1);
+        float3 sb = f3(bc.x, bc.y, 1.0f - bc.x - bc.y);
+        const uint32_t *ind = sc.indices + I->firstIndex + 3 * (size_t)tri;
+        const ptc_vertex *V0 = &sc.vertices[I->firstVertex + __ldg(ind + 0)];
+        const ptc_vertex *V1 = &sc.vertices[I->firstVertex + __ldg(ind + 1)];
+        const ptc_vertex *V2 = &sc.vertices[I->firstVertex + __ldg(ind + 2)];
+        float3 q0 = ld3(V0->position), q1 = ld3(V1->position), q2 = ld3(V2->position);
+        float3 w0 = mulPoint(I->m, q0), w1 = mulPoint(I->m, q1), w2 = mulPoint(I->m, q2);
+        float area = 0.5f * length(cross(w1 - w0, w2 - w0));
+        float3 sp = mulPoint(I->m, q0 * sb.x + q1 * sb.y + q2 * sb.z);
+        /* transpose(inverse(M)) * n, NOT normalised (trap T5) */
+        float3 sn = mulNormal(I->nrm, ld3(V0->normal) * sb.x + ld3(V1->normal) * sb.y + ld3(V2->normal) * sb.z);
+        float su = sb.x * __ldg(&V0->uv[0]) + sb.y * __ldg(&V1->uv[0]) + sb.z * __ldg(&V2->uv[0]);
+        float sv = sb.x * __ldg(&V0->uv[1]) + sb.y * __ldg(&V1->uv[1]) + sb.z * __ldg(&V2->uv[1]);
+        float3 d = sp - origin;
+        ls.tmax = length(d);
+        ls.dir = d / ls.tmax;
+        float dp = dot(-ls.dir, sn);
+        if (dp > 0.0f) {
+            float4 et = texFetch(sc, __ldg(&mat->tex2[0]), su * __ldg(&mat->uv_tiling[0]), sv * __ldg(&mat->uv_tiling[1]));
+            ls.radiance = ld3(mat->emissive) * __ldg(&mat->emissive[3]) * f3(et);
+            float dd = length(origin - sp);
+            ls.pdf = pick * (1.0f / (float)nt) * (1.0f / area) * (dd * dd) / dp;
+        } else {
+            ls.radiance = f3(0.0f);
+            ls.pdf = 0.0f;
+        }
+        ls.delta = false;
+    }
+    return ls;
+}
+
+/* requests produced by one shading event */
+struct Requests {
+    bool shadow, probe;
+    float3 shOrigin, shDir, shContrib;
+    float shTmax;
+    float3 prBeta;
+    float prPdf;
+};
+
+/* ------------------------------------------------------------------ k_raygen */
+__global__ void __launch_bounds__(256) k_raygen(Wave w, const __grid_constant__ RenderConst rc, uint32_t nSlots, uint32_t firstSample) {
+    uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot == 0) w.counters[CNT_ACTIVE] = nSlots;
+    if (slot >= nSlots) return;
+    const uint32_t p = slot % rc.nPixLocal, s = slot / rc.nPixLocal;
+    const uint32_t pixel = rc.pixmap ? rc.pixmap[p] : p;
+    const uint32_t px = pixel % rc.width, py = pixel / rc.width;
+    uint32_t rng = rngSeed(px, py, rc.width, firstSample + s);
+    const float u0 = rnd(rng), u1 = rnd(rng);
+    const float dx = (((float)px + u0) / (float)rc.width) * 2.0f - 1.0f;
+    const float dy = (((float)py + u1) / (float)rc.height) * 2.0f - 1.0f;
+    float3 oc = f3(0.0f), dc;
+    if (rc.cameraType == PTC_CAMERA_ORTHOGRAPHIC) { /* documented deviation T10 */
+        oc = f3(dx * 0.5f * rc.orthoW, -dy * 0.5f * rc.orthoH, 0.0f);
+        dc = f3(0.0f, 0.0f, -1.0f);
+    } else { /* projectionInverse * (d.x, d.y, 1, 1), no w divide (raygen.rgen.glsl:67-71) */
+        const float *pi = rc.sd.projection_inverse;
+        float3 target = f3(pi[0] * dx + pi[4] * dy + pi[8] + pi[12], pi[1] * dx + pi[5] * dy + pi[9] + pi[13], pi[2] * dx + pi[6] * dy + pi[10] + pi[14]);
+        dc = normalize(target);
+    }
+    const float lensRadius = rc.sd.exposure[2];
+    if (lensRadius > 0.0f) { /* raygen.rgen.glsl:74-85 */
+        const float l0 = rnd(rng), l1 = rnd(rng);
+        float2 disk = concentricDisk(l0, l1);
+        float ft = rc.sd.exposure[3] / (-dc.z);
+        float3 focus = oc + dc * ft;
+        oc = oc + f3(lensRadius * disk.x, lensRadius * disk.y, 0.0f);
+        dc = normalize(focus - oc);
+    }
+    const float *vi = rc.sd.view_inverse;
+    /* same evaluation order as the oracle's xform_point / xform_dir */
+    float3 o = f3(((vi[0] * oc.x + vi[4] * oc.y) + vi[8] * oc.z) + vi[12], ((vi[1] * oc.x + vi[5] * oc.y) + vi[9] * oc.z) + vi[13],
+                  ((vi[2] * oc.x + vi[6] * oc.y) + vi[10] * oc.z) + vi[14]);
+    float3 d = f3((vi[0] * dc.x + vi[4] * dc.y) + vi[8] * dc.z, (vi[1] * dc.x + vi[5] * dc.y) + vi[9] * dc.z, (vi[2] * dc.x + vi[6] * dc.y) + vi[10] * dc.z);
+    uint32_t flags = 0;
+    if (rc.sd.volumes[0] != -1.0f) flags |= PF_INVOL | ((uint32_t)(int)rc.sd.volumes[0] << PF_VOL_SHIFT);
+    w.orgRng[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(rng));
+    w.dirFlags[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(flags));
+    w.beta[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    w.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    w.aovAlbedo[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    w.aovNormal[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+/* ------------------------------------------------------------------ k_extend */
+__global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_constant__ DScene sc, uint32_t bounce) {
+    __shared__ int32_t stack[24 * TRV_BLOCK];
+    const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_ACTIVE];
+    const uint32_t *__restrict__ q = w.queue[bounce & 1u];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const uint32_t slot = bounce == 0u ? i : q[i];
+        const float4 o = w.orgRng[slot], d = w.dirFlags[slot];
+        trv::Ray ray;
+        ray.o = f3(o);
+        ray.d = f3(d);
+        ray.tmin = 0.001f;
+        ray.tmax = 10000.0f;
+        trv::HitRec h = trv::closestHit(sc, ray, stack + threadIdx.x);
+        w.hit[slot] = make_float4(h.t, h.u, h.v, __int_as_float(h.pos));
+    }
+}
+
+/* ------------------------------------------------------------------ k_shade */
+/* process_volume_hit.glsl:1-80. Returns sampledMedium; on scattering fills the requests and the new ray. */
+PTC_D bool volumeEvent(const DScene &sc, const RenderConst &rc, uint32_t &rng, uint32_t flags, float3 &origin, float3 &dir, float3 &beta,
+                       float vtstart, float vtend, Requests &rq) {
+    Medium md = loadMedium(sc, flags >> PF_VOL_SHIFT);
+    const float g = fmaxf(fminf(md.g, 0.99f), -0.99f);
+    const float3 wdir = normalize(dir);
+    const float3 wo = -wdir;
+    const float distInside = fmaxf(vtend - vtstart, PT_EPSILON);
+    const uint32_t channel = min((uint32_t)(rnd(rng) * 3.0f), 2u);
+    const float hitDistance = -logf(1.0f - rnd(rng)) / comp(md.sigma_t, (int)channel);
+    const bool sampled = hitDistance < distInside;
+    const float3 T = exp3(-(md.sigma_t * fminf(hitDistance, distInside)));
+    const float3 density = sampled ? (md.sigma_t * T) : T;
+    float pdf = (density.x + density.y + density.z) * 0.3333333f;
+    if (pdf == 0.0f) pdf = 1.0f;
+    beta *= sampled ? (T * md.sigma_s / pdf) : (T / pdf);
+    if (sampled) {
+        const float3 sp = origin + wdir * (vtstart + hitDistance);
+        LightSample ls = sampleLight(sc, rc, rng, sp);
+        if (!isBlack(ls.radiance)) {
+            const float p = hg(dot(wo, ls.dir), g);
+            if (p != 0.0f) {
+                float3 c = ls.radiance * p * beta / ls.pdf;
+                if (!ls.delta) c = c * powerHeuristic(ls.pdf, p);
+                rq.shadow = true;
+                rq.shOrigin = sp;
+                rq.shDir = ls.dir;
+                rq.shTmax = ls.tmax;
+                rq.shContrib = c;
+            }
+        }
+        const float h0 = rnd(rng), h1 = rnd(rng);
+        float3 nd;
+        const float spdf = hgSample(wo, nd, h0, h1, g);
+        origin = sp;
+        dir = nd;
+        rq.probe = true;
+        rq.prBeta = beta;
+        rq.prPdf = spdf;
+    }
+    return sampled;
+}
+
+/* russian_roulette.glsl:1-11; returns true when the path dies */
+PTC_D bool roulette(uint32_t &rng, uint32_t depth, float3 &beta) {
+    const float r = rnd(rng);
+    if (depth > 3u) {
+        const float mb = max3(beta);
+        if (r >= mb) return true;
+        beta = beta * (1.0f / mb);
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(128) k_shade(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce) {
+    const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_ACTIVE];
+    const uint32_t *__restrict__ q = w.queue[bounce & 1u];
+    uint32_t *__restrict__ qNext = w.queue[(bounce + 1u) & 1u];
+    uint32_t *cntNext = &w.counters[(bounce + 1u) * CNT_STRIDE + CNT_ACTIVE];
+    uint32_t *cntShadow = &w.counters[bounce * CNT_STRIDE + CNT_SHADOW];
+    uint32_t *cntProbe = &w.counters[bounce * CNT_STRIDE + CNT_PROBE];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounded = (count + 31u) & ~31u;
+    const bool lastBounce = bounce + 1u >= rc.depth;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+        const bool valid = i < count;
+        uint32_t slot = 0;
+        bool alive = false;
+        Requests rq;
+        rq.shadow = rq.probe = false;
+        if (valid) {
+            slot = bounce == 0u ? i : q[i];
+            const float4 h = w.hit[slot];
+            const float4 o4 = w.orgRng[slot], d4 = w.dirFlags[slot];
+            float3 origin = f3(o4), dir = f3(d4);
+            uint32_t rng = __float_as_uint(o4.w), flags = __float_as_uint(d4.w);
+            flags = (flags & ~PF_DEPTH_MASK) | (bounce & PF_DEPTH_MASK);
+            float3 beta = f3(w.beta[slot]);
+            float3 radiance = f3(w.radiance[slot]);
+            const float3 rayDir = dir;
+            const int32_t triPos = __float_as_int(h.w);
+            bool stop = false;
+            bool doRoulette = true;
+
+            if (triPos >= 0) {
+                Surf s;
+                loadSurf(sc, triPos, h.y, h.z, true, s);
+                Frame fr;
+                fr.n = s.n;
+                fr.t = s.t;
+                const bool flipped = fixFrame(fr, rayDir);
+                bool sampledMedium = false;
+                if (flags & PF_INVOL) sampledMedium = volumeEvent(sc, rc, rng, flags, origin, dir, beta, 0.001f, h.x, rq);
+                if (!sampledMedium) {
+                    const ptc_material *mat = s.mat;
+                    const float tu = s.uv.x * __ldg(&mat->uv_tiling[0]), tv = s.uv.y * __ldg(&mat->uv_tiling[1]);
+                    const bool lambert = (int)__ldg(&mat->uv_tiling[2]) == PTC_MATERIAL_LAMBERT;
+                    bool passThrough = false;
+                    if (__ldg(&mat->metallic_roughness_ao[3]) > 0.0f) { /* stochastic transparency, rchit :66-96 */
+                        const float alpha = __ldg(&mat->albedo[3]) * texFetch(sc, __ldg(&mat->tex2[3]), tu, tv).x;
+                        const float r = rnd(rng);
+                        if (alpha < PT_EPSILON || r > alpha) {
+                            if (s.inst->volFront != s.inst->volBack) volumeChange(s.inst, flipped, flags);
+                            origin = s.pos;
+                            dir = normalize(rayDir);
+                            passThrough = true;
+                            doRoulette = false;
+                        }
+                    }
+                    if (!passThrough) {
+                        applyNormal(fr, normalFromMap(f3(texFetch(sc, __ldg(&mat->tex2[1]), tu, tv))));
+                        const float3 albedo = ld3(mat->albedo) * f3(texFetch(sc, __ldg(&mat->tex1[0]), tu, tv));
+                        const float3 emissive = ld3(mat->emissive) * __ldg(&mat->emissive[3]) * f3(texFetch(sc, __ldg(&mat->tex2[0]), tu, tv));
+                        Pbr pbr;
+                        pbr.albedo = albedo;
+                        pbr.metallic = 0.0f;
+                        pbr.roughness = 1.0f;
+                        if (!lambert) {
+                            pbr.metallic = __ldg(&mat->metallic_roughness_ao[0]) * texFetch(sc, __ldg(&mat->tex1[1]), tu, tv).x;
+                            pbr.roughness = fmaxf(__ldg(&mat->metallic_roughness_ao[1]) * texFetch(sc, __ldg(&mat->tex1[2]), tu, tv).x, 0.035f);
+                        }
+                        const bool first = !(flags & PF_SURFACE);
+                        if (first) {
+                            w.aovAlbedo[slot] = make_float4(albedo.x, albedo.y, albedo.z, 0.0f);
+                            float3 nn = fr.n * 0.5f + f3(0.5f);
+                            w.aovNormal[slot] = make_float4(nn.x, nn.y, nn.z, 0.0f);
+                        }
+                        if (first && !isBlackEps(emissive, lambert ? 0.05f : 0.1f) && !flipped) {
+                            radiance += emissive * beta; /* emission only at the first surface (trap T2) */
+                            stop = true;
+                            doRoulette = false;
+                        } else {
+                            flags |= PF_SURFACE;
+                            const float3 wo = toLocal(fr, -rayDir);
+                            LightSample ls = sampleLight(sc, rc, rng, s.pos);
+                            if (!isBlack(ls.radiance)) {
+                                const float3 wi = toLocal(fr, ls.dir);
+                                float3 F;
+                                float bsdfPdf;
+                                if (lambert) {
+                                    const float c = clampf(wi.y, 0.0f, 1.0f);
+                                    F = albedo * PT_INV_PI * c;
+                                    bsdfPdf = c * PT_INV_PI;
+                                } else {
+                                    F = pbrEval(pbr, wi, wo);
+                                    bsdfPdf = ls.delta ? 0.0f : pbrPdf(wi, wo, pbr);
+                                }
+                                if (!isBlack(F)) {
+                                    float3 c = ls.radiance * F * beta / ls.pdf;
+                                    if (!ls.delta) c = c * powerHeuristic(ls.pdf, bsdfPdf);
+                                    rq.shadow = true;
+                                    rq.shOrigin = s.pos;
+                                    rq.shDir = ls.dir;
+                                    rq.shTmax = ls.tmax;
+                                    rq.shContrib = c;
+                                }
+                            }
+                            float spdf;
+                            float3 wiL;
+                            if (lambert) {
+                                const float a0 = rnd(rng), a1 = rnd(rng);
+                                wiL = cosineHemisphere(a0, a1, spdf);
+                                origin = s.pos;
+                                dir = toWorld(fr, wiL);
+                                beta *= albedo;
+                            } else {
+                                const float a0 = rnd(rng), a1 = rnd(rng), a2 = rnd(rng);
+                                const float3 F = pbrSample(wiL, wo, spdf, pbr, a0, a1, a2);
+                                origin = s.pos;
+                                dir = toWorld(fr, wiL);
+                                if (isBlack(F)) {
+                                    stop = true;
+                                    doRoulette = false;
+                                } else {
+                                    beta *= clamp3(F / spdf, 0.0f, 1.0f);
+                                }
+                            }
+                            if (!stop) {
+                                rq.probe = true;
+                                rq.prBeta = beta;
+                                rq.prPdf = spdf;
+                            }
+                        }
+                    }
+                }
+            } else { /* rayPrimary.rmiss.glsl:40-106 */
+                bool sampledMedium = false;
+                if (flags & PF_INVOL) {
+                    const float vtend = fminf((float)(uint32_t)rc.sd.volumes[2], 10000.0f);
+                    sampledMedium = volumeEvent(sc, rc, rng, flags, origin, dir, beta, 0.001f, vtend, rq);
+                }
+                if (!sampledMedium) {
+                    stop = true;
+                    doRoulette = false;
+                    const float *bg = rc.sd.background;
+                    const bool first = !(flags & PF_SURFACE);
+                    float3 col = f3(0.0f), aov = f3(0.0f);
+                    if (bg[3] == 0.0f) {
+                        col = aov = f3(bg[0], bg[1], bg[2]);
+                    } else if (bg[3] == 1.0f) {
+                        col = aov = envFetch(sc, rayDir) * rc.sd.exposure[1];
+                    } else if (bg[3] == 2.0f) {
+                        aov = f3(bg[0], bg[1], bg[2]);
+                        col = first ? aov : envFetch(sc, rayDir);
+                    }
+                    if (first) {
+                        w.aovAlbedo[slot] = make_float4(aov.x, aov.y, aov.z, 0.0f);
+                        w.aovNormal[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    }
+                    radiance += col * beta;
+                }
+            }
+            if (doRoulette && !stop) stop = roulette(rng, bounce, beta);
+            /* requests that can only return black are dropped (result-identical) */
+            if (rq.probe && !sc.anyEmissive) rq.probe = false;
+            w.orgRng[slot] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng));
+            w.dirFlags[slot] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(flags));
+            w.beta[slot] = make_float4(beta.x, beta.y, beta.z, 0.0f);
+            w.radiance[slot] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+            if (rq.shadow) {
+                w.shOrgTmax[slot] = make_float4(rq.shOrigin.x, rq.shOrigin.y, rq.shOrigin.z, rq.shTmax);
+                w.shDirVol[slot] = make_float4(rq.shDir.x, rq.shDir.y, rq.shDir.z, __uint_as_float(flags));
+                w.shContrib[slot] = make_float4(rq.shContrib.x, rq.shContrib.y, rq.shContrib.z, 0.0f);
+            }
+            if (rq.probe) w.prBetaPdf[slot] = make_float4(rq.prBeta.x, rq.prBeta.y, rq.prBeta.z, rq.prPdf);
+            alive = !stop && !lastBounce;
+        }
+        queuePush(qNext, cntNext, alive, slot);
+        queuePush(w.qShadow, cntShadow, rq.shadow, slot);
+        queuePush(w.qProbe, cntProbe, rq.probe, slot);
+    }
+}
+
+/* ------------------------------------------------------------------ k_shadow */
+/* lightSampling.glsl:108-144 with nearest-first candidate order (trap T1) */
+__global__ void __launch_bounds__(TRV_BLOCK) k_shadow(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce) {
+    __shared__ int32_t stack[24 * TRV_BLOCK];
+    const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_SHADOW];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounded = (count + 31u) & ~31u;
+    const float zfarTrunc = (float)(uint32_t)rc.sd.volumes[2];
+    uint32_t hops = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+        if (i < count) {
+            const uint32_t slot = w.qShadow[i];
+            const float4 o4 = w.shOrgTmax[slot], d4 = w.shDirVol[slot];
+            float3 origin = f3(o4);
+            const float3 dir = f3(d4);
+            uint32_t vol = __float_as_uint(d4.w);
+            const float tmin = 0.0001f;
+            float distanceT = o4.w - tmin;
+            float3 thr = f3(1.0f);
+            bool shadowed = false;
+            if (!sc.anyTransparent) {
+                /* every surface is opaque: any hit shadows; otherwise raySecondary.rmiss */
+                trv::Ray ray{origin, dir, tmin, distanceT};
+                hops++;
+                shadowed = trv::occluded(sc, ray, stack + threadIdx.x);
+                if (!shadowed && (vol & PF_INVOL)) {
+                    thr = transmittance(sc, vol >> PF_VOL_SHIFT, tmin, fminf(zfarTrunc, distanceT));
+                    shadowed = !(max3(thr) > PT_EPSILON);
+                }
+            } else {
+                bool stop = false;
+                for (uint32_t d = 0; d < rc.depth && !stop; d++) {
+                    float vtmin = tmin;
+                    trv::Ray ray{origin, dir, tmin, distanceT};
+                    hops++;
+                    float t0 = tmin;
+                    uint32_t id0 = 0xffffffffu;
+                    bool ended = false;
+                    while (!ended) {
+                        trv::HitRec h = trv::nextHit(sc, ray, t0, id0, stack + threadIdx.x);
+                        if (h.pos < 0) break;
+                        Surf s;
+                        loadSurf(sc, h.pos, h.u, h.v, false, s);
+                        const ptc_material *mat = s.mat;
+                        if (!(__ldg(&mat->metallic_roughness_ao[3]) >= 0.99f)) { /* raySecondary.rahit.glsl:42-47 */
+                            stop = shadowed = ended = true;
+                            break;
+                        }
+                        const float alpha = __ldg(&mat->albedo[3]) *
+                                            texFetch(sc, __ldg(&mat->tex2[3]), s.uv.x * __ldg(&mat->uv_tiling[0]), s.uv.y * __ldg(&mat->uv_tiling[1])).x;
+                        thr = thr * (1.0f - alpha);
+                        if (s.inst->volFront != s.inst->volBack) { /* accept: raySecondary.rchit.glsl:32-78 */
+                            const bool flipped = dot(s.n, dir) > 0.0f;
+                            if (vol & PF_INVOL) {
+                                thr = thr * transmittance(sc, vol >> PF_VOL_SHIFT, vtmin, h.t);
+                                if (max3(thr) < PT_EPSILON) {
+                                    stop = shadowed = ended = true;
+                                    break;
+                                }
+                            }
+                            vtmin = h.t;
+                            volumeChange(s.inst, flipped, vol);
+                            origin = s.pos;
+                            ended = true;
+                            break;
+                        }
+                        if (max3(thr) > PT_EPSILON) { /* ignoreIntersectionEXT */
+                            shadowed = false;
+                            t0 = h.t;
+                            id0 = h.worldId;
+                            continue;
+                        }
+                        stop = shadowed = ended = true;
+                    }
+                    if (!ended) { /* raySecondary.rmiss.glsl:17-44 */
+                        stop = true;
+                        shadowed = false;
+                        if (vol & PF_INVOL) {
+                            thr = thr * transmittance(sc, vol >> PF_VOL_SHIFT, vtmin, fminf(zfarTrunc, distanceT));
+                            shadowed = !(max3(thr) > PT_EPSILON);
+                        }
+                    }
+                    distanceT -= vtmin;
+                }
+            }
+            if (!shadowed) {
+                const float3 c = f3(w.shContrib[slot]) * thr;
+                float4 r = w.radiance[slot];
+                r.x += c.x;
+                r.y += c.y;
+                r.z += c.z;
+                w.radiance[slot] = r;
+            }
+        }
+    }
+    statAdd(&w.stats[ST_SHADOW_HOPS], hops);
+}
+
+/* ------------------------------------------------------------------ k_probe */
+/* next_event_estimation.glsl:1-33 + rayNEE.* with nearest-first candidate order (trap T1) */
+__global__ void __launch_bounds__(TRV_BLOCK) k_probe(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce) {
+    __shared__ int32_t stack[24 * TRV_BLOCK];
+    const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_PROBE];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t rounded = (count + 31u) & ~31u;
+    const float tmin = 0.0001f, tmax = rc.sd.volumes[2];
+    uint32_t hops = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
+        if (i < count) {
+            const uint32_t slot = w.qProbe[i];
+            const float4 o4 = w.orgRng[slot], d4 = w.dirFlags[slot], bp = w.prBetaPdf[slot];
+            float3 origin = f3(o4);
+            const float3 dir = f3(d4);
+            uint32_t vol = __float_as_uint(d4.w);
+            float3 thr = f3(1.0f), emissive = f3(0.0f);
+            float pdf = 0.0f;
+            bool stop = false;
+            for (uint32_t d = 0; d < rc.depth && !stop; d++) {
+                float vtmin = tmin;
+                trv::Ray ray{origin, dir, tmin, tmax};
+                hops++;
+                float t0 = tmin;
+                uint32_t id0 = 0xffffffffu;
+                bool ended = false;
+                while (!ended) {
+                    trv::HitRec h = trv::nextHit(sc, ray, t0, id0, stack + threadIdx.x);
+                    if (h.pos < 0) break;
+                    Surf s;
+                    loadSurf(sc, h.pos, h.u, h.v, false, s);
+                    const ptc_material *mat = s.mat;
+                    const float tu = s.uv.x * __ldg(&mat->uv_tiling[0]), tv = s.uv.y * __ldg(&mat->uv_tiling[1]);
+                    const float3 em = ld3(mat->emissive) * __ldg(&mat->emissive[3]) * f3(texFetch(sc, __ldg(&mat->tex2[0]), tu, tv));
+                    const bool isTransparent = __ldg(&mat->metallic_roughness_ao[3]) >= 0.99f;
+                    if (isBlackEps(em, 0.05f)) { /* rayNEE.rahit.glsl:44-71 */
+                        if (!isTransparent) {
+                            stop = ended = true;
+                            thr = f3(0.0f);
+                            emissive = f3(0.0f);
+                            break;
+                        }
+                        const float alpha = __ldg(&mat->albedo[3]) * texFetch(sc, __ldg(&mat->tex2[3]), tu, tv).x;
+                        thr = thr * (1.0f - alpha);
+                        if (s.inst->volFront != s.inst->volBack) { /* accept: rayNEE.rchit.glsl:33-82 */
+                            const bool flipped = dot(s.n, dir) > 0.0f;
+                            if (vol & PF_INVOL) {
+                                thr = thr * transmittance(sc, vol >> PF_VOL_SHIFT, vtmin, h.t);
+                                if (max3(thr) < PT_EPSILON) {
+                                    stop = ended = true;
+                                    thr = f3(0.0f);
+                                    emissive = f3(0.0f);
+                                    break;
+                                }
+                            }
+                            vtmin = h.t;
+                            volumeChange(s.inst, flipped, vol);
+                            origin = s.pos;
+                            ended = true;
+                            break;
+                        }
+                        t0 = h.t; /* ignoreIntersectionEXT */
+                        id0 = h.worldId;
+                        continue;
+                    }
+                    /* emissive surface, rayNEE.rahit.glsl:73-131 */
+                    stop = ended = true;
+                    if (vol & PF_INVOL) {
+                        thr = thr * transmittance(sc, vol >> PF_VOL_SHIFT, vtmin, h.t);
+                        if (max3(thr) < PT_EPSILON) {
+                            thr = f3(0.0f);
+                            emissive = f3(0.0f);
+                            break;
+                        }
+                    }
+                    if (dot(s.n, dir) > 0.0f) { /* back face */
+                        emissive = f3(0.0f);
+                        thr = f3(0.0f);
+                        break;
+                    }
+                    emissive = em;
+                    const float3 w0 = mulPoint(s.inst->m, s.p0), w1 = mulPoint(s.inst->m, s.p1), w2 = mulPoint(s.inst->m, s.p2);
+                    const float area = 0.5f * length(cross(w1 - w0, w2 - w0));
+                    const float pointPdf = (1.0f / (float)s.inst->numTriangles) * (1.0f / area);
+                    const float dp = dot(-dir, s.n);
+                    if (dp > 0.0f) {
+                        /* rayNEE.rahit.glsl:122 measures from gl_ObjectRayOriginEXT (trap T6) unless the flag asks otherwise */
+                        const float3 ro = (rc.flags & PTC_FLAG_WORLD_ORIGIN_PROBE_PDF) ? origin : mulPoint(s.inst->w2o, origin);
+                        const float dd = length(ro - s.pos);
+                        pdf = pointPdf * (dd * dd) / dp * (1.0f / (float)rc.totalLights);
+                    } else {
+                        pdf = 0.0f;
+                        emissive = f3(0.0f);
+                    }
+                }
+                if (!ended) { /* rayNEE.rmiss.glsl:12-19 */
+                    stop = true;
+                    emissive = f3(0.0f);
+                    pdf = 0.0f;
+                }
+            }
+            if (!isBlack(emissive)) {
+                const float wgt = powerHeuristic(bp.w, pdf);
+                const float3 c = thr * emissive * f3(bp) * wgt;
+                float4 r = w.radiance[slot];
+                r.x += c.x;
+                r.y += c.y;
+                r.z += c.z;
+                w.radiance[slot] = r;
+            }
+        }
+    }
+    statAdd(&w.stats[ST_PROBE_HOPS], hops);
+}
+
+/* ------------------------------------------------------------------ k_accumulate (raygen.rgen.glsl:126-144) */
+__global__ void __launch_bounds__(256) k_accumulate(Wave w, const __grid_constant__ RenderConst rc, uint32_t nSamples, float4 *__restrict__ accR,
+                                                    float4 *__restrict__ accA, float4 *__restrict__ accN) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= rc.nPixLocal) return;
+    const float total = (float)rc.totalSamples;
+    float3 cr = f3(0.0f), ca = f3(0.0f), cn = f3(0.0f);
+    for (uint32_t s = 0; s < nSamples; s++) {
+        const size_t slot = (size_t)s * rc.nPixLocal + p;
+        cr += f3(w.radiance[slot]) / total;
+        ca += f3(w.aovAlbedo[slot]) / total;
+        cn += f3(w.aovNormal[slot]) / total;
+    }
+    const uint32_t pixel = rc.pixmap ? rc.pixmap[p] : p;
+    float4 r = accR[pixel], a = accA[pixel], n = accN[pixel];
+    accR[pixel] = make_float4(r.x + cr.x, r.y + cr.y, r.z + cr.z, 1.0f);
+    accA[pixel] = make_float4(a.x + ca.x, a.y + ca.y, a.z + ca.z, 1.0f);
+    accN[pixel] = make_float4(n.x + cn.x, n.y + cn.y, n.z + cn.z, 1.0f);
+}
+
+/* sums the per-bounce queue counters into the statistics block */
+__global__ void k_collect_stats(Wave w, uint32_t depth) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long seg = 0, sh = 0, pr = 0;
+    for (uint32_t d = 0; d < depth; d++) {
+        seg += w.counters[d * CNT_STRIDE + CNT_ACTIVE];
+        sh += w.counters[d * CNT_STRIDE + CNT_SHADOW];
+        pr += w.counters[d * CNT_STRIDE + CNT_PROBE];
+    }
+    w.stats[ST_SEGMENTS] += seg;
+    w.stats[ST_SHADOW_RAYS] += sh;
+    w.stats[ST_PROBE_RAYS] += pr;
+}
+
+/* ------------------------------------------------------------------ parity-hook kernels */
+__global__ void __launch_bounds__(TRV_BLOCK) k_trace_closest(const __grid_constant__ DScene sc, const float *__restrict__ rays, int n, int *inst, int *prim,
+                                                             float *t, float *u, float *v) {
+    __shared__ int32_t stack[24 * TRV_BLOCK];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *r = rays + (size_t)i * 8;
+    trv::Ray ray{f3(r[0], r[1], r[2]), f3(r[4], r[5], r[6]), r[3], r[7]};
+    trv::HitRec h = trv::closestHit(sc, ray, stack + threadIdx.x);
+    if (h.pos >= 0) {
+        inst[i] = (int)__float_as_uint(sc.tris[3 * (size_t)h.pos + 0].w);
+        prim[i] = (int)__float_as_uint(sc.tris[3 * (size_t)h.pos + 1].w);
+        t[i] = h.t;
+        u[i] = h.u;
+        v[i] = h.v;
+    } else {
+        inst[i] = -1;
+        prim[i] = -1;
+        t[i] = r[7];
+        u[i] = 0.0f;
+        v[i] = 0.0f;
+    }
+}
+
+__global__ void k_bsdf_eval(int n, const float *params, const float *wi, const float *wo, float *outF, float *outPdf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Pbr p{f3(params[i * 5], params[i * 5 + 1], params[i * 5 + 2]), params[i * 5 + 3], params[i * 5 + 4]};
+    float3 a = f3(wi[i * 3], wi[i * 3 + 1], wi[i * 3 + 2]), b = f3(wo[i * 3], wo[i * 3 + 1], wo[i * 3 + 2]);
+    float3 F = pbrEval(p, a, b);
+    outF[i * 3] = F.x;
+    outF[i * 3 + 1] = F.y;
+    outF[i * 3 + 2] = F.z;
+    outPdf[i] = pbrPdf(a, b, p);
+}
+__global__ void k_bsdf_sample(int n, const float *params, const float *wo, const float *u, float *outWi, float *outF, float *outPdf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Pbr p{f3(params[i * 5], params[i * 5 + 1], params[i * 5 + 2]), params[i * 5 + 3], params[i * 5 + 4]};
+    float3 b = f3(wo[i * 3], wo[i * 3 + 1], wo[i * 3 + 2]), wi;
+    float pdf;
+    float3 F = pbrSample(wi, b, pdf, p, u[i * 3], u[i * 3 + 1], u[i * 3 + 2]);
+    outWi[i * 3] = wi.x;
+    outWi[i * 3 + 1] = wi.y;
+    outWi[i * 3 + 2] = wi.z;
+    outF[i * 3] = F.x;
+    outF[i * 3 + 1] = F.y;
+    outF[i * 3 + 2] = F.z;
+    outPdf[i] = pdf;
+}
+__global__ void k_env_lookup(const __grid_constant__ DScene sc, int n, const float *dirs, float *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float3 c = envFetch(sc, f3(dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2]));
+    out[i * 3] = c.x;
+    out[i * 3 + 1] = c.y;
+    out[i * 3 + 2] = c.z;
+}
+
+/* ------------------------------------------------------------------ equirect -> cubemap (skyboxCubemapWrite.frag.glsl:12-15) */
+__global__ void k_equirect_to_cube(cudaTextureObject_t equirect, uint32_t N, float4 *__restrict__ faces) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
+    if (i >= N || j >= N) return;
+    const float sc = 2.0f * ((float)i + 0.5f) / (float)N - 1.0f, tc = 2.0f * ((float)j + 0.5f) / (float)N - 1.0f;
+    float3 d;
+    switch (f) { /* inverse of the cubemap face selection rules */
+        case 0: d = f3(1.0f, -tc, -sc); break;
+        case 1: d = f3(-1.0f, -tc, sc); break;
+        case 2: d = f3(sc, 1.0f, tc); break;
+        case 3: d = f3(sc, -1.0f, -tc); break;
+        case 4: d = f3(sc, -tc, 1.0f); break;
+        default: d = f3(-sc, -tc, -1.0f); break;
+    }
+    d = normalize(d);
+    /* include/environmentMap.glsl:1-10 */
+    float ux = atan2f(d.z, d.x) * 0.1591f + 0.5f + 0.25f;
+    ux = ux - floorf(ux);
+    const float uy = asinf(clampf(d.y, -1.0f, 1.0f)) * 0.3183f + 0.5f;
+    faces[((size_t)f * N + j) * N + i] = tex2D<float4>(equirect, ux, uy);
+}
+
+}  // namespace wf
