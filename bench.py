@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200 path tracer.
+
+Metric (BASELINE.json): Mpath-segments/s (and s/frame) of the offline path-traced render
+  workload C2: procedural Sponza-class atrium (~300 k triangles, 24 textured PBR materials, HDR
+  environment), 1920x1080, batch size 16, depth 9; a frame is 1024 spp = 64 batches.
+One "step" = one batch (16 samples per pixel over the whole image) of that render.
+
+  python bench.py --gpus N --steps K --warmup W            # the CUDA product
+  python bench.py --impl reference ...                      # the reference estimator on the host cores (CPU oracle)
+
+N > 1: one process per GPU under torchrun; the scene is replicated, batches are dealt round-robin to
+the ranks (sample split, weak scaling: K batches per rank) and the three accumulation buffers are summed
+onto rank 0 with one NCCL reduce inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME_SPP = 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--scene", default="Atrium")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--depth", type=int, default=0)
+    ap.add_argument("--texsize", type=int, default=1024)
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-spp", type=int, default=1, help="samples per pixel of one CPU-baseline step")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes_per_ray(n_tris):
+    """k_extend: ideal root-to-leaf descent of the binary LBVH."""
+    import math
+    depth = max(1, math.ceil(math.log2(max(n_tris, 2))))
+    state = 4 + 16 + 16 + 16  # queue id, origin+rng, direction+flags read; hit record written
+    return state + depth * 64 + 48, depth
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def build_engine(args, backend):
+    from vviewer_b200 import capi
+    eng = capi.HostEngine(backend_lib=backend)
+    eng.build_scene(args.scene, texture_size=args.texsize, scale=args.scale)
+    eng.set_render_info(width=args.width, height=args.height, batch_size=args.batch, depth=args.depth)
+    return eng
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference estimator (CPU oracle restating the GLSL shaders) on the host cores.
+    The reference's own binary cannot run here (Vulkan RT pipeline, no lavapipe: BASELINE.md §2)."""
+    if rank != 0:
+        return
+    from vviewer_b200 import capi
+    eng = build_engine(args, capi.ORACLE_LIB)
+    ri = eng.render_info()
+    ctx = capi.Context(capi.load_oracle())
+    ctx.upload_scene(eng.scene_desc())
+    ctx.build_accel()
+    rp = eng.render_params()
+    spp = max(1, args.cpu_spp)
+    rp.batch_size = spp
+    seg = 0
+    ms = 0.0
+    for i in range(args.warmup + args.steps):
+        rp.samples = spp
+        ctx.render(rp, want_aovs=False)
+        st = ctx.stats()
+        if i >= args.warmup:
+            seg += st["segments"]
+            ms += st["render_ms"]
+    cores = os.cpu_count()
+    value = seg / ms / 1e3 if ms > 0 else 0.0
+    sample = "%dx%d x %d spp per step (a full step is %d spp)" % (ri["width"], ri["height"], spp, ri["batch_size"])
+    line = {"impl": "reference", "metric": "Mpath-segments/s", "value": value, "unit": "Msegments/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2 %s %dx%d batch %d depth %d" % (args.scene, ri["width"], ri["height"], ri["batch_size"], ri["depth"]),
+                       "triangles": ctx.stats()["n_triangles"]},
+            "cpu_baseline": {"value": value, "unit": "Msegments/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "Msegments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def run_cuda(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    from vviewer_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cuda = capi.load_cuda()
+    eng = build_engine(args, capi.CUDA_LIB)
+    if not eng.backend_ok():
+        raise RuntimeError("CUDA backend failed: " + eng.last_error())
+    ri = eng.render_info()
+    W, H, B, D = ri["width"], ri["height"], ri["batch_size"], ri["depth"]
+    desc = eng.scene_desc()
+    ctx = capi.Context(cuda, device=local_rank)
+    ctx.upload_scene(desc)
+    ctx.build_accel()
+    build_stats = ctx.stats()
+
+    # device-resident accumulation targets (torch owns the memory so NCCL can reduce them)
+    acc = torch.zeros((3, H, W, 4), dtype=torch.float32, device="cuda")
+    ptrs = [acc[i].data_ptr() for i in range(3)]
+
+    def render(n_batches, flags=0):
+        rp = eng.render_params()
+        rp.samples = n_batches * B * world
+        rp.batch_size = B
+        rp.flags = flags
+        if world > 1:
+            rp.split_mode, rp.rank, rp.world = capi.PTC_SPLIT_SAMPLE, rank, world
+        ctx.render_device(rp, *ptrs)
+        return ctx.stats()
+
+    def sync():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    render(max(args.warmup, 3))
+    if dist is not None:
+        dist.reduce(acc, dst=0)
+    sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    t0 = time.perf_counter()
+    st = render(args.steps)             # K batches on this rank, device-timed with CUDA events on the library's stream
+    ev0.record()
+    if dist is not None:
+        dist.reduce(acc, dst=0)         # sum of the accumulation buffers over NVLink (the only exchange of the path)
+    ev1.record()
+    sync()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = st["render_ms"] + (ev0.elapsed_time(ev1) if dist is not None else 0.0)
+    clocks = sampler.stop() if rank == 0 else None
+
+    t = torch.tensor([dev_ms, float(st["segments"]), float(st["kernel_launches"]), wall_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms, wall_ms = float(tmax[0]), float(tmax[3])
+        segments, launches = float(tsum[1]), int(tsum[2])
+    else:
+        segments, launches = float(st["segments"]), int(st["kernel_launches"])
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    value = segments / dev_ms / 1e3  # Msegments/s, whole job
+    # ---- roofline of the dominant kernel (k_extend), timed live with CUDA events on the launching stream
+    stp = render(2, flags=capi.PTC_FLAG_TIME_KERNELS)
+    bytes_per_ray, bvh_depth = algorithmic_bytes_per_ray(build_stats["n_triangles"])
+    peak, peak_kind = measured_peak()
+    rays = stp["segments"]
+    avg_launch_ms = stp["trace_ms"] / max(stp["trace_launches"], 1)
+    achieved = rays * bytes_per_ray / (stp["trace_ms"] * 1e-3) / 1e9 if stp["trace_ms"] > 0 else 0.0
+    share = {"extend": stp["trace_ms"], "shade": stp["shade_ms"], "shadow_probe": stp["shadow_ms"]}
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("k_extend_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "bytes_per_ray": bytes_per_ray, "bvh_depth": bvh_depth,
+                "avg_launch_ms": avg_launch_ms, "kernel_ms_share": share}
+
+    # ---- end to end through the public API (RendererPathTracing::render via the C++ plugin): host scene in,
+    # host images out; includes flatten, H2D upload of the scene, BVH build, render and D2H of the 3 targets
+    e2e = None
+    if world == 1:
+        eng.set_render_info(samples=args.steps * B)
+        eng.render_to_memory()  # warm-up of the plugin path (allocations)
+        t0 = time.perf_counter()
+        eng.render_to_memory()
+        e2e_s = time.perf_counter() - t0
+        est = eng.stats()
+        d = desc.contents
+        h2d = d.n_vertices * 68 + d.n_indices * 4 + d.n_instances * 128 + d.n_materials * 128 + d.env.width * d.env.height * 16
+        h2d += sum(d.textures[i].width * d.textures[i].height * d.textures[i].channels for i in range(d.n_textures))
+        d2h = 3 * W * H * 16
+        e2e = {"value": est["segments"] / e2e_s / 1e6, "unit": "Msegments/s", "h2d_bytes_per_step": int(h2d / args.steps),
+               "d2h_bytes_per_step": int(d2h / args.steps), "seconds": e2e_s, "note": "one render() call of %d batches: scene upload + LBVH build + render + readback" % args.steps}
+    else:
+        e2e = {"value": segments / wall_ms / 1e3, "unit": "Msegments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "multi-GPU: wall clock of render_device + NCCL reduce, scene resident"}
+
+    # ---- CPU baseline: the oracle on the host cores, bounded sample of the same workload
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        octx = capi.Context(capi.load_oracle())
+        octx.upload_scene(desc)
+        octx.build_accel()
+        rp = eng.render_params()
+        rp.samples = rp.batch_size = max(1, args.cpu_spp)
+        octx.render(rp, want_aovs=False)
+        ost = octx.stats()
+        cpu = {"value": ost["segments"] / ost["render_ms"] / 1e3, "unit": "Msegments/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "%dx%d x %d spp (1/%d of a step), %.1f s" % (W, H, rp.samples, B // max(rp.samples, 1), ost["render_ms"] / 1e3)}
+        octx.close()
+
+    ms_per_step = dev_ms / args.steps
+    line = {"metric": "Mpath-segments/s", "value": value, "unit": "Msegments/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2 %s %dx%d batch %d depth %d (frame = %d spp)" % (args.scene, W, H, B, D, FRAME_SPP),
+                       "triangles": build_stats["n_triangles"], "l2": "inputs larger than L2 (%.1f GB of path state streamed per step)" % (W * H * B * 192 / 1e9),
+                       "split": "sample" if world > 1 else "none"},
+            "s_per_frame": ms_per_step * (FRAME_SPP / B) / world / 1e3, "segments_per_path": segments / (args.steps * world * W * H * B),
+            "build_ms": build_stats["build_ms"], "wall_ms": wall_ms, "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
+            "cpu_baseline": cpu, "e2e": e2e}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_cuda(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

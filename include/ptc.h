@@ -168,6 +168,7 @@ typedef struct ptc_render_params {
 } ptc_render_params;
 
 #define PTC_FLAG_WORLD_ORIGIN_PROBE_PDF 1u /* use the world-space ray origin in the probe-ray pdf instead of reproducing rayNEE.rahit.glsl:122 */
+#define PTC_FLAG_TIME_KERNELS 2u          /* bracket every kernel class with CUDA events (fills ptc_stats.*_ms; serialises launches) */
 
 typedef struct ptc_stats {
     uint64_t segments;    /* iterations of the raygen depth loop (raygen.rgen.glsl:100-124) */

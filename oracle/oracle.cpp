@@ -100,6 +100,7 @@ struct ptc_ctx {
     QueryBVH bvh;
     LBVH lbvh;
     bool accelBuilt = false;
+    bool anyEmissive = false; /* some instanced material can pass the probe's emissive test (|e| > 0.05) */
     /* render */
     std::atomic<float> progress{0.0f};
     ptc_stats stats{};
@@ -485,6 +486,7 @@ struct Tracer {
     /* pt/next_event_estimation.glsl:1-33 + rayNEE.rahit/.rchit/.rmiss */
     void nextEventEstimation(Payload &P, float sampleDirectionPDF) {
         /* result-identical shortcut: without an emissive instance the probe can only return black */
+        if (!c->anyEmissive) return;
         st.probe_rays++;
         const float tmin = 0.0001f;
         const float tmax = zfar;
@@ -895,6 +897,12 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *s) {
         I.worldToObject = inverseAffine(I.model);
         if (I.d.mesh_index >= s->n_meshes) return fail(c, "instance mesh index out of range");
         if (I.d.material_index >= s->n_materials) return fail(c, "instance material index out of range");
+    }
+    c->anyEmissive = false;
+    for (uint32_t i = 0; i < s->n_instances; i++) {
+        const ptc_material &m = c->materials[c->instances[i].d.material_index];
+        for (int k = 0; k < 3; k++)
+            if (std::fabs(m.emissive[3] * m.emissive[k]) > 0.05f) c->anyEmissive = true;
     }
     c->textures.resize(s->n_textures);
     for (uint32_t t = 0; t < s->n_textures; t++) {

@@ -1,0 +1,79 @@
+/*
+ * offlinerender — headless driver of the path tracer, same shape as the reference's
+ * src/bin/offlinerender/main.cpp:13-25 (create engine, initResources, create a scene, render) with the
+ * command line the reference lacks (SURVEY.md §5 "Config / flags").
+ *
+ *   offlinerender --scene Atrium [--width W --height H --spp N --batch B --depth D] [--out name]
+ *                 [--png] [--exposure E] [--all-files] [--texsize T] [--scale S] [--camera 0|1] [--list]
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../host/scenes.hpp"
+
+using namespace vengine;
+
+int main(int argc, char **argv) {
+    std::string scene = "Cornell", out, backend;
+    scenes::Options opt;
+    int width = 0, height = 0, spp = 0, batch = 0, depth = 0;
+    bool png = false, allFiles = false;
+    float exposure = 0.0f;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
+        if (a == "--scene") scene = next();
+        else if (a == "--width") width = std::atoi(next());
+        else if (a == "--height") height = std::atoi(next());
+        else if (a == "--spp") spp = std::atoi(next());
+        else if (a == "--batch") batch = std::atoi(next());
+        else if (a == "--depth") depth = std::atoi(next());
+        else if (a == "--out") out = next();
+        else if (a == "--png") png = true;
+        else if (a == "--exposure") exposure = (float)std::atof(next());
+        else if (a == "--all-files") allFiles = true;
+        else if (a == "--texsize") opt.textureSize = std::atoi(next());
+        else if (a == "--scale") opt.scale = (float)std::atof(next());
+        else if (a == "--camera") opt.camera = std::atoi(next());
+        else if (a == "--backend") backend = next(); /* any library exporting include/ptc.h; default = CUDA */
+        else if (a == "--list") {
+            for (auto &n : scenes::list()) std::printf("%s\n", n.c_str());
+            return 0;
+        } else {
+            std::fprintf(stderr, "unknown argument %s\n", a.c_str());
+            return 2;
+        }
+    }
+    Engine engine("offlinerender", backend);
+    engine.initResources();
+    auto &pt = engine.renderer().rendererPathTracing();
+    if (!pt.isRayTracingEnabled()) {
+        std::fprintf(stderr, "path tracing backend unavailable: %s\n", pt.lastError().c_str());
+        return 1;
+    }
+    if (!scenes::build(engine, scene, opt)) {
+        std::fprintf(stderr, "unknown scene '%s' (use --list)\n", scene.c_str());
+        return 2;
+    }
+    auto &ri = pt.renderInfo();
+    if (width > 0) ri.width = (uint32_t)width;
+    if (height > 0) ri.height = (uint32_t)height;
+    if (spp > 0) ri.samples = (uint32_t)spp;
+    if (batch > 0) ri.batchSize = (uint32_t)batch;
+    if (depth > 0) ri.depth = (uint32_t)depth;
+    if (!out.empty()) ri.filename = out;
+    if (png) ri.fileType = FileType::PNG;
+    ri.exposure = exposure;
+    if (allFiles) ri.writeAllFiles = true;
+    pt.render();
+    const ptc_stats &st = pt.lastStats();
+    std::printf("{\"backend\": \"%s\", \"scene\": \"%s\", \"width\": %u, \"height\": %u, \"spp\": %u, \"segments\": %llu, \"shadow_rays\": %llu, "
+                "\"probe_rays\": %llu, \"render_ms\": %.3f, \"build_ms\": %.3f, \"triangles\": %llu, \"Mseg_per_s\": %.2f}\n",
+                pt.backendName(), scene.c_str(), ri.width, ri.height, ri.samples, (unsigned long long)st.segments,
+                (unsigned long long)st.shadow_rays, (unsigned long long)st.probe_rays, st.render_ms, st.build_ms,
+                (unsigned long long)st.n_triangles, st.render_ms > 0 ? st.segments / st.render_ms / 1e3 : 0.0);
+    engine.releaseResources();
+    return 0;
+}

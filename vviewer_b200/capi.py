@@ -90,6 +90,7 @@ class ptc_stats(C.Structure):
 
 PTC_SPLIT_NONE, PTC_SPLIT_TILE, PTC_SPLIT_SAMPLE = 0, 1, 2
 PTC_FLAG_WORLD_ORIGIN_PROBE_PDF = 1
+PTC_FLAG_TIME_KERNELS = 2
 
 # every symbol include/ptc.h declares
 PTC_SYMBOLS = ["ptc_create", "ptc_destroy", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_build_accel", "ptc_render",

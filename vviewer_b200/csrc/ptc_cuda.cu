@@ -304,7 +304,7 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     const int gridShade = c->smCount * 8;
     uint64_t launches = 0, traceLaunches = 0;
     double traceMs = 0, shadeMs = 0, shadowMs = 0;
-    const bool timeKernels = std::getenv("PTC_TIME_KERNELS") != nullptr;
+    const bool timeKernels = (rp->flags & PTC_FLAG_TIME_KERNELS) != 0;
     auto timed = [&](double &acc, auto &&launch) {
         if (timeKernels) CUDA_TRY(cudaEventRecord(c->evA, s));
         launch();

@@ -622,7 +622,7 @@ static void atrium(Engine &e, const Options &opt, bool fog) {
     /* floor: bumpy tile grid */
     {
         MeshBuilder b("atriumFloorMesh");
-        b.surface(N(256), N(128), [&](float u, float v) {
+        b.surface(N(224), N(112), [&](float u, float v) {
             float x = -L + 2 * L * u, z = -Wd + 2 * Wd * v;
             float y = 0.02f * fbm(u * 4, v * 2, 11, 8) + 0.01f * std::sin(x * 6.0f) * std::sin(z * 6.0f);
             return vec3(x, y, z);
@@ -713,7 +713,7 @@ static void atrium(Engine &e, const Options &opt, bool fog) {
         for (int k = 0; k < nDrapes; k++) {
             MeshBuilder b("atriumDrapeMesh" + std::to_string(k));
             float x0 = -L + 6.0f + k * 7.0f;
-            b.surface(N(96), N(96), [&](float u, float v) {
+            b.surface(N(80), N(80), [&](float u, float v) {
                 float z = -3.5f + 7.0f * u;
                 float sag = 1.5f * (1.0f - std::pow(2 * u - 1, 2.0f));
                 float y = 2 * Hs - 0.5f - sag - 3.0f * v;
