@@ -1,0 +1,292 @@
+"""Parity tests proper: the CUDA product against the CPU oracle and against the reference's golden images.
+All of them call through the C-ABI (include/ptc.h) or through the C++ RendererPathTracing plugin.  Need a B200."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from imgmetrics import mean_lum_ratio, mse, p99_rel_err, rgbe_roundtrip
+from test_oracle_units import check_lbvh, look_down_params, make_quad_scene
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "tests", "golden", "reference_images")
+
+GOLDEN_SCENES = ["FurnacePBR", "FurnaceLambert", "EnvironmentMap", "EnvironmentMapPBR00", "EnvironmentMapPBR01", "EnvironmentMapPBR10",
+                 "EnvironmentMapPBR11", "EnvironmentMapLambert", "Volume0", "Volume1", "Volume2", "Volume3", "Volume4", "Volume5", "Volume6",
+                 "Volume7", "Volume8", "Volume9", "PointLight", "DirectionalLight", "MeshLight", "Transparency", "NormalMap", "Hierarchy",
+                 "DepthOfField", "SharedComponents"]
+
+
+@pytest.fixture(scope="module")
+def engine(capi):
+    eng = capi.HostEngine()  # default backend: the CUDA library
+    assert eng.backend_ok(), eng.last_error()
+    yield eng
+    eng.close()
+
+
+def both(capi, desc):
+    out = {}
+    for label, lib in (("cuda", capi.load_cuda()), ("oracle", capi.load_oracle())):
+        ctx = capi.Context(lib)
+        ctx.upload_scene(desc)
+        ctx.build_accel()
+        out[label] = ctx
+    return out["cuda"], out["oracle"]
+
+
+# ---------------------------------------------------------------- (1) LBVH build: bit-exact against the CPU reference build
+@pytest.mark.parametrize("scene,kw", [("Volume5", {}), ("Cornell", {}), ("MeshLight", {}), ("SharedComponents", {}), ("Hierarchy", {}),
+                                      ("Atrium", dict(texture_size=4, scale=0.3)), ("Atrium", dict(texture_size=4, scale=1.0))])
+def test_lbvh_bit_exact(capi, engine, scene, kw):
+    engine.build_scene(scene, **kw)
+    cu, orc = both(capi, engine.scene_desc())
+    a, b = cu.get_lbvh(), orc.get_lbvh()
+    assert a["n"] == b["n"] > 0
+    for k in ("morton", "order", "parent", "left", "right", "aabb"):
+        assert np.array_equal(a[k], b[k]), "LBVH field %s differs (%d entries)" % (k, int(np.sum(a[k] != b[k])))
+    if a["n"] < 50000:
+        check_lbvh(a)
+    cu.close()
+    orc.close()
+
+
+def test_lbvh_single_triangle_and_empty(capi):
+    d, keep = make_quad_scene(capi)
+    keep[2][0].tri_count = 1
+    keep[3][0].num_triangles = 1
+    cu, orc = both(capi, C.byref(d))
+    a, b = cu.get_lbvh(), orc.get_lbvh()
+    assert a["n"] == b["n"] == 1 and np.array_equal(a["aabb"], b["aabb"]) and np.array_equal(a["morton"], b["morton"])
+    rays = np.array([[-0.5, 2, 0.5, 1e-3, 0, -1, 0, 1e4], [0.9, 2, -0.9, 1e-3, 0, -1, 0, 1e4]], np.float32)
+    ra, rb = cu.trace_closest(rays), orc.trace_closest(rays)
+    assert np.array_equal(ra[0], rb[0]) and np.allclose(ra[2], rb[2])
+    cu.close()
+    orc.close()
+    e = capi.ptc_scene_desc()
+    cu, orc = both(capi, C.byref(e))
+    assert cu.get_lbvh()["n"] == 0
+    ra = cu.trace_closest(rays)
+    assert list(ra[0]) == [-1, -1]
+    ia, _, _ = cu.render(look_down_params(capi, bg=(0.25, 0.5, 0.75)))
+    ib, _, _ = orc.render(look_down_params(capi, bg=(0.25, 0.5, 0.75)))
+    assert np.allclose(ia, ib, atol=1e-6) and np.allclose(ia[..., :3], (0.25, 0.5, 0.75), atol=1e-6)
+    cu.close()
+    orc.close()
+
+
+# ---------------------------------------------------------------- (2) ray sets: ids identical, |dt| <= 1e-4 * max(1, t)
+def ray_set(rng, n, lo, hi, aim=None):
+    o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    if aim is None:
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+    else:
+        d = (rng.uniform(aim[0], aim[1], (n, 3)) - o).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return np.concatenate([o, np.full((n, 1), 1e-3, np.float32), d, np.full((n, 1), 1e4, np.float32)], axis=1)
+
+
+@pytest.mark.parametrize("scene,kw,box", [("EnvironmentMap", {}, 4.0), ("Hierarchy", {}, 12.0), ("SharedComponents", {}, 60.0),
+                                          ("Cornell", {}, 1.0), ("Atrium", dict(texture_size=4, scale=0.25), 8.0)])
+def test_ray_set_parity(capi, engine, scene, kw, box):
+    engine.build_scene(scene, **kw)
+    cu, orc = both(capi, engine.scene_desc())
+    rng = np.random.default_rng(11)
+    rays = np.concatenate([ray_set(rng, 30000, -box, box), ray_set(rng, 30000, -box, box, aim=(-box / 4, box / 4))])
+    ia, pa, ta, ua, va = cu.trace_closest(rays)
+    ib, pb, tb, ub, vb = orc.trace_closest(rays)
+    assert (ib >= 0).mean() > 0.2
+    same = (ia == ib) & (pa == pb)
+    # a differing id is only acceptable on a shared edge / coplanar overlap where both report the same t
+    bad = ~same
+    assert bad.mean() <= 2e-4, "id mismatches: %d" % int(bad.sum())
+    if bad.any():
+        assert np.all(np.abs(ta[bad] - tb[bad]) <= 1e-4 * np.maximum(1.0, tb[bad]))
+    hit = same & (ib >= 0)
+    assert np.all(np.abs(ta[hit] - tb[hit]) <= 1e-4 * np.maximum(1.0, tb[hit]))
+    assert np.all(np.abs(ua[hit] - ub[hit]) <= 1e-4) and np.all(np.abs(va[hit] - vb[hit]) <= 1e-4)
+    cu.close()
+    orc.close()
+
+
+# ---------------------------------------------------------------- (3) BSDF: 1e-5 relative on 1e5 random configurations
+def test_bsdf_parity(capi):
+    cu, orc = capi.Context(capi.load_cuda()), capi.Context(capi.load_oracle())
+    rng = np.random.default_rng(5)
+    n = 100000
+    def dirs():
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        d[:, 1] = np.abs(d[:, 1])
+        return d
+    wi, wo = dirs(), dirs()
+    wi[: n // 20, 1] *= -1  # some below the horizon
+    params = np.stack([rng.uniform(0, 1, n), rng.uniform(0, 1, n), rng.uniform(0, 1, n), rng.uniform(0, 1, n), rng.uniform(0.035, 1, n)],
+                      axis=1).astype(np.float32)
+    fa, pa = cu.bsdf_eval(params, wi, wo)
+    fb, pb = orc.bsdf_eval(params, wi, wo)
+    tol = 1e-5
+    assert np.all(np.abs(fa - fb) <= tol * np.maximum(np.abs(fb), 1e-3))
+    assert np.all(np.abs(pa - pb) <= tol * np.maximum(np.abs(pb), 1e-3))
+    u = rng.uniform(0, 1, (n, 3)).astype(np.float32)
+    wa, fa, pa = cu.bsdf_sample(params, wo, u)
+    wb, fb, pb = orc.bsdf_sample(params, wo, u)
+    # sampling goes through sincos / sqrt whose last-bit differences are amplified by the reflection: 1e-4
+    ok = pb >= 1e-6
+    assert np.all(np.abs(wa - wb)[ok] <= 2e-4)
+    assert np.all(np.abs(pa - pb)[ok] <= 2e-3 * np.maximum(np.abs(pb[ok]), 1e-3))
+    assert np.all((pa < 1e-6) == (pb < 1e-6)) or np.mean((pa < 1e-6) != (pb < 1e-6)) < 1e-4
+    cu.close()
+    orc.close()
+
+
+# ---------------------------------------------------------------- (4) environment: equirect -> cubemap kernel + cubemap lookup
+def test_env_lookup_parity(capi, engine):
+    engine.build_scene("EnvironmentMapLambert")
+    cu, orc = both(capi, engine.scene_desc())
+    rng = np.random.default_rng(9)
+    d = rng.normal(size=(50000, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    a, b = cu.env_lookup(d), orc.env_lookup(d)
+    # hardware bilinear weights have 8 fractional bits; the resampling itself went through the same equirect taps
+    err = np.abs(a - b).max(axis=1) / np.maximum(b.max(axis=1), 0.05)
+    assert np.percentile(err, 99) < 0.03 and np.median(err) < 2e-3
+    assert abs(a.mean() / b.mean() - 1) < 1e-3
+    cu.close()
+    orc.close()
+
+
+# ---------------------------------------------------------------- (5) renders: CUDA vs oracle at matched samples (same RNG streams)
+@pytest.mark.parametrize("scene", GOLDEN_SCENES + ["Denoise", "Cornell"])
+def test_render_matches_oracle(capi, engine, scene):
+    engine.build_scene(scene)
+    engine.set_render_info(width=128, height=128, samples=8, batch_size=4)
+    desc, rp = engine.scene_desc(), engine.render_params()
+    cu, orc = both(capi, desc)
+    ra, aa, na = cu.render(rp)
+    rb, ab, nb = orc.render(rp)
+    sa, sb = cu.stats(), orc.stats()
+    # both consume the same random streams, so only float rounding (and the rare path it flips) can differ
+    d = np.abs(ra[..., :3] - rb[..., :3]).max(axis=-1)
+    assert np.mean(d > 1e-3 * np.maximum(1.0, rb[..., :3].max(axis=-1))) < 0.01, "radiance differs in %.3f %% of pixels" % (100 * np.mean(d > 1e-3))
+    assert abs(ra[..., :3].mean() / max(rb[..., :3].mean(), 1e-9) - 1) < 2e-3
+    assert np.mean(np.abs(aa - ab).max(axis=-1) > 1e-3) < 0.01 and np.mean(np.abs(na - nb).max(axis=-1) > 1e-3) < 0.01
+    assert np.all(ra[..., 3] == 1.0)
+    assert abs(sa["segments"] - sb["segments"]) <= 1e-3 * sb["segments"]
+    assert abs(sa["probe_rays"] - sb["probe_rays"]) <= 1e-3 * max(sb["probe_rays"], 1000)
+    cu.close()
+    orc.close()
+
+
+# ---------------------------------------------------------------- (6) renders: CUDA vs the reference's golden images
+GOLDEN_LIMITS = {"mse": 2e-4, "lum": 0.01, "p99": 0.05}
+# low-variance scenes (delta or small lights) must do much better
+TIGHT = {"PointLight": 1e-5, "DirectionalLight": 1e-5, "FurnaceLambert": 5e-6, "SharedComponents": 1e-5}
+# scenes whose golden itself carries fireflies from the point light inside the medium: luminance and structure only
+NOISY_GOLDEN = {"Volume4": 4e-3, "Volume8": 2e-3, "Volume5": 1e-3, "Volume9": 1.5e-3}
+
+
+@pytest.mark.parametrize("scene", GOLDEN_SCENES)
+def test_render_matches_reference_golden(capi, engine, scene, tmp_path):
+    """Same recipe as the reference's TEST_F (RenderTests.cpp), rendered through RendererPathTracing::render() at 4x the golden's
+    samples, compared with assets/unittests/<scene>_ref.hdr after the same RGBE quantisation."""
+    engine.build_scene(scene)
+    ri = engine.render_info()
+    engine.set_render_info(samples=4 * ri["samples"])
+    out = str(tmp_path / (scene + "_test"))
+    engine.render(out)  # writes <out>.hdr like the reference
+    img = capi.read_hdr(out + ".hdr")
+    ref = capi.read_hdr(os.path.join(REF_DIR, scene + "_ref.hdr"))
+    m, lum, p99 = mse(img, ref), mean_lum_ratio(img, ref), p99_rel_err(img, ref)
+    limit = TIGHT.get(scene, NOISY_GOLDEN.get(scene, GOLDEN_LIMITS["mse"]))
+    assert m <= limit, "MSE %.3e > %.1e" % (m, limit)
+    assert abs(lum - 1) <= (0.02 if scene in NOISY_GOLDEN else GOLDEN_LIMITS["lum"]), "mean luminance ratio %.4f" % lum
+    if scene not in NOISY_GOLDEN:
+        assert p99 <= GOLDEN_LIMITS["p99"] * (2 if scene in ("Transparency", "NormalMap", "DepthOfField", "EnvironmentMap") else 1), "p99 rel err %.4f" % p99
+
+
+def test_denoise_aovs_match_reference(capi, engine, tmp_path):
+    """Denoise_ref_{radiance,albedo,normal}.hdr pin the AOV conventions (first-hit albedo, n*0.5+0.5, background albedo = env)."""
+    engine.build_scene("Denoise")
+    ri = engine.render_info()
+    engine.set_render_info(samples=4 * ri["samples"])
+    out = str(tmp_path / "Denoise_test")
+    engine.render(out)
+    for suffix, lim in (("_radiance", 2e-4), ("_albedo", 2e-4), ("_normal", 5e-5)):
+        img = capi.read_hdr(out + suffix + ".hdr")
+        ref = capi.read_hdr(os.path.join(REF_DIR, "Denoise_ref" + suffix + ".hdr"))
+        assert mse(img, ref) <= lim, (suffix, mse(img, ref))
+        assert abs(mean_lum_ratio(img, ref) - 1) <= 0.01
+
+
+# ---------------------------------------------------------------- (7) edge cases and partitions
+def test_samples_dropped_and_alpha(capi):
+    d, keep = make_quad_scene(capi)
+    cu = capi.Context(capi.load_cuda())
+    cu.upload_scene(C.byref(d))
+    cu.build_accel()
+    rad, alb, nrm = cu.render(look_down_params(capi, spp=70, batch=16))
+    assert cu.stats()["segments"] == 2 * 16 * 16 * 64  # trap T7
+    assert np.allclose(rad[..., :3], 0.5, atol=2e-6) and np.all(rad[..., 3] == 1.0)
+    assert np.allclose(alb[..., :3], 0.5, atol=1e-6)
+    cu.close()
+
+
+@pytest.mark.parametrize("mode", ["tile", "sample"])
+def test_partition_sums_to_full_render(capi, engine, mode):
+    from vviewer_b200 import parallel
+    engine.build_scene("MeshLight")
+    engine.set_render_info(width=160, height=96, samples=16, batch_size=4)
+    cu = capi.Context(capi.load_cuda())
+    cu.upload_scene(engine.scene_desc())
+    cu.build_accel()
+    full = np.stack(cu.render(engine.render_params()))
+    seg_full = cu.stats()["segments"]
+    world = 3
+    total = np.zeros_like(full)
+    seg = 0
+    for r in range(world):
+        rp = parallel.partition(engine.render_params(), r, world, mode, tile_size=32)
+        part = np.stack(cu.render(rp))
+        total[..., :3] += part[..., :3]
+        seg += cu.stats()["segments"]
+    assert seg == seg_full
+    assert np.allclose(total[..., :3], full[..., :3], rtol=1e-5, atol=1e-6)
+    cu.close()
+
+
+def test_errors_are_reported_not_thrown(capi):
+    cu = capi.Context(capi.load_cuda())
+    with pytest.raises(RuntimeError, match="ptc_upload_scene|ptc_build_accel"):
+        cu.build_accel()
+    d, keep = make_quad_scene(capi)
+    keep[3][0].material_index = 7
+    with pytest.raises(RuntimeError, match="material index"):
+        cu.upload_scene(C.byref(d))
+    cu.close()
+
+
+# ---------------------------------------------------------------- (8) BASELINE-size properties (1920x1080 atrium)
+def test_full_size_determinism_and_linearity(capi, engine):
+    """At the benchmark's size the oracle is too slow, so check size-independent properties: two runs are bit-identical,
+    and radiance is linear in the environment intensity (same random streams -> exactly 2x up to rounding)."""
+    engine.build_scene("Atrium", texture_size=64)
+    engine.set_render_info(samples=4, batch_size=4)
+    cu = capi.Context(capi.load_cuda())
+    cu.upload_scene(engine.scene_desc())
+    cu.build_accel()
+    rp = engine.render_params()
+    assert (rp.width, rp.height) == (1920, 1080)
+    a = cu.render(rp, want_aovs=False)
+    sa = cu.stats()
+    b = cu.render(rp, want_aovs=False)
+    assert np.array_equal(a, b) and sa["segments"] == cu.stats()["segments"]
+    rp.scene.exposure[1] = 2.0
+    c = cu.render(rp, want_aovs=False)
+    assert np.allclose(c[..., :3], 2.0 * a[..., :3], rtol=1e-5, atol=1e-7)
+    assert 3.0 < sa["segments"] / (1920 * 1080 * 4) < 5.0
+    cu.close()

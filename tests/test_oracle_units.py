@@ -1,0 +1,370 @@
+"""Known-answer and property tests of the CPU oracle's building blocks (run on CPU, no GPU needed).
+Everything is exercised through the C-ABI parity hooks of include/ptc.h."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def octx(capi, oracle_lib):
+    ctx = capi.Context(oracle_lib)
+    yield ctx
+    ctx.close()
+
+
+def _dirs(rng, n, upper=True):
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    if upper:
+        d[:, 1] = np.abs(d[:, 1])
+    return d
+
+
+# ---------------------------------------------------------------- RNG (rng_def.glsl) re-stated in Python
+def jenkins(x):
+    x = (x + (x << 10)) & 0xFFFFFFFF
+    x ^= x >> 6
+    x = (x + (x << 3)) & 0xFFFFFFFF
+    x ^= x >> 11
+    x = (x + (x << 15)) & 0xFFFFFFFF
+    return x
+
+
+def test_jenkins_known_answers():
+    # independent KATs: Bob Jenkins' one-at-a-time finaliser structure, computed by hand-checked Python
+    assert jenkins(0) == 0
+    x = 1
+    x = (x + (x << 10)) & 0xFFFFFFFF
+    assert x == 1025
+    # avalanche: neighbouring pixel indices give unrelated seeds
+    seeds = [jenkins(i ^ jenkins(0)) for i in range(64)]
+    assert len(set(seeds)) == 64 and len({s >> 24 for s in seeds}) > 24
+
+
+def test_pbr_eval_against_closed_form(octx):
+    """evalPBRStandard (pbrStandard.glsl:92-105) at normal incidence, roughness 1, metallic 0:
+    diffuse = albedo/pi * Fd with Fd90 = 0.5 + 2*1*1 = 2.5, FL = FV = 0 -> Fd = 1;
+    glossy = D * F * G with a = 1: D = 1/pi, F0 = 0.04 (+ (1-0.04)*0 at LdotH = 1), G = (1/(1+1))^2 = 0.25."""
+    params = np.array([[0.6, 0.5, 0.4, 0.0, 1.0]], np.float32)
+    wi = np.array([[0, 1, 0]], np.float32)
+    f, pdf = octx.bsdf_eval(params, wi, wi)
+    expect = np.array([0.6, 0.5, 0.4]) / np.pi + 0.04 * (1 / np.pi) * 0.25
+    assert np.allclose(f[0], expect, rtol=1e-5)
+    # pdf = 0.5 * cos/pi (diffuse ratio = 1/(1+0.1)...) -> ratio d = max(1-0,0.1)=1, g = max(1-1,0.1)=0.1 -> 1/1.1
+    r = 1.0 / 1.1
+    pdf_micro = (1.0 / np.pi) / 4.0  # alpha2 = 1 -> D*NdotH = 1/pi, / (4 * wo.wh)
+    assert np.isclose(pdf[0], r / np.pi + (1 - r) * pdf_micro, rtol=1e-5)
+
+
+def test_pbr_eval_below_horizon_is_black(octx):
+    params = np.array([[0.6, 0.6, 0.6, 0.5, 0.5]], np.float32)
+    wi = np.array([[0.3, -0.2, 0.1]], np.float32)
+    wi /= np.linalg.norm(wi)
+    wo = np.array([[0, 1, 0]], np.float32)
+    f, pdf = octx.bsdf_eval(params, wi, wo)
+    assert np.all(f == 0) and pdf[0] == 0
+
+
+def test_pbr_reciprocity_of_specular_lobe(octx):
+    """f/NdotL is symmetric in (wi, wo) for the metallic lobe (no diffuse term when metallic = 1)."""
+    rng = np.random.default_rng(3)
+    n = 2000
+    wi, wo = _dirs(rng, n), _dirs(rng, n)
+    wi[:, 1] = np.maximum(wi[:, 1], 0.05)
+    wo[:, 1] = np.maximum(wo[:, 1], 0.05)
+    wi /= np.linalg.norm(wi, axis=1, keepdims=True)
+    wo /= np.linalg.norm(wo, axis=1, keepdims=True)
+    params = np.tile(np.array([[0.9, 0.6, 0.3, 1.0, 0.4]], np.float32), (n, 1))
+    f1, _ = octx.bsdf_eval(params, wi, wo)
+    f2, _ = octx.bsdf_eval(params, wo, wi)
+    a = f1 / wi[:, 1:2]
+    b = f2 / wo[:, 1:2]
+    assert np.allclose(a, b, rtol=2e-3, atol=1e-6)
+
+
+def test_pbr_pdf_integrates_to_one(octx):
+    """pdfPBRStandard (pbrStandard.glsl:123-137) is a density over the upper hemisphere."""
+    rng = np.random.default_rng(5)
+    n = 400000
+    u = rng.uniform(size=(n, 2))
+    z = u[:, 0]
+    r = np.sqrt(np.maximum(0, 1 - z * z))
+    phi = 2 * np.pi * u[:, 1]
+    wi = np.stack([r * np.cos(phi), z, r * np.sin(phi)], axis=1).astype(np.float32)  # uniform hemisphere, pdf 1/2pi
+    wo = np.tile(np.array([[0.4, 0.8, 0.2]], np.float32) / np.linalg.norm([0.4, 0.8, 0.2]), (n, 1)).astype(np.float32)
+    for rough, metal in ((0.6, 0.0), (0.35, 1.0)):
+        params = np.tile(np.array([[0.8, 0.8, 0.8, metal, rough]], np.float32), (n, 1))
+        _, pdf = octx.bsdf_eval(params, wi, wo)
+        integral = float(np.mean(pdf.astype(np.float64)) * 2 * np.pi)
+        assert 0.93 < integral < 1.03, integral  # the GGX vndf-less pdf loses a little below the horizon
+
+
+def test_pbr_sample_consistent_with_eval(octx):
+    """samplePBRStandard returns f and pdf equal to eval/pdf at the sampled direction (pbrStandard.glsl:139-165)."""
+    rng = np.random.default_rng(7)
+    n = 5000
+    wo = _dirs(rng, n)
+    params = np.stack([rng.uniform(0.1, 1, n), rng.uniform(0.1, 1, n), rng.uniform(0.1, 1, n), rng.uniform(0, 1, n),
+                       rng.uniform(0.05, 1, n)], axis=1).astype(np.float32)
+    u = rng.uniform(0.001, 0.999, (n, 3)).astype(np.float32)
+    wi, f, pdf = octx.bsdf_sample(params, wo, u)
+    f2, pdf2 = octx.bsdf_eval(params, wi, wo)
+    ok = pdf >= 1e-6
+    assert ok.mean() > 0.8
+    assert np.allclose(pdf[ok], pdf2[ok], rtol=1e-5, atol=1e-7)
+    assert np.allclose(f[ok], f2[ok], rtol=1e-5, atol=1e-7)
+    assert np.allclose(np.linalg.norm(wi[ok], axis=1), 1.0, atol=1e-3)
+
+
+# ---------------------------------------------------------------- tiny hand-made scene through the C-ABI
+def make_quad_scene(capi, emissive=False):
+    """One unit quad in the plane y = 0 (two triangles), white Lambert, no textures beyond the three defaults."""
+    V = (capi.ptc_vertex * 4)()
+    pos = [(-1, 0, 1), (1, 0, 1), (-1, 0, -1), (1, 0, -1)]
+    for i, p in enumerate(pos):
+        V[i].position[:] = p
+        V[i].normal[:] = (0, 1, 0)
+        V[i].tangent[:] = (1, 0, 0)
+        V[i].bitangent[:] = (0, 0, -1)
+        V[i].uv[:] = ((p[0] + 1) / 2, (1 - p[2]) / 2)
+        V[i].color[:] = (1, 1, 1)
+    I = (C.c_uint32 * 6)(1, 2, 0, 1, 3, 2)
+    M = (capi.ptc_mesh * 1)()
+    M[0].first_index, M[0].tri_count, M[0].first_vertex, M[0].vertex_count = 0, 2, 0, 4
+    inst = (capi.ptc_instance * 1)()
+    inst[0].model[:] = (1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1)
+    inst[0].id[:] = (1, -1, -1, 0)
+    inst[0].material_index, inst[0].mesh_index, inst[0].num_triangles = 0, 0, 2
+    mat = (capi.ptc_material * 1)()
+    mat[0].albedo[:] = (0.5, 0.5, 0.5, 1)
+    mat[0].metallic_roughness_ao[:] = (0, 1, 1, 0)
+    mat[0].emissive[:] = (1, 1, 1, 2.0) if emissive else (0, 0, 0, 1)
+    mat[0].tex1[:] = (1, 0, 0, 0)
+    mat[0].tex2[:] = (1, 2, 0, 0)
+    mat[0].uv_tiling[:] = (1, 1, 2, 0)  # Lambert
+    tex_data = [(C.c_uint8 * 4)(255, 255, 255, 255), (C.c_uint8 * 4)(255, 255, 255, 255), (C.c_uint8 * 4)(0x80, 0x80, 0xFF, 0xFF)]
+    T = (capi.ptc_texture * 3)()
+    for i in range(3):
+        T[i].width = T[i].height = 1
+        T[i].channels = 4
+        T[i].srgb = 1 if i == 1 else 0
+        T[i].data = C.cast(tex_data[i], C.POINTER(C.c_uint8))
+    d = capi.ptc_scene_desc()
+    d.vertices, d.n_vertices = V, 4
+    d.indices, d.n_indices = I, 6
+    d.meshes, d.n_meshes = M, 1
+    d.instances, d.n_instances = inst, 1
+    d.materials, d.n_materials = mat, 1
+    d.textures, d.n_textures = T, 3
+    keep = (V, I, M, inst, mat, T, tex_data)
+    return d, keep
+
+
+def look_down_params(capi, w=16, h=16, spp=64, batch=16, depth=4, bg=(1.0, 1.0, 1.0)):
+    """Camera at (0, 3, 0) looking straight down on the quad, 20 degree fov so every pixel sees the quad."""
+    import math
+    rp = capi.ptc_render_params()
+    # view inverse: camera x = world x, camera y = world -z, camera -z (forward) = world -y
+    vinv = np.array([[1, 0, 0, 0], [0, 0, 1, 3], [0, -1, 0, 0], [0, 0, 0, 1]], np.float32)
+    t = math.tan(math.radians(20) / 2)
+    zn, zf = 0.5, 50.0
+    proj = np.zeros((4, 4), np.float32)
+    proj[0, 0] = 1 / t
+    proj[1, 1] = -1 / t
+    proj[2, 2] = zf / (zn - zf)
+    proj[3, 2] = -1
+    proj[2, 3] = -(zf * zn) / (zf - zn)
+    rp.scene.view[:] = np.linalg.inv(vinv).T.flatten()
+    rp.scene.view_inverse[:] = vinv.T.flatten()
+    rp.scene.projection[:] = proj.T.flatten()
+    rp.scene.projection_inverse[:] = np.linalg.inv(proj).T.flatten()
+    rp.scene.exposure[:] = (0, 1, 0, 10)
+    rp.scene.background[:] = (bg[0], bg[1], bg[2], 0)
+    rp.scene.volumes[:] = (-1, zn, zf, 0)
+    rp.samples, rp.batch_size, rp.depth, rp.width, rp.height = spp, batch, depth, w, h
+    rp.world = 1
+    return rp
+
+
+def test_white_furnace_single_quad(capi, oracle_lib):
+    """A Lambert quad (albedo 0.5) under a uniform white background: every path is hit -> bounce -> miss, so each pixel is
+    exactly albedo * 1 = 0.5; first-hit AOVs are the albedo and n*0.5+0.5 = (0.5, 1, 0.5) (tilted by the 8-bit default normal map)."""
+    d, keep = make_quad_scene(capi)
+    ctx = capi.Context(oracle_lib)
+    ctx.upload_scene(C.byref(d))
+    ctx.build_accel()
+    rad, alb, nrm = ctx.render(look_down_params(capi))
+    assert np.allclose(rad[..., :3], 0.5, atol=2e-6)
+    assert np.all(rad[..., 3] == 1.0)
+    assert np.allclose(alb[..., :3], 0.5, atol=1e-6)
+    assert np.allclose(nrm[..., 1], 1.0, atol=1e-4) and np.allclose(nrm[..., 0], 0.5, atol=3e-3) and np.allclose(nrm[..., 2], 0.5, atol=3e-3)
+    st = ctx.stats()
+    assert st["segments"] == 2 * 16 * 16 * 64  # hit + miss for every path
+    assert st["shadow_rays"] == 0 and st["probe_rays"] == 0
+    ctx.close()
+
+
+def test_emission_only_on_first_hit(capi, oracle_lib):
+    """Trap T2: an emissive surface seen directly adds emissive * beta and stops (rchit :113-124)."""
+    d, keep = make_quad_scene(capi, emissive=True)
+    ctx = capi.Context(oracle_lib)
+    ctx.upload_scene(C.byref(d))
+    ctx.build_accel()
+    rad, _, _ = ctx.render(look_down_params(capi, bg=(0, 0, 0)))
+    assert np.allclose(rad[..., :3], 2.0, atol=1e-5)
+    assert ctx.stats()["segments"] == 16 * 16 * 64
+    ctx.close()
+
+
+def test_samples_dropped_when_not_multiple_of_batch(capi, oracle_lib):
+    """Trap T7: batches = samples / batchSize, remainder dropped, normalisation by batches*batchSize."""
+    d, keep = make_quad_scene(capi)
+    ctx = capi.Context(oracle_lib)
+    ctx.upload_scene(C.byref(d))
+    ctx.build_accel()
+    rad, _, _ = ctx.render(look_down_params(capi, spp=70, batch=16))
+    assert ctx.stats()["segments"] == 2 * 16 * 16 * 64
+    assert np.allclose(rad[..., :3], 0.5, atol=2e-6)
+    ctx.close()
+
+
+def test_empty_scene_renders_background(capi, oracle_lib):
+    d = capi.ptc_scene_desc()
+    ctx = capi.Context(oracle_lib)
+    ctx.upload_scene(C.byref(d))
+    ctx.build_accel()
+    rad, alb, nrm = ctx.render(look_down_params(capi, bg=(0.25, 0.5, 0.75)))
+    assert np.allclose(rad[..., :3], (0.25, 0.5, 0.75), atol=1e-6)
+    assert np.allclose(alb[..., :3], (0.25, 0.5, 0.75), atol=1e-6) and np.all(nrm[..., :3] == 0)
+    ctx.close()
+
+
+def test_trace_closest_hits_and_misses(capi, oracle_lib):
+    d, keep = make_quad_scene(capi)
+    ctx = capi.Context(oracle_lib)
+    ctx.upload_scene(C.byref(d))
+    ctx.build_accel()
+    rays = np.array([[0.25, 2, 0.25, 1e-3, 0, -1, 0, 1e4],      # hit at t = 2
+                     [0.25, 2, 0.25, 1e-3, 0, 1, 0, 1e4],       # pointing away
+                     [0.25, 2, 0.25, 1e-3, 0, -1, 0, 1.5],      # tmax before the surface
+                     [5, 2, 0, 1e-3, 0, -1, 0, 1e4],            # beside the quad
+                     [0.0, -1, 0.0, 1e-3, 0, 1, 0, 1e4]], np.float32)  # from below: no culling
+    inst, prim, t, u, v = ctx.trace_closest(rays)
+    assert list(inst) == [0, -1, -1, -1, 0]
+    assert np.isclose(t[0], 2.0) and np.isclose(t[4], 1.0)
+    assert prim[0] in (0, 1) and 0 <= u[0] <= 1 and 0 <= v[0] <= 1 and u[0] + v[0] <= 1
+    ctx.close()
+
+
+# ---------------------------------------------------------------- LBVH reference build
+def naive_expand(v, bits):
+    out = 0
+    for i in range(bits):
+        out |= ((v >> i) & 1) << (3 * i)
+    return out
+
+
+def check_lbvh(L, tris_bounds=None):
+    n = L["n"]
+    assert np.all(L["morton"][:-1] <= L["morton"][1:])
+    assert sorted(L["order"].tolist()) == list(range(n))
+    if n == 1:
+        return
+    nn = 2 * n - 1
+    parent, left, right, box = L["parent"], L["left"], L["right"], L["aabb"]
+    assert parent[0] == -1 and np.all(parent[1:] >= 0)
+    seen = np.zeros(nn, bool)
+    for i in range(n - 1):
+        for c in (left[i], right[i]):
+            assert 0 <= c < nn and not seen[c] and parent[c] == i
+            seen[c] = True
+            assert np.all(box[i, :3] <= box[c, :3]) and np.all(box[i, 3:] >= box[c, 3:])
+        assert np.array_equal(box[i, :3], np.minimum(box[left[i], :3], box[right[i], :3]))
+        assert np.array_equal(box[i, 3:], np.maximum(box[left[i], 3:], box[right[i], 3:]))
+    assert seen[1:].all() and not seen[0]
+    # equal keys are ordered by triangle id (stable sort = index tie-break)
+    eq = L["morton"][:-1] == L["morton"][1:]
+    assert np.all(L["order"][:-1][eq] < L["order"][1:][eq])
+
+
+@pytest.mark.parametrize("scene,bits", [("Volume5", 10), ("EnvironmentMap", 10)])
+def test_oracle_lbvh_invariants(capi, oracle_lib, scene, bits):
+    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng.build_scene(scene)
+    ctx = capi.Context(oracle_lib)
+    ctx.upload_scene(eng.scene_desc())
+    ctx.build_accel()
+    L = ctx.get_lbvh()
+    check_lbvh(L)
+    assert int(L["morton"].max()) < (1 << (3 * bits))
+    ctx.close()
+    eng.close()
+
+
+def test_oracle_lbvh_63bit_for_large_scenes(capi, oracle_lib):
+    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng.build_scene("Atrium", texture_size=4, scale=0.3)
+    ctx = capi.Context(oracle_lib)
+    ctx.upload_scene(eng.scene_desc())
+    ctx.build_accel()
+    L = ctx.get_lbvh()
+    assert L["n"] > 65536
+    check_lbvh(L)
+    assert int(L["morton"].max()) >= (1 << 40)  # 63-bit codes in use
+    ctx.close()
+    eng.close()
+
+
+def test_morton_bit_expansion_reference():
+    # the magic-number expansions used on both sides equal the naive bit loop
+    def e21(v):
+        v &= 0x1fffff
+        v = (v | v << 32) & 0x1f00000000ffff
+        v = (v | v << 16) & 0x1f0000ff0000ff
+        v = (v | v << 8) & 0x100f00f00f00f00f
+        v = (v | v << 4) & 0x10c30c30c30c30c3
+        v = (v | v << 2) & 0x1249249249249249
+        return v
+
+    def e10(v):
+        v &= 0x3ff
+        v = (v * 0x00010001) & 0xFF0000FF
+        v = (v * 0x00000101) & 0x0F00F00F
+        v = (v * 0x00000011) & 0xC30C30C3
+        v = (v * 0x00000005) & 0x49249249
+        return v
+
+    rng = np.random.default_rng(0)
+    for v in [0, 1, 2, 0x1fffff, 0x155555] + rng.integers(0, 1 << 21, 200).tolist():
+        assert e21(v) == naive_expand(v, 21)
+    for v in [0, 1, 1023, 0x2aa] + rng.integers(0, 1 << 10, 200).tolist():
+        assert e10(v) == naive_expand(v, 10)
+
+
+def test_env_cubemap_lookup_matches_equirect(capi, oracle_lib):
+    """createCubemap semantics: cubemap(dir) == bilinear equirect(sampleEquirectangularMap(dir)) up to resampling blur."""
+    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng.build_scene("EnvironmentMapLambert")
+    d = eng.scene_desc().contents
+    W, H = d.env.width, d.env.height
+    eq = np.ctypeslib.as_array(d.env.equirect_rgba, shape=(H, W, 4))
+    ctx = capi.Context(oracle_lib)
+    ctx.upload_scene(eng.scene_desc())
+    rng = np.random.default_rng(2)
+    dirs = _dirs(rng, 4000, upper=False)
+    got = ctx.env_lookup(dirs)
+    u = (np.arctan2(dirs[:, 2], dirs[:, 0]) * 0.1591 + 0.5 + 0.25) % 1.0
+    v = np.arcsin(np.clip(dirs[:, 1], -1, 1)) * 0.3183 + 0.5
+    x = np.clip((u * W).astype(int), 0, W - 1)
+    y = np.clip((v * H).astype(int), 0, H - 1)
+    want = eq[y, x, :3]
+    # compare on smooth regions only (nearest vs filtered lookups differ at edges)
+    err = np.abs(got - want).max(axis=1) / np.maximum(want.max(axis=1), 0.05)
+    assert np.median(err) < 0.03 and np.mean(err < 0.25) > 0.9
+    # the brightest region (sun/sky) is above the horizon
+    up = ctx.env_lookup(np.array([[0, 1, 0]], np.float32))[0]
+    down = ctx.env_lookup(np.array([[0, -1, 0]], np.float32))[0]
+    assert up.sum() > down.sum()
+    ctx.close()
+    eng.close()
