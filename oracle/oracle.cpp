@@ -118,6 +118,10 @@ vec4f sampleTexture(const Texture &T, float u, float v) {
     float x = u * (float)T.w - 0.5f, y = v * (float)T.h - 0.5f;
     float fx = std::floor(x), fy = std::floor(y);
     float ax = x - fx, ay = y - fy;
+    /* NVIDIA texture units (the reference ran on an RTX GPU, the product on a B200) hold the bilinear weights in
+     * 1.8 fixed point (CUDA programming guide, "Linear Filtering") */
+    ax = std::floor(ax * 256.0f + 0.5f) * (1.0f / 256.0f);
+    ay = std::floor(ay * 256.0f + 0.5f) * (1.0f / 256.0f);
     long ix = (long)fx, iy = (long)fy;
     auto wrap = [](long i, long n) {
         long m = i % n;

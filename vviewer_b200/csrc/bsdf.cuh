@@ -67,60 +67,79 @@ PTC_D float powerHeuristic(float fPdf, float gPdf) { /* MIS.glsl:5-10 with nf = 
 }
 
 /* ------------------------------------------------------------------ PBR standard (pbrStandard.glsl, common.glsl) */
+/* evalPBRStandard / pdfPBRStandard are written with explicit round-to-nearest intrinsics (never contracted into
+ * FMAs) in the exact operation order of the oracle: GTR2's 1 + (a^2 - 1) NdotH^2 cancels catastrophically for
+ * glossy lobes, so a single differently-rounded product upstream would already break the 1e-5 BSDF parity bar. */
 struct Pbr {
     float3 albedo;
     float metallic, roughness;
 };
+PTC_D float rmul(float a, float b) { return __fmul_rn(a, b); }
+PTC_D float radd(float a, float b) { return __fadd_rn(a, b); }
+PTC_D float rsub(float a, float b) { return __fsub_rn(a, b); }
+PTC_D float rdiv(float a, float b) { return __fdiv_rn(a, b); }
+PTC_D float rdot(float3 a, float3 b) { return radd(radd(rmul(a.x, b.x), rmul(a.y, b.y)), rmul(a.z, b.z)); }
+PTC_D float3 rnormalize(float3 a) {
+    const float l = __fsqrt_rn(rdot(a, a));
+    return f3(rdiv(a.x, l), rdiv(a.y, l), rdiv(a.z, l));
+}
+PTC_D float rmix(float a, float b, float t) { return radd(rmul(a, rsub(1.0f, t)), rmul(b, t)); }
 PTC_D float schlickW(float c) {
-    float m = clampf(1.0f - c, 0.0f, 1.0f);
-    return (m * m) * (m * m) * m;
+    float m = clampf(rsub(1.0f, c), 0.0f, 1.0f);
+    return rmul(rmul(rmul(m, m), rmul(m, m)), m);
 }
 PTC_D float gtr2(float NdotH, float a) {
-    float a2 = a * a;
-    float t = 1.0f + (a2 - 1.0f) * NdotH * NdotH;
-    return a2 / (PT_PI * t * t);
+    float a2 = rmul(a, a);
+    float t = radd(1.0f, rmul(rmul(rsub(a2, 1.0f), NdotH), NdotH));
+    return rdiv(a2, rmul(rmul(PT_PI, t), t));
 }
 PTC_D float smithGGX(float NdotV, float alphaG) {
-    float a = alphaG * alphaG, b = NdotV * NdotV;
-    return 1.0f / (fabsf(NdotV) + fmaxf(sqrtf(a + b - a * b), PT_EPSILON));
+    float a = rmul(alphaG, alphaG), b = rmul(NdotV, NdotV);
+    return rdiv(1.0f, radd(fabsf(NdotV), fmaxf(__fsqrt_rn(rsub(radd(a, b), rmul(a, b))), PT_EPSILON)));
 }
 PTC_D float diffuseRatio(const Pbr &p) { /* :83-90 */
-    float d = fmaxf(1.0f - p.metallic, 0.1f), g = fmaxf(1.0f - p.roughness, 0.1f);
-    return d / (d + g);
+    float d = fmaxf(rsub(1.0f, p.metallic), 0.1f), g = fmaxf(rsub(1.0f, p.roughness), 0.1f);
+    return rdiv(d, radd(d, g));
 }
-PTC_D float3 pbrEval(const Pbr &p, float3 wi, float3 wo) { /* evalPBRStandard :92-105 with H = normalize(wi + wo) */
+PTC_D float3 pbrEval(const Pbr &p, float3 wi, float3 wo) { /* evalPBRStandard :92-105 with H = normalize(wo + wi) */
     float NdotL = wi.y, NdotV = wo.y;
     if (NdotL < 0.0f || NdotV < 0.0f) return f3(0.0f);
-    float3 H = normalize(wo + wi);
-    float NdotH = H.y, LdotH = dot(wi, H);
+    float3 H = rnormalize(f3(radd(wo.x, wi.x), radd(wo.y, wi.y), radd(wo.z, wi.z)));
+    float NdotH = H.y, LdotH = rdot(wi, H);
     /* Disney diffuse :10-19 */
     float FL = schlickW(NdotL), FV = schlickW(NdotV);
-    float Fd90 = 0.5f + 2.0f * LdotH * LdotH * p.roughness;
-    float Fd = mixf(1.0f, Fd90, FL) * mixf(1.0f, Fd90, FV);
-    float3 diffuse = p.albedo * ((1.0f / PT_PI) * Fd);
+    float Fd90 = radd(0.5f, rmul(rmul(rmul(2.0f, LdotH), LdotH), p.roughness));
+    float Fd = rmul(rmix(1.0f, Fd90, FL), rmix(1.0f, Fd90, FV));
+    float kd = rmul(rdiv(1.0f, PT_PI), Fd);
+    float3 diffuse = f3(rmul(p.albedo.x, kd), rmul(p.albedo.y, kd), rmul(p.albedo.z, kd));
     /* microfacet :25-44 (specular 0.5, specularTint 0 -> Cspec0 = mix(0.04, albedo, metallic)) */
-    float3 Cspec0 = mix3(f3(0.5f * 0.08f), p.albedo, p.metallic);
-    float a = fmaxf(0.001f, p.roughness * p.roughness);
+    const float s0 = rmul(0.5f, 0.08f);
+    float3 Cspec0 = f3(rmix(s0, p.albedo.x, p.metallic), rmix(s0, p.albedo.y, p.metallic), rmix(s0, p.albedo.z, p.metallic));
+    float a = fmaxf(0.001f, rmul(p.roughness, p.roughness));
     float Ds = gtr2(NdotH, a);
-    float3 Fs = mix3(Cspec0, f3(1.0f), schlickW(LdotH));
-    float Gs = smithGGX(NdotL, a) * smithGGX(NdotV, a);
-    float3 glossy = Fs * (Gs * Ds);
-    return (diffuse * (1.0f - p.metallic) + glossy) * NdotL;
+    float FH = schlickW(LdotH);
+    float3 Fs = f3(rmix(Cspec0.x, 1.0f, FH), rmix(Cspec0.y, 1.0f, FH), rmix(Cspec0.z, 1.0f, FH));
+    float Gs = rmul(smithGGX(NdotL, a), smithGGX(NdotV, a));
+    float gd = rmul(Gs, Ds);
+    float km = rsub(1.0f, p.metallic);
+    return f3(rmul(radd(rmul(diffuse.x, km), rmul(Fs.x, gd)), NdotL), rmul(radd(rmul(diffuse.y, km), rmul(Fs.y, gd)), NdotL),
+              rmul(radd(rmul(diffuse.z, km), rmul(Fs.z, gd)), NdotL));
 }
 PTC_D float pbrPdfMicrofacet(float3 wi, float3 wo, const Pbr &p) { /* :46-63 */
     if (!(wo.y > 0.0f) || !(wi.y > 0.0f)) return 0.0f;
-    float3 wh = normalize(wo + wi);
+    float3 wh = rnormalize(f3(radd(wo.x, wi.x), radd(wo.y, wi.y), radd(wo.z, wi.z)));
     float NdotH = fmaxf(wh.y, PT_EPSILON);
-    float a2 = p.roughness * p.roughness;
-    a2 *= a2;
-    float denom = NdotH * NdotH * (a2 - 1.0f) + 1.0f;
+    float a2 = rmul(p.roughness, p.roughness);
+    a2 = rmul(a2, a2);
+    float denom = radd(rmul(rmul(NdotH, NdotH), rsub(a2, 1.0f)), 1.0f);
     if (denom == 0.0f) return 0.0f;
-    return (a2 * NdotH / (PT_PI * denom * denom)) / (4.0f * dot(wo, wh));
+    float pd = rdiv(rmul(a2, NdotH), rmul(rmul(PT_PI, denom), denom));
+    return rdiv(pd, rmul(4.0f, rdot(wo, wh)));
 }
 PTC_D float pbrPdf(float3 wi, float3 wo, const Pbr &p) { /* :123-137 */
     if (wi.y < 0.0f) return 0.0f;
     float r = diffuseRatio(p);
-    return (wi.y * PT_INV_PI) * r + pbrPdfMicrofacet(wi, wo, p) * (1.0f - r);
+    return radd(rmul(rmul(wi.y, PT_INV_PI), r), rmul(pbrPdfMicrofacet(wi, wo, p), rsub(1.0f, r)));
 }
 PTC_D float3 pbrSample(float3 &wi, float3 wo, float &pdf, const Pbr &p, float u0, float u1, float lobe) { /* :139-165 */
     if (lobe <= diffuseRatio(p)) {
