@@ -9,6 +9,10 @@
  * Node fetches are 128-bit (4 x float4 per binary node: both child boxes + child links), triangle fetches are
  * 3 x float4; the traversal stack lives in shared memory (one column per thread, bank-conflict free) with a
  * local-memory spill that is never reached by LBVH depths seen in practice.
+ *
+ * The traversal is a resumable state machine (Trav) so that kernels can run it warp-convergently: persistent warps
+ * pull rays from a global counter with warp-aggregated atomics and replace finished rays while the other lanes keep
+ * traversing (Aila & Laine 2009 "while-while" with dynamic fetch) instead of letting the warp fragment.
  */
 #pragma once
 #include "common.cuh"
@@ -16,7 +20,9 @@
 namespace trv {
 
 #define TRV_STACK 64
+#define TRV_SHARED_STACK 24
 #define TRV_BLOCK 128 /* threads per block of every kernel that traverses */
+#define TRV_DONE 0x7fffffff
 
 struct Ray {
     float3 o, d;
@@ -44,37 +50,61 @@ PTC_D bool intersectTri(const float4 v0, const float4 e1, const float4 e2, const
     return true;
 }
 
-/* Generic ordered query: the smallest (t, id) that is lexicographically greater than (t0, id0) and has
- * t < tmax.  Closest hit = (t0, id0) = (tmin, 0xffffffff).  anyHit = true returns at the first candidate. */
-template <bool ANY_HIT>
-PTC_D HitRec traverse(const DScene &sc, const Ray &ray, float t0, uint32_t id0, int32_t *stack /* shared, stride blockDim.x */) {
+/* Ordered query state: finds the smallest (t, id) lexicographically greater than (t0, id0) with t < tmax.
+ * Closest hit: (t0, id0) = (tmin, 0xffffffff). */
+struct Trav {
+    float3 o, d, idir, ood;
+    float tmin, tmax, t0;
+    uint32_t id0;
     HitRec best;
-    best.t = ray.tmax;
-    best.u = best.v = 0.0f;
-    best.pos = -1;
-    best.worldId = 0xffffffffu;
-    if (sc.nTris == 0) return best;
-
-    const float ooeps = 1e-20f;
-    float3 idir = f3(1.0f / (fabsf(ray.d.x) > ooeps ? ray.d.x : copysignf(ooeps, ray.d.x)),
-                     1.0f / (fabsf(ray.d.y) > ooeps ? ray.d.y : copysignf(ooeps, ray.d.y)),
-                     1.0f / (fabsf(ray.d.z) > ooeps ? ray.d.z : copysignf(ooeps, ray.d.z)));
-    float3 ood = ray.o * idir;
-    const float4 *__restrict__ nodes = sc.bvhNodes;
-    const float4 *__restrict__ tris = sc.tris;
-
-    int sp = 0;
-    int32_t node = sc.rootIsLeaf ? ~0 : 0;
-    const int stride = blockDim.x;
+    int32_t node;
+    int sp;
     int32_t spill[TRV_STACK];
 
-    while (true) {
-        while (node >= 0) {
+    PTC_D void init(const DScene &sc, const Ray &ray, float t0_, uint32_t id0_) {
+        o = ray.o;
+        d = ray.d;
+        tmin = ray.tmin;
+        tmax = ray.tmax;
+        t0 = t0_;
+        id0 = id0_;
+        const float ooeps = 1e-20f;
+        idir = f3(1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x)), 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y)),
+                  1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z)));
+        ood = o * idir;
+        best.t = tmax;
+        best.u = best.v = 0.0f;
+        best.pos = -1;
+        best.worldId = 0xffffffffu;
+        sp = 0;
+        node = sc.nTris == 0 ? TRV_DONE : (sc.rootIsLeaf ? ~0 : 0);
+    }
+    PTC_D bool done() const { return node == TRV_DONE; }
+    PTC_D int32_t pop(const int32_t *stack, int stride) {
+        if (sp == 0) return TRV_DONE;
+        --sp;
+        return sp < TRV_SHARED_STACK ? stack[sp * stride] : spill[sp - TRV_SHARED_STACK];
+    }
+    PTC_D void push(int32_t *stack, int stride, int32_t v) {
+        if (sp < TRV_SHARED_STACK)
+            stack[sp * stride] = v;
+        else if (sp - TRV_SHARED_STACK < TRV_STACK)
+            spill[sp - TRV_SHARED_STACK] = v;
+        ++sp;
+    }
+
+    /* one outer iteration of the while-while loop: descend to the next leaf, test it, pop. Returns done(). */
+    template <bool ANY_HIT>
+    PTC_D bool advance(const DScene &sc, int32_t *stack) {
+        const float4 *__restrict__ nodes = sc.bvhNodes;
+        const float4 *__restrict__ tris = sc.tris;
+        const int stride = blockDim.x;
+        while (node >= 0 && node != TRV_DONE) {
             const float4 n0 = __ldg(&nodes[4 * (size_t)node + 0]);
             const float4 n1 = __ldg(&nodes[4 * (size_t)node + 1]);
             const float4 n2 = __ldg(&nodes[4 * (size_t)node + 2]);
             const float4 n3 = __ldg(&nodes[4 * (size_t)node + 3]);
-            /* slab test of both children; far side widened by 2 ulp so a boundary hit is never lost (Ize 2013) */
+            /* slab test of both children; the interval is widened by 2 ulp so a boundary hit is never lost (Ize 2013) */
             float l0x = n0.x * idir.x - ood.x, l1x = n0.y * idir.x - ood.x;
             float l0y = n0.z * idir.y - ood.y, l1y = n0.w * idir.y - ood.y;
             float l0z = n2.x * idir.z - ood.z, l1z = n2.y * idir.z - ood.z;
@@ -85,16 +115,10 @@ PTC_D HitRec traverse(const DScene &sc, const Ray &ray, float t0, uint32_t id0, 
             float r0z = n2.z * idir.z - ood.z, r1z = n2.w * idir.z - ood.z;
             float rmin = fmaxf(fmaxf(fminf(r0x, r1x), fminf(r0y, r1y)), fmaxf(fminf(r0z, r1z), t0));
             float rmax = fminf(fminf(fmaxf(r0x, r1x), fmaxf(r0y, r1y)), fminf(fmaxf(r0z, r1z), best.t)) * 1.0000004f;
-            /* lmin is shrunk symmetrically */
-            bool hl = lmin * 0.9999996f <= lmax, hr = rmin * 0.9999996f <= rmax;
-            int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
+            const bool hl = lmin * 0.9999996f <= lmax, hr = rmin * 0.9999996f <= rmax;
+            const int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
             if (!hl && !hr) {
-                if (sp == 0) {
-                    node = 0x7fffffff;
-                    break;
-                }
-                --sp;
-                node = sp < 24 ? stack[sp * stride] : spill[sp - 24];
+                node = pop(stack, stride);
             } else {
                 node = hl ? cl : cr;
                 if (hl && hr) {
@@ -103,15 +127,11 @@ PTC_D HitRec traverse(const DScene &sc, const Ray &ray, float t0, uint32_t id0, 
                         node = cr;
                         farNode = cl;
                     }
-                    if (sp < 24)
-                        stack[sp * stride] = farNode;
-                    else if (sp - 24 < TRV_STACK)
-                        spill[sp - 24] = farNode;
-                    ++sp;
+                    push(stack, stride, farNode);
                 }
             }
         }
-        if (node == 0x7fffffff) break;
+        if (node == TRV_DONE) return true;
         /* leaf: one triangle */
         {
             const int32_t pos = ~node;
@@ -119,29 +139,71 @@ PTC_D HitRec traverse(const DScene &sc, const Ray &ray, float t0, uint32_t id0, 
             const float4 e1 = __ldg(&tris[3 * (size_t)pos + 1]);
             const float4 e2 = __ldg(&tris[3 * (size_t)pos + 2]);
             float t, u, v;
-            if (intersectTri(v0, e1, e2, ray.o, ray.d, t, u, v)) {
+            if (intersectTri(v0, e1, e2, o, d, t, u, v)) {
                 const uint32_t wid = __float_as_uint(e2.w);
                 const bool after = t > t0 || (t == t0 && id0 != 0xffffffffu && wid > id0);
-                const bool inRange = after && t < ray.tmax && t > ray.tmin;
+                const bool inRange = after && t < tmax && t > tmin;
                 if (inRange && (t < best.t || (t == best.t && wid < best.worldId))) {
                     best.t = t;
                     best.u = u;
                     best.v = v;
                     best.pos = pos;
                     best.worldId = wid;
-                    if (ANY_HIT) return best;
+                    if (ANY_HIT) {
+                        node = TRV_DONE;
+                        return true;
+                    }
                 }
             }
         }
-        if (sp == 0) break;
-        --sp;
-        node = sp < 24 ? stack[sp * stride] : spill[sp - 24];
+        node = pop(stack, stride);
+        return node == TRV_DONE;
     }
-    return best;
-}
+};
 
+/* run-to-completion wrappers (used by the chain kernels and the parity hooks) */
+template <bool ANY_HIT>
+PTC_D HitRec traverse(const DScene &sc, const Ray &ray, float t0, uint32_t id0, int32_t *stack) {
+    Trav tr;
+    tr.init(sc, ray, t0, id0);
+    while (!tr.done()) tr.advance<ANY_HIT>(sc, stack);
+    return tr.best;
+}
 PTC_D HitRec closestHit(const DScene &sc, const Ray &ray, int32_t *stack) { return traverse<false>(sc, ray, ray.tmin, 0xffffffffu, stack); }
 PTC_D HitRec nextHit(const DScene &sc, const Ray &ray, float t0, uint32_t id0, int32_t *stack) { return traverse<false>(sc, ray, t0, id0, stack); }
 PTC_D bool occluded(const DScene &sc, const Ray &ray, int32_t *stack) { return traverse<true>(sc, ray, ray.tmin, 0xffffffffu, stack).pos >= 0; }
+
+/* ------------------------------------------------------------------ persistent-warp work distribution */
+/* Each warp owns a chunk [pos, end) of the work list, refilled with ONE global atomic per chunk; lanes that need work
+ * take consecutive items with a ballot/popc rank.  All 32 lanes must call fetch(). */
+struct WarpFeeder {
+    uint32_t pos = 0, end = 0;
+    bool exhausted = false;
+    static constexpr uint32_t CHUNK = 256;
+
+    /* returns the work index for this lane or 0xffffffff */
+    PTC_D uint32_t fetch(bool need, uint32_t *__restrict__ counter, uint32_t count) {
+        const unsigned m = __ballot_sync(0xffffffffu, need);
+        if (m == 0u) return 0xffffffffu;
+        const uint32_t lane = threadIdx.x & 31u;
+        if (pos >= end && !exhausted) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(counter, CHUNK);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            pos = base;
+            end = min(base + CHUNK, count);
+            if (base >= count) {
+                exhausted = true;
+                pos = end = 0;
+            }
+        }
+        const uint32_t avail = end - pos;
+        const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+        const uint32_t n = min((uint32_t)__popc(m), avail);
+        const uint32_t idx = (need && rank < avail) ? pos + rank : 0xffffffffu;
+        pos += n;
+        return idx;
+    }
+};
 
 }  // namespace trv
