@@ -229,6 +229,11 @@ PTC_API int ptc_trace_closest(ptc_ctx *ctx, const float *rays, int n, int *inst,
 PTC_API int ptc_get_lbvh(ptc_ctx *ctx, uint64_t *n_out, uint64_t *morton, uint32_t *order, int32_t *parent, int32_t *left,
                          int32_t *right, float *aabb);
 
+/* Wide (8-ary, compressed) BVH dump for the bit-exact collapse check: node_words[n_nodes * 20] (80 B per node, layout
+ * in vviewer_b200/csrc/lbvh.cuh), tri_order[n_tris] (position in the traversal triangle array -> world triangle id).
+ * Pass NULL arrays to query the counts. */
+PTC_API int ptc_get_wide_bvh(ptc_ctx *ctx, uint64_t *n_nodes_out, uint64_t *n_tris_out, uint32_t *node_words, uint32_t *tri_order);
+
 /* BSDF parity hooks (src/lib/vengine/shaders/include/brdfs/pbrStandard.glsl:92-165).  Per item:
  * params = albedo rgb, metallic, roughness (5 floats); wi, wo local frame (y = normal).
  * eval: out_f[3], out_pdf[1].   sample: u[3] = (u0, u1, lobe pick) -> out_wi[3], out_f[3], out_pdf[1]. */

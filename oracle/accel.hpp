@@ -14,6 +14,9 @@
 #include <cstdint>
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <cstdlib>
 #include "omath.hpp"
 
 namespace orc {
@@ -227,6 +230,7 @@ struct LBVH {
     std::vector<uint64_t> morton; /* sorted */
     std::vector<uint32_t> order;  /* sorted position -> world triangle id */
     std::vector<int32_t> parent, left, right; /* 2n-1 nodes; internal 0..n-2, leaf k -> n-1+k */
+    std::vector<int32_t> rangeEnd;            /* internal node i covers sorted positions [min(i, rangeEnd[i]), max(i, rangeEnd[i])] */
     std::vector<AABB> box;
 
     static inline int clz64(uint64_t x) { return x ? __builtin_clzll(x) : 64; }
@@ -275,6 +279,7 @@ struct LBVH {
         left.assign(nn, -1);
         right.assign(nn, -1);
         box.assign(nn, AABB());
+        rangeEnd.assign(n, 0);
         for (uint64_t k = 0; k < n; k++) box[n - 1 + k] = tb[order[k]];
         for (int64_t i = 0; i + 1 < (int64_t)n; i++) {
             /* Karras 2012, "Maximizing parallelism in the construction of BVHs, octrees and k-d trees" */
@@ -301,6 +306,7 @@ struct LBVH {
             right[i] = R;
             parent[L] = (int32_t)i;
             parent[R] = (int32_t)i;
+            rangeEnd[i] = (int32_t)j;
         }
         if (n > 1) fit(0);
     }
@@ -326,6 +332,187 @@ struct LBVH {
                 box[x] = b;
             }
         }
+    }
+};
+
+
+/* ------------------------------------------------------------------ reference collapse to the 8-wide compressed BVH
+ * CPU restatement of the device collapse (vviewer_b200/csrc/lbvh.cuh, which documents the 80-byte node layout and the
+ * child selection / slot assignment rules); sequential, breadth first through a FIFO, which yields the same numbering as
+ * the device's level-by-level passes.  Float arithmetic is plain IEEE single (this file is compiled with
+ * -ffp-contract=off), matching the device's explicit round-to-nearest intrinsics. */
+struct WideBVH {
+    std::vector<uint32_t> words;    /* 20 per node */
+    std::vector<uint32_t> triOrder; /* traversal position -> world triangle id */
+    uint64_t nNodes = 0;
+
+    static float bitsToFloat(uint32_t b) {
+        float f;
+        memcpy(&f, &b, 4);
+        return f;
+    }
+    static uint32_t floatToBits(float f) {
+        uint32_t b;
+        memcpy(&b, &f, 4);
+        return b;
+    }
+    static float halfArea(const AABB &b) {
+        float ex = b.hi.x - b.lo.x, ey = b.hi.y - b.lo.y, ez = b.hi.z - b.lo.z;
+        float a = ex * ey;
+        float c = ey * ez;
+        float e = ez * ex;
+        return (a + c) + e;
+    }
+
+    void build(const LBVH &L) {
+        words.clear();
+        triOrder.clear();
+        nNodes = 0;
+        const int64_t n = (int64_t)L.n;
+        if (n == 0) return;
+        triOrder.resize(n);
+        auto subTris = [&](int32_t node) -> uint32_t {
+            if (node >= n - 1) return 1u;
+            int32_t j = L.rangeEnd[node];
+            return (uint32_t)std::abs(j - node) + 1u;
+        };
+        auto subFirst = [&](int32_t node) -> uint32_t {
+            if (node >= n - 1) return (uint32_t)(node - (n - 1));
+            return (uint32_t)std::min(node, L.rangeEnd[node]);
+        };
+        const uint32_t LEAF = 3;
+        std::vector<int32_t> fifo; /* binary root of wide node k */
+        fifo.push_back(0);
+        uint32_t triBase = 0;
+        for (size_t id = 0; id < fifo.size(); id++) {
+            const int32_t root = fifo[id];
+            /* ---- children */
+            std::vector<int32_t> list{root};
+            for (int phase = 0; phase < 2; phase++) {
+                const uint32_t thr = phase == 0 ? LEAF : 1u;
+                while (list.size() < 8) {
+                    int bi = -1;
+                    float ba = -1.0f;
+                    for (size_t i = 0; i < list.size(); i++) {
+                        float a = halfArea(L.box[list[i]]);
+                        if (subTris(list[i]) > thr && a > ba) {
+                            ba = a;
+                            bi = (int)i;
+                        }
+                    }
+                    if (bi < 0) break;
+                    int32_t c = list[bi];
+                    list[bi] = L.left[c];
+                    list.push_back(L.right[c]);
+                }
+            }
+            /* ---- slots */
+            const AABB &rb = L.box[root];
+            const float ncx = (rb.lo.x + rb.hi.x) * 0.5f, ncy = (rb.lo.y + rb.hi.y) * 0.5f, ncz = (rb.lo.z + rb.hi.z) * 0.5f;
+            const int len = (int)list.size();
+            float vx[8], vy[8], vz[8];
+            for (int i = 0; i < len; i++) {
+                const AABB &b = L.box[list[i]];
+                vx[i] = (b.lo.x + b.hi.x) * 0.5f - ncx;
+                vy[i] = (b.lo.y + b.hi.y) * 0.5f - ncy;
+                vz[i] = (b.lo.z + b.hi.z) * 0.5f - ncz;
+            }
+            int32_t slotChild[8];
+            for (int s = 0; s < 8; s++) slotChild[s] = -1;
+            uint32_t childDone = 0, slotDone = 0;
+            for (int it = 0; it < len; it++) {
+                int bc = -1, bs = -1;
+                float bcost = 0.0f;
+                for (int c = 0; c < len; c++) {
+                    if (childDone & (1u << c)) continue;
+                    for (int sl = 0; sl < 8; sl++) {
+                        if (slotDone & (1u << sl)) continue;
+                        float cost = (((sl & 4) ? vx[c] : -vx[c]) + ((sl & 2) ? vy[c] : -vy[c])) + ((sl & 1) ? vz[c] : -vz[c]);
+                        if (bc < 0 || cost > bcost) {
+                            bcost = cost;
+                            bc = c;
+                            bs = sl;
+                        }
+                    }
+                }
+                childDone |= 1u << bc;
+                slotDone |= 1u << bs;
+                slotChild[bs] = list[bc];
+            }
+            /* ---- quantisation frame */
+            const float plo[3] = {rb.lo.x, rb.lo.y, rb.lo.z}, phi[3] = {rb.hi.x, rb.hi.y, rb.hi.z};
+            uint32_t e[3];
+            float scale[3], inv[3];
+            for (int a = 0; a < 3; a++) {
+                const float extent = phi[a] - plo[a];
+                const float sdiv = extent / 255.0f;
+                const uint32_t b = floatToBits(sdiv);
+                uint32_t ee = (b >> 23) & 0xffu;
+                if (b & 0x7fffffu) ee++;
+                ee = std::min(std::max(ee, 1u), 253u);
+                while (ee < 253u && extent * bitsToFloat((254u - ee) << 23) > 255.0f) ee++;
+                e[a] = ee;
+                scale[a] = bitsToFloat(ee << 23);
+                inv[a] = bitsToFloat((254u - ee) << 23);
+            }
+            /* ---- record */
+            uint32_t meta[8], qlo[3][8], qhi[3][8];
+            uint32_t imask = 0, off = 0;
+            const uint32_t childBase = (uint32_t)fifo.size();
+            for (int sl = 0; sl < 8; sl++) {
+                const int32_t c = slotChild[sl];
+                if (c < 0) {
+                    meta[sl] = 0;
+                    for (int a = 0; a < 3; a++) {
+                        qlo[a][sl] = 255u;
+                        qhi[a][sl] = 0u;
+                    }
+                    continue;
+                }
+                const AABB &cb = L.box[c];
+                const float clo[3] = {cb.lo.x, cb.lo.y, cb.lo.z}, chi[3] = {cb.hi.x, cb.hi.y, cb.hi.z};
+                for (int a = 0; a < 3; a++) {
+                    float ql = std::floor((clo[a] - plo[a]) * inv[a]);
+                    ql = std::min(std::max(ql, 0.0f), 255.0f);
+                    while (ql > 0.0f && plo[a] + ql * scale[a] > clo[a]) ql -= 1.0f;
+                    float qh = std::ceil((chi[a] - plo[a]) * inv[a]);
+                    qh = std::min(std::max(qh, 0.0f), 255.0f);
+                    while (qh < 255.0f && plo[a] + qh * scale[a] < chi[a]) qh += 1.0f;
+                    qlo[a][sl] = (uint32_t)ql;
+                    qhi[a][sl] = (uint32_t)qh;
+                }
+                const uint32_t ct = subTris(c);
+                if (ct > LEAF) {
+                    meta[sl] = 0x20u | (24u + (uint32_t)sl);
+                    imask |= 1u << sl;
+                    fifo.push_back(c);
+                } else {
+                    meta[sl] = (((1u << ct) - 1u) << 5) | off;
+                    const uint32_t first = subFirst(c);
+                    for (uint32_t j = 0; j < ct; j++) triOrder[triBase + off + j] = L.order[first + j];
+                    off += ct;
+                }
+            }
+            auto pack4 = [](const uint32_t *b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
+            uint32_t w[20];
+            w[0] = floatToBits(rb.lo.x);
+            w[1] = floatToBits(rb.lo.y);
+            w[2] = floatToBits(rb.lo.z);
+            w[3] = e[0] | (e[1] << 8) | (e[2] << 16) | (imask << 24);
+            w[4] = childBase;
+            w[5] = triBase;
+            w[6] = pack4(meta);
+            w[7] = pack4(meta + 4);
+            for (int a = 0; a < 3; a++) {
+                w[8 + 2 * a] = pack4(qlo[a]);
+                w[9 + 2 * a] = pack4(qlo[a] + 4);
+                w[14 + 2 * a] = pack4(qhi[a]);
+                w[15 + 2 * a] = pack4(qhi[a] + 4);
+            }
+            words.insert(words.end(), w, w + 20);
+            triBase += off;
+        }
+        nNodes = fifo.size();
     }
 };
 

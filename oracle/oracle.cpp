@@ -1094,6 +1094,18 @@ PTC_API int ptc_get_lbvh(ptc_ctx *c, uint64_t *n_out, uint64_t *morton, uint32_t
     return 0;
 }
 
+PTC_API int ptc_get_wide_bvh(ptc_ctx *c, uint64_t *n_nodes_out, uint64_t *n_tris_out, uint32_t *node_words, uint32_t *tri_order) {
+    if (!c) return 1;
+    if (c->lbvh.n != c->tris.size() || c->lbvh.morton.empty()) c->lbvh.build(c->tris);
+    WideBVH W;
+    W.build(c->lbvh);
+    if (n_nodes_out) *n_nodes_out = W.nNodes;
+    if (n_tris_out) *n_tris_out = c->lbvh.n;
+    if (node_words) std::copy(W.words.begin(), W.words.end(), node_words);
+    if (tri_order) std::copy(W.triOrder.begin(), W.triOrder.end(), tri_order);
+    return 0;
+}
+
 PTC_API int ptc_bsdf_eval(ptc_ctx *, int n, const float *params, const float *wi, const float *wo, float *out_f, float *out_pdf) {
     for (int i = 0; i < n; i++) {
         PBRStandard pbr{vec3(params[i * 5], params[i * 5 + 1], params[i * 5 + 2]), params[i * 5 + 3], params[i * 5 + 4]};

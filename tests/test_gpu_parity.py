@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from imgmetrics import mean_lum_ratio, mse, p99_rel_err, rgbe_roundtrip
-from test_oracle_units import check_lbvh, look_down_params, make_quad_scene
+from test_oracle_units import check_lbvh, check_wide_bvh, look_down_params, make_quad_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -55,6 +55,26 @@ def test_lbvh_bit_exact(capi, engine, scene, kw):
     orc.close()
 
 
+@pytest.mark.parametrize("scene,kw", [("Volume5", {}), ("Cornell", {}), ("MeshLight", {}), ("SharedComponents", {}), ("Hierarchy", {}),
+                                      ("Atrium", dict(texture_size=4, scale=0.3)), ("Atrium", dict(texture_size=4, scale=1.0))])
+def test_wide_bvh_bit_exact(capi, engine, scene, kw):
+    """The on-device collapse of the LBVH into the 8-wide compressed BVH equals the CPU reference collapse byte for byte:
+    same children per node, same octant slots, same exponents and quantised boxes, same breadth-first numbering, same
+    triangle order."""
+    engine.build_scene(scene, **kw)
+    cu, orc = both(capi, engine.scene_desc())
+    a, b = cu.get_wide_bvh(), orc.get_wide_bvh()
+    assert a["n_tris"] == b["n_tris"] > 0 and a["n_nodes"] == b["n_nodes"] > 0
+    assert np.array_equal(a["tri_order"], b["tri_order"])
+    diff = np.any(a["words"] != b["words"], axis=1)
+    assert not diff.any(), "wide nodes differ: %d of %d, first %d" % (int(diff.sum()), len(diff), int(np.argmax(diff)))
+    if a["n_tris"] < 50000:
+        check_wide_bvh(a, cu.get_lbvh())
+    assert cu.stats()["n_bvh_nodes"] == a["n_nodes"]
+    cu.close()
+    orc.close()
+
+
 def test_lbvh_single_triangle_and_empty(capi):
     d, keep = make_quad_scene(capi)
     keep[2][0].tri_count = 1
@@ -62,6 +82,8 @@ def test_lbvh_single_triangle_and_empty(capi):
     cu, orc = both(capi, C.byref(d))
     a, b = cu.get_lbvh(), orc.get_lbvh()
     assert a["n"] == b["n"] == 1 and np.array_equal(a["aabb"], b["aabb"]) and np.array_equal(a["morton"], b["morton"])
+    wa, wb = cu.get_wide_bvh(), orc.get_wide_bvh()
+    assert wa["n_nodes"] == wb["n_nodes"] == 1 and np.array_equal(wa["words"], wb["words"]) and np.array_equal(wa["tri_order"], wb["tri_order"])
     rays = np.array([[-0.5, 2, 0.5, 1e-3, 0, -1, 0, 1e4], [0.9, 2, -0.9, 1e-3, 0, -1, 0, 1e4]], np.float32)
     ra, rb = cu.trace_closest(rays), orc.trace_closest(rays)
     assert np.array_equal(ra[0], rb[0]) and np.allclose(ra[2], rb[2])
@@ -69,7 +91,7 @@ def test_lbvh_single_triangle_and_empty(capi):
     orc.close()
     e = capi.ptc_scene_desc()
     cu, orc = both(capi, C.byref(e))
-    assert cu.get_lbvh()["n"] == 0
+    assert cu.get_lbvh()["n"] == 0 and cu.get_wide_bvh()["n_nodes"] == 0
     ra = cu.trace_closest(rays)
     assert list(ra[0]) == [-1, -1]
     ia, _, _ = cu.render(look_down_params(capi, bg=(0.25, 0.5, 0.75)))

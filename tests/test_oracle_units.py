@@ -316,6 +316,83 @@ def test_oracle_lbvh_63bit_for_large_scenes(capi, oracle_lib):
     eng.close()
 
 
+def decode_wide_node(w):
+    """80-byte wide node (20 uint32) -> dict; layout documented in vviewer_b200/csrc/lbvh.cuh."""
+    w = np.asarray(w, np.uint32)
+    p = w[:3].view(np.float32)
+    e = [(int(w[3]) >> (8 * a)) & 0xff for a in range(3)]
+    scale = np.array([2.0 ** (x - 127) for x in e], np.float32)
+    by = w[6:20].view(np.uint8)
+    meta = by[0:8]
+    q = by[8:].reshape(6, 8).astype(np.float32)  # qlo x,y,z then qhi x,y,z
+    # the build guarantees conservativeness of the box as reconstructed in single precision (q * 2^e is exact, one rounded add)
+    lo = p[None, :] + q[0:3].T * scale[None, :]
+    hi = p[None, :] + q[3:6].T * scale[None, :]
+    return dict(p=p, imask=int(w[3]) >> 24, child_base=int(w[4]), tri_base=int(w[5]), meta=meta, lo=lo, hi=hi, q=q)
+
+
+def check_wide_bvh(W, L):
+    """Structural invariants of the 8-wide compressed BVH against the binary LBVH it was collapsed from."""
+    n, nn = W["n_tris"], W["n_nodes"]
+    assert n == L["n"]
+    if n == 0:
+        assert nn == 0
+        return
+    assert sorted(W["tri_order"].tolist()) == list(range(n))
+    # bounds of every world triangle from the LBVH leaves
+    tri_box = np.zeros((n, 6), np.float32)
+    tri_box[L["order"]] = L["aabb"][n - 1:]
+    next_child, next_tri, visited = 1, 0, 0
+    for i in range(nn):  # breadth-first numbering: children and triangles are handed out in node order
+        nd = decode_wide_node(W["words"][i])
+        inner = [s for s in range(8) if (nd["meta"][s] >> 5) == 1 and (nd["meta"][s] & 0x1f) >= 24]
+        assert nd["imask"] == sum(1 << s for s in inner)
+        for s in inner:
+            assert (nd["meta"][s] & 0x1f) == 24 + s
+        if inner:
+            assert nd["child_base"] == next_child
+        ntri = 0
+        for s in range(8):
+            m = int(nd["meta"][s])
+            if m == 0:
+                assert nd["q"][0, s] == 255 and nd["q"][3, s] == 0  # empty slot: inverted box
+                continue
+            if s in inner:
+                ch = decode_wide_node(W["words"][nd["child_base"] + inner.index(s)])
+                assert np.all(nd["lo"][s] <= ch["p"])
+                continue
+            cnt = {1: 1, 3: 2, 7: 3}[m >> 5]
+            off = m & 0x1f
+            assert off == ntri and off + cnt <= 24
+            for k in range(cnt):
+                b = tri_box[W["tri_order"][nd["tri_base"] + off + k]]
+                assert np.all(nd["lo"][s] <= b[:3]) and np.all(nd["hi"][s] >= b[3:]), (i, s, nd["lo"][s], nd["hi"][s], b)
+            ntri += cnt
+        if ntri:
+            assert nd["tri_base"] == next_tri
+        next_child += len(inner)
+        next_tri += ntri
+        visited += 1
+    assert next_child == nn and next_tri == n
+
+
+@pytest.mark.parametrize("scene,kw", [("Volume5", {}), ("Cornell", {}), ("Hierarchy", {}), ("Atrium", dict(texture_size=4, scale=0.05))])
+def test_oracle_wide_bvh_invariants(capi, oracle_lib, scene, kw):
+    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng.build_scene(scene, **kw)
+    ctx = capi.Context(oracle_lib)
+    ctx.upload_scene(eng.scene_desc())
+    ctx.build_accel()
+    W, L = ctx.get_wide_bvh(), ctx.get_lbvh()
+    check_wide_bvh(W, L)
+    if L["n"] > 64:
+        # the collapse must actually widen the tree: on average more than 3 children per node
+        kids = sum(int(np.count_nonzero(decode_wide_node(w)["meta"])) for w in W["words"])
+        assert kids / W["n_nodes"] > 3.0
+    ctx.close()
+    eng.close()
+
+
 def test_morton_bit_expansion_reference():
     # the magic-number expansions used on both sides equal the naive bit loop
     def e21(v):

@@ -94,7 +94,7 @@ PTC_FLAG_TIME_KERNELS = 2
 
 # every symbol include/ptc.h declares
 PTC_SYMBOLS = ["ptc_create", "ptc_destroy", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_build_accel", "ptc_render",
-               "ptc_render_device", "ptc_progress", "ptc_get_stats", "ptc_trace_closest", "ptc_get_lbvh", "ptc_bsdf_eval",
+               "ptc_render_device", "ptc_progress", "ptc_get_stats", "ptc_trace_closest", "ptc_get_lbvh", "ptc_get_wide_bvh", "ptc_bsdf_eval",
                "ptc_bsdf_sample", "ptc_env_lookup"]
 VH_SYMBOLS = ["vh_engine_create", "vh_engine_destroy", "vh_backend_ok", "vh_last_error", "vh_scene_list", "vh_build_scene",
               "vh_set_render_info", "vh_get_render_info", "vh_scene_desc", "vh_render_params", "vh_render_to_memory", "vh_render",
@@ -130,6 +130,8 @@ def _declare_ptc(lib):
     lib.ptc_trace_closest.restype = C.c_int
     lib.ptc_get_lbvh.argtypes = [vp, C.POINTER(u64), vp, vp, vp, vp, vp, vp]
     lib.ptc_get_lbvh.restype = C.c_int
+    lib.ptc_get_wide_bvh.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), vp, vp]
+    lib.ptc_get_wide_bvh.restype = C.c_int
     lib.ptc_bsdf_eval.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
     lib.ptc_bsdf_eval.restype = C.c_int
     lib.ptc_bsdf_sample.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
@@ -294,6 +296,17 @@ class Context:
             k = u64(0)
             self._check(self.lib.ptc_get_lbvh(self.ctx, C.byref(k), np_ptr(out["morton"]), np_ptr(out["order"]), np_ptr(out["parent"]),
                                               np_ptr(out["left"]), np_ptr(out["right"]), np_ptr(out["aabb"])), "ptc_get_lbvh")
+        return out
+
+    def get_wide_bvh(self):
+        """8-wide compressed BVH: words (n_nodes, 20) uint32 and tri_order (n_tris,) uint32."""
+        nn, nt = u64(0), u64(0)
+        self._check(self.lib.ptc_get_wide_bvh(self.ctx, C.byref(nn), C.byref(nt), None, None), "ptc_get_wide_bvh")
+        out = dict(n_nodes=int(nn.value), n_tris=int(nt.value), words=np.zeros((int(nn.value), 20), np.uint32),
+                   tri_order=np.zeros(int(nt.value), np.uint32))
+        if out["n_nodes"]:
+            self._check(self.lib.ptc_get_wide_bvh(self.ctx, C.byref(nn), C.byref(nt), np_ptr(out["words"]), np_ptr(out["tri_order"])),
+                        "ptc_get_wide_bvh")
         return out
 
     def bsdf_eval(self, params, wi, wo):

@@ -70,10 +70,10 @@ struct DScene {
     uint32_t nInstances, nMaterials, nLightInstances, nTextures;
     uint32_t hasCubemap;
     /* acceleration structure (see lbvh.cuh) */
-    const float4 *bvhNodes; /* 4 x float4 per internal node */
-    const float4 *tris;     /* 3 x float4 per world triangle, Morton order */
+    const float4 *bvhNodes; /* 5 x float4 per 8-wide compressed node, breadth first, node 0 = root */
+    const float4 *tris;     /* 3 x float4 per world triangle, wide-node order */
     uint32_t nTris;
-    int32_t rootIsLeaf; /* 1 when the scene has a single triangle */
+    uint32_t nWideNodes;
     /* scene-level switches that let whole ray types be skipped without changing any result */
     uint32_t anyEmissive;    /* some instanced material can pass the probe's emissive test */
     uint32_t anyTransparent; /* some instanced material has the transparent flag */

@@ -11,13 +11,19 @@
  *   radix sort  stable LSD sort of (code, triangle id) pairs
  *   k_karras    Karras 2012 hierarchy, ties broken by sorted index
  *   k_fit       bottom-up AABB fit with per-node arrival counters
- *   k_emit      traversal nodes (both children's boxes in one 64 B record) + Morton-ordered triangles
+ *   collapse    binary LBVH -> 8-wide compressed BVH (80 B nodes: origin, per-axis power-of-two scale, 8-bit
+ *               quantised child boxes, octant-ordered child slots; leaves of <= 3 triangles), level by level
+ *               (k_wide_select -> inclusive scan -> k_wide_emit) so that node and triangle numbering is
+ *               deterministic (breadth first); layout after Ylitie, Karras, Laine 2017
+ *   k_gather    triangles in wide-node order
  *
- * Every step is bit-exact against the CPU reference build in oracle/accel.hpp (tests/test_lbvh_parity.py).
+ * Every step is bit-exact against the CPU reference build in oracle/accel.hpp
+ * (tests/test_gpu_parity.py::test_lbvh_bit_exact, ::test_wide_bvh_bit_exact).
  */
 #pragma once
 #include "common.cuh"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 namespace lbvh {
 
@@ -136,6 +142,8 @@ __global__ void k_morton(const float4 *__restrict__ boundsLo, const float4 *__re
     ids[i] = i;
 }
 
+#define WIDE_LEAF_TRIS 3 /* triangles per leaf of the wide BVH */
+
 /* common-prefix length of sorted keys i and j; equal keys fall back to the index (Karras 2012, section 4) */
 PTC_D int delta(const uint64_t *__restrict__ keys, int64_t n, int64_t i, int64_t j) {
     if (j < 0 || j >= n) return -1;
@@ -146,7 +154,7 @@ PTC_D int delta(const uint64_t *__restrict__ keys, int64_t n, int64_t i, int64_t
 
 /* node numbering: internal 0..n-2, leaf k -> n-1+k */
 __global__ void k_karras(const uint64_t *__restrict__ keys, uint32_t n, int32_t *__restrict__ parent, int32_t *__restrict__ left,
-                         int32_t *__restrict__ right) {
+                         int32_t *__restrict__ right, int32_t *__restrict__ rangeEnd, uint32_t *__restrict__ bigNodes) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= (int64_t)n - 1) return;
     int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -171,6 +179,8 @@ __global__ void k_karras(const uint64_t *__restrict__ keys, uint32_t n, int32_t 
     right[i] = R;
     parent[L] = (int32_t)i;
     parent[R] = (int32_t)i;
+    rangeEnd[i] = (int32_t)j; /* node i covers the sorted range [min(i, j), max(i, j)] */
+    if (hi - lo + 1 > WIDE_LEAF_TRIS) atomicAdd(bigNodes, 1u); /* upper bound of the wide node count */
 }
 
 /* bottom-up fit: the second thread to arrive at a node owns it (fmin/fmax are exact, so order is irrelevant) */
@@ -199,54 +209,254 @@ __global__ void k_fit(uint32_t n, const uint32_t *__restrict__ order, const floa
     }
 }
 
-/* traversal records. Internal node i = 4 x float4:
- *   n0 = (L.lo.x, L.hi.x, L.lo.y, L.hi.y)   n1 = (R.lo.x, R.hi.x, R.lo.y, R.hi.y)
- *   n2 = (L.lo.z, L.hi.z, R.lo.z, R.hi.z)   n3 = (bits(childL), bits(childR), 0, 0)
- * child >= 0: internal node index; child < 0: ~(sorted triangle position). */
-__global__ void k_emit_nodes(uint32_t n, const int32_t *__restrict__ left, const int32_t *__restrict__ right, const float4 *__restrict__ nodeLo,
-                             const float4 *__restrict__ nodeHi, float4 *__restrict__ out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i + 1 >= n) return;
-    int32_t L = left[i], R = right[i];
-    float4 llo = nodeLo[L], lhi = nodeHi[L], rlo = nodeLo[R], rhi = nodeHi[R];
-    int32_t cl = L >= (int32_t)(n - 1) ? ~(L - (int32_t)(n - 1)) : L;
-    int32_t cr = R >= (int32_t)(n - 1) ? ~(R - (int32_t)(n - 1)) : R;
-    out[4 * (size_t)i + 0] = make_float4(llo.x, lhi.x, llo.y, lhi.y);
-    out[4 * (size_t)i + 1] = make_float4(rlo.x, rhi.x, rlo.y, rhi.y);
-    out[4 * (size_t)i + 2] = make_float4(llo.z, lhi.z, rlo.z, rhi.z);
-    out[4 * (size_t)i + 3] = make_float4(__int_as_float(cl), __int_as_float(cr), 0.0f, 0.0f);
+/* ------------------------------------------------------------------ collapse to the 8-wide compressed BVH
+ * Wide node = 80 B = 5 x 128-bit words (20 x u32):
+ *   w0..2  origin p = node box lo (float bits)          w3   ex | ey << 8 | ez << 16 | imask << 24
+ *   w4     index of the first internal child            w5   position of the node's first triangle
+ *   w6,7   meta[8]: internal child in slot s -> 0x20 | (24 + s); leaf -> (unary triangle count) << 5 | offset; empty 0
+ *   w8,9   qlo.x[8]   w10,11 qlo.y[8]   w12,13 qlo.z[8]   w14,15 qhi.x[8]   w16,17 qhi.y[8]   w18,19 qhi.z[8]
+ * child box = p + q * 2^(e - 127), conservative.  ex/ey/ez are biased exponent bytes; imask marks the internal slots.
+ * Internal children of a node are consecutive (slot order) starting at w4; triangles of its leaf children are
+ * consecutive (slot order) starting at w5.  Node 0 is the root; numbering is breadth first.
+ *
+ * Children of a wide node: start from {binary root}; while fewer than 8, open the child of largest half-area with more
+ * than 3 triangles (first wins ties; the opened child is replaced by its left child, the right child is appended);
+ * then the same with "more than 1 triangle".  Children with more than 3 triangles become wide nodes, the rest leaves.
+ * Slots: greedy assignment maximising dot(child centre - node centre, (+-1, +-1, +-1)_slot), so that the slot equal to
+ * the ray's direction-sign octant holds the nearest child. */
+struct WideTmp {
+    int32_t slotChild[8];
+};
+
+PTC_D uint32_t subTris(int32_t node, uint32_t n, const int32_t *__restrict__ rangeEnd) {
+    if (node >= (int32_t)(n - 1)) return 1u;
+    const int32_t j = rangeEnd[node];
+    return (uint32_t)(j > node ? j - node : node - j) + 1u;
+}
+PTC_D uint32_t subFirst(int32_t node, uint32_t n, const int32_t *__restrict__ rangeEnd) {
+    if (node >= (int32_t)(n - 1)) return (uint32_t)(node - (int32_t)(n - 1));
+    const int32_t j = rangeEnd[node];
+    return (uint32_t)(j < node ? j : node);
+}
+PTC_D float halfArea(float4 lo, float4 hi) {
+    const float ex = __fsub_rn(hi.x, lo.x), ey = __fsub_rn(hi.y, lo.y), ez = __fsub_rn(hi.z, lo.z);
+    return __fadd_rn(__fadd_rn(__fmul_rn(ex, ey), __fmul_rn(ey, ez)), __fmul_rn(ez, ex));
 }
 
-__global__ void k_gather_tris(uint32_t n, const uint32_t *__restrict__ order, const float4 *__restrict__ in, float4 *__restrict__ out) {
+/* one thread per wide node of the current level: choose children and slots, count internal children / triangles */
+__global__ void k_wide_select(uint32_t n, uint32_t count, uint32_t levelBase, const int32_t *__restrict__ rootOf, const int32_t *__restrict__ left,
+                              const int32_t *__restrict__ right, const int32_t *__restrict__ rangeEnd, const float4 *__restrict__ nodeLo,
+                              const float4 *__restrict__ nodeHi, WideTmp *__restrict__ tmp, unsigned long long *__restrict__ counts) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int32_t root = rootOf[levelBase + k];
+    int32_t list[8];
+    uint32_t tris[8];
+    float area[8];
+    int len = 1;
+    list[0] = root;
+    tris[0] = subTris(root, n, rangeEnd);
+    area[0] = halfArea(nodeLo[root], nodeHi[root]);
+    for (int phase = 0; phase < 2; phase++) {
+        const uint32_t thr = phase == 0 ? (uint32_t)WIDE_LEAF_TRIS : 1u;
+        while (len < 8) {
+            int bi = -1;
+            float ba = -1.0f;
+            for (int i = 0; i < len; i++)
+                if (tris[i] > thr && area[i] > ba) {
+                    ba = area[i];
+                    bi = i;
+                }
+            if (bi < 0) break;
+            const int32_t c = list[bi], L = left[c], R = right[c];
+            list[bi] = L;
+            tris[bi] = subTris(L, n, rangeEnd);
+            area[bi] = halfArea(nodeLo[L], nodeHi[L]);
+            list[len] = R;
+            tris[len] = subTris(R, n, rangeEnd);
+            area[len] = halfArea(nodeLo[R], nodeHi[R]);
+            len++;
+        }
+    }
+    /* slot assignment */
+    const float4 rlo = nodeLo[root], rhi = nodeHi[root];
+    const float ncx = __fmul_rn(__fadd_rn(rlo.x, rhi.x), 0.5f), ncy = __fmul_rn(__fadd_rn(rlo.y, rhi.y), 0.5f), ncz = __fmul_rn(__fadd_rn(rlo.z, rhi.z), 0.5f);
+    float vx[8], vy[8], vz[8];
+    for (int i = 0; i < len; i++) {
+        const float4 lo = nodeLo[list[i]], hi = nodeHi[list[i]];
+        vx[i] = __fsub_rn(__fmul_rn(__fadd_rn(lo.x, hi.x), 0.5f), ncx);
+        vy[i] = __fsub_rn(__fmul_rn(__fadd_rn(lo.y, hi.y), 0.5f), ncy);
+        vz[i] = __fsub_rn(__fmul_rn(__fadd_rn(lo.z, hi.z), 0.5f), ncz);
+    }
+    int32_t slotChild[8];
+    for (int s = 0; s < 8; s++) slotChild[s] = -1;
+    uint32_t childDone = 0, slotDone = 0;
+    for (int it = 0; it < len; it++) {
+        int bc = -1, bs = -1;
+        float bcost = 0.0f;
+        for (int c = 0; c < len; c++) {
+            if (childDone & (1u << c)) continue;
+            for (int sl = 0; sl < 8; sl++) {
+                if (slotDone & (1u << sl)) continue;
+                const float cost = __fadd_rn(__fadd_rn((sl & 4) ? vx[c] : -vx[c], (sl & 2) ? vy[c] : -vy[c]), (sl & 1) ? vz[c] : -vz[c]);
+                if (bc < 0 || cost > bcost) {
+                    bcost = cost;
+                    bc = c;
+                    bs = sl;
+                }
+            }
+        }
+        childDone |= 1u << bc;
+        slotDone |= 1u << bs;
+        slotChild[bs] = list[bc];
+    }
+    uint32_t nInternal = 0, nTris = 0;
+    WideTmp t;
+    for (int sl = 0; sl < 8; sl++) {
+        const int32_t c = slotChild[sl];
+        t.slotChild[sl] = c;
+        if (c < 0) continue;
+        const uint32_t ct = subTris(c, n, rangeEnd);
+        if (ct > (uint32_t)WIDE_LEAF_TRIS) nInternal++; else nTris += ct;
+    }
+    tmp[levelBase + k] = t;
+    counts[k] = (unsigned long long)nInternal | ((unsigned long long)nTris << 32);
+}
+
+/* biased exponent byte e with extent <= 255 * 2^(e - 127) */
+PTC_D uint32_t wideExponent(float extent) {
+    const float s = __fdiv_rn(extent, 255.0f);
+    const uint32_t b = __float_as_uint(s);
+    uint32_t e = (b >> 23) & 0xffu;
+    if (b & 0x7fffffu) e++;
+    if (e < 1u) e = 1u;
+    if (e > 253u) e = 253u;
+    return e;
+}
+PTC_D float pow2Biased(uint32_t e) { return __uint_as_float(e << 23); }
+
+__global__ void k_wide_emit(uint32_t n, uint32_t count, uint32_t levelBase, uint32_t nextBase, uint32_t levelTriBase, int32_t *__restrict__ rootOf,
+                            const int32_t *__restrict__ rangeEnd, const float4 *__restrict__ nodeLo, const float4 *__restrict__ nodeHi,
+                            const WideTmp *__restrict__ tmp, const unsigned long long *__restrict__ counts,
+                            const unsigned long long *__restrict__ inclusive, uint4 *__restrict__ wide, uint32_t *__restrict__ triMap) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const unsigned long long excl = inclusive[k] - counts[k];
+    const uint32_t childBase = nextBase + (uint32_t)(excl & 0xffffffffull);
+    const uint32_t triBase = levelTriBase + (uint32_t)(excl >> 32);
+    const uint32_t id = levelBase + k;
+    const int32_t root = rootOf[id];
+    const WideTmp t = tmp[id];
+    const float4 lo = nodeLo[root], hi = nodeHi[root];
+    const float plo[3] = {lo.x, lo.y, lo.z}, phi[3] = {hi.x, hi.y, hi.z};
+    uint32_t e[3];
+    float scale[3], inv[3];
+    for (int a = 0; a < 3; a++) {
+        const float extent = __fsub_rn(phi[a], plo[a]);
+        uint32_t ee = wideExponent(extent);
+        while (ee < 253u && __fmul_rn(extent, pow2Biased(254u - ee)) > 255.0f) ee++;
+        e[a] = ee;
+        scale[a] = pow2Biased(ee);
+        inv[a] = pow2Biased(254u - ee);
+    }
+    uint32_t meta[8], qlo[3][8], qhi[3][8];
+    uint32_t imask = 0, rank = 0, off = 0;
+    for (int sl = 0; sl < 8; sl++) {
+        const int32_t c = t.slotChild[sl];
+        if (c < 0) {
+            meta[sl] = 0;
+            for (int a = 0; a < 3; a++) {
+                qlo[a][sl] = 255u;
+                qhi[a][sl] = 0u;
+            }
+            continue;
+        }
+        const float4 clo4 = nodeLo[c], chi4 = nodeHi[c];
+        const float clo[3] = {clo4.x, clo4.y, clo4.z}, chi[3] = {chi4.x, chi4.y, chi4.z};
+        for (int a = 0; a < 3; a++) {
+            float ql = floorf(__fmul_rn(__fsub_rn(clo[a], plo[a]), inv[a]));
+            ql = fminf(fmaxf(ql, 0.0f), 255.0f);
+            while (ql > 0.0f && __fadd_rn(plo[a], __fmul_rn(ql, scale[a])) > clo[a]) ql -= 1.0f;
+            float qh = ceilf(__fmul_rn(__fsub_rn(chi[a], plo[a]), inv[a]));
+            qh = fminf(fmaxf(qh, 0.0f), 255.0f);
+            while (qh < 255.0f && __fadd_rn(plo[a], __fmul_rn(qh, scale[a])) < chi[a]) qh += 1.0f;
+            qlo[a][sl] = (uint32_t)ql;
+            qhi[a][sl] = (uint32_t)qh;
+        }
+        const uint32_t ct = subTris(c, n, rangeEnd);
+        if (ct > (uint32_t)WIDE_LEAF_TRIS) {
+            meta[sl] = 0x20u | (24u + (uint32_t)sl);
+            imask |= 1u << sl;
+            rootOf[childBase + rank] = c;
+            rank++;
+        } else {
+            meta[sl] = (((1u << ct) - 1u) << 5) | off;
+            const uint32_t first = subFirst(c, n, rangeEnd);
+            for (uint32_t j = 0; j < ct; j++) triMap[triBase + off + j] = first + j;
+            off += ct;
+        }
+    }
+    auto pack4 = [](const uint32_t *b) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
+    uint4 w0, w1, w2, w3, w4;
+    w0.x = __float_as_uint(lo.x);
+    w0.y = __float_as_uint(lo.y);
+    w0.z = __float_as_uint(lo.z);
+    w0.w = e[0] | (e[1] << 8) | (e[2] << 16) | (imask << 24);
+    w1.x = childBase;
+    w1.y = triBase;
+    w1.z = pack4(meta);
+    w1.w = pack4(meta + 4);
+    w2 = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
+    w3 = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
+    w4 = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+    uint4 *out = wide + 5 * (size_t)id;
+    out[0] = w0;
+    out[1] = w1;
+    out[2] = w2;
+    out[3] = w3;
+    out[4] = w4;
+}
+
+/* triangles in wide-node order: position k holds sorted triangle triMap[k] = world triangle order[triMap[k]] */
+__global__ void k_gather_tris(uint32_t n, const uint32_t *__restrict__ triMap, const uint32_t *__restrict__ order, const float4 *__restrict__ in,
+                              float4 *__restrict__ out, uint32_t *__restrict__ wideOrder) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    uint32_t t = order[k];
+    uint32_t t = order[triMap[k]];
     float4 a = in[3 * (size_t)t + 0], b = in[3 * (size_t)t + 1], c = in[3 * (size_t)t + 2];
     c.w = __uint_as_float(t); /* world triangle id: the tie-break key of the hit rule */
     out[3 * (size_t)k + 0] = a;
     out[3 * (size_t)k + 1] = b;
     out[3 * (size_t)k + 2] = c;
+    wideOrder[k] = t;
 }
 
 struct Build {
-    DBuf<float4> trisUnsorted, trisSorted, triLo, triHi, nodeLo, nodeHi, nodes;
+    DBuf<float4> trisUnsorted, trisSorted, triLo, triHi, nodeLo, nodeHi;
+    DBuf<uint4> wide;              /* 5 x uint4 per wide node */
     DBuf<uint64_t> keys, keysSorted;
-    DBuf<uint32_t> ids, order, arrivals, sceneBounds;
-    DBuf<int32_t> parent, left, right;
-    DBuf<uint8_t> sortTemp;
+    DBuf<uint32_t> ids, order, arrivals, sceneBounds, triMap, wideOrder, bigNodes;
+    DBuf<int32_t> parent, left, right, rangeEnd, rootOf;
+    DBuf<WideTmp> wideTmp;
+    DBuf<unsigned long long> counts, inclusive;
+    DBuf<uint8_t> sortTemp, scanTemp;
     uint32_t n = 0;
+    uint32_t nWide = 0, wideLevels = 0;
     int bits = 0;
 
     size_t bytes() const {
-        return trisUnsorted.bytes() + trisSorted.bytes() + triLo.bytes() + triHi.bytes() + nodeLo.bytes() + nodeHi.bytes() + nodes.bytes() +
+        return trisUnsorted.bytes() + trisSorted.bytes() + triLo.bytes() + triHi.bytes() + nodeLo.bytes() + nodeHi.bytes() + wide.bytes() +
                keys.bytes() + keysSorted.bytes() + ids.bytes() + order.bytes() + arrivals.bytes() + parent.bytes() + left.bytes() +
-               right.bytes() + sortTemp.bytes();
+               right.bytes() + sortTemp.bytes() + triMap.bytes() + wideOrder.bytes() + rangeEnd.bytes() + rootOf.bytes() + wideTmp.bytes() +
+               counts.bytes() + inclusive.bytes() + scanTemp.bytes();
     }
+    size_t traversalBytes() const { return (size_t)nWide * 80 + (size_t)n * 48; }
 
     /* returns the number of kernel launches */
     int run(const ptc_vertex *vertices, const uint32_t *indices, const DInstance *instances, uint32_t nInstances, uint32_t nTris,
             cudaStream_t s) {
         n = nTris;
+        nWide = wideLevels = 0;
         if (n == 0) return 0;
         const int B = 256;
         const uint32_t G = (n + B - 1) / B;
@@ -262,17 +472,21 @@ struct Build {
         parent.alloc(nn);
         left.alloc(nn);
         right.alloc(nn);
+        rangeEnd.alloc(n);
         nodeLo.alloc(nn);
         nodeHi.alloc(nn);
         arrivals.alloc(n);
-        nodes.alloc(4 * (size_t)(n > 1 ? n - 1 : 1));
+        triMap.alloc(n);
+        wideOrder.alloc(n);
         sceneBounds.alloc(6);
+        bigNodes.alloc(1);
         uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
         CUDA_TRY(cudaMemcpyAsync(sceneBounds.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemsetAsync(parent.p, 0xff, nn * sizeof(int32_t), s));
         CUDA_TRY(cudaMemsetAsync(left.p, 0xff, nn * sizeof(int32_t), s));
         CUDA_TRY(cudaMemsetAsync(right.p, 0xff, nn * sizeof(int32_t), s));
         CUDA_TRY(cudaMemsetAsync(arrivals.p, 0, n * sizeof(uint32_t), s));
+        CUDA_TRY(cudaMemsetAsync(bigNodes.p, 0, sizeof(uint32_t), s));
         int launches = 0;
         k_flatten<<<G, B, 0, s>>>(vertices, indices, instances, nInstances, n, trisUnsorted.p, triLo.p, triHi.p, sceneBounds.p);
         launches++;
@@ -286,16 +500,49 @@ struct Build {
         CUDA_TRY(cub::DeviceRadixSort::SortPairs(sortTemp.p, tempBytes, keys.p, keysSorted.p, ids.p, order.p, (int)n, 0, endBit, s));
         launches += (endBit + 7) / 8 * 2 + 1;
         if (n > 1) {
-            k_karras<<<(n - 1 + B - 1) / B, B, 0, s>>>(keysSorted.p, n, parent.p, left.p, right.p);
+            k_karras<<<(n - 1 + B - 1) / B, B, 0, s>>>(keysSorted.p, n, parent.p, left.p, right.p, rangeEnd.p, bigNodes.p);
             launches++;
         }
         k_fit<<<G, B, 0, s>>>(n, order.p, triLo.p, triHi.p, parent.p, left.p, right.p, nodeLo.p, nodeHi.p, arrivals.p);
         launches++;
-        if (n > 1) {
-            k_emit_nodes<<<(n - 1 + B - 1) / B, B, 0, s>>>(n, left.p, right.p, nodeLo.p, nodeHi.p, nodes.p);
-            launches++;
+
+        /* ---- collapse, one level at a time */
+        uint32_t big = 0;
+        CUDA_TRY(cudaMemcpyAsync(&big, bigNodes.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        const size_t maxWide = (size_t)big + 1; /* every wide node but the root is rooted at a distinct binary node with > 3 triangles */
+        wide.alloc(5 * maxWide);
+        wideTmp.alloc(maxWide);
+        rootOf.alloc(maxWide);
+        counts.alloc(maxWide);
+        inclusive.alloc(maxWide);
+        size_t scanBytes = 0;
+        cub::DeviceScan::InclusiveSum(nullptr, scanBytes, counts.p, inclusive.p, (int)maxWide, s);
+        scanTemp.alloc(scanBytes);
+        const int32_t binaryRoot = 0; /* internal node 0 is the root; a single triangle is leaf node 0 = n - 1 */
+        CUDA_TRY(cudaMemcpyAsync(rootOf.p, &binaryRoot, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        uint32_t levelBase = 0, levelCount = 1, triBase = 0;
+        while (levelCount > 0) {
+            if ((size_t)levelBase + levelCount > maxWide) throw CudaError{"wide BVH collapse exceeded its node bound"};
+            const uint32_t g = (levelCount + 127) / 128;
+            k_wide_select<<<g, 128, 0, s>>>(n, levelCount, levelBase, rootOf.p, left.p, right.p, rangeEnd.p, nodeLo.p, nodeHi.p, wideTmp.p, counts.p);
+            size_t sb = scanBytes;
+            CUDA_TRY(cub::DeviceScan::InclusiveSum(scanTemp.p, sb, counts.p, inclusive.p, (int)levelCount, s));
+            const uint32_t nextBase = levelBase + levelCount;
+            k_wide_emit<<<g, 128, 0, s>>>(n, levelCount, levelBase, nextBase, triBase, rootOf.p, rangeEnd.p, nodeLo.p, nodeHi.p, wideTmp.p, counts.p,
+                                         inclusive.p, wide.p, triMap.p);
+            launches += 3;
+            unsigned long long total = 0;
+            CUDA_TRY(cudaMemcpyAsync(&total, inclusive.p + (levelCount - 1), sizeof(total), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            triBase += (uint32_t)(total >> 32);
+            levelBase = nextBase;
+            levelCount = (uint32_t)(total & 0xffffffffull);
+            wideLevels++;
         }
-        k_gather_tris<<<G, B, 0, s>>>(n, order.p, trisUnsorted.p, trisSorted.p);
+        nWide = levelBase;
+        if (triBase != n) throw CudaError{"wide BVH collapse lost triangles"};
+        k_gather_tris<<<G, B, 0, s>>>(n, triMap.p, order.p, trisUnsorted.p, trisSorted.p, wideOrder.p);
         launches++;
         CUDA_TRY(cudaGetLastError());
         return launches;

@@ -121,10 +121,10 @@ DScene makeDScene(ptc_ctx *c) {
     s.nLightInstances = c->nLightInstances;
     s.nTextures = c->nTextures;
     s.hasCubemap = c->cubeTex ? 1u : 0u;
-    s.bvhNodes = c->accel.nodes.p;
+    s.bvhNodes = (const float4 *)c->accel.wide.p;
     s.tris = c->accel.trisSorted.p;
     s.nTris = c->accelBuilt ? c->accel.n : 0u;
-    s.rootIsLeaf = c->accel.n == 1 ? 1 : 0;
+    s.nWideNodes = c->accel.nWide;
     s.anyEmissive = c->anyEmissive ? 1u : 0u;
     s.anyTransparent = c->anyTransparent ? 1u : 0u;
     s.anyVolume = c->anyVolumeChange ? 1u : 0u;
@@ -530,7 +530,7 @@ PTC_API int ptc_build_accel(ptc_ctx *c) {
     c->accelBuilt = true;
     c->stats.build_ms = ms;
     c->stats.n_triangles = c->nWorldTris;
-    c->stats.n_bvh_nodes = c->nWorldTris ? 2ull * c->nWorldTris - 1 : 0;
+    c->stats.n_bvh_nodes = c->accel.nWide;
     c->stats.scene_bytes = c->accel.bytes() + c->vertices.bytes() + c->indices.bytes() + c->instances.bytes() + c->materials.bytes();
     return 0;
     PTC_GUARD_END(c)
@@ -640,6 +640,21 @@ PTC_API int ptc_get_lbvh(ptc_ctx *c, uint64_t *n_out, uint64_t *morton, uint32_t
             aabb[i * 6 + 3] = hi[i].x; aabb[i * 6 + 4] = hi[i].y; aabb[i * 6 + 5] = hi[i].z;
         }
     }
+    return 0;
+    PTC_GUARD_END(c)
+}
+
+PTC_API int ptc_get_wide_bvh(ptc_ctx *c, uint64_t *n_nodes_out, uint64_t *n_tris_out, uint32_t *node_words, uint32_t *tri_order) {
+    if (!c) return 1;
+    if (!c->accelBuilt) return fail(c, "ptc_build_accel has not been called");
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    const lbvh::Build &B = c->accel;
+    if (n_nodes_out) *n_nodes_out = B.n ? B.nWide : 0;
+    if (n_tris_out) *n_tris_out = B.n;
+    if (B.n == 0) return 0;
+    if (node_words) CUDA_TRY(cudaMemcpy(node_words, B.wide.p, (size_t)B.nWide * 80, cudaMemcpyDeviceToHost));
+    if (tri_order) CUDA_TRY(cudaMemcpy(tri_order, B.wideOrder.p, (size_t)B.n * 4, cudaMemcpyDeviceToHost));
     return 0;
     PTC_GUARD_END(c)
 }

@@ -6,9 +6,8 @@
  * triangle id); no face culling (VulkanScene.cpp:364-377).  Moeller-Trumbore on (v0, e1, e2), same operation
  * order as oracle/accel.hpp::intersectTri.
  *
- * Node fetches are 128-bit (4 x float4 per binary node: both child boxes + child links), triangle fetches are
- * 3 x float4; the traversal stack lives in shared memory (one column per thread, bank-conflict free) with a
- * local-memory spill that is never reached by LBVH depths seen in practice.
+ * Node fetches are 128-bit (5 x float4 per 8-wide compressed node), triangle fetches are 3 x float4; the traversal
+ * stack lives in shared memory (one 8-byte column per thread) with a local-memory spill for pathological depths.
  *
  * The traversal is a resumable state machine (Trav) so that kernels can run it warp-convergently: persistent warps
  * pull rays from a global counter with warp-aggregated atomics and replace finished rays while the other lanes keep
@@ -19,8 +18,8 @@
 
 namespace trv {
 
-#define TRV_STACK 64
-#define TRV_SHARED_STACK 24
+#define TRV_STACK 88        /* local-memory spill entries (binary LBVH depth bounds the wide depth: <= 63 + 32 levels) */
+#define TRV_SHARED_STACK 8  /* shared-memory entries per thread (8 B each) */
 #define TRV_BLOCK 128 /* threads per block of every kernel that traverses */
 #define TRV_DONE 0x7fffffff
 
@@ -50,16 +49,31 @@ PTC_D bool intersectTri(const float4 v0, const float4 e1, const float4 e2, const
     return true;
 }
 
+/* per-byte sign extension: every byte becomes 0xff when its top bit is set, else 0x00 (PRMT with replicate-sign selectors) */
+PTC_D uint32_t signExtendBytes(uint32_t x) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0, 0x0000ba98;" : "=r"(r) : "r"(x));
+    return r;
+}
+
+/* byte `sel` of w as the float 32768 + byte: bits 0x47000000 | byte << 8 (exact) */
+PTC_D float byteToFloat(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x47000000u, sel)); }
+
 /* Ordered query state: finds the smallest (t, id) lexicographically greater than (t0, id0) with t < tmax.
- * Closest hit: (t0, id0) = (tmin, 0xffffffff). */
+ * Closest hit: (t0, id0) = (tmin, 0xffffffff).
+ *
+ * Traversal of the 8-wide compressed BVH (layout in lbvh.cuh).  The state holds a "node group" (index of the first
+ * internal child of the last visited node + an 8-bit hit mask in traversal order + the node's imask) and a "triangle
+ * group" (first triangle + 24-bit hit mask); the stack holds postponed node groups only. */
 struct Trav {
-    float3 o, d, idir, ood;
+    float3 o, d, idir;
     float tmin, tmax, t0;
     uint32_t id0;
     HitRec best;
-    int32_t node;
+    uint2 ng, tg;
+    uint32_t octinv4;
     int sp;
-    int32_t spill[TRV_STACK];
+    uint2 spill[TRV_STACK];
 
     PTC_D void init(const DScene &sc, const Ray &ray, float t0_, uint32_t id0_) {
         o = ray.o;
@@ -71,21 +85,25 @@ struct Trav {
         const float ooeps = 1e-20f;
         idir = f3(1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x)), 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y)),
                   1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z)));
-        ood = o * idir;
+        /* octant of the direction signs; slot (oct) of every node is visited first */
+        const uint32_t oct = (idir.x < 0.0f ? 4u : 0u) | (idir.y < 0.0f ? 2u : 0u) | (idir.z < 0.0f ? 1u : 0u);
+        octinv4 = (7u - oct) * 0x01010101u;
         best.t = tmax;
         best.u = best.v = 0.0f;
         best.pos = -1;
         best.worldId = 0xffffffffu;
         sp = 0;
-        node = sc.nTris == 0 ? TRV_DONE : (sc.rootIsLeaf ? ~0 : 0);
+        tg = make_uint2(0u, 0u);
+        /* the root is "child 0 of a virtual node group" whose only hit sits at the top bit */
+        ng = sc.nTris == 0 ? make_uint2(0u, 0u) : make_uint2(0u, 0x80000000u);
+        if (sc.nTris == 0) sp = -1;
     }
-    PTC_D bool done() const { return node == TRV_DONE; }
-    PTC_D int32_t pop(const int32_t *stack, int stride) {
-        if (sp == 0) return TRV_DONE;
+    PTC_D bool done() const { return sp < 0; }
+    PTC_D uint2 pop(const uint2 *stack, int stride) {
         --sp;
         return sp < TRV_SHARED_STACK ? stack[sp * stride] : spill[sp - TRV_SHARED_STACK];
     }
-    PTC_D void push(int32_t *stack, int stride, int32_t v) {
+    PTC_D void push(uint2 *stack, int stride, uint2 v) {
         if (sp < TRV_SHARED_STACK)
             stack[sp * stride] = v;
         else if (sp - TRV_SHARED_STACK < TRV_STACK)
@@ -93,85 +111,126 @@ struct Trav {
         ++sp;
     }
 
-    /* one outer iteration of the while-while loop: descend to the next leaf, test it, pop. Returns done(). */
-    template <bool ANY_HIT>
-    PTC_D bool advance(const DScene &sc, int32_t *stack) {
+    /* Visits the nearest pending child node (8 quantised boxes at once): updates the node group and returns the
+     * triangle group (first triangle, 24-bit mask) the visit exposes.  Requires ng.y > 0x00ffffff. */
+    PTC_D uint2 nodeStep(const DScene &sc, uint2 *stack) {
         const float4 *__restrict__ nodes = sc.bvhNodes;
-        const float4 *__restrict__ tris = sc.tris;
         const int stride = blockDim.x;
-        while (node >= 0 && node != TRV_DONE) {
-            const float4 n0 = __ldg(&nodes[4 * (size_t)node + 0]);
-            const float4 n1 = __ldg(&nodes[4 * (size_t)node + 1]);
-            const float4 n2 = __ldg(&nodes[4 * (size_t)node + 2]);
-            const float4 n3 = __ldg(&nodes[4 * (size_t)node + 3]);
-            /* slab test of both children; the interval is widened by 2 ulp so a boundary hit is never lost (Ize 2013) */
-            float l0x = n0.x * idir.x - ood.x, l1x = n0.y * idir.x - ood.x;
-            float l0y = n0.z * idir.y - ood.y, l1y = n0.w * idir.y - ood.y;
-            float l0z = n2.x * idir.z - ood.z, l1z = n2.y * idir.z - ood.z;
-            float lmin = fmaxf(fmaxf(fminf(l0x, l1x), fminf(l0y, l1y)), fmaxf(fminf(l0z, l1z), t0));
-            float lmax = fminf(fminf(fmaxf(l0x, l1x), fmaxf(l0y, l1y)), fminf(fmaxf(l0z, l1z), best.t)) * 1.0000004f;
-            float r0x = n1.x * idir.x - ood.x, r1x = n1.y * idir.x - ood.x;
-            float r0y = n1.z * idir.y - ood.y, r1y = n1.w * idir.y - ood.y;
-            float r0z = n2.z * idir.z - ood.z, r1z = n2.w * idir.z - ood.z;
-            float rmin = fmaxf(fmaxf(fminf(r0x, r1x), fminf(r0y, r1y)), fmaxf(fminf(r0z, r1z), t0));
-            float rmax = fminf(fminf(fmaxf(r0x, r1x), fmaxf(r0y, r1y)), fminf(fmaxf(r0z, r1z), best.t)) * 1.0000004f;
-            const bool hl = lmin * 0.9999996f <= lmax, hr = rmin * 0.9999996f <= rmax;
-            const int32_t cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
-            if (!hl && !hr) {
-                node = pop(stack, stride);
-            } else {
-                node = hl ? cl : cr;
-                if (hl && hr) {
-                    int32_t farNode = cr;
-                    if (rmin < lmin) {
-                        node = cr;
-                        farNode = cl;
-                    }
-                    push(stack, stride, farNode);
-                }
-            }
-        }
-        if (node == TRV_DONE) return true;
-        /* leaf: one triangle */
+        uint2 tgOut;
         {
-            const int32_t pos = ~node;
-            const float4 v0 = __ldg(&tris[3 * (size_t)pos + 0]);
-            const float4 e1 = __ldg(&tris[3 * (size_t)pos + 1]);
-            const float4 e2 = __ldg(&tris[3 * (size_t)pos + 2]);
-            float t, u, v;
-            if (intersectTri(v0, e1, e2, o, d, t, u, v)) {
-                const uint32_t wid = __float_as_uint(e2.w);
-                const bool after = t > t0 || (t == t0 && id0 != 0xffffffffu && wid > id0);
-                const bool inRange = after && t < tmax && t > tmin;
-                if (inRange && (t < best.t || (t == best.t && wid < best.worldId))) {
-                    best.t = t;
-                    best.u = u;
-                    best.v = v;
-                    best.pos = pos;
-                    best.worldId = wid;
-                    if (ANY_HIT) {
-                        node = TRV_DONE;
-                        return true;
-                    }
+            const uint32_t hits = ng.y;
+            const uint32_t bit = 31u - (uint32_t)__clz(hits);
+            ng.y &= ~(1u << bit);
+            if (ng.y > 0x00ffffffu) push(stack, stride, ng);
+            const uint32_t slot = (bit - 24u) ^ (octinv4 & 0xffu);
+            const uint32_t rel = __popc(hits & ~(0xffffffffu << slot) & 0xffu);
+            const float4 *np = nodes + 5 * (size_t)(ng.x + rel);
+            const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+            const uint32_t ei = __float_as_uint(n0.w);
+            /* plane distance t = q * a + b with a = 2^e / d, b = (p - o) / d.  The byte q is turned into the float 32768 + q
+             * by ONE byte permute (0x47000000 | q << 8), so t = (32768 + q) * a + (b - 32768 a).  Rounding of that constant
+             * (<= 2^-9 |a|) and of b near the node is covered by moving the near planes down / the far planes up by 1/128 of
+             * a quantisation step; rounding of b for far-away nodes (t ~ |b|) by the relative 1e-6 margin on the final test.
+             * Near and far planes share a and c, so a flat box (q_near == q_far) can never come out inverted. */
+            const float ax = __uint_as_float((ei & 0xffu) << 23) * idir.x, ay = __uint_as_float(((ei >> 8) & 0xffu) << 23) * idir.y,
+                        az = __uint_as_float(((ei >> 16) & 0xffu) << 23) * idir.z;
+            const float cx = fmaf(-32768.0f, ax, (n0.x - o.x) * idir.x), cy = fmaf(-32768.0f, ay, (n0.y - o.y) * idir.y),
+                        cz = fmaf(-32768.0f, az, (n0.z - o.z) * idir.z);
+            const float px = fabsf(ax) * 0.0078125f, py = fabsf(ay) * 0.0078125f, pz = fabsf(az) * 0.0078125f;
+            const float bnx = cx - px, bny = cy - py, bnz = cz - pz, bfx = cx + px, bfy = cy + py, bfz = cz + pz;
+            const float tlo = t0 * 0.999999f, thi = best.t * 1.000001f;
+            const uint32_t imask = ei >> 24;
+            ng.x = __float_as_uint(n1.x);
+            tgOut.x = __float_as_uint(n1.y);
+            uint32_t hitmask = 0;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
+                const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+                const uint32_t innerMask4 = signExtendBytes(isInner4 << 3); /* 0xff in the bytes of internal children */
+                const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
+                const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+                const uint32_t qlx = __float_as_uint(half ? n2.y : n2.x), qly = __float_as_uint(half ? n2.w : n2.z);
+                const uint32_t qlz = __float_as_uint(half ? n3.y : n3.x), qhx = __float_as_uint(half ? n3.w : n3.z);
+                const uint32_t qhy = __float_as_uint(half ? n4.y : n4.x), qhz = __float_as_uint(half ? n4.w : n4.z);
+                const uint32_t nx = idir.x < 0.0f ? qhx : qlx, fx = idir.x < 0.0f ? qlx : qhx;
+                const uint32_t ny = idir.y < 0.0f ? qhy : qly, fy = idir.y < 0.0f ? qly : qhy;
+                const uint32_t nz = idir.z < 0.0f ? qhz : qlz, fz = idir.z < 0.0f ? qlz : qhz;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t sel = 0x7504u | ((uint32_t)j << 4);
+                    const float tnx = fmaf(byteToFloat(nx, sel), ax, bnx), tny = fmaf(byteToFloat(ny, sel), ay, bny),
+                                tnz = fmaf(byteToFloat(nz, sel), az, bnz);
+                    const float tfx = fmaf(byteToFloat(fx, sel), ax, bfx), tfy = fmaf(byteToFloat(fy, sel), ay, bfy),
+                                tfz = fmaf(byteToFloat(fz, sel), az, bfz);
+                    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tlo));
+                    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, thi));
+                    if (tn * 0.999999f <= tf) hitmask |= ((childBits4 >> (8 * j)) & 0xffu) << ((bitIndex4 >> (8 * j)) & 0xffu);
                 }
             }
+            ng.y = (hitmask & 0xff000000u) | imask;
+            tgOut.y = hitmask & 0x00ffffffu;
         }
-        node = pop(stack, stride);
-        return node == TRV_DONE;
+        return tgOut;
+    }
+
+    /* tests the triangle at position pos of the traversal order; returns true when it became the best hit */
+    PTC_D bool triTest(const DScene &sc, int32_t pos) {
+        const float4 *__restrict__ tris = sc.tris;
+        const float4 v0 = __ldg(&tris[3 * (size_t)pos + 0]);
+        const float4 e1 = __ldg(&tris[3 * (size_t)pos + 1]);
+        const float4 e2 = __ldg(&tris[3 * (size_t)pos + 2]);
+        float t, u, v;
+        if (intersectTri(v0, e1, e2, o, d, t, u, v)) {
+            const uint32_t wid = __float_as_uint(e2.w);
+            const bool after = t > t0 || (t == t0 && id0 != 0xffffffffu && wid > id0);
+            const bool inRange = after && t < tmax && t > tmin;
+            if (inRange && (t < best.t || (t == best.t && wid < best.worldId))) {
+                best.t = t;
+                best.u = u;
+                best.v = v;
+                best.pos = pos;
+                best.worldId = wid;
+                return true;
+            }
+        }
+        return false;
+    }
+
+    /* one step: node visit, the triangles it exposes, pop. Returns done(). */
+    template <bool ANY_HIT>
+    PTC_D bool advance(const DScene &sc, uint2 *stack) {
+        if (ng.y > 0x00ffffffu) tg = nodeStep(sc, stack);
+        while (tg.y != 0u) {
+            const uint32_t k = 31u - (uint32_t)__clz(tg.y);
+            tg.y &= ~(1u << k);
+            if (triTest(sc, (int32_t)(tg.x + k)) && ANY_HIT) {
+                sp = -1;
+                return true;
+            }
+        }
+        if (ng.y <= 0x00ffffffu) {
+            if (sp == 0) {
+                sp = -1;
+                return true;
+            }
+            ng = pop(stack, blockDim.x);
+        }
+        return false;
     }
 };
 
 /* run-to-completion wrappers (used by the chain kernels and the parity hooks) */
 template <bool ANY_HIT>
-PTC_D HitRec traverse(const DScene &sc, const Ray &ray, float t0, uint32_t id0, int32_t *stack) {
+PTC_D HitRec traverse(const DScene &sc, const Ray &ray, float t0, uint32_t id0, uint2 *stack) {
     Trav tr;
     tr.init(sc, ray, t0, id0);
     while (!tr.done()) tr.advance<ANY_HIT>(sc, stack);
     return tr.best;
 }
-PTC_D HitRec closestHit(const DScene &sc, const Ray &ray, int32_t *stack) { return traverse<false>(sc, ray, ray.tmin, 0xffffffffu, stack); }
-PTC_D HitRec nextHit(const DScene &sc, const Ray &ray, float t0, uint32_t id0, int32_t *stack) { return traverse<false>(sc, ray, t0, id0, stack); }
-PTC_D bool occluded(const DScene &sc, const Ray &ray, int32_t *stack) { return traverse<true>(sc, ray, ray.tmin, 0xffffffffu, stack).pos >= 0; }
+PTC_D HitRec closestHit(const DScene &sc, const Ray &ray, uint2 *stack) { return traverse<false>(sc, ray, ray.tmin, 0xffffffffu, stack); }
+PTC_D HitRec nextHit(const DScene &sc, const Ray &ray, float t0, uint32_t id0, uint2 *stack) { return traverse<false>(sc, ray, t0, id0, stack); }
+PTC_D bool occluded(const DScene &sc, const Ray &ray, uint2 *stack) { return traverse<true>(sc, ray, ray.tmin, 0xffffffffu, stack).pos >= 0; }
 
 /* ------------------------------------------------------------------ persistent-warp work distribution */
 /* Each warp owns a chunk [pos, end) of the work list, refilled with ONE global atomic per chunk; lanes that need work

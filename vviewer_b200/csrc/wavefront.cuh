@@ -281,20 +281,31 @@ __global__ void __launch_bounds__(256) k_raygen(Wave w, const __grid_constant__ 
 }
 
 /* ------------------------------------------------------------------ k_extend */
-/* Persistent warps: every warp pulls rays from the bounce's queue (one global atomic per 256 rays), keeps one resumable
- * traversal per lane and replaces finished rays as soon as fewer than EXTEND_MIN_ACTIVE lanes are still traversing, so the
- * warp stays converged instead of fragmenting (ncu: 5.4 -> see profiles/ threads per instruction). */
-#define EXTEND_MIN_ACTIVE 22
+/* Persistent warps: every warp pulls rays from the bounce's queue (one global atomic per 256 rays) and keeps one traversal per
+ * lane.  All 32 lanes run the same loop body:
+ *   node phase      every lane with node work visits ONE wide node (8 boxes); triangle groups the visit exposes are NOT tested
+ *                   right away (that ran at 2.8 of 32 lanes, profiles/r1_v2) but stashed in a per-lane shared-memory ring;
+ *   triangle phase  entered by warp vote once enough lanes hold stashed triangles (or lanes are blocked on them): every lane
+ *                   with a stash tests one triangle per iteration;
+ *   refill          finished lanes fetch new rays as soon as fewer than EXTEND_MIN_ACTIVE lanes are traversing. */
+#define EXTEND_MIN_ACTIVE 24
+#define EXTEND_STASH 4      /* stashed triangle groups per lane */
+#define EXTEND_TRI_ENTER 12 /* lanes with stashed triangles that trigger a triangle phase */
+#define EXTEND_TRI_LEAVE 6  /* the phase ends when fewer lanes than this still hold triangles */
+#define EXTEND_BLOCKED 4    /* lanes that have nothing but stashed triangles left */
 __global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_constant__ DScene sc, uint32_t bounce) {
-    __shared__ int32_t stackMem[TRV_SHARED_STACK * TRV_BLOCK];
-    int32_t *stack = stackMem + threadIdx.x;
+    __shared__ uint2 stackMem[TRV_SHARED_STACK * TRV_BLOCK];
+    __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
+    uint2 *stack = stackMem + threadIdx.x;
+    uint2 *stash = stashMem + threadIdx.x;
     const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_ACTIVE];
     uint32_t *fetchCounter = &w.counters[bounce * CNT_STRIDE + CNT_FETCH];
     const uint32_t *__restrict__ q = w.queue[bounce & 1u];
     trv::WarpFeeder feeder;
     trv::Trav tr;
-    tr.node = TRV_DONE;
-    uint32_t slot = 0;
+    tr.sp = -1;
+    tr.ng = tr.tg = make_uint2(0u, 0u);
+    uint32_t slot = 0, nStash = 0;
     bool active = false;
     while (true) {
         const uint32_t i = feeder.fetch(!active, fetchCounter, count);
@@ -307,16 +318,55 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_const
             ray.tmin = 0.001f;
             ray.tmax = 10000.0f;
             tr.init(sc, ray, ray.tmin, 0xffffffffu);
-            active = true;
+            nStash = 0;
+            active = !tr.done();
+            if (!active) w.hit[slot] = make_float4(tr.best.t, tr.best.u, tr.best.v, __int_as_float(tr.best.pos));
         }
-        if (!__any_sync(0xffffffffu, active)) break;
-        while (active) {
-            if (tr.advance<false>(sc, stack)) {
+        if (!__any_sync(0xffffffffu, active)) {
+            if (!__any_sync(0xffffffffu, i != 0xffffffffu)) break; /* nothing left to fetch */
+            continue;                                              /* every fetched ray finished at once (empty scene) */
+        }
+        while (true) { /* warp-convergent: no lane leaves this loop alone */
+            if (active && tr.ng.y > 0x00ffffffu) {
+                const uint2 g = tr.nodeStep(sc, stack);
+                if (g.y != 0u) {
+                    if (nStash == EXTEND_STASH) { /* ring full: make room by finishing the current group now (rare) */
+                        while (tr.tg.y != 0u) {
+                            const uint32_t k = 31u - (uint32_t)__clz(tr.tg.y);
+                            tr.tg.y &= ~(1u << k);
+                            tr.triTest(sc, (int32_t)(tr.tg.x + k));
+                        }
+                        tr.tg = stash[(--nStash) * TRV_BLOCK];
+                    }
+                    if (tr.tg.y == 0u)
+                        tr.tg = g;
+                    else
+                        stash[(nStash++) * TRV_BLOCK] = g;
+                }
+                if (tr.ng.y <= 0x00ffffffu && tr.sp > 0) tr.ng = tr.pop(stack, TRV_BLOCK);
+            }
+            const bool hasNode = active && tr.ng.y > 0x00ffffffu;
+            bool hasTri = active && tr.tg.y != 0u;
+            const unsigned mN = __ballot_sync(0xffffffffu, hasNode);
+            unsigned mT = __ballot_sync(0xffffffffu, hasTri);
+            if (__popc(mT) >= EXTEND_TRI_ENTER || __popc(mT & ~mN) >= EXTEND_BLOCKED || (mN == 0u && mT != 0u)) {
+                do {
+                    if (hasTri) {
+                        const uint32_t k = 31u - (uint32_t)__clz(tr.tg.y);
+                        tr.tg.y &= ~(1u << k);
+                        tr.triTest(sc, (int32_t)(tr.tg.x + k));
+                        if (tr.tg.y == 0u && nStash > 0u) tr.tg = stash[(--nStash) * TRV_BLOCK];
+                        hasTri = tr.tg.y != 0u;
+                    }
+                    mT = __ballot_sync(0xffffffffu, hasTri);
+                } while (__popc(mT) >= EXTEND_TRI_LEAVE || (mT & ~mN) != 0u);
+            }
+            if (active && !hasNode && !hasTri) {
                 w.hit[slot] = make_float4(tr.best.t, tr.best.u, tr.best.v, __int_as_float(tr.best.pos));
                 active = false;
-            } else if (!feeder.exhausted && __popc(__activemask()) < EXTEND_MIN_ACTIVE) {
-                break;
             }
+            const unsigned mA = __ballot_sync(0xffffffffu, active);
+            if (mA == 0u || (!feeder.exhausted && __popc(mA) < EXTEND_MIN_ACTIVE)) break;
         }
     }
 }
@@ -558,7 +608,7 @@ __global__ void __launch_bounds__(128) k_shade(Wave w, const __grid_constant__ D
 /* ------------------------------------------------------------------ k_shadow */
 /* lightSampling.glsl:108-144 with nearest-first candidate order (trap T1) */
 __global__ void __launch_bounds__(TRV_BLOCK) k_shadow(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce) {
-    __shared__ int32_t stack[24 * TRV_BLOCK];
+    __shared__ uint2 stack[TRV_SHARED_STACK * TRV_BLOCK];
     const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_SHADOW];
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounded = (count + 31u) & ~31u;
@@ -656,7 +706,7 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_shadow(Wave w, const __grid_const
 /* ------------------------------------------------------------------ k_probe */
 /* next_event_estimation.glsl:1-33 + rayNEE.* with nearest-first candidate order (trap T1) */
 __global__ void __launch_bounds__(TRV_BLOCK) k_probe(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce) {
-    __shared__ int32_t stack[24 * TRV_BLOCK];
+    __shared__ uint2 stack[TRV_SHARED_STACK * TRV_BLOCK];
     const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_PROBE];
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounded = (count + 31u) & ~31u;
@@ -805,7 +855,7 @@ __global__ void k_collect_stats(Wave w, uint32_t depth) {
 /* ------------------------------------------------------------------ parity-hook kernels */
 __global__ void __launch_bounds__(TRV_BLOCK) k_trace_closest(const __grid_constant__ DScene sc, const float *__restrict__ rays, int n, int *inst, int *prim,
                                                              float *t, float *u, float *v) {
-    __shared__ int32_t stack[24 * TRV_BLOCK];
+    __shared__ uint2 stack[TRV_SHARED_STACK * TRV_BLOCK];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float *r = rays + (size_t)i * 8;
