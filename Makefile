@@ -33,6 +33,12 @@ $(LIBDIR)/offlinerender: vviewer_b200/bin/offlinerender/main.cpp $(LIBDIR)/libve
 
 oracle: $(ORCDIR)/liboracle.so
 
+# diagnosis build with traversal counters (tools/trav_stats.py); never loaded by the product, tests or bench
+stats: $(LIBDIR)/libptc_cuda_stats.so
+$(LIBDIR)/libptc_cuda_stats.so: $(CUDA_SRCS) $(CUDA_HDRS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVCCFLAGS) -DPTC_TRAV_STATS -shared -o $@ vviewer_b200/csrc/ptc_cuda.cu -lcudart
+
 # -ffp-contract=off: the world-space flatten and the LBVH reference build must round exactly like the
 # device kernels, which use explicit __fmul_rn/__fadd_rn
 $(ORCDIR)/liboracle.so: oracle/oracle.cpp oracle/omath.hpp oracle/bsdf.hpp oracle/accel.hpp include/ptc.h
@@ -42,4 +48,4 @@ $(ORCDIR)/liboracle.so: oracle/oracle.cpp oracle/omath.hpp oracle/bsdf.hpp oracl
 clean:
 	rm -rf $(LIBDIR) $(ORCDIR)
 
-.PHONY: all oracle clean
+.PHONY: all oracle stats clean

@@ -432,8 +432,10 @@ __global__ void k_gather_tris(uint32_t n, const uint32_t *__restrict__ triMap, c
 }
 
 struct Build {
-    DBuf<float4> trisUnsorted, trisSorted, triLo, triHi, nodeLo, nodeHi;
-    DBuf<uint4> wide;              /* 5 x uint4 per wide node */
+    DBuf<float4> trisUnsorted, triLo, triHi, nodeLo, nodeHi;
+    DBuf<float4> trav;             /* what traversal reads, ONE allocation so that one L2 access-policy window covers it:
+                                      [5 x float4 per wide node, breadth first][3 x float4 per triangle, wide-node order] */
+    DBuf<uint4> wide;              /* collapse output before compaction (sized by the node bound) */
     DBuf<uint64_t> keys, keysSorted;
     DBuf<uint32_t> ids, order, arrivals, sceneBounds, triMap, wideOrder, bigNodes;
     DBuf<int32_t> parent, left, right, rangeEnd, rootOf;
@@ -445,12 +447,14 @@ struct Build {
     int bits = 0;
 
     size_t bytes() const {
-        return trisUnsorted.bytes() + trisSorted.bytes() + triLo.bytes() + triHi.bytes() + nodeLo.bytes() + nodeHi.bytes() + wide.bytes() +
+        return trisUnsorted.bytes() + trav.bytes() + triLo.bytes() + triHi.bytes() + nodeLo.bytes() + nodeHi.bytes() + wide.bytes() +
                keys.bytes() + keysSorted.bytes() + ids.bytes() + order.bytes() + arrivals.bytes() + parent.bytes() + left.bytes() +
                right.bytes() + sortTemp.bytes() + triMap.bytes() + wideOrder.bytes() + rangeEnd.bytes() + rootOf.bytes() + wideTmp.bytes() +
                counts.bytes() + inclusive.bytes() + scanTemp.bytes();
     }
     size_t traversalBytes() const { return (size_t)nWide * 80 + (size_t)n * 48; }
+    const float4 *wideNodes() const { return trav.p; }
+    const float4 *sortedTris() const { return trav.p ? trav.p + 5 * (size_t)nWide : nullptr; }
 
     /* returns the number of kernel launches */
     int run(const ptc_vertex *vertices, const uint32_t *indices, const DInstance *instances, uint32_t nInstances, uint32_t nTris,
@@ -462,7 +466,6 @@ struct Build {
         const uint32_t G = (n + B - 1) / B;
         size_t nn = 2 * (size_t)n - 1;
         trisUnsorted.alloc(3 * (size_t)n);
-        trisSorted.alloc(3 * (size_t)n);
         triLo.alloc(n);
         triHi.alloc(n);
         keys.alloc(n);
@@ -542,7 +545,9 @@ struct Build {
         }
         nWide = levelBase;
         if (triBase != n) throw CudaError{"wide BVH collapse lost triangles"};
-        k_gather_tris<<<G, B, 0, s>>>(n, triMap.p, order.p, trisUnsorted.p, trisSorted.p, wideOrder.p);
+        trav.alloc(5 * (size_t)nWide + 3 * (size_t)n);
+        CUDA_TRY(cudaMemcpyAsync(trav.p, wide.p, (size_t)nWide * 80, cudaMemcpyDeviceToDevice, s));
+        k_gather_tris<<<G, B, 0, s>>>(n, triMap.p, order.p, trisUnsorted.p, trav.p + 5 * (size_t)nWide, wideOrder.p);
         launches++;
         CUDA_TRY(cudaGetLastError());
         return launches;

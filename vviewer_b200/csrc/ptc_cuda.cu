@@ -30,6 +30,7 @@ struct ptc_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     int smCount = 148;
+    size_t persistMax = 0, windowMax = 0; /* L2 persisting carve-out and access-policy window limits of the device */
 
     /* scene */
     DBuf<ptc_vertex> vertices;
@@ -121,8 +122,8 @@ DScene makeDScene(ptc_ctx *c) {
     s.nLightInstances = c->nLightInstances;
     s.nTextures = c->nTextures;
     s.hasCubemap = c->cubeTex ? 1u : 0u;
-    s.bvhNodes = (const float4 *)c->accel.wide.p;
-    s.tris = c->accel.trisSorted.p;
+    s.bvhNodes = c->accel.wideNodes();
+    s.tris = c->accel.sortedTris();
     s.nTris = c->accelBuilt ? c->accel.n : 0u;
     s.nWideNodes = c->accel.nWide;
     s.anyEmissive = c->anyEmissive ? 1u : 0u;
@@ -200,6 +201,29 @@ void createCubemap(ptc_ctx *c, const ptc_env &env) {
     cudaDestroyTextureObject(eqTex);
     cudaFreeArray(eqArray);
     c->cubeN = N;
+}
+
+/* L2 persistence for what every ray touches: the wide nodes (breadth first, so the top levels come first) and as much of
+ * the triangle array as the persisting carve-out holds.  The path state streams through L2 (6 GB per batch at 1080p x 16)
+ * and would otherwise keep evicting the BVH. */
+void setTraversalWindow(ptc_ctx *c) {
+    cudaStreamAttrValue attr{};
+    cudaCtxResetPersistingL2Cache(); /* lines of a previous scene */
+    const size_t bytes = c->accel.n ? c->accel.traversalBytes() : 0;
+    if (bytes == 0 || c->persistMax == 0 || c->windowMax == 0) {
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        return;
+    }
+    const size_t carve = std::min(c->persistMax, bytes);
+    CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+    const size_t window = std::min(bytes, c->windowMax);
+    attr.accessPolicyWindow.base_ptr = (void *)c->accel.trav.p;
+    attr.accessPolicyWindow.num_bytes = window;
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CUDA_TRY(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
 }
 
 void ensureWave(ptc_ctx *c, size_t slots, uint32_t depth) {
@@ -378,6 +402,10 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     c->stats.shadow_hops = hs[wf::ST_SHADOW_HOPS];
     c->stats.probe_rays = hs[wf::ST_PROBE_RAYS];
     c->stats.probe_hops = hs[wf::ST_PROBE_HOPS];
+    c->stats.reserved[0] = hs[wf::ST_NODE_VISITS]; /* filled only by -DPTC_TRAV_STATS builds (tools/) */
+    c->stats.reserved[1] = hs[wf::ST_TRI_TESTS];
+    c->stats.reserved[2] = hs[wf::ST_NODE_ITERS];
+    c->stats.reserved[3] = hs[wf::ST_TRI_ITERS];
     c->stats.render_ms = ms;
     c->stats.trace_ms = traceMs;
     c->stats.shade_ms = shadeMs;
@@ -433,6 +461,8 @@ PTC_API int ptc_create(ptc_ctx **out, const int *device_ids, int n_devices) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
     if (prop.major != 10) return fail(c, std::string("device '") + prop.name + "' is not sm_100; this build targets B200 only");
     c->smCount = prop.multiProcessorCount;
+    c->persistMax = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
+    c->windowMax = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->evA));
     CUDA_TRY(cudaEventCreate(&c->evB));
@@ -528,6 +558,7 @@ PTC_API int ptc_build_accel(ptc_ctx *c) {
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, c->evA, c->evB));
     c->accelBuilt = true;
+    setTraversalWindow(c);
     c->stats.build_ms = ms;
     c->stats.n_triangles = c->nWorldTris;
     c->stats.n_bvh_nodes = c->accel.nWide;
@@ -653,7 +684,7 @@ PTC_API int ptc_get_wide_bvh(ptc_ctx *c, uint64_t *n_nodes_out, uint64_t *n_tris
     if (n_nodes_out) *n_nodes_out = B.n ? B.nWide : 0;
     if (n_tris_out) *n_tris_out = B.n;
     if (B.n == 0) return 0;
-    if (node_words) CUDA_TRY(cudaMemcpy(node_words, B.wide.p, (size_t)B.nWide * 80, cudaMemcpyDeviceToHost));
+    if (node_words) CUDA_TRY(cudaMemcpy(node_words, B.wideNodes(), (size_t)B.nWide * 80, cudaMemcpyDeviceToHost));
     if (tri_order) CUDA_TRY(cudaMemcpy(tri_order, B.wideOrder.p, (size_t)B.n * 4, cudaMemcpyDeviceToHost));
     return 0;
     PTC_GUARD_END(c)

@@ -65,6 +65,16 @@ PTC_D float byteToFloat(uint32_t w, uint32_t sel) { return __uint_as_float(__byt
  * Traversal of the 8-wide compressed BVH (layout in lbvh.cuh).  The state holds a "node group" (index of the first
  * internal child of the last visited node + an 8-bit hit mask in traversal order + the node's imask) and a "triangle
  * group" (first triangle + 24-bit hit mask); the stack holds postponed node groups only. */
+struct Stack {
+    uint2 *shared; /* this thread's column: entry k at shared[k * TRV_BLOCK] */
+    uint2 *spill;  /* TRV_STACK local-memory entries */
+};
+/* declares the stack of the calling thread inside a kernel */
+#define TRV_DECLARE_STACK(name)                                    \
+    __shared__ uint2 name##Shared[TRV_SHARED_STACK * TRV_BLOCK];   \
+    uint2 name##Spill[TRV_STACK];                                  \
+    const trv::Stack name{name##Shared + threadIdx.x, name##Spill}
+
 struct Trav {
     float3 o, d, idir;
     float tmin, tmax, t0;
@@ -73,7 +83,6 @@ struct Trav {
     uint2 ng, tg;
     uint32_t octinv4;
     int sp;
-    uint2 spill[TRV_STACK];
 
     PTC_D void init(const DScene &sc, const Ray &ray, float t0_, uint32_t id0_) {
         o = ray.o;
@@ -99,29 +108,30 @@ struct Trav {
         if (sc.nTris == 0) sp = -1;
     }
     PTC_D bool done() const { return sp < 0; }
-    PTC_D uint2 pop(const uint2 *stack, int stride) {
+    /* the stack: TRV_SHARED_STACK entries in a shared-memory column, deeper entries in the caller's local spill array
+     * (kept OUT of this struct so that the traversal state itself stays in registers) */
+    PTC_D uint2 pop(const Stack &st) {
         --sp;
-        return sp < TRV_SHARED_STACK ? stack[sp * stride] : spill[sp - TRV_SHARED_STACK];
+        return sp < TRV_SHARED_STACK ? st.shared[sp * TRV_BLOCK] : st.spill[sp - TRV_SHARED_STACK];
     }
-    PTC_D void push(uint2 *stack, int stride, uint2 v) {
+    PTC_D void push(const Stack &st, uint2 v) {
         if (sp < TRV_SHARED_STACK)
-            stack[sp * stride] = v;
+            st.shared[sp * TRV_BLOCK] = v;
         else if (sp - TRV_SHARED_STACK < TRV_STACK)
-            spill[sp - TRV_SHARED_STACK] = v;
+            st.spill[sp - TRV_SHARED_STACK] = v;
         ++sp;
     }
 
     /* Visits the nearest pending child node (8 quantised boxes at once): updates the node group and returns the
      * triangle group (first triangle, 24-bit mask) the visit exposes.  Requires ng.y > 0x00ffffff. */
-    PTC_D uint2 nodeStep(const DScene &sc, uint2 *stack) {
+    PTC_D uint2 nodeStep(const DScene &sc, const Stack &stack) {
         const float4 *__restrict__ nodes = sc.bvhNodes;
-        const int stride = blockDim.x;
         uint2 tgOut;
         {
             const uint32_t hits = ng.y;
             const uint32_t bit = 31u - (uint32_t)__clz(hits);
             ng.y &= ~(1u << bit);
-            if (ng.y > 0x00ffffffu) push(stack, stride, ng);
+            if (ng.y > 0x00ffffffu) push(stack, ng);
             const uint32_t slot = (bit - 24u) ^ (octinv4 & 0xffu);
             const uint32_t rel = __popc(hits & ~(0xffffffffu << slot) & 0xffu);
             const float4 *np = nodes + 5 * (size_t)(ng.x + rel);
@@ -199,7 +209,7 @@ struct Trav {
 
     /* one step: node visit, the triangles it exposes, pop. Returns done(). */
     template <bool ANY_HIT>
-    PTC_D bool advance(const DScene &sc, uint2 *stack) {
+    PTC_D bool advance(const DScene &sc, const Stack &stack) {
         if (ng.y > 0x00ffffffu) tg = nodeStep(sc, stack);
         while (tg.y != 0u) {
             const uint32_t k = 31u - (uint32_t)__clz(tg.y);
@@ -214,7 +224,7 @@ struct Trav {
                 sp = -1;
                 return true;
             }
-            ng = pop(stack, blockDim.x);
+            ng = pop(stack);
         }
         return false;
     }
@@ -222,15 +232,15 @@ struct Trav {
 
 /* run-to-completion wrappers (used by the chain kernels and the parity hooks) */
 template <bool ANY_HIT>
-PTC_D HitRec traverse(const DScene &sc, const Ray &ray, float t0, uint32_t id0, uint2 *stack) {
+PTC_D HitRec traverse(const DScene &sc, const Ray &ray, float t0, uint32_t id0, const Stack &stack) {
     Trav tr;
     tr.init(sc, ray, t0, id0);
     while (!tr.done()) tr.advance<ANY_HIT>(sc, stack);
     return tr.best;
 }
-PTC_D HitRec closestHit(const DScene &sc, const Ray &ray, uint2 *stack) { return traverse<false>(sc, ray, ray.tmin, 0xffffffffu, stack); }
-PTC_D HitRec nextHit(const DScene &sc, const Ray &ray, float t0, uint32_t id0, uint2 *stack) { return traverse<false>(sc, ray, t0, id0, stack); }
-PTC_D bool occluded(const DScene &sc, const Ray &ray, uint2 *stack) { return traverse<true>(sc, ray, ray.tmin, 0xffffffffu, stack).pos >= 0; }
+PTC_D HitRec closestHit(const DScene &sc, const Ray &ray, const Stack &stack) { return traverse<false>(sc, ray, ray.tmin, 0xffffffffu, stack); }
+PTC_D HitRec nextHit(const DScene &sc, const Ray &ray, float t0, uint32_t id0, const Stack &stack) { return traverse<false>(sc, ray, t0, id0, stack); }
+PTC_D bool occluded(const DScene &sc, const Ray &ray, const Stack &stack) { return traverse<true>(sc, ray, ray.tmin, 0xffffffffu, stack).pos >= 0; }
 
 /* ------------------------------------------------------------------ persistent-warp work distribution */
 /* Each warp owns a chunk [pos, end) of the work list, refilled with ONE global atomic per chunk; lanes that need work

@@ -26,7 +26,7 @@ namespace wf {
 #define PF_VOL_SHIFT 16
 
 enum { CNT_ACTIVE = 0, CNT_SHADOW = 1, CNT_PROBE = 2, CNT_FETCH = 3, CNT_STRIDE = 4 };
-enum { ST_SEGMENTS = 0, ST_SHADOW_RAYS, ST_SHADOW_HOPS, ST_PROBE_RAYS, ST_PROBE_HOPS, ST_COUNT };
+enum { ST_SEGMENTS = 0, ST_SHADOW_RAYS, ST_SHADOW_HOPS, ST_PROBE_RAYS, ST_PROBE_HOPS, ST_NODE_VISITS, ST_TRI_TESTS, ST_NODE_ITERS, ST_TRI_ITERS, ST_COUNT };
 
 struct Wave {
     float4 *orgRng;    /* origin.xyz, rng state */
@@ -58,6 +58,11 @@ struct RenderConst {
 };
 
 PTC_D uint32_t laneId() { return threadIdx.x & 31u; }
+
+/* path state is written once and read once per kernel, and a batch's state (6 GB at 1080p x 16) is far larger than L2:
+ * stream it (evict-first) so that it does not displace the BVH, the materials and the textures */
+PTC_D float4 ldS(const float4 *p) { return __ldcs(p); }
+PTC_D void stS(float4 *p, float4 v) { __stcs(p, v); }
 
 /* ballot/popc compaction: every lane of the warp must call this */
 PTC_D void queuePush(uint32_t *__restrict__ queue, uint32_t *__restrict__ counter, bool pred, uint32_t value) {
@@ -272,12 +277,12 @@ __global__ void __launch_bounds__(256) k_raygen(Wave w, const __grid_constant__ 
     float3 d = f3((vi[0] * dc.x + vi[4] * dc.y) + vi[8] * dc.z, (vi[1] * dc.x + vi[5] * dc.y) + vi[9] * dc.z, (vi[2] * dc.x + vi[6] * dc.y) + vi[10] * dc.z);
     uint32_t flags = 0;
     if (rc.sd.volumes[0] != -1.0f) flags |= PF_INVOL | ((uint32_t)(int)rc.sd.volumes[0] << PF_VOL_SHIFT);
-    w.orgRng[slot] = make_float4(o.x, o.y, o.z, __uint_as_float(rng));
-    w.dirFlags[slot] = make_float4(d.x, d.y, d.z, __uint_as_float(flags));
-    w.beta[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-    w.radiance[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    w.aovAlbedo[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    w.aovNormal[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    stS(&w.orgRng[slot], make_float4(o.x, o.y, o.z, __uint_as_float(rng)));
+    stS(&w.dirFlags[slot], make_float4(d.x, d.y, d.z, __uint_as_float(flags)));
+    stS(&w.beta[slot], make_float4(1.0f, 1.0f, 1.0f, 0.0f));
+    stS(&w.radiance[slot], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    stS(&w.aovAlbedo[slot], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    stS(&w.aovNormal[slot], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
 }
 
 /* ------------------------------------------------------------------ k_extend */
@@ -294,9 +299,8 @@ __global__ void __launch_bounds__(256) k_raygen(Wave w, const __grid_constant__ 
 #define EXTEND_TRI_LEAVE 6  /* the phase ends when fewer lanes than this still hold triangles */
 #define EXTEND_BLOCKED 4    /* lanes that have nothing but stashed triangles left */
 __global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_constant__ DScene sc, uint32_t bounce) {
-    __shared__ uint2 stackMem[TRV_SHARED_STACK * TRV_BLOCK];
+    TRV_DECLARE_STACK(stack);
     __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
-    uint2 *stack = stackMem + threadIdx.x;
     uint2 *stash = stashMem + threadIdx.x;
     const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_ACTIVE];
     uint32_t *fetchCounter = &w.counters[bounce * CNT_STRIDE + CNT_FETCH];
@@ -307,11 +311,17 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_const
     tr.ng = tr.tg = make_uint2(0u, 0u);
     uint32_t slot = 0, nStash = 0;
     bool active = false;
+#ifdef PTC_TRAV_STATS
+    uint32_t cNode = 0, cTri = 0, cNodeIt = 0, cTriIt = 0;
+#define TRV_COUNT(x) (x)++
+#else
+#define TRV_COUNT(x)
+#endif
     while (true) {
         const uint32_t i = feeder.fetch(!active, fetchCounter, count);
         if (i != 0xffffffffu) {
             slot = bounce == 0u ? i : q[i];
-            const float4 o = w.orgRng[slot], d = w.dirFlags[slot];
+            const float4 o = ldS(&w.orgRng[slot]), d = ldS(&w.dirFlags[slot]);
             trv::Ray ray;
             ray.o = f3(o);
             ray.d = f3(d);
@@ -320,14 +330,16 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_const
             tr.init(sc, ray, ray.tmin, 0xffffffffu);
             nStash = 0;
             active = !tr.done();
-            if (!active) w.hit[slot] = make_float4(tr.best.t, tr.best.u, tr.best.v, __int_as_float(tr.best.pos));
+            if (!active) stS(&w.hit[slot], make_float4(tr.best.t, tr.best.u, tr.best.v, __int_as_float(tr.best.pos)));
         }
         if (!__any_sync(0xffffffffu, active)) {
             if (!__any_sync(0xffffffffu, i != 0xffffffffu)) break; /* nothing left to fetch */
             continue;                                              /* every fetched ray finished at once (empty scene) */
         }
         while (true) { /* warp-convergent: no lane leaves this loop alone */
+            TRV_COUNT(cNodeIt);
             if (active && tr.ng.y > 0x00ffffffu) {
+                TRV_COUNT(cNode);
                 const uint2 g = tr.nodeStep(sc, stack);
                 if (g.y != 0u) {
                     if (nStash == EXTEND_STASH) { /* ring full: make room by finishing the current group now (rare) */
@@ -343,7 +355,7 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_const
                     else
                         stash[(nStash++) * TRV_BLOCK] = g;
                 }
-                if (tr.ng.y <= 0x00ffffffu && tr.sp > 0) tr.ng = tr.pop(stack, TRV_BLOCK);
+                if (tr.ng.y <= 0x00ffffffu && tr.sp > 0) tr.ng = tr.pop(stack);
             }
             const bool hasNode = active && tr.ng.y > 0x00ffffffu;
             bool hasTri = active && tr.tg.y != 0u;
@@ -351,7 +363,9 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_const
             unsigned mT = __ballot_sync(0xffffffffu, hasTri);
             if (__popc(mT) >= EXTEND_TRI_ENTER || __popc(mT & ~mN) >= EXTEND_BLOCKED || (mN == 0u && mT != 0u)) {
                 do {
+                    TRV_COUNT(cTriIt);
                     if (hasTri) {
+                        TRV_COUNT(cTri);
                         const uint32_t k = 31u - (uint32_t)__clz(tr.tg.y);
                         tr.tg.y &= ~(1u << k);
                         tr.triTest(sc, (int32_t)(tr.tg.x + k));
@@ -362,13 +376,21 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_const
                 } while (__popc(mT) >= EXTEND_TRI_LEAVE || (mT & ~mN) != 0u);
             }
             if (active && !hasNode && !hasTri) {
-                w.hit[slot] = make_float4(tr.best.t, tr.best.u, tr.best.v, __int_as_float(tr.best.pos));
+                stS(&w.hit[slot], make_float4(tr.best.t, tr.best.u, tr.best.v, __int_as_float(tr.best.pos)));
                 active = false;
             }
             const unsigned mA = __ballot_sync(0xffffffffu, active);
             if (mA == 0u || (!feeder.exhausted && __popc(mA) < EXTEND_MIN_ACTIVE)) break;
         }
     }
+#ifdef PTC_TRAV_STATS
+    statAdd(&w.stats[ST_NODE_VISITS], cNode);
+    statAdd(&w.stats[ST_TRI_TESTS], cTri);
+    if (laneId() == 0) {
+        atomicAdd(&w.stats[ST_NODE_ITERS], (unsigned long long)cNodeIt);
+        atomicAdd(&w.stats[ST_TRI_ITERS], (unsigned long long)cTriIt);
+    }
+#endif
 }
 
 /* ------------------------------------------------------------------ k_shade */
@@ -444,13 +466,13 @@ __global__ void __launch_bounds__(128) k_shade(Wave w, const __grid_constant__ D
         rq.shadow = rq.probe = false;
         if (valid) {
             slot = bounce == 0u ? i : q[i];
-            const float4 h = w.hit[slot];
-            const float4 o4 = w.orgRng[slot], d4 = w.dirFlags[slot];
+            const float4 h = ldS(&w.hit[slot]);
+            const float4 o4 = ldS(&w.orgRng[slot]), d4 = ldS(&w.dirFlags[slot]);
             float3 origin = f3(o4), dir = f3(d4);
             uint32_t rng = __float_as_uint(o4.w), flags = __float_as_uint(d4.w);
             flags = (flags & ~PF_DEPTH_MASK) | (bounce & PF_DEPTH_MASK);
-            float3 beta = f3(w.beta[slot]);
-            float3 radiance = f3(w.radiance[slot]);
+            float3 beta = f3(ldS(&w.beta[slot]));
+            float3 radiance = f3(ldS(&w.radiance[slot]));
             const float3 rayDir = dir;
             const int32_t triPos = __float_as_int(h.w);
             bool stop = false;
@@ -495,9 +517,9 @@ __global__ void __launch_bounds__(128) k_shade(Wave w, const __grid_constant__ D
                         }
                         const bool first = !(flags & PF_SURFACE);
                         if (first) {
-                            w.aovAlbedo[slot] = make_float4(albedo.x, albedo.y, albedo.z, 0.0f);
+                            stS(&w.aovAlbedo[slot], make_float4(albedo.x, albedo.y, albedo.z, 0.0f));
                             float3 nn = fr.n * 0.5f + f3(0.5f);
-                            w.aovNormal[slot] = make_float4(nn.x, nn.y, nn.z, 0.0f);
+                            stS(&w.aovNormal[slot], make_float4(nn.x, nn.y, nn.z, 0.0f));
                         }
                         if (first && !isBlackEps(emissive, lambert ? 0.05f : 0.1f) && !flipped) {
                             radiance += emissive * beta; /* emission only at the first surface (trap T2) */
@@ -578,8 +600,8 @@ __global__ void __launch_bounds__(128) k_shade(Wave w, const __grid_constant__ D
                         col = first ? aov : envFetch(sc, rayDir);
                     }
                     if (first) {
-                        w.aovAlbedo[slot] = make_float4(aov.x, aov.y, aov.z, 0.0f);
-                        w.aovNormal[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        stS(&w.aovAlbedo[slot], make_float4(aov.x, aov.y, aov.z, 0.0f));
+                        stS(&w.aovNormal[slot], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
                     }
                     radiance += col * beta;
                 }
@@ -587,16 +609,16 @@ __global__ void __launch_bounds__(128) k_shade(Wave w, const __grid_constant__ D
             if (doRoulette && !stop) stop = roulette(rng, bounce, beta);
             /* requests that can only return black are dropped (result-identical) */
             if (rq.probe && !sc.anyEmissive) rq.probe = false;
-            w.orgRng[slot] = make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng));
-            w.dirFlags[slot] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(flags));
-            w.beta[slot] = make_float4(beta.x, beta.y, beta.z, 0.0f);
-            w.radiance[slot] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+            stS(&w.orgRng[slot], make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng)));
+            stS(&w.dirFlags[slot], make_float4(dir.x, dir.y, dir.z, __uint_as_float(flags)));
+            stS(&w.beta[slot], make_float4(beta.x, beta.y, beta.z, 0.0f));
+            stS(&w.radiance[slot], make_float4(radiance.x, radiance.y, radiance.z, 0.0f));
             if (rq.shadow) {
-                w.shOrgTmax[slot] = make_float4(rq.shOrigin.x, rq.shOrigin.y, rq.shOrigin.z, rq.shTmax);
-                w.shDirVol[slot] = make_float4(rq.shDir.x, rq.shDir.y, rq.shDir.z, __uint_as_float(flags));
-                w.shContrib[slot] = make_float4(rq.shContrib.x, rq.shContrib.y, rq.shContrib.z, 0.0f);
+                stS(&w.shOrgTmax[slot], make_float4(rq.shOrigin.x, rq.shOrigin.y, rq.shOrigin.z, rq.shTmax));
+                stS(&w.shDirVol[slot], make_float4(rq.shDir.x, rq.shDir.y, rq.shDir.z, __uint_as_float(flags)));
+                stS(&w.shContrib[slot], make_float4(rq.shContrib.x, rq.shContrib.y, rq.shContrib.z, 0.0f));
             }
-            if (rq.probe) w.prBetaPdf[slot] = make_float4(rq.prBeta.x, rq.prBeta.y, rq.prBeta.z, rq.prPdf);
+            if (rq.probe) stS(&w.prBetaPdf[slot], make_float4(rq.prBeta.x, rq.prBeta.y, rq.prBeta.z, rq.prPdf));
             alive = !stop && !lastBounce;
         }
         queuePush(qNext, cntNext, alive, slot);
@@ -608,7 +630,7 @@ __global__ void __launch_bounds__(128) k_shade(Wave w, const __grid_constant__ D
 /* ------------------------------------------------------------------ k_shadow */
 /* lightSampling.glsl:108-144 with nearest-first candidate order (trap T1) */
 __global__ void __launch_bounds__(TRV_BLOCK) k_shadow(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce) {
-    __shared__ uint2 stack[TRV_SHARED_STACK * TRV_BLOCK];
+    TRV_DECLARE_STACK(stack);
     const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_SHADOW];
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounded = (count + 31u) & ~31u;
@@ -617,7 +639,7 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_shadow(Wave w, const __grid_const
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
         if (i < count) {
             const uint32_t slot = w.qShadow[i];
-            const float4 o4 = w.shOrgTmax[slot], d4 = w.shDirVol[slot];
+            const float4 o4 = ldS(&w.shOrgTmax[slot]), d4 = ldS(&w.shDirVol[slot]);
             float3 origin = f3(o4);
             const float3 dir = f3(d4);
             uint32_t vol = __float_as_uint(d4.w);
@@ -629,7 +651,7 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_shadow(Wave w, const __grid_const
                 /* every surface is opaque: any hit shadows; otherwise raySecondary.rmiss */
                 trv::Ray ray{origin, dir, tmin, distanceT};
                 hops++;
-                shadowed = trv::occluded(sc, ray, stack + threadIdx.x);
+                shadowed = trv::occluded(sc, ray, stack);
                 if (!shadowed && (vol & PF_INVOL)) {
                     thr = transmittance(sc, vol >> PF_VOL_SHIFT, tmin, fminf(zfarTrunc, distanceT));
                     shadowed = !(max3(thr) > PT_EPSILON);
@@ -644,7 +666,7 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_shadow(Wave w, const __grid_const
                     uint32_t id0 = 0xffffffffu;
                     bool ended = false;
                     while (!ended) {
-                        trv::HitRec h = trv::nextHit(sc, ray, t0, id0, stack + threadIdx.x);
+                        trv::HitRec h = trv::nextHit(sc, ray, t0, id0, stack);
                         if (h.pos < 0) break;
                         Surf s;
                         loadSurf(sc, h.pos, h.u, h.v, false, s);
@@ -691,12 +713,12 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_shadow(Wave w, const __grid_const
                 }
             }
             if (!shadowed) {
-                const float3 c = f3(w.shContrib[slot]) * thr;
-                float4 r = w.radiance[slot];
+                const float3 c = f3(ldS(&w.shContrib[slot])) * thr;
+                float4 r = ldS(&w.radiance[slot]);
                 r.x += c.x;
                 r.y += c.y;
                 r.z += c.z;
-                w.radiance[slot] = r;
+                stS(&w.radiance[slot], r);
             }
         }
     }
@@ -706,7 +728,7 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_shadow(Wave w, const __grid_const
 /* ------------------------------------------------------------------ k_probe */
 /* next_event_estimation.glsl:1-33 + rayNEE.* with nearest-first candidate order (trap T1) */
 __global__ void __launch_bounds__(TRV_BLOCK) k_probe(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce) {
-    __shared__ uint2 stack[TRV_SHARED_STACK * TRV_BLOCK];
+    TRV_DECLARE_STACK(stack);
     const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_PROBE];
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t rounded = (count + 31u) & ~31u;
@@ -715,7 +737,7 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_probe(Wave w, const __grid_consta
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
         if (i < count) {
             const uint32_t slot = w.qProbe[i];
-            const float4 o4 = w.orgRng[slot], d4 = w.dirFlags[slot], bp = w.prBetaPdf[slot];
+            const float4 o4 = ldS(&w.orgRng[slot]), d4 = ldS(&w.dirFlags[slot]), bp = ldS(&w.prBetaPdf[slot]);
             float3 origin = f3(o4);
             const float3 dir = f3(d4);
             uint32_t vol = __float_as_uint(d4.w);
@@ -730,7 +752,7 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_probe(Wave w, const __grid_consta
                 uint32_t id0 = 0xffffffffu;
                 bool ended = false;
                 while (!ended) {
-                    trv::HitRec h = trv::nextHit(sc, ray, t0, id0, stack + threadIdx.x);
+                    trv::HitRec h = trv::nextHit(sc, ray, t0, id0, stack);
                     if (h.pos < 0) break;
                     Surf s;
                     loadSurf(sc, h.pos, h.u, h.v, false, s);
@@ -807,11 +829,11 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_probe(Wave w, const __grid_consta
             if (!isBlack(emissive)) {
                 const float wgt = powerHeuristic(bp.w, pdf);
                 const float3 c = thr * emissive * f3(bp) * wgt;
-                float4 r = w.radiance[slot];
+                float4 r = ldS(&w.radiance[slot]);
                 r.x += c.x;
                 r.y += c.y;
                 r.z += c.z;
-                w.radiance[slot] = r;
+                stS(&w.radiance[slot], r);
             }
         }
     }
@@ -827,9 +849,9 @@ __global__ void __launch_bounds__(256) k_accumulate(Wave w, const __grid_constan
     float3 cr = f3(0.0f), ca = f3(0.0f), cn = f3(0.0f);
     for (uint32_t s = 0; s < nSamples; s++) {
         const size_t slot = (size_t)s * rc.nPixLocal + p;
-        cr += f3(w.radiance[slot]) / total;
-        ca += f3(w.aovAlbedo[slot]) / total;
-        cn += f3(w.aovNormal[slot]) / total;
+        cr += f3(ldS(&w.radiance[slot])) / total;
+        ca += f3(ldS(&w.aovAlbedo[slot])) / total;
+        cn += f3(ldS(&w.aovNormal[slot])) / total;
     }
     const uint32_t pixel = rc.pixmap ? rc.pixmap[p] : p;
     float4 r = accR[pixel], a = accA[pixel], n = accN[pixel];
@@ -855,12 +877,12 @@ __global__ void k_collect_stats(Wave w, uint32_t depth) {
 /* ------------------------------------------------------------------ parity-hook kernels */
 __global__ void __launch_bounds__(TRV_BLOCK) k_trace_closest(const __grid_constant__ DScene sc, const float *__restrict__ rays, int n, int *inst, int *prim,
                                                              float *t, float *u, float *v) {
-    __shared__ uint2 stack[TRV_SHARED_STACK * TRV_BLOCK];
+    TRV_DECLARE_STACK(stack);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float *r = rays + (size_t)i * 8;
     trv::Ray ray{f3(r[0], r[1], r[2]), f3(r[4], r[5], r[6]), r[3], r[7]};
-    trv::HitRec h = trv::closestHit(sc, ray, stack + threadIdx.x);
+    trv::HitRec h = trv::closestHit(sc, ray, stack);
     if (h.pos >= 0) {
         inst[i] = (int)__float_as_uint(sc.tris[3 * (size_t)h.pos + 0].w);
         prim[i] = (int)__float_as_uint(sc.tris[3 * (size_t)h.pos + 1].w);
