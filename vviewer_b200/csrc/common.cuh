@@ -58,6 +58,8 @@ struct DInstance {
     uint32_t pad;
 };
 
+#define TEX_WHITE 0xffffffffu /* texture whose every texel is (255, 255, 255, 255): reads as exactly 1 without a fetch */
+
 struct DScene {
     const ptc_vertex *vertices;
     const uint32_t *indices;
@@ -65,13 +67,15 @@ struct DScene {
     const ptc_material *materials;
     const ptc_light_data *lightData;
     const ptc_light_instance *lightInstances;
-    const cudaTextureObject_t *textures;
+    const cudaTextureObject_t *texClasses; /* one LAYERED texture object per (width, height, sRGB) class */
+    const uint32_t *texRef;                /* per texture: class << 16 | layer, or TEX_WHITE */
     cudaTextureObject_t cubemap;
     uint32_t nInstances, nMaterials, nLightInstances, nTextures;
     uint32_t hasCubemap;
     /* acceleration structure (see lbvh.cuh) */
     const float4 *bvhNodes; /* 5 x float4 per 8-wide compressed node, breadth first, node 0 = root */
     const float4 *tris;     /* 3 x float4 per world triangle, wide-node order */
+    const float4 *shading;  /* 9 x float4 per world triangle, same order (lbvh.cuh::k_gather_shading) */
     uint32_t nTris;
     uint32_t nWideNodes;
     /* scene-level switches that let whole ray types be skipped without changing any result */

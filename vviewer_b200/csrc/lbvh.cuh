@@ -431,8 +431,35 @@ __global__ void k_gather_tris(uint32_t n, const uint32_t *__restrict__ triMap, c
     wideOrder[k] = t;
 }
 
+/* Shading records, one per triangle in traversal order, 9 x float4 = 144 B, object space (same numbers the reference's
+ * closest-hit shaders fetch through InstanceData -> index buffer -> 3 x Vertex, process_hit.glsl:1-17, in one contiguous read):
+ *   r0 = (p0, uv0.x) r1 = (p1, uv0.y) r2 = (p2, uv1.x) r3 = (n0, uv1.y) r4 = (n1, uv2.x) r5 = (n2, uv2.y)
+ *   r6 = (tangent0, bits(instance)) r7 = (tangent1, bits(primitive)) r8 = (tangent2, 0) */
+__global__ void k_gather_shading(uint32_t n, const uint32_t *__restrict__ wideOrder, const float4 *__restrict__ trisUnsorted,
+                                 const ptc_vertex *__restrict__ vertices, const uint32_t *__restrict__ indices,
+                                 const DInstance *__restrict__ instances, float4 *__restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t t = wideOrder[k];
+    const uint32_t inst = __float_as_uint(trisUnsorted[3 * (size_t)t + 0].w), prim = __float_as_uint(trisUnsorted[3 * (size_t)t + 1].w);
+    const DInstance &I = instances[inst];
+    const uint32_t *ind = indices + I.firstIndex + 3 * (size_t)prim;
+    const ptc_vertex &a = vertices[I.firstVertex + ind[0]], &b = vertices[I.firstVertex + ind[1]], &c = vertices[I.firstVertex + ind[2]];
+    float4 *r = out + 9 * (size_t)k;
+    r[0] = make_float4(a.position[0], a.position[1], a.position[2], a.uv[0]);
+    r[1] = make_float4(b.position[0], b.position[1], b.position[2], a.uv[1]);
+    r[2] = make_float4(c.position[0], c.position[1], c.position[2], b.uv[0]);
+    r[3] = make_float4(a.normal[0], a.normal[1], a.normal[2], b.uv[1]);
+    r[4] = make_float4(b.normal[0], b.normal[1], b.normal[2], c.uv[0]);
+    r[5] = make_float4(c.normal[0], c.normal[1], c.normal[2], c.uv[1]);
+    r[6] = make_float4(a.tangent[0], a.tangent[1], a.tangent[2], __uint_as_float(inst));
+    r[7] = make_float4(b.tangent[0], b.tangent[1], b.tangent[2], __uint_as_float(prim));
+    r[8] = make_float4(c.tangent[0], c.tangent[1], c.tangent[2], 0.0f);
+}
+
 struct Build {
     DBuf<float4> trisUnsorted, triLo, triHi, nodeLo, nodeHi;
+    DBuf<float4> shading;          /* 9 x float4 per triangle, traversal order (k_gather_shading) */
     DBuf<float4> trav;             /* what traversal reads, ONE allocation so that one L2 access-policy window covers it:
                                       [5 x float4 per wide node, breadth first][3 x float4 per triangle, wide-node order] */
     DBuf<uint4> wide;              /* collapse output before compaction (sized by the node bound) */
@@ -447,7 +474,7 @@ struct Build {
     int bits = 0;
 
     size_t bytes() const {
-        return trisUnsorted.bytes() + trav.bytes() + triLo.bytes() + triHi.bytes() + nodeLo.bytes() + nodeHi.bytes() + wide.bytes() +
+        return trisUnsorted.bytes() + trav.bytes() + shading.bytes() + triLo.bytes() + triHi.bytes() + nodeLo.bytes() + nodeHi.bytes() + wide.bytes() +
                keys.bytes() + keysSorted.bytes() + ids.bytes() + order.bytes() + arrivals.bytes() + parent.bytes() + left.bytes() +
                right.bytes() + sortTemp.bytes() + triMap.bytes() + wideOrder.bytes() + rangeEnd.bytes() + rootOf.bytes() + wideTmp.bytes() +
                counts.bytes() + inclusive.bytes() + scanTemp.bytes();
@@ -548,6 +575,9 @@ struct Build {
         trav.alloc(5 * (size_t)nWide + 3 * (size_t)n);
         CUDA_TRY(cudaMemcpyAsync(trav.p, wide.p, (size_t)nWide * 80, cudaMemcpyDeviceToDevice, s));
         k_gather_tris<<<G, B, 0, s>>>(n, triMap.p, order.p, trisUnsorted.p, trav.p + 5 * (size_t)nWide, wideOrder.p);
+        launches++;
+        shading.alloc(9 * (size_t)n);
+        k_gather_shading<<<G, B, 0, s>>>(n, wideOrder.p, trisUnsorted.p, vertices, indices, instances, shading.p);
         launches++;
         CUDA_TRY(cudaGetLastError());
         return launches;

@@ -18,7 +18,9 @@
 
 namespace {
 
-struct TextureSlot {
+/* all textures of one (width, height, sRGB) class live in one layered array behind one texture object */
+struct TextureClass {
+    uint32_t width = 0, height = 0, srgb = 0, layers = 0;
     cudaArray_t array = nullptr;
     cudaTextureObject_t tex = 0;
 };
@@ -39,8 +41,9 @@ struct ptc_ctx {
     DBuf<ptc_material> materials;
     DBuf<ptc_light_data> lightData;
     DBuf<ptc_light_instance> lightInstances;
-    DBuf<cudaTextureObject_t> texTable;
-    std::vector<TextureSlot> textures;
+    DBuf<cudaTextureObject_t> texClassTable;
+    DBuf<uint32_t> texRef;
+    std::vector<TextureClass> texClasses;
     cudaArray_t cubeArray = nullptr;
     cudaTextureObject_t cubeTex = 0;
     uint32_t cubeN = 0;
@@ -61,11 +64,11 @@ struct ptc_ctx {
     ptc_stats stats{};
 
     void freeTextures() {
-        for (auto &t : textures) {
+        for (auto &t : texClasses) {
             if (t.tex) cudaDestroyTextureObject(t.tex);
             if (t.array) cudaFreeArray(t.array);
         }
-        textures.clear();
+        texClasses.clear();
         if (cubeTex) cudaDestroyTextureObject(cubeTex);
         if (cubeArray) cudaFreeArray(cubeArray);
         cubeTex = 0;
@@ -115,7 +118,9 @@ DScene makeDScene(ptc_ctx *c) {
     s.materials = c->materials.p;
     s.lightData = c->lightData.p;
     s.lightInstances = c->lightInstances.p;
-    s.textures = c->texTable.p;
+    s.texClasses = c->texClassTable.p;
+    s.texRef = c->texRef.p;
+    s.shading = c->accel.shading.p;
     s.cubemap = c->cubeTex;
     s.nInstances = c->nInstances;
     s.nMaterials = c->nMaterials;
@@ -132,27 +137,78 @@ DScene makeDScene(ptc_ctx *c) {
     return s;
 }
 
-void createTexture2D(ptc_ctx *c, const ptc_texture &in, TextureSlot &slot) {
-    /* every texture becomes RGBA8 (an R8 source reads back as (r, 0, 0, 1) like VK_FORMAT_R8_UNORM) */
-    std::vector<uint8_t> rgba((size_t)in.width * in.height * 4);
-    for (size_t p = 0; p < (size_t)in.width * in.height; p++) {
-        uint8_t px[4] = {0, 0, 0, 255};
-        for (uint32_t k = 0; k < in.channels && k < 4; k++) px[k] = in.data[p * in.channels + k];
-        std::memcpy(&rgba[p * 4], px, 4);
+/* Uploads the scene's 8-bit textures: every texture becomes RGBA8 (an R8 source reads back as (r, 0, 0, 1) like
+ * VK_FORMAT_R8_UNORM), grouped into layered arrays by (width, height, sRGB).  Sampler = the reference's
+ * (VulkanTexture.cpp:219-232): linear, REPEAT, normalised coordinates, sRGB decode before filtering. */
+void createTextures(ptc_ctx *c, const ptc_scene_desc *sd) {
+    const uint32_t n = sd->n_textures;
+    std::vector<uint32_t> ref(n, 0);
+    std::vector<std::vector<uint32_t>> members;
+    for (uint32_t t = 0; t < n; t++) {
+        const ptc_texture &in = sd->textures[t];
+        const size_t texels = (size_t)in.width * in.height;
+        bool white = in.channels == 4;
+        for (size_t p = 0; white && p < texels * 4; p++) white = in.data[p] == 255;
+        if (white) {
+            ref[t] = TEX_WHITE;
+            continue;
+        }
+        uint32_t cls = 0;
+        for (; cls < c->texClasses.size(); cls++) {
+            const TextureClass &k = c->texClasses[cls];
+            if (k.width == in.width && k.height == in.height && k.srgb == (in.srgb ? 1u : 0u) && members[cls].size() < 2048) break;
+        }
+        if (cls == c->texClasses.size()) {
+            TextureClass k;
+            k.width = in.width;
+            k.height = in.height;
+            k.srgb = in.srgb ? 1u : 0u;
+            c->texClasses.push_back(k);
+            members.emplace_back();
+        }
+        if (cls > 0xfffeu) throw CudaError{"too many texture classes"};
+        ref[t] = (cls << 16) | (uint32_t)members[cls].size();
+        members[cls].push_back(t);
     }
-    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
-    CUDA_TRY(cudaMallocArray(&slot.array, &fmt, in.width, in.height));
-    CUDA_TRY(cudaMemcpy2DToArray(slot.array, 0, 0, rgba.data(), (size_t)in.width * 4, (size_t)in.width * 4, in.height, cudaMemcpyHostToDevice));
-    cudaResourceDesc rd{};
-    rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = slot.array;
-    cudaTextureDesc td{};
-    td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap; /* REPEAT */
-    td.filterMode = cudaFilterModeLinear;
-    td.readMode = cudaReadModeNormalizedFloat;
-    td.normalizedCoords = 1;
-    td.sRGB = in.srgb ? 1 : 0; /* VK_FORMAT_R8G8B8A8_SRGB: decode before filtering */
-    CUDA_TRY(cudaCreateTextureObject(&slot.tex, &rd, &td, nullptr));
+    std::vector<cudaTextureObject_t> table(c->texClasses.size());
+    for (size_t cls = 0; cls < c->texClasses.size(); cls++) {
+        TextureClass &k = c->texClasses[cls];
+        k.layers = (uint32_t)members[cls].size();
+        const size_t texels = (size_t)k.width * k.height;
+        std::vector<uint8_t> rgba(texels * 4 * k.layers);
+        for (uint32_t l = 0; l < k.layers; l++) {
+            const ptc_texture &in = sd->textures[members[cls][l]];
+            uint8_t *dst = rgba.data() + texels * 4 * l;
+            for (size_t p = 0; p < texels; p++) {
+                uint8_t px[4] = {0, 0, 0, 255};
+                for (uint32_t ch = 0; ch < in.channels && ch < 4; ch++) px[ch] = in.data[p * in.channels + ch];
+                std::memcpy(dst + p * 4, px, 4);
+            }
+        }
+        cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+        CUDA_TRY(cudaMalloc3DArray(&k.array, &fmt, make_cudaExtent(k.width, k.height, k.layers), cudaArrayLayered));
+        cudaMemcpy3DParms cp{};
+        cp.srcPtr = make_cudaPitchedPtr(rgba.data(), (size_t)k.width * 4, k.width, k.height);
+        cp.dstArray = k.array;
+        cp.extent = make_cudaExtent(k.width, k.height, k.layers);
+        cp.kind = cudaMemcpyHostToDevice;
+        CUDA_TRY(cudaMemcpy3D(&cp));
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = k.array;
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap; /* REPEAT */
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 1;
+        td.sRGB = k.srgb ? 1 : 0; /* VK_FORMAT_R8G8B8A8_SRGB: decode before filtering */
+        CUDA_TRY(cudaCreateTextureObject(&k.tex, &rd, &td, nullptr));
+        table[cls] = k.tex;
+    }
+    c->nTextures = n;
+    c->texRef.upload(ref.data(), ref.size(), c->stream);
+    c->texClassTable.upload(table.data(), table.size(), c->stream);
+    CUDA_TRY(cudaStreamSynchronize(c->stream)); /* the host vectors die here */
 }
 
 void createCubemap(ptc_ctx *c, const ptc_env &env) {
@@ -324,8 +380,16 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     rc.pixmap = pixmapPtr;
     DScene sc = makeDScene(c);
 
-    const int gridTrace = c->smCount * 8;  /* persistent: 8 blocks of 128 threads per SM */
-    const int gridShade = c->smCount * 8;
+    /* persistent kernels: exactly as many blocks as are resident at once (multiples of the SM count) */
+    auto residentGrid = [&](const void *kernel, int block) {
+        int perSm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, block, 0) != cudaSuccess || perSm < 1) perSm = 1;
+        return c->smCount * perSm;
+    };
+    const int gridExtend = residentGrid((const void *)wf::k_extend, TRV_BLOCK);
+    const int gridShade = residentGrid((const void *)wf::k_shade, 128);
+    const int gridShadow = residentGrid((const void *)wf::k_shadow, TRV_BLOCK);
+    const int gridProbe = residentGrid((const void *)wf::k_probe, TRV_BLOCK);
     uint64_t launches = 0, traceLaunches = 0;
     double traceMs = 0, shadeMs = 0, shadowMs = 0;
     const bool timeKernels = (rp->flags & PTC_FLAG_TIME_KERNELS) != 0;
@@ -359,16 +423,16 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
                 wf::k_raygen<<<(nSlots + 255) / 256, 256, 0, s>>>(w, rc, nSlots, b * rp->batch_size + s0);
                 launches++;
                 for (uint32_t d = 0; d < rp->depth; d++) {
-                    timed(traceMs, [&] { wf::k_extend<<<gridTrace, TRV_BLOCK, 0, s>>>(w, sc, d); });
+                    timed(traceMs, [&] { wf::k_extend<<<gridExtend, TRV_BLOCK, 0, s>>>(w, sc, d); });
                     timed(shadeMs, [&] { wf::k_shade<<<gridShade, 128, 0, s>>>(w, sc, rc, d); });
                     launches += 2;
                     traceLaunches++;
                     if (rc.totalLights > 0) {
-                        timed(shadowMs, [&] { wf::k_shadow<<<gridTrace, TRV_BLOCK, 0, s>>>(w, sc, rc, d); });
+                        timed(shadowMs, [&] { wf::k_shadow<<<gridShadow, TRV_BLOCK, 0, s>>>(w, sc, rc, d); });
                         launches++;
                     }
                     if (c->anyEmissive) {
-                        timed(shadowMs, [&] { wf::k_probe<<<gridTrace, TRV_BLOCK, 0, s>>>(w, sc, rc, d); });
+                        timed(shadowMs, [&] { wf::k_probe<<<gridProbe, TRV_BLOCK, 0, s>>>(w, sc, rc, d); });
                         launches++;
                     }
                 }
@@ -529,16 +593,12 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
     c->instances.upload(inst.data(), inst.size(), s);
 
     c->freeTextures();
-    c->textures.resize(sd->n_textures);
-    std::vector<cudaTextureObject_t> table(sd->n_textures);
     for (uint32_t t = 0; t < sd->n_textures; t++) {
         const ptc_texture &in = sd->textures[t];
         if (in.channels != 1 && in.channels != 4) return fail(c, "texture channels must be 1 or 4");
-        createTexture2D(c, in, c->textures[t]);
-        table[t] = c->textures[t].tex;
+        if (!in.data || !in.width || !in.height) return fail(c, "texture without data");
     }
-    c->nTextures = sd->n_textures;
-    c->texTable.upload(table.data(), table.size(), s);
+    createTextures(c, sd);
     createCubemap(c, sd->env);
     CUDA_TRY(cudaStreamSynchronize(s));
     c->sceneUploaded = true;

@@ -88,9 +88,15 @@ PTC_D float3 mulNormal(const float *a /*3x3 row-major inverse*/, float3 n) { /* 
 }
 PTC_D float3 ld3(const float *p) { return f3(__ldg(p), __ldg(p + 1), __ldg(p + 2)); }
 
+/* Bindless material maps.  A warp's 32 hits touch many different textures, and a texture instruction needs a warp-uniform
+ * handle (per-lane handles are serialised by a compiler-generated loop over the unique handles: 12 % of k_shade's
+ * instructions at 6 of 32 lanes, profiles/r1_v2).  So textures of one (width, height, sRGB) class share ONE layered texture
+ * object and the lane picks its layer; all-white textures (the engine's defaults) are not fetched at all. */
 PTC_D float4 texFetch(const DScene &sc, uint32_t idx, float u, float v) {
     if (idx >= sc.nTextures) return make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-    return tex2D<float4>(sc.textures[idx], u, v);
+    const uint32_t r = __ldg(&sc.texRef[idx]);
+    if (r == TEX_WHITE) return make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    return tex2DLayered<float4>(__ldg(&sc.texClasses[r >> 16]), u, v, (int)(r & 0xffffu));
 }
 PTC_D float3 envFetch(const DScene &sc, float3 d) {
     if (!sc.hasCubemap) return f3(0.0f);
@@ -107,28 +113,23 @@ struct Surf {
     float3 pos, n, t; /* world position, unnormalised->normalised world normal / tangent */
 };
 PTC_D void loadSurf(const DScene &sc, int32_t triPos, float u, float v, bool wantFrame, Surf &s) {
-    const float4 a = __ldg(&sc.tris[3 * (size_t)triPos + 0]);
-    const float4 b = __ldg(&sc.tris[3 * (size_t)triPos + 1]);
-    const uint32_t instIdx = __float_as_uint(a.w), prim = __float_as_uint(b.w);
-    const DInstance *I = &sc.instances[instIdx];
+    const float4 *__restrict__ r = sc.shading + 9 * (size_t)triPos;
+    const float4 r0 = __ldg(r + 0), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3), r4 = __ldg(r + 4), r5 = __ldg(r + 5), r6 = __ldg(r + 6);
+    const DInstance *I = &sc.instances[__float_as_uint(r6.w)];
     s.inst = I;
     s.mat = &sc.materials[I->material];
-    const uint32_t *ind = sc.indices + I->firstIndex + 3 * (size_t)prim;
-    const ptc_vertex *V0 = &sc.vertices[I->firstVertex + __ldg(ind + 0)];
-    const ptc_vertex *V1 = &sc.vertices[I->firstVertex + __ldg(ind + 1)];
-    const ptc_vertex *V2 = &sc.vertices[I->firstVertex + __ldg(ind + 2)];
     const float w0 = 1.0f - u - v, w1 = u, w2 = v;
-    s.p0 = ld3(V0->position);
-    s.p1 = ld3(V1->position);
-    s.p2 = ld3(V2->position);
-    s.uv = make_float2(__ldg(&V0->uv[0]) * w0 + __ldg(&V1->uv[0]) * w1 + __ldg(&V2->uv[0]) * w2,
-                       __ldg(&V0->uv[1]) * w0 + __ldg(&V1->uv[1]) * w1 + __ldg(&V2->uv[1]) * w2);
+    s.p0 = f3(r0);
+    s.p1 = f3(r1);
+    s.p2 = f3(r2);
+    s.uv = make_float2(r0.w * w0 + r2.w * w1 + r4.w * w2, r1.w * w0 + r3.w * w1 + r5.w * w2);
     float3 lp = s.p0 * w0 + s.p1 * w1 + s.p2 * w2;
     s.pos = mulPoint(I->m, lp);
-    float3 ln = ld3(V0->normal) * w0 + ld3(V1->normal) * w1 + ld3(V2->normal) * w2;
+    float3 ln = f3(r3) * w0 + f3(r4) * w1 + f3(r5) * w2;
     s.n = normalize(mulNormal(I->nrm, ln));
     if (wantFrame) {
-        float3 lt = ld3(V0->tangent) * w0 + ld3(V1->tangent) * w1 + ld3(V2->tangent) * w2;
+        const float4 r7 = __ldg(r + 7), r8 = __ldg(r + 8);
+        float3 lt = f3(r6) * w0 + f3(r7) * w1 + f3(r8) * w2;
         s.t = normalize(mulNormal(I->nrm, lt));
     }
 }
@@ -448,7 +449,7 @@ PTC_D bool roulette(uint32_t &rng, uint32_t depth, float3 &beta) {
     return false;
 }
 
-__global__ void __launch_bounds__(128) k_shade(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce) {
+__global__ void __launch_bounds__(128, 6) k_shade(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce) {
     const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_ACTIVE];
     const uint32_t *__restrict__ q = w.queue[bounce & 1u];
     uint32_t *__restrict__ qNext = w.queue[(bounce + 1u) & 1u];
