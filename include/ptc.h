@@ -205,6 +205,15 @@ PTC_API int ptc_upload_scene(ptc_ctx *ctx, const ptc_scene_desc *scene);
 /* replaces the driver BLAS/TLAS builds: on-device LBVH over world-space triangles */
 PTC_API int ptc_build_accel(ptc_ctx *ctx);
 
+/* Hierarchy over the Morton-sorted triangles, before the collapse to the 8-wide compressed BVH:
+ *   PTC_HIERARCHY_LBVH  Karras 2012 radix tree (splits at the highest differing Morton bit)
+ *   PTC_HIERARCHY_PLOC  parallel locally-ordered clustering (Meister & Bittner 2018) with the given search radius
+ *                       (1..32, 0 = default 16): bottom-up merging of area-nearest neighbours along the Morton order.
+ * Both are built on the device and restated on the CPU by the oracle, bit for bit.  Default: PLOC (fewer node visits per
+ * ray); the environment variable PTC_HIERARCHY=lbvh|ploc overrides the default at ptc_create.  Call before ptc_build_accel. */
+enum ptc_hierarchy { PTC_HIERARCHY_LBVH = 0, PTC_HIERARCHY_PLOC = 1 };
+PTC_API int ptc_set_build_options(ptc_ctx *ctx, uint32_t hierarchy, uint32_t ploc_radius);
+
 /* ---------------------------------------------------------------- render */
 /* replaces render(VkDescriptorSet) batch loop + readback (VulkanRendererPathTracing.cpp:791-956).
  * Outputs: width*height*4 floats each, row-major, top-left origin, alpha = 1; any may be NULL. Blocking. */

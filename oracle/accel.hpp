@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <functional>
 #include "omath.hpp"
 
 namespace orc {
@@ -230,7 +231,9 @@ struct LBVH {
     std::vector<uint64_t> morton; /* sorted */
     std::vector<uint32_t> order;  /* sorted position -> world triangle id */
     std::vector<int32_t> parent, left, right; /* 2n-1 nodes; internal 0..n-2, leaf k -> n-1+k */
-    std::vector<int32_t> rangeEnd;            /* internal node i covers sorted positions [min(i, rangeEnd[i]), max(i, rangeEnd[i])] */
+    std::vector<uint32_t> subCount;           /* triangles below each internal node */
+    int32_t root = 0;                         /* Karras: 0; PLOC: n - 2 (the last node created); single triangle: leaf 0 */
+    uint32_t hierarchy = 1, plocRadius = 16;  /* PTC_HIERARCHY_PLOC by default, like the device build */
     std::vector<AABB> box;
 
     static inline int clz64(uint64_t x) { return x ? __builtin_clzll(x) : 64; }
@@ -279,8 +282,13 @@ struct LBVH {
         left.assign(nn, -1);
         right.assign(nn, -1);
         box.assign(nn, AABB());
-        rangeEnd.assign(n, 0);
+        subCount.assign(n, 0);
+        root = 0;
         for (uint64_t k = 0; k < n; k++) box[n - 1 + k] = tb[order[k]];
+        if (hierarchy == 1 && n > 1) {
+            ploc();
+            return;
+        }
         for (int64_t i = 0; i + 1 < (int64_t)n; i++) {
             /* Karras 2012, "Maximizing parallelism in the construction of BVHs, octrees and k-d trees" */
             int d = (delta(i, i + 1) - delta(i, i - 1)) >= 0 ? 1 : -1;
@@ -306,9 +314,68 @@ struct LBVH {
             right[i] = R;
             parent[L] = (int32_t)i;
             parent[R] = (int32_t)i;
-            rangeEnd[i] = (int32_t)j;
+            subCount[i] = (uint32_t)(hi - lo + 1);
         }
         if (n > 1) fit(0);
+    }
+    static float mergedHalfArea(const AABB &a, const AABB &b) {
+        AABB m = a;
+        m.grow(b);
+        float ex = m.hi.x - m.lo.x, ey = m.hi.y - m.lo.y, ez = m.hi.z - m.lo.z;
+        float p = ex * ey;
+        float q = ey * ez;
+        float r = ez * ex;
+        return (p + q) + r;
+    }
+    /* Parallel locally-ordered clustering (Meister & Bittner 2018), restated sequentially round by round exactly like
+     * vviewer_b200/csrc/lbvh.cuh: nearest neighbour by merged half-area within +-radius positions of the Morton-ordered
+     * cluster list (ties: smaller position), mutual pairs merge into a node numbered in position order, list compacted. */
+    void ploc() {
+        const int64_t r = (int64_t)std::min<uint32_t>(std::max<uint32_t>(plocRadius, 1u), 32u);
+        std::vector<int32_t> cid(n), cidNext;
+        for (uint64_t k = 0; k < n; k++) cid[k] = (int32_t)(n - 1 + k);
+        uint32_t nextNode = 0;
+        auto tris = [&](int32_t node) { return node >= (int32_t)(n - 1) ? 1u : subCount[node]; };
+        while (cid.size() > 1) {
+            const int64_t c = (int64_t)cid.size();
+            std::vector<int64_t> nn(c);
+            for (int64_t i = 0; i < c; i++) {
+                float bestA = 0.0f;
+                int64_t best = -1;
+                for (int64_t j = std::max<int64_t>(0, i - r); j <= std::min<int64_t>(c - 1, i + r); j++) {
+                    if (j == i) continue;
+                    float a = mergedHalfArea(box[cid[i]], box[cid[j]]);
+                    if (best < 0 || a < bestA) {
+                        bestA = a;
+                        best = j;
+                    }
+                }
+                nn[i] = best;
+            }
+            cidNext.clear();
+            for (int64_t i = 0; i < c; i++) {
+                const int64_t j = nn[i];
+                const bool mutual = nn[j] == i;
+                if (mutual && i > j) continue; /* merged into its partner */
+                if (mutual) {
+                    const int32_t id = (int32_t)nextNode++;
+                    const int32_t L = cid[i], R = cid[j];
+                    left[id] = L;
+                    right[id] = R;
+                    parent[L] = id;
+                    parent[R] = id;
+                    subCount[id] = tris(L) + tris(R);
+                    AABB b = box[L];
+                    b.grow(box[R]);
+                    box[id] = b;
+                    cidNext.push_back(id);
+                } else {
+                    cidNext.push_back(cid[i]);
+                }
+            }
+            cid.swap(cidNext);
+        }
+        root = (int32_t)(n - 2);
     }
     void fit(int32_t root) {
         /* iterative post-order */
@@ -371,18 +438,19 @@ struct WideBVH {
         const int64_t n = (int64_t)L.n;
         if (n == 0) return;
         triOrder.resize(n);
-        auto subTris = [&](int32_t node) -> uint32_t {
-            if (node >= n - 1) return 1u;
-            int32_t j = L.rangeEnd[node];
-            return (uint32_t)std::abs(j - node) + 1u;
-        };
-        auto subFirst = [&](int32_t node) -> uint32_t {
-            if (node >= n - 1) return (uint32_t)(node - (n - 1));
-            return (uint32_t)std::min(node, L.rangeEnd[node]);
+        auto subTris = [&](int32_t node) -> uint32_t { return node >= n - 1 ? 1u : L.subCount[node]; };
+        /* sorted positions of the triangles below a small subtree, left to right */
+        std::function<void(int32_t, std::vector<uint32_t> &)> subLeaves = [&](int32_t node, std::vector<uint32_t> &out) {
+            if (node >= n - 1) {
+                out.push_back((uint32_t)(node - (n - 1)));
+                return;
+            }
+            subLeaves(L.left[node], out);
+            subLeaves(L.right[node], out);
         };
         const uint32_t LEAF = 3;
         std::vector<int32_t> fifo; /* binary root of wide node k */
-        fifo.push_back(0);
+        fifo.push_back(n == 1 ? 0 : L.root);
         uint32_t triBase = 0;
         for (size_t id = 0; id < fifo.size(); id++) {
             const int32_t root = fifo[id];
@@ -488,8 +556,9 @@ struct WideBVH {
                     fifo.push_back(c);
                 } else {
                     meta[sl] = (((1u << ct) - 1u) << 5) | off;
-                    const uint32_t first = subFirst(c);
-                    for (uint32_t j = 0; j < ct; j++) triOrder[triBase + off + j] = L.order[first + j];
+                    std::vector<uint32_t> leaves;
+                    subLeaves(c, leaves);
+                    for (uint32_t j = 0; j < ct; j++) triOrder[triBase + off + j] = L.order[leaves[j]];
                     off += ct;
                 }
             }

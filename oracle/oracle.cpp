@@ -82,6 +82,7 @@ float srgbToLinear(float c) { return c <= 0.04045f ? c / 12.92f : std::pow((c + 
 
 struct ptc_ctx {
     std::string err;
+    uint32_t hierarchy = 1, plocRadius = 16; /* ptc_set_build_options / PTC_HIERARCHY, like the device build */
     /* scene */
     std::vector<ptc_vertex> vertices;
     std::vector<uint32_t> indices;
@@ -879,6 +880,14 @@ PTC_API const char *ptc_backend_name(void) { return "cpu-oracle"; }
 PTC_API int ptc_create(ptc_ctx **out, const int *, int) {
     if (!out) return 1;
     *out = new ptc_ctx();
+    if (const char *h = getenv("PTC_HIERARCHY")) {
+        if (!strcmp(h, "lbvh")) (*out)->hierarchy = 0;
+        if (!strcmp(h, "ploc")) (*out)->hierarchy = 1;
+    }
+    if (const char *r = getenv("PTC_PLOC_RADIUS")) {
+        const int v = atoi(r);
+        if (v >= 1 && v <= 32) (*out)->plocRadius = (uint32_t)v;
+    }
     return 0;
 }
 PTC_API void ptc_destroy(ptc_ctx *ctx) { delete ctx; }
@@ -1073,10 +1082,23 @@ PTC_API int ptc_trace_closest(ptc_ctx *c, const float *rays, int n, int *inst, i
     return 0;
 }
 
+PTC_API int ptc_set_build_options(ptc_ctx *c, uint32_t hierarchy, uint32_t ploc_radius) {
+    if (!c) return 1;
+    if (hierarchy > 1 || ploc_radius > 32) return fail(c, "bad build options");
+    c->hierarchy = hierarchy;
+    c->plocRadius = ploc_radius ? ploc_radius : 16u;
+    c->lbvh = LBVH();
+    return 0;
+}
+
 PTC_API int ptc_get_lbvh(ptc_ctx *c, uint64_t *n_out, uint64_t *morton, uint32_t *order, int32_t *parent, int32_t *left,
                          int32_t *right, float *aabb) {
     if (!c) return 1;
-    if (c->lbvh.n != c->tris.size() || c->lbvh.morton.empty()) c->lbvh.build(c->tris);
+    if (c->lbvh.n != c->tris.size() || c->lbvh.morton.empty()) {
+        c->lbvh.hierarchy = c->hierarchy;
+        c->lbvh.plocRadius = c->plocRadius;
+        c->lbvh.build(c->tris);
+    }
     const LBVH &L = c->lbvh;
     if (n_out) *n_out = L.n;
     if (L.n == 0) return 0;
@@ -1096,7 +1118,11 @@ PTC_API int ptc_get_lbvh(ptc_ctx *c, uint64_t *n_out, uint64_t *morton, uint32_t
 
 PTC_API int ptc_get_wide_bvh(ptc_ctx *c, uint64_t *n_nodes_out, uint64_t *n_tris_out, uint32_t *node_words, uint32_t *tri_order) {
     if (!c) return 1;
-    if (c->lbvh.n != c->tris.size() || c->lbvh.morton.empty()) c->lbvh.build(c->tris);
+    if (c->lbvh.n != c->tris.size() || c->lbvh.morton.empty()) {
+        c->lbvh.hierarchy = c->hierarchy;
+        c->lbvh.plocRadius = c->plocRadius;
+        c->lbvh.build(c->tris);
+    }
     WideBVH W;
     W.build(c->lbvh);
     if (n_nodes_out) *n_nodes_out = W.nNodes;

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from imgmetrics import mean_lum_ratio, mse, p99_rel_err, rgbe_roundtrip
-from test_oracle_units import check_lbvh, check_wide_bvh, look_down_params, make_quad_scene
+from test_oracle_units import HIERARCHIES, check_lbvh, check_wide_bvh, look_down_params, make_quad_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -29,12 +29,12 @@ def engine(capi):
     eng.close()
 
 
-def both(capi, desc):
+def both(capi, desc, hierarchy=None):
     out = {}
     for label, lib in (("cuda", capi.load_cuda()), ("oracle", capi.load_oracle())):
         ctx = capi.Context(lib)
         ctx.upload_scene(desc)
-        ctx.build_accel()
+        ctx.build_accel(hierarchy)
         out[label] = ctx
     return out["cuda"], out["oracle"]
 
@@ -42,9 +42,11 @@ def both(capi, desc):
 # ---------------------------------------------------------------- (1) LBVH build: bit-exact against the CPU reference build
 @pytest.mark.parametrize("scene,kw", [("Volume5", {}), ("Cornell", {}), ("MeshLight", {}), ("SharedComponents", {}), ("Hierarchy", {}),
                                       ("Atrium", dict(texture_size=4, scale=0.3)), ("Atrium", dict(texture_size=4, scale=1.0))])
-def test_lbvh_bit_exact(capi, engine, scene, kw):
+@pytest.mark.parametrize("hierarchy", HIERARCHIES)
+def test_lbvh_bit_exact(capi, engine, scene, kw, hierarchy):
+    """Morton codes, sorted order, hierarchy (Karras radix tree or PLOC) and node boxes equal the CPU reference build."""
     engine.build_scene(scene, **kw)
-    cu, orc = both(capi, engine.scene_desc())
+    cu, orc = both(capi, engine.scene_desc(), hierarchy)
     a, b = cu.get_lbvh(), orc.get_lbvh()
     assert a["n"] == b["n"] > 0
     for k in ("morton", "order", "parent", "left", "right", "aabb"):
@@ -57,12 +59,13 @@ def test_lbvh_bit_exact(capi, engine, scene, kw):
 
 @pytest.mark.parametrize("scene,kw", [("Volume5", {}), ("Cornell", {}), ("MeshLight", {}), ("SharedComponents", {}), ("Hierarchy", {}),
                                       ("Atrium", dict(texture_size=4, scale=0.3)), ("Atrium", dict(texture_size=4, scale=1.0))])
-def test_wide_bvh_bit_exact(capi, engine, scene, kw):
+@pytest.mark.parametrize("hierarchy", HIERARCHIES)
+def test_wide_bvh_bit_exact(capi, engine, scene, kw, hierarchy):
     """The on-device collapse of the LBVH into the 8-wide compressed BVH equals the CPU reference collapse byte for byte:
     same children per node, same octant slots, same exponents and quantised boxes, same breadth-first numbering, same
     triangle order."""
     engine.build_scene(scene, **kw)
-    cu, orc = both(capi, engine.scene_desc())
+    cu, orc = both(capi, engine.scene_desc(), hierarchy)
     a, b = cu.get_wide_bvh(), orc.get_wide_bvh()
     assert a["n_tris"] == b["n_tris"] > 0 and a["n_nodes"] == b["n_nodes"] > 0
     assert np.array_equal(a["tri_order"], b["tri_order"])
@@ -115,9 +118,10 @@ def ray_set(rng, n, lo, hi, aim=None):
 @pytest.mark.parametrize("scene,kw,box,coplanar", [("EnvironmentMap", {}, 4.0, False), ("Hierarchy", {}, 12.0, False),
                                                    ("SharedComponents", {}, 60.0, False), ("Cornell", {}, 1.0, True),
                                                    ("Atrium", dict(texture_size=4, scale=0.25), 8.0, False)])
-def test_ray_set_parity(capi, engine, scene, kw, box, coplanar):
+@pytest.mark.parametrize("hierarchy", HIERARCHIES)
+def test_ray_set_parity(capi, engine, scene, kw, box, coplanar, hierarchy):
     engine.build_scene(scene, **kw)
-    cu, orc = both(capi, engine.scene_desc())
+    cu, orc = both(capi, engine.scene_desc(), hierarchy)
     rng = np.random.default_rng(11)
     rays = np.concatenate([ray_set(rng, 30000, -box, box), ray_set(rng, 30000, -box, box, aim=(-box / 4, box / 4))])
     ia, pa, ta, ua, va = cu.trace_closest(rays)

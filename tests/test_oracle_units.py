@@ -273,7 +273,9 @@ def check_lbvh(L, tris_bounds=None):
         return
     nn = 2 * n - 1
     parent, left, right, box = L["parent"], L["left"], L["right"], L["aabb"]
-    assert parent[0] == -1 and np.all(parent[1:] >= 0)
+    roots = np.where(parent < 0)[0]
+    assert len(roots) == 1 and roots[0] in (0, n - 2)  # Karras numbers the root 0, PLOC creates it last
+    root = int(roots[0])
     seen = np.zeros(nn, bool)
     for i in range(n - 1):
         for c in (left[i], right[i]):
@@ -282,19 +284,23 @@ def check_lbvh(L, tris_bounds=None):
             assert np.all(box[i, :3] <= box[c, :3]) and np.all(box[i, 3:] >= box[c, 3:])
         assert np.array_equal(box[i, :3], np.minimum(box[left[i], :3], box[right[i], :3]))
         assert np.array_equal(box[i, 3:], np.maximum(box[left[i], 3:], box[right[i], 3:]))
-    assert seen[1:].all() and not seen[0]
+    assert not seen[root] and seen.sum() == nn - 1
     # equal keys are ordered by triangle id (stable sort = index tie-break)
     eq = L["morton"][:-1] == L["morton"][1:]
     assert np.all(L["order"][:-1][eq] < L["order"][1:][eq])
 
 
+HIERARCHIES = [0, 1]  # PTC_HIERARCHY_LBVH (Karras), PTC_HIERARCHY_PLOC
+
+
+@pytest.mark.parametrize("hierarchy", HIERARCHIES)
 @pytest.mark.parametrize("scene,bits", [("Volume5", 10), ("EnvironmentMap", 10)])
-def test_oracle_lbvh_invariants(capi, oracle_lib, scene, bits):
+def test_oracle_lbvh_invariants(capi, oracle_lib, scene, bits, hierarchy):
     eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
     eng.build_scene(scene)
     ctx = capi.Context(oracle_lib)
     ctx.upload_scene(eng.scene_desc())
-    ctx.build_accel()
+    ctx.build_accel(hierarchy)
     L = ctx.get_lbvh()
     check_lbvh(L)
     assert int(L["morton"].max()) < (1 << (3 * bits))
@@ -302,12 +308,13 @@ def test_oracle_lbvh_invariants(capi, oracle_lib, scene, bits):
     eng.close()
 
 
-def test_oracle_lbvh_63bit_for_large_scenes(capi, oracle_lib):
+@pytest.mark.parametrize("hierarchy", HIERARCHIES)
+def test_oracle_lbvh_63bit_for_large_scenes(capi, oracle_lib, hierarchy):
     eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
     eng.build_scene("Atrium", texture_size=4, scale=0.3)
     ctx = capi.Context(oracle_lib)
     ctx.upload_scene(eng.scene_desc())
-    ctx.build_accel()
+    ctx.build_accel(hierarchy)
     L = ctx.get_lbvh()
     assert L["n"] > 65536
     check_lbvh(L)
@@ -376,19 +383,45 @@ def check_wide_bvh(W, L):
     assert next_child == nn and next_tri == n
 
 
+@pytest.mark.parametrize("hierarchy", HIERARCHIES)
 @pytest.mark.parametrize("scene,kw", [("Volume5", {}), ("Cornell", {}), ("Hierarchy", {}), ("Atrium", dict(texture_size=4, scale=0.05))])
-def test_oracle_wide_bvh_invariants(capi, oracle_lib, scene, kw):
+def test_oracle_wide_bvh_invariants(capi, oracle_lib, scene, kw, hierarchy):
     eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
     eng.build_scene(scene, **kw)
     ctx = capi.Context(oracle_lib)
     ctx.upload_scene(eng.scene_desc())
-    ctx.build_accel()
+    ctx.build_accel(hierarchy)
     W, L = ctx.get_wide_bvh(), ctx.get_lbvh()
     check_wide_bvh(W, L)
     if L["n"] > 64:
         # the collapse must actually widen the tree: on average more than 3 children per node
         kids = sum(int(np.count_nonzero(decode_wide_node(w)["meta"])) for w in W["words"])
         assert kids / W["n_nodes"] > 3.0
+    ctx.close()
+    eng.close()
+
+
+def sah_cost(L):
+    """Surface-area-heuristic cost of a binary hierarchy (internal nodes 1.2, leaves 1), relative to the root area."""
+    n = L["n"]
+    box = L["aabb"].astype(np.float64)
+    e = box[:, 3:] - box[:, :3]
+    area = e[:, 0] * e[:, 1] + e[:, 1] * e[:, 2] + e[:, 2] * e[:, 0]
+    root = int(np.where(L["parent"] < 0)[0][0])
+    return (1.2 * area[:n - 1].sum() + area[n - 1:].sum()) / area[root]
+
+
+def test_ploc_hierarchy_is_better_than_karras(capi, oracle_lib):
+    """PLOC exists to lower the traversal cost: its SAH cost on the atrium must be clearly below the Karras tree's."""
+    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng.build_scene("Atrium", texture_size=4, scale=0.1)
+    ctx = capi.Context(oracle_lib)
+    ctx.upload_scene(eng.scene_desc())
+    cost = {}
+    for h in HIERARCHIES:
+        ctx.build_accel(h)
+        cost[h] = sah_cost(ctx.get_lbvh())
+    assert cost[1] < 0.85 * cost[0], cost
     ctx.close()
     eng.close()
 

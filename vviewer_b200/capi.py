@@ -93,9 +93,10 @@ class ptc_stats(C.Structure):
 PTC_SPLIT_NONE, PTC_SPLIT_TILE, PTC_SPLIT_SAMPLE = 0, 1, 2
 PTC_FLAG_WORLD_ORIGIN_PROBE_PDF = 1
 PTC_FLAG_TIME_KERNELS = 2
+PTC_HIERARCHY_LBVH, PTC_HIERARCHY_PLOC = 0, 1
 
 # every symbol include/ptc.h declares
-PTC_SYMBOLS = ["ptc_create", "ptc_destroy", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_build_accel", "ptc_render",
+PTC_SYMBOLS = ["ptc_create", "ptc_destroy", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_set_build_options", "ptc_build_accel", "ptc_render",
                "ptc_render_device", "ptc_progress", "ptc_get_stats", "ptc_trace_closest", "ptc_get_lbvh", "ptc_get_wide_bvh", "ptc_bsdf_eval",
                "ptc_bsdf_sample", "ptc_env_lookup"]
 VH_SYMBOLS = ["vh_engine_create", "vh_engine_destroy", "vh_backend_ok", "vh_last_error", "vh_scene_list", "vh_build_scene",
@@ -118,6 +119,8 @@ def _declare_ptc(lib):
     lib.ptc_backend_name.restype = C.c_char_p
     lib.ptc_upload_scene.argtypes = [vp, C.POINTER(ptc_scene_desc)]
     lib.ptc_upload_scene.restype = C.c_int
+    lib.ptc_set_build_options.argtypes = [vp, u32, u32]
+    lib.ptc_set_build_options.restype = C.c_int
     lib.ptc_build_accel.argtypes = [vp]
     lib.ptc_build_accel.restype = C.c_int
     lib.ptc_render.argtypes = [vp, C.POINTER(ptc_render_params), vp, vp, vp]
@@ -251,7 +254,12 @@ class Context:
     def upload_scene(self, desc_ptr):
         self._check(self.lib.ptc_upload_scene(self.ctx, desc_ptr), "ptc_upload_scene")
 
-    def build_accel(self):
+    def set_build_options(self, hierarchy, ploc_radius=0):
+        self._check(self.lib.ptc_set_build_options(self.ctx, hierarchy, ploc_radius), "ptc_set_build_options")
+
+    def build_accel(self, hierarchy=None, ploc_radius=0):
+        if hierarchy is not None:
+            self.set_build_options(hierarchy, ploc_radius)
         self._check(self.lib.ptc_build_accel(self.ctx), "ptc_build_accel")
 
     def render(self, params, want_aovs=True):

@@ -13,6 +13,8 @@
 #include "wavefront.cuh"
 
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -32,6 +34,7 @@ struct ptc_ctx {
     std::string err;
     cudaStream_t stream = nullptr;
     int smCount = 148;
+    wf::ExtendTune tune{EXTEND_MIN_ACTIVE, EXTEND_TRI_ENTER, EXTEND_TRI_LEAVE, EXTEND_BLOCKED};
     size_t persistMax = 0, windowMax = 0; /* L2 persisting carve-out and access-policy window limits of the device */
 
     /* scene */
@@ -131,6 +134,7 @@ DScene makeDScene(ptc_ctx *c) {
     s.tris = c->accel.sortedTris();
     s.nTris = c->accelBuilt ? c->accel.n : 0u;
     s.nWideNodes = c->accel.nWide;
+    s.prmtMagic = 0x47000000u;
     s.anyEmissive = c->anyEmissive ? 1u : 0u;
     s.anyTransparent = c->anyTransparent ? 1u : 0u;
     s.anyVolume = c->anyVolumeChange ? 1u : 0u;
@@ -423,7 +427,7 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
                 wf::k_raygen<<<(nSlots + 255) / 256, 256, 0, s>>>(w, rc, nSlots, b * rp->batch_size + s0);
                 launches++;
                 for (uint32_t d = 0; d < rp->depth; d++) {
-                    timed(traceMs, [&] { wf::k_extend<<<gridExtend, TRV_BLOCK, 0, s>>>(w, sc, d); });
+                    timed(traceMs, [&] { wf::k_extend<<<gridExtend, TRV_BLOCK, 0, s>>>(w, sc, d, c->tune); });
                     timed(shadeMs, [&] { wf::k_shade<<<gridShade, 128, 0, s>>>(w, sc, rc, d); });
                     launches += 2;
                     traceLaunches++;
@@ -527,6 +531,18 @@ PTC_API int ptc_create(ptc_ctx **out, const int *device_ids, int n_devices) {
     c->smCount = prop.multiProcessorCount;
     c->persistMax = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
     c->windowMax = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
+    if (const char *h = getenv("PTC_HIERARCHY")) {
+        if (!strcmp(h, "lbvh")) c->accel.hierarchy = PTC_HIERARCHY_LBVH;
+        if (!strcmp(h, "ploc")) c->accel.hierarchy = PTC_HIERARCHY_PLOC;
+    }
+    if (const char *r = getenv("PTC_PLOC_RADIUS")) {
+        const int v = atoi(r);
+        if (v >= 1 && v <= PLOC_MAX_RADIUS) c->accel.plocRadius = (uint32_t)v;
+    }
+    if (const char *t = getenv("PTC_EXTEND_TUNE")) { /* "minActive,triEnter,triLeave,blocked" */
+        unsigned a, b, d, e;
+        if (sscanf(t, "%u,%u,%u,%u", &a, &b, &d, &e) == 4) c->tune = wf::ExtendTune{a, b, d, e};
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->evA));
     CUDA_TRY(cudaEventCreate(&c->evB));
@@ -604,6 +620,16 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
     c->sceneUploaded = true;
     return 0;
     PTC_GUARD_END(c)
+}
+
+PTC_API int ptc_set_build_options(ptc_ctx *c, uint32_t hierarchy, uint32_t ploc_radius) {
+    if (!c) return 1;
+    if (hierarchy != PTC_HIERARCHY_LBVH && hierarchy != PTC_HIERARCHY_PLOC) return fail(c, "unknown hierarchy");
+    if (ploc_radius > PLOC_MAX_RADIUS) return fail(c, "ploc_radius must be <= 32");
+    c->accel.hierarchy = hierarchy;
+    c->accel.plocRadius = ploc_radius ? ploc_radius : 16u;
+    c->accelBuilt = false;
+    return 0;
 }
 
 PTC_API int ptc_build_accel(ptc_ctx *c) {

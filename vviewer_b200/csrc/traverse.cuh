@@ -56,9 +56,15 @@ PTC_D uint32_t signExtendBytes(uint32_t x) {
     return r;
 }
 
-/* byte `sel` of w as the float 32768 + byte: bits 0x47000000 | byte << 8 (exact) */
-PTC_D float byteToFloat(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x47000000u, sel)); }
-
+/* byte j of w as the float 32768 + byte: bits 0x47000000 | byte << 8 (exact), ONE byte permute.  `magic` must hold
+ * 0x47000000 and come from kernel-parameter space (DScene::prmtMagic): PRMT takes a single immediate, and it has to be the
+ * selector, otherwise every call pays an extra move of the selector into a register (ptxas folds any in-kernel constant). */
+template <int J>
+PTC_D float byteToFloat(uint32_t w, uint32_t magic) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(magic), "n"(0x7504 | (J << 4)));
+    return __uint_as_float(r);
+}
 /* Ordered query state: finds the smallest (t, id) lexicographically greater than (t0, id0) with t < tmax.
  * Closest hit: (t0, id0) = (tmin, 0xffffffff).
  *
@@ -149,6 +155,7 @@ struct Trav {
             const float px = fabsf(ax) * 0.0078125f, py = fabsf(ay) * 0.0078125f, pz = fabsf(az) * 0.0078125f;
             const float bnx = cx - px, bny = cy - py, bnz = cz - pz, bfx = cx + px, bfy = cy + py, bfz = cz + pz;
             const float tlo = t0 * 0.999999f, thi = best.t * 1.000001f;
+            const uint32_t magic = sc.prmtMagic;
             const uint32_t imask = ei >> 24;
             ng.x = __float_as_uint(n1.x);
             tgOut.x = __float_as_uint(n1.y);
@@ -166,17 +173,18 @@ struct Trav {
                 const uint32_t nx = idir.x < 0.0f ? qhx : qlx, fx = idir.x < 0.0f ? qlx : qhx;
                 const uint32_t ny = idir.y < 0.0f ? qhy : qly, fy = idir.y < 0.0f ? qly : qhy;
                 const uint32_t nz = idir.z < 0.0f ? qhz : qlz, fz = idir.z < 0.0f ? qlz : qhz;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t sel = 0x7504u | ((uint32_t)j << 4);
-                    const float tnx = fmaf(byteToFloat(nx, sel), ax, bnx), tny = fmaf(byteToFloat(ny, sel), ay, bny),
-                                tnz = fmaf(byteToFloat(nz, sel), az, bnz);
-                    const float tfx = fmaf(byteToFloat(fx, sel), ax, bfx), tfy = fmaf(byteToFloat(fy, sel), ay, bfy),
-                                tfz = fmaf(byteToFloat(fz, sel), az, bfz);
-                    const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tlo));
-                    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, thi));
-                    if (tn * 0.999999f <= tf) hitmask |= ((childBits4 >> (8 * j)) & 0xffu) << ((bitIndex4 >> (8 * j)) & 0xffu);
-                }
+#define TRV_CHILD(J)                                                                                                          \
+    {                                                                                                                         \
+        const float tnx = fmaf(byteToFloat<J>(nx, magic), ax, bnx), tny = fmaf(byteToFloat<J>(ny, magic), ay, bny),           \
+                    tnz = fmaf(byteToFloat<J>(nz, magic), az, bnz);                                                           \
+        const float tfx = fmaf(byteToFloat<J>(fx, magic), ax, bfx), tfy = fmaf(byteToFloat<J>(fy, magic), ay, bfy),           \
+                    tfz = fmaf(byteToFloat<J>(fz, magic), az, bfz);                                                           \
+        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tlo));                                                             \
+        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, thi));                                                             \
+        if (tn * 0.999999f <= tf) hitmask |= ((childBits4 >> (8 * J)) & 0xffu) << ((bitIndex4 >> (8 * J)) & 0xffu);           \
+    }
+                TRV_CHILD(0) TRV_CHILD(1) TRV_CHILD(2) TRV_CHILD(3)
+#undef TRV_CHILD
             }
             ng.y = (hitmask & 0xff000000u) | imask;
             tgOut.y = hitmask & 0x00ffffffu;

@@ -299,7 +299,10 @@ __global__ void __launch_bounds__(256) k_raygen(Wave w, const __grid_constant__ 
 #define EXTEND_TRI_ENTER 12 /* lanes with stashed triangles that trigger a triangle phase */
 #define EXTEND_TRI_LEAVE 6  /* the phase ends when fewer lanes than this still hold triangles */
 #define EXTEND_BLOCKED 4    /* lanes that have nothing but stashed triangles left */
-__global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_constant__ DScene sc, uint32_t bounce) {
+struct ExtendTune { /* warp-vote thresholds; defaults above, overridable through PTC_EXTEND_TUNE for tuning runs */
+    uint32_t minActive, triEnter, triLeave, blocked;
+};
+__global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_constant__ DScene sc, uint32_t bounce, ExtendTune tune) {
     TRV_DECLARE_STACK(stack);
     __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
     uint2 *stash = stashMem + threadIdx.x;
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_const
             bool hasTri = active && tr.tg.y != 0u;
             const unsigned mN = __ballot_sync(0xffffffffu, hasNode);
             unsigned mT = __ballot_sync(0xffffffffu, hasTri);
-            if (__popc(mT) >= EXTEND_TRI_ENTER || __popc(mT & ~mN) >= EXTEND_BLOCKED || (mN == 0u && mT != 0u)) {
+            if (__popc(mT) >= tune.triEnter || __popc(mT & ~mN) >= tune.blocked || (mN == 0u && mT != 0u)) {
                 do {
                     TRV_COUNT(cTriIt);
                     if (hasTri) {
@@ -374,14 +377,14 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_const
                         hasTri = tr.tg.y != 0u;
                     }
                     mT = __ballot_sync(0xffffffffu, hasTri);
-                } while (__popc(mT) >= EXTEND_TRI_LEAVE || (mT & ~mN) != 0u);
+                } while (__popc(mT) >= tune.triLeave || (mT & ~mN) != 0u);
             }
             if (active && !hasNode && !hasTri) {
                 stS(&w.hit[slot], make_float4(tr.best.t, tr.best.u, tr.best.v, __int_as_float(tr.best.pos)));
                 active = false;
             }
             const unsigned mA = __ballot_sync(0xffffffffu, active);
-            if (mA == 0u || (!feeder.exhausted && __popc(mA) < EXTEND_MIN_ACTIVE)) break;
+            if (mA == 0u || (!feeder.exhausted && __popc(mA) < tune.minActive)) break;
         }
     }
 #ifdef PTC_TRAV_STATS
