@@ -91,11 +91,12 @@ class ClockSampler:
 
 
 def algorithmic_bytes_per_ray(n_tris):
-    """k_extend: ideal root-to-leaf descent of the binary LBVH."""
+    """k_extend: one ideal root-to-leaf descent of the 8-wide compressed BVH:
+    D = ceil(log8(N / 3)) nodes of 80 B + one leaf of 3 triangles of 48 B + the ray's state records."""
     import math
-    depth = max(1, math.ceil(math.log2(max(n_tris, 2))))
+    depth = max(1, math.ceil(math.log(max(n_tris / 3.0, 2.0), 8)))
     state = 4 + 16 + 16 + 16  # queue id, origin+rng, direction+flags read; hit record written
-    return state + depth * 64 + 48, depth
+    return state + depth * 80 + 3 * 48, depth
 
 
 def measured_peak():

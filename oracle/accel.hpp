@@ -17,6 +17,7 @@
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
+#include <cstdio>
 #include <functional>
 #include "omath.hpp"
 
@@ -336,8 +337,10 @@ struct LBVH {
         for (uint64_t k = 0; k < n; k++) cid[k] = (int32_t)(n - 1 + k);
         uint32_t nextNode = 0;
         auto tris = [&](int32_t node) { return node >= (int32_t)(n - 1) ? 1u : subCount[node]; };
+        uint32_t rounds = 0;
         while (cid.size() > 1) {
             const int64_t c = (int64_t)cid.size();
+            rounds++;
             std::vector<int64_t> nn(c);
             for (int64_t i = 0; i < c; i++) {
                 float bestA = 0.0f;
@@ -376,6 +379,7 @@ struct LBVH {
             cid.swap(cidNext);
         }
         root = (int32_t)(n - 2);
+        if (getenv("PTC_VERBOSE")) fprintf(stderr, "[oracle] PLOC: %llu triangles, %u rounds\n", (unsigned long long)n, rounds);
     }
     void fit(int32_t root) {
         /* iterative post-order */

@@ -28,6 +28,10 @@
 #include "common.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
 
 namespace lbvh {
 
@@ -614,6 +618,15 @@ struct Build {
         n = nTris;
         nWide = wideLevels = 0;
         if (n == 0) return 0;
+        const bool verbose = getenv("PTC_VERBOSE") != nullptr;
+        auto now = [&] {
+            if (verbose) cudaStreamSynchronize(s);
+            return std::chrono::steady_clock::now();
+        };
+        auto msSince = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        const auto tStart = now();
         const int B = 256;
         const uint32_t G = (n + B - 1) / B;
         size_t nn = 2 * (size_t)n - 1;
@@ -654,6 +667,7 @@ struct Build {
         sortTemp.alloc(tempBytes);
         CUDA_TRY(cub::DeviceRadixSort::SortPairs(sortTemp.p, tempBytes, keys.p, keysSorted.p, ids.p, order.p, (int)n, 0, endBit, s));
         launches += (endBit + 7) / 8 * 2 + 1;
+        const auto tSorted = now();
         size_t scanBytes = 0;
         binaryRoot = 0;
         plocRounds = 0;
@@ -704,6 +718,7 @@ struct Build {
             binaryRoot = (int32_t)(n - 2);
         }
 
+        const auto tHierarchy = now();
         /* ---- collapse, one level at a time */
         uint32_t big = 0;
         CUDA_TRY(cudaMemcpyAsync(&big, bigNodes.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -739,6 +754,7 @@ struct Build {
         }
         nWide = levelBase;
         if (triBase != n) throw CudaError{"wide BVH collapse lost triangles"};
+        const auto tCollapsed = now();
         trav.alloc(5 * (size_t)nWide + 3 * (size_t)n);
         CUDA_TRY(cudaMemcpyAsync(trav.p, wide.p, (size_t)nWide * 80, cudaMemcpyDeviceToDevice, s));
         k_gather_tris<<<G, B, 0, s>>>(n, triMap.p, order.p, trisUnsorted.p, trav.p + 5 * (size_t)nWide, wideOrder.p);
@@ -747,6 +763,12 @@ struct Build {
         k_gather_shading<<<G, B, 0, s>>>(n, wideOrder.p, trisUnsorted.p, vertices, indices, instances, shading.p);
         launches++;
         CUDA_TRY(cudaGetLastError());
+        if (verbose) {
+            const auto tEnd = now();
+            fprintf(stderr, "[ptc] build: %u triangles | alloc+flatten+morton+sort %.2f ms | hierarchy %.2f ms (%s, %u rounds) | collapse %.2f ms (%u levels, %u wide nodes) | gather %.2f ms\n",
+                    n, msSince(tStart, tSorted), msSince(tSorted, tHierarchy), hierarchy == PTC_HIERARCHY_PLOC ? "PLOC" : "Karras", plocRounds,
+                    msSince(tHierarchy, tCollapsed), wideLevels, nWide, msSince(tCollapsed, tEnd));
+        }
         return launches;
     }
 };

@@ -432,11 +432,11 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
                     launches += 2;
                     traceLaunches++;
                     if (rc.totalLights > 0) {
-                        timed(shadowMs, [&] { wf::k_shadow<<<gridShadow, TRV_BLOCK, 0, s>>>(w, sc, rc, d); });
+                        timed(shadowMs, [&] { wf::k_shadow<<<gridShadow, TRV_BLOCK, 0, s>>>(w, sc, rc, d, c->tune); });
                         launches++;
                     }
                     if (c->anyEmissive) {
-                        timed(shadowMs, [&] { wf::k_probe<<<gridProbe, TRV_BLOCK, 0, s>>>(w, sc, rc, d); });
+                        timed(shadowMs, [&] { wf::k_probe<<<gridProbe, TRV_BLOCK, 0, s>>>(w, sc, rc, d, c->tune); });
                         launches++;
                     }
                 }

@@ -97,6 +97,10 @@ struct Trav {
         tmax = ray.tmax;
         t0 = t0_;
         id0 = id0_;
+        start(sc);
+    }
+    /* (re)starts the query described by o, d, tmin, tmax, t0, id0 */
+    PTC_D void start(const DScene &sc) {
         const float ooeps = 1e-20f;
         idir = f3(1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x)), 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y)),
                   1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z)));

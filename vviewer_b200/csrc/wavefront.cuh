@@ -25,7 +25,7 @@ namespace wf {
 #define PF_INVOL 0x200u   /* insideVolume */
 #define PF_VOL_SHIFT 16
 
-enum { CNT_ACTIVE = 0, CNT_SHADOW = 1, CNT_PROBE = 2, CNT_FETCH = 3, CNT_STRIDE = 4 };
+enum { CNT_ACTIVE = 0, CNT_SHADOW = 1, CNT_PROBE = 2, CNT_FETCH = 3, CNT_FETCH_SHADOW = 4, CNT_FETCH_PROBE = 5, CNT_STRIDE = 8 };
 enum { ST_SEGMENTS = 0, ST_SHADOW_RAYS, ST_SHADOW_HOPS, ST_PROBE_RAYS, ST_PROBE_HOPS, ST_NODE_VISITS, ST_TRI_TESTS, ST_NODE_ITERS, ST_TRI_ITERS, ST_COUNT };
 
 struct Wave {
@@ -286,14 +286,21 @@ __global__ void __launch_bounds__(256) k_raygen(Wave w, const __grid_constant__ 
     stS(&w.aovNormal[slot], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
 }
 
-/* ------------------------------------------------------------------ k_extend */
-/* Persistent warps: every warp pulls rays from the bounce's queue (one global atomic per 256 rays) and keeps one traversal per
- * lane.  All 32 lanes run the same loop body:
+/* ------------------------------------------------------------------ warp-persistent traversal loop */
+/* Shared by k_extend, k_shadow and k_probe.  Every warp pulls work items from a queue (one global atomic per 256 items) and
+ * keeps one traversal per lane.  All 32 lanes run the same loop body:
  *   node phase      every lane with node work visits ONE wide node (8 boxes); triangle groups the visit exposes are NOT tested
- *                   right away (that ran at 2.8 of 32 lanes, profiles/r1_v2) but stashed in a per-lane shared-memory ring;
+ *                   right away (that ran at 2.8 of 32 lanes, profiles/README.md) but stashed in a per-lane shared-memory ring;
  *   triangle phase  entered by warp vote once enough lanes hold stashed triangles (or lanes are blocked on them): every lane
  *                   with a stash tests one triangle per iteration;
- *   refill          finished lanes fetch new rays as soon as fewer than EXTEND_MIN_ACTIVE lanes are traversing. */
+ *   completion      a lane whose query is finished hands the hit to its Policy, which either starts the item's next query
+ *                   (shadow / probe chains: the next hop, or the next-nearest candidate) or retires the item;
+ *   refill          retired lanes fetch new items as soon as fewer than tune.minActive lanes are traversing.
+ * Policy (one object per lane):
+ *   bool begin(uint32_t index, trv::Trav &tr)   load item `index` and describe its first query in tr (o, d, tmin, tmax, t0, id0);
+ *                                               false = the item retired at once
+ *   bool next(trv::Trav &tr)                    the query is done (tr.best); true = tr describes another query to run
+ *   bool anyHit()                                                          the running query may stop at the first accepted triangle */
 #define EXTEND_MIN_ACTIVE 24
 #define EXTEND_STASH 4      /* stashed triangle groups per lane */
 #define EXTEND_TRI_ENTER 12 /* lanes with stashed triangles that trigger a triangle phase */
@@ -302,48 +309,42 @@ __global__ void __launch_bounds__(256) k_raygen(Wave w, const __grid_constant__ 
 struct ExtendTune { /* warp-vote thresholds; defaults above, overridable through PTC_EXTEND_TUNE for tuning runs */
     uint32_t minActive, triEnter, triLeave, blocked;
 };
-__global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_constant__ DScene sc, uint32_t bounce, ExtendTune tune) {
-    TRV_DECLARE_STACK(stack);
-    __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
-    uint2 *stash = stashMem + threadIdx.x;
-    const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_ACTIVE];
-    uint32_t *fetchCounter = &w.counters[bounce * CNT_STRIDE + CNT_FETCH];
-    const uint32_t *__restrict__ q = w.queue[bounce & 1u];
-    trv::WarpFeeder feeder;
-    trv::Trav tr;
-    tr.sp = -1;
-    tr.ng = tr.tg = make_uint2(0u, 0u);
-    uint32_t slot = 0, nStash = 0;
-    bool active = false;
+struct TraceCounters { /* -DPTC_TRAV_STATS builds only (tools/trav_stats.py) */
+    uint32_t node = 0, tri = 0, nodeIt = 0, triIt = 0;
+};
 #ifdef PTC_TRAV_STATS
-    uint32_t cNode = 0, cTri = 0, cNodeIt = 0, cTriIt = 0;
 #define TRV_COUNT(x) (x)++
 #else
 #define TRV_COUNT(x)
 #endif
+
+template <class Policy>
+PTC_D void traceLoop(const DScene &sc, Policy &pol, uint32_t count, uint32_t *fetchCounter, const ExtendTune tune, const trv::Stack &stack, uint2 *stash,
+                     TraceCounters &cnt) {
+    trv::WarpFeeder feeder;
+    trv::Trav tr;
+    tr.sp = -1;
+    tr.ng = tr.tg = make_uint2(0u, 0u);
+    tr.best.pos = -1;
+    uint32_t nStash = 0;
+    bool active = false;  /* the lane owns an item */
+    bool pending = false; /* tr describes a query that has not been started yet */
     while (true) {
         const uint32_t i = feeder.fetch(!active, fetchCounter, count);
-        if (i != 0xffffffffu) {
-            slot = bounce == 0u ? i : q[i];
-            const float4 o = ldS(&w.orgRng[slot]), d = ldS(&w.dirFlags[slot]);
-            trv::Ray ray;
-            ray.o = f3(o);
-            ray.d = f3(d);
-            ray.tmin = 0.001f;
-            ray.tmax = 10000.0f;
-            tr.init(sc, ray, ray.tmin, 0xffffffffu);
-            nStash = 0;
-            active = !tr.done();
-            if (!active) stS(&w.hit[slot], make_float4(tr.best.t, tr.best.u, tr.best.v, __int_as_float(tr.best.pos)));
-        }
+        if (i != 0xffffffffu) active = pending = pol.begin(i, tr);
         if (!__any_sync(0xffffffffu, active)) {
             if (!__any_sync(0xffffffffu, i != 0xffffffffu)) break; /* nothing left to fetch */
-            continue;                                              /* every fetched ray finished at once (empty scene) */
+            continue;
         }
         while (true) { /* warp-convergent: no lane leaves this loop alone */
-            TRV_COUNT(cNodeIt);
+            if (pending) {
+                tr.start(sc);
+                nStash = 0;
+                pending = false;
+            }
+            TRV_COUNT(cnt.nodeIt);
             if (active && tr.ng.y > 0x00ffffffu) {
-                TRV_COUNT(cNode);
+                TRV_COUNT(cnt.node);
                 const uint2 g = tr.nodeStep(sc, stack);
                 if (g.y != 0u) {
                     if (nStash == EXTEND_STASH) { /* ring full: make room by finishing the current group now (rare) */
@@ -367,9 +368,9 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_const
             unsigned mT = __ballot_sync(0xffffffffu, hasTri);
             if (__popc(mT) >= tune.triEnter || __popc(mT & ~mN) >= tune.blocked || (mN == 0u && mT != 0u)) {
                 do {
-                    TRV_COUNT(cTriIt);
+                    TRV_COUNT(cnt.triIt);
                     if (hasTri) {
-                        TRV_COUNT(cTri);
+                        TRV_COUNT(cnt.tri);
                         const uint32_t k = 31u - (uint32_t)__clz(tr.tg.y);
                         tr.tg.y &= ~(1u << k);
                         tr.triTest(sc, (int32_t)(tr.tg.x + k));
@@ -379,22 +380,60 @@ __global__ void __launch_bounds__(TRV_BLOCK) k_extend(Wave w, const __grid_const
                     mT = __ballot_sync(0xffffffffu, hasTri);
                 } while (__popc(mT) >= tune.triLeave || (mT & ~mN) != 0u);
             }
-            if (active && !hasNode && !hasTri) {
-                stS(&w.hit[slot], make_float4(tr.best.t, tr.best.u, tr.best.v, __int_as_float(tr.best.pos)));
-                active = false;
+            /* query complete: nothing left to visit, or an occlusion query that already has its answer */
+            if (active && ((!hasNode && !hasTri) || (pol.anyHit() && tr.best.pos >= 0))) {
+                active = pending = pol.next(tr);
+                tr.ng.y = 0u;
+                tr.tg.y = 0u;
             }
             const unsigned mA = __ballot_sync(0xffffffffu, active);
             if (mA == 0u || (!feeder.exhausted && __popc(mA) < tune.minActive)) break;
         }
     }
+}
+
+PTC_D void traceCountersFlush(const Wave &w, const TraceCounters &cnt) {
 #ifdef PTC_TRAV_STATS
-    statAdd(&w.stats[ST_NODE_VISITS], cNode);
-    statAdd(&w.stats[ST_TRI_TESTS], cTri);
+    statAdd(&w.stats[ST_NODE_VISITS], cnt.node);
+    statAdd(&w.stats[ST_TRI_TESTS], cnt.tri);
     if (laneId() == 0) {
-        atomicAdd(&w.stats[ST_NODE_ITERS], (unsigned long long)cNodeIt);
-        atomicAdd(&w.stats[ST_TRI_ITERS], (unsigned long long)cTriIt);
+        atomicAdd(&w.stats[ST_NODE_ITERS], (unsigned long long)cnt.nodeIt);
+        atomicAdd(&w.stats[ST_TRI_ITERS], (unsigned long long)cnt.triIt);
     }
 #endif
+}
+
+/* ------------------------------------------------------------------ k_extend */
+/* closest hit of the path ray: traceRayEXT at raygen.rgen.glsl:110 (tmin 1e-3, tmax 1e4) */
+struct ExtendPolicy {
+    const Wave &w;
+    const uint32_t *__restrict__ q;
+    uint32_t bounce, slot;
+    PTC_D ExtendPolicy(const Wave &w_, uint32_t bounce_) : w(w_), q(w_.queue[bounce_ & 1u]), bounce(bounce_), slot(0) {}
+    PTC_D bool anyHit() const { return false; }
+    PTC_D bool begin(uint32_t i, trv::Trav &tr) {
+        slot = bounce == 0u ? i : q[i];
+        const float4 o = ldS(&w.orgRng[slot]), d = ldS(&w.dirFlags[slot]);
+        tr.o = f3(o);
+        tr.d = f3(d);
+        tr.tmin = tr.t0 = 0.001f;
+        tr.tmax = 10000.0f;
+        tr.id0 = 0xffffffffu;
+        return true;
+    }
+    PTC_D bool next(trv::Trav &tr) {
+        const trv::HitRec &h = tr.best;
+        stS(&w.hit[slot], make_float4(h.t, h.u, h.v, __int_as_float(h.pos)));
+        return false;
+    }
+};
+__global__ void __launch_bounds__(TRV_BLOCK, 8) k_extend(Wave w, const __grid_constant__ DScene sc, uint32_t bounce, ExtendTune tune) {
+    TRV_DECLARE_STACK(stack);
+    __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
+    ExtendPolicy pol(w, bounce);
+    TraceCounters cnt;
+    traceLoop(sc, pol, w.counters[bounce * CNT_STRIDE + CNT_ACTIVE], &w.counters[bounce * CNT_STRIDE + CNT_FETCH], tune, stack, stashMem + threadIdx.x, cnt);
+    traceCountersFlush(w, cnt);
 }
 
 /* ------------------------------------------------------------------ k_shade */
@@ -632,216 +671,206 @@ __global__ void __launch_bounds__(128, 6) k_shade(Wave w, const __grid_constant_
 }
 
 /* ------------------------------------------------------------------ k_shadow */
-/* lightSampling.glsl:108-144 with nearest-first candidate order (trap T1) */
-__global__ void __launch_bounds__(TRV_BLOCK) k_shadow(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce) {
-    TRV_DECLARE_STACK(stack);
-    const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_SHADOW];
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t rounded = (count + 31u) & ~31u;
-    const float zfarTrunc = (float)(uint32_t)rc.sd.volumes[2];
-    uint32_t hops = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
-        if (i < count) {
-            const uint32_t slot = w.qShadow[i];
-            const float4 o4 = ldS(&w.shOrgTmax[slot]), d4 = ldS(&w.shDirVol[slot]);
-            float3 origin = f3(o4);
-            const float3 dir = f3(d4);
-            uint32_t vol = __float_as_uint(d4.w);
-            const float tmin = 0.0001f;
-            float distanceT = o4.w - tmin;
-            float3 thr = f3(1.0f);
-            bool shadowed = false;
-            if (!sc.anyTransparent) {
-                /* every surface is opaque: any hit shadows; otherwise raySecondary.rmiss */
-                trv::Ray ray{origin, dir, tmin, distanceT};
-                hops++;
-                shadowed = trv::occluded(sc, ray, stack);
-                if (!shadowed && (vol & PF_INVOL)) {
-                    thr = transmittance(sc, vol >> PF_VOL_SHIFT, tmin, fminf(zfarTrunc, distanceT));
-                    shadowed = !(max3(thr) > PT_EPSILON);
-                }
-            } else {
-                bool stop = false;
-                for (uint32_t d = 0; d < rc.depth && !stop; d++) {
-                    float vtmin = tmin;
-                    trv::Ray ray{origin, dir, tmin, distanceT};
-                    hops++;
-                    float t0 = tmin;
-                    uint32_t id0 = 0xffffffffu;
-                    bool ended = false;
-                    while (!ended) {
-                        trv::HitRec h = trv::nextHit(sc, ray, t0, id0, stack);
-                        if (h.pos < 0) break;
-                        Surf s;
-                        loadSurf(sc, h.pos, h.u, h.v, false, s);
-                        const ptc_material *mat = s.mat;
-                        if (!(__ldg(&mat->metallic_roughness_ao[3]) >= 0.99f)) { /* raySecondary.rahit.glsl:42-47 */
-                            stop = shadowed = ended = true;
-                            break;
-                        }
-                        const float alpha = __ldg(&mat->albedo[3]) *
-                                            texFetch(sc, __ldg(&mat->tex2[3]), s.uv.x * __ldg(&mat->uv_tiling[0]), s.uv.y * __ldg(&mat->uv_tiling[1])).x;
-                        thr = thr * (1.0f - alpha);
-                        if (s.inst->volFront != s.inst->volBack) { /* accept: raySecondary.rchit.glsl:32-78 */
-                            const bool flipped = dot(s.n, dir) > 0.0f;
-                            if (vol & PF_INVOL) {
-                                thr = thr * transmittance(sc, vol >> PF_VOL_SHIFT, vtmin, h.t);
-                                if (max3(thr) < PT_EPSILON) {
-                                    stop = shadowed = ended = true;
-                                    break;
-                                }
-                            }
-                            vtmin = h.t;
-                            volumeChange(s.inst, flipped, vol);
-                            origin = s.pos;
-                            ended = true;
-                            break;
-                        }
-                        if (max3(thr) > PT_EPSILON) { /* ignoreIntersectionEXT */
-                            shadowed = false;
-                            t0 = h.t;
-                            id0 = h.worldId;
-                            continue;
-                        }
-                        stop = shadowed = ended = true;
-                    }
-                    if (!ended) { /* raySecondary.rmiss.glsl:17-44 */
-                        stop = true;
-                        shadowed = false;
-                        if (vol & PF_INVOL) {
-                            thr = thr * transmittance(sc, vol >> PF_VOL_SHIFT, vtmin, fminf(zfarTrunc, distanceT));
-                            shadowed = !(max3(thr) > PT_EPSILON);
-                        }
-                    }
-                    distanceT -= vtmin;
-                }
-            }
-            if (!shadowed) {
-                const float3 c = f3(ldS(&w.shContrib[slot])) * thr;
-                float4 r = ldS(&w.radiance[slot]);
-                r.x += c.x;
-                r.y += c.y;
-                r.z += c.z;
-                stS(&w.radiance[slot], r);
-            }
-        }
+/* lightSampling.glsl:108-144 + raySecondary.rahit/.rchit/.rmiss with nearest-first candidate order (trap T1), as a
+ * per-lane state machine on top of traceLoop: one query = the next-nearest candidate of the current hop. */
+struct ShadowPolicy {
+    const Wave &w;
+    const DScene &sc;
+    const RenderConst &rc;
+    uint32_t slot, vol, hop, hops;
+    float3 origin, thr; /* the direction lives in the traversal state */
+    float distanceT, vtmin;
+    bool opaqueScene;
+    PTC_D ShadowPolicy(const Wave &w_, const DScene &sc_, const RenderConst &rc_)
+        : w(w_), sc(sc_), rc(rc_), slot(0), vol(0), hop(0), hops(0), distanceT(0.0f), vtmin(0.0f), opaqueScene(!sc_.anyTransparent) {}
+    PTC_D bool anyHit() const { return opaqueScene; } /* every surface is opaque: any hit shadows */
+    PTC_D void startHop(trv::Trav &tr) {
+        const float tmin = 0.0001f;
+        vtmin = tmin;
+        tr.o = origin;
+        tr.tmin = tr.t0 = tmin;
+        tr.tmax = distanceT;
+        tr.id0 = 0xffffffffu;
+        hops++;
     }
-    statAdd(&w.stats[ST_SHADOW_HOPS], hops);
+    PTC_D bool begin(uint32_t i, trv::Trav &tr) {
+        slot = w.qShadow[i];
+        const float4 o4 = ldS(&w.shOrgTmax[slot]), d4 = ldS(&w.shDirVol[slot]);
+        origin = f3(o4);
+        tr.d = f3(d4);
+        vol = __float_as_uint(d4.w);
+        distanceT = o4.w - 0.0001f;
+        thr = f3(1.0f);
+        hop = 0;
+        if (rc.depth == 0u) return finish(false);
+        startHop(tr);
+        return true;
+    }
+    PTC_D bool finish(bool shadowed) {
+        if (!shadowed) {
+            const float3 c = f3(ldS(&w.shContrib[slot])) * thr;
+            float4 r = ldS(&w.radiance[slot]);
+            r.x += c.x;
+            r.y += c.y;
+            r.z += c.z;
+            stS(&w.radiance[slot], r);
+        }
+        return false;
+    }
+    PTC_D bool next(trv::Trav &tr) {
+        const trv::HitRec h = tr.best;
+        const float3 dir = tr.d;
+        if (h.pos < 0) { /* raySecondary.rmiss.glsl:17-44 */
+            bool shadowed = false;
+            if (vol & PF_INVOL) {
+                const float zfarTrunc = (float)(uint32_t)rc.sd.volumes[2];
+                thr = thr * transmittance(sc, vol >> PF_VOL_SHIFT, vtmin, fminf(zfarTrunc, distanceT));
+                shadowed = !(max3(thr) > PT_EPSILON);
+            }
+            return finish(shadowed);
+        }
+        if (opaqueScene) return finish(true);
+        Surf s;
+        loadSurf(sc, h.pos, h.u, h.v, false, s);
+        const ptc_material *mat = s.mat;
+        if (!(__ldg(&mat->metallic_roughness_ao[3]) >= 0.99f)) return finish(true); /* raySecondary.rahit.glsl:42-47 */
+        const float alpha =
+            __ldg(&mat->albedo[3]) * texFetch(sc, __ldg(&mat->tex2[3]), s.uv.x * __ldg(&mat->uv_tiling[0]), s.uv.y * __ldg(&mat->uv_tiling[1])).x;
+        thr = thr * (1.0f - alpha);
+        if (s.inst->volFront != s.inst->volBack) { /* accept: raySecondary.rchit.glsl:32-78 */
+            const bool flipped = dot(s.n, dir) > 0.0f;
+            if (vol & PF_INVOL) {
+                thr = thr * transmittance(sc, vol >> PF_VOL_SHIFT, vtmin, h.t);
+                if (max3(thr) < PT_EPSILON) return finish(true);
+            }
+            volumeChange(s.inst, flipped, vol);
+            origin = s.pos;
+            distanceT -= h.t;
+            if (++hop >= rc.depth) return finish(false); /* lightSampling.glsl:118: the hop loop runs out */
+            startHop(tr);
+            return true;
+        }
+        if (max3(thr) > PT_EPSILON) { /* ignoreIntersectionEXT: same ray, next-nearest candidate */
+            tr.t0 = h.t;
+            tr.id0 = h.worldId;
+            return true;
+        }
+        return finish(true);
+    }
+};
+__global__ void __launch_bounds__(TRV_BLOCK, 6) k_shadow(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
+                                                      ExtendTune tune) {
+    TRV_DECLARE_STACK(stack);
+    __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
+    ShadowPolicy pol(w, sc, rc);
+    TraceCounters cnt;
+    traceLoop(sc, pol, w.counters[bounce * CNT_STRIDE + CNT_SHADOW], &w.counters[bounce * CNT_STRIDE + CNT_FETCH_SHADOW], tune, stack,
+              stashMem + threadIdx.x, cnt);
+    statAdd(&w.stats[ST_SHADOW_HOPS], pol.hops);
 }
 
 /* ------------------------------------------------------------------ k_probe */
-/* next_event_estimation.glsl:1-33 + rayNEE.* with nearest-first candidate order (trap T1) */
-__global__ void __launch_bounds__(TRV_BLOCK) k_probe(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce) {
-    TRV_DECLARE_STACK(stack);
-    const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_PROBE];
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t rounded = (count + 31u) & ~31u;
-    const float tmin = 0.0001f, tmax = rc.sd.volumes[2];
-    uint32_t hops = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
-        if (i < count) {
-            const uint32_t slot = w.qProbe[i];
-            const float4 o4 = ldS(&w.orgRng[slot]), d4 = ldS(&w.dirFlags[slot]), bp = ldS(&w.prBetaPdf[slot]);
-            float3 origin = f3(o4);
-            const float3 dir = f3(d4);
-            uint32_t vol = __float_as_uint(d4.w);
-            float3 thr = f3(1.0f), emissive = f3(0.0f);
-            float pdf = 0.0f;
-            bool stop = false;
-            for (uint32_t d = 0; d < rc.depth && !stop; d++) {
-                float vtmin = tmin;
-                trv::Ray ray{origin, dir, tmin, tmax};
-                hops++;
-                float t0 = tmin;
-                uint32_t id0 = 0xffffffffu;
-                bool ended = false;
-                while (!ended) {
-                    trv::HitRec h = trv::nextHit(sc, ray, t0, id0, stack);
-                    if (h.pos < 0) break;
-                    Surf s;
-                    loadSurf(sc, h.pos, h.u, h.v, false, s);
-                    const ptc_material *mat = s.mat;
-                    const float tu = s.uv.x * __ldg(&mat->uv_tiling[0]), tv = s.uv.y * __ldg(&mat->uv_tiling[1]);
-                    const float3 em = ld3(mat->emissive) * __ldg(&mat->emissive[3]) * f3(texFetch(sc, __ldg(&mat->tex2[0]), tu, tv));
-                    const bool isTransparent = __ldg(&mat->metallic_roughness_ao[3]) >= 0.99f;
-                    if (isBlackEps(em, 0.05f)) { /* rayNEE.rahit.glsl:44-71 */
-                        if (!isTransparent) {
-                            stop = ended = true;
-                            thr = f3(0.0f);
-                            emissive = f3(0.0f);
-                            break;
-                        }
-                        const float alpha = __ldg(&mat->albedo[3]) * texFetch(sc, __ldg(&mat->tex2[3]), tu, tv).x;
-                        thr = thr * (1.0f - alpha);
-                        if (s.inst->volFront != s.inst->volBack) { /* accept: rayNEE.rchit.glsl:33-82 */
-                            const bool flipped = dot(s.n, dir) > 0.0f;
-                            if (vol & PF_INVOL) {
-                                thr = thr * transmittance(sc, vol >> PF_VOL_SHIFT, vtmin, h.t);
-                                if (max3(thr) < PT_EPSILON) {
-                                    stop = ended = true;
-                                    thr = f3(0.0f);
-                                    emissive = f3(0.0f);
-                                    break;
-                                }
-                            }
-                            vtmin = h.t;
-                            volumeChange(s.inst, flipped, vol);
-                            origin = s.pos;
-                            ended = true;
-                            break;
-                        }
-                        t0 = h.t; /* ignoreIntersectionEXT */
-                        id0 = h.worldId;
-                        continue;
-                    }
-                    /* emissive surface, rayNEE.rahit.glsl:73-131 */
-                    stop = ended = true;
-                    if (vol & PF_INVOL) {
-                        thr = thr * transmittance(sc, vol >> PF_VOL_SHIFT, vtmin, h.t);
-                        if (max3(thr) < PT_EPSILON) {
-                            thr = f3(0.0f);
-                            emissive = f3(0.0f);
-                            break;
-                        }
-                    }
-                    if (dot(s.n, dir) > 0.0f) { /* back face */
-                        emissive = f3(0.0f);
-                        thr = f3(0.0f);
-                        break;
-                    }
-                    emissive = em;
-                    const float3 w0 = mulPoint(s.inst->m, s.p0), w1 = mulPoint(s.inst->m, s.p1), w2 = mulPoint(s.inst->m, s.p2);
-                    const float area = 0.5f * length(cross(w1 - w0, w2 - w0));
-                    const float pointPdf = (1.0f / (float)s.inst->numTriangles) * (1.0f / area);
-                    const float dp = dot(-dir, s.n);
-                    if (dp > 0.0f) {
-                        /* rayNEE.rahit.glsl:122 measures from gl_ObjectRayOriginEXT (trap T6) unless the flag asks otherwise */
-                        const float3 ro = (rc.flags & PTC_FLAG_WORLD_ORIGIN_PROBE_PDF) ? origin : mulPoint(s.inst->w2o, origin);
-                        const float dd = length(ro - s.pos);
-                        pdf = pointPdf * (dd * dd) / dp * (1.0f / (float)rc.totalLights);
-                    } else {
-                        pdf = 0.0f;
-                        emissive = f3(0.0f);
-                    }
-                }
-                if (!ended) { /* rayNEE.rmiss.glsl:12-19 */
-                    stop = true;
-                    emissive = f3(0.0f);
-                    pdf = 0.0f;
-                }
-            }
-            if (!isBlack(emissive)) {
-                const float wgt = powerHeuristic(bp.w, pdf);
-                const float3 c = thr * emissive * f3(bp) * wgt;
-                float4 r = ldS(&w.radiance[slot]);
-                r.x += c.x;
-                r.y += c.y;
-                r.z += c.z;
-                stS(&w.radiance[slot], r);
-            }
-        }
+/* next_event_estimation.glsl:1-33 + rayNEE.rahit/.rchit/.rmiss with nearest-first candidate order (trap T1) */
+struct ProbePolicy {
+    const Wave &w;
+    const DScene &sc;
+    const RenderConst &rc;
+    uint32_t slot, vol, hop, hops;
+    float3 origin, thr; /* the direction lives in the traversal state */
+    float vtmin;
+    PTC_D ProbePolicy(const Wave &w_, const DScene &sc_, const RenderConst &rc_) : w(w_), sc(sc_), rc(rc_), slot(0), vol(0), hop(0), hops(0), vtmin(0.0f) {}
+    PTC_D bool anyHit() const { return false; }
+    PTC_D void startHop(trv::Trav &tr) {
+        const float tmin = 0.0001f;
+        vtmin = tmin;
+        tr.o = origin;
+        tr.tmin = tr.t0 = tmin;
+        tr.tmax = rc.sd.volumes[2];
+        tr.id0 = 0xffffffffu;
+        hops++;
     }
-    statAdd(&w.stats[ST_PROBE_HOPS], hops);
+    PTC_D bool begin(uint32_t i, trv::Trav &tr) {
+        slot = w.qProbe[i];
+        const float4 o4 = ldS(&w.orgRng[slot]), d4 = ldS(&w.dirFlags[slot]);
+        origin = f3(o4);
+        tr.d = f3(d4);
+        vol = __float_as_uint(d4.w);
+        thr = f3(1.0f);
+        hop = 0;
+        if (rc.depth == 0u) return false;
+        startHop(tr);
+        return true;
+    }
+    PTC_D bool finish(float3 emissive, float pdf) {
+        if (!isBlack(emissive)) {
+            const float4 bp = ldS(&w.prBetaPdf[slot]);
+            const float wgt = powerHeuristic(bp.w, pdf);
+            const float3 c = thr * emissive * f3(bp) * wgt;
+            float4 r = ldS(&w.radiance[slot]);
+            r.x += c.x;
+            r.y += c.y;
+            r.z += c.z;
+            stS(&w.radiance[slot], r);
+        }
+        return false;
+    }
+    PTC_D bool next(trv::Trav &tr) {
+        const trv::HitRec h = tr.best;
+        const float3 dir = tr.d;
+        if (h.pos < 0) return false; /* rayNEE.rmiss.glsl:12-19: nothing (the environment is not included, trap T6) */
+        Surf s;
+        loadSurf(sc, h.pos, h.u, h.v, false, s);
+        const ptc_material *mat = s.mat;
+        const float tu = s.uv.x * __ldg(&mat->uv_tiling[0]), tv = s.uv.y * __ldg(&mat->uv_tiling[1]);
+        const float3 em = ld3(mat->emissive) * __ldg(&mat->emissive[3]) * f3(texFetch(sc, __ldg(&mat->tex2[0]), tu, tv));
+        const bool isTransparent = __ldg(&mat->metallic_roughness_ao[3]) >= 0.99f;
+        if (isBlackEps(em, 0.05f)) { /* rayNEE.rahit.glsl:44-71 */
+            if (!isTransparent) return false;
+            const float alpha = __ldg(&mat->albedo[3]) * texFetch(sc, __ldg(&mat->tex2[3]), tu, tv).x;
+            thr = thr * (1.0f - alpha);
+            if (s.inst->volFront != s.inst->volBack) { /* accept: rayNEE.rchit.glsl:33-82 */
+                const bool flipped = dot(s.n, dir) > 0.0f;
+                if (vol & PF_INVOL) {
+                    thr = thr * transmittance(sc, vol >> PF_VOL_SHIFT, vtmin, h.t);
+                    if (max3(thr) < PT_EPSILON) return false;
+                }
+                volumeChange(s.inst, flipped, vol);
+                origin = s.pos;
+                if (++hop >= rc.depth) return false; /* the hop loop runs out without an emitter */
+                startHop(tr);
+                return true;
+            }
+            tr.t0 = h.t; /* ignoreIntersectionEXT: same ray, next-nearest candidate */
+            tr.id0 = h.worldId;
+            return true;
+        }
+        /* emissive surface, rayNEE.rahit.glsl:73-131 */
+        if (vol & PF_INVOL) {
+            thr = thr * transmittance(sc, vol >> PF_VOL_SHIFT, vtmin, h.t);
+            if (max3(thr) < PT_EPSILON) return false;
+        }
+        if (dot(s.n, dir) > 0.0f) return false; /* back face */
+        const float3 w0 = mulPoint(s.inst->m, s.p0), w1 = mulPoint(s.inst->m, s.p1), w2 = mulPoint(s.inst->m, s.p2);
+        const float area = 0.5f * length(cross(w1 - w0, w2 - w0));
+        const float pointPdf = (1.0f / (float)s.inst->numTriangles) * (1.0f / area);
+        const float dp = dot(-dir, s.n);
+        if (!(dp > 0.0f)) return false;
+        /* rayNEE.rahit.glsl:122 measures from gl_ObjectRayOriginEXT (trap T6) unless the flag asks otherwise */
+        const float3 ro = (rc.flags & PTC_FLAG_WORLD_ORIGIN_PROBE_PDF) ? origin : mulPoint(s.inst->w2o, origin);
+        const float dd = length(ro - s.pos);
+        const float pdf = pointPdf * (dd * dd) / dp * (1.0f / (float)rc.totalLights);
+        return finish(em, pdf);
+    }
+};
+__global__ void __launch_bounds__(TRV_BLOCK, 6) k_probe(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
+                                                     ExtendTune tune) {
+    TRV_DECLARE_STACK(stack);
+    __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
+    ProbePolicy pol(w, sc, rc);
+    TraceCounters cnt;
+    traceLoop(sc, pol, w.counters[bounce * CNT_STRIDE + CNT_PROBE], &w.counters[bounce * CNT_STRIDE + CNT_FETCH_PROBE], tune, stack,
+              stashMem + threadIdx.x, cnt);
+    statAdd(&w.stats[ST_PROBE_HOPS], pol.hops);
 }
 
 /* ------------------------------------------------------------------ k_accumulate (raygen.rgen.glsl:126-144) */
