@@ -168,6 +168,7 @@ typedef struct ptc_render_params {
 } ptc_render_params;
 
 #define PTC_FLAG_WORLD_ORIGIN_PROBE_PDF 1u /* use the world-space ray origin in the probe-ray pdf instead of reproducing rayNEE.rahit.glsl:122 */
+#define PTC_FLAG_SAMPLER_SOBOL 4u         /* low-discrepancy sampler (shuffled, Owen-scrambled Sobol; plays the role of the reference's optional PMJ02BN sampler, rng_pmj.glsl) instead of the default xorshift stream */
 #define PTC_FLAG_TIME_KERNELS 2u          /* bracket every kernel class with CUDA events (fills ptc_stats.*_ms; serialises launches) */
 
 typedef struct ptc_stats {
@@ -250,6 +251,12 @@ PTC_API int ptc_bsdf_eval(ptc_ctx *ctx, int n, const float *params, const float 
                           float *out_pdf);
 PTC_API int ptc_bsdf_sample(ptc_ctx *ctx, int n, const float *params, const float *wo, const float *u, float *out_wi,
                             float *out_f, float *out_pdf);
+
+/* Sampler parity hook: the rand2D() points (x, y interleaved in out_xy[2 * count]) that the sampler selected by `flags`
+ * (PTC_FLAG_SAMPLER_SOBOL or 0) hands to pixel (px, py) of an image `width` wide at dimension `dimension`, for the global
+ * sample indices first_index .. first_index + count - 1. */
+PTC_API int ptc_sampler_points(ptc_ctx *ctx, uint32_t px, uint32_t py, uint32_t width, uint32_t first_index, uint32_t count,
+                               uint32_t dimension, uint32_t flags, float *out_xy);
 
 /* Environment lookup parity hook: n directions (xyz) -> rgb of the backend's cubemap at LOD 0. */
 PTC_API int ptc_env_lookup(ptc_ctx *ctx, int n, const float *dirs, float *out_rgb);

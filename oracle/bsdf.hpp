@@ -50,10 +50,63 @@ inline uint32_t initRNG(uint32_t px, uint32_t py, uint32_t resx, uint32_t frame)
     uint32_t s = pixelIdx ^ jenkinsHash(frame);
     return jenkinsHash(s);
 }
+/* Low-discrepancy mode (PTC_FLAG_SAMPLER_SOBOL): shuffled + Owen-scrambled Sobol points (Burley 2020), the role the
+ * reference gives to its optional PMJ02BN sampler (include/rng/rng_pmj.glsl:66-107: rand1D / rand2D keyed by pixel,
+ * sample index and a running dimension).  Restated integer for integer like vviewer_b200/csrc/bsdf.cuh. */
+inline uint32_t hashCombine(uint32_t seed, uint32_t v) { return seed ^ (v + (seed << 6) + (seed >> 2)); }
+inline uint32_t reverseBits32(uint32_t x) {
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+    x = ((x >> 8) & 0x00ff00ffu) | ((x & 0x00ff00ffu) << 8);
+    return (x >> 16) | (x << 16);
+}
+inline uint32_t laineKarras(uint32_t x, uint32_t seed) {
+    x += seed;
+    x ^= x * 0x6c50b47cu;
+    x ^= x * 0xb82f1e52u;
+    x ^= x * 0xc7afe638u;
+    x ^= x * 0x8d22f6e6u;
+    return x;
+}
+inline uint32_t owenScramble(uint32_t x, uint32_t seed) { return reverseBits32(laineKarras(reverseBits32(x), seed)); }
+inline uint32_t sobolDim1(uint32_t i) {
+    uint32_t v = 0x80000000u, r = 0;
+    for (; i; i >>= 1) {
+        if (i & 1u) r ^= v;
+        v ^= v >> 1;
+    }
+    return r;
+}
 struct Rng {
-    uint32_t state;
-    float rand1D() { return uintToFloat(xorshift(state)); }
+    uint32_t state;         /* xorshift state, or the next dimension */
+    uint32_t pixelSeed = 0; /* low discrepancy only */
+    uint32_t index = 0;     /* global sample index */
+    bool ld = false;
+    void init(uint32_t px, uint32_t py, uint32_t resx, uint32_t sampleIndex, bool lowDiscrepancy) {
+        ld = lowDiscrepancy;
+        index = sampleIndex;
+        pixelSeed = jenkinsHash(px * resx + py);
+        state = ld ? 0u : initRNG(px, py, resx, sampleIndex);
+    }
+    float rand1D() {
+        if (ld) {
+            uint32_t seed = jenkinsHash(hashCombine(pixelSeed, state));
+            state += 1;
+            uint32_t idx = owenScramble(index, seed);
+            return uintToFloat(owenScramble(reverseBits32(idx), hashCombine(seed, 1u)));
+        }
+        return uintToFloat(xorshift(state));
+    }
     vec2 rand2D() {
+        if (ld) {
+            uint32_t seed = jenkinsHash(hashCombine(pixelSeed, state));
+            state += 2;
+            uint32_t idx = owenScramble(index, seed);
+            uint32_t x = owenScramble(reverseBits32(idx), hashCombine(seed, 1u));
+            uint32_t y = owenScramble(sobolDim1(idx), hashCombine(seed, 2u));
+            return {uintToFloat(x), uintToFloat(y)};
+        }
         float a = rand1D();
         float b = rand1D();
         return {a, b};

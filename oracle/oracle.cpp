@@ -799,7 +799,7 @@ struct Tracer {
     /* raygen.rgen.glsl:55-129 for one sample of one pixel */
     void samplePixel(uint32_t px, uint32_t py, uint32_t sampleIndex, vec3 &radiance, vec3 &albedo, vec3 &normal) {
         Payload P;
-        P.rng.state = initRNG(px, py, rp->width, sampleIndex);
+        P.rng.init(px, py, rp->width, sampleIndex, (rp->flags & PTC_FLAG_SAMPLER_SOBOL) != 0u);
         const mat4 projInv = mat4_from(rp->scene.projection_inverse);
         const mat4 viewInv = mat4_from(rp->scene.view_inverse);
         float lensRadius = rp->scene.exposure[2];
@@ -1157,6 +1157,22 @@ PTC_API int ptc_bsdf_sample(ptc_ctx *, int n, const float *params, const float *
     }
     return 0;
 }
+PTC_API int ptc_sampler_points(ptc_ctx *, uint32_t px, uint32_t py, uint32_t width, uint32_t first_index, uint32_t count, uint32_t dimension,
+                               uint32_t flags, float *out_xy) {
+    for (uint32_t i = 0; i < count; i++) {
+        Rng r;
+        r.init(px, py, width, first_index + i, (flags & PTC_FLAG_SAMPLER_SOBOL) != 0u);
+        if (r.ld)
+            r.state = dimension;
+        else
+            for (uint32_t k = 0; k < dimension; k++) r.rand1D();
+        vec2 p = r.rand2D();
+        out_xy[2 * i] = p.x;
+        out_xy[2 * i + 1] = p.y;
+    }
+    return 0;
+}
+
 PTC_API int ptc_env_lookup(ptc_ctx *c, int n, const float *dirs, float *out_rgb) {
     if (!c) return 1;
     for (int i = 0; i < n; i++) {

@@ -199,11 +199,28 @@ def test_env_lookup_parity(capi, engine):
 
 
 # ---------------------------------------------------------------- (5) renders: CUDA vs oracle at matched samples (same RNG streams)
-@pytest.mark.parametrize("scene", GOLDEN_SCENES + ["Denoise", "Cornell"])
-def test_render_matches_oracle(capi, engine, scene):
+def test_sampler_points_bit_exact(capi):
+    """Both samplers (default xorshift stream, shuffled Owen-scrambled Sobol) are integer arithmetic: identical on both sides."""
+    cu, orc = capi.Context(capi.load_cuda()), capi.Context(capi.load_oracle())
+    for flags in (0, capi.PTC_FLAG_SAMPLER_SOBOL):
+        for (px, py, w, first, count, dim) in [(0, 0, 256, 0, 1024, 0), (1919, 1079, 1920, 4000, 96, 7), (5, 9, 64, 1 << 20, 33, 40)]:
+            a = cu.sampler_points(px, py, w, first, count, dim, flags)
+            b = orc.sampler_points(px, py, w, first, count, dim, flags)
+            assert np.array_equal(a, b), (flags, px, py, dim)
+    cu.close()
+    orc.close()
+
+
+SOBOL_SCENES = ["Cornell", "Volume5", "DepthOfField", "EnvironmentMapPBR01", "MeshLight"]
+
+
+@pytest.mark.parametrize("scene,sobol", [(s, False) for s in GOLDEN_SCENES + ["Denoise", "Cornell"]] + [(s, True) for s in SOBOL_SCENES])
+def test_render_matches_oracle(capi, engine, scene, sobol):
     engine.build_scene(scene)
     engine.set_render_info(width=128, height=128, samples=8, batch_size=4)
     desc, rp = engine.scene_desc(), engine.render_params()
+    if sobol:
+        rp.flags |= capi.PTC_FLAG_SAMPLER_SOBOL
     cu, orc = both(capi, desc)
     ra, aa, na = cu.render(rp)
     rb, ab, nb = orc.render(rp)

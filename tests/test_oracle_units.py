@@ -478,3 +478,56 @@ def test_env_cubemap_lookup_matches_equirect(capi, oracle_lib):
     assert up.sum() > down.sum()
     ctx.close()
     eng.close()
+
+
+# ---------------------------------------------------------------- low-discrepancy sampler (PTC_FLAG_SAMPLER_SOBOL)
+def is_02_net(pts, m):
+    """True when 2^m points form a (0, m, 2)-net in base 2: every dyadic box of area 2^-m holds exactly one point."""
+    n = 1 << m
+    assert len(pts) == n
+    for a in range(m + 1):
+        b = m - a
+        ix = np.floor(pts[:, 0] * (1 << a)).astype(np.int64)
+        iy = np.floor(pts[:, 1] * (1 << b)).astype(np.int64)
+        if len(np.unique(ix * (1 << b) + iy)) != n:
+            return False
+    return True
+
+
+def test_sobol_sampler_points_are_scrambled_nets(octx, capi):
+    for (px, py, dim) in [(0, 0, 0), (17, 5, 0), (17, 5, 2), (100, 200, 14), (3, 3, 101)]:
+        for m in (4, 6, 8):
+            p = octx.sampler_points(px, py, 256, 0, 1 << m, dim, capi.PTC_FLAG_SAMPLER_SOBOL)
+            assert p.min() >= 0.0 and p.max() < 1.0
+            assert is_02_net(p, m), (px, py, dim, m)
+    # different pixels and different dimensions get different (decorrelated) point sets
+    a = octx.sampler_points(1, 1, 256, 0, 64, 0, capi.PTC_FLAG_SAMPLER_SOBOL)
+    b = octx.sampler_points(2, 1, 256, 0, 64, 0, capi.PTC_FLAG_SAMPLER_SOBOL)
+    c = octx.sampler_points(1, 1, 256, 0, 64, 2, capi.PTC_FLAG_SAMPLER_SOBOL)
+    assert not np.array_equal(a, b) and not np.array_equal(a, c)
+    # the default stream is not a net (sanity check of the checker) and is unchanged by the new code path
+    r = octx.sampler_points(17, 5, 256, 0, 256, 0, 0)
+    assert not is_02_net(r, 8)
+
+
+def test_sobol_sampler_lowers_the_error_of_a_render(capi, oracle_lib):
+    """Same estimator, same sample count: the low-discrepancy points must beat the default stream on a smooth integrand
+    (environment-lit diffuse sphere), measured against a high sample count render."""
+    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng.build_scene("EnvironmentMapLambert")
+    eng.set_render_info(width=48, height=48, samples=16, batch_size=16, depth=3)
+    ctx = capi.Context(oracle_lib)
+    ctx.upload_scene(eng.scene_desc())
+    ctx.build_accel()
+    rp = eng.render_params()
+    rp.samples = rp.batch_size = 2048
+    ref = ctx.render(rp, want_aovs=False)[0][..., :3]
+    err = {}
+    for flags in (0, capi.PTC_FLAG_SAMPLER_SOBOL):
+        rp.samples = rp.batch_size = 16
+        rp.flags = flags
+        img = ctx.render(rp, want_aovs=False)[0][..., :3]
+        err[flags] = float(np.mean((img - ref) ** 2))
+    assert err[capi.PTC_FLAG_SAMPLER_SOBOL] < 0.8 * err[0], err
+    ctx.close()
+    eng.close()

@@ -93,12 +93,13 @@ class ptc_stats(C.Structure):
 PTC_SPLIT_NONE, PTC_SPLIT_TILE, PTC_SPLIT_SAMPLE = 0, 1, 2
 PTC_FLAG_WORLD_ORIGIN_PROBE_PDF = 1
 PTC_FLAG_TIME_KERNELS = 2
+PTC_FLAG_SAMPLER_SOBOL = 4
 PTC_HIERARCHY_LBVH, PTC_HIERARCHY_PLOC = 0, 1
 
 # every symbol include/ptc.h declares
 PTC_SYMBOLS = ["ptc_create", "ptc_destroy", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_set_build_options", "ptc_build_accel", "ptc_render",
                "ptc_render_device", "ptc_progress", "ptc_get_stats", "ptc_trace_closest", "ptc_get_lbvh", "ptc_get_wide_bvh", "ptc_bsdf_eval",
-               "ptc_bsdf_sample", "ptc_env_lookup"]
+               "ptc_bsdf_sample", "ptc_sampler_points", "ptc_env_lookup"]
 VH_SYMBOLS = ["vh_engine_create", "vh_engine_destroy", "vh_backend_ok", "vh_last_error", "vh_scene_list", "vh_build_scene",
               "vh_set_render_info", "vh_get_render_info", "vh_scene_desc", "vh_render_params", "vh_render_to_memory", "vh_render",
               "vh_get_stats", "vh_read_hdr", "vh_write_hdr"]
@@ -141,6 +142,8 @@ def _declare_ptc(lib):
     lib.ptc_bsdf_eval.restype = C.c_int
     lib.ptc_bsdf_sample.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
     lib.ptc_bsdf_sample.restype = C.c_int
+    lib.ptc_sampler_points.argtypes = [vp, u32, u32, u32, u32, u32, u32, u32, vp]
+    lib.ptc_sampler_points.restype = C.c_int
     lib.ptc_env_lookup.argtypes = [vp, C.c_int, vp, vp]
     lib.ptc_env_lookup.restype = C.c_int
     return lib
@@ -317,6 +320,11 @@ class Context:
         if out["n_nodes"]:
             self._check(self.lib.ptc_get_wide_bvh(self.ctx, C.byref(nn), C.byref(nt), np_ptr(out["words"]), np_ptr(out["tri_order"])),
                         "ptc_get_wide_bvh")
+        return out
+
+    def sampler_points(self, px, py, width, first_index, count, dimension, flags):
+        out = np.zeros((count, 2), np.float32)
+        self._check(self.lib.ptc_sampler_points(self.ctx, px, py, width, first_index, count, dimension, flags, np_ptr(out)), "ptc_sampler_points")
         return out
 
     def bsdf_eval(self, params, wi, wo):

@@ -28,11 +28,91 @@ PTC_HD uint32_t jenkins(uint32_t x) {
 PTC_HD uint32_t rngSeed(uint32_t px, uint32_t py, uint32_t width, uint32_t sampleIndex) {
     return jenkins((px * width + py) ^ jenkins(sampleIndex));
 }
-PTC_D float rnd(uint32_t &s) {
-    s ^= s << 13;
-    s ^= s >> 17;
-    s ^= s << 5;
-    return __uint_as_float(0x3f800000u | (s >> 9)) - 1.0f;
+/* Sampler state of one path.  Two modes:
+ *   default            the reference's default generator (rng_def.glsl): xorshift32 on `s`;
+ *   low discrepancy    (PTC_FLAG_SAMPLER_SOBOL; the reference's optional PMJ02BN sampler, rng_pmj.glsl:66-107, plays this
+ *                      role, its tables are not reproduced) shuffled + Owen-scrambled Sobol points (Burley 2020, "Practical
+ *                      hash-based Owen scrambling"): `s` counts dimensions, the global sample index is shuffled per
+ *                      (pixel, dimension) and the first two Sobol dimensions are scrambled per (pixel, dimension), so that
+ *                      the samples of one pixel are a scrambled (0, m, 2)-net in every dimension pair.
+ * rnd() = rand1D, rnd2() = rand2D of the reference; both modes draw in the same program order. */
+struct Rng {
+    uint32_t s;         /* xorshift state, or the next dimension */
+    uint32_t pixelSeed; /* low discrepancy only */
+    uint32_t index;     /* global sample index of the path (batch * batchSize + s) */
+    uint32_t ld;
+};
+PTC_HD uint32_t hashCombine(uint32_t seed, uint32_t v) { return seed ^ (v + (seed << 6) + (seed >> 2)); }
+PTC_HD uint32_t reverseBits32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __brev(x);
+#else
+    x = ((x >> 1) & 0x55555555u) | ((x & 0x55555555u) << 1);
+    x = ((x >> 2) & 0x33333333u) | ((x & 0x33333333u) << 2);
+    x = ((x >> 4) & 0x0f0f0f0fu) | ((x & 0x0f0f0f0fu) << 4);
+    x = ((x >> 8) & 0x00ff00ffu) | ((x & 0x00ff00ffu) << 8);
+    return (x >> 16) | (x << 16);
+#endif
+}
+PTC_HD uint32_t laineKarras(uint32_t x, uint32_t seed) { /* a hash whose bit k only depends on bits <= k */
+    x += seed;
+    x ^= x * 0x6c50b47cu;
+    x ^= x * 0xb82f1e52u;
+    x ^= x * 0xc7afe638u;
+    x ^= x * 0x8d22f6e6u;
+    return x;
+}
+PTC_HD uint32_t owenScramble(uint32_t x, uint32_t seed) { return reverseBits32(laineKarras(reverseBits32(x), seed)); }
+PTC_HD uint32_t sobolDim1(uint32_t i) { /* second Sobol dimension: direction numbers v_k = v_(k-1) ^ (v_(k-1) >> 1) */
+    uint32_t v = 0x80000000u, r = 0;
+    for (; i; i >>= 1) {
+        if (i & 1u) r ^= v;
+        v ^= v >> 1;
+    }
+    return r;
+}
+PTC_HD float bitsToUnitFloat(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(0x3f800000u | (x >> 9)) - 1.0f;
+#else
+    uint32_t b = 0x3f800000u | (x >> 9);
+    float f;
+    memcpy(&f, &b, 4);
+    return f - 1.0f;
+#endif
+}
+PTC_D Rng rngInit(uint32_t px, uint32_t py, uint32_t width, uint32_t sampleIndex, bool lowDiscrepancy) {
+    Rng r;
+    r.ld = lowDiscrepancy ? 1u : 0u;
+    r.index = sampleIndex;
+    r.pixelSeed = jenkins(px * width + py);
+    r.s = lowDiscrepancy ? 0u : rngSeed(px, py, width, sampleIndex);
+    return r;
+}
+PTC_D float rnd(Rng &r) {
+    if (r.ld) {
+        const uint32_t seed = jenkins(hashCombine(r.pixelSeed, r.s));
+        r.s += 1u;
+        const uint32_t idx = owenScramble(r.index, seed);
+        return bitsToUnitFloat(owenScramble(reverseBits32(idx), hashCombine(seed, 1u)));
+    }
+    r.s ^= r.s << 13;
+    r.s ^= r.s >> 17;
+    r.s ^= r.s << 5;
+    return __uint_as_float(0x3f800000u | (r.s >> 9)) - 1.0f;
+}
+PTC_D float2 rnd2(Rng &r) {
+    if (r.ld) {
+        const uint32_t seed = jenkins(hashCombine(r.pixelSeed, r.s));
+        r.s += 2u;
+        const uint32_t idx = owenScramble(r.index, seed);
+        const uint32_t x = owenScramble(reverseBits32(idx), hashCombine(seed, 1u));
+        const uint32_t y = owenScramble(sobolDim1(idx), hashCombine(seed, 2u));
+        return make_float2(bitsToUnitFloat(x), bitsToUnitFloat(y));
+    }
+    const float a = rnd(r);
+    const float b = rnd(r);
+    return make_float2(a, b);
 }
 
 /* ------------------------------------------------------------------ samplers (sampling.glsl) */

@@ -428,7 +428,7 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
                 launches++;
                 for (uint32_t d = 0; d < rp->depth; d++) {
                     timed(traceMs, [&] { wf::k_extend<<<gridExtend, TRV_BLOCK, 0, s>>>(w, sc, d, c->tune); });
-                    timed(shadeMs, [&] { wf::k_shade<<<gridShade, 128, 0, s>>>(w, sc, rc, d); });
+                    timed(shadeMs, [&] { wf::k_shade<<<gridShade, 128, 0, s>>>(w, sc, rc, d, b * rp->batch_size + s0); });
                     launches += 2;
                     traceLaunches++;
                     if (rc.totalLights > 0) {
@@ -817,6 +817,23 @@ PTC_API int ptc_bsdf_sample(ptc_ctx *c, int n, const float *params, const float 
     CUDA_TRY(cudaMemcpyAsync(out_f, dF.p, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(out_pdf, dPdf.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+    PTC_GUARD_END(c)
+}
+
+PTC_API int ptc_sampler_points(ptc_ctx *c, uint32_t px, uint32_t py, uint32_t width, uint32_t first_index, uint32_t count, uint32_t dimension,
+                               uint32_t flags, float *out_xy) {
+    if (!c || !c->stream) return fail(c, "context has no CUDA device");
+    if (count == 0) return 0;
+    if (!out_xy) return fail(c, "null argument");
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    DBuf<float> dO;
+    dO.alloc((size_t)count * 2);
+    wf::k_sampler_points<<<(count + 255) / 256, 256, 0, c->stream>>>(px, py, width, first_index, count, dimension, flags, dO.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_xy, dO.p, (size_t)count * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
     PTC_GUARD_END(c)
 }

@@ -166,7 +166,7 @@ struct LightSample {
     float pdf, tmax;
     bool delta;
 };
-PTC_D LightSample sampleLight(const DScene &sc, const RenderConst &rc, uint32_t &rng, float3 origin) {
+PTC_D LightSample sampleLight(const DScene &sc, const RenderConst &rc, Rng &rng, float3 origin) {
     LightSample ls;
     ls.delta = true;
     ls.radiance = f3(0.0f);
@@ -199,8 +199,8 @@ PTC_D LightSample sampleLight(const DScene &sc, const RenderConst &rc, uint32_t 
         const ptc_material *mat = &sc.materials[I->material];
         const uint32_t nt = I->numTriangles;
         uint32_t tri = min((uint32_t)(rnd(rng) * (float)nt), nt - 1u);
-        const float u0 = rnd(rng), u1 = rnd(rng);
-        float2 bc = sampleTriangle(u0, u1);
+        const float2 u01 = rnd2(rng);
+        float2 bc = sampleTriangle(u01.x, u01.y);
         float3 sb = f3(bc.x, bc.y, 1.0f - bc.x - bc.y);
         const uint32_t *ind = sc.indices + I->firstIndex + 3 * (size_t)tri;
         const ptc_vertex *V0 = &sc.vertices[I->firstVertex + __ldg(ind + 0)];
@@ -249,8 +249,9 @@ __global__ void __launch_bounds__(256) k_raygen(Wave w, const __grid_constant__ 
     const uint32_t p = slot % rc.nPixLocal, s = slot / rc.nPixLocal;
     const uint32_t pixel = rc.pixmap ? rc.pixmap[p] : p;
     const uint32_t px = pixel % rc.width, py = pixel / rc.width;
-    uint32_t rng = rngSeed(px, py, rc.width, firstSample + s);
-    const float u0 = rnd(rng), u1 = rnd(rng);
+    Rng rng = rngInit(px, py, rc.width, firstSample + s, (rc.flags & PTC_FLAG_SAMPLER_SOBOL) != 0u);
+    const float2 u01 = rnd2(rng);
+    const float u0 = u01.x, u1 = u01.y;
     const float dx = (((float)px + u0) / (float)rc.width) * 2.0f - 1.0f;
     const float dy = (((float)py + u1) / (float)rc.height) * 2.0f - 1.0f;
     float3 oc = f3(0.0f), dc;
@@ -264,8 +265,8 @@ __global__ void __launch_bounds__(256) k_raygen(Wave w, const __grid_constant__ 
     }
     const float lensRadius = rc.sd.exposure[2];
     if (lensRadius > 0.0f) { /* raygen.rgen.glsl:74-85 */
-        const float l0 = rnd(rng), l1 = rnd(rng);
-        float2 disk = concentricDisk(l0, l1);
+        const float2 l01 = rnd2(rng);
+        float2 disk = concentricDisk(l01.x, l01.y);
         float ft = rc.sd.exposure[3] / (-dc.z);
         float3 focus = oc + dc * ft;
         oc = oc + f3(lensRadius * disk.x, lensRadius * disk.y, 0.0f);
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(256) k_raygen(Wave w, const __grid_constant__ 
     float3 d = f3((vi[0] * dc.x + vi[4] * dc.y) + vi[8] * dc.z, (vi[1] * dc.x + vi[5] * dc.y) + vi[9] * dc.z, (vi[2] * dc.x + vi[6] * dc.y) + vi[10] * dc.z);
     uint32_t flags = 0;
     if (rc.sd.volumes[0] != -1.0f) flags |= PF_INVOL | ((uint32_t)(int)rc.sd.volumes[0] << PF_VOL_SHIFT);
-    stS(&w.orgRng[slot], make_float4(o.x, o.y, o.z, __uint_as_float(rng)));
+    stS(&w.orgRng[slot], make_float4(o.x, o.y, o.z, __uint_as_float(rng.s)));
     stS(&w.dirFlags[slot], make_float4(d.x, d.y, d.z, __uint_as_float(flags)));
     stS(&w.beta[slot], make_float4(1.0f, 1.0f, 1.0f, 0.0f));
     stS(&w.radiance[slot], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(TRV_BLOCK, 8) k_extend(Wave w, const __grid_co
 
 /* ------------------------------------------------------------------ k_shade */
 /* process_volume_hit.glsl:1-80. Returns sampledMedium; on scattering fills the requests and the new ray. */
-PTC_D bool volumeEvent(const DScene &sc, const RenderConst &rc, uint32_t &rng, uint32_t flags, float3 &origin, float3 &dir, float3 &beta,
+PTC_D bool volumeEvent(const DScene &sc, const RenderConst &rc, Rng &rng, uint32_t flags, float3 &origin, float3 &dir, float3 &beta,
                        float vtstart, float vtend, Requests &rq) {
     Medium md = loadMedium(sc, flags >> PF_VOL_SHIFT);
     const float g = fmaxf(fminf(md.g, 0.99f), -0.99f);
@@ -468,9 +469,9 @@ PTC_D bool volumeEvent(const DScene &sc, const RenderConst &rc, uint32_t &rng, u
                 rq.shContrib = c;
             }
         }
-        const float h0 = rnd(rng), h1 = rnd(rng);
+        const float2 h01 = rnd2(rng);
         float3 nd;
-        const float spdf = hgSample(wo, nd, h0, h1, g);
+        const float spdf = hgSample(wo, nd, h01.x, h01.y, g);
         origin = sp;
         dir = nd;
         rq.probe = true;
@@ -481,7 +482,7 @@ PTC_D bool volumeEvent(const DScene &sc, const RenderConst &rc, uint32_t &rng, u
 }
 
 /* russian_roulette.glsl:1-11; returns true when the path dies */
-PTC_D bool roulette(uint32_t &rng, uint32_t depth, float3 &beta) {
+PTC_D bool roulette(Rng &rng, uint32_t depth, float3 &beta) {
     const float r = rnd(rng);
     if (depth > 3u) {
         const float mb = max3(beta);
@@ -491,7 +492,8 @@ PTC_D bool roulette(uint32_t &rng, uint32_t depth, float3 &beta) {
     return false;
 }
 
-__global__ void __launch_bounds__(128, 6) k_shade(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce) {
+__global__ void __launch_bounds__(128, 6) k_shade(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
+                                                         uint32_t firstSample) {
     const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_ACTIVE];
     const uint32_t *__restrict__ q = w.queue[bounce & 1u];
     uint32_t *__restrict__ qNext = w.queue[(bounce + 1u) & 1u];
@@ -512,7 +514,16 @@ __global__ void __launch_bounds__(128, 6) k_shade(Wave w, const __grid_constant_
             const float4 h = ldS(&w.hit[slot]);
             const float4 o4 = ldS(&w.orgRng[slot]), d4 = ldS(&w.dirFlags[slot]);
             float3 origin = f3(o4), dir = f3(d4);
-            uint32_t rng = __float_as_uint(o4.w), flags = __float_as_uint(d4.w);
+            uint32_t flags = __float_as_uint(d4.w);
+            Rng rng;
+            rng.s = __float_as_uint(o4.w);
+            rng.ld = (rc.flags & PTC_FLAG_SAMPLER_SOBOL) ? 1u : 0u;
+            rng.index = rng.pixelSeed = 0u;
+            if (rng.ld) { /* the sampler's key is a function of the slot: (pixel, global sample index) */
+                const uint32_t p = slot % rc.nPixLocal, pixel = rc.pixmap ? rc.pixmap[p] : p;
+                rng.pixelSeed = jenkins((pixel % rc.width) * rc.width + pixel / rc.width);
+                rng.index = firstSample + slot / rc.nPixLocal;
+            }
             flags = (flags & ~PF_DEPTH_MASK) | (bounce & PF_DEPTH_MASK);
             float3 beta = f3(ldS(&w.beta[slot]));
             float3 radiance = f3(ldS(&w.radiance[slot]));
@@ -597,14 +608,15 @@ __global__ void __launch_bounds__(128, 6) k_shade(Wave w, const __grid_constant_
                             float spdf;
                             float3 wiL;
                             if (lambert) {
-                                const float a0 = rnd(rng), a1 = rnd(rng);
-                                wiL = cosineHemisphere(a0, a1, spdf);
+                                const float2 a01 = rnd2(rng);
+                                wiL = cosineHemisphere(a01.x, a01.y, spdf);
                                 origin = s.pos;
                                 dir = toWorld(fr, wiL);
                                 beta *= albedo;
                             } else {
-                                const float a0 = rnd(rng), a1 = rnd(rng), a2 = rnd(rng);
-                                const float3 F = pbrSample(wiL, wo, spdf, pbr, a0, a1, a2);
+                                const float2 a01 = rnd2(rng);
+                                const float a2 = rnd(rng);
+                                const float3 F = pbrSample(wiL, wo, spdf, pbr, a01.x, a01.y, a2);
                                 origin = s.pos;
                                 dir = toWorld(fr, wiL);
                                 if (isBlack(F)) {
@@ -652,7 +664,7 @@ __global__ void __launch_bounds__(128, 6) k_shade(Wave w, const __grid_constant_
             if (doRoulette && !stop) stop = roulette(rng, bounce, beta);
             /* requests that can only return black are dropped (result-identical) */
             if (rq.probe && !sc.anyEmissive) rq.probe = false;
-            stS(&w.orgRng[slot], make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng)));
+            stS(&w.orgRng[slot], make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng.s)));
             stS(&w.dirFlags[slot], make_float4(dir.x, dir.y, dir.z, __uint_as_float(flags)));
             stS(&w.beta[slot], make_float4(beta.x, beta.y, beta.z, 0.0f));
             stS(&w.radiance[slot], make_float4(radiance.x, radiance.y, radiance.z, 0.0f));
@@ -956,6 +968,19 @@ __global__ void k_bsdf_sample(int n, const float *params, const float *wo, const
     outF[i * 3 + 1] = F.y;
     outF[i * 3 + 2] = F.z;
     outPdf[i] = pdf;
+}
+__global__ void k_sampler_points(uint32_t px, uint32_t py, uint32_t width, uint32_t firstIndex, uint32_t count, uint32_t dimension, uint32_t flags,
+                                 float *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Rng r = rngInit(px, py, width, firstIndex + i, (flags & PTC_FLAG_SAMPLER_SOBOL) != 0u);
+    if (r.ld)
+        r.s = dimension;
+    else
+        for (uint32_t k = 0; k < dimension; k++) rnd(r);
+    const float2 p = rnd2(r);
+    out[2 * i] = p.x;
+    out[2 * i + 1] = p.y;
 }
 __global__ void k_env_lookup(const __grid_constant__ DScene sc, int n, const float *dirs, float *out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -547,6 +547,7 @@ ptc_render_params CudaRendererPathTracing::makeRenderParams() {
     rp.split_mode = PTC_SPLIT_NONE;
     rp.rank = 0;
     rp.world = 1;
+    rp.flags = renderInfo().lowDiscrepancySampler ? PTC_FLAG_SAMPLER_SOBOL : 0u;
     return rp;
 }
 

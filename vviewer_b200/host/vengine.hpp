@@ -571,6 +571,9 @@ public:
         uint32_t height = 1080u;
         bool denoise = false;
         bool writeAllFiles = false;
+        /* extension: the reference selects its sampler at shader-compile time (SAMPLING_RTGEMS / SAMPLING_PMJ in
+         * defines_pt.glsl); here it is a render setting.  true = low-discrepancy (PTC_FLAG_SAMPLER_SOBOL) */
+        bool lowDiscrepancySampler = false;
     };
     virtual ~RendererPathTracing() {}
     RenderInfo &renderInfo() { return m_renderInfo; }
