@@ -179,24 +179,29 @@ void createTextures(ptc_ctx *c, const ptc_scene_desc *sd) {
         TextureClass &k = c->texClasses[cls];
         k.layers = (uint32_t)members[cls].size();
         const size_t texels = (size_t)k.width * k.height;
-        std::vector<uint8_t> rgba(texels * 4 * k.layers);
-        for (uint32_t l = 0; l < k.layers; l++) {
-            const ptc_texture &in = sd->textures[members[cls][l]];
-            uint8_t *dst = rgba.data() + texels * 4 * l;
-            for (size_t p = 0; p < texels; p++) {
-                uint8_t px[4] = {0, 0, 0, 255};
-                for (uint32_t ch = 0; ch < in.channels && ch < 4; ch++) px[ch] = in.data[p * in.channels + ch];
-                std::memcpy(dst + p * 4, px, 4);
-            }
-        }
         cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
         CUDA_TRY(cudaMalloc3DArray(&k.array, &fmt, make_cudaExtent(k.width, k.height, k.layers), cudaArrayLayered));
-        cudaMemcpy3DParms cp{};
-        cp.srcPtr = make_cudaPitchedPtr(rgba.data(), (size_t)k.width * 4, k.width, k.height);
-        cp.dstArray = k.array;
-        cp.extent = make_cudaExtent(k.width, k.height, k.layers);
-        cp.kind = cudaMemcpyHostToDevice;
-        CUDA_TRY(cudaMemcpy3D(&cp));
+        std::vector<uint8_t> rgba; /* staging only for R8 sources */
+        for (uint32_t l = 0; l < k.layers; l++) {
+            const ptc_texture &in = sd->textures[members[cls][l]];
+            const uint8_t *src = in.data;
+            if (in.channels != 4) {
+                rgba.resize(texels * 4);
+                for (size_t p = 0; p < texels; p++) {
+                    uint8_t px[4] = {0, 0, 0, 255};
+                    for (uint32_t ch = 0; ch < in.channels && ch < 4; ch++) px[ch] = in.data[p * in.channels + ch];
+                    std::memcpy(rgba.data() + p * 4, px, 4);
+                }
+                src = rgba.data();
+            }
+            cudaMemcpy3DParms cp{};
+            cp.srcPtr = make_cudaPitchedPtr((void *)src, (size_t)k.width * 4, k.width, k.height);
+            cp.dstArray = k.array;
+            cp.dstPos = make_cudaPos(0, 0, l);
+            cp.extent = make_cudaExtent(k.width, k.height, 1);
+            cp.kind = cudaMemcpyHostToDevice;
+            CUDA_TRY(cudaMemcpy3D(&cp)); /* synchronous: the staging vector is reused */
+        }
         cudaResourceDesc rd{};
         rd.resType = cudaResourceTypeArray;
         rd.res.array.array = k.array;
