@@ -15,7 +15,8 @@ CXXFLAGS  := -O2 -std=c++17 -fPIC -fvisibility=hidden -Wall -Wno-unused-variable
 CUDA_SRCS := $(wildcard vviewer_b200/csrc/*.cu)
 CUDA_HDRS := $(wildcard vviewer_b200/csrc/*.cuh) include/ptc.h
 HOST_SRCS := vviewer_b200/host/vengine.cpp vviewer_b200/host/io_image.cpp vviewer_b200/host/io_obj.cpp \
-             vviewer_b200/host/scenes.cpp vviewer_b200/host/capi.cpp
+             vviewer_b200/host/scenes.cpp vviewer_b200/host/capi.cpp \
+             vviewer_b200/host/io_jpeg.cpp vviewer_b200/host/io_gltf.cpp vviewer_b200/host/io_scene.cpp
 HOST_HDRS := $(wildcard vviewer_b200/host/*.hpp) include/ptc.h include/vengine_host.h
 
 all: $(LIBDIR)/libptc_cuda.so $(LIBDIR)/libvengine_host.so $(LIBDIR)/offlinerender

@@ -29,6 +29,15 @@ PTC_API const char *vh_last_error(vh_engine *e);
 PTC_API const char *vh_scene_list(void); /* comma-separated recipe names */
 /* build a recipe scene (vviewer_b200/host/scenes.hpp); texture_size/scale <= 0 keep the defaults */
 PTC_API int vh_build_scene(vh_engine *e, const char *name, int texture_size, float scale, int camera);
+/* Engine::importModel (VulkanEngine.cpp:157-192): .obj (+ .mtl) and .gltf / .glb; path relative to the asset root or absolute */
+PTC_API int vh_import_model(vh_engine *e, const char *path, int import_materials);
+/* addModel3D (core/SceneUtils.cpp:76-130) under the scene root, then Scene::update */
+PTC_API int vh_add_model(vh_engine *e, const char *model_name);
+/* scene files of core/io/Import.cpp / Export.cpp: <dir>/scene.json + <dir>/assets/ */
+PTC_API int vh_import_scene(vh_engine *e, const char *scene_json);
+PTC_API int vh_export_scene(vh_engine *e, const char *directory);
+/* JSON text describing models / materials / textures / scene objects / camera (valid until the next call); for tests */
+PTC_API const char *vh_describe(vh_engine *e);
 PTC_API void vh_set_render_info(vh_engine *e, int width, int height, int samples, int batch_size, int depth); /* <= 0 keeps */
 PTC_API void vh_get_render_info(vh_engine *e, int *width, int *height, int *samples, int *batch_size, int *depth);
 
@@ -44,6 +53,12 @@ PTC_API int vh_get_stats(vh_engine *e, ptc_stats *out);
 /* Radiance HDR helpers (RGBA32F in memory, top row first) */
 PTC_API int vh_read_hdr(const char *path, int *w, int *h, float *rgba_out);
 PTC_API int vh_write_hdr(const char *path, int w, int h, int channels, const float *data);
+
+/* PNG / JPEG decode from memory with the reference's conventions (stbi_load_from_memory(..., STBI_rgb_alpha),
+ * src/lib/vengine/core/io/AssimpLoadModel.cpp:190; flip = stbi_set_flip_vertically_on_load, core/Image.cpp:39).
+ * Call with out == NULL to get the size (w * h * channels bytes), then again with a buffer. */
+PTC_API int vh_decode_image(const uint8_t *bytes, uint64_t n_bytes, int flip, int *w, int *h, int *channels, int *src_channels, uint8_t *out,
+                            uint64_t out_capacity);
 
 #ifdef __cplusplus
 }

@@ -181,6 +181,18 @@ def _declare_vh(lib):
     lib.vh_read_hdr.restype = C.c_int
     lib.vh_write_hdr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, vp]
     lib.vh_write_hdr.restype = C.c_int
+    lib.vh_import_model.argtypes = [vp, C.c_char_p, C.c_int]
+    lib.vh_import_model.restype = C.c_int
+    lib.vh_add_model.argtypes = [vp, C.c_char_p]
+    lib.vh_add_model.restype = C.c_int
+    lib.vh_import_scene.argtypes = [vp, C.c_char_p]
+    lib.vh_import_scene.restype = C.c_int
+    lib.vh_export_scene.argtypes = [vp, C.c_char_p]
+    lib.vh_export_scene.restype = C.c_int
+    lib.vh_describe.argtypes = [vp]
+    lib.vh_describe.restype = C.c_char_p
+    lib.vh_decode_image.argtypes = [vp, C.c_uint64, C.c_int, _ip, _ip, _ip, _ip, vp, C.c_uint64]
+    lib.vh_decode_image.restype = C.c_int
     return lib
 
 
@@ -387,8 +399,32 @@ class HostEngine:
 
     def build_scene(self, name, texture_size=0, scale=0.0, camera=0):
         rc = self.lib.vh_build_scene(self.h, name.encode(), int(texture_size), float(scale), int(camera))
+        if rc == 3:
+            raise RuntimeError("scene recipe %r failed: %s" % (name, self.last_error()))
         if rc != 0:
             raise RuntimeError("unknown scene recipe %r" % name)
+
+    def import_model(self, path, import_materials=True):
+        """Engine::importModel: .obj (+ .mtl), .gltf, .glb"""
+        if self.lib.vh_import_model(self.h, path.encode(), int(bool(import_materials))) != 0:
+            raise RuntimeError(self.last_error())
+
+    def add_model(self, model_name):
+        """addModel3D under the scene root + Scene::update"""
+        if self.lib.vh_add_model(self.h, model_name.encode()) != 0:
+            raise RuntimeError(self.last_error())
+
+    def import_scene(self, scene_json):
+        if self.lib.vh_import_scene(self.h, scene_json.encode()) != 0:
+            raise RuntimeError(self.last_error())
+
+    def export_scene(self, directory):
+        if self.lib.vh_export_scene(self.h, directory.encode()) != 0:
+            raise RuntimeError(self.last_error())
+
+    def describe(self):
+        import json
+        return json.loads(self.lib.vh_describe(self.h).decode())
 
     def set_render_info(self, width=0, height=0, samples=0, batch_size=0, depth=0):
         self.lib.vh_set_render_info(self.h, width, height, samples, batch_size, depth)
@@ -425,6 +461,19 @@ class HostEngine:
         s = ptc_stats()
         self.lib.vh_get_stats(self.h, C.byref(s))
         return s.as_dict()
+
+
+def decode_image(data, flip=False):
+    """PNG / JPEG bytes -> (uint8 array H x W x C, channel count of the file) through the host library's own decoders"""
+    lib = load_host()
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    w, h, c, sc = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    if lib.vh_decode_image(buf, len(data), int(flip), C.byref(w), C.byref(h), C.byref(c), C.byref(sc), None, 0) != 0:
+        raise RuntimeError("cannot decode image")
+    out = np.zeros((h.value, w.value, c.value), np.uint8)
+    if lib.vh_decode_image(buf, len(data), int(flip), None, None, None, None, np_ptr(out), out.size) != 0:
+        raise RuntimeError("cannot decode image")
+    return out, sc.value
 
 
 def read_hdr(path):

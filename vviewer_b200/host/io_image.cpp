@@ -40,11 +40,17 @@ static void flipRows(uint8_t *data, int rowBytes, int h) {
 /* ---------------------------------------------------------------- PNG in */
 static uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
-bool loadImageU8(const std::string &path, ImageU8 &out, bool flipVertically) {
-    std::vector<uint8_t> file;
-    if (!readFile(path, file) || file.size() < 33) return false;
-    static const uint8_t sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
-    if (std::memcmp(file.data(), sig, 8) != 0) return false;
+static const uint8_t kPngSignature[8] = {137, 80, 78, 71, 13, 10, 26, 10};
+
+/* PNG from memory; rows top first.  srcChannels = the channel count stbi reports for the file */
+static bool decodePNG(const uint8_t *bytes, size_t nBytes, ImageU8 &out, int *srcChannels) {
+    if (nBytes < 33 || std::memcmp(bytes, kPngSignature, 8) != 0) return false;
+    struct View {
+        const uint8_t *d;
+        size_t n;
+        size_t size() const { return n; }
+        const uint8_t &operator[](size_t i) const { return d[i]; }
+    } file{bytes, nBytes};
     uint32_t w = 0, h = 0;
     int bitDepth = 0, colorType = 0, interlace = 0;
     std::vector<uint8_t> idat, plte, trns;
@@ -135,8 +141,24 @@ bool loadImageU8(const std::string &path, ImageU8 &out, bool flipVertically) {
         else
             std::memcpy(&out.data[p * 4], px, 4);
     }
-    if (flipVertically) flipRows(out.data.data(), out.width * out.channels, out.height);
+    if (srcChannels) *srcChannels = infoCh;
     return true;
+}
+
+bool decodeImageU8(const uint8_t *bytes, size_t nBytes, ImageU8 &out, int *srcChannels, bool flipVertically) {
+    bool ok = false;
+    if (nBytes >= 8 && std::memcmp(bytes, kPngSignature, 8) == 0)
+        ok = decodePNG(bytes, nBytes, out, srcChannels);
+    else if (nBytes >= 3 && bytes[0] == 0xFF && bytes[1] == 0xD8 && bytes[2] == 0xFF)
+        ok = decodeJPEG(bytes, nBytes, out, srcChannels);
+    if (ok && flipVertically) flipRows(out.data.data(), out.width * out.channels, out.height);
+    return ok;
+}
+
+bool loadImageU8(const std::string &path, ImageU8 &out, bool flipVertically, int *srcChannels) {
+    std::vector<uint8_t> file;
+    if (!readFile(path, file)) return false;
+    return decodeImageU8(file.data(), file.size(), out, srcChannels, flipVertically);
 }
 
 /* ---------------------------------------------------------------- PNG out */
@@ -153,8 +175,7 @@ bool writeImagePNG(const std::string &path, int w, int h, int channels, const ui
     if (compress2(comp.data(), &clen, raw.data(), (uLong)raw.size(), 6) != Z_OK) return false;
     FILE *f = std::fopen(path.c_str(), "wb");
     if (!f) return false;
-    static const uint8_t sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
-    std::fwrite(sig, 1, 8, f);
+    std::fwrite(kPngSignature, 1, 8, f);
     auto chunk = [&](const char *type, const uint8_t *d, uint32_t len) {
         uint8_t hdr[8] = {(uint8_t)(len >> 24), (uint8_t)(len >> 16), (uint8_t)(len >> 8), (uint8_t)len, (uint8_t)type[0], (uint8_t)type[1],
                           (uint8_t)type[2], (uint8_t)type[3]};

@@ -295,6 +295,21 @@ static void hierarchy(Engine &e) {
     testRenderInfo(e, "Hierarchy", 2048, 64);
 }
 
+/* RenderTests.cpp:788-831: the glTF import path (DamagedHelmet: embedded buffers, 5 JPEG textures, emissive + normal + AO maps) */
+static void gltf(Engine &e) {
+    Scene &scene = e.scene();
+    makeCamera(scene, vec3(0, 0.5f, 2), vec3(vm::radians(-20.0f), 0, 0));
+    BaseMeshes bm = baseMeshes(e);
+    addMeshObject(scene, "plane", Transform({0, -1, 0}, {5, 5, 5}), bm.plane, e.materials().get("defaultMaterial"));
+    const std::string assetName = "assets/models/DamagedHelmet.gltf";
+    if (!e.importModel(AssetInfo(assetName), true)) throw std::runtime_error("GLTF scene: cannot import " + assetName);
+    addModel3D(scene, nullptr, assetName, std::nullopt, std::nullopt);
+    scene.environmentType() = EnvironmentType::HDRI;
+    scene.environmentIntensity() = 1.0f;
+    scene.update();
+    testRenderInfo(e, "GLTF", 2048, 64);
+}
+
 /* RenderTests.cpp:905-967 */
 static void depthOfField(Engine &e) {
     Scene &scene = e.scene();
@@ -946,7 +961,7 @@ static void instanced(Engine &e, const Options &opt) {
 std::vector<std::string> list() {
     return {"FurnacePBR", "FurnaceLambert", "EnvironmentMap", "EnvironmentMapPBR00", "EnvironmentMapPBR01", "EnvironmentMapPBR10", "EnvironmentMapPBR11",
             "EnvironmentMapLambert", "Volume0", "Volume1", "Volume2", "Volume3", "Volume4", "Volume5", "Volume6", "Volume7", "Volume8", "Volume9",
-            "PointLight", "DirectionalLight", "MeshLight", "Transparency", "NormalMap", "Hierarchy", "DepthOfField", "SharedComponents", "Denoise",
+            "PointLight", "DirectionalLight", "MeshLight", "Transparency", "NormalMap", "GLTF", "Hierarchy", "DepthOfField", "SharedComponents", "Denoise",
             "Cornell", "Atrium", "Fog", "Instanced", "Progressive"};
 }
 
@@ -963,6 +978,7 @@ bool build(Engine &e, const std::string &name, const Options &opt) {
     else if (name == "MeshLight") lights(e, 2);
     else if (name == "Transparency") transparency(e);
     else if (name == "NormalMap") normalMap(e);
+    else if (name == "GLTF") gltf(e);
     else if (name == "Hierarchy") hierarchy(e);
     else if (name == "DepthOfField") depthOfField(e);
     else if (name == "SharedComponents") sharedComponents(e);

@@ -122,6 +122,71 @@ Material *Materials::createMaterial(const AssetInfo &info, MaterialType type) {
     }
 }
 
+/* vulkan/resources/VulkanMaterials.cpp:154-233 */
+std::vector<Material *> Materials::createImportedMaterials(const std::vector<ImportedMaterial> &imported) {
+    auto getTexture = [&](const ImportedTexture &tex) -> Texture * {
+        if (tex.image) {
+            Texture *t = m_textures.createTexture(tex.name, *tex.image, tex.colorSpace);
+            if (t) {
+                t->embedded = tex.embedded;
+                t->filepath = tex.filepath;
+            }
+            return t;
+        }
+        return m_textures.get(tex.name); /* a texture some model embedded earlier, referenced by name */
+    };
+    std::vector<Material *> out;
+    for (const ImportedMaterial &mat : imported) {
+        if (mat.type == ImportedMaterialType::EMBEDDED) {
+            out.push_back(nullptr);
+        } else if (mat.type == ImportedMaterialType::LAMBERT) {
+            auto *m = createMaterial<MaterialLambert>(mat.info);
+            out.push_back(m);
+            if (!m) continue;
+            m->albedo() = mat.albedo;
+            m->ao() = mat.ao;
+            m->emissive() = vec4(mat.emissiveColor, mat.emissiveStrength);
+            Texture *t;
+            if (mat.albedoTexture && (t = getTexture(*mat.albedoTexture))) m->setAlbedoTexture(t);
+            if (mat.aoTexture && (t = getTexture(*mat.aoTexture))) m->setAOTexture(t);
+            if (mat.emissiveTexture && (t = getTexture(*mat.emissiveTexture))) m->setEmissiveTexture(t);
+            if (mat.normalTexture && (t = getTexture(*mat.normalTexture))) m->setNormalTexture(t);
+            if (mat.alphaTexture && (t = getTexture(*mat.alphaTexture))) m->setAlphaTexture(t);
+            m->setTransparent(mat.transparent);
+            m->uTiling() = mat.scale.x;
+            m->vTiling() = mat.scale.y;
+        } else if (mat.type == ImportedMaterialType::PBR_STANDARD) {
+            auto *m = createMaterial<MaterialPBRStandard>(mat.info);
+            out.push_back(m);
+            if (!m) continue;
+            m->albedo() = mat.albedo;
+            m->roughness() = mat.roughness;
+            m->metallic() = mat.metallic;
+            m->ao() = mat.ao;
+            m->emissive() = vec4(mat.emissiveColor, mat.emissiveStrength);
+            Texture *t;
+            if (mat.albedoTexture && (t = getTexture(*mat.albedoTexture))) m->setAlbedoTexture(t);
+            if (mat.roughnessTexture && (t = getTexture(*mat.roughnessTexture))) m->setRoughnessTexture(t);
+            if (mat.metallicTexture && (t = getTexture(*mat.metallicTexture))) m->setMetallicTexture(t);
+            if (mat.aoTexture && (t = getTexture(*mat.aoTexture))) m->setAOTexture(t);
+            if (mat.emissiveTexture && (t = getTexture(*mat.emissiveTexture))) m->setEmissiveTexture(t);
+            if (mat.normalTexture && (t = getTexture(*mat.normalTexture))) m->setNormalTexture(t);
+            if (mat.alphaTexture && (t = getTexture(*mat.alphaTexture))) m->setAlphaTexture(t);
+            m->setTransparent(mat.transparent);
+            m->uTiling() = mat.scale.x;
+            m->vTiling() = mat.scale.y;
+        } else {
+            auto *m = createMaterial<MaterialVolume>(mat.info);
+            out.push_back(m);
+            if (!m) continue;
+            m->sigmaS() = vec4(mat.sigmaS, 1.0f);
+            m->sigmaA() = vec4(mat.sigmaA, 1.0f);
+            m->g() = mat.g;
+        }
+    }
+    return out;
+}
+
 /* ====================================================================== transform */
 void Transform::setRotation(vec3 forward, vec3 up) {
     vec3 newZ = vm::normalize(-forward);
@@ -313,6 +378,7 @@ Model3D *Engine::addModel(std::unique_ptr<Model3D> model) {
     Model3D *raw = model.get();
     for (auto &m : raw->meshes) {
         m->poolIndex = (uint32_t)m_meshPool.size();
+        m->model = raw;
         m_meshPool.push_back(m.get());
     }
     m_ownedModels.push_back(std::move(model));
@@ -320,14 +386,65 @@ Model3D *Engine::addModel(std::unique_ptr<Model3D> model) {
     return raw;
 }
 
-Model3D *Engine::importModel(const AssetInfo &info, bool) {
+/* VulkanEngine::importModel (VulkanEngine.cpp:157-192) + VulkanModel3D::importNode (VulkanModel3D.cpp:47-76) */
+Model3D *Engine::importModel(const AssetInfo &info, bool importMaterials) {
     if (m_models.has(info.name)) return m_models.get(info.name);
+    const std::string path = assetPath(info.filepath);
+    std::string ext;
+    size_t dot = path.find_last_of('.');
+    if (dot != std::string::npos) ext = path.substr(dot + 1);
+    for (char &c : ext) c = (char)std::tolower((unsigned char)c);
+
+    ImportedModelNode root;
+    std::vector<ImportedMaterial> importedMaterials;
+    std::string err;
+    bool ok;
+    if (ext == "obj")
+        ok = loadOBJ(path, root, importMaterials ? &importedMaterials : nullptr, &err);
+    else if (ext == "gltf" || ext == "glb")
+        ok = loadGLTF(path, root, importMaterials ? &importedMaterials : nullptr, &err);
+    else {
+        ok = false;
+        err = "unsupported model format ." + ext + " (" + path + ")"; /* the reference also lists .fbx, served by assimp */
+    }
+    if (!ok) {
+        std::fprintf(stderr, "Engine::importModel(): Failed to import a model: %s\n", err.c_str());
+        return nullptr;
+    }
+    std::vector<Material *> materials;
+    if (importMaterials) materials = m_materials->createImportedMaterials(importedMaterials);
+
     auto model = std::make_unique<Model3D>();
     model->name = info.name;
-    std::string err;
-    if (!loadOBJ(assetPath(info.filepath), *model, &err)) {
-        std::fprintf(stderr, "Engine::importModel(): %s\n", err.c_str());
-        return nullptr;
+    model->filepath = path;
+    model->internal = info.source == AssetSource::ENGINE;
+    /* importNode() appends the children of EVERY node to the model's root (`m_nodeTree.add()`, VulkanModel3D.cpp:73):
+     * the tree is flattened to root + all descendants, each keeping its local transform (SURVEY trap T13) */
+    std::vector<ImportedModelNode *> descendants; /* pre-order, the order importNode() appends them in */
+    std::function<void(ImportedModelNode &)> collect = [&](ImportedModelNode &n) {
+        for (ImportedModelNode &c : n.children) {
+            descendants.push_back(&c);
+            collect(c);
+        }
+    };
+    collect(root);
+    {
+        Model3D::Model3DNode &dst = model->nodeTree;
+        dst.name = root.name;
+        dst.transform = root.transform;
+        auto take = [&](ImportedModelNode &src, Model3D::Model3DNode &node) {
+            node.name = src.name;
+            node.transform = src.transform;
+            for (size_t i = 0; i < src.meshes.size(); i++) {
+                int32_t mi = src.materialIndices[i];
+                node.meshes.push_back(src.meshes[i].get());
+                node.materials.push_back(mi >= 0 && (size_t)mi < materials.size() ? materials[(size_t)mi] : nullptr);
+                model->meshes.push_back(std::move(src.meshes[i]));
+            }
+        };
+        take(root, dst);
+        dst.children.resize(descendants.size());
+        for (size_t i = 0; i < descendants.size(); i++) take(*descendants[i], dst.children[i]);
     }
     return addModel(std::move(model));
 }
@@ -337,6 +454,7 @@ EnvironmentMap *Engine::importEnvironmentMap(const AssetInfo &info) {
         if (e->name == info.name) return e.get();
     auto env = std::make_unique<EnvironmentMap>();
     env->name = info.name;
+    env->filepath = assetPath(info.filepath);
     if (!loadImageHDR(assetPath(info.filepath), env->equirect, true)) {
         std::fprintf(stderr, "Engine::importEnvironmentMap(): unable to load %s\n", info.filepath.c_str());
         return nullptr;

@@ -44,6 +44,7 @@ enum class AssetSource { DISK = 0, ENGINE = 1 };
 struct AssetInfo { /* core/Asset.hpp */
     std::string name, filepath;
     AssetSource source = AssetSource::DISK;
+    bool embedded = false; /* AssetLocation::DISK_EMBEDDED: lives inside a model file */
     AssetInfo() {}
     AssetInfo(const char *n) : name(n), filepath(n) {}
     AssetInfo(const std::string &n) : name(n), filepath(n) {}
@@ -84,7 +85,11 @@ struct ImageF32 {
     std::vector<float> data;
 };
 /* io_image.cpp */
-bool loadImageU8(const std::string &path, ImageU8 &out, bool flipVertically);     /* PNG (8-bit, non-interlaced) */
+/* PNG (8/16-bit, non-interlaced) or JPEG (baseline / progressive). 1-channel files stay 1 channel, everything else becomes
+ * RGBA (Image<stbi_uc>::loadDiskImage); srcChannels = the channel count of the file as stbi reports it */
+bool loadImageU8(const std::string &path, ImageU8 &out, bool flipVertically, int *srcChannels = nullptr);
+bool decodeImageU8(const uint8_t *bytes, size_t nBytes, ImageU8 &out, int *srcChannels, bool flipVertically);
+bool decodeJPEG(const uint8_t *bytes, size_t nBytes, ImageU8 &outRGBA, int *srcChannels); /* io_jpeg.cpp; rows top first */
 bool loadImageHDR(const std::string &path, ImageF32 &out, bool flipVertically);   /* Radiance RGBE -> RGBA32F */
 bool writeImageHDR(const std::string &path, int w, int h, int channels, const float *data); /* like stbi_write_hdr */
 bool writeImagePNG(const std::string &path, int w, int h, int channels, const uint8_t *data);
@@ -96,6 +101,8 @@ void writeToDisk(const std::vector<float> &in, const std::string &filename, File
 class Texture {
 public:
     std::string name;
+    std::string filepath;  /* disk textures; empty for engine-made and embedded ones */
+    bool embedded = false; /* decoded out of a model file (AssetLocation::DISK_EMBEDDED) */
     ImageU8 image;
     ColorSpace colorSpace = ColorSpace::sRGB;
     uint32_t bindlessResourceIndex = 0; /* slot in the texture table (VulkanTextures.cpp:145) */
@@ -107,6 +114,7 @@ public:
     Texture *createTexture(const AssetInfo &info, ColorSpace colorSpace = ColorSpace::sRGB);
     Texture *createTexture(const std::string &name, const ImageU8 &image, ColorSpace colorSpace);
     Texture *get(const std::string &name) const { return m_map.get(name); }
+    Texture *bySlot(uint32_t slot) const { return slot < m_textures.size() ? m_textures[slot].get() : nullptr; }
     const std::vector<std::unique_ptr<Texture>> &all() const { return m_textures; }
 
 private:
@@ -116,7 +124,7 @@ private:
 
 class EnvironmentMap {
 public:
-    std::string name;
+    std::string name, filepath;
     ImageF32 equirect; /* RGBA32F, flipped like Image<float>::loadDiskImage (core/Image.cpp:27-43) */
 };
 
@@ -124,6 +132,7 @@ public:
 enum class MaterialType { MATERIAL_NOT_SET = -1, MATERIAL_PBR_STANDARD = 0, MATERIAL_SKYBOX = 1, MATERIAL_LAMBERT = 2, MATERIAL_VOLUME = 3 };
 typedef uint32_t MaterialIndex;
 class Materials;
+struct ImportedMaterial;
 
 class Material { /* core/Material.hpp */
 public:
@@ -131,6 +140,7 @@ public:
     virtual ~Material() {}
     virtual MaterialType type() const = 0;
     const std::string &name() const { return m_info.name; }
+    bool isEmbedded() const { return m_info.embedded; }
     MaterialIndex materialIndex() const { return m_index; }
     virtual bool isEmissive() const { return false; }
     virtual bool isTransparent() const { return false; }
@@ -213,7 +223,10 @@ public:
         return m;
     }
     Material *createMaterial(const AssetInfo &info, MaterialType type);
+    /* vulkan/resources/VulkanMaterials.cpp:154-233; EMBEDDED entries give nullptr */
+    std::vector<Material *> createImportedMaterials(const std::vector<ImportedMaterial> &imported);
     Material *get(const std::string &n) const { return m_map.get(n); }
+    const std::map<std::string, Material *> &all() const { return m_map.all(); }
     std::vector<ptc_material> &blocks() { return m_blocks; }
     const std::vector<ptc_material> &blocks() const { return m_blocks; }
     Textures &textures() { return m_textures; }
@@ -247,31 +260,6 @@ private:
 typedef Light PointLight;
 typedef Light DirectionalLight;
 
-/* ------------------------------------------------------------------ geometry */
-typedef ptc_vertex Vertex; /* core/Mesh.hpp:15-40 */
-class Mesh {
-public:
-    std::string name;
-    std::vector<Vertex> vertices;
-    std::vector<uint32_t> indices;
-    uint32_t nTriangles() const { return (uint32_t)(indices.size() / 3); }
-    uint32_t poolIndex = 0; /* index into the engine's mesh list */
-};
-class Model3D {
-public:
-    std::string name;
-    std::vector<std::unique_ptr<Mesh>> meshes;
-    Mesh *mesh(const std::string &n) const {
-        for (auto &m : meshes)
-            if (m->name == n) return m.get();
-        return nullptr;
-    }
-};
-/* io_obj.cpp: OBJ import with the conventions of core/io/AssimpLoadModel.cpp (Triangulate | FlipUVs |
- * CalcTangentSpace followed by uv.y = 1 - uv.y) */
-bool loadOBJ(const std::string &path, Model3D &out, std::string *err);
-void computeTangents(Mesh &mesh);
-
 /* ------------------------------------------------------------------ math/Transform.cpp */
 class Transform {
 public:
@@ -284,6 +272,7 @@ public:
     vec3 &position() { return m_position; }
     const vec3 &position() const { return m_position; }
     vec3 &scale() { return m_scale; }
+    const vec3 &scale() const { return m_scale; }
     const quat &rotation() const { return m_rotation; }
     void setRotation(const quat &q) {
         m_rotation = q;
@@ -307,6 +296,128 @@ private:
     quat m_rotation;
     vec3 m_x, m_y, m_z;
 };
+
+/* ------------------------------------------------------------------ geometry */
+typedef ptc_vertex Vertex; /* core/Mesh.hpp:15-40 */
+class Model3D;
+class Mesh {
+public:
+    std::string name;
+    std::vector<Vertex> vertices;
+    std::vector<uint32_t> indices;
+    uint32_t nTriangles() const { return (uint32_t)(indices.size() / 3); }
+    uint32_t poolIndex = 0; /* index into the engine's mesh list */
+    Model3D *model = nullptr; /* Mesh::m_model */
+};
+class Model3D { /* core/Model3D.hpp */
+public:
+    struct Model3DNode {
+        std::string name;
+        std::vector<Mesh *> meshes;
+        std::vector<Material *> materials; /* per mesh; nullptr = none imported */
+        Transform transform;
+        std::vector<Model3DNode> children;
+    };
+    std::string name, filepath;
+    bool internal = false; /* engine-provided (AssetSource::ENGINE): not exported */
+    std::vector<std::unique_ptr<Mesh>> meshes;
+    Model3DNode nodeTree;
+    Mesh *mesh(const std::string &n) const {
+        for (auto &m : meshes)
+            if (m->name == n) return m.get();
+        return nullptr;
+    }
+};
+void computeTangents(Mesh &mesh);
+void computeNormals(Mesh &mesh); /* area-weighted vertex normals for files that carry none */
+
+/* ------------------------------------------------------------------ core/io/ImportTypes.hpp */
+enum class ImportedMaterialType { LAMBERT = 0, PBR_STANDARD = 1, EMBEDDED = 2, VOLUME = 3 };
+struct ImportedTexture {
+    std::string name;                /* texture asset name */
+    std::string filepath;            /* STANDALONE textures of a scene file */
+    bool embedded = true;            /* AssetLocation::DISK_EMBEDDED vs DISK_STANDALONE */
+    std::shared_ptr<ImageU8> image;  /* decoded texels (already flipped like every stbi load of the reference, trap T11) */
+    ColorSpace colorSpace = ColorSpace::sRGB;
+};
+struct ImportedMaterial {
+    AssetInfo info;
+    ImportedMaterialType type = ImportedMaterialType::PBR_STANDARD;
+    vec4 albedo{1, 1, 1, 1};
+    std::optional<ImportedTexture> albedoTexture;
+    float roughness = 0.5f;
+    std::optional<ImportedTexture> roughnessTexture;
+    float metallic = 0.5f;
+    std::optional<ImportedTexture> metallicTexture;
+    float ao = 1.0f;
+    std::optional<ImportedTexture> aoTexture;
+    vec3 emissiveColor{0, 0, 0};
+    std::optional<ImportedTexture> emissiveTexture;
+    float emissiveStrength = 1.0f;
+    std::optional<ImportedTexture> normalTexture;
+    std::optional<ImportedTexture> alphaTexture;
+    bool transparent = false;
+    vec2 scale{1, 1};
+    vec3 sigmaS{0.2f, 0.2f, 0.2f};
+    vec3 sigmaA{0, 0, 0};
+    float g = 0.0f;
+};
+struct ImportedModelNode {
+    std::string name;
+    std::vector<std::unique_ptr<Mesh>> meshes;
+    std::vector<int32_t> materialIndices; /* per mesh, -1 = none */
+    Transform transform;
+    std::vector<ImportedModelNode> children;
+};
+struct ImportedCamera {
+    vec3 position{0, 0, 0}, target{0, 0, -1}, up{0, 1, 0};
+    float znear = 0.01f, zfar = 200.0f, lensRadius = 0.0f, focalDistance = 10.0f, fov = 60.0f;
+    std::string volumeMaterial;
+};
+struct ImportedModel {
+    std::string name, filepath;
+};
+struct ImportedLight {
+    std::string name;
+    LightType type = LightType::POINT_LIGHT;
+    vec3 color{1, 1, 1};
+    float intensity = 1.0f;
+};
+struct ImportedEnvironment {
+    std::string path;
+    vec3 backgroundColor{0, 0, 0};
+    int environmentType = 0; /* EnvironmentType::SOLID_COLOR */
+};
+struct ImportedSceneObject {
+    std::string name;
+    bool active = true;
+    Transform transform;
+    bool hasMesh = false, hasMaterial = false, hasLight = false, hasVolume = false;
+    std::string modelName, submesh; /* mesh component */
+    std::string materialName;
+    std::string lightName;
+    bool lightShadows = true;
+    std::string volumeFront, volumeBack;
+    std::vector<ImportedSceneObject> children;
+};
+struct ImportedScene {
+    ImportedCamera camera;
+    std::vector<ImportedSceneObject> objects; /* roots */
+    std::vector<ImportedModel> models;
+    std::vector<ImportedMaterial> materials;
+    std::vector<ImportedLight> lights;
+    ImportedEnvironment environment;
+    bool hasEnvironment = false;
+    std::string sceneFolder; /* with trailing '/' */
+};
+/* io_obj.cpp / io_gltf.cpp: model import with the conventions of core/io/AssimpLoadModel.cpp (aiProcess_Triangulate |
+ * aiProcess_FlipUVs | aiProcess_CalcTangentSpace followed by uv.y = 1 - uv.y); materials == nullptr skips them */
+bool loadOBJ(const std::string &path, ImportedModelNode &root, std::vector<ImportedMaterial> *materials, std::string *err);
+bool loadGLTF(const std::string &path, ImportedModelNode &root, std::vector<ImportedMaterial> *materials, std::string *err);
+/* glm::decompose restricted to affine matrices without shear (AssimpLoadModel.cpp:154-160) */
+Transform decomposeTransform(const mat4 &m);
+/* io_scene.cpp: the scene file format of core/io/Import.cpp:504-565 / Export.cpp:628-784; throws std::runtime_error */
+void importSceneFile(const std::string &filename, ImportedScene &out);
 
 /* ------------------------------------------------------------------ core/Camera.cpp */
 enum class CameraType { PERSPECTIVE = 0, ORTHOGRAPHIC = 1 };
@@ -464,6 +575,7 @@ public:
     void setActive(bool a) { m_active = a; }
     void setLocalTransform(const Transform &t) { m_localTransform = t; }
     Transform &localTransform() { return m_localTransform; }
+    const Transform &localTransform() const { return m_localTransform; }
     SceneObject *parent() const { return m_parent; }
     const std::vector<SceneObject *> &children() const { return m_children; }
     SceneObject *addChild(SceneObject *c) {
@@ -537,6 +649,7 @@ public:
     void clear();
     void update(); /* Scene.cpp:105-145 */
     SceneObjectVector getSceneObjectsFlat() const;
+    const SceneObjectVector &sceneGraph() const { return m_sceneGraph; }
     Light *createLight(const AssetInfo &info, LightType type, vec4 color = vec4(1, 1, 1, 1));
     InstancesManager &instancesManager() { return m_instances; }
     ptc_scene_data getSceneData() const; /* Scene.cpp:31-44 + VulkanScene.cpp:85-92 */
@@ -556,6 +669,10 @@ private:
     std::vector<std::unique_ptr<Light>> m_lights;
     InstancesManager m_instances;
 };
+
+/* core/SceneUtils.cpp:76-130: instantiates an imported model's node tree under `parent` (root transform and material can be overridden) */
+void addModel3D(Scene &scene, SceneObject *parent, const std::string &modelName, std::optional<Transform> overrideRootTransform = std::nullopt,
+                std::optional<std::string> overrideMaterial = std::nullopt);
 
 /* ------------------------------------------------------------------ core/Renderer.hpp:11-39 */
 class RendererPathTracing {
@@ -652,6 +769,11 @@ public:
     Model3D *importModel(const AssetInfo &info, bool importMaterials = true); /* VulkanEngine.cpp:157-192 */
     EnvironmentMap *importEnvironmentMap(const AssetInfo &info);              /* VulkanEngine.cpp:194-232 */
     Model3D *addModel(std::unique_ptr<Model3D> model);                       /* procedural meshes */
+    /* the vviewer "Import scene" action (src/bin/vviewer/UI/MainWindow.cpp:580-680) without the UI: parse the scene file, import its
+     * models / materials / lights, rebuild the scene graph, camera and environment.  false + message on failure */
+    bool importScene(const std::string &filename, std::string *err = nullptr);
+    /* Scene::exportScene (core/Scene.cpp:174, core/io/Export.cpp:628-784): writes <name>/scene.json + <name>/assets/ */
+    bool exportScene(const std::string &name, std::string *err = nullptr);
     std::string assetPath(const std::string &rel) const;
     const std::vector<Mesh *> &meshPool() const { return m_meshPool; }
     /* flatten the current scene (after Scene::update) into the POD arrays of include/ptc.h */
