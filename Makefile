@@ -46,7 +46,15 @@ $(ORCDIR)/liboracle.so: oracle/oracle.cpp oracle/omath.hpp oracle/bsdf.hpp oracl
 	@mkdir -p $(ORCDIR)
 	$(CXX) -O3 -std=c++17 -fPIC -fvisibility=hidden -ffp-contract=off -fopenmp -Wall -Iinclude -shared -o $@ oracle/oracle.cpp
 
-clean:
-	rm -rf $(LIBDIR) $(ORCDIR)
+# oracle/_ref: the only part of the reference that compiles here is its vendored image decoder (stb_image.h); it is built
+# from the sources where they lie under /root/reference (nothing is copied) and used by tests/golden/make_image_fixtures.py
+REFSTB := /root/reference/src/lib/external/stb
+oracle-ref:
+	@if [ -f $(REFSTB)/stb_image.h ]; then mkdir -p oracle/_ref && \
+	  gcc -O2 -w -I$(REFSTB) -o oracle/_ref/stb_decode oracle/ref_tools/stb_decode.c -lm && echo built oracle/_ref/stb_decode; \
+	else echo "/root/reference absent: oracle/_ref not rebuilt"; fi
 
-.PHONY: all oracle stats clean
+clean:
+	rm -rf $(LIBDIR) $(ORCDIR) oracle/_ref
+
+.PHONY: all oracle oracle-ref stats clean

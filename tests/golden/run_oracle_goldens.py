@@ -5,8 +5,8 @@ and writes tests/golden/oracle_vs_reference.json (committed).  Run here on CPU:
     python tests/golden/run_oracle_goldens.py [--spp-scale 1.0] [names...]
 
 Metrics: RGB MSE after the same RGBE quantisation the goldens went through, mean-luminance ratio,
-99th percentile relative error after a 3x3 box filter.  GLTF_ref needs the glTF importer (not
-built yet) and Denoise_ref needs OIDN (out of scope); Denoise_ref_{radiance,albedo,normal} are checked instead."""
+99th percentile relative error after a 3x3 box filter.  GLTF_ref goes through the from-scratch glTF importer
+(vviewer_b200/host/io_gltf.cpp); Denoise_ref needs OIDN (out of scope): Denoise_ref_{radiance,albedo,normal} are checked instead."""
 import json
 import os
 import sys
@@ -23,7 +23,7 @@ from vviewer_b200 import capi  # noqa: E402
 
 SCENES = ["FurnacePBR", "FurnaceLambert", "EnvironmentMap", "EnvironmentMapPBR00", "EnvironmentMapPBR01", "EnvironmentMapPBR10",
           "EnvironmentMapPBR11", "EnvironmentMapLambert", "Volume0", "Volume1", "Volume2", "Volume3", "Volume4", "Volume5", "Volume6",
-          "Volume7", "Volume8", "Volume9", "PointLight", "DirectionalLight", "MeshLight", "Transparency", "NormalMap", "Hierarchy",
+          "Volume7", "Volume8", "Volume9", "PointLight", "DirectionalLight", "MeshLight", "Transparency", "NormalMap", "GLTF", "Hierarchy",
           "DepthOfField", "SharedComponents", "Denoise"]
 
 

@@ -1,0 +1,408 @@
+"""Model / texture / scene import without assimp or stb, CPU only.
+
+* image decoders against the REFERENCE decoder's outputs (tests/golden/stb_decode_fixtures.json, made by
+  tests/golden/make_image_fixtures.py with oracle/_ref/stb_decode = the reference's vendored stb_image.h);
+* glTF 2.0 / GLB (AssimpLoadModel.cpp:381-470, 543-563), OBJ + MTL (:303-350), addModel3D (SceneUtils.cpp:76-130);
+* scene.json import / export (core/io/Import.cpp:504-565, Export.cpp:628-784)."""
+import base64
+import hashlib
+import json
+import math
+import os
+import shutil
+import struct
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIXTURES = json.load(open(os.path.join(ROOT, "tests", "golden", "stb_decode_fixtures.json")))
+HELMET = os.path.join(ROOT, "assets", "models", "DamagedHelmet.gltf")
+
+
+@pytest.fixture()
+def engine(capi):
+    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    yield eng
+    eng.close()
+
+
+def helmet_images():
+    g = json.load(open(HELMET))
+    return [base64.b64decode(im["uri"][im["uri"].index(",") + 1:]) for im in g["images"]]
+
+
+def check_against_stb(img, file_channels, key):
+    fx = FIXTURES[key]
+    assert (img.shape[1], img.shape[0], file_channels) == (fx["w"], fx["h"], fx["file_channels"])
+    if img.shape[2] == 1:  # the reference keeps grey images single channel (core/Image.cpp:17-19); the fixture is RGBA
+        rgba = np.concatenate([np.repeat(img, 3, axis=2), np.full_like(img, 255)], axis=2)
+    else:
+        rgba = img
+    for y, x, *texel in fx["probes"]:
+        assert list(rgba[y, x]) == texel, (key, y, x)
+    assert hashlib.sha256(np.ascontiguousarray(rgba).tobytes()).hexdigest() == fx["sha256"], key
+
+
+# ---------------------------------------------------------------- decoders: bit-exact against stb_image
+@pytest.mark.parametrize("name", ["checkerboard", "normal", "circular_gradient"])
+@pytest.mark.parametrize("flip", [False, True])
+def test_png_decoder_matches_stb(capi, name, flip):
+    data = open(os.path.join(ROOT, "assets", "textures", name + ".png"), "rb").read()
+    img, c = capi.decode_image(data, flip)
+    check_against_stb(img, c, "assets/textures/%s.png%s" % (name, "|flip" if flip else ""))
+
+
+@pytest.mark.parametrize("index", range(5))
+def test_jpeg_decoder_matches_stb(capi, index):
+    """baseline Huffman JPEG, 4:2:0 / 4:4:4 with stb's fixed-point IDCT, h2v2 fancy upsampling and YCbCr constants"""
+    data = helmet_images()[index]
+    img, c = capi.decode_image(data, True)
+    check_against_stb(img, c, "DamagedHelmet.gltf#image%d|flip" % index)
+    if index == 0:
+        img, c = capi.decode_image(data, False)
+        check_against_stb(img, c, "DamagedHelmet.gltf#image0")
+
+
+def test_hdr_decoder_matches_stb(capi):
+    img = capi.read_hdr(os.path.join(ROOT, "assets", "HDR", "harbor.hdr"))
+    fx = FIXTURES["assets/HDR/harbor.hdr"]
+    assert img.shape == (fx["h"], fx["w"], 4)
+    assert hashlib.sha256(img.tobytes()).hexdigest() == fx["sha256"]
+    # the reference loads it flipped (core/Image.cpp:39): same rows in reverse order
+    assert hashlib.sha256(np.ascontiguousarray(img[::-1]).tobytes()).hexdigest() == FIXTURES["assets/HDR/harbor.hdr|flip"]["sha256"]
+
+
+def test_decoder_rejects_garbage(capi):
+    for data in (b"", b"not an image", b"\x89PNG\r\n\x1a\n" + b"\0" * 40, b"\xff\xd8\xff\xe0" + b"\0" * 64, helmet_images()[2][:5000]):
+        with pytest.raises(RuntimeError):
+            capi.decode_image(data or b"\0", False)
+
+
+# ---------------------------------------------------------------- glTF
+def test_gltf_import_helmet(capi, engine):
+    engine.import_model("assets/models/DamagedHelmet.gltf", True)
+    d = engine.describe()
+    model = [m for m in d["models"] if m["name"].endswith("DamagedHelmet.gltf")][0]
+    g = json.load(open(HELMET))
+    acc = g["accessors"]
+    prim = g["meshes"][0]["primitives"][0]
+    mesh = model["meshes"][0]
+    assert mesh["vertices"] == acc[prim["attributes"]["POSITION"]]["count"] == 14556
+    assert mesh["triangles"] == acc[prim["indices"]]["count"] // 3 == 15452
+    lo, hi = acc[prim["attributes"]["POSITION"]]["min"], acc[prim["attributes"]["POSITION"]]["max"]
+    assert np.allclose(mesh["bounds"], lo + hi, atol=1e-6)
+    # assimp's glTF importer hands over v' = 1 - v and the engine applies aiProcess_FlipUVs and then 1 - v (trap T11):
+    # net v = -v_gltf... the loader keeps whatever reproduces the golden; here: range and orientation are pinned
+    assert -1.0 <= mesh["uvBounds"][1] <= mesh["uvBounds"][3] <= 0.0 and 0.0 <= mesh["uvBounds"][0] <= mesh["uvBounds"][2] <= 1.0
+    # generated tangent frames are orthonormal (aiProcess_CalcTangentSpace semantics)
+    assert mesh["meanAbsTangentDotNormal"] < 1e-4 and abs(mesh["meanTangentLength"] - 1) < 1e-4 and abs(mesh["meanNormalLength"] - 1) < 1e-4
+    # node transform: rotation quaternion of the glTF node (x, y, z, w) = (0.7071, 0, 0, 0.7071)
+    node = g["nodes"][g["scenes"][0]["nodes"][0]]
+    tr = model["nodeTree"]["transform"]
+    q = node.get("rotation", [0, 0, 0, 1])
+    assert np.allclose(tr[6:10], [q[3], q[0], q[1], q[2]], atol=1e-6) and np.allclose(tr[0:3], 0) and np.allclose(tr[3:6], 1, atol=1e-6)
+
+    mat = [m for m in d["materials"] if m["name"] == "DamagedHelmet:Material_MR"][0]
+    assert mat["embedded"] and mat["type"] == 0 and mat["emissiveFlag"] and not mat["transparentFlag"]
+    assert mat["albedo"] == [1, 1, 1, 1] and mat["metallicRoughnessAO"][:3] == [1, 1, 1]
+    tex = {t["name"]: t for t in d["textures"]}
+    names = mat["textures"]
+    for slot, srgb, ch in (("albedo", True, 4), ("emissive", True, 4), ("normal", False, 4), ("metallic", False, 1), ("roughness", False, 1), ("ao", False, 1)):
+        t = tex[names[slot]]
+        assert (t["width"], t["height"], t["channels"], t["srgb"], t["embedded"]) == (2048, 2048, ch, srgb, True), slot
+
+
+def test_gltf_metallic_roughness_channel_split(capi, engine):
+    """AssimpLoadModel.cpp:436-457: the glTF metallicRoughness image is split, G -> roughness, B -> metallic; AO uses R."""
+    engine.import_model("assets/models/DamagedHelmet.gltf", True)
+    desc = engine.scene_desc().contents
+    d = engine.describe()
+    order = [t["name"] for t in d["textures"]]
+    mr, _ = capi.decode_image(helmet_images()[1], True)
+    occ, _ = capi.decode_image(helmet_images()[3], True)
+
+    def texels(name):
+        t = desc.textures[order.index(name)]
+        n = t.width * t.height * t.channels
+        return np.ctypeslib.as_array(t.data, shape=(n,)).reshape(t.height, t.width, t.channels)
+
+    assert np.array_equal(texels("DamagedHelmet:Material_MR:roughness")[..., 0], mr[..., 1])
+    assert np.array_equal(texels("DamagedHelmet:Material_MR:metallic")[..., 0], mr[..., 2])
+    assert np.array_equal(texels("DamagedHelmet:Material_MR:ao")[..., 0], occ[..., 0])
+
+
+def make_glb(gltf_path, out_path):
+    g = json.load(open(gltf_path))
+    blob = bytearray()
+    views = g["bufferViews"]
+    # move the buffer and the images into one BIN chunk
+    buf = base64.b64decode(g["buffers"][0]["uri"].split(",", 1)[1])
+    blob += buf
+    for im in g["images"]:
+        data = base64.b64decode(im.pop("uri").split(",", 1)[1])
+        while len(blob) % 4:
+            blob.append(0)
+        views.append({"buffer": 0, "byteOffset": len(blob), "byteLength": len(data)})
+        im["bufferView"] = len(views) - 1
+        im["mimeType"] = "image/jpeg"
+        blob += data
+    while len(blob) % 4:
+        blob.append(0)
+    g["buffers"] = [{"byteLength": len(blob)}]
+    js = json.dumps(g, separators=(",", ":")).encode()
+    js += b" " * (-len(js) % 4)
+    total = 12 + 8 + len(js) + 8 + len(blob)
+    with open(out_path, "wb") as f:
+        f.write(struct.pack("<III", 0x46546C67, 2, total))
+        f.write(struct.pack("<II", len(js), 0x4E4F534A) + js)
+        f.write(struct.pack("<II", len(blob), 0x004E4942) + bytes(blob))
+
+
+def test_glb_equals_gltf(capi, engine, tmp_path):
+    """binary container (GLB: JSON + BIN chunks, images through bufferViews) gives the same meshes and textures"""
+    engine.import_model("assets/models/DamagedHelmet.gltf", True)
+    a = engine.describe()
+    glb = str(tmp_path / "DamagedHelmet.glb")
+    make_glb(HELMET, glb)
+    engine.import_model(glb, True)
+    b = engine.describe()
+    ma = [m for m in a["models"] if m["name"].endswith(".gltf")][0]["meshes"][0]
+    mb = [m for m in b["models"] if m["name"].endswith(".glb")][0]["meshes"][0]
+    for k in ("vertices", "triangles", "bounds", "uvBounds", "indexHash", "vertexHash"):
+        assert ma[k] == mb[k], k
+    ha = sorted(t["hash"] for t in a["textures"] if t["embedded"])
+    hb = sorted(t["hash"] for t in b["textures"] if t["embedded"] and t["name"] not in {x["name"] for x in a["textures"]})
+    assert len(ha) == 6 and (hb == ha or hb == [])  # same texels (or the textures were shared by name)
+
+
+def test_gltf_errors(capi, engine, tmp_path):
+    with pytest.raises(RuntimeError):
+        engine.import_model("assets/models/nothing.gltf", True)
+    bad = tmp_path / "bad.gltf"
+    bad.write_text("{ \"asset\": {\"version\": \"2.0\"}, \"meshes\": [ {\"primitives\": [ {\"attributes\": {\"POSITION\": 7}} ] } ] ")
+    with pytest.raises(RuntimeError):
+        engine.import_model(str(bad), True)
+    bad.write_text(json.dumps({"asset": {"version": "2.0"}, "scenes": [{"nodes": [0]}], "nodes": [{"mesh": 0}],
+                               "meshes": [{"primitives": [{"attributes": {"POSITION": 7}}]}]}))
+    with pytest.raises(RuntimeError):
+        engine.import_model(str(bad), True)
+    assert "bad.gltf" in engine.last_error() or engine.last_error()
+
+
+# ---------------------------------------------------------------- OBJ + MTL
+OBJ = """mtllib quad.mtl
+o Quad
+v -1 0 -1
+v 1 0 -1
+v 1 0 1
+v -1 0 1
+vt 0 0
+vt 1 0
+vt 1 1
+vt 0 1
+vn 0 1 0
+usemtl shiny
+f 1/1/1 4/4/1 3/3/1 2/2/1
+o Tri
+usemtl glow
+f 1/1/1 3/3/1 2/2/1
+"""
+MTL = """newmtl shiny
+Kd 0.8 0.2 0.1
+Ks 0.5 0.5 0.5
+Ns 96
+d 1.0
+map_Kd checker.png
+newmtl glow
+Kd 0.1 0.1 0.1
+Ke 2.0 1.0 0.5
+d 0.5
+"""
+
+
+def test_obj_mtl_import(capi, engine, tmp_path):
+    (tmp_path / "quad.obj").write_text(OBJ)
+    (tmp_path / "quad.mtl").write_text(MTL)
+    shutil.copy(os.path.join(ROOT, "assets", "textures", "checkerboard.png"), tmp_path / "checker.png")
+    path = str(tmp_path / "quad.obj")
+    engine.import_model(path, True)
+    d = engine.describe()
+    model = [m for m in d["models"] if m["name"] == path][0]
+    meshes = {m["name"]: m for m in model["meshes"]}
+    assert len(meshes) == 2
+    quad = [m for m in model["meshes"] if m["triangles"] == 2][0]  # polygon fan-triangulated
+    tri = [m for m in model["meshes"] if m["triangles"] == 1][0]
+    assert quad["vertices"] == 4 and tri["vertices"] == 3
+    assert np.allclose(quad["bounds"], [-1, 0, -1, 1, 0, 1])
+    mats = {m["name"]: m for m in d["materials"]}
+    shiny = [m for n, m in mats.items() if "shiny" in n][0]
+    glow = [m for n, m in mats.items() if "glow" in n][0]
+    assert np.allclose(shiny["albedo"][:3], [0.8, 0.2, 0.1], atol=1e-6)
+    tex = {t["name"]: t for t in d["textures"]}
+    assert tex[shiny["textures"]["albedo"]]["width"] == 1080 and tex[shiny["textures"]["albedo"]]["srgb"]
+    # pseudo-PBR from the .mtl (AssimpLoadModel.cpp:319-334): metallic = 1 - d / (d + s), roughness = 1 - Ns / 100
+    assert shiny["metallicRoughnessAO"][0] == pytest.approx(1 - 0.8 / (0.8 + 0.5), abs=1e-6)
+    assert shiny["metallicRoughnessAO"][1] == pytest.approx(1 - 96 / 100, abs=1e-6)
+    assert shiny["type"] == 0 and glow["type"] == 0  # always PBR_STANDARD (:273)
+    assert not glow["emissiveFlag"]  # the reference's OBJ path never reads Ke
+    assert glow["metallicRoughnessAO"][0] == pytest.approx(0.0, abs=1e-6)  # no Ks: 1 - d / (d + 0)
+    # materials not imported: sub-meshes get no material name
+    engine2 = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    engine2.import_model(path, False)
+    m2 = [m for m in engine2.describe()["models"] if m["name"] == path][0]
+    assert all(ms["material"] == "" for ms in m2["nodeTree"]["children"][0]["meshes"])
+    engine2.close()
+
+
+def test_add_model_builds_node_tree(capi, engine):
+    """addModel3D: one scene object per model node, mesh + material components from the sub-meshes"""
+    engine.build_scene("FurnaceLambert")
+    before = engine.scene_desc().contents.n_instances
+    engine.import_model("assets/models/arrow.obj", False)
+    engine.add_model("assets/models/arrow.obj")
+    desc = engine.scene_desc().contents
+    d = engine.describe()
+    arrow = [m for m in d["models"] if m["name"].endswith("arrow.obj")][0]
+    n_meshes = len(arrow["meshes"])
+    assert n_meshes >= 1 and desc.n_instances == before + n_meshes
+    with pytest.raises(RuntimeError):
+        engine.add_model("assets/models/not_imported.obj")
+
+
+# ---------------------------------------------------------------- scene.json
+def flattened(engine):
+    """instances (model matrix, triangle count, volume ids), their materials, and the light instances, in a canonical order"""
+    d = engine.scene_desc().contents
+    rows = []
+    for i in range(d.n_instances):
+        it = d.instances[i]
+        m = d.materials[it.material_index]
+        rows.append(np.concatenate([np.array(it.model, np.float64), [it.num_triangles], [float(it.id[1] >= 0), float(it.id[2] >= 0)],
+                                    list(m.albedo), list(m.metallic_roughness_ao), list(m.emissive), list(m.uv_tiling)[:3]]))
+    rows.sort(key=lambda r: (r[16], round(r[12], 1), round(r[13], 1), round(r[14], 1)))
+    lights = [np.concatenate([list(d.light_instances[i].position), [d.light_instances[i].info[3]]]) for i in range(d.n_light_instances)]
+    lights.sort(key=lambda r: (r[4], round(r[0], 1), round(r[1], 1), round(r[2], 1)))
+    return np.array(rows), np.array(lights)
+
+
+@pytest.mark.parametrize("scene", ["Hierarchy", "Volume6", "MeshLight", "NormalMap", "PointLight", "SharedComponents"])
+def test_scene_export_import_roundtrip(capi, engine, scene, tmp_path):
+    engine.build_scene(scene)
+    engine.set_render_info(width=48, height=48, samples=4, batch_size=4)
+    a = flattened(engine)
+    rp_a = engine.render_params()
+    img_a = engine.render_to_memory()[0]
+    engine.export_scene(str(tmp_path))
+    doc = json.load(open(tmp_path / "scene.json"))
+    for key in ("version", "camera", "scene", "models", "materials", "lights", "environment"):
+        assert key in doc, key
+    other = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    other.import_scene(str(tmp_path / "scene.json"))
+    other.set_render_info(width=48, height=48, samples=4, batch_size=4, depth=engine.render_info()["depth"])
+    b = flattened(other)
+    # rotations travel as Euler angles in degrees (Export.cpp / Import.cpp:190-203): single-precision eulerAngles() loses
+    # digits next to the 90 degree pitch singularity the Hierarchy recipe sits on, hence 2e-3 on matrix entries
+    assert a[0].shape == b[0].shape and np.allclose(a[0], b[0], atol=2e-3), "instances / materials differ"
+    assert a[1].shape == b[1].shape and np.allclose(a[1], b[1], atol=2e-3), "lights differ"
+    rp_b = other.render_params()
+    assert np.allclose(list(rp_a.scene.view), list(rp_b.scene.view), atol=1e-5)
+    assert np.allclose(list(rp_a.scene.projection), list(rp_b.scene.projection), atol=1e-5)
+    assert np.allclose(list(rp_a.scene.background), list(rp_b.scene.background)) and np.allclose(list(rp_a.scene.volumes), list(rp_b.scene.volumes))
+    img_b = other.render_to_memory()[0]
+    if rp_a.scene.exposure[1] != 1.0:
+        # the reference's file format has no field for the environment intensity (Export.cpp:756-777, Import.cpp:489-503):
+        # it comes back as the default 1 and the image legitimately differs
+        assert rp_b.scene.exposure[1] == 1.0
+        other.close()
+        return
+    # instance / material order may differ, so light picks can: compare statistically tight, not bitwise
+    assert abs(img_a[..., :3].mean() - img_b[..., :3].mean()) <= 0.05 * max(img_a[..., :3].mean(), 1e-3)
+    other.close()
+
+
+def test_scene_import_reference_format(capi, engine, tmp_path):
+    """a hand-written scene.json in the reference's dialect: vectors as objects or arrays, rotation as Euler degrees or
+    quaternion, camera by rotation, children, lights, volume components (Import.cpp:50-337, 469-503)"""
+    os.makedirs(tmp_path / "assets" / "models")
+    shutil.copy(os.path.join(ROOT, "assets", "models", "cube.obj"), tmp_path / "assets" / "models" / "cube.obj")
+    s = math.sin(math.radians(45) / 2)
+    doc = {
+        "version": "1.0", "name": "handwritten",
+        "camera": {"position": {"x": 0, "y": 1, "z": 6}, "rotation": [0, 0, 0], "fov": 45, "znear": 0.1, "zfar": 80, "lensRadius": 0.02,
+                   "focalDistance": 6},
+        "scene": [
+            {"name": "parent", "transform": {"position": [1, 0, 0], "scale": [2], "rotation": [0, 45, 0]},
+             "children": [
+                 {"name": "box", "transform": {"position": {"x": 0, "y": 0.5, "z": 0}, "scale": {"x": 0.5, "y": 0.5, "z": 0.5},
+                                               "rotation": [0, s, 0, math.cos(math.radians(45) / 2)]},  # 4-element array = quaternion (x, y, z, w), Import.cpp:196-202
+                  "mesh": {"modelName": "cube", "submesh": "Cube"}, "material": {"name": "red"},
+                  "volume": {"frontFacing": "fog", "backFacing": ""}},
+                 {"name": "hidden", "active": False, "mesh": {"modelName": "cube", "submesh": "Cube"}, "material": {"name": "red"}}]},
+            {"name": "lamp", "transform": {"position": [0, 4, 0]}, "light": {"name": "bulb", "shadows": False}},
+            {"name": "sun", "transform": {"rotation": [-60, 0, 0]}, "light": {"name": "sunlight"}}],
+        "models": [{"name": "cube", "filepath": "assets/models/cube.obj"}],
+        "materials": [
+            {"name": "red", "type": "LAMBERT", "albedo": {"value": [0.9, 0.1, 0.1, 1.0]}, "emissive": {"value": [0, 0, 0, 1]}, "ao": {"value": 1.0},
+             "normal": {}, "alpha": {}, "transparent": False, "scale": [2, 3]},
+            {"name": "fog", "type": "VOLUME", "scattering": {"value": [0.2, 0.2, 0.2]}, "absorption": {"value": {"r": 0.01, "g": 0.02, "b": 0.03}}, "g": 0.4}],
+        "lights": [{"name": "bulb", "type": "POINT", "color": [1, 0.5, 0.25], "intensity": 7.0},
+                   {"name": "sunlight", "type": "DIRECTIONAL", "color": {"r": 1, "g": 1, "b": 1}, "intensity": 2.0}],
+        "environment": {"environmentType": 0, "backgroundColor": [0.1, 0.2, 0.3]}}
+    (tmp_path / "scene.json").write_text(json.dumps(doc))
+    engine.import_scene(str(tmp_path / "scene.json"))
+    d = engine.scene_desc().contents
+    rp = engine.render_params()
+    assert d.n_instances == 1 and d.n_light_instances == 2  # the inactive object is skipped
+    inst = d.instances[0]
+    model = np.array(inst.model, np.float32).reshape(4, 4).T
+
+    def rot_y(deg):
+        c, s_ = math.cos(math.radians(deg)), math.sin(math.radians(deg))
+        return np.array([[c, 0, s_, 0], [0, 1, 0, 0], [-s_, 0, c, 0], [0, 0, 0, 1]])
+
+    def trs(t, sc, r):
+        m = np.eye(4)
+        m[:3, 3] = t
+        return m @ r @ np.diag([sc, sc, sc, 1])
+
+    expect = trs([1, 0, 0], 2, rot_y(45)) @ trs([0, 0.5, 0], 0.5, rot_y(45))
+    assert np.allclose(model, expect, atol=1e-5)
+    mat = d.materials[inst.material_index]
+    assert tuple(mat.albedo) == pytest.approx((0.9, 0.1, 0.1, 1.0)) and mat.uv_tiling[2] == 2.0  # MaterialType::MATERIAL_LAMBERT
+    assert tuple(mat.uv_tiling)[:2] == pytest.approx((2.0, 3.0))
+    fog = d.materials[int(inst.id[1])]
+    assert tuple(fog.albedo)[:3] == pytest.approx((0.01, 0.02, 0.03)) and tuple(fog.metallic_roughness_ao)[:3] == pytest.approx((0.2, 0.2, 0.2))
+    assert fog.emissive[0] == pytest.approx(0.4) and inst.id[2] == -1
+    kinds = sorted(d.light_instances[i].info[3] for i in range(2))
+    assert kinds == [0, 1]
+    for i in range(2):
+        li = d.light_instances[i]
+        ld = d.light_data[li.info[0]]
+        if li.info[3] == 0:
+            assert tuple(li.position)[:3] == pytest.approx((0, 4, 0)) and li.position[3] == 0.0  # shadows off
+            assert tuple(ld.color) == pytest.approx((1, 0.5, 0.25, 7.0))
+        else:
+            # direction = modelMatrix * (0,0,1,0) with rotation -60 deg about x
+            assert np.allclose(list(li.position)[:3], [0, math.sin(math.radians(60)), math.cos(math.radians(60))], atol=1e-5)
+    vinv = np.array(rp.scene.view_inverse, np.float32).reshape(4, 4).T
+    assert np.allclose(vinv[:3, 3], [0, 1, 6]) and np.allclose(vinv[:3, 2], [0, 0, 1], atol=1e-6)
+    assert tuple(rp.scene.background) == pytest.approx((0.1, 0.2, 0.3, 0.0))
+    assert rp.scene.exposure[2] == pytest.approx(0.02) and rp.scene.exposure[3] == pytest.approx(6.0)
+    assert rp.scene.volumes[1] == pytest.approx(0.1) and rp.scene.volumes[2] == pytest.approx(80.0)
+
+
+def test_scene_import_errors(capi, engine, tmp_path):
+    with pytest.raises(RuntimeError):
+        engine.import_scene(str(tmp_path / "missing.json"))
+    p = tmp_path / "scene.json"
+    p.write_text("{ \"camera\": { \"position\": [0,0,0] ")
+    with pytest.raises(RuntimeError):
+        engine.import_scene(str(p))
+    p.write_text(json.dumps({"camera": {"position": [0, 0, 0]}, "scene": [], "models": [], "materials": [], "lights": []}))
+    with pytest.raises(RuntimeError):  # camera without target or rotation (Import.cpp:226-228)
+        engine.import_scene(str(p))
+    p.write_text(json.dumps({"camera": {"position": [0, 0, 0], "target": [0, 0, -1], "up": [0, 1, 0]}, "scene": [], "models": [],
+                             "materials": [{"name": "m", "type": "GLASS"}], "lights": []}))
+    with pytest.raises(RuntimeError):  # unknown material type (Import.cpp:398-401)
+        engine.import_scene(str(p))

@@ -102,7 +102,8 @@ PTC_SYMBOLS = ["ptc_create", "ptc_destroy", "ptc_last_error", "ptc_backend_name"
                "ptc_bsdf_sample", "ptc_sampler_points", "ptc_env_lookup"]
 VH_SYMBOLS = ["vh_engine_create", "vh_engine_destroy", "vh_backend_ok", "vh_last_error", "vh_scene_list", "vh_build_scene",
               "vh_set_render_info", "vh_get_render_info", "vh_scene_desc", "vh_render_params", "vh_render_to_memory", "vh_render",
-              "vh_get_stats", "vh_read_hdr", "vh_write_hdr"]
+              "vh_get_stats", "vh_read_hdr", "vh_write_hdr", "vh_import_model", "vh_add_model", "vh_import_scene", "vh_export_scene",
+              "vh_describe", "vh_decode_image"]
 
 _fp = C.POINTER(f32)
 _ip = C.POINTER(C.c_int)

@@ -76,6 +76,7 @@ struct BitReader {
     uint64_t acc = 0;
     int bits = 0;
     int marker = -1; /* marker byte seen in the stream (p stays on its FF) */
+    int starved = 0; /* zero bytes fed after the END of the data (not after a marker): a truncated file */
 
     void fill() {
         while (bits <= 56) {
@@ -85,6 +86,7 @@ struct BitReader {
                     byte = *p++;
                 } else if (p + 1 >= end) {
                     p = end;
+                    ++starved;
                 } else if (p[1] == 0x00) { /* stuffed data byte FF */
                     byte = 0xFF;
                     p += 2;
@@ -94,6 +96,8 @@ struct BitReader {
                 } else {
                     marker = p[1];
                 }
+            } else if (marker < 0) {
+                ++starved;
             }
             acc |= (uint64_t)byte << (56 - bits);
             bits += 8;
@@ -498,7 +502,7 @@ struct Decoder {
             int w = (c.x + 7) >> 3, h = (c.y + 7) >> 3;
             for (int by = 0; by < h; by++)
                 for (int bx = 0; bx < w; bx++) {
-                    if (!decodeUnit(c, bx, by)) return false;
+                    if (!decodeUnit(c, bx, by) || br.starved > 16) return false;
                     if (--todo <= 0) {
                         if (!consumeRestart()) return true;
                         todo = restartInterval;
@@ -515,6 +519,7 @@ struct Decoder {
                         for (int h = 0; h < c.h; h++)
                             if (!decodeUnit(c, mx * c.h + h, my * c.v + v)) return false;
                 }
+                if (br.starved > 16) return false; /* ran off the end of the file inside the entropy-coded data */
                 if (--todo <= 0) {
                     if (!consumeRestart()) return true;
                     todo = restartInterval;

@@ -234,7 +234,11 @@ SceneObjectVector Scene::getSceneObjectsFlat() const {
     return v;
 }
 
+/* VulkanScene.cpp:115-142: lights live in the asset manager's lights map; an existing name returns the existing light */
 Light *Scene::createLight(const AssetInfo &info, LightType type, vec4 color) {
+    if (type != LightType::POINT_LIGHT && type != LightType::DIRECTIONAL_LIGHT) return nullptr;
+    AssetMap<Light> &lights = m_engine.lightsMap();
+    if (lights.has(info.name)) return lights.get(info.name);
     ptc_light_data ld{};
     ld.color[0] = color.x; ld.color[1] = color.y; ld.color[2] = color.z; ld.color[3] = color.w;
     ld.type[0] = (uint32_t)type;
@@ -242,7 +246,7 @@ Light *Scene::createLight(const AssetInfo &info, LightType type, vec4 color) {
     m_lightData.reserve(1024); /* Light holds a reference into the table */
     m_lightData.push_back(ld);
     m_lights.push_back(std::make_unique<Light>(info, type, m_lightData, (LightIndex)(m_lightData.size() - 1)));
-    return m_lights.back().get();
+    return lights.add(info.name, m_lights.back().get());
 }
 
 ptc_scene_data Scene::getSceneData() const {
