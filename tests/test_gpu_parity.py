@@ -231,7 +231,8 @@ def test_render_matches_oracle(capi, engine, scene, sobol):
     limit = 0.02 if scene in ("NormalMap", "Transparency", "GLTF") else 0.01
     assert np.mean(d > 1e-3 * np.maximum(1.0, rb[..., :3].max(axis=-1))) < limit, "radiance differs in %.3f %% of pixels" % (100 * np.mean(d > 1e-3))
     assert abs(ra[..., :3].mean() / max(rb[..., :3].mean(), 1e-9) - 1) < 2e-3
-    assert np.mean(np.abs(aa - ab).max(axis=-1) > 1e-3) < 0.01 and np.mean(np.abs(na - nb).max(axis=-1) > 1e-3) < 0.01
+    assert np.mean(np.abs(aa - ab).max(axis=-1) > 1e-3) < limit and np.mean(np.abs(na - nb).max(axis=-1) > 1e-3) < 0.01
+    assert np.abs(aa - ab).max() < 2e-2  # filter-weight rounding only: never a different texel
     assert np.all(ra[..., 3] == 1.0)
     assert abs(sa["segments"] - sb["segments"]) <= 1e-3 * sb["segments"]
     assert abs(sa["probe_rays"] - sb["probe_rays"]) <= 1e-3 * max(sb["probe_rays"], 1000)
@@ -290,6 +291,38 @@ def test_samples_dropped_and_alpha(capi):
     assert cu.stats()["segments"] == 2 * 16 * 16 * 64  # trap T7
     assert np.allclose(rad[..., :3], 0.5, atol=2e-6) and np.all(rad[..., 3] == 1.0)
     assert np.allclose(alb[..., :3], 0.5, atol=1e-6)
+    cu.close()
+
+
+def test_texture_identity_cache(capi):
+    """ptc_texture.uid: content with a non-zero uid is immutable by contract and keeps its device copy across uploads
+    (the reference uploads textures once, at import); uid 0 or a new uid uploads again."""
+    d, keep = make_quad_scene(capi)
+    T, tex_data = keep[5], keep[6]
+    albedo = tex_data[1]  # sRGB albedo texture of the quad's material (tex1[0] = 1)
+    albedo[0], albedo[1], albedo[2] = 255, 255, 254  # not the all-white fast path
+    for i in range(3):
+        T[i].uid = 100 + i
+    cu = capi.Context(capi.load_cuda())
+
+    def albedo_aov():
+        cu.upload_scene(C.byref(d))
+        cu.build_accel()
+        return cu.render(look_down_params(capi, spp=16, batch=16))[1][..., :3].mean(axis=(0, 1))
+
+    a0 = albedo_aov()
+    assert np.allclose(a0[:2], 0.5, atol=1e-3)
+    albedo[0] = 0  # same uid: the caller broke the contract, the device copy is (legitimately) still the old one
+    assert np.allclose(albedo_aov(), a0, atol=1e-7)
+    T[1].uid = 200  # new identity: uploaded again
+    a1 = albedo_aov()
+    assert a1[0] < 1e-3 and np.allclose(a1[1], 0.5, atol=1e-3)
+    albedo[0] = 255
+    T[1].uid = 0  # anonymous content is always uploaded
+    assert np.allclose(albedo_aov(), a0, atol=1e-7)
+    albedo[1] = 0
+    a2 = albedo_aov()
+    assert a2[1] < 1e-3
     cu.close()
 
 

@@ -52,11 +52,11 @@ class ptc_light_instance(C.Structure):
 
 
 class ptc_texture(C.Structure):
-    _fields_ = [("width", u32), ("height", u32), ("channels", u32), ("srgb", u32), ("data", C.POINTER(C.c_uint8))]
+    _fields_ = [("width", u32), ("height", u32), ("channels", u32), ("srgb", u32), ("data", C.POINTER(C.c_uint8)), ("uid", u64)]
 
 
 class ptc_env(C.Structure):
-    _fields_ = [("equirect_rgba", C.POINTER(f32)), ("width", u32), ("height", u32)]
+    _fields_ = [("equirect_rgba", C.POINTER(f32)), ("width", u32), ("height", u32), ("uid", u64)]
 
 
 class ptc_scene_desc(C.Structure):
@@ -443,10 +443,15 @@ class HostEngine:
         self.lib.vh_render_params(self.h, C.byref(p))
         return p
 
-    def render_to_memory(self):
+    def render_to_memory(self, out=None):
+        """RendererPathTracing::render() into host arrays; `out` = three reusable float32 arrays of width*height*4"""
         ri = self.render_info()
         n = ri["width"] * ri["height"] * 4
-        rad, alb, nrm = (np.zeros(n, np.float32) for _ in range(3))
+        if out is not None:
+            rad, alb, nrm = (o.reshape(-1) for o in out)
+            assert all(o.size == n and o.dtype == np.float32 and o.flags.c_contiguous for o in (rad, alb, nrm))
+        else:
+            rad, alb, nrm = (np.empty(n, np.float32) for _ in range(3))
         rc = self.lib.vh_render_to_memory(self.h, np_ptr(rad), np_ptr(alb), np_ptr(nrm))
         if rc != 0:
             raise RuntimeError("RendererPathTracing::render failed: %s" % self.last_error())

@@ -66,17 +66,30 @@ struct ptc_ctx {
     std::atomic<float> progress{0.0f};
     ptc_stats stats{};
 
-    void freeTextures() {
+    /* identity of what the texture arrays / the cubemap were built from (ptc_texture.uid, ptc_env.uid): an upload whose
+     * textures are the same immutable objects keeps the device copies, like the reference, which uploads at import */
+    std::vector<uint64_t> texSignature;
+    uint64_t envSignature[3] = {0, 0, 0};
+
+    void freeTextureClasses() {
         for (auto &t : texClasses) {
             if (t.tex) cudaDestroyTextureObject(t.tex);
             if (t.array) cudaFreeArray(t.array);
         }
         texClasses.clear();
+        texSignature.clear();
+    }
+    void freeCubemap() {
         if (cubeTex) cudaDestroyTextureObject(cubeTex);
         if (cubeArray) cudaFreeArray(cubeArray);
         cubeTex = 0;
         cubeArray = nullptr;
         cubeN = 0;
+        envSignature[0] = envSignature[1] = envSignature[2] = 0;
+    }
+    void freeTextures() {
+        freeTextureClasses();
+        freeCubemap();
     }
     ~ptc_ctx() {
         cudaSetDevice(device);
@@ -613,14 +626,33 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
     c->nWorldTris = (uint32_t)tri;
     c->instances.upload(inst.data(), inst.size(), s);
 
-    c->freeTextures();
+    std::vector<uint64_t> sig;
+    bool allIdentified = sd->n_textures > 0;
     for (uint32_t t = 0; t < sd->n_textures; t++) {
         const ptc_texture &in = sd->textures[t];
         if (in.channels != 1 && in.channels != 4) return fail(c, "texture channels must be 1 or 4");
         if (!in.data || !in.width || !in.height) return fail(c, "texture without data");
+        allIdentified = allIdentified && in.uid != 0;
+        sig.push_back(in.uid);
+        sig.push_back(((uint64_t)in.width << 32) | in.height);
+        sig.push_back(((uint64_t)in.channels << 32) | in.srgb);
     }
-    createTextures(c, sd);
-    createCubemap(c, sd->env);
+    if (!(allIdentified && sig == c->texSignature && c->nTextures == sd->n_textures)) {
+        c->freeTextureClasses();
+        createTextures(c, sd);
+        if (allIdentified) c->texSignature = sig;
+    }
+    const ptc_env &env = sd->env;
+    const bool hasEnv = env.equirect_rgba && env.width && env.height;
+    if (!(hasEnv && env.uid != 0 && c->cubeTex && c->envSignature[0] == env.uid && c->envSignature[1] == env.width && c->envSignature[2] == env.height)) {
+        c->freeCubemap();
+        createCubemap(c, env);
+        if (hasEnv && env.uid != 0) {
+            c->envSignature[0] = env.uid;
+            c->envSignature[1] = env.width;
+            c->envSignature[2] = env.height;
+        }
+    }
     CUDA_TRY(cudaStreamSynchronize(s));
     c->sceneUploaded = true;
     return 0;

@@ -331,12 +331,7 @@ PTC_API int vh_render_params(vh_engine *h, ptc_render_params *out) {
 
 PTC_API int vh_render_to_memory(vh_engine *h, float *radiance, float *albedo, float *normal) {
     if (!h) return 1;
-    std::vector<float> r, a, n;
-    if (!h->engine->renderer().rendererPathTracing().renderToMemory(r, a, n)) return 2;
-    if (radiance) std::memcpy(radiance, r.data(), r.size() * sizeof(float));
-    if (albedo) std::memcpy(albedo, a.data(), a.size() * sizeof(float));
-    if (normal) std::memcpy(normal, n.data(), n.size() * sizeof(float));
-    return 0;
+    return h->engine->renderer().rendererPathTracing().renderToBuffers(radiance, albedo, normal) ? 0 : 2;
 }
 
 PTC_API int vh_render(vh_engine *h, const char *filename) {

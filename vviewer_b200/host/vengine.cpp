@@ -4,6 +4,7 @@
 #include "vengine.hpp"
 
 #include <dlfcn.h>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -11,6 +12,11 @@
 #include <stdexcept>
 
 namespace vengine {
+
+uint64_t nextResourceUid() {
+    static std::atomic<uint64_t> counter{0};
+    return ++counter;
+}
 
 uint32_t Entity::s_nextId = 1;
 
@@ -553,6 +559,7 @@ void Engine::flatten(FlatScene &out) {
         pt.channels = (uint32_t)t->image.channels;
         pt.srgb = t->colorSpace == ColorSpace::sRGB ? 1u : 0u;
         pt.data = t->image.data.data();
+        pt.uid = t->uid;
         out.textures.push_back(pt);
     }
     ptc_scene_desc &d = out.desc;
@@ -577,6 +584,7 @@ void Engine::flatten(FlatScene &out) {
         d.env.equirect_rgba = env->equirect.data.data();
         d.env.width = (uint32_t)env->equirect.width;
         d.env.height = (uint32_t)env->equirect.height;
+        d.env.uid = env->uid;
     }
 }
 
@@ -674,6 +682,15 @@ ptc_render_params CudaRendererPathTracing::makeRenderParams() {
 }
 
 bool CudaRendererPathTracing::renderToMemory(std::vector<float> &radiance, std::vector<float> &albedo, std::vector<float> &normal) {
+    const RenderInfo &ri = renderInfo();
+    const size_t n = (size_t)ri.width * ri.height * 4;
+    radiance.resize(n);
+    albedo.resize(n);
+    normal.resize(n);
+    return renderToBuffers(radiance.data(), albedo.data(), normal.data());
+}
+
+bool CudaRendererPathTracing::renderToBuffers(float *radiance, float *albedo, float *normal) {
     if (!m_isInitialized) {
         std::fprintf(stderr, "CudaRendererPathTracing::render(): backend not initialised: %s\n", m_error.c_str());
         return false;
@@ -686,17 +703,24 @@ bool CudaRendererPathTracing::renderToMemory(std::vector<float> &radiance, std::
     }
     m_renderInProgress = true;
     bool ok = false;
+    const bool verbose = std::getenv("PTC_VERBOSE") != nullptr;
+    auto tick = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        auto now = std::chrono::steady_clock::now();
+        if (verbose) std::fprintf(stderr, "[render] %-10s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tick).count());
+        tick = now;
+    };
     do {
         FlatScene flat;
         m_engine.flatten(flat);
+        lap("flatten");
         ptc_render_params rp = makeRenderParams();
         if (m_backend.upload_scene(m_ctx, &flat.desc) != 0) break;
+        lap("upload");
         if (m_backend.build_accel(m_ctx) != 0) break;
-        size_t n = (size_t)rp.width * rp.height * 4;
-        radiance.assign(n, 0.0f);
-        albedo.assign(n, 0.0f);
-        normal.assign(n, 0.0f);
-        if (m_backend.render(m_ctx, &rp, radiance.data(), albedo.data(), normal.data()) != 0) break;
+        lap("build");
+        if (m_backend.render(m_ctx, &rp, radiance, albedo, normal) != 0) break;
+        lap("render+d2h");
         m_backend.get_stats(m_ctx, &m_stats);
         ok = true;
     } while (false);

@@ -98,6 +98,8 @@ float linearToSRGB(float v);
 void applyExposure(std::vector<float> &in, float exposure, uint32_t channels);
 void writeToDisk(const std::vector<float> &in, const std::string &filename, FileType type, uint32_t w, uint32_t h, uint32_t channels);
 
+uint64_t nextResourceUid(); /* process-wide, never 0 */
+
 class Texture {
 public:
     std::string name;
@@ -106,6 +108,7 @@ public:
     ImageU8 image;
     ColorSpace colorSpace = ColorSpace::sRGB;
     uint32_t bindlessResourceIndex = 0; /* slot in the texture table (VulkanTextures.cpp:145) */
+    uint64_t uid = nextResourceUid();   /* textures are immutable once created: identity for ptc_texture.uid */
 };
 
 class Textures { /* vulkan/resources/VulkanTextures.cpp:71-145 */
@@ -126,6 +129,7 @@ class EnvironmentMap {
 public:
     std::string name, filepath;
     ImageF32 equirect; /* RGBA32F, flipped like Image<float>::loadDiskImage (core/Image.cpp:27-43) */
+    uint64_t uid = nextResourceUid();
 };
 
 /* ------------------------------------------------------------------ materials */
@@ -728,6 +732,8 @@ public:
     float renderProgress() override;
     /* extras used by tools / tests */
     bool renderToMemory(std::vector<float> &radiance, std::vector<float> &albedo, std::vector<float> &normal);
+    /* same, into caller-owned width * height * 4 floats each (any may be null: that target is not read back) */
+    bool renderToBuffers(float *radiance, float *albedo, float *normal);
     ptc_render_params makeRenderParams();
     const ptc_stats &lastStats() const { return m_stats; }
     const std::string &lastError() const { return m_error; }
