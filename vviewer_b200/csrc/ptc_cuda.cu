@@ -57,11 +57,23 @@ struct ptc_ctx {
 
     /* render state */
     DBuf<float4> accR, accA, accN;
-    DBuf<float4> wOrgRng, wDirFlags, wBeta, wRadiance, wHit, wAovA, wAovN, wShOrg, wShDir, wShContrib, wPrBeta;
-    DBuf<uint32_t> wQueue0, wQueue1, wQShadow, wQProbe, wCounters, pixmap;
-    DBuf<unsigned long long> wStats;
-    size_t waveCapacity = 0;
-    cudaEvent_t evA = nullptr, evB = nullptr;
+    /* two wavefronts in flight (see renderImpl): each has its own path state, queues, counters and stream */
+    struct WaveBufs {
+        DBuf<float4> orgRng, dirFlags, beta, radiance, hit, aovA, aovN, shOrg, shDir, shContrib, prBeta;
+        DBuf<uint32_t> queue0, queue1, qShadow, qProbe, counters;
+        DBuf<unsigned long long> stats;
+        size_t capacity = 0;
+    } wave[2];
+    DBuf<uint32_t> pixmap;
+    cudaStream_t stream2 = nullptr; /* second wavefront; c->stream carries the first and everything else */
+    cudaEvent_t evA = nullptr, evB = nullptr, evAcc[2] = {nullptr, nullptr}, evFork = nullptr;
+    static constexpr int RING = 8;
+    cudaEvent_t evItem[RING] = {};
+    /* resident blocks per SM of the traversal / shading kernels while two wavefronts overlap; 0 = one wavefront at a time,
+     * the default: measured on the bench scene the overlap LOSES (2069 Mseg/s alone; 4+3 blocks 2030, 5+2 1888, 6+1 1604,
+     * profiles/r1_v4_overlap_sweep.log) - k_shade needs >= 3 blocks per SM to keep DRAM busy and k_extend loses as much
+     * with 4 as the overlap wins.  PTC_OVERLAP=t,s turns it on for experiments. */
+    int overlapTrace = 0, overlapShade = 0;
 
     std::atomic<float> progress{0.0f};
     ptc_stats stats{};
@@ -96,6 +108,12 @@ struct ptc_ctx {
         freeTextures();
         if (evA) cudaEventDestroy(evA);
         if (evB) cudaEventDestroy(evB);
+        if (evFork) cudaEventDestroy(evFork);
+        for (cudaEvent_t e : evAcc)
+            if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : evItem)
+            if (e) cudaEventDestroy(e);
+        if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -291,6 +309,7 @@ void setTraversalWindow(ptc_ctx *c) {
     if (bytes == 0 || c->persistMax == 0 || c->windowMax == 0) {
         attr.accessPolicyWindow.num_bytes = 0;
         cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaStreamSetAttribute(c->stream2, cudaStreamAttributeAccessPolicyWindow, &attr);
         return;
     }
     const size_t carve = std::min(c->persistMax, bytes);
@@ -302,50 +321,53 @@ void setTraversalWindow(ptc_ctx *c) {
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
     attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     CUDA_TRY(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    CUDA_TRY(cudaStreamSetAttribute(c->stream2, cudaStreamAttributeAccessPolicyWindow, &attr));
 }
 
-void ensureWave(ptc_ctx *c, size_t slots, uint32_t depth) {
-    if (slots > c->waveCapacity) {
-        c->wOrgRng.alloc(slots);
-        c->wDirFlags.alloc(slots);
-        c->wBeta.alloc(slots);
-        c->wRadiance.alloc(slots);
-        c->wHit.alloc(slots);
-        c->wAovA.alloc(slots);
-        c->wAovN.alloc(slots);
-        c->wShOrg.alloc(slots);
-        c->wShDir.alloc(slots);
-        c->wShContrib.alloc(slots);
-        c->wPrBeta.alloc(slots);
-        c->wQueue0.alloc(slots);
-        c->wQueue1.alloc(slots);
-        c->wQShadow.alloc(slots);
-        c->wQProbe.alloc(slots);
-        c->waveCapacity = slots;
+void ensureWave(ptc_ctx *c, int k, size_t slots, uint32_t depth) {
+    ptc_ctx::WaveBufs &w = c->wave[k];
+    if (slots > w.capacity) {
+        w.orgRng.alloc(slots);
+        w.dirFlags.alloc(slots);
+        w.beta.alloc(slots);
+        w.radiance.alloc(slots);
+        w.hit.alloc(slots);
+        w.aovA.alloc(slots);
+        w.aovN.alloc(slots);
+        w.shOrg.alloc(slots);
+        w.shDir.alloc(slots);
+        w.shContrib.alloc(slots);
+        w.prBeta.alloc(slots);
+        w.queue0.alloc(slots);
+        w.queue1.alloc(slots);
+        w.qShadow.alloc(slots);
+        w.qProbe.alloc(slots);
+        w.capacity = slots;
     }
-    c->wCounters.alloc((size_t)(depth + 2) * wf::CNT_STRIDE);
-    c->wStats.alloc(wf::ST_COUNT);
+    w.counters.alloc((size_t)(depth + 2) * wf::CNT_STRIDE);
+    w.stats.alloc(wf::ST_COUNT);
 }
 
-wf::Wave makeWave(ptc_ctx *c) {
+wf::Wave makeWave(ptc_ctx *c, int k) {
+    ptc_ctx::WaveBufs &b = c->wave[k];
     wf::Wave w{};
-    w.orgRng = c->wOrgRng.p;
-    w.dirFlags = c->wDirFlags.p;
-    w.beta = c->wBeta.p;
-    w.radiance = c->wRadiance.p;
-    w.hit = c->wHit.p;
-    w.aovAlbedo = c->wAovA.p;
-    w.aovNormal = c->wAovN.p;
-    w.shOrgTmax = c->wShOrg.p;
-    w.shDirVol = c->wShDir.p;
-    w.shContrib = c->wShContrib.p;
-    w.prBetaPdf = c->wPrBeta.p;
-    w.queue[0] = c->wQueue0.p;
-    w.queue[1] = c->wQueue1.p;
-    w.qShadow = c->wQShadow.p;
-    w.qProbe = c->wQProbe.p;
-    w.counters = c->wCounters.p;
-    w.stats = c->wStats.p;
+    w.orgRng = b.orgRng.p;
+    w.dirFlags = b.dirFlags.p;
+    w.beta = b.beta.p;
+    w.radiance = b.radiance.p;
+    w.hit = b.hit.p;
+    w.aovAlbedo = b.aovA.p;
+    w.aovNormal = b.aovN.p;
+    w.shOrgTmax = b.shOrg.p;
+    w.shDirVol = b.shDir.p;
+    w.shContrib = b.shContrib.p;
+    w.prBetaPdf = b.prBeta.p;
+    w.queue[0] = b.queue0.p;
+    w.queue[1] = b.queue1.p;
+    w.qShadow = b.qShadow.p;
+    w.qProbe = b.qProbe.p;
+    w.counters = b.counters.p;
+    w.stats = b.stats.p;
     return w;
 }
 
@@ -379,13 +401,30 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     CUDA_TRY(cudaMemsetAsync(dA, 0, nPix * sizeof(float4), s));
     CUDA_TRY(cudaMemsetAsync(dN, 0, nPix * sizeof(float4), s));
 
-    /* samples of one batch run concurrently; very large batches are cut into chunks that fit the wave */
-    const size_t maxSlots = (size_t)1 << 26;
+    /* Samples of one batch run concurrently as a wavefront; very large batches are cut into chunks that fit the wave.
+     *
+     * Optional (PTC_OVERLAP, off by default - see ptc_ctx::overlapTrace): two wavefronts in flight, each on its own stream.
+     * k_extend is instruction-issue bound (3-4 % of DRAM throughput) and k_shade is DRAM bound (~30 % issue), so the
+     * traversal of one wavefront can overlap the shading of the other.  Both are persistent kernels that pull work from
+     * device queues, so they are launched with FEWER resident blocks per SM (overlapTrace + overlapShade share an SM's
+     * registers) and any mix of phases keeps the SMs full.  A batch is split into two half-batch wavefronts, so the
+     * path-state memory is what one full batch uses.  Work items are accumulated in a fixed order (event chain), which
+     * keeps the image deterministic. */
+    const bool timeKernels = (rp->flags & PTC_FLAG_TIME_KERNELS) != 0;
+    const bool overlap = c->overlapTrace > 0 && c->overlapShade > 0 && !timeKernels && nPixLocal > 0;
+    const int nWaves = overlap ? 2 : 1;
+    size_t maxSlots = (size_t)1 << (overlap ? 25 : 26);
+    if (const char *ms = getenv("PTC_MAX_SLOTS")) maxSlots = std::max<size_t>(1, (size_t)atoll(ms)); /* tests: force chunking */
     uint32_t chunkSamples = rp->batch_size;
     if (nPixLocal > 0) chunkSamples = (uint32_t)std::max<size_t>(1, std::min<size_t>(rp->batch_size, maxSlots / nPixLocal));
-    ensureWave(c, (size_t)chunkSamples * std::max(1u, nPixLocal), rp->depth);
-    wf::Wave w = makeWave(c);
-    CUDA_TRY(cudaMemsetAsync(c->wStats.p, 0, wf::ST_COUNT * sizeof(unsigned long long), s));
+    if (overlap && chunkSamples == rp->batch_size && rp->batch_size >= 2) chunkSamples = (rp->batch_size + 1) / 2;
+    wf::Wave waves[2];
+    cudaStream_t streams[2] = {s, c->stream2};
+    for (int k = 0; k < nWaves; k++) {
+        ensureWave(c, k, (size_t)chunkSamples * std::max(1u, nPixLocal), rp->depth);
+        waves[k] = makeWave(c, k);
+        CUDA_TRY(cudaMemsetAsync(c->wave[k].stats.p, 0, wf::ST_COUNT * sizeof(unsigned long long), s));
+    }
 
     wf::RenderConst rc{};
     rc.sd = rp->scene;
@@ -403,23 +442,24 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     DScene sc = makeDScene(c);
 
     /* persistent kernels: exactly as many blocks as are resident at once (multiples of the SM count) */
-    auto residentGrid = [&](const void *kernel, int block) {
+    auto residentGrid = [&](const void *kernel, int block, int cap) {
         int perSm = 1;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, block, 0) != cudaSuccess || perSm < 1) perSm = 1;
+        if (cap > 0) perSm = std::min(perSm, cap);
         return c->smCount * perSm;
     };
-    const int gridExtend = residentGrid((const void *)wf::k_extend, TRV_BLOCK);
-    const int gridShade = residentGrid((const void *)wf::k_shade, 128);
-    const int gridShadow = residentGrid((const void *)wf::k_shadow, TRV_BLOCK);
-    const int gridProbe = residentGrid((const void *)wf::k_probe, TRV_BLOCK);
+    const int capTrace = overlap ? c->overlapTrace : 0, capShade = overlap ? c->overlapShade : 0;
+    const int gridExtend = residentGrid((const void *)wf::k_extend, TRV_BLOCK, capTrace);
+    const int gridShade = residentGrid((const void *)wf::k_shade, 128, capShade);
+    const int gridShadow = residentGrid((const void *)wf::k_shadow, TRV_BLOCK, capTrace);
+    const int gridProbe = residentGrid((const void *)wf::k_probe, TRV_BLOCK, capTrace);
     uint64_t launches = 0, traceLaunches = 0;
     double traceMs = 0, shadeMs = 0, shadowMs = 0;
-    const bool timeKernels = (rp->flags & PTC_FLAG_TIME_KERNELS) != 0;
-    auto timed = [&](double &acc, auto &&launch) {
-        if (timeKernels) CUDA_TRY(cudaEventRecord(c->evA, s));
+    auto timed = [&](double &acc, cudaStream_t st, auto &&launch) {
+        if (timeKernels) CUDA_TRY(cudaEventRecord(c->evA, st));
         launch();
         if (timeKernels) {
-            CUDA_TRY(cudaEventRecord(c->evB, s));
+            CUDA_TRY(cudaEventRecord(c->evB, st));
             CUDA_TRY(cudaEventSynchronize(c->evB));
             float ms = 0;
             CUDA_TRY(cudaEventElapsedTime(&ms, c->evA, c->evB));
@@ -431,48 +471,63 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     CUDA_TRY(cudaEventCreate(&evStart));
     CUDA_TRY(cudaEventCreate(&evStop));
     CUDA_TRY(cudaEventRecord(evStart, s));
-    uint32_t myBatches = 0, doneBatches = 0;
+    /* the second stream starts after the clears above */
+    if (overlap) {
+        CUDA_TRY(cudaEventRecord(c->evFork, s));
+        CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->evFork, 0));
+    }
+    uint32_t myBatches = 0;
     for (uint32_t b = 0; b < batches; b++)
         if (!(rp->split_mode == PTC_SPLIT_SAMPLE && world > 1 && (b % world) != rp->rank)) myBatches++;
+    const uint32_t chunksPerBatch = (rp->batch_size + chunkSamples - 1) / chunkSamples;
+    const uint64_t totalItems = (uint64_t)myBatches * chunksPerBatch;
 
+    uint64_t item = 0;
     if (nPixLocal > 0) {
         for (uint32_t b = 0; b < batches; b++) {
             if (rp->split_mode == PTC_SPLIT_SAMPLE && world > 1 && (b % world) != rp->rank) continue;
-            for (uint32_t s0 = 0; s0 < rp->batch_size; s0 += chunkSamples) {
+            for (uint32_t s0 = 0; s0 < rp->batch_size; s0 += chunkSamples, item++) {
+                const int k = (int)(item % (uint64_t)nWaves);
+                cudaStream_t st = streams[k];
+                const wf::Wave &w = waves[k];
+                /* at most RING work items in flight; renderProgress() follows the completed ones without draining the pipeline */
+                if (item >= (uint64_t)ptc_ctx::RING) {
+                    CUDA_TRY(cudaEventSynchronize(c->evItem[item % ptc_ctx::RING]));
+                    c->progress = (float)(item - ptc_ctx::RING + 1) / (float)totalItems;
+                }
                 const uint32_t ns = std::min(chunkSamples, rp->batch_size - s0);
                 const uint32_t nSlots = ns * nPixLocal;
-                CUDA_TRY(cudaMemsetAsync(c->wCounters.p, 0, (size_t)(rp->depth + 2) * wf::CNT_STRIDE * sizeof(uint32_t), s));
-                wf::k_raygen<<<(nSlots + 255) / 256, 256, 0, s>>>(w, rc, nSlots, b * rp->batch_size + s0);
+                CUDA_TRY(cudaMemsetAsync(w.counters, 0, (size_t)(rp->depth + 2) * wf::CNT_STRIDE * sizeof(uint32_t), st));
+                wf::k_raygen<<<(nSlots + 255) / 256, 256, 0, st>>>(w, rc, nSlots, b * rp->batch_size + s0);
                 launches++;
                 for (uint32_t d = 0; d < rp->depth; d++) {
-                    timed(traceMs, [&] { wf::k_extend<<<gridExtend, TRV_BLOCK, 0, s>>>(w, sc, d, c->tune); });
-                    timed(shadeMs, [&] { wf::k_shade<<<gridShade, 128, 0, s>>>(w, sc, rc, d, b * rp->batch_size + s0); });
+                    timed(traceMs, st, [&] { wf::k_extend<<<gridExtend, TRV_BLOCK, 0, st>>>(w, sc, d, c->tune); });
+                    timed(shadeMs, st, [&] { wf::k_shade<<<gridShade, 128, 0, st>>>(w, sc, rc, d, b * rp->batch_size + s0); });
                     launches += 2;
                     traceLaunches++;
                     if (rc.totalLights > 0) {
-                        timed(shadowMs, [&] { wf::k_shadow<<<gridShadow, TRV_BLOCK, 0, s>>>(w, sc, rc, d, c->tune); });
+                        timed(shadowMs, st, [&] { wf::k_shadow<<<gridShadow, TRV_BLOCK, 0, st>>>(w, sc, rc, d, c->tune); });
                         launches++;
                     }
                     if (c->anyEmissive) {
-                        timed(shadowMs, [&] { wf::k_probe<<<gridProbe, TRV_BLOCK, 0, s>>>(w, sc, rc, d, c->tune); });
+                        timed(shadowMs, st, [&] { wf::k_probe<<<gridProbe, TRV_BLOCK, 0, st>>>(w, sc, rc, d, c->tune); });
                         launches++;
                     }
                 }
-                wf::k_collect_stats<<<1, 32, 0, s>>>(w, rp->depth);
-                wf::k_accumulate<<<(nPixLocal + 255) / 256, 256, 0, s>>>(w, rc, ns, dR, dA, dN);
+                wf::k_collect_stats<<<1, 32, 0, st>>>(w, rp->depth);
+                /* accumulate in item order: item i adds after item i - 1 (which ran on the other stream) */
+                if (overlap && item > 0) CUDA_TRY(cudaStreamWaitEvent(st, c->evAcc[(item - 1) & 1u], 0));
+                wf::k_accumulate<<<(nPixLocal + 255) / 256, 256, 0, st>>>(w, rc, ns, dR, dA, dN);
+                if (overlap) CUDA_TRY(cudaEventRecord(c->evAcc[item & 1u], st));
+                CUDA_TRY(cudaEventRecord(c->evItem[item % ptc_ctx::RING], st));
                 launches += 2;
-            }
-            doneBatches++;
-            CUDA_TRY(cudaGetLastError());
-            /* renderProgress(): batches complete when the stream reaches this point; keep the queue short
-             * enough that the number is meaningful without stalling the device */
-            if ((doneBatches & 3u) == 0u) {
-                CUDA_TRY(cudaStreamSynchronize(s));
-                c->progress = (float)doneBatches / (float)myBatches;
+                CUDA_TRY(cudaGetLastError());
             }
         }
     }
-    /* alpha = 1 everywhere, including pixels owned by other ranks when this image is the reduce root's term */
+    /* join: the first stream waits for the last work item of the second */
+    if (overlap && item > 0) CUDA_TRY(cudaStreamWaitEvent(s, c->evAcc[(item - 1) & 1u], 0));
+    if (overlap && item > 1) CUDA_TRY(cudaStreamWaitEvent(s, c->evAcc[(item - 2) & 1u], 0));
     CUDA_TRY(cudaEventRecord(evStop, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     float ms = 0;
@@ -480,8 +535,12 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     cudaEventDestroy(evStart);
     cudaEventDestroy(evStop);
 
-    unsigned long long hs[wf::ST_COUNT];
-    CUDA_TRY(cudaMemcpy(hs, c->wStats.p, sizeof(hs), cudaMemcpyDeviceToHost));
+    unsigned long long hs[wf::ST_COUNT] = {};
+    for (int k = 0; k < nWaves; k++) {
+        unsigned long long one[wf::ST_COUNT];
+        CUDA_TRY(cudaMemcpy(one, c->wave[k].stats.p, sizeof(one), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < wf::ST_COUNT; i++) hs[i] += one[i];
+    }
     c->stats.segments = hs[wf::ST_SEGMENTS];
     c->stats.path_rays = hs[wf::ST_SEGMENTS];
     c->stats.shadow_rays = hs[wf::ST_SHADOW_RAYS];
@@ -561,9 +620,19 @@ PTC_API int ptc_create(ptc_ctx **out, const int *device_ids, int n_devices) {
         unsigned a, b, d, e;
         if (sscanf(t, "%u,%u,%u,%u", &a, &b, &d, &e) == 4) c->tune = wf::ExtendTune{a, b, d, e};
     }
+    if (const char *o = getenv("PTC_OVERLAP")) { /* "traceBlocksPerSM,shadeBlocksPerSM"; "0" = one wavefront at a time */
+        int a = 0, b = 0;
+        const int got = sscanf(o, "%d,%d", &a, &b);
+        if (got == 2 && a > 0 && b > 0) c->overlapTrace = a, c->overlapShade = b;
+        else if (got >= 1 && a == 0) c->overlapTrace = c->overlapShade = 0;
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&c->evA));
     CUDA_TRY(cudaEventCreate(&c->evB));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+    for (cudaEvent_t &e : c->evAcc) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaEvent_t &e : c->evItem) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     return 0;
     PTC_GUARD_END(c)
 }
