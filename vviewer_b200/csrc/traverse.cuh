@@ -158,6 +158,8 @@ struct Trav {
                         cz = fmaf(-32768.0f, az, (n0.z - o.z) * idir.z);
             const float px = fabsf(ax) * 0.0078125f, py = fabsf(ay) * 0.0078125f, pz = fabsf(az) * 0.0078125f;
             const float bnx = cx - px, bny = cy - py, bnz = cz - pz, bfx = cx + px, bfy = cy + py, bfz = cz + pz;
+            const float2 ax2 = make_float2(ax, ax), ay2 = make_float2(ay, ay), az2 = make_float2(az, az);
+            const float2 bx2 = make_float2(bnx, bfx), by2 = make_float2(bny, bfy), bz2 = make_float2(bnz, bfz);
             const float tlo = t0 * 0.999999f, thi = best.t * 1.000001f;
             const uint32_t magic = sc.prmtMagic;
             const uint32_t imask = ei >> 24;
@@ -177,14 +179,15 @@ struct Trav {
                 const uint32_t nx = idir.x < 0.0f ? qhx : qlx, fx = idir.x < 0.0f ? qlx : qhx;
                 const uint32_t ny = idir.y < 0.0f ? qhy : qly, fy = idir.y < 0.0f ? qly : qhy;
                 const uint32_t nz = idir.z < 0.0f ? qhz : qlz, fz = idir.z < 0.0f ? qlz : qhz;
+/* near and far plane of one axis in ONE packed instruction (Blackwell FFMA2, fma.rn.f32x2: two independent IEEE FMAs,
+ * bit-identical to two FFMAs): (t_near, t_far) = (q_near, q_far) * (a, a) + (b_near, b_far) */
 #define TRV_CHILD(J)                                                                                                          \
     {                                                                                                                         \
-        const float tnx = fmaf(byteToFloat<J>(nx, magic), ax, bnx), tny = fmaf(byteToFloat<J>(ny, magic), ay, bny),           \
-                    tnz = fmaf(byteToFloat<J>(nz, magic), az, bnz);                                                           \
-        const float tfx = fmaf(byteToFloat<J>(fx, magic), ax, bfx), tfy = fmaf(byteToFloat<J>(fy, magic), ay, bfy),           \
-                    tfz = fmaf(byteToFloat<J>(fz, magic), az, bfz);                                                           \
-        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tlo));                                                             \
-        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, thi));                                                             \
+        const float2 tx = __ffma2_rn(make_float2(byteToFloat<J>(nx, magic), byteToFloat<J>(fx, magic)), ax2, bx2);            \
+        const float2 ty = __ffma2_rn(make_float2(byteToFloat<J>(ny, magic), byteToFloat<J>(fy, magic)), ay2, by2);            \
+        const float2 tz = __ffma2_rn(make_float2(byteToFloat<J>(nz, magic), byteToFloat<J>(fz, magic)), az2, bz2);            \
+        const float tn = fmaxf(fmaxf(tx.x, ty.x), fmaxf(tz.x, tlo));                                                          \
+        const float tf = fminf(fminf(tx.y, ty.y), fminf(tz.y, thi));                                                          \
         if (tn * 0.999999f <= tf) hitmask |= ((childBits4 >> (8 * J)) & 0xffu) << ((bitIndex4 >> (8 * J)) & 0xffu);           \
     }
                 TRV_CHILD(0) TRV_CHILD(1) TRV_CHILD(2) TRV_CHILD(3)
@@ -192,6 +195,7 @@ struct Trav {
             }
             ng.y = (hitmask & 0xff000000u) | imask;
             tgOut.y = hitmask & 0x00ffffffu;
+            /* (measured: starting the next node's fetch here with prefetch.global.L1 - CCTL.PF1 x3 - costs 11 %, 2053 -> 1833 Mseg/s) */
         }
         return tgOut;
     }
