@@ -174,6 +174,12 @@ typedef struct ptc_render_params {
 
 #define PTC_FLAG_WORLD_ORIGIN_PROBE_PDF 1u /* use the world-space ray origin in the probe-ray pdf instead of reproducing rayNEE.rahit.glsl:122 */
 #define PTC_FLAG_SAMPLER_SOBOL 4u         /* low-discrepancy sampler (shuffled, Owen-scrambled Sobol; plays the role of the reference's optional PMJ02BN sampler, rng_pmj.glsl) instead of the default xorshift stream */
+/* Extension, off for parity: the reference never light-samples the environment (lightSampling.glsl:101-106 is a TODO, trap T3).
+ * With this flag an HDRI environment (type 1 or 2) becomes one more light of the uniform light pick: directions are drawn from a
+ * 512 x 256 luminance x cos(latitude) table over the equirectangular domain, the shadow chain decides visibility, and both this
+ * sample and the environment radiance found by a sampled direction (miss) are weighted with the power heuristic.  Same
+ * expectation as without the flag, far lower variance under small bright sources (sun). */
+#define PTC_FLAG_ENV_IMPORTANCE 8u
 #define PTC_FLAG_TIME_KERNELS 2u          /* bracket every kernel class with CUDA events (fills ptc_stats.*_ms; serialises launches) */
 
 typedef struct ptc_stats {
@@ -265,6 +271,12 @@ PTC_API int ptc_sampler_points(ptc_ctx *ctx, uint32_t px, uint32_t py, uint32_t 
 
 /* Environment lookup parity hook: n directions (xyz) -> rgb of the backend's cubemap at LOD 0. */
 PTC_API int ptc_env_lookup(ptc_ctx *ctx, int n, const float *dirs, float *out_rgb);
+
+/* Environment importance-sampling parity hooks (PTC_FLAG_ENV_IMPORTANCE): n pairs of uniform numbers -> the sampled unit
+ * directions (xyz) and their solid-angle densities; n directions -> the density the sampler has for them.  Error without an
+ * environment. */
+PTC_API int ptc_env_sample(ptc_ctx *ctx, int n, const float *u01, float *out_dirs, float *out_pdf);
+PTC_API int ptc_env_pdf(ptc_ctx *ctx, int n, const float *dirs, float *out_pdf);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,7 @@
 #include "omath.hpp"
 #include "bsdf.hpp"
 #include "accel.hpp"
+#include "envdist.hpp"
 
 #include <atomic>
 #include <chrono>
@@ -95,6 +96,7 @@ struct ptc_ctx {
     /* environment cubemap, 6 faces of N*N rgba */
     uint32_t cubeN = 0;
     std::vector<float> cube;
+    envdist::Tables envTables; /* PTC_FLAG_ENV_IMPORTANCE */
     /* accel */
     std::vector<WorldTri> tris;
     std::vector<uint64_t> instFirstTri;
@@ -244,6 +246,7 @@ struct Payload { /* pt/structs_pt.glsl:4-30 */
     bool stop = false, insideVolume = false;
     float vtmin = 0.001f;
     uint32_t volumeMaterialIndex = 0;
+    float lastPdf = 0.0f; /* PTC_FLAG_ENV_IMPORTANCE: density of the last sampled direction (0 = camera ray) */
     Rng rng;
 };
 
@@ -265,7 +268,8 @@ struct HitInfo { /* pt/process_hit.glsl + pt/construct_frame.glsl */
 struct Tracer {
     const ptc_ctx *c;
     const ptc_render_params *rp;
-    uint32_t depth, totalLights;
+    uint32_t depth, totalLights; /* totalLights counts the environment when it is light-sampled */
+    bool envLight = false;       /* PTC_FLAG_ENV_IMPORTANCE and an HDRI environment (type 1 or 2) */
     float zfar;
     Stats st;
     std::vector<Hit> scratch;
@@ -413,8 +417,27 @@ struct Tracer {
         float pdf = 1.0f / (float)totalLights;
         uint32_t randomLight = (uint32_t)(P.rng.rand1D() * (float)totalLights);
         if (randomLight >= totalLights) randomLight = totalLights - 1;
-        const ptc_light_instance &light = c->lightInstances[randomLight];
         float tmax = 10000.0f;
+        if (envLight && randomLight == totalLights - 1) {
+            /* extension (no reference counterpart, trap T3): the environment is the last light; direction by luminance
+             * importance sampling (oracle/envdist.hpp), radiance as the miss shader would return it after a bounce */
+            vec2 u2 = P.rng.rand2D();
+            float eu, ev, puv;
+            envdist::sampleUV(c->envTables, u2.x, u2.y, eu, ev, puv);
+            vec3 d;
+            envdist::direction(eu, ev, d.x, d.y, d.z);
+            lsr.direction = d;
+            lsr.radiance = sampleCubemap(c, d) * (rp->scene.background[3] == 1.0f ? rp->scene.exposure[1] : 1.0f);
+            lsr.pdf = pdf * envdist::solidAnglePdf(puv, ev);
+            lsr.isDeltaLight = false;
+            if (!(lsr.pdf > 0.0f)) lsr.radiance = vec3(0.0f);
+            if (!isBlack(lsr.radiance)) {
+                vec3 thr = shadowChain(originPosition, lsr.direction, tmax, P.insideVolume, P.volumeMaterialIndex);
+                lsr.radiance = lsr.radiance * thr;
+            }
+            return lsr;
+        }
+        const ptc_light_instance &light = c->lightInstances[randomLight];
         if (light.info[3] == 0) {
             const ptc_light_data &ld = c->lightData[light.info[0]];
             vec3 lp = v3(light.position);
@@ -648,6 +671,7 @@ struct Tracer {
             float sampleDirectionPDF = HG_Sample(wo, sampleDirectionWorld, P.rng.rand2D(), g);
             P.origin = scatteringPosition;
             P.direction = sampleDirectionWorld;
+            P.lastPdf = sampleDirectionPDF;
             nextEventEstimation(P, sampleDirectionPDF);
         }
         return sampledMedium;
@@ -751,9 +775,19 @@ struct Tracer {
                 }
                 P.beta *= vclamp(F / sampleDirectionPDF, 0.0f, 1.0f);
             }
+            P.lastPdf = sampleDirectionPDF;
             nextEventEstimation(P, sampleDirectionPDF);
         }
         russianRoulette(P);
+    }
+
+    /* PTC_FLAG_ENV_IMPORTANCE: power-heuristic weight of an environment hit by a sampled direction against the light
+     * sampler's density for the same direction (1 for camera rays and when the option is off) */
+    float envMisWeight(const Payload &P, vec3 rayDir) const {
+        if (!envLight || !(P.lastPdf > 0.0f)) return 1.0f;
+        vec2 uv = sampleEquirectangularMap(normalize(rayDir));
+        float pl = (1.0f / (float)totalLights) * envdist::solidAnglePdf(envdist::pdfUV(c->envTables, uv.x, uv.y), uv.y);
+        return PowerHeuristic(1, P.lastPdf, 1, pl);
     }
 
     /* rayPrimary.rmiss.glsl:40-106 */
@@ -779,7 +813,7 @@ struct Tracer {
                     P.albedo = col;
                     P.normal = vec3(0.0f);
                 }
-                P.radiance += col * P.beta;
+                P.radiance += col * P.beta * envMisWeight(P, rayDir);
             } else if (bg[3] == 2.0f) {
                 vec3 env = sampleCubemap(c, rayDir);
                 vec3 solid = v3(bg);
@@ -788,7 +822,7 @@ struct Tracer {
                     P.normal = vec3(0.0f);
                     P.radiance += solid * P.beta;
                 } else {
-                    P.radiance += env * P.beta;
+                    P.radiance += env * P.beta * envMisWeight(P, rayDir);
                 }
             }
             return;
@@ -937,6 +971,7 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *s) {
         }
     }
     buildCubemap(c, s->env);
+    envdist::build(s->env.equirect_rgba, s->env.width, s->env.height, c->envTables);
 
     /* flatten to world space: instance order, then primitive order */
     c->tris.clear();
@@ -1000,6 +1035,9 @@ PTC_API int ptc_render(ptc_ctx *c, const ptc_render_params *rp, float *radiance,
         T.rp = rp;
         T.depth = rp->depth;
         T.totalLights = (uint32_t)c->lightInstances.size();
+        T.envLight = (rp->flags & PTC_FLAG_ENV_IMPORTANCE) != 0u && c->cubeN > 0 && c->envTables.valid &&
+                     (rp->scene.background[3] == 1.0f || rp->scene.background[3] == 2.0f);
+        if (T.envLight) T.totalLights += 1u;
         T.zfar = rp->scene.volumes[2];
 #pragma omp for schedule(dynamic, 1)
         for (int y = 0; y < (int)H; y++) {
@@ -1169,6 +1207,27 @@ PTC_API int ptc_sampler_points(ptc_ctx *, uint32_t px, uint32_t py, uint32_t wid
         vec2 p = r.rand2D();
         out_xy[2 * i] = p.x;
         out_xy[2 * i + 1] = p.y;
+    }
+    return 0;
+}
+
+PTC_API int ptc_env_sample(ptc_ctx *c, int n, const float *u01, float *out_dirs, float *out_pdf) {
+    if (!c) return 1;
+    if (!c->envTables.valid) return fail(c, "no environment");
+    for (int i = 0; i < n; i++) {
+        float u, v, puv;
+        envdist::sampleUV(c->envTables, u01[2 * i], u01[2 * i + 1], u, v, puv);
+        envdist::direction(u, v, out_dirs[3 * i], out_dirs[3 * i + 1], out_dirs[3 * i + 2]);
+        out_pdf[i] = envdist::solidAnglePdf(puv, v);
+    }
+    return 0;
+}
+PTC_API int ptc_env_pdf(ptc_ctx *c, int n, const float *dirs, float *out_pdf) {
+    if (!c) return 1;
+    if (!c->envTables.valid) return fail(c, "no environment");
+    for (int i = 0; i < n; i++) {
+        vec2 uv = sampleEquirectangularMap(normalize(vec3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2])));
+        out_pdf[i] = envdist::solidAnglePdf(envdist::pdfUV(c->envTables, uv.x, uv.y), uv.y);
     }
     return 0;
 }

@@ -295,6 +295,51 @@ def test_samples_dropped_and_alpha(capi):
     cu.close()
 
 
+# ---------------------------------------------------------------- environment importance sampling (PTC_FLAG_ENV_IMPORTANCE)
+def test_env_sampler_parity(capi, engine):
+    """same tables (built on the host from the same input, bit-identical) and same inversion: directions and densities agree to
+    float rounding of the device's sin / cos / atan2"""
+    engine.build_scene("EnvironmentMapLambert")
+    cu, orc = both(capi, engine.scene_desc())
+    u = np.random.default_rng(5).uniform(size=(100000, 2)).astype(np.float32)
+    da, pa = cu.env_sample(u)
+    db, pb = orc.env_sample(u)
+    assert np.abs(da - db).max() < 2e-6
+    assert np.max(np.abs(pa / pb - 1)) < 1e-4
+    d = np.random.default_rng(6).normal(size=(100000, 3)).astype(np.float32)
+    qa, qb = cu.env_pdf(d), orc.env_pdf(d)
+    # a direction within rounding of a bin edge may fall into the neighbouring bin on one side
+    assert np.mean(np.abs(qa / qb - 1) > 1e-4) < 1e-3
+    cu.close()
+    orc.close()
+
+
+@pytest.mark.parametrize("scene,env_type", [("EnvironmentMapLambert", 1), ("EnvironmentMapPBR00", 1), ("EnvironmentMapPBR11", 2), ("Volume0", None),
+                                            ("NormalMap", None), ("MeshLight", None), ("DepthOfField", None)])
+def test_env_importance_matches_oracle(capi, engine, scene, env_type):
+    engine.build_scene(scene)
+    engine.set_render_info(width=128, height=128, samples=8, batch_size=4)
+    desc, rp = engine.scene_desc(), engine.render_params()
+    rp.flags |= capi.PTC_FLAG_ENV_IMPORTANCE
+    if env_type is not None:
+        rp.scene.background[3] = float(env_type)
+    cu, orc = both(capi, desc)
+    ra, aa, na = cu.render(rp)
+    rb, ab, nb = orc.render(rp)
+    sa, sb = cu.stats(), orc.stats()
+    d = np.abs(ra[..., :3] - rb[..., :3]).max(axis=-1)
+    assert np.mean(d > 1e-3 * np.maximum(1.0, rb[..., :3].max(axis=-1))) < 0.02, "radiance differs in %.3f %% of pixels" % (100 * np.mean(d > 1e-3))
+    assert abs(ra[..., :3].mean() / max(rb[..., :3].mean(), 1e-9) - 1) < 3e-3
+    assert abs(sa["segments"] - sb["segments"]) <= 1e-3 * sb["segments"]
+    # (shadow-ray counts are not comparable: the device drops requests whose BSDF value is black before tracing them)
+    if rp.scene.background[3] != 0.0:
+        rp.flags &= ~capi.PTC_FLAG_ENV_IMPORTANCE
+        cu.render(rp, want_aovs=False)
+        assert cu.stats()["shadow_rays"] < sa["shadow_rays"]  # the flag really adds the environment to the light pick
+    cu.close()
+    orc.close()
+
+
 def test_texture_identity_cache(capi):
     """ptc_texture.uid: content with a non-zero uid is immutable by contract and keeps its device copy across uploads
     (the reference uploads textures once, at import); uid 0 or a new uid uploads again."""

@@ -4,9 +4,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vviewer_b200 import capi
 eng = capi.HostEngine()
 scene = sys.argv[1] if len(sys.argv) > 1 else "GLTF"
-eng.build_scene(scene)
-eng.set_render_info(width=128, height=128, samples=8, batch_size=4)
+flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+if scene == "Atrium":
+    eng.build_scene(scene, texture_size=64, scale=0.05)
+    eng.set_render_info(width=160, height=90, samples=8, batch_size=4)
+else:
+    eng.build_scene(scene)
+    eng.set_render_info(width=128, height=128, samples=8, batch_size=4)
 desc, rp = eng.scene_desc(), eng.render_params()
+rp.flags |= flags
 res = {}
 for label, lib in (("cuda", capi.load_cuda()), ("oracle", capi.load_oracle())):
     ctx = capi.Context(lib); ctx.upload_scene(desc); ctx.build_accel(); res[label] = ctx.render(rp); print(label, ctx.stats()["segments"]); ctx.close()

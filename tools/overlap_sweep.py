@@ -12,7 +12,7 @@ from vviewer_b200 import capi
 scene, batches = sys.argv[1], int(sys.argv[2])
 eng = capi.HostEngine()
 eng.build_scene(scene)
-ctx = capi.Context(capi.load_cuda())
+ctx = capi.Context(capi.load_ptc(os.environ["PTC_LIB"]) if os.environ.get("PTC_LIB") else capi.load_cuda())  # PTC_LIB: experimental build variants (tools only)
 ctx.upload_scene(eng.scene_desc()); ctx.build_accel()
 rp = eng.render_params()
 rp.samples = 3 * rp.batch_size
@@ -23,7 +23,7 @@ for rep in range(2):
     ctx.render(rp, want_aovs=False)
     st = ctx.stats()
     best = max(best, st["segments"] / st["render_ms"] / 1e3)
-print("%%-8s %%-10s %%8.1f Mseg/s  %%7.2f ms/batch" %% (os.environ.get("PTC_OVERLAP", "default"), scene, best, st["segments"] / best / 1e3 / batches))
+print(os.path.basename(os.environ.get("PTC_LIB", "")), "%%-8s %%-10s %%8.1f Mseg/s  %%7.2f ms/batch" %% (os.environ.get("PTC_OVERLAP", "default"), scene, best, st["segments"] / best / 1e3 / batches))
 ''' % ROOT
 
 scene = sys.argv[1] if len(sys.argv) > 1 else "Atrium"

@@ -4,7 +4,7 @@
  * command line the reference lacks (SURVEY.md §5 "Config / flags").
  *
  *   offlinerender --scene Atrium [--width W --height H --spp N --batch B --depth D] [--out name]
- *                 [--png] [--exposure E] [--all-files] [--texsize T] [--scale S] [--camera 0|1] [--sampler default|sobol] [--list]
+ *                 [--png] [--exposure E] [--all-files] [--texsize T] [--scale S] [--camera 0|1] [--sampler default|sobol] [--env-importance] [--list]
  */
 #include <cstdio>
 #include <cstdlib>
@@ -19,7 +19,7 @@ int main(int argc, char **argv) {
     std::string scene = "Cornell", out, backend;
     scenes::Options opt;
     int width = 0, height = 0, spp = 0, batch = 0, depth = 0;
-    bool png = false, allFiles = false, sobol = false;
+    bool png = false, allFiles = false, sobol = false, envImportance = false;
     float exposure = 0.0f;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -38,6 +38,7 @@ int main(int argc, char **argv) {
         else if (a == "--scale") opt.scale = (float)std::atof(next());
         else if (a == "--camera") opt.camera = std::atoi(next());
         else if (a == "--sampler") sobol = std::string(next()) == "sobol";
+        else if (a == "--env-importance") envImportance = true;
         else if (a == "--backend") backend = next(); /* any library exporting include/ptc.h; default = CUDA */
         else if (a == "--list") {
             for (auto &n : scenes::list()) std::printf("%s\n", n.c_str());
@@ -69,6 +70,7 @@ int main(int argc, char **argv) {
     ri.exposure = exposure;
     if (allFiles) ri.writeAllFiles = true;
     ri.lowDiscrepancySampler = sobol;
+    ri.environmentImportanceSampling = envImportance;
     pt.render();
     const ptc_stats &st = pt.lastStats();
     std::printf("{\"backend\": \"%s\", \"scene\": \"%s\", \"width\": %u, \"height\": %u, \"spp\": %u, \"segments\": %llu, \"shadow_rays\": %llu, "

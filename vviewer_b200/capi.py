@@ -94,12 +94,13 @@ PTC_SPLIT_NONE, PTC_SPLIT_TILE, PTC_SPLIT_SAMPLE = 0, 1, 2
 PTC_FLAG_WORLD_ORIGIN_PROBE_PDF = 1
 PTC_FLAG_TIME_KERNELS = 2
 PTC_FLAG_SAMPLER_SOBOL = 4
+PTC_FLAG_ENV_IMPORTANCE = 8
 PTC_HIERARCHY_LBVH, PTC_HIERARCHY_PLOC = 0, 1
 
 # every symbol include/ptc.h declares
 PTC_SYMBOLS = ["ptc_create", "ptc_destroy", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_set_build_options", "ptc_build_accel", "ptc_render",
                "ptc_render_device", "ptc_progress", "ptc_get_stats", "ptc_trace_closest", "ptc_get_lbvh", "ptc_get_wide_bvh", "ptc_bsdf_eval",
-               "ptc_bsdf_sample", "ptc_sampler_points", "ptc_env_lookup"]
+               "ptc_bsdf_sample", "ptc_sampler_points", "ptc_env_lookup", "ptc_env_sample", "ptc_env_pdf"]
 VH_SYMBOLS = ["vh_engine_create", "vh_engine_destroy", "vh_backend_ok", "vh_last_error", "vh_scene_list", "vh_build_scene",
               "vh_set_render_info", "vh_get_render_info", "vh_scene_desc", "vh_render_params", "vh_render_to_memory", "vh_render",
               "vh_get_stats", "vh_read_hdr", "vh_write_hdr", "vh_import_model", "vh_add_model", "vh_import_scene", "vh_export_scene",
@@ -147,6 +148,10 @@ def _declare_ptc(lib):
     lib.ptc_sampler_points.restype = C.c_int
     lib.ptc_env_lookup.argtypes = [vp, C.c_int, vp, vp]
     lib.ptc_env_lookup.restype = C.c_int
+    lib.ptc_env_sample.argtypes = [vp, C.c_int, vp, vp, vp]
+    lib.ptc_env_sample.restype = C.c_int
+    lib.ptc_env_pdf.argtypes = [vp, C.c_int, vp, vp]
+    lib.ptc_env_pdf.restype = C.c_int
     return lib
 
 
@@ -367,6 +372,18 @@ class Context:
         out = np.zeros_like(dirs)
         self._check(self.lib.ptc_env_lookup(self.ctx, dirs.shape[0], np_ptr(dirs), np_ptr(out)), "ptc_env_lookup")
         return out
+
+    def env_sample(self, u01):
+        u01 = np.ascontiguousarray(u01, np.float32).reshape(-1, 2)
+        dirs, pdf = np.zeros((u01.shape[0], 3), np.float32), np.zeros(u01.shape[0], np.float32)
+        self._check(self.lib.ptc_env_sample(self.ctx, u01.shape[0], np_ptr(u01), np_ptr(dirs), np_ptr(pdf)), "ptc_env_sample")
+        return dirs, pdf
+
+    def env_pdf(self, dirs):
+        dirs = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        pdf = np.zeros(dirs.shape[0], np.float32)
+        self._check(self.lib.ptc_env_pdf(self.ctx, dirs.shape[0], np_ptr(dirs), np_ptr(pdf)), "ptc_env_pdf")
+        return pdf
 
 
 class HostEngine:

@@ -70,6 +70,7 @@ struct DScene {
     const cudaTextureObject_t *texClasses; /* one LAYERED texture object per (width, height, sRGB) class */
     const uint32_t *texRef;                /* per texture: class << 16 | layer, or TEX_WHITE */
     cudaTextureObject_t cubemap;
+    const float *envCdfV, *envCdfU; /* PTC_FLAG_ENV_IMPORTANCE tables (envdist.cuh), nullptr without an environment */
     uint32_t nInstances, nMaterials, nLightInstances, nTextures;
     uint32_t hasCubemap;
     /* acceleration structure (see lbvh.cuh) */

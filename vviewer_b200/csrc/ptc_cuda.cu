@@ -50,6 +50,7 @@ struct ptc_ctx {
     cudaArray_t cubeArray = nullptr;
     cudaTextureObject_t cubeTex = 0;
     uint32_t cubeN = 0;
+    DBuf<float> envCdfV, envCdfU; /* PTC_FLAG_ENV_IMPORTANCE tables, valid while cubeTex is */
     uint32_t nInstances = 0, nMaterials = 0, nLightInstances = 0, nTextures = 0, nWorldTris = 0;
     bool anyEmissive = false, anyTransparent = false, anyVolumeChange = false;
     bool sceneUploaded = false, accelBuilt = false;
@@ -156,6 +157,8 @@ DScene makeDScene(ptc_ctx *c) {
     s.texRef = c->texRef.p;
     s.shading = c->accel.shading.p;
     s.cubemap = c->cubeTex;
+    s.envCdfV = c->cubeTex ? c->envCdfV.p : nullptr;
+    s.envCdfU = c->cubeTex ? c->envCdfU.p : nullptr;
     s.nInstances = c->nInstances;
     s.nMaterials = c->nMaterials;
     s.nLightInstances = c->nLightInstances;
@@ -297,6 +300,12 @@ void createCubemap(ptc_ctx *c, const ptc_env &env) {
     cudaDestroyTextureObject(eqTex);
     cudaFreeArray(eqArray);
     c->cubeN = N;
+    /* importance tables of the same input (host pass, ~10 ms for 3072 x 1536; kept with the cubemap by ptc_env.uid) */
+    std::vector<float> cdfV, cdfU;
+    envd::buildTables(env.equirect_rgba, env.width, env.height, cdfV, cdfU);
+    c->envCdfV.upload(cdfV.data(), cdfV.size(), c->stream);
+    c->envCdfU.upload(cdfU.data(), cdfU.size(), c->stream);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
 }
 
 /* L2 persistence for what every ray touches: the wide nodes (breadth first, so the top levels come first) and as much of
@@ -436,6 +445,8 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     rc.orthoW = rp->ortho_width;
     rc.orthoH = rp->ortho_height;
     rc.totalLights = c->nLightInstances;
+    rc.envLight = ((rp->flags & PTC_FLAG_ENV_IMPORTANCE) && c->cubeTex && (rp->scene.background[3] == 1.0f || rp->scene.background[3] == 2.0f)) ? 1u : 0u;
+    rc.totalLights += rc.envLight;
     rc.flags = rp->flags;
     rc.nPixLocal = nPixLocal;
     rc.pixmap = pixmapPtr;
@@ -957,6 +968,44 @@ PTC_API int ptc_env_lookup(ptc_ctx *c, int n, const float *dirs, float *out_rgb)
     wf::k_env_lookup<<<(n + 255) / 256, 256, 0, s>>>(sc, n, dD.p, dO.p);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out_rgb, dO.p, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+    PTC_GUARD_END(c)
+}
+
+PTC_API int ptc_env_sample(ptc_ctx *c, int n, const float *u01, float *out_dirs, float *out_pdf) {
+    if (!c || !c->stream) return fail(c, "context has no CUDA device");
+    if (!c->cubeTex || !c->envCdfV.p) return fail(c, "no environment");
+    if (n <= 0) return 0;
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    DBuf<float> dU, dD, dP;
+    dU.upload(u01, (size_t)n * 2, s);
+    dD.alloc((size_t)n * 3);
+    dP.alloc((size_t)n);
+    wf::k_env_sample<<<(n + 255) / 256, 256, 0, s>>>(makeDScene(c), n, dU.p, dD.p, dP.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_dirs, dD.p, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(out_pdf, dP.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+    PTC_GUARD_END(c)
+}
+
+PTC_API int ptc_env_pdf(ptc_ctx *c, int n, const float *dirs, float *out_pdf) {
+    if (!c || !c->stream) return fail(c, "context has no CUDA device");
+    if (!c->cubeTex || !c->envCdfV.p) return fail(c, "no environment");
+    if (n <= 0) return 0;
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    DBuf<float> dD, dP;
+    dD.upload(dirs, (size_t)n * 3, s);
+    dP.alloc((size_t)n);
+    wf::k_env_pdf<<<(n + 255) / 256, 256, 0, s>>>(makeDScene(c), n, dD.p, dP.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out_pdf, dP.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return 0;
     PTC_GUARD_END(c)

@@ -19,7 +19,9 @@
 namespace trv {
 
 #define TRV_STACK 88        /* local-memory spill entries (binary LBVH depth bounds the wide depth: <= 63 + 32 levels) */
+#ifndef TRV_SHARED_STACK
 #define TRV_SHARED_STACK 8  /* shared-memory entries per thread (8 B each) */
+#endif
 #define TRV_BLOCK 128 /* threads per block of every kernel that traverses */
 #define TRV_DONE 0x7fffffff
 

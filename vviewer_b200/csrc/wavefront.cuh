@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "bsdf.cuh"
 #include "traverse.cuh"
+#include "envdist.cuh"
 
 namespace wf {
 
@@ -51,7 +52,8 @@ struct RenderConst {
     uint32_t width, height, depth, totalSamples;
     uint32_t cameraType;
     float orthoW, orthoH;
-    uint32_t totalLights;
+    uint32_t totalLights;    /* light instances, + 1 when the environment is light-sampled */
+    uint32_t envLight;       /* PTC_FLAG_ENV_IMPORTANCE and an HDRI environment: light index totalLights - 1 is the environment */
     uint32_t flags;
     uint32_t nPixLocal;      /* pixels rendered by this rank */
     const uint32_t *pixmap;  /* local pixel -> global pixel, or nullptr = identity */
@@ -177,6 +179,19 @@ PTC_D LightSample sampleLight(const DScene &sc, const RenderConst &rc, Rng &rng,
     if (totalLights == 0u) return ls;
     const float pick = 1.0f / (float)totalLights;
     uint32_t li = min((uint32_t)(rnd(rng) * (float)totalLights), totalLights - 1u);
+    if (rc.envLight && li == totalLights - 1u) {
+        /* extension (trap T3, include/ptc.h PTC_FLAG_ENV_IMPORTANCE): the environment as the last light */
+        const float2 u01 = rnd2(rng);
+        const envd::DeviceTables et{sc.envCdfV, sc.envCdfU};
+        float eu, ev, puv;
+        envd::sampleUV(et, u01.x, u01.y, eu, ev, puv);
+        ls.dir = envd::direction(eu, ev);
+        ls.radiance = envFetch(sc, ls.dir) * (rc.sd.background[3] == 1.0f ? rc.sd.exposure[1] : 1.0f);
+        ls.pdf = pick * envd::solidAnglePdf(puv, ev);
+        ls.delta = false;
+        if (!(ls.pdf > 0.0f)) ls.radiance = f3(0.0f);
+        return ls;
+    }
     const ptc_light_instance *L = &sc.lightInstances[li];
     const uint32_t type = __ldg(&L->info[3]);
     if (type == 0u) { /* point */
@@ -525,7 +540,9 @@ __global__ void __launch_bounds__(128, 6) k_shade(Wave w, const __grid_constant_
                 rng.index = firstSample + slot / rc.nPixLocal;
             }
             flags = (flags & ~PF_DEPTH_MASK) | (bounce & PF_DEPTH_MASK);
-            float3 beta = f3(ldS(&w.beta[slot]));
+            const float4 beta4 = ldS(&w.beta[slot]);
+            float3 beta = f3(beta4);
+            float lastPdf = beta4.w; /* density of the direction this segment was sampled with (0 = camera ray) */
             float3 radiance = f3(ldS(&w.radiance[slot]));
             const float3 rayDir = dir;
             const int32_t triPos = __float_as_int(h.w);
@@ -658,15 +675,23 @@ __global__ void __launch_bounds__(128, 6) k_shade(Wave w, const __grid_constant_
                         stS(&w.aovAlbedo[slot], make_float4(aov.x, aov.y, aov.z, 0.0f));
                         stS(&w.aovNormal[slot], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
                     }
+                    /* environment found by a sampled direction while it is also light-sampled: power heuristic */
+                    if (rc.envLight && lastPdf > 0.0f && (bg[3] == 1.0f || (bg[3] == 2.0f && !first))) {
+                        const float2 uv = envd::equirectUV(normalize(rayDir));
+                        const envd::DeviceTables et{sc.envCdfV, sc.envCdfU};
+                        const float pl = (1.0f / (float)rc.totalLights) * envd::solidAnglePdf(envd::pdfUV(et, uv.x, uv.y), uv.y);
+                        col = col * powerHeuristic(lastPdf, pl);
+                    }
                     radiance += col * beta;
                 }
             }
             if (doRoulette && !stop) stop = roulette(rng, bounce, beta);
+            if (rq.probe) lastPdf = rq.prPdf; /* a new direction was sampled (surface or medium) */
             /* requests that can only return black are dropped (result-identical) */
             if (rq.probe && !sc.anyEmissive) rq.probe = false;
             stS(&w.orgRng[slot], make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng.s)));
             stS(&w.dirFlags[slot], make_float4(dir.x, dir.y, dir.z, __uint_as_float(flags)));
-            stS(&w.beta[slot], make_float4(beta.x, beta.y, beta.z, 0.0f));
+            stS(&w.beta[slot], make_float4(beta.x, beta.y, beta.z, lastPdf));
             stS(&w.radiance[slot], make_float4(radiance.x, radiance.y, radiance.z, 0.0f));
             if (rq.shadow) {
                 stS(&w.shOrgTmax[slot], make_float4(rq.shOrigin.x, rq.shOrigin.y, rq.shOrigin.z, rq.shTmax));
@@ -989,6 +1014,26 @@ __global__ void k_env_lookup(const __grid_constant__ DScene sc, int n, const flo
     out[i * 3] = c.x;
     out[i * 3 + 1] = c.y;
     out[i * 3 + 2] = c.z;
+}
+
+__global__ void k_env_sample(const __grid_constant__ DScene sc, int n, const float *u01, float *dirs, float *pdf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const envd::DeviceTables et{sc.envCdfV, sc.envCdfU};
+    float u, v, puv;
+    envd::sampleUV(et, u01[2 * i], u01[2 * i + 1], u, v, puv);
+    const float3 d = envd::direction(u, v);
+    dirs[i * 3] = d.x;
+    dirs[i * 3 + 1] = d.y;
+    dirs[i * 3 + 2] = d.z;
+    pdf[i] = envd::solidAnglePdf(puv, v);
+}
+__global__ void k_env_pdf(const __grid_constant__ DScene sc, int n, const float *dirs, float *pdf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const envd::DeviceTables et{sc.envCdfV, sc.envCdfU};
+    const float2 uv = envd::equirectUV(normalize(f3(dirs[i * 3], dirs[i * 3 + 1], dirs[i * 3 + 2])));
+    pdf[i] = envd::solidAnglePdf(envd::pdfUV(et, uv.x, uv.y), uv.y);
 }
 
 /* ------------------------------------------------------------------ equirect -> cubemap (skyboxCubemapWrite.frag.glsl:12-15) */

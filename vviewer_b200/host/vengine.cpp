@@ -678,6 +678,7 @@ ptc_render_params CudaRendererPathTracing::makeRenderParams() {
     rp.rank = 0;
     rp.world = 1;
     rp.flags = renderInfo().lowDiscrepancySampler ? PTC_FLAG_SAMPLER_SOBOL : 0u;
+    if (renderInfo().environmentImportanceSampling) rp.flags |= PTC_FLAG_ENV_IMPORTANCE;
     return rp;
 }
 

@@ -695,6 +695,9 @@ public:
         /* extension: the reference selects its sampler at shader-compile time (SAMPLING_RTGEMS / SAMPLING_PMJ in
          * defines_pt.glsl); here it is a render setting.  true = low-discrepancy (PTC_FLAG_SAMPLER_SOBOL) */
         bool lowDiscrepancySampler = false;
+        /* extension, off for parity (the reference never light-samples the environment, lightSampling.glsl:101-106):
+         * luminance importance sampling of the HDRI environment + MIS (PTC_FLAG_ENV_IMPORTANCE) */
+        bool environmentImportanceSampling = false;
     };
     virtual ~RendererPathTracing() {}
     RenderInfo &renderInfo() { return m_renderInfo; }
