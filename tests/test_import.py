@@ -406,3 +406,21 @@ def test_scene_import_errors(capi, engine, tmp_path):
                              "materials": [{"name": "m", "type": "GLASS"}], "lights": []}))
     with pytest.raises(RuntimeError):  # unknown material type (Import.cpp:398-401)
         engine.import_scene(str(p))
+
+
+def test_offlinerender_scene_file_entry(capi, tmp_path):
+    """the data-driven entry: `offlinerender --scene file.json` renders what `--scene Recipe --export-scene dir` wrote"""
+    import subprocess
+    exe = os.path.join(capi.LIB_DIR, "offlinerender")
+    common = ["--backend", capi.ORACLE_LIB, "--width", "48", "--height", "48", "--spp", "8", "--batch", "4"]
+    a = subprocess.run([exe, "--scene", "MeshLight", "--export-scene", str(tmp_path / "ml"), "--out", str(tmp_path / "a")] + common,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
+    assert a.returncode == 0, a.stderr
+    b = subprocess.run([exe, "--scene", str(tmp_path / "ml" / "scene.json"), "--out", str(tmp_path / "b")] + common,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
+    assert b.returncode == 0, b.stderr
+    sa, sb = json.loads(a.stdout.strip().splitlines()[-1]), json.loads(b.stdout.strip().splitlines()[-1])
+    assert sa["segments"] == sb["segments"] and sa["triangles"] == sb["triangles"] and sa["probe_rays"] == sb["probe_rays"]
+    assert np.array_equal(capi.read_hdr(str(tmp_path / "a.hdr")), capi.read_hdr(str(tmp_path / "b.hdr")))
+    bad = subprocess.run([exe, "--scene", str(tmp_path / "nothing.json")] + common, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
+    assert bad.returncode == 2 and "cannot import" in bad.stderr

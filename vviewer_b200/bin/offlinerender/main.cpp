@@ -3,7 +3,9 @@
  * src/bin/offlinerender/main.cpp:13-25 (create engine, initResources, create a scene, render) with the
  * command line the reference lacks (SURVEY.md §5 "Config / flags").
  *
- *   offlinerender --scene Atrium [--width W --height H --spp N --batch B --depth D] [--out name]
+ *   offlinerender --scene Atrium | --scene path/to/scene.json   (a recipe name, or a scene file of core/io/Import.cpp's format)
+ *                 [--export-scene DIR]  (writes DIR/scene.json + DIR/assets like Scene::exportScene, then renders)
+ *                 [--width W --height H --spp N --batch B --depth D] [--out name]
  *                 [--png] [--exposure E] [--all-files] [--texsize T] [--scale S] [--camera 0|1] [--sampler default|sobol] [--env-importance] [--list]
  */
 #include <cstdio>
@@ -16,7 +18,7 @@
 using namespace vengine;
 
 int main(int argc, char **argv) {
-    std::string scene = "Cornell", out, backend;
+    std::string scene = "Cornell", out, backend, exportDir;
     scenes::Options opt;
     int width = 0, height = 0, spp = 0, batch = 0, depth = 0;
     bool png = false, allFiles = false, sobol = false, envImportance = false;
@@ -39,6 +41,7 @@ int main(int argc, char **argv) {
         else if (a == "--camera") opt.camera = std::atoi(next());
         else if (a == "--sampler") sobol = std::string(next()) == "sobol";
         else if (a == "--env-importance") envImportance = true;
+        else if (a == "--export-scene") exportDir = next();
         else if (a == "--backend") backend = next(); /* any library exporting include/ptc.h; default = CUDA */
         else if (a == "--list") {
             for (auto &n : scenes::list()) std::printf("%s\n", n.c_str());
@@ -55,9 +58,23 @@ int main(int argc, char **argv) {
         std::fprintf(stderr, "path tracing backend unavailable: %s\n", pt.lastError().c_str());
         return 1;
     }
-    if (!scenes::build(engine, scene, opt)) {
-        std::fprintf(stderr, "unknown scene '%s' (use --list)\n", scene.c_str());
+    const bool isFile = scene.size() > 5 && scene.compare(scene.size() - 5, 5, ".json") == 0;
+    if (isFile) {
+        std::string err;
+        if (!engine.importScene(scene, &err)) {
+            std::fprintf(stderr, "cannot import %s: %s\n", scene.c_str(), err.c_str());
+            return 2;
+        }
+    } else if (!scenes::build(engine, scene, opt)) {
+        std::fprintf(stderr, "unknown scene '%s' (use --list, or pass a scene.json)\n", scene.c_str());
         return 2;
+    }
+    if (!exportDir.empty()) {
+        std::string err;
+        if (!engine.exportScene(exportDir, &err)) {
+            std::fprintf(stderr, "cannot export to %s: %s\n", exportDir.c_str(), err.c_str());
+            return 2;
+        }
     }
     auto &ri = pt.renderInfo();
     if (width > 0) ri.width = (uint32_t)width;

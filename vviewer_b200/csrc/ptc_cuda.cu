@@ -72,7 +72,7 @@ struct ptc_ctx {
     cudaEvent_t evItem[RING] = {};
     /* resident blocks per SM of the traversal / shading kernels while two wavefronts overlap; 0 = one wavefront at a time,
      * the default: measured on the bench scene the overlap LOSES (2069 Mseg/s alone; 4+3 blocks 2030, 5+2 1888, 6+1 1604,
-     * profiles/r1_v4_overlap_sweep.log) - k_shade needs >= 3 blocks per SM to keep DRAM busy and k_extend loses as much
+     * profiles/r1_v4_kernel_experiments.log) - k_shade needs >= 3 blocks per SM to keep DRAM busy and k_extend loses as much
      * with 4 as the overlap wins.  PTC_OVERLAP=t,s turns it on for experiments. */
     int overlapTrace = 0, overlapShade = 0;
 
@@ -169,6 +169,7 @@ DScene makeDScene(ptc_ctx *c) {
     s.nTris = c->accelBuilt ? c->accel.n : 0u;
     s.nWideNodes = c->accel.nWide;
     s.prmtMagic = 0x47000000u;
+    s.prmtMagicH = 0x64006400u;
     s.anyEmissive = c->anyEmissive ? 1u : 0u;
     s.anyTransparent = c->anyTransparent ? 1u : 0u;
     s.anyVolume = c->anyVolumeChange ? 1u : 0u;

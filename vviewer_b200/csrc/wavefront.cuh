@@ -443,7 +443,10 @@ struct ExtendPolicy {
         return false;
     }
 };
-__global__ void __launch_bounds__(TRV_BLOCK, 8) k_extend(Wave w, const __grid_constant__ DScene sc, uint32_t bounce, ExtendTune tune) {
+#ifndef TRV_EXTEND_MINBLOCKS
+#define TRV_EXTEND_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(TRV_BLOCK, TRV_EXTEND_MINBLOCKS) k_extend(Wave w, const __grid_constant__ DScene sc, uint32_t bounce, ExtendTune tune) {
     TRV_DECLARE_STACK(stack);
     __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
     ExtendPolicy pol(w, bounce);
