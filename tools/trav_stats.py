@@ -7,7 +7,7 @@ batches = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 scene = sys.argv[2] if len(sys.argv) > 2 else "Atrium"
 eng = capi.HostEngine()
 eng.build_scene(scene, texture_size=256)
-lib = capi.load_ptc(os.path.join(capi.LIB_DIR, "libptc_cuda_stats.so"))
+lib = capi.load_ptc(os.environ.get("PTC_LIB") or os.path.join(capi.LIB_DIR, "libptc_cuda_stats.so"))
 ctx = capi.Context(lib)
 ctx.upload_scene(eng.scene_desc())
 ctx.build_accel()

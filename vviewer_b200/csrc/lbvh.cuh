@@ -150,7 +150,12 @@ __global__ void k_morton(const float4 *__restrict__ boundsLo, const float4 *__re
     ids[i] = i;
 }
 
+#ifndef WIDE_LEAF_TRIS
 #define WIDE_LEAF_TRIS 3 /* triangles per leaf of the wide BVH */
+#endif
+#ifndef WIDE_PHASES
+#define WIDE_PHASES 2 /* 2: free slots are filled by splitting leaves down to single triangles */
+#endif
 
 /* common-prefix length of sorted keys i and j; equal keys fall back to the index (Karras 2012, section 4) */
 PTC_D int delta(const uint64_t *__restrict__ keys, int64_t n, int64_t i, int64_t j) {
@@ -380,7 +385,7 @@ __global__ void k_wide_select(uint32_t n, uint32_t count, uint32_t levelBase, co
     list[0] = root;
     tris[0] = subTris(root, n, subCount);
     area[0] = halfArea(nodeLo[root], nodeHi[root]);
-    for (int phase = 0; phase < 2; phase++) {
+    for (int phase = 0; phase < WIDE_PHASES; phase++) {
         const uint32_t thr = phase == 0 ? (uint32_t)WIDE_LEAF_TRIS : 1u;
         while (len < 8) {
             int bi = -1;
