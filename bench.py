@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--texsize", type=int, default=1024)
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-spp", type=int, default=1, help="samples per pixel of one CPU-baseline step")
+    ap.add_argument("--cpu-spp", type=int, default=1, help="samples per pixel of one step of the reference arm (--impl reference)")
+    ap.add_argument("--cpu-baseline-spp", type=int, default=12, help="samples per pixel of the cpu_baseline leg of the CUDA arm (about 10-15 s of CPU work)")
     return ap.parse_args()
 
 
@@ -282,11 +283,11 @@ def run_cuda(args, rank, world, local_rank):
         octx.upload_scene(desc)
         octx.build_accel()
         rp = eng.render_params()
-        rp.samples = rp.batch_size = max(1, args.cpu_spp)
+        rp.samples = rp.batch_size = max(1, args.cpu_baseline_spp)
         octx.render(rp, want_aovs=False)
         ost = octx.stats()
         cpu = {"value": ost["segments"] / ost["render_ms"] / 1e3, "unit": "Msegments/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "%dx%d x %d spp (1/%d of a step), %.1f s" % (W, H, rp.samples, B // max(rp.samples, 1), ost["render_ms"] / 1e3)}
+               "sample": "%dx%d x %d spp (%d/%d of a step), %.1f s of all host cores (OpenMP over image rows)" % (W, H, rp.samples, rp.samples, B, ost["render_ms"] / 1e3)}
         octx.close()
 
     ms_per_step = dev_ms / args.steps
