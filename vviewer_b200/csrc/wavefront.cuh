@@ -546,7 +546,9 @@ __global__ void __launch_bounds__(128, 6) k_shade(Wave w, const __grid_constant_
             const float4 beta4 = ldS(&w.beta[slot]);
             float3 beta = f3(beta4);
             float lastPdf = beta4.w; /* density of the direction this segment was sampled with (0 = camera ray) */
-            float3 radiance = f3(ldS(&w.radiance[slot]));
+            float3 radiance = f3(0.0f); /* what THIS event adds (at most one term: first-hit emission or the miss); the slot's running
+                                           sum is only read and written when there is something to add: 32 B of state traffic less per segment */
+            bool radianceAdded = false;
             const float3 rayDir = dir;
             const int32_t triPos = __float_as_int(h.w);
             bool stop = false;
@@ -596,7 +598,8 @@ __global__ void __launch_bounds__(128, 6) k_shade(Wave w, const __grid_constant_
                             stS(&w.aovNormal[slot], make_float4(nn.x, nn.y, nn.z, 0.0f));
                         }
                         if (first && !isBlackEps(emissive, lambert ? 0.05f : 0.1f) && !flipped) {
-                            radiance += emissive * beta; /* emission only at the first surface (trap T2) */
+                            radiance = emissive * beta; /* emission only at the first surface (trap T2) */
+                            radianceAdded = true;
                             stop = true;
                             doRoulette = false;
                         } else {
@@ -685,24 +688,31 @@ __global__ void __launch_bounds__(128, 6) k_shade(Wave w, const __grid_constant_
                         const float pl = (1.0f / (float)rc.totalLights) * envd::solidAnglePdf(envd::pdfUV(et, uv.x, uv.y), uv.y);
                         col = col * powerHeuristic(lastPdf, pl);
                     }
-                    radiance += col * beta;
+                    radiance = col * beta;
+                    radianceAdded = true;
                 }
             }
             if (doRoulette && !stop) stop = roulette(rng, bounce, beta);
             if (rq.probe) lastPdf = rq.prPdf; /* a new direction was sampled (surface or medium) */
             /* requests that can only return black are dropped (result-identical) */
             if (rq.probe && !sc.anyEmissive) rq.probe = false;
-            stS(&w.orgRng[slot], make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng.s)));
-            stS(&w.dirFlags[slot], make_float4(dir.x, dir.y, dir.z, __uint_as_float(flags)));
-            stS(&w.beta[slot], make_float4(beta.x, beta.y, beta.z, lastPdf));
-            stS(&w.radiance[slot], make_float4(radiance.x, radiance.y, radiance.z, 0.0f));
+            alive = !stop && !lastBounce;
+            /* a finished path's state is never read again (a probe request still needs the new origin and direction) */
+            if (alive || rq.probe) {
+                stS(&w.orgRng[slot], make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng.s)));
+                stS(&w.dirFlags[slot], make_float4(dir.x, dir.y, dir.z, __uint_as_float(flags)));
+            }
+            if (alive) stS(&w.beta[slot], make_float4(beta.x, beta.y, beta.z, lastPdf));
+            if (radianceAdded) {
+                const float3 sum = f3(ldS(&w.radiance[slot])) + radiance; /* same single addition as before: bit-identical */
+                stS(&w.radiance[slot], make_float4(sum.x, sum.y, sum.z, 0.0f));
+            }
             if (rq.shadow) {
                 stS(&w.shOrgTmax[slot], make_float4(rq.shOrigin.x, rq.shOrigin.y, rq.shOrigin.z, rq.shTmax));
                 stS(&w.shDirVol[slot], make_float4(rq.shDir.x, rq.shDir.y, rq.shDir.z, __uint_as_float(flags)));
                 stS(&w.shContrib[slot], make_float4(rq.shContrib.x, rq.shContrib.y, rq.shContrib.z, 0.0f));
             }
             if (rq.probe) stS(&w.prBetaPdf[slot], make_float4(rq.prBeta.x, rq.prBeta.y, rq.prBeta.z, rq.prPdf));
-            alive = !stop && !lastBounce;
         }
         queuePush(qNext, cntNext, alive, slot);
         queuePush(w.qShadow, cntShadow, rq.shadow, slot);
