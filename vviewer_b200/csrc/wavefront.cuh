@@ -511,7 +511,12 @@ PTC_D bool roulette(Rng &rng, uint32_t depth, float3 &beta) {
     return false;
 }
 
-__global__ void __launch_bounds__(128, 6) k_shade(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
+/* 8 blocks per SM (64 registers, 240 B of spills) beats 6 (80 registers, 80 B) and 5 (96 registers, none): the kernel is DRAM bound and
+ * wants warps in flight more than registers - measured 4: 2027, 5: 2123, 6: 2081, 7: 2126, 8: 2139, 9: 2115, 10: 2097, 12: 2011 Mseg/s */
+#ifndef SHADE_MINBLOCKS
+#define SHADE_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, SHADE_MINBLOCKS) k_shade(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
                                                          uint32_t firstSample) {
     const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_ACTIVE];
     const uint32_t *__restrict__ q = w.queue[bounce & 1u];
@@ -809,7 +814,12 @@ struct ShadowPolicy {
         return finish(true);
     }
 };
-__global__ void __launch_bounds__(TRV_BLOCK, 6) k_shadow(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
+/* shadow / probe chains: 7 blocks per SM (72 registers) - measured on fog / progressive / Cornell: 5: 795 / 1462 / 1985, 6: 826 / 1500 / 2036,
+ * 7: 847 / 1529 / 2071, 8: 845 / 1523 / 2027 Mseg/s */
+#ifndef CHAIN_MINBLOCKS
+#define CHAIN_MINBLOCKS 7
+#endif
+__global__ void __launch_bounds__(TRV_BLOCK, CHAIN_MINBLOCKS) k_shadow(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
                                                       ExtendTune tune) {
     TRV_DECLARE_STACK(stack);
     __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
@@ -913,7 +923,7 @@ struct ProbePolicy {
         return finish(em, pdf);
     }
 };
-__global__ void __launch_bounds__(TRV_BLOCK, 6) k_probe(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
+__global__ void __launch_bounds__(TRV_BLOCK, CHAIN_MINBLOCKS) k_probe(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
                                                      ExtendTune tune) {
     TRV_DECLARE_STACK(stack);
     __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
