@@ -462,7 +462,12 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     };
     const int capTrace = overlap ? c->overlapTrace : 0, capShade = overlap ? c->overlapShade : 0;
     const int gridExtend = residentGrid((const void *)wf::k_extend, TRV_BLOCK, capTrace);
-    const int gridShade = residentGrid((const void *)wf::k_shade, 128, capShade);
+    /* k_shade specialisation (wavefront.cuh): lights in the pick / media reachable */
+    const bool hasLights = rc.totalLights > 0, hasVolumes = c->anyVolumeChange || rp->scene.volumes[0] != -1.0f;
+    using ShadeFn = void (*)(wf::Wave, const DScene, const wf::RenderConst, uint32_t, uint32_t);
+    const ShadeFn shadeFn = hasLights ? (hasVolumes ? (ShadeFn)wf::k_shade<true, true> : (ShadeFn)wf::k_shade<true, false>)
+                                      : (hasVolumes ? (ShadeFn)wf::k_shade<false, true> : (ShadeFn)wf::k_shade<false, false>);
+    const int gridShade = residentGrid((const void *)shadeFn, 128, capShade);
     const int gridShadow = residentGrid((const void *)wf::k_shadow, TRV_BLOCK, capTrace);
     const int gridProbe = residentGrid((const void *)wf::k_probe, TRV_BLOCK, capTrace);
     uint64_t launches = 0, traceLaunches = 0;
@@ -514,7 +519,7 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
                 launches++;
                 for (uint32_t d = 0; d < rp->depth; d++) {
                     timed(traceMs, st, [&] { wf::k_extend<<<gridExtend, TRV_BLOCK, 0, st>>>(w, sc, d, c->tune); });
-                    timed(shadeMs, st, [&] { wf::k_shade<<<gridShade, 128, 0, st>>>(w, sc, rc, d, b * rp->batch_size + s0); });
+                    timed(shadeMs, st, [&] { shadeFn<<<gridShade, 128, 0, st>>>(w, sc, rc, d, b * rp->batch_size + s0); });
                     launches += 2;
                     traceLaunches++;
                     if (rc.totalLights > 0) {

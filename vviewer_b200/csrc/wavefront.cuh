@@ -516,6 +516,10 @@ PTC_D bool roulette(Rng &rng, uint32_t depth, float3 &beta) {
 #ifndef SHADE_MINBLOCKS
 #define SHADE_MINBLOCKS 8
 #endif
+/* LIGHTS: the light pick is not empty (rc.totalLights > 0); VOLUMES: a path can be inside a medium (camera volume or an instance that
+ * changes it).  The common "environment only, no media" scene gets a kernel without the light-sampling and free-flight code (fewer
+ * registers under the same launch bound); the instantiations are result-identical where their preconditions hold. */
+template <bool LIGHTS, bool VOLUMES>
 __global__ void __launch_bounds__(128, SHADE_MINBLOCKS) k_shade(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
                                                          uint32_t firstSample) {
     const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_ACTIVE];
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(128, SHADE_MINBLOCKS) k_shade(Wave w, const __
                 fr.t = s.t;
                 const bool flipped = fixFrame(fr, rayDir);
                 bool sampledMedium = false;
-                if (flags & PF_INVOL) sampledMedium = volumeEvent(sc, rc, rng, flags, origin, dir, beta, 0.001f, h.x, rq);
+                if (VOLUMES && (flags & PF_INVOL)) sampledMedium = volumeEvent(sc, rc, rng, flags, origin, dir, beta, 0.001f, h.x, rq);
                 if (!sampledMedium) {
                     const ptc_material *mat = s.mat;
                     const float tu = s.uv.x * __ldg(&mat->uv_tiling[0]), tv = s.uv.y * __ldg(&mat->uv_tiling[1]);
@@ -578,7 +582,7 @@ __global__ void __launch_bounds__(128, SHADE_MINBLOCKS) k_shade(Wave w, const __
                         const float alpha = __ldg(&mat->albedo[3]) * texFetch(sc, __ldg(&mat->tex2[3]), tu, tv).x;
                         const float r = rnd(rng);
                         if (alpha < PT_EPSILON || r > alpha) {
-                            if (s.inst->volFront != s.inst->volBack) volumeChange(s.inst, flipped, flags);
+                            if (VOLUMES && s.inst->volFront != s.inst->volBack) volumeChange(s.inst, flipped, flags);
                             origin = s.pos;
                             dir = normalize(rayDir);
                             passThrough = true;
@@ -611,8 +615,10 @@ __global__ void __launch_bounds__(128, SHADE_MINBLOCKS) k_shade(Wave w, const __
                         } else {
                             flags |= PF_SURFACE;
                             const float3 wo = toLocal(fr, -rayDir);
-                            LightSample ls = sampleLight(sc, rc, rng, s.pos);
-                            if (!isBlack(ls.radiance)) {
+                            LightSample ls;
+                            ls.radiance = f3(0.0f);
+                            if (LIGHTS) ls = sampleLight(sc, rc, rng, s.pos);
+                            if (LIGHTS && !isBlack(ls.radiance)) {
                                 const float3 wi = toLocal(fr, ls.dir);
                                 float3 F;
                                 float bsdfPdf;
@@ -665,7 +671,7 @@ __global__ void __launch_bounds__(128, SHADE_MINBLOCKS) k_shade(Wave w, const __
                 }
             } else { /* rayPrimary.rmiss.glsl:40-106 */
                 bool sampledMedium = false;
-                if (flags & PF_INVOL) {
+                if (VOLUMES && (flags & PF_INVOL)) {
                     const float vtend = fminf((float)(uint32_t)rc.sd.volumes[2], 10000.0f);
                     sampledMedium = volumeEvent(sc, rc, rng, flags, origin, dir, beta, 0.001f, vtend, rq);
                 }
