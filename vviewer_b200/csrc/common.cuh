@@ -79,8 +79,7 @@ struct DScene {
     const float4 *shading;  /* 9 x float4 per world triangle, same order (lbvh.cuh::k_gather_shading) */
     uint32_t nTris;
     uint32_t nWideNodes;
-    uint32_t prmtMagic;  /* 0x47000000, see traverse.cuh::byteToFloat */
-    uint32_t prmtMagicH; /* 0x64006400, see traverse.cuh::pairToFloat2 */
+    uint32_t prmtMagic; /* 0x47000000, see traverse.cuh::byteToFloat */
     /* scene-level switches that let whole ray types be skipped without changing any result */
     uint32_t anyEmissive;    /* some instanced material can pass the probe's emissive test */
     uint32_t anyTransparent; /* some instanced material has the transparent flag */

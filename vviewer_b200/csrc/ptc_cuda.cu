@@ -169,7 +169,6 @@ DScene makeDScene(ptc_ctx *c) {
     s.nTris = c->accelBuilt ? c->accel.n : 0u;
     s.nWideNodes = c->accel.nWide;
     s.prmtMagic = 0x47000000u;
-    s.prmtMagicH = 0x64006400u;
     s.anyEmissive = c->anyEmissive ? 1u : 0u;
     s.anyTransparent = c->anyTransparent ? 1u : 0u;
     s.anyVolume = c->anyVolumeChange ? 1u : 0u;

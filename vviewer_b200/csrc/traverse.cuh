@@ -14,8 +14,6 @@
  * traversing (Aila & Laine 2009 "while-while" with dynamic fetch) instead of letting the warp fragment.
  */
 #pragma once
-#include <cuda_fp16.h>
-
 #include "common.cuh"
 
 namespace trv {
@@ -68,17 +66,6 @@ PTC_D float byteToFloat(uint32_t w, uint32_t magic) {
     uint32_t r;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(magic), "n"(0x7504 | (J << 4)));
     return __uint_as_float(r);
-}
-/* bytes 2 * PAIR and 2 * PAIR + 1 of w as the floats 1024 + byte: ONE byte permute builds the two halves 0x6400 | byte
- * (1024 + byte, exact in fp16), HADD2.F32 converts each on the FMA pipe.  `magicH` must hold 0x64006400 (DScene::prmtMagicH, from
- * kernel-parameter space so that PRMT keeps its immediate slot for the selector). */
-PTC_D float2 pairToFloat2(uint32_t w, uint32_t magicH, int pair) {
-    uint32_t r;
-    if (pair == 0)
-        asm("prmt.b32 %0, %1, %2, 0x5150;" : "=r"(r) : "r"(w), "r"(magicH));
-    else
-        asm("prmt.b32 %0, %1, %2, 0x5352;" : "=r"(r) : "r"(w), "r"(magicH));
-    return __half22float2(*reinterpret_cast<const __half2 *>(&r));
 }
 /* Ordered query state: finds the smallest (t, id) lexicographically greater than (t0, id0) with t < tmax.
  * Closest hit: (t0, id0) = (tmin, 0xffffffff).
@@ -169,17 +156,10 @@ struct Trav {
              * Near and far planes share a and c, so a flat box (q_near == q_far) can never come out inverted. */
             const float ax = __uint_as_float((ei & 0xffu) << 23) * idir.x, ay = __uint_as_float(((ei >> 8) & 0xffu) << 23) * idir.y,
                         az = __uint_as_float(((ei >> 16) & 0xffu) << 23) * idir.z;
-#ifdef TRV_HALF_CONV
-            const float qbias = -1024.0f; /* bytes arrive as the halves 1024 + q, see pairToFloat2 */
-#else
-            const float qbias = -32768.0f;
-#endif
-            const float cx = fmaf(qbias, ax, (n0.x - o.x) * idir.x), cy = fmaf(qbias, ay, (n0.y - o.y) * idir.y),
-                        cz = fmaf(qbias, az, (n0.z - o.z) * idir.z);
+            const float cx = fmaf(-32768.0f, ax, (n0.x - o.x) * idir.x), cy = fmaf(-32768.0f, ay, (n0.y - o.y) * idir.y),
+                        cz = fmaf(-32768.0f, az, (n0.z - o.z) * idir.z);
             const float px = fabsf(ax) * 0.0078125f, py = fabsf(ay) * 0.0078125f, pz = fabsf(az) * 0.0078125f;
             const float bnx = cx - px, bny = cy - py, bnz = cz - pz, bfx = cx + px, bfy = cy + py, bfz = cz + pz;
-            const float2 ax2 = make_float2(ax, ax), ay2 = make_float2(ay, ay), az2 = make_float2(az, az);
-            const float2 bx2 = make_float2(bnx, bfx), by2 = make_float2(bny, bfy), bz2 = make_float2(bnz, bfz);
             const float tlo = t0 * 0.999999f, thi = best.t * 1.000001f;
             const uint32_t magic = sc.prmtMagic;
             const uint32_t imask = ei >> 24;
@@ -199,72 +179,11 @@ struct Trav {
                 const uint32_t nx = idir.x < 0.0f ? qhx : qlx, fx = idir.x < 0.0f ? qlx : qhx;
                 const uint32_t ny = idir.y < 0.0f ? qhy : qly, fy = idir.y < 0.0f ? qly : qhy;
                 const uint32_t nz = idir.z < 0.0f ? qhz : qlz, fz = idir.z < 0.0f ? qlz : qhz;
-#if defined(TRV_HALF_CONV) || defined(TRV_SIGN_MASK)
-                /* ALU-pipe diet (the kernel is bound by the ALU pipe - PRMT / FMNMX / LOP3 / SHF - at 65 % busy, FMA pipe 24 %):
-                 * TRV_HALF_CONV: bytes of TWO children become the halves (1024 + q) with one PRMT (0x6400 | q), converted to float by
-                 *   HADD2.F32 on the FMA pipe: 3 instead of 6 ALU instructions per child for the conversion;
-                 * TRV_SIGN_MASK: m = max3(near), M = min3(far), d = min3(M - k m, t_hi - k m, M - t_lo) (3 FMNMX3 instead of 2 FMNMX3 +
-                 *   2 FMNMX + FSETP); the sign bytes of the four d are gathered with 3 PRMTs into a byte mask and the hit bits are
-                 *   assembled without predicates. */
-                float dmiss[4];
-#ifdef TRV_HALF_CONV
-#pragma unroll
-                for (int pair = 0; pair < 2; pair++) {
-                    const float2 vnx = pairToFloat2(nx, sc.prmtMagicH, pair), vny = pairToFloat2(ny, sc.prmtMagicH, pair), vnz = pairToFloat2(nz, sc.prmtMagicH, pair);
-                    const float2 vfx = pairToFloat2(fx, sc.prmtMagicH, pair), vfy = pairToFloat2(fy, sc.prmtMagicH, pair), vfz = pairToFloat2(fz, sc.prmtMagicH, pair);
-#define TRV_EVAL(K, C)                                                                                                        \
-    {                                                                                                                         \
-        const float m = fmaxf(fmaxf(fmaf(vnx.C, ax, bnx), fmaf(vny.C, ay, bny)), fmaf(vnz.C, az, bnz));                       \
-        const float M = fminf(fminf(fmaf(vfx.C, ax, bfx), fmaf(vfy.C, ay, bfy)), fmaf(vfz.C, az, bfz));                       \
-        dmiss[K] = fminf(fminf(fmaf(m, -0.999999f, M), fmaf(m, -0.999999f, thi)), M - tlo);                                   \
-    }
-                    TRV_EVAL(2 * pair, x) TRV_EVAL(2 * pair + 1, y)
-#undef TRV_EVAL
-                }
-#else
-#define TRV_EVAL(J)                                                                                                           \
-    {                                                                                                                         \
-        const float m = fmaxf(fmaxf(fmaf(byteToFloat<J>(nx, magic), ax, bnx), fmaf(byteToFloat<J>(ny, magic), ay, bny)),      \
-                              fmaf(byteToFloat<J>(nz, magic), az, bnz));                                                      \
-        const float M = fminf(fminf(fmaf(byteToFloat<J>(fx, magic), ax, bfx), fmaf(byteToFloat<J>(fy, magic), ay, bfy)),      \
-                              fmaf(byteToFloat<J>(fz, magic), az, bfz));                                                      \
-        dmiss[J] = fminf(fminf(fmaf(m, -0.999999f, M), fmaf(m, -0.999999f, thi)), M - tlo);                                   \
-    }
-                TRV_EVAL(0) TRV_EVAL(1) TRV_EVAL(2) TRV_EVAL(3)
-#undef TRV_EVAL
-#endif
-#ifdef TRV_SIGN_MASK
-                {
-                    /* byte J = 0xff when d_J is negative (child J missed): sign-replicating byte permutes */
-                    uint32_t s01, s23, miss4;
-                    asm("prmt.b32 %0, %1, %2, 0x00fb;" : "=r"(s01) : "r"(__float_as_uint(dmiss[0])), "r"(__float_as_uint(dmiss[1])));
-                    asm("prmt.b32 %0, %1, %2, 0x00fb;" : "=r"(s23) : "r"(__float_as_uint(dmiss[2])), "r"(__float_as_uint(dmiss[3])));
-                    asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(miss4) : "r"(s01), "r"(s23));
-                    const uint32_t cb = childBits4 & ~miss4;
-                    hitmask |= (__byte_perm(cb, 0u, 0x4440) << (bitIndex4 & 31u)) | (__byte_perm(cb, 0u, 0x4441) << ((bitIndex4 >> 8) & 31u)) |
-                               (__byte_perm(cb, 0u, 0x4442) << ((bitIndex4 >> 16) & 31u)) | (__byte_perm(cb, 0u, 0x4443) << ((bitIndex4 >> 24) & 31u));
-                }
-#else
-#pragma unroll
-                for (int J = 0; J < 4; J++)
-                    if (!(dmiss[J] < 0.0f)) hitmask |= ((childBits4 >> (8 * J)) & 0xffu) << ((bitIndex4 >> (8 * J)) & 0xffu);
-#endif
-#else
-#ifdef TRV_PACKED_FMA
-/* Experiment, off: near and far plane of one axis in ONE packed instruction (Blackwell FFMA2, fma.rn.f32x2: two independent IEEE
- * FMAs, bit-identical to two FFMAs): (t_near, t_far) = (q_near, q_far) * (a, a) + (b_near, b_far).  Measured on the bench scene:
- * 4.5 % fewer instructions, issue slots 72 -> 67 % busy, ALU pipe unchanged at 65 % - and 0.7 % SLOWER (2033 vs 2048 Mseg/s, same
- * box, three alternating runs): the kernel is bound by the ALU pipe (PRMT / FMNMX / LOP3 / SHF) and L2 latency, not by issue or FMA. */
-#define TRV_CHILD(J)                                                                                                          \
-    {                                                                                                                         \
-        const float2 tx = __ffma2_rn(make_float2(byteToFloat<J>(nx, magic), byteToFloat<J>(fx, magic)), ax2, bx2);            \
-        const float2 ty = __ffma2_rn(make_float2(byteToFloat<J>(ny, magic), byteToFloat<J>(fy, magic)), ay2, by2);            \
-        const float2 tz = __ffma2_rn(make_float2(byteToFloat<J>(nz, magic), byteToFloat<J>(fz, magic)), az2, bz2);            \
-        const float tn = fmaxf(fmaxf(tx.x, ty.x), fmaxf(tz.x, tlo));                                                          \
-        const float tf = fminf(fminf(tx.y, ty.y), fminf(tz.y, thi));                                                          \
-        if (tn * 0.999999f <= tf) hitmask |= ((childBits4 >> (8 * J)) & 0xffu) << ((bitIndex4 >> (8 * J)) & 0xffu);           \
-    }
-#else
+                /* Variants of this test that were measured and rejected (profiles/r1_v4_kernel_experiments.log; the code is in the
+                 * history at "k_extend experiments recorded"): near / far plane of an axis in one packed FFMA2 (-4.5 % instructions, -0.7 %
+                 * speed), bytes converted through fp16 halves on the FMA pipe (+-0), FMNMX3-only interval test with a sign-byte gather and
+                 * an unpredicated hit mask (+0.3 %), next-node prefetch (-11 %).  The kernel is bound by the dependency chain of its
+                 * L1-missing fetches at the occupancy the register file allows, not by the instruction count of either pipe. */
 #define TRV_CHILD(J)                                                                                                          \
     {                                                                                                                         \
         const float tnx = fmaf(byteToFloat<J>(nx, magic), ax, bnx), tny = fmaf(byteToFloat<J>(ny, magic), ay, bny),           \
@@ -275,10 +194,8 @@ struct Trav {
         const float tf = fminf(fminf(tfx, tfy), fminf(tfz, thi));                                                             \
         if (tn * 0.999999f <= tf) hitmask |= ((childBits4 >> (8 * J)) & 0xffu) << ((bitIndex4 >> (8 * J)) & 0xffu);           \
     }
-#endif
                 TRV_CHILD(0) TRV_CHILD(1) TRV_CHILD(2) TRV_CHILD(3)
 #undef TRV_CHILD
-#endif
             }
             ng.y = (hitmask & 0xff000000u) | imask;
             tgOut.y = hitmask & 0x00ffffffu;
