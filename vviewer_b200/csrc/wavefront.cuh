@@ -137,6 +137,13 @@ PTC_D void loadSurf(const DScene &sc, int32_t triPos, float u, float v, bool wan
     }
 }
 
+/* material of the triangle at a traversal position without touching the rest of its record: the any-hit shaders of the shadow and
+ * probe rays decide most candidates from the material alone (opaque and not emissive: the ray ends there) */
+PTC_D const ptc_material *hitMaterial(const DScene &sc, int32_t triPos) {
+    const float4 r6 = __ldg(sc.shading + 9 * (size_t)triPos + 6);
+    return &sc.materials[sc.instances[__float_as_uint(r6.w)].material];
+}
+
 /* ------------------------------------------------------------------ volumes */
 struct Medium {
     float3 sigma_s, sigma_t;
@@ -565,15 +572,16 @@ __global__ void __launch_bounds__(128, SHADE_MINBLOCKS) k_shade(Wave w, const __
             bool doRoulette = true;
 
             if (triPos >= 0) {
-                Surf s;
-                loadSurf(sc, triPos, h.y, h.z, true, s);
-                Frame fr;
-                fr.n = s.n;
-                fr.t = s.t;
-                const bool flipped = fixFrame(fr, rayDir);
+                /* the free flight comes first: a path that scatters inside the medium never looks at the surface (no record fetch) */
                 bool sampledMedium = false;
                 if (VOLUMES && (flags & PF_INVOL)) sampledMedium = volumeEvent(sc, rc, rng, flags, origin, dir, beta, 0.001f, h.x, rq);
                 if (!sampledMedium) {
+                    Surf s;
+                    loadSurf(sc, triPos, h.y, h.z, true, s);
+                    Frame fr;
+                    fr.n = s.n;
+                    fr.t = s.t;
+                    const bool flipped = fixFrame(fr, rayDir);
                     const ptc_material *mat = s.mat;
                     const float tu = s.uv.x * __ldg(&mat->uv_tiling[0]), tv = s.uv.y * __ldg(&mat->uv_tiling[1]);
                     const bool lambert = (int)__ldg(&mat->uv_tiling[2]) == PTC_MATERIAL_LAMBERT;
@@ -792,10 +800,10 @@ struct ShadowPolicy {
             return finish(shadowed);
         }
         if (opaqueScene) return finish(true);
+        if (!(__ldg(&hitMaterial(sc, h.pos)->metallic_roughness_ao[3]) >= 0.99f)) return finish(true); /* raySecondary.rahit.glsl:42-47 */
         Surf s;
         loadSurf(sc, h.pos, h.u, h.v, false, s);
         const ptc_material *mat = s.mat;
-        if (!(__ldg(&mat->metallic_roughness_ao[3]) >= 0.99f)) return finish(true); /* raySecondary.rahit.glsl:42-47 */
         const float alpha =
             __ldg(&mat->albedo[3]) * texFetch(sc, __ldg(&mat->tex2[3]), s.uv.x * __ldg(&mat->uv_tiling[0]), s.uv.y * __ldg(&mat->uv_tiling[1])).x;
         thr = thr * (1.0f - alpha);
@@ -885,6 +893,12 @@ struct ProbePolicy {
         const trv::HitRec h = tr.best;
         const float3 dir = tr.d;
         if (h.pos < 0) return false; /* rayNEE.rmiss.glsl:12-19: nothing (the environment is not included, trap T6) */
+        {
+            /* rayNEE.rahit.glsl:44-54 decided from the material alone: the emissive texel is in [0, 1], so a material whose emissive
+             * factor is already below the threshold cannot pass it, and an opaque one ends the ray (result-identical shortcut) */
+            const ptc_material *m0 = hitMaterial(sc, h.pos);
+            if (!(__ldg(&m0->metallic_roughness_ao[3]) >= 0.99f) && isBlackEps(ld3(m0->emissive) * __ldg(&m0->emissive[3]), 0.05f)) return false;
+        }
         Surf s;
         loadSurf(sc, h.pos, h.u, h.v, false, s);
         const ptc_material *mat = s.mat;
