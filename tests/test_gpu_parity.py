@@ -236,7 +236,8 @@ def test_render_matches_oracle(capi, engine, scene, sobol):
     assert np.mean(np.abs(aa - ab).max(axis=-1) > 2e-2) < 2e-3
     assert np.all(ra[..., 3] == 1.0)
     assert abs(sa["segments"] - sb["segments"]) <= 1e-3 * sb["segments"]
-    assert abs(sa["probe_rays"] - sb["probe_rays"]) <= 1e-3 * max(sb["probe_rays"], 1000)
+    # the device does not trace probe rays that miss the world boxes of all emitters (they can only return black)
+    assert sa["probe_rays"] <= sb["probe_rays"] + 1e-3 * max(sb["probe_rays"], 1000)
     cu.close()
     orc.close()
 

@@ -58,6 +58,7 @@ struct DInstance {
     uint32_t pad;
 };
 
+#define PTC_MAX_EMISSIVE_BOXES 16
 #define TEX_WHITE 0xffffffffu /* texture whose every texel is (255, 255, 255, 255): reads as exactly 1 without a fetch */
 
 struct DScene {
@@ -82,6 +83,10 @@ struct DScene {
     uint32_t prmtMagic; /* 0x47000000, see traverse.cuh::byteToFloat */
     /* scene-level switches that let whole ray types be skipped without changing any result */
     uint32_t anyEmissive;    /* some instanced material can pass the probe's emissive test */
+    /* world boxes (lo, hi pairs) of the instances whose material can pass that test, when there are at most PTC_MAX_EMISSIVE_BOXES of
+     * them (else 0): a probe ray that misses every box can only return black and is not traced */
+    const float4 *emissiveBoxes;
+    uint32_t nEmissiveBoxes;
     uint32_t anyTransparent; /* some instanced material has the transparent flag */
     uint32_t anyVolume;      /* some instance changes the volume, or the camera starts inside one */
 };

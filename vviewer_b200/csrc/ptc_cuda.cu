@@ -51,6 +51,8 @@ struct ptc_ctx {
     cudaTextureObject_t cubeTex = 0;
     uint32_t cubeN = 0;
     DBuf<float> envCdfV, envCdfU; /* PTC_FLAG_ENV_IMPORTANCE tables, valid while cubeTex is */
+    DBuf<float4> emissiveBoxes;   /* DScene::emissiveBoxes */
+    uint32_t nEmissiveBoxes = 0;
     uint32_t nInstances = 0, nMaterials = 0, nLightInstances = 0, nTextures = 0, nWorldTris = 0;
     bool anyEmissive = false, anyTransparent = false, anyVolumeChange = false;
     bool sceneUploaded = false, accelBuilt = false;
@@ -170,6 +172,8 @@ DScene makeDScene(ptc_ctx *c) {
     s.nWideNodes = c->accel.nWide;
     s.prmtMagic = 0x47000000u;
     s.anyEmissive = c->anyEmissive ? 1u : 0u;
+    s.emissiveBoxes = c->emissiveBoxes.p;
+    s.nEmissiveBoxes = c->nEmissiveBoxes;
     s.anyTransparent = c->anyTransparent ? 1u : 0u;
     s.anyVolume = c->anyVolumeChange ? 1u : 0u;
     return s;
@@ -674,6 +678,8 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
     c->nInstances = sd->n_instances;
 
     std::vector<DInstance> inst(sd->n_instances);
+    std::vector<float4> emBoxes;
+    uint32_t nEmissiveInst = 0;
     uint64_t tri = 0;
     c->anyEmissive = c->anyTransparent = c->anyVolumeChange = false;
     for (uint32_t i = 0; i < sd->n_instances; i++) {
@@ -702,14 +708,37 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
         tri += m.tri_count;
         const ptc_material &mat = sd->materials[in.material_index];
         const float ei = mat.emissive[3];
-        if (std::fabs(ei * mat.emissive[0]) > 0.05f || std::fabs(ei * mat.emissive[1]) > 0.05f || std::fabs(ei * mat.emissive[2]) > 0.05f)
+        if (std::fabs(ei * mat.emissive[0]) > 0.05f || std::fabs(ei * mat.emissive[1]) > 0.05f || std::fabs(ei * mat.emissive[2]) > 0.05f) {
             c->anyEmissive = true;
+            /* world box of this emitter (DScene::emissiveBoxes), padded against the rounding of the device's own transform */
+            if (++nEmissiveInst <= PTC_MAX_EMISSIVE_BOXES && m.vertex_count > 0) {
+                if ((uint64_t)m.first_vertex + m.vertex_count > sd->n_vertices) return fail(c, "mesh vertex range out of bounds");
+                float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+                for (uint32_t v = 0; v < m.vertex_count; v++) {
+                    const float *p = sd->vertices[m.first_vertex + v].position;
+                    for (int r = 0; r < 3; r++) {
+                        const float wv = M[r] * p[0] + M[4 + r] * p[1] + M[8 + r] * p[2] + M[12 + r];
+                        lo[r] = std::min(lo[r], wv);
+                        hi[r] = std::max(hi[r], wv);
+                    }
+                }
+                for (int r = 0; r < 3; r++) {
+                    const float pad = 1e-4f * (std::fabs(lo[r]) + std::fabs(hi[r]) + (hi[r] - lo[r])) + 1e-5f;
+                    lo[r] -= pad;
+                    hi[r] += pad;
+                }
+                emBoxes.push_back(make_float4(lo[0], lo[1], lo[2], 0.0f));
+                emBoxes.push_back(make_float4(hi[0], hi[1], hi[2], 0.0f));
+            }
+        }
         if (mat.metallic_roughness_ao[3] > 0.0f) c->anyTransparent = true;
         if (in.id[1] != in.id[2]) c->anyVolumeChange = true;
     }
     if (tri >= 0x7fffffffull) return fail(c, "more than 2^31 world triangles");
     c->nWorldTris = (uint32_t)tri;
     c->instances.upload(inst.data(), inst.size(), s);
+    c->nEmissiveBoxes = (nEmissiveInst >= 1 && nEmissiveInst <= PTC_MAX_EMISSIVE_BOXES && emBoxes.size() == 2 * (size_t)nEmissiveInst) ? nEmissiveInst : 0u;
+    if (c->nEmissiveBoxes) c->emissiveBoxes.upload(emBoxes.data(), emBoxes.size(), s);
 
     std::vector<uint64_t> sig;
     bool allIdentified = sd->n_textures > 0;

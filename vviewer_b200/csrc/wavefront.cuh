@@ -255,6 +255,24 @@ PTC_D LightSample sampleLight(const DScene &sc, const RenderConst &rc, Rng &rng,
     return ls;
 }
 
+/* Does the line origin + t dir, t >= 0, meet the (padded) world box of any emissive instance?  The probe chain of
+ * next_event_estimation.glsl only ever adds radiance when it ends on an emissive triangle, and all its hops stay on this line, so a
+ * ray that misses every box is not traced (result-identical). */
+PTC_D bool rayMeetsEmitters(const DScene &sc, float3 o, float3 d) {
+    const float3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); /* +-inf for axis-parallel rays: the slab test handles it, NaN = inside */
+    for (uint32_t k = 0; k < sc.nEmissiveBoxes; k++) {
+        const float4 lo = __ldg(sc.emissiveBoxes + 2 * k), hi = __ldg(sc.emissiveBoxes + 2 * k + 1);
+        const float tx0 = (lo.x - o.x) * inv.x, tx1 = (hi.x - o.x) * inv.x;
+        const float ty0 = (lo.y - o.y) * inv.y, ty1 = (hi.y - o.y) * inv.y;
+        const float tz0 = (lo.z - o.z) * inv.z, tz1 = (hi.z - o.z) * inv.z;
+        /* fminf / fmaxf drop NaNs (0 * inf when the origin lies on a slab plane of a parallel ray), which keeps the test conservative */
+        const float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+        const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
+        if (tn <= tf * 1.00001f + 1e-6f) return true;
+    }
+    return false;
+}
+
 /* requests produced by one shading event */
 struct Requests {
     bool shadow, probe;
@@ -716,6 +734,7 @@ __global__ void __launch_bounds__(128, SHADE_MINBLOCKS) k_shade(Wave w, const __
             if (rq.probe) lastPdf = rq.prPdf; /* a new direction was sampled (surface or medium) */
             /* requests that can only return black are dropped (result-identical) */
             if (rq.probe && !sc.anyEmissive) rq.probe = false;
+            if (rq.probe && sc.nEmissiveBoxes != 0u && !rayMeetsEmitters(sc, origin, dir)) rq.probe = false;
             alive = !stop && !lastBounce;
             /* a finished path's state is never read again (a probe request still needs the new origin and direction) */
             if (alive || rq.probe) {
