@@ -12,10 +12,12 @@
 #include "traverse.cuh"
 #include "wavefront.cuh"
 
+#include <array>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 namespace {
@@ -679,6 +681,8 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
 
     std::vector<DInstance> inst(sd->n_instances);
     std::vector<float4> emBoxes;
+    std::map<uint32_t, std::array<float, 6>> meshBox; /* object-space boxes of the meshes of emissive instances */
+    float unionLo[3] = {1e30f, 1e30f, 1e30f}, unionHi[3] = {-1e30f, -1e30f, -1e30f};
     uint32_t nEmissiveInst = 0;
     uint64_t tri = 0;
     c->anyEmissive = c->anyTransparent = c->anyVolumeChange = false;
@@ -710,12 +714,27 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
         const float ei = mat.emissive[3];
         if (std::fabs(ei * mat.emissive[0]) > 0.05f || std::fabs(ei * mat.emissive[1]) > 0.05f || std::fabs(ei * mat.emissive[2]) > 0.05f) {
             c->anyEmissive = true;
-            /* world box of this emitter (DScene::emissiveBoxes), padded against the rounding of the device's own transform */
-            if (++nEmissiveInst <= PTC_MAX_EMISSIVE_BOXES && m.vertex_count > 0) {
+            /* world box of this emitter (DScene::emissiveBoxes): the mesh's object-space box (computed once per mesh) through the
+             * instance transform, padded against the rounding of the device's own transform */
+            nEmissiveInst++;
+            if (m.vertex_count > 0) {
                 if ((uint64_t)m.first_vertex + m.vertex_count > sd->n_vertices) return fail(c, "mesh vertex range out of bounds");
+                auto it = meshBox.find(in.mesh_index);
+                if (it == meshBox.end()) {
+                    std::array<float, 6> ob = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
+                    for (uint32_t v = 0; v < m.vertex_count; v++) {
+                        const float *p = sd->vertices[m.first_vertex + v].position;
+                        for (int r = 0; r < 3; r++) {
+                            ob[r] = std::min(ob[r], p[r]);
+                            ob[3 + r] = std::max(ob[3 + r], p[r]);
+                        }
+                    }
+                    it = meshBox.emplace(in.mesh_index, ob).first;
+                }
+                const std::array<float, 6> &ob = it->second;
                 float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
-                for (uint32_t v = 0; v < m.vertex_count; v++) {
-                    const float *p = sd->vertices[m.first_vertex + v].position;
+                for (int corner = 0; corner < 8; corner++) {
+                    const float p[3] = {ob[(corner & 1) ? 3 : 0], ob[(corner & 2) ? 4 : 1], ob[(corner & 4) ? 5 : 2]};
                     for (int r = 0; r < 3; r++) {
                         const float wv = M[r] * p[0] + M[4 + r] * p[1] + M[8 + r] * p[2] + M[12 + r];
                         lo[r] = std::min(lo[r], wv);
@@ -726,9 +745,13 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
                     const float pad = 1e-4f * (std::fabs(lo[r]) + std::fabs(hi[r]) + (hi[r] - lo[r])) + 1e-5f;
                     lo[r] -= pad;
                     hi[r] += pad;
+                    unionLo[r] = std::min(unionLo[r], lo[r]);
+                    unionHi[r] = std::max(unionHi[r], hi[r]);
                 }
-                emBoxes.push_back(make_float4(lo[0], lo[1], lo[2], 0.0f));
-                emBoxes.push_back(make_float4(hi[0], hi[1], hi[2], 0.0f));
+                if (nEmissiveInst <= PTC_MAX_EMISSIVE_BOXES) {
+                    emBoxes.push_back(make_float4(lo[0], lo[1], lo[2], 0.0f));
+                    emBoxes.push_back(make_float4(hi[0], hi[1], hi[2], 0.0f));
+                }
             }
         }
         if (mat.metallic_roughness_ao[3] > 0.0f) c->anyTransparent = true;
@@ -737,7 +760,13 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
     if (tri >= 0x7fffffffull) return fail(c, "more than 2^31 world triangles");
     c->nWorldTris = (uint32_t)tri;
     c->instances.upload(inst.data(), inst.size(), s);
-    c->nEmissiveBoxes = (nEmissiveInst >= 1 && nEmissiveInst <= PTC_MAX_EMISSIVE_BOXES && emBoxes.size() == 2 * (size_t)nEmissiveInst) ? nEmissiveInst : 0u;
+    /* few emitters: one box each; many: the box around all of them */
+    if (nEmissiveInst > PTC_MAX_EMISSIVE_BOXES) {
+        emBoxes.clear();
+        emBoxes.push_back(make_float4(unionLo[0], unionLo[1], unionLo[2], 0.0f));
+        emBoxes.push_back(make_float4(unionHi[0], unionHi[1], unionHi[2], 0.0f));
+    }
+    c->nEmissiveBoxes = nEmissiveInst >= 1 ? (uint32_t)(emBoxes.size() / 2) : 0u;
     if (c->nEmissiveBoxes) c->emissiveBoxes.upload(emBoxes.data(), emBoxes.size(), s);
 
     std::vector<uint64_t> sig;
