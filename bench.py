@@ -250,9 +250,16 @@ def run_cuda(args, rank, world, local_rank):
             traffic = json.load(open(tp)).get("k_extend_dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # second kernel (k_shade, DRAM bound): algorithmic bytes per segment with the actual record sizes - queue id 4,
+    # hit + origin + direction + throughput read 64, new origin + direction + throughput written 48, shading record 144, three texture
+    # taps of 16 B (albedo, normal, roughness of the bench scene's materials)
+    shade_bytes = 4 + 64 + 48 + 144 + 3 * 16
+    shade_gbs = stp["segments"] * shade_bytes / (stp["shade_ms"] * 1e-3) / 1e9 if stp["shade_ms"] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "bytes_per_ray": bytes_per_ray, "bvh_depth": bvh_depth,
-                "avg_launch_ms": avg_launch_ms, "kernel_ms_share": share}
+                "avg_launch_ms": avg_launch_ms, "kernel_ms_share": share,
+                "k_shade": {"achieved": shade_gbs, "frac": shade_gbs / peak, "bytes_per_segment": shade_bytes,
+                            "note": "algorithmic bytes; the DRAM traffic at 32 B sector granularity is about twice that (profiles/r1_v3_k_shade_full_raw.csv)"}}
 
     # ---- end to end through the public API (RendererPathTracing::render via the C++ plugin): host scene in,
     # host images out; includes flatten, H2D upload of the scene, BVH build, render and D2H of the 3 targets
