@@ -49,6 +49,9 @@ PTC_API int vh_render_params(vh_engine *e, ptc_render_params *out);
 PTC_API int vh_render_to_memory(vh_engine *e, float *radiance_rgba, float *albedo_rgba, float *normal_rgba);
 PTC_API int vh_render(vh_engine *e, const char *filename);
 PTC_API int vh_get_stats(vh_engine *e, ptc_stats *out);
+/* RendererPathTracing::renderProgress() (core/Renderer.hpp:37): 0..1, may be polled from another thread while vh_render* runs
+ * (the reference's UI does exactly that, MainWindow.cpp:874-896) */
+PTC_API float vh_render_progress(vh_engine *e);
 
 /* Radiance HDR helpers (RGBA32F in memory, top row first) */
 PTC_API int vh_read_hdr(const char *path, int *w, int *h, float *rgba_out);

@@ -375,6 +375,37 @@ def test_chunked_and_overlapped_wavefronts_equal_the_plain_render(capi, engine, 
         assert np.abs(a - b).max() <= 2e-6 * max(1.0, float(np.abs(a).max()))
 
 
+def test_render_progress_polled_from_another_thread(capi):
+    """renderProgress() is read by the UI thread while render() runs on a worker (MainWindow.cpp:874-896): monotone, within [0, 1],
+    1 when the call returns; with many short batches intermediate values are seen"""
+    import threading
+    eng = capi.HostEngine()
+    eng.build_scene("Cornell")
+    eng.set_render_info(width=256, height=256, samples=4 * 96, batch_size=4)
+    assert eng.render_progress() in (0.0, 1.0)
+    seen = []
+    stop = threading.Event()
+
+    def poll():
+        while not stop.is_set():
+            seen.append(eng.render_progress())
+
+    t = threading.Thread(target=poll)
+    t.start()
+    try:
+        eng.render_to_memory()  # ctypes releases the GIL during the call
+    finally:
+        stop.set()
+        t.join()
+    assert eng.render_progress() == 1.0
+    vals = np.array(seen, np.float64)
+    assert len(vals) > 10 and vals.min() >= 0.0 and vals.max() <= 1.0
+    rising = vals[np.argmax(vals < 0.999):] if np.any(vals < 0.999) else vals  # from the first poll inside the render on
+    assert np.all(np.diff(rising) >= -1e-7), "progress went backwards"
+    assert np.any((vals > 0.02) & (vals < 0.98)), "no intermediate progress value observed"
+    eng.close()
+
+
 def test_texture_identity_cache(capi):
     """ptc_texture.uid: content with a non-zero uid is immutable by contract and keeps its device copy across uploads
     (the reference uploads textures once, at import); uid 0 or a new uid uploads again."""

@@ -104,7 +104,7 @@ PTC_SYMBOLS = ["ptc_create", "ptc_destroy", "ptc_last_error", "ptc_backend_name"
 VH_SYMBOLS = ["vh_engine_create", "vh_engine_destroy", "vh_backend_ok", "vh_last_error", "vh_scene_list", "vh_build_scene",
               "vh_set_render_info", "vh_get_render_info", "vh_scene_desc", "vh_render_params", "vh_render_to_memory", "vh_render",
               "vh_get_stats", "vh_read_hdr", "vh_write_hdr", "vh_import_model", "vh_add_model", "vh_import_scene", "vh_export_scene",
-              "vh_describe", "vh_decode_image"]
+              "vh_describe", "vh_decode_image", "vh_render_progress"]
 
 _fp = C.POINTER(f32)
 _ip = C.POINTER(C.c_int)
@@ -183,6 +183,8 @@ def _declare_vh(lib):
     lib.vh_render.restype = C.c_int
     lib.vh_get_stats.argtypes = [vp, C.POINTER(ptc_stats)]
     lib.vh_get_stats.restype = C.c_int
+    lib.vh_render_progress.argtypes = [vp]
+    lib.vh_render_progress.restype = f32
     lib.vh_read_hdr.argtypes = [C.c_char_p, _ip, _ip, vp]
     lib.vh_read_hdr.restype = C.c_int
     lib.vh_write_hdr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, vp]
@@ -474,6 +476,10 @@ class HostEngine:
             raise RuntimeError("RendererPathTracing::render failed: %s" % self.last_error())
         shape = (ri["height"], ri["width"], 4)
         return rad.reshape(shape), alb.reshape(shape), nrm.reshape(shape)
+
+    def render_progress(self):
+        """RendererPathTracing::renderProgress(); safe to call from another thread while a render runs"""
+        return float(self.lib.vh_render_progress(self.h))
 
     def render(self, filename):
         rc = self.lib.vh_render(self.h, filename.encode())

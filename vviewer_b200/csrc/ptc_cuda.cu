@@ -394,6 +394,7 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     const uint32_t tile = rp->tile_size ? rp->tile_size : 32u;
     const size_t nPix = (size_t)W * H;
     cudaStream_t s = c->stream;
+    c->progress = 0.0f; /* renderProgress() restarts with every render (VulkanRendererPathTracing.cpp:228-231) */
 
     /* pixel set of this rank */
     uint32_t nPixLocal = (uint32_t)nPix;

@@ -343,6 +343,8 @@ PTC_API int vh_render(vh_engine *h, const char *filename) {
     return 0;
 }
 
+PTC_API float vh_render_progress(vh_engine *h) { return h ? h->engine->renderer().rendererPathTracing().renderProgress() : 0.0f; }
+
 PTC_API int vh_get_stats(vh_engine *h, ptc_stats *out) {
     if (!h || !out) return 1;
     *out = h->engine->renderer().rendererPathTracing().lastStats();
