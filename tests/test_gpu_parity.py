@@ -375,6 +375,25 @@ def test_chunked_and_overlapped_wavefronts_equal_the_plain_render(capi, engine, 
         assert np.abs(a - b).max() <= 2e-6 * max(1.0, float(np.abs(a).max()))
 
 
+def test_shadow_rays_through_alpha_tested_foliage(capi, engine):
+    """media-free scene with transparent materials and a light: the device looks at every triangle a shadow ray crosses in one
+    traversal (order-independent product of 1 - alpha), the oracle walks the candidates nearest first (raySecondary.rahit.glsl)"""
+    engine.build_scene("Instanced", texture_size=64, scale=0.004)
+    engine.set_render_info(width=160, height=90, samples=8, batch_size=4)
+    desc, rp = engine.scene_desc(), engine.render_params()
+    cu, orc = both(capi, desc)
+    ra = cu.render(rp)[0]
+    rb = orc.render(rp)[0]
+    sa, sb = cu.stats(), orc.stats()
+    assert sb["shadow_rays"] > 10000 and sa["shadow_rays"] > 10000
+    d = np.abs(ra[..., :3] - rb[..., :3]).max(axis=-1)
+    assert np.mean(d > 1e-3 * np.maximum(1.0, rb[..., :3].max(axis=-1))) < 0.03, "radiance differs in %.3f %% of pixels" % (100 * np.mean(d > 1e-3))
+    assert abs(ra[..., :3].mean() / rb[..., :3].mean() - 1) < 5e-3
+    assert abs(sa["segments"] - sb["segments"]) <= 2e-3 * sb["segments"]
+    cu.close()
+    orc.close()
+
+
 def test_render_progress_polled_from_another_thread(capi):
     """renderProgress() is read by the UI thread while render() runs on a worker (MainWindow.cpp:874-896): monotone, within [0, 1],
     1 when the call returns; with many short batches intermediate values are seen"""

@@ -360,6 +360,23 @@ struct TraceCounters { /* -DPTC_TRAV_STATS builds only (tools/trav_stats.py) */
 #define TRV_COUNT(x)
 #endif
 
+/* One stashed triangle.  Policies with ALL_HITS (the shadow ray in scenes without media) look at EVERY triangle the ray crosses in
+ * traversal order instead of asking for the next-nearest one again and again: Policy::candidate() returns true when the ray is
+ * decided (it is then marked as hit, which ends the occlusion query). */
+template <class Policy>
+PTC_D void testTriangle(const DScene &sc, Policy &pol, trv::Trav &tr, int32_t pos) {
+    if constexpr (Policy::ALL_HITS) {
+        if (pol.allHits()) {
+            const float4 *__restrict__ tris = sc.tris;
+            const float4 v0 = __ldg(&tris[3 * (size_t)pos + 0]), e1 = __ldg(&tris[3 * (size_t)pos + 1]), e2 = __ldg(&tris[3 * (size_t)pos + 2]);
+            float t, u, v;
+            if (tr.best.pos < 0 && trv::intersectTri(v0, e1, e2, tr.o, tr.d, t, u, v) && t > tr.tmin && t < tr.tmax && pol.candidate(pos, u, v)) tr.best.pos = pos;
+            return;
+        }
+    }
+    tr.triTest(sc, pos);
+}
+
 template <class Policy>
 PTC_D void traceLoop(const DScene &sc, Policy &pol, uint32_t count, uint32_t *fetchCounter, const ExtendTune tune, const trv::Stack &stack, uint2 *stash,
                      TraceCounters &cnt) {
@@ -393,7 +410,7 @@ PTC_D void traceLoop(const DScene &sc, Policy &pol, uint32_t count, uint32_t *fe
                         while (tr.tg.y != 0u) {
                             const uint32_t k = 31u - (uint32_t)__clz(tr.tg.y);
                             tr.tg.y &= ~(1u << k);
-                            tr.triTest(sc, (int32_t)(tr.tg.x + k));
+                            testTriangle(sc, pol, tr, (int32_t)(tr.tg.x + k));
                         }
                         tr.tg = stash[(--nStash) * TRV_BLOCK];
                     }
@@ -415,7 +432,7 @@ PTC_D void traceLoop(const DScene &sc, Policy &pol, uint32_t count, uint32_t *fe
                         TRV_COUNT(cnt.tri);
                         const uint32_t k = 31u - (uint32_t)__clz(tr.tg.y);
                         tr.tg.y &= ~(1u << k);
-                        tr.triTest(sc, (int32_t)(tr.tg.x + k));
+                        testTriangle(sc, pol, tr, (int32_t)(tr.tg.x + k));
                         if (tr.tg.y == 0u && nStash > 0u) tr.tg = stash[(--nStash) * TRV_BLOCK];
                         hasTri = tr.tg.y != 0u;
                     }
@@ -448,6 +465,7 @@ PTC_D void traceCountersFlush(const Wave &w, const TraceCounters &cnt) {
 /* ------------------------------------------------------------------ k_extend */
 /* closest hit of the path ray: traceRayEXT at raygen.rgen.glsl:110 (tmin 1e-3, tmax 1e4) */
 struct ExtendPolicy {
+    static constexpr bool ALL_HITS = false;
     const Wave &w;
     const uint32_t *__restrict__ q;
     uint32_t bounce, slot;
@@ -763,16 +781,33 @@ __global__ void __launch_bounds__(128, SHADE_MINBLOCKS) k_shade(Wave w, const __
 /* lightSampling.glsl:108-144 + raySecondary.rahit/.rchit/.rmiss with nearest-first candidate order (trap T1), as a
  * per-lane state machine on top of traceLoop: one query = the next-nearest candidate of the current hop. */
 struct ShadowPolicy {
+    /* Without media (no instance changes the volume, the camera is in none) the shadow chain is one ray whose transmittance is the
+     * product of (1 - alpha) over the transparent surfaces it crosses, zero if any of them is opaque (raySecondary.rahit.glsl:31-72):
+     * independent of the order, so one traversal that looks at every crossed triangle replaces one ordered query per surface. */
+    static constexpr bool ALL_HITS = true;
     const Wave &w;
     const DScene &sc;
     const RenderConst &rc;
     uint32_t slot, vol, hop, hops;
     float3 origin, thr; /* the direction lives in the traversal state */
     float distanceT, vtmin;
-    bool opaqueScene;
+    bool opaqueScene, everyHit;
     PTC_D ShadowPolicy(const Wave &w_, const DScene &sc_, const RenderConst &rc_)
-        : w(w_), sc(sc_), rc(rc_), slot(0), vol(0), hop(0), hops(0), distanceT(0.0f), vtmin(0.0f), opaqueScene(!sc_.anyTransparent) {}
-    PTC_D bool anyHit() const { return opaqueScene; } /* every surface is opaque: any hit shadows */
+        : w(w_), sc(sc_), rc(rc_), slot(0), vol(0), hop(0), hops(0), distanceT(0.0f), vtmin(0.0f), opaqueScene(!sc_.anyTransparent),
+          everyHit(sc_.anyTransparent && !sc_.anyVolume && rc_.sd.volumes[0] == -1.0f) {}
+    PTC_D bool anyHit() const { return opaqueScene || everyHit; } /* every surface is opaque: any hit shadows; all-hits: a decided ray is marked hit */
+    PTC_D bool allHits() const { return everyHit; }
+    /* a triangle the ray crosses (all-hits mode): true = the ray is shadowed */
+    PTC_D bool candidate(int32_t pos, float u, float v) {
+        const float4 *__restrict__ r = sc.shading + 9 * (size_t)pos;
+        const ptc_material *mat = &sc.materials[sc.instances[__float_as_uint(__ldg(r + 6).w)].material];
+        if (!(__ldg(&mat->metallic_roughness_ao[3]) >= 0.99f)) return true; /* raySecondary.rahit.glsl:42-47 */
+        const float w0 = 1.0f - u - v;
+        const float uu = __ldg(r + 0).w * w0 + __ldg(r + 2).w * u + __ldg(r + 4).w * v, vv = __ldg(r + 1).w * w0 + __ldg(r + 3).w * u + __ldg(r + 5).w * v;
+        const float alpha = __ldg(&mat->albedo[3]) * texFetch(sc, __ldg(&mat->tex2[3]), uu * __ldg(&mat->uv_tiling[0]), vv * __ldg(&mat->uv_tiling[1])).x;
+        thr = thr * (1.0f - alpha);
+        return !(max3(thr) > PT_EPSILON);
+    }
     PTC_D void startHop(trv::Trav &tr) {
         const float tmin = 0.0001f;
         vtmin = tmin;
@@ -818,7 +853,7 @@ struct ShadowPolicy {
             }
             return finish(shadowed);
         }
-        if (opaqueScene) return finish(true);
+        if (opaqueScene || everyHit) return finish(true);
         if (!(__ldg(&hitMaterial(sc, h.pos)->metallic_roughness_ao[3]) >= 0.99f)) return finish(true); /* raySecondary.rahit.glsl:42-47 */
         Surf s;
         loadSurf(sc, h.pos, h.u, h.v, false, s);
@@ -866,6 +901,7 @@ __global__ void __launch_bounds__(TRV_BLOCK, CHAIN_MINBLOCKS) k_shadow(Wave w, c
 /* ------------------------------------------------------------------ k_probe */
 /* next_event_estimation.glsl:1-33 + rayNEE.rahit/.rchit/.rmiss with nearest-first candidate order (trap T1) */
 struct ProbePolicy {
+    static constexpr bool ALL_HITS = false; /* the probe's any-hit decisions depend on the order of the candidates */
     const Wave &w;
     const DScene &sc;
     const RenderConst &rc;
