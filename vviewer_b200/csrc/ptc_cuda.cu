@@ -470,6 +470,7 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     const int gridExtend = residentGrid((const void *)wf::k_extend, TRV_BLOCK, capTrace);
     /* k_shade specialisation (wavefront.cuh): lights in the pick / media reachable */
     const bool hasLights = rc.totalLights > 0, hasVolumes = c->anyVolumeChange || rp->scene.volumes[0] != -1.0f;
+    rc.fuseProbe = (c->anyEmissive && hasLights && !c->anyTransparent && !hasVolumes && getenv("PTC_NO_PROBE_FUSION") == nullptr) ? 1u : 0u;
     using ShadeFn = void (*)(wf::Wave, const DScene, const wf::RenderConst, uint32_t, uint32_t);
     const ShadeFn shadeFn = hasLights ? (hasVolumes ? (ShadeFn)wf::k_shade<true, true> : (ShadeFn)wf::k_shade<true, false>)
                                       : (hasVolumes ? (ShadeFn)wf::k_shade<false, true> : (ShadeFn)wf::k_shade<false, false>);

@@ -24,6 +24,7 @@ namespace wf {
 #define PF_DEPTH_MASK 0xffu
 #define PF_SURFACE 0x100u /* surfaceDepth > 0 */
 #define PF_INVOL 0x200u   /* insideVolume */
+#define PF_PROBE_DEFERRED 0x400u /* the BSDF probe of the previous event is answered by this segment's closest hit (RenderConst::fuseProbe) */
 #define PF_VOL_SHIFT 16
 
 enum { CNT_ACTIVE = 0, CNT_SHADOW = 1, CNT_PROBE = 2, CNT_FETCH = 3, CNT_FETCH_SHADOW = 4, CNT_FETCH_PROBE = 5, CNT_STRIDE = 8 };
@@ -53,6 +54,7 @@ struct RenderConst {
     uint32_t cameraType;
     float orthoW, orthoH;
     uint32_t totalLights;    /* light instances, + 1 when the environment is light-sampled */
+    uint32_t fuseProbe;      /* opaque, media-free scene: the probe ray of a path that goes on is its next path ray (see k_shade) */
     uint32_t envLight;       /* PTC_FLAG_ENV_IMPORTANCE and an HDRI environment: light index totalLights - 1 is the environment */
     uint32_t flags;
     uint32_t nPixLocal;      /* pixels rendered by this rank */
@@ -637,6 +639,27 @@ __global__ void __launch_bounds__(128, SHADE_MINBLOCKS) k_shade(Wave w, const __
                         applyNormal(fr, normalFromMap(f3(texFetch(sc, __ldg(&mat->tex2[1]), tu, tv))));
                         const float3 albedo = ld3(mat->albedo) * f3(texFetch(sc, __ldg(&mat->tex1[0]), tu, tv));
                         const float3 emissive = ld3(mat->emissive) * __ldg(&mat->emissive[3]) * f3(texFetch(sc, __ldg(&mat->tex2[0]), tu, tv));
+                        if (LIGHTS && !VOLUMES && (flags & PF_PROBE_DEFERRED)) {
+                            /* The previous event's BSDF probe (next_event_estimation.glsl:1-33) travels along this very ray.  With only
+                             * opaque surfaces and no media its first candidate decides it (rayNEE.rahit.glsl:44-54, 73-131) and that candidate
+                             * is this closest hit, so the probe was not traced: same terms, same place in the sum.  (The probe's range is
+                             * [1e-4, zfar), the path ray's [1e-3, 1e4): the far end is checked, a surface in the first millimetre is not seen.) */
+                            flags &= ~PF_PROBE_DEFERRED;
+                            if (!isBlackEps(emissive, 0.05f) && h.x < rc.sd.volumes[2] && !(dot(s.n, rayDir) > 0.0f)) {
+                                const float3 w0 = mulPoint(s.inst->m, s.p0), w1 = mulPoint(s.inst->m, s.p1), w2 = mulPoint(s.inst->m, s.p2);
+                                const float area = 0.5f * length(cross(w1 - w0, w2 - w0));
+                                const float pointPdf = (1.0f / (float)s.inst->numTriangles) * (1.0f / area);
+                                const float dp = dot(-rayDir, s.n);
+                                if (dp > 0.0f) {
+                                    const float3 ro = (rc.flags & PTC_FLAG_WORLD_ORIGIN_PROBE_PDF) ? origin : mulPoint(s.inst->w2o, origin);
+                                    const float dd = length(ro - s.pos);
+                                    const float pdfL = pointPdf * (dd * dd) / dp * (1.0f / (float)rc.totalLights);
+                                    const float4 bp = ldS(&w.prBetaPdf[slot]);
+                                    radiance = emissive * f3(bp) * powerHeuristic(bp.w, pdfL);
+                                    radianceAdded = !isBlack(emissive);
+                                }
+                            }
+                        }
                         Pbr pbr;
                         pbr.albedo = albedo;
                         pbr.metallic = 0.0f;
@@ -754,6 +777,13 @@ __global__ void __launch_bounds__(128, SHADE_MINBLOCKS) k_shade(Wave w, const __
             if (rq.probe && !sc.anyEmissive) rq.probe = false;
             if (rq.probe && sc.nEmissiveBoxes != 0u && !rayMeetsEmitters(sc, origin, dir)) rq.probe = false;
             alive = !stop && !lastBounce;
+            flags &= ~PF_PROBE_DEFERRED; /* (a miss or a pass-through leaves it set; the probe of a missed ray adds nothing) */
+            bool deferProbe = false;
+            if (LIGHTS && !VOLUMES && rq.probe && rc.fuseProbe && alive) { /* the next path ray answers this probe */
+                deferProbe = true;
+                rq.probe = false;
+                flags |= PF_PROBE_DEFERRED;
+            }
             /* a finished path's state is never read again (a probe request still needs the new origin and direction) */
             if (alive || rq.probe) {
                 stS(&w.orgRng[slot], make_float4(origin.x, origin.y, origin.z, __uint_as_float(rng.s)));
@@ -769,7 +799,7 @@ __global__ void __launch_bounds__(128, SHADE_MINBLOCKS) k_shade(Wave w, const __
                 stS(&w.shDirVol[slot], make_float4(rq.shDir.x, rq.shDir.y, rq.shDir.z, __uint_as_float(flags)));
                 stS(&w.shContrib[slot], make_float4(rq.shContrib.x, rq.shContrib.y, rq.shContrib.z, 0.0f));
             }
-            if (rq.probe) stS(&w.prBetaPdf[slot], make_float4(rq.prBeta.x, rq.prBeta.y, rq.prBeta.z, rq.prPdf));
+            if (rq.probe || deferProbe) stS(&w.prBetaPdf[slot], make_float4(rq.prBeta.x, rq.prBeta.y, rq.prBeta.z, rq.prPdf));
         }
         queuePush(qNext, cntNext, alive, slot);
         queuePush(w.qShadow, cntShadow, rq.shadow, slot);
