@@ -375,6 +375,33 @@ def test_chunked_and_overlapped_wavefronts_equal_the_plain_render(capi, engine, 
         assert np.abs(a - b).max() <= 2e-6 * max(1.0, float(np.abs(a).max()))
 
 
+@pytest.mark.parametrize("scene,kw", [("Cornell", {}), ("MeshLight", {}), ("Progressive", {"scale": 0.05})])
+def test_probe_folded_into_next_segment_equals_traced_probe(capi, engine, scene, kw):
+    """opaque, media-free scenes: a surviving path's BSDF probe is evaluated on its next segment's closest hit instead of being traced
+    (PTC_NO_PROBE_FUSION=1 traces it).  Same terms in the same order: images agree to rounding, far fewer probe rays."""
+    engine.build_scene(scene, **kw)
+    engine.set_render_info(width=128, height=96, samples=16, batch_size=8)
+    desc, rp = engine.scene_desc(), engine.render_params()
+    cu = capi.Context(capi.load_cuda())
+    cu.upload_scene(desc)
+    cu.build_accel()
+    fused = cu.render(rp)[0]
+    sf = cu.stats()
+    os.environ["PTC_NO_PROBE_FUSION"] = "1"
+    try:
+        traced = cu.render(rp)[0]
+        st = cu.stats()
+    finally:
+        del os.environ["PTC_NO_PROBE_FUSION"]
+    cu.close()
+    assert np.isfinite(fused).all() and np.isfinite(traced).all()
+    assert st["probe_rays"] > 4 * max(sf["probe_rays"], 1) and sf["segments"] == st["segments"]
+    d = np.abs(fused[..., :3] - traced[..., :3]).max(axis=-1)
+    # a surface inside the first millimetre of the ray is seen by the traced probe only: a handful of pixels at most
+    assert np.mean(d > 1e-4 * np.maximum(1.0, traced[..., :3].max(axis=-1))) < 2e-3
+    assert abs(fused[..., :3].mean() / traced[..., :3].mean() - 1) < 1e-4
+
+
 def test_shadow_rays_through_alpha_tested_foliage(capi, engine):
     """media-free scene with transparent materials and a light: the device looks at every triangle a shadow ray crosses in one
     traversal (order-independent product of 1 - alpha), the oracle walks the candidates nearest first (raySecondary.rahit.glsl)"""

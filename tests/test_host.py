@@ -171,3 +171,17 @@ def test_atrium_is_sponza_class(capi):
     assert len(used) >= 20 and d.n_light_instances == 0
     assert eng.render_info() == dict(width=1920, height=1080, samples=1024, batch_size=16, depth=9)
     eng.close()
+
+
+@pytest.mark.parametrize("scene,kw", [("Progressive", {"scale": 0.05}), ("Cornell", {}), ("Fog", {"scale": 0.02, "texture_size": 16}),
+                                      ("Instanced", {"scale": 0.004, "texture_size": 16})])
+def test_workload_scenes_render_finite_images(capi, scene, kw):
+    """emissive meshes must not contain zero-area triangles: the light sampler divides by the triangle area (lightSampling.glsl:44-100)
+    and the power heuristic of an infinite pdf is NaN - the sphere of the progressive workload once had collapsed pole triangles"""
+    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng.build_scene(scene, **kw)
+    eng.set_render_info(width=96, height=64, samples=8, batch_size=8)
+    rad, alb, nrm = eng.render_to_memory()
+    assert np.isfinite(rad).all() and np.isfinite(alb).all() and np.isfinite(nrm).all()
+    assert rad[..., :3].mean() > 0
+    eng.close()

@@ -398,7 +398,11 @@ struct MeshBuilder {
         mesh->indices.push_back(c);
     }
     /* parametric surface p(u,v) on an nu x nv grid, smooth normals by finite differences */
-    void surface(int nu, int nv, const std::function<vec3(float, float)> &p, bool flip = false, float uvScaleU = 1, float uvScaleV = 1) {
+    /* dropDegenerate: leave out triangles with coincident corners (the poles of a sphere).  An EMISSIVE mesh must not contain them: the
+     * light sampler picks triangles uniformly and divides by their area (lightSampling.glsl:44-100), so a zero-area triangle gives an
+     * infinite pdf and the power heuristic returns NaN - in the reference exactly as here. */
+    void surface(int nu, int nv, const std::function<vec3(float, float)> &p, bool flip = false, float uvScaleU = 1, float uvScaleV = 1,
+                 bool dropDegenerate = false) {
         uint32_t base = (uint32_t)mesh->vertices.size();
         const float eps = 1e-3f;
         for (int j = 0; j <= nv; j++)
@@ -416,12 +420,21 @@ struct MeshBuilder {
         for (int j = 0; j < nv; j++)
             for (int i = 0; i < nu; i++) {
                 uint32_t a = base + j * (nu + 1) + i, b = a + 1, c = a + (nu + 1), d = c + 1;
+                auto put = [&](uint32_t x, uint32_t y, uint32_t z) {
+                    if (dropDegenerate) {
+                        auto pos = [&](uint32_t k) { const float *q = mesh->vertices[k].position; return vec3(q[0], q[1], q[2]); };
+                        const vec3 px = pos(x), py = pos(y), pz = pos(z);
+                        const float e2 = std::max(vm::dot(py - px, py - px), std::max(vm::dot(pz - px, pz - px), vm::dot(pz - py, pz - py)));
+                        if (vm::length(vm::cross(py - px, pz - px)) <= 1e-5f * e2) return; /* incl. sin(pi) != 0 in float at the far pole */
+                    }
+                    tri(x, y, z);
+                };
                 if (!flip) {
-                    tri(a, b, d);
-                    tri(a, d, c);
+                    put(a, b, d);
+                    put(a, d, c);
                 } else {
-                    tri(a, d, b);
-                    tri(a, c, d);
+                    put(a, d, b);
+                    put(a, c, d);
                 }
             }
     }
@@ -801,7 +814,7 @@ static void progressive(Engine &e, const Options &opt) {
         b.surface(16, 10, [&](float u, float v) {
             float th = 3.14159265f * v, ph = TWO_PI * u;
             return vec3(std::sin(th) * std::cos(ph), std::cos(th), std::sin(th) * std::sin(ph));
-        }, true);
+        }, true, 1, 1, true);
         sphere = registerMesh(e, "progressive/sphere", b.finish());
     }
     auto floorM = e.materials().createMaterial<MaterialPBRStandard>(AssetInfo("progressiveFloor"));
