@@ -502,13 +502,18 @@ __global__ void __launch_bounds__(TRV_BLOCK, TRV_EXTEND_MINBLOCKS) k_extend(Wave
 }
 
 /* ------------------------------------------------------------------ k_shade */
-/* process_volume_hit.glsl:1-80. Returns sampledMedium; on scattering fills the requests and the new ray. */
-PTC_D bool volumeEvent(const DScene &sc, const RenderConst &rc, Rng &rng, uint32_t flags, float3 &origin, float3 &dir, float3 &beta,
-                       float vtstart, float vtend, Requests &rq) {
+/* process_volume_hit.glsl:1-40: free flight through the medium the path is in.  Returns true when the path scatters before vtend
+ * (then sp is the scattering point); beta takes the transmittance / collision weights either way.  The light and phase-function
+ * sampling of a scattering event (:47-78) happen in k_shade next to the surface's, so that a warp samples its lights once. */
+struct MediumHit {
+    float3 sp, wo;
+    float g;
+};
+PTC_D bool freeFlight(const DScene &sc, Rng &rng, uint32_t flags, float3 origin, float3 dir, float3 &beta, float vtstart, float vtend, MediumHit &mh) {
     Medium md = loadMedium(sc, flags >> PF_VOL_SHIFT);
-    const float g = fmaxf(fminf(md.g, 0.99f), -0.99f);
+    mh.g = fmaxf(fminf(md.g, 0.99f), -0.99f);
     const float3 wdir = normalize(dir);
-    const float3 wo = -wdir;
+    mh.wo = -wdir;
     const float distInside = fmaxf(vtend - vtstart, PT_EPSILON);
     const uint32_t channel = min((uint32_t)(rnd(rng) * 3.0f), 2u);
     const float hitDistance = -logf(1.0f - rnd(rng)) / comp(md.sigma_t, (int)channel);
@@ -518,30 +523,7 @@ PTC_D bool volumeEvent(const DScene &sc, const RenderConst &rc, Rng &rng, uint32
     float pdf = (density.x + density.y + density.z) * 0.3333333f;
     if (pdf == 0.0f) pdf = 1.0f;
     beta *= sampled ? (T * md.sigma_s / pdf) : (T / pdf);
-    if (sampled) {
-        const float3 sp = origin + wdir * (vtstart + hitDistance);
-        LightSample ls = sampleLight(sc, rc, rng, sp);
-        if (!isBlack(ls.radiance)) {
-            const float p = hg(dot(wo, ls.dir), g);
-            if (p != 0.0f) {
-                float3 c = ls.radiance * p * beta / ls.pdf;
-                if (!ls.delta) c = c * powerHeuristic(ls.pdf, p);
-                rq.shadow = true;
-                rq.shOrigin = sp;
-                rq.shDir = ls.dir;
-                rq.shTmax = ls.tmax;
-                rq.shContrib = c;
-            }
-        }
-        const float2 h01 = rnd2(rng);
-        float3 nd;
-        const float spdf = hgSample(wo, nd, h01.x, h01.y, g);
-        origin = sp;
-        dir = nd;
-        rq.probe = true;
-        rq.prBeta = beta;
-        rq.prPdf = spdf;
-    }
+    mh.sp = origin + wdir * (vtstart + hitDistance);
     return sampled;
 }
 
@@ -564,8 +546,11 @@ PTC_D bool roulette(Rng &rng, uint32_t depth, float3 &beta) {
 /* LIGHTS: the light pick is not empty (rc.totalLights > 0); VOLUMES: a path can be inside a medium (camera volume or an instance that
  * changes it).  The common "environment only, no media" scene gets a kernel without the light-sampling and free-flight code (fewer
  * registers under the same launch bound); the instantiations are result-identical where their preconditions hold. */
+#ifndef SHADE_MINBLOCKS_LV
+#define SHADE_MINBLOCKS_LV 6 /* the instantiation with lights AND media (the largest): fog 5: 1291, 6: 1298, 7: 1273, 8: 1266 Mseg/s */
+#endif
 template <bool LIGHTS, bool VOLUMES>
-__global__ void __launch_bounds__(128, SHADE_MINBLOCKS) k_shade(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
+__global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV : SHADE_MINBLOCKS) k_shade(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
                                                          uint32_t firstSample) {
     const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_ACTIVE];
     const uint32_t *__restrict__ q = w.queue[bounce & 1u];
@@ -609,166 +594,193 @@ __global__ void __launch_bounds__(128, SHADE_MINBLOCKS) k_shade(Wave w, const __
             bool stop = false;
             bool doRoulette = true;
 
-            if (triPos >= 0) {
-                /* the free flight comes first: a path that scatters inside the medium never looks at the surface (no record fetch) */
-                bool sampledMedium = false;
-                if (VOLUMES && (flags & PF_INVOL)) sampledMedium = volumeEvent(sc, rc, rng, flags, origin, dir, beta, 0.001f, h.x, rq);
-                if (!sampledMedium) {
-                    Surf s;
-                    loadSurf(sc, triPos, h.y, h.z, true, s);
-                    Frame fr;
-                    fr.n = s.n;
-                    fr.t = s.t;
-                    const bool flipped = fixFrame(fr, rayDir);
-                    const ptc_material *mat = s.mat;
-                    const float tu = s.uv.x * __ldg(&mat->uv_tiling[0]), tv = s.uv.y * __ldg(&mat->uv_tiling[1]);
-                    const bool lambert = (int)__ldg(&mat->uv_tiling[2]) == PTC_MATERIAL_LAMBERT;
-                    bool passThrough = false;
-                    if (__ldg(&mat->metallic_roughness_ao[3]) > 0.0f) { /* stochastic transparency, rchit :66-96 */
-                        const float alpha = __ldg(&mat->albedo[3]) * texFetch(sc, __ldg(&mat->tex2[3]), tu, tv).x;
-                        const float r = rnd(rng);
-                        if (alpha < PT_EPSILON || r > alpha) {
-                            if (VOLUMES && s.inst->volFront != s.inst->volBack) volumeChange(s.inst, flipped, flags);
-                            origin = s.pos;
-                            dir = normalize(rayDir);
-                            passThrough = true;
-                            doRoulette = false;
-                        }
+            /* A. free flight, for rays that hit and rays that leave alike (process_volume_hit.glsl via rchit :60-64 and rmiss :44-51) */
+            bool sampledMedium = false;
+            MediumHit mh{};
+            if (VOLUMES && (flags & PF_INVOL)) {
+                const float vtend = triPos >= 0 ? h.x : fminf((float)(uint32_t)rc.sd.volumes[2], 10000.0f);
+                sampledMedium = freeFlight(sc, rng, flags, origin, dir, beta, 0.001f, vtend, mh);
+            }
+            /* B. what kind of event is this, and where does it sample its light from */
+            bool surfaceEvent = false; /* a surface that scatters (not passed through, not the first-hit emitter) */
+            float3 lightPoint = mh.sp;
+            Surf s;
+            Frame fr;
+            float3 albedo = f3(0.0f), wo = f3(0.0f);
+            Pbr pbr;
+            bool lambert = false;
+            if (!sampledMedium && triPos >= 0) {
+                loadSurf(sc, triPos, h.y, h.z, true, s);
+                fr.n = s.n;
+                fr.t = s.t;
+                const bool flipped = fixFrame(fr, rayDir);
+                const ptc_material *mat = s.mat;
+                const float tu = s.uv.x * __ldg(&mat->uv_tiling[0]), tv = s.uv.y * __ldg(&mat->uv_tiling[1]);
+                lambert = (int)__ldg(&mat->uv_tiling[2]) == PTC_MATERIAL_LAMBERT;
+                bool passThrough = false;
+                if (__ldg(&mat->metallic_roughness_ao[3]) > 0.0f) { /* stochastic transparency, rchit :66-96 */
+                    const float alpha = __ldg(&mat->albedo[3]) * texFetch(sc, __ldg(&mat->tex2[3]), tu, tv).x;
+                    const float r = rnd(rng);
+                    if (alpha < PT_EPSILON || r > alpha) {
+                        if (VOLUMES && s.inst->volFront != s.inst->volBack) volumeChange(s.inst, flipped, flags);
+                        origin = s.pos;
+                        dir = normalize(rayDir);
+                        passThrough = true;
+                        doRoulette = false;
                     }
-                    if (!passThrough) {
-                        applyNormal(fr, normalFromMap(f3(texFetch(sc, __ldg(&mat->tex2[1]), tu, tv))));
-                        const float3 albedo = ld3(mat->albedo) * f3(texFetch(sc, __ldg(&mat->tex1[0]), tu, tv));
-                        const float3 emissive = ld3(mat->emissive) * __ldg(&mat->emissive[3]) * f3(texFetch(sc, __ldg(&mat->tex2[0]), tu, tv));
-                        if (LIGHTS && !VOLUMES && (flags & PF_PROBE_DEFERRED)) {
-                            /* The previous event's BSDF probe (next_event_estimation.glsl:1-33) travels along this very ray.  With only
-                             * opaque surfaces and no media its first candidate decides it (rayNEE.rahit.glsl:44-54, 73-131) and that candidate
-                             * is this closest hit, so the probe was not traced: same terms, same place in the sum.  (The probe's range is
-                             * [1e-4, zfar), the path ray's [1e-3, 1e4): the far end is checked, a surface in the first millimetre is not seen.) */
-                            flags &= ~PF_PROBE_DEFERRED;
-                            if (!isBlackEps(emissive, 0.05f) && h.x < rc.sd.volumes[2] && !(dot(s.n, rayDir) > 0.0f)) {
-                                const float3 w0 = mulPoint(s.inst->m, s.p0), w1 = mulPoint(s.inst->m, s.p1), w2 = mulPoint(s.inst->m, s.p2);
-                                const float area = 0.5f * length(cross(w1 - w0, w2 - w0));
-                                const float pointPdf = (1.0f / (float)s.inst->numTriangles) * (1.0f / area);
-                                const float dp = dot(-rayDir, s.n);
-                                if (dp > 0.0f) {
-                                    const float3 ro = (rc.flags & PTC_FLAG_WORLD_ORIGIN_PROBE_PDF) ? origin : mulPoint(s.inst->w2o, origin);
-                                    const float dd = length(ro - s.pos);
-                                    const float pdfL = pointPdf * (dd * dd) / dp * (1.0f / (float)rc.totalLights);
-                                    const float4 bp = ldS(&w.prBetaPdf[slot]);
-                                    radiance = emissive * f3(bp) * powerHeuristic(bp.w, pdfL);
-                                    radianceAdded = !isBlack(emissive);
-                                }
-                            }
-                        }
-                        Pbr pbr;
-                        pbr.albedo = albedo;
-                        pbr.metallic = 0.0f;
-                        pbr.roughness = 1.0f;
-                        if (!lambert) {
-                            pbr.metallic = __ldg(&mat->metallic_roughness_ao[0]) * texFetch(sc, __ldg(&mat->tex1[1]), tu, tv).x;
-                            pbr.roughness = fmaxf(__ldg(&mat->metallic_roughness_ao[1]) * texFetch(sc, __ldg(&mat->tex1[2]), tu, tv).x, 0.035f);
-                        }
-                        const bool first = !(flags & PF_SURFACE);
-                        if (first) {
-                            stS(&w.aovAlbedo[slot], make_float4(albedo.x, albedo.y, albedo.z, 0.0f));
-                            float3 nn = fr.n * 0.5f + f3(0.5f);
-                            stS(&w.aovNormal[slot], make_float4(nn.x, nn.y, nn.z, 0.0f));
-                        }
-                        if (first && !isBlackEps(emissive, lambert ? 0.05f : 0.1f) && !flipped) {
-                            radiance = emissive * beta; /* emission only at the first surface (trap T2) */
-                            radianceAdded = true;
-                            stop = true;
-                            doRoulette = false;
-                        } else {
-                            flags |= PF_SURFACE;
-                            const float3 wo = toLocal(fr, -rayDir);
-                            LightSample ls;
-                            ls.radiance = f3(0.0f);
-                            if (LIGHTS) ls = sampleLight(sc, rc, rng, s.pos);
-                            if (LIGHTS && !isBlack(ls.radiance)) {
-                                const float3 wi = toLocal(fr, ls.dir);
-                                float3 F;
-                                float bsdfPdf;
-                                if (lambert) {
-                                    const float c = clampf(wi.y, 0.0f, 1.0f);
-                                    F = albedo * PT_INV_PI * c;
-                                    bsdfPdf = c * PT_INV_PI;
-                                } else {
-                                    F = pbrEval(pbr, wi, wo);
-                                    bsdfPdf = ls.delta ? 0.0f : pbrPdf(wi, wo, pbr);
-                                }
-                                if (!isBlack(F)) {
-                                    float3 c = ls.radiance * F * beta / ls.pdf;
-                                    if (!ls.delta) c = c * powerHeuristic(ls.pdf, bsdfPdf);
-                                    rq.shadow = true;
-                                    rq.shOrigin = s.pos;
-                                    rq.shDir = ls.dir;
-                                    rq.shTmax = ls.tmax;
-                                    rq.shContrib = c;
-                                }
-                            }
-                            float spdf;
-                            float3 wiL;
-                            if (lambert) {
-                                const float2 a01 = rnd2(rng);
-                                wiL = cosineHemisphere(a01.x, a01.y, spdf);
-                                origin = s.pos;
-                                dir = toWorld(fr, wiL);
-                                beta *= albedo;
-                            } else {
-                                const float2 a01 = rnd2(rng);
-                                const float a2 = rnd(rng);
-                                const float3 F = pbrSample(wiL, wo, spdf, pbr, a01.x, a01.y, a2);
-                                origin = s.pos;
-                                dir = toWorld(fr, wiL);
-                                if (isBlack(F)) {
-                                    stop = true;
-                                    doRoulette = false;
-                                } else {
-                                    beta *= clamp3(F / spdf, 0.0f, 1.0f);
-                                }
-                            }
-                            if (!stop) {
-                                rq.probe = true;
-                                rq.prBeta = beta;
-                                rq.prPdf = spdf;
+                }
+                if (!passThrough) {
+                    applyNormal(fr, normalFromMap(f3(texFetch(sc, __ldg(&mat->tex2[1]), tu, tv))));
+                    albedo = ld3(mat->albedo) * f3(texFetch(sc, __ldg(&mat->tex1[0]), tu, tv));
+                    const float3 emissive = ld3(mat->emissive) * __ldg(&mat->emissive[3]) * f3(texFetch(sc, __ldg(&mat->tex2[0]), tu, tv));
+                    if (LIGHTS && !VOLUMES && (flags & PF_PROBE_DEFERRED)) {
+                        /* The previous event's BSDF probe (next_event_estimation.glsl:1-33) travels along this very ray.  With only
+                         * opaque surfaces and no media its first candidate decides it (rayNEE.rahit.glsl:44-54, 73-131) and that candidate
+                         * is this closest hit, so the probe was not traced: same terms, same place in the sum.  (The probe's range is
+                         * [1e-4, zfar), the path ray's [1e-3, 1e4): the far end is checked, a surface in the first millimetre is not seen.) */
+                        flags &= ~PF_PROBE_DEFERRED;
+                        if (!isBlackEps(emissive, 0.05f) && h.x < rc.sd.volumes[2] && !(dot(s.n, rayDir) > 0.0f)) {
+                            const float3 w0 = mulPoint(s.inst->m, s.p0), w1 = mulPoint(s.inst->m, s.p1), w2 = mulPoint(s.inst->m, s.p2);
+                            const float area = 0.5f * length(cross(w1 - w0, w2 - w0));
+                            const float pointPdf = (1.0f / (float)s.inst->numTriangles) * (1.0f / area);
+                            const float dp = dot(-rayDir, s.n);
+                            if (dp > 0.0f) {
+                                const float3 ro = (rc.flags & PTC_FLAG_WORLD_ORIGIN_PROBE_PDF) ? origin : mulPoint(s.inst->w2o, origin);
+                                const float dd = length(ro - s.pos);
+                                const float pdfL = pointPdf * (dd * dd) / dp * (1.0f / (float)rc.totalLights);
+                                const float4 bp = ldS(&w.prBetaPdf[slot]);
+                                radiance = emissive * f3(bp) * powerHeuristic(bp.w, pdfL);
+                                radianceAdded = !isBlack(emissive);
                             }
                         }
                     }
-                }
-            } else { /* rayPrimary.rmiss.glsl:40-106 */
-                bool sampledMedium = false;
-                if (VOLUMES && (flags & PF_INVOL)) {
-                    const float vtend = fminf((float)(uint32_t)rc.sd.volumes[2], 10000.0f);
-                    sampledMedium = volumeEvent(sc, rc, rng, flags, origin, dir, beta, 0.001f, vtend, rq);
-                }
-                if (!sampledMedium) {
-                    stop = true;
-                    doRoulette = false;
-                    const float *bg = rc.sd.background;
+                    pbr.albedo = albedo;
+                    pbr.metallic = 0.0f;
+                    pbr.roughness = 1.0f;
+                    if (!lambert) {
+                        pbr.metallic = __ldg(&mat->metallic_roughness_ao[0]) * texFetch(sc, __ldg(&mat->tex1[1]), tu, tv).x;
+                        pbr.roughness = fmaxf(__ldg(&mat->metallic_roughness_ao[1]) * texFetch(sc, __ldg(&mat->tex1[2]), tu, tv).x, 0.035f);
+                    }
                     const bool first = !(flags & PF_SURFACE);
-                    float3 col = f3(0.0f), aov = f3(0.0f);
-                    if (bg[3] == 0.0f) {
-                        col = aov = f3(bg[0], bg[1], bg[2]);
-                    } else if (bg[3] == 1.0f) {
-                        col = aov = envFetch(sc, rayDir) * rc.sd.exposure[1];
-                    } else if (bg[3] == 2.0f) {
-                        aov = f3(bg[0], bg[1], bg[2]);
-                        col = first ? aov : envFetch(sc, rayDir);
-                    }
                     if (first) {
-                        stS(&w.aovAlbedo[slot], make_float4(aov.x, aov.y, aov.z, 0.0f));
-                        stS(&w.aovNormal[slot], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+                        stS(&w.aovAlbedo[slot], make_float4(albedo.x, albedo.y, albedo.z, 0.0f));
+                        float3 nn = fr.n * 0.5f + f3(0.5f);
+                        stS(&w.aovNormal[slot], make_float4(nn.x, nn.y, nn.z, 0.0f));
                     }
-                    /* environment found by a sampled direction while it is also light-sampled: power heuristic */
-                    if (rc.envLight && lastPdf > 0.0f && (bg[3] == 1.0f || (bg[3] == 2.0f && !first))) {
-                        const float2 uv = envd::equirectUV(normalize(rayDir));
-                        const envd::DeviceTables et{sc.envCdfV, sc.envCdfU};
-                        const float pl = (1.0f / (float)rc.totalLights) * envd::solidAnglePdf(envd::pdfUV(et, uv.x, uv.y), uv.y);
-                        col = col * powerHeuristic(lastPdf, pl);
+                    if (first && !isBlackEps(emissive, lambert ? 0.05f : 0.1f) && !flipped) {
+                        radiance = emissive * beta; /* emission only at the first surface (trap T2) */
+                        radianceAdded = true;
+                        stop = true;
+                        doRoulette = false;
+                    } else {
+                        flags |= PF_SURFACE;
+                        wo = toLocal(fr, -rayDir);
+                        surfaceEvent = true;
+                        lightPoint = s.pos;
                     }
-                    radiance = col * beta;
-                    radianceAdded = true;
+                }
+            } else if (!sampledMedium) { /* rayPrimary.rmiss.glsl:53-106 */
+                stop = true;
+                doRoulette = false;
+                const float *bg = rc.sd.background;
+                const bool first = !(flags & PF_SURFACE);
+                float3 col = f3(0.0f), aov = f3(0.0f);
+                if (bg[3] == 0.0f) {
+                    col = aov = f3(bg[0], bg[1], bg[2]);
+                } else if (bg[3] == 1.0f) {
+                    col = aov = envFetch(sc, rayDir) * rc.sd.exposure[1];
+                } else if (bg[3] == 2.0f) {
+                    aov = f3(bg[0], bg[1], bg[2]);
+                    col = first ? aov : envFetch(sc, rayDir);
+                }
+                if (first) {
+                    stS(&w.aovAlbedo[slot], make_float4(aov.x, aov.y, aov.z, 0.0f));
+                    stS(&w.aovNormal[slot], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+                }
+                /* environment found by a sampled direction while it is also light-sampled: power heuristic */
+                if (rc.envLight && lastPdf > 0.0f && (bg[3] == 1.0f || (bg[3] == 2.0f && !first))) {
+                    const float2 uv = envd::equirectUV(normalize(rayDir));
+                    const envd::DeviceTables et{sc.envCdfV, sc.envCdfU};
+                    const float pl = (1.0f / (float)rc.totalLights) * envd::solidAnglePdf(envd::pdfUV(et, uv.x, uv.y), uv.y);
+                    col = col * powerHeuristic(lastPdf, pl);
+                }
+                radiance = col * beta;
+                radianceAdded = true;
+            }
+            /* C. one light sample for every lane that scatters, in the medium or on a surface (lightSampling.glsl:1-106) */
+            LightSample ls;
+            ls.radiance = f3(0.0f);
+            if (LIGHTS && (sampledMedium || surfaceEvent)) ls = sampleLight(sc, rc, rng, lightPoint);
+            /* D. its weight, the shadow request, and the next direction */
+            if (VOLUMES && sampledMedium) { /* process_volume_hit.glsl:47-78 */
+                if (LIGHTS && !isBlack(ls.radiance)) {
+                    const float p = hg(dot(mh.wo, ls.dir), mh.g);
+                    if (p != 0.0f) {
+                        float3 c = ls.radiance * p * beta / ls.pdf;
+                        if (!ls.delta) c = c * powerHeuristic(ls.pdf, p);
+                        rq.shadow = true;
+                        rq.shOrigin = mh.sp;
+                        rq.shDir = ls.dir;
+                        rq.shTmax = ls.tmax;
+                        rq.shContrib = c;
+                    }
+                }
+                const float2 h01 = rnd2(rng);
+                float3 nd;
+                const float spdf = hgSample(mh.wo, nd, h01.x, h01.y, mh.g);
+                origin = mh.sp;
+                dir = nd;
+                rq.probe = true;
+                rq.prBeta = beta;
+                rq.prPdf = spdf;
+            } else if (surfaceEvent) {
+                if (LIGHTS && !isBlack(ls.radiance)) {
+                    const float3 wi = toLocal(fr, ls.dir);
+                    float3 F;
+                    float bsdfPdf;
+                    if (lambert) {
+                        const float c = clampf(wi.y, 0.0f, 1.0f);
+                        F = albedo * PT_INV_PI * c;
+                        bsdfPdf = c * PT_INV_PI;
+                    } else {
+                        F = pbrEval(pbr, wi, wo);
+                        bsdfPdf = ls.delta ? 0.0f : pbrPdf(wi, wo, pbr);
+                    }
+                    if (!isBlack(F)) {
+                        float3 c = ls.radiance * F * beta / ls.pdf;
+                        if (!ls.delta) c = c * powerHeuristic(ls.pdf, bsdfPdf);
+                        rq.shadow = true;
+                        rq.shOrigin = s.pos;
+                        rq.shDir = ls.dir;
+                        rq.shTmax = ls.tmax;
+                        rq.shContrib = c;
+                    }
+                }
+                float spdf;
+                float3 wiL;
+                if (lambert) {
+                    const float2 a01 = rnd2(rng);
+                    wiL = cosineHemisphere(a01.x, a01.y, spdf);
+                    origin = s.pos;
+                    dir = toWorld(fr, wiL);
+                    beta *= albedo;
+                } else {
+                    const float2 a01 = rnd2(rng);
+                    const float a2 = rnd(rng);
+                    const float3 F = pbrSample(wiL, wo, spdf, pbr, a01.x, a01.y, a2);
+                    origin = s.pos;
+                    dir = toWorld(fr, wiL);
+                    if (isBlack(F)) {
+                        stop = true;
+                        doRoulette = false;
+                    } else {
+                        beta *= clamp3(F / spdf, 0.0f, 1.0f);
+                    }
+                }
+                if (!stop) {
+                    rq.probe = true;
+                    rq.prBeta = beta;
+                    rq.prPdf = spdf;
                 }
             }
             if (doRoulette && !stop) stop = roulette(rng, bounce, beta);
