@@ -475,7 +475,9 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     const ShadeFn shadeFn = hasLights ? (hasVolumes ? (ShadeFn)wf::k_shade<true, true> : (ShadeFn)wf::k_shade<true, false>)
                                       : (hasVolumes ? (ShadeFn)wf::k_shade<false, true> : (ShadeFn)wf::k_shade<false, false>);
     const int gridShade = residentGrid((const void *)shadeFn, 128, capShade);
-    const int gridShadow = residentGrid((const void *)wf::k_shadow, TRV_BLOCK, capTrace);
+    using ChainFn = void (*)(wf::Wave, const DScene, const wf::RenderConst, uint32_t, wf::ExtendTune);
+    const ChainFn shadowFn = c->anyTransparent ? (ChainFn)wf::k_shadow<false> : (ChainFn)wf::k_shadow<true>;
+    const int gridShadow = residentGrid((const void *)shadowFn, TRV_BLOCK, capTrace);
     const int gridProbe = residentGrid((const void *)wf::k_probe, TRV_BLOCK, capTrace);
     uint64_t launches = 0, traceLaunches = 0;
     double traceMs = 0, shadeMs = 0, shadowMs = 0;
@@ -530,7 +532,7 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
                     launches += 2;
                     traceLaunches++;
                     if (rc.totalLights > 0) {
-                        timed(shadowMs, st, [&] { wf::k_shadow<<<gridShadow, TRV_BLOCK, 0, st>>>(w, sc, rc, d, c->tune); });
+                        timed(shadowMs, st, [&] { shadowFn<<<gridShadow, TRV_BLOCK, 0, st>>>(w, sc, rc, d, c->tune); });
                         launches++;
                     }
                     if (c->anyEmissive) {

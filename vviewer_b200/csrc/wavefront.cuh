@@ -822,21 +822,23 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
 /* ------------------------------------------------------------------ k_shadow */
 /* lightSampling.glsl:108-144 + raySecondary.rahit/.rchit/.rmiss with nearest-first candidate order (trap T1), as a
  * per-lane state machine on top of traceLoop: one query = the next-nearest candidate of the current hop. */
+template <bool OPAQUE> /* OPAQUE: no material of the scene is transparent - every hit shadows, the candidate code is not compiled */
 struct ShadowPolicy {
     /* Without media (no instance changes the volume, the camera is in none) the shadow chain is one ray whose transmittance is the
      * product of (1 - alpha) over the transparent surfaces it crosses, zero if any of them is opaque (raySecondary.rahit.glsl:31-72):
      * independent of the order, so one traversal that looks at every crossed triangle replaces one ordered query per surface. */
-    static constexpr bool ALL_HITS = true;
+    static constexpr bool ALL_HITS = !OPAQUE;
+    static constexpr bool opaqueScene = OPAQUE;
     const Wave &w;
     const DScene &sc;
     const RenderConst &rc;
     uint32_t slot, vol, hop, hops;
     float3 origin, thr; /* the direction lives in the traversal state */
     float distanceT, vtmin;
-    bool opaqueScene, everyHit;
+    bool everyHit;
     PTC_D ShadowPolicy(const Wave &w_, const DScene &sc_, const RenderConst &rc_)
-        : w(w_), sc(sc_), rc(rc_), slot(0), vol(0), hop(0), hops(0), distanceT(0.0f), vtmin(0.0f), opaqueScene(!sc_.anyTransparent),
-          everyHit(sc_.anyTransparent && !sc_.anyVolume && rc_.sd.volumes[0] == -1.0f) {}
+        : w(w_), sc(sc_), rc(rc_), slot(0), vol(0), hop(0), hops(0), distanceT(0.0f), vtmin(0.0f),
+          everyHit(!OPAQUE && !sc_.anyVolume && rc_.sd.volumes[0] == -1.0f) {}
     PTC_D bool anyHit() const { return opaqueScene || everyHit; } /* every surface is opaque: any hit shadows; all-hits: a decided ray is marked hit */
     PTC_D bool allHits() const { return everyHit; }
     /* a triangle the ray crosses (all-hits mode): true = the ray is shadowed */
@@ -929,11 +931,12 @@ struct ShadowPolicy {
 #ifndef CHAIN_MINBLOCKS
 #define CHAIN_MINBLOCKS 7
 #endif
+template <bool OPAQUE>
 __global__ void __launch_bounds__(TRV_BLOCK, CHAIN_MINBLOCKS) k_shadow(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
                                                       ExtendTune tune) {
     TRV_DECLARE_STACK(stack);
     __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
-    ShadowPolicy pol(w, sc, rc);
+    ShadowPolicy<OPAQUE> pol(w, sc, rc);
     TraceCounters cnt;
     traceLoop(sc, pol, w.counters[bounce * CNT_STRIDE + CNT_SHADOW], &w.counters[bounce * CNT_STRIDE + CNT_FETCH_SHADOW], tune, stack,
               stashMem + threadIdx.x, cnt);
