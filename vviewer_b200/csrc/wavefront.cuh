@@ -345,11 +345,11 @@ __global__ void __launch_bounds__(256) k_raygen(Wave w, const __grid_constant__ 
  *                                               false = the item retired at once
  *   bool next(trv::Trav &tr)                    the query is done (tr.best); true = tr describes another query to run
  *   bool anyHit()                                                          the running query may stop at the first accepted triangle */
-#define EXTEND_MIN_ACTIVE 24
+#define EXTEND_MIN_ACTIVE 28
 #define EXTEND_STASH 4      /* stashed triangle groups per lane */
 #define EXTEND_TRI_ENTER 12 /* lanes with stashed triangles that trigger a triangle phase */
 #define EXTEND_TRI_LEAVE 6  /* the phase ends when fewer lanes than this still hold triangles */
-#define EXTEND_BLOCKED 4    /* lanes that have nothing but stashed triangles left */
+#define EXTEND_BLOCKED 8    /* lanes that have nothing but stashed triangles left */
 struct ExtendTune { /* warp-vote thresholds; defaults above, overridable through PTC_EXTEND_TUNE for tuning runs */
     uint32_t minActive, triEnter, triLeave, blocked;
 };
