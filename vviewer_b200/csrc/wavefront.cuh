@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256) k_raygen(Wave w, const __grid_constant__ 
 }
 
 /* ------------------------------------------------------------------ warp-persistent traversal loop */
-/* Shared by k_extend, k_shadow and k_probe.  Every warp pulls work items from a queue (one global atomic per 256 items) and
+/* Shared by k_extend, k_shadow and k_probe.  Every warp pulls work items from a queue (one global atomic per 64 items) and
  * keeps one traversal per lane.  All 32 lanes run the same loop body:
  *   node phase      every lane with node work visits ONE wide node (8 boxes); triangle groups the visit exposes are NOT tested
  *                   right away (that ran at 2.8 of 32 lanes, profiles/README.md) but stashed in a per-lane shared-memory ring;
