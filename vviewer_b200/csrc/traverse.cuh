@@ -273,7 +273,12 @@ struct WarpFeeder {
 #ifndef TRV_FEED_CHUNK
 #define TRV_FEED_CHUNK 64
 #endif
-    static constexpr uint32_t CHUNK = TRV_FEED_CHUNK;
+    uint32_t chunk = TRV_FEED_CHUNK;
+    /* small launches (late bounces) get smaller chunks, so that every resident warp still finds work: about four chunks per warp */
+    PTC_D void sizeFor(uint32_t count) {
+        const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+        chunk = min((uint32_t)TRV_FEED_CHUNK, max(8u, (count / (warps * 4u)) & ~7u));
+    }
 
     /* returns the work index for this lane or 0xffffffff */
     PTC_D uint32_t fetch(bool need, uint32_t *__restrict__ counter, uint32_t count) {
@@ -282,10 +287,10 @@ struct WarpFeeder {
         const uint32_t lane = threadIdx.x & 31u;
         if (pos >= end && !exhausted) {
             uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(counter, CHUNK);
+            if (lane == 0) base = atomicAdd(counter, chunk);
             base = __shfl_sync(0xffffffffu, base, 0);
             pos = base;
-            end = min(base + CHUNK, count);
+            end = min(base + chunk, count);
             if (base >= count) {
                 exhausted = true;
                 pos = end = 0;

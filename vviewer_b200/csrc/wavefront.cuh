@@ -383,6 +383,7 @@ template <class Policy>
 PTC_D void traceLoop(const DScene &sc, Policy &pol, uint32_t count, uint32_t *fetchCounter, const ExtendTune tune, const trv::Stack &stack, uint2 *stash,
                      TraceCounters &cnt) {
     trv::WarpFeeder feeder;
+    feeder.sizeFor(count);
     trv::Trav tr;
     tr.sp = -1;
     tr.ng = tr.tg = make_uint2(0u, 0u);
