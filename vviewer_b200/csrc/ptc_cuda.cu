@@ -467,7 +467,10 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
         return c->smCount * perSm;
     };
     const int capTrace = overlap ? c->overlapTrace : 0, capShade = overlap ? c->overlapShade : 0;
-    const int gridExtend = residentGrid((const void *)wf::k_extend, TRV_BLOCK, capTrace);
+    using ExtendFn = void (*)(wf::Wave, const DScene, uint32_t, wf::ExtendTune);
+    const bool mediaInScene = c->anyVolumeChange || rp->scene.volumes[0] != -1.0f; /* = hasVolumes below: k_shade<*, true> writes the next tmax */
+    const ExtendFn extendFn = mediaInScene ? (ExtendFn)wf::k_extend<true> : (ExtendFn)wf::k_extend<false>;
+    const int gridExtend = residentGrid((const void *)extendFn, TRV_BLOCK, capTrace);
     /* k_shade specialisation (wavefront.cuh): lights in the pick / media reachable */
     const bool hasLights = rc.totalLights > 0, hasVolumes = c->anyVolumeChange || rp->scene.volumes[0] != -1.0f;
     rc.fuseProbe = (c->anyEmissive && hasLights && !c->anyTransparent && !hasVolumes && getenv("PTC_NO_PROBE_FUSION") == nullptr) ? 1u : 0u;
@@ -527,7 +530,7 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
                 wf::k_raygen<<<(nSlots + 255) / 256, 256, 0, st>>>(w, rc, nSlots, b * rp->batch_size + s0);
                 launches++;
                 for (uint32_t d = 0; d < rp->depth; d++) {
-                    timed(traceMs, st, [&] { wf::k_extend<<<gridExtend, TRV_BLOCK, 0, st>>>(w, sc, d, c->tune); });
+                    timed(traceMs, st, [&] { extendFn<<<gridExtend, TRV_BLOCK, 0, st>>>(w, sc, d, c->tune); });
                     timed(shadeMs, st, [&] { shadeFn<<<gridShade, 128, 0, st>>>(w, sc, rc, d, b * rp->batch_size + s0); });
                     launches += 2;
                     traceLaunches++;

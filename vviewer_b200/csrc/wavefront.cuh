@@ -467,6 +467,10 @@ PTC_D void traceCountersFlush(const Wave &w, const TraceCounters &cnt) {
 
 /* ------------------------------------------------------------------ k_extend */
 /* closest hit of the path ray: traceRayEXT at raygen.rgen.glsl:110 (tmin 1e-3, tmax 1e4) */
+/* VOLUMES: the scene has media.  A path inside a medium already knows how far it will fly (k_shade draws the free-flight distance of
+ * the NEXT segment from a copy of the random stream and leaves 1e-3 + distance in the slot's hit record): the ray only needs to be traced
+ * that far - a surface beyond the scattering point changes nothing (process_volume_hit.glsl:13-25). */
+template <bool VOLUMES>
 struct ExtendPolicy {
     static constexpr bool ALL_HITS = false;
     const Wave &w;
@@ -481,6 +485,7 @@ struct ExtendPolicy {
         tr.d = f3(d);
         tr.tmin = tr.t0 = 0.001f;
         tr.tmax = 10000.0f;
+        if (VOLUMES && bounce > 0u) tr.tmax = ldS(&w.hit[slot]).x;
         tr.id0 = 0xffffffffu;
         return true;
     }
@@ -493,10 +498,11 @@ struct ExtendPolicy {
 #ifndef TRV_EXTEND_MINBLOCKS
 #define TRV_EXTEND_MINBLOCKS 8
 #endif
+template <bool VOLUMES>
 __global__ void __launch_bounds__(TRV_BLOCK, TRV_EXTEND_MINBLOCKS) k_extend(Wave w, const __grid_constant__ DScene sc, uint32_t bounce, ExtendTune tune) {
     TRV_DECLARE_STACK(stack);
     __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
-    ExtendPolicy pol(w, bounce);
+    ExtendPolicy<VOLUMES> pol(w, bounce);
     TraceCounters cnt;
     traceLoop(sc, pol, w.counters[bounce * CNT_STRIDE + CNT_ACTIVE], &w.counters[bounce * CNT_STRIDE + CNT_FETCH], tune, stack, stashMem + threadIdx.x, cnt);
     traceCountersFlush(w, cnt);
@@ -803,6 +809,20 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
                 stS(&w.dirFlags[slot], make_float4(dir.x, dir.y, dir.z, __uint_as_float(flags)));
             }
             if (alive) stS(&w.beta[slot], make_float4(beta.x, beta.y, beta.z, lastPdf));
+            if (VOLUMES && alive) {
+                /* how far the next segment has to be traced (ExtendPolicy): inside a medium its free-flight distance is already
+                 * determined - the next event draws the same two numbers from the stored state (freeFlight) */
+                float tmaxNext = 10000.0f;
+                if (flags & PF_INVOL) {
+                    Rng ahead = rng;
+                    const Medium md = loadMedium(sc, flags >> PF_VOL_SHIFT);
+                    const uint32_t channel = min((uint32_t)(rnd(ahead) * 3.0f), 2u);
+                    const float hitDistance = -logf(1.0f - rnd(ahead)) / comp(md.sigma_t, (int)channel);
+                    /* only when the path scatters before the far end the miss shader uses (rayPrimary.rmiss.glsl:44-51) */
+                    if (hitDistance < fminf((float)(uint32_t)rc.sd.volumes[2], 10000.0f) - 0.001f) tmaxNext = fminf(0.001f + hitDistance, 10000.0f);
+                }
+                stS(&w.hit[slot], make_float4(tmaxNext, 0.0f, 0.0f, __int_as_float(-1)));
+            }
             if (radianceAdded) {
                 const float3 sum = f3(ldS(&w.radiance[slot])) + radiance; /* same single addition as before: bit-identical */
                 stS(&w.radiance[slot], make_float4(sum.x, sum.y, sum.z, 0.0f));
