@@ -126,7 +126,13 @@ def run_reference(args, rank, world):
     from vviewer_b200 import capi
     eng = build_engine(args, capi.ORACLE_LIB)
     ri = eng.render_info()
-    ctx = capi.Context(capi.load_oracle())
+    oracle = capi.load_oracle()
+    try:  # torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm uses ALL host cores whatever the environment says
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(os.cpu_count()))
+    except OSError:
+        pass
+    ctx = capi.Context(oracle)
     ctx.upload_scene(eng.scene_desc())
     ctx.build_accel()
     rp = eng.render_params()
@@ -317,6 +323,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is the CPU implementation on ALL host cores
+        # (set before the OpenMP runtime of the oracle library starts)
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
         run_reference(args, rank, world)
     else:
         run_cuda(args, rank, world, local_rank)
