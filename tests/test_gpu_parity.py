@@ -341,10 +341,11 @@ def test_env_importance_matches_oracle(capi, engine, scene, env_type):
     orc.close()
 
 
-@pytest.mark.parametrize("env", [{"PTC_MAX_SLOTS": str(96 * 96 * 3)}, {"PTC_OVERLAP": "5,2"}, {"PTC_OVERLAP": "4,3", "PTC_MAX_SLOTS": str(96 * 96)}])
+@pytest.mark.parametrize("env", [{"PTC_OVERLAP": "0", "PTC_MAX_SLOTS": str(96 * 96 * 3)}, {"PTC_OVERLAP": "5,2"}, {}, {"PTC_OVERLAP": "4,3", "PTC_MAX_SLOTS": str(96 * 96)}])
 def test_chunked_and_overlapped_wavefronts_equal_the_plain_render(capi, engine, env):
-    """a batch cut into chunks (what 4K frames need) and the optional two-stream overlap of wavefronts (PTC_OVERLAP, read when the context
-    is created) only change the order of float additions into the accumulators"""
+    """a batch cut into chunks (what 4K frames need) and the two-stream overlap of wavefronts (PTC_OVERLAP, read when the context is
+    created; {} = the default, two uncapped wavefronts) only change the order of float additions into the accumulators, compared with
+    one wavefront at a time (PTC_OVERLAP=0)"""
     engine.build_scene("Cornell")
     engine.set_render_info(width=96, height=96, samples=24, batch_size=8)
     desc, rp = engine.scene_desc(), engine.render_params()
@@ -358,17 +359,20 @@ def test_chunked_and_overlapped_wavefronts_equal_the_plain_render(capi, engine, 
         ctx.close()
         return out, st
 
-    plain, sp = render()
-    saved = {k: os.environ.get(k) for k in env}
-    os.environ.update(env)
-    try:
-        other, so = render()
-    finally:
-        for k, v in saved.items():
-            if v is None:
-                os.environ.pop(k, None)
-            else:
-                os.environ[k] = v
+    def with_env(e):
+        saved = {k: os.environ.get(k) for k in e}
+        os.environ.update(e)
+        try:
+            return render()
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+    plain, sp = with_env({"PTC_OVERLAP": "0"})
+    other, so = with_env(env)
     assert so["segments"] == sp["segments"] and so["shadow_rays"] == sp["shadow_rays"] and so["probe_rays"] == sp["probe_rays"]
     assert so["kernel_launches"] > sp["kernel_launches"]  # really ran in more pieces
     for a, b in zip(plain, other):

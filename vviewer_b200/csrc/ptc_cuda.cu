@@ -74,11 +74,13 @@ struct ptc_ctx {
     cudaEvent_t evA = nullptr, evB = nullptr, evAcc[2] = {nullptr, nullptr}, evFork = nullptr;
     static constexpr int RING = 8;
     cudaEvent_t evItem[RING] = {};
-    /* resident blocks per SM of the traversal / shading kernels while two wavefronts overlap; 0 = one wavefront at a time,
-     * the default: measured on the bench scene the overlap LOSES (2069 Mseg/s alone; 4+3 blocks 2030, 5+2 1888, 6+1 1604,
-     * profiles/r1_v4_kernel_experiments.log) - k_shade needs >= 3 blocks per SM to keep DRAM busy and k_extend loses as much
-     * with 4 as the overlap wins.  PTC_OVERLAP=t,s turns it on for experiments. */
-    int overlapTrace = 0, overlapShade = 0;
+    /* Two wavefronts (half batches) in flight on two streams; the numbers cap the resident blocks per SM of the traversal / shading
+     * kernels, 0 = one wavefront at a time.  Default: uncapped - every kernel asks for the whole GPU, so the other wavefront's kernel
+     * simply fills the SMs that the running kernel's last, longest rays leave idle (atrium +0.2 %, fog +1.2 %, Cornell +3.4 %).
+     * SHARING the SMs between the issue-bound k_extend and the DRAM-bound k_shade loses: 4+3 blocks 2030, 5+2 1888, 6+1 1604 against
+     * 2069 Mseg/s alone (profiles/r1_v4_kernel_experiments.log) - k_shade needs >= 3 blocks per SM to keep DRAM busy and k_extend
+     * loses as much with 4 as the overlap wins.  PTC_OVERLAP=t,s / PTC_OVERLAP=0 for experiments. */
+    int overlapTrace = 64, overlapShade = 64;
 
     std::atomic<float> progress{0.0f};
     ptc_stats stats{};
@@ -419,11 +421,9 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
 
     /* Samples of one batch run concurrently as a wavefront; very large batches are cut into chunks that fit the wave.
      *
-     * Optional (PTC_OVERLAP, off by default - see ptc_ctx::overlapTrace): two wavefronts in flight, each on its own stream.
-     * k_extend is instruction-issue bound (3-4 % of DRAM throughput) and k_shade is DRAM bound (~30 % issue), so the
-     * traversal of one wavefront can overlap the shading of the other.  Both are persistent kernels that pull work from
-     * device queues, so they are launched with FEWER resident blocks per SM (overlapTrace + overlapShade share an SM's
-     * registers) and any mix of phases keeps the SMs full.  A batch is split into two half-batch wavefronts, so the
+     * Two wavefronts are in flight, each on its own stream (PTC_OVERLAP, see ptc_ctx::overlapTrace): the kernels of one fill the SMs
+     * that the tail of the other's running kernel leaves idle.  All of them are persistent kernels that pull work from device
+     * queues, so any number of resident blocks makes progress.  A batch is split into two half-batch wavefronts, so the
      * path-state memory is what one full batch uses.  Work items are accumulated in a fixed order (event chain), which
      * keeps the image deterministic. */
     const bool timeKernels = (rp->flags & PTC_FLAG_TIME_KERNELS) != 0;
