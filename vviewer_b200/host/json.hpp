@@ -26,7 +26,7 @@ public:
     Value() {}
     Value(bool b) : m_type(Type::Bool), m_bool(b) {}
     Value(double d) : m_type(Type::Number), m_num(d) {}
-    Value(float d) : m_type(Type::Number), m_num((double)d), m_single(true) {}
+    Value(float d) : m_type(Type::Number), m_single(true), m_num((double)d) {}
     Value(int d) : m_type(Type::Number), m_num(d) {}
     Value(unsigned d) : m_type(Type::Number), m_num(d) {}
     Value(const char *s) : m_type(Type::String), m_str(s) {}
