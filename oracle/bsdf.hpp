@@ -159,11 +159,16 @@ inline vec2 concentricSampleDisk(vec2 r) {
     return {rr * std::cos(theta), rr * std::sin(theta)};
 }
 
-/* pt/MIS.glsl:5-10 */
+/* pt/MIS.glsl:5-10.  One guard the shader lacks: a density above sqrt(FLT_MAX) = 1.8e19 (a mesh light seen exactly edge-on:
+ * d^2 / cos -> inf, lightSampling.glsl:92) squares to inf and the shader's inf / inf is NaN, which poisons the pixel for good
+ * (seen once in 134 M samples of the MeshLight recipe).  The limit of the expression is returned instead; finite cases are
+ * the shader's arithmetic unchanged.  The device code carries the same guard. */
 inline float PowerHeuristic(int nf, float fPdf, int ng, float gPdf) {
     float f = nf * fPdf;
     float g = ng * gPdf;
-    return (f * f) / (f * f + g * g);
+    float f2 = f * f, g2 = g * g;
+    if (std::isinf(f2)) return std::isinf(g2) ? 0.5f : 1.0f;
+    return f2 / (f2 + g2);
 }
 
 /* include/brdfs/common.glsl:3-7 */

@@ -3,6 +3,7 @@ tests/golden/reference_images/): renders every RenderTests.cpp recipe with the o
 and writes tests/golden/oracle_vs_reference.json (committed).  Run here on CPU:
 
     python tests/golden/run_oracle_goldens.py [--spp-scale 1.0] [names...]
+    python tests/golden/run_oracle_goldens.py --backend cuda [--spp-scale 4.0] [names...]   (on a B200: writes cuda_vs_reference.json)
 
 Metrics: RGB MSE after the same RGBE quantisation the goldens went through, mean-luminance ratio,
 99th percentile relative error after a 3x3 box filter.  GLTF_ref goes through the from-scratch glTF importer
@@ -36,14 +37,18 @@ def compare(img, ref_path):
 def main():
     args = sys.argv[1:]
     scale = 1.0
-    if args and args[0] == "--spp-scale":
-        scale = float(args[1])
+    backend = "oracle"
+    while args and args[0] in ("--spp-scale", "--backend"):
+        if args[0] == "--spp-scale":
+            scale = float(args[1])
+        else:
+            backend = args[1]
         args = args[2:]
     names = args or SCENES
-    out_path = os.path.join(HERE, "oracle_vs_reference.json")
+    out_path = os.path.join(HERE, "oracle_vs_reference.json" if backend == "oracle" else "cuda_vs_reference.json")
     results = json.load(open(out_path)) if os.path.exists(out_path) else {}
     for name in names:
-        eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+        eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB) if backend == "oracle" else capi.HostEngine()
         eng.build_scene(name)
         ri = eng.render_info()
         spp = max(ri["batch_size"], int(ri["samples"] * scale) // ri["batch_size"] * ri["batch_size"])

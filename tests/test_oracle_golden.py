@@ -6,6 +6,8 @@ SURVEY §8c limits and (2) re-renders a few cheap recipes live so a regression o
 import json
 import os
 
+import numpy as np
+
 import pytest
 
 from imgmetrics import mean_lum_ratio, mse, p99_rel_err, rgbe_roundtrip
@@ -54,3 +56,16 @@ def test_oracle_rerender_matches_golden(capi, scene, spp_div):
     assert mse(q, ref) <= 2e-4
     assert abs(mean_lum_ratio(q, ref) - 1) <= 0.01
     assert p99_rel_err(q, ref) <= 0.06 * (2 if spp_div > 1 else 1)
+
+
+CUDA_RESULTS = json.load(open(os.path.join(ROOT, "tests", "golden", "cuda_vs_reference.json")))
+
+
+@pytest.mark.parametrize("scene", ALL)
+def test_committed_cuda_results_within_limits(scene):
+    """tests/golden/cuda_vs_reference.json: every recipe rendered on a B200 through RendererPathTracing::render() at 4x the golden's
+    sample count (run_oracle_goldens.py --backend cuda); the live check is tests/test_gpu_parity.py::test_render_matches_reference_golden"""
+    r = CUDA_RESULTS[scene]
+    assert np.isfinite([r["mse"], r["lum_ratio"], r["p99_rel"]]).all(), r
+    assert r["mse"] <= NOISY.get(scene, 2e-4), r
+    assert abs(r["lum_ratio"] - 1) <= 0.01, r

@@ -531,3 +531,16 @@ def test_sobol_sampler_lowers_the_error_of_a_render(capi, oracle_lib):
     assert err[capi.PTC_FLAG_SAMPLER_SOBOL] < 0.8 * err[0], err
     ctx.close()
     eng.close()
+
+
+def test_power_heuristic_does_not_overflow_to_nan(capi, oracle_lib):
+    """a mesh light seen edge-on from a point in its own plane: the light density d^2 / cos exceeds sqrt(FLT_MAX); the shader's
+    f^2 / (f^2 + g^2) would be inf / inf.  The render must stay finite."""
+    d, keep = make_quad_scene(capi, emissive=True)
+    ctx = capi.Context(oracle_lib)
+    ctx.upload_scene(C.byref(d))
+    ctx.build_accel()
+    rp = look_down_params(capi, w=24, h=24, spp=256, batch=32, depth=4, bg=(0.0, 0.0, 0.0))
+    rad = ctx.render(rp)[0]
+    assert np.isfinite(rad).all()
+    ctx.close()

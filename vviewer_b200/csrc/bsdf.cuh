@@ -141,8 +141,11 @@ PTC_D float2 sampleTriangle(float u0, float u1) { /* :42-46 */
     float a = sqrtf(1.0f - u0);
     return make_float2(1.0f - a, a * u1);
 }
-PTC_D float powerHeuristic(float fPdf, float gPdf) { /* MIS.glsl:5-10 with nf = ng = 1 */
+/* MIS.glsl:5-10 with nf = ng = 1.  One guard the shader lacks (same in oracle/bsdf.hpp): a density above sqrt(FLT_MAX) - a mesh light
+ * seen exactly edge-on - squares to inf and inf / inf is NaN; the limit of the expression is returned instead. */
+PTC_D float powerHeuristic(float fPdf, float gPdf) {
     float f2 = fPdf * fPdf, g2 = gPdf * gPdf;
+    if (isinf(f2)) return isinf(g2) ? 0.5f : 1.0f;
     return f2 / (f2 + g2);
 }
 

@@ -275,6 +275,13 @@ PTC_D bool rayMeetsEmitters(const DScene &sc, float3 o, float3 d) {
     return false;
 }
 
+#ifdef PTC_NAN_TRAP
+#define NAN_TRAP(cond, ...) do { if (cond) printf(__VA_ARGS__); } while (0)
+#else
+#define NAN_TRAP(cond, ...) do { } while (0)
+#endif
+#define BAD3(v) (!(isfinite((v).x) && isfinite((v).y) && isfinite((v).z)))
+
 /* requests produced by one shading event */
 struct Requests {
     bool shadow, probe;
@@ -658,6 +665,8 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
                                 const float4 bp = ldS(&w.prBetaPdf[slot]);
                                 radiance = emissive * f3(bp) * powerHeuristic(bp.w, pdfL);
                                 radianceAdded = !isBlack(emissive);
+                                NAN_TRAP(BAD3(radiance), "[trap] deferred probe slot %u bounce %u: e %g %g %g bp %g %g %g %g pdfL %g area %g dd %g dp %g\n", slot, bounce, emissive.x, emissive.y,
+                                         emissive.z, bp.x, bp.y, bp.z, bp.w, pdfL, area, dd, dp);
                             }
                         }
                     }
@@ -756,6 +765,8 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
                     if (!isBlack(F)) {
                         float3 c = ls.radiance * F * beta / ls.pdf;
                         if (!ls.delta) c = c * powerHeuristic(ls.pdf, bsdfPdf);
+                        NAN_TRAP(BAD3(c), "[trap] surface NEE slot %u bounce %u: c %g %g %g L %g %g %g F %g %g %g beta %g %g %g lpdf %g bpdf %g delta %d lambert %d wi %g %g %g wo %g %g %g\n", slot, bounce,
+                                 c.x, c.y, c.z, ls.radiance.x, ls.radiance.y, ls.radiance.z, F.x, F.y, F.z, beta.x, beta.y, beta.z, ls.pdf, bsdfPdf, (int)ls.delta, (int)lambert, wi.x, wi.y, wi.z, wo.x, wo.y, wo.z);
                         rq.shadow = true;
                         rq.shOrigin = s.pos;
                         rq.shDir = ls.dir;
@@ -790,6 +801,9 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
                     rq.prPdf = spdf;
                 }
             }
+            NAN_TRAP(BAD3(beta) || BAD3(dir) || BAD3(origin), "[trap] state slot %u bounce %u: beta %g %g %g dir %g %g %g origin %g %g %g surfaceEvent %d lambert %d\n", slot, bounce, beta.x, beta.y,
+                     beta.z, dir.x, dir.y, dir.z, origin.x, origin.y, origin.z, (int)surfaceEvent, (int)lambert);
+            NAN_TRAP(radianceAdded && BAD3(radiance), "[trap] radiance term slot %u bounce %u: %g %g %g\n", slot, bounce, radiance.x, radiance.y, radiance.z);
             if (doRoulette && !stop) stop = roulette(rng, bounce, beta);
             if (rq.probe) lastPdf = rq.prPdf; /* a new direction was sampled (surface or medium) */
             /* requests that can only return black are dropped (result-identical) */
