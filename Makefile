@@ -23,7 +23,7 @@ all: $(LIBDIR)/libptc_cuda.so $(LIBDIR)/libvengine_host.so $(LIBDIR)/offlinerend
 
 $(LIBDIR)/libptc_cuda.so: $(CUDA_SRCS) $(CUDA_HDRS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(NVCCFLAGS) -shared -o $@ vviewer_b200/csrc/ptc_cuda.cu -lcudart
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ vviewer_b200/csrc/ptc_cuda.cu -lcudart -ldl
 
 $(LIBDIR)/libvengine_host.so: $(HOST_SRCS) $(HOST_HDRS)
 	@mkdir -p $(LIBDIR)
@@ -38,7 +38,7 @@ oracle: $(ORCDIR)/liboracle.so
 stats: $(LIBDIR)/libptc_cuda_stats.so
 $(LIBDIR)/libptc_cuda_stats.so: $(CUDA_SRCS) $(CUDA_HDRS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(NVCCFLAGS) -DPTC_TRAV_STATS -shared -o $@ vviewer_b200/csrc/ptc_cuda.cu -lcudart
+	$(NVCC) $(NVCCFLAGS) -DPTC_TRAV_STATS -shared -o $@ vviewer_b200/csrc/ptc_cuda.cu -lcudart -ldl
 
 # -ffp-contract=off: the world-space flatten and the LBVH reference build must round exactly like the
 # device kernels, which use explicit __fmul_rn/__fadd_rn

@@ -9,9 +9,12 @@ One "step" = one batch (16 samples per pixel over the whole image) of that rende
   python bench.py --gpus N --steps K --warmup W            # the CUDA product
   python bench.py --impl reference ...                      # the reference estimator on the host cores (CPU oracle)
 
-N > 1: one process per GPU under torchrun; the scene is replicated, batches are dealt round-robin to
-the ranks (sample split, weak scaling: K batches per rank) and the three accumulation buffers are summed
-onto rank 0 with one NCCL reduce inside the timed region.
+N > 1: one process per GPU under torchrun.  Every rank owns one engine / one context of the product; the contexts join ONE
+NCCL communicator inside the product (ptc_comm_unique_id / ptc_comm_init_rank - torch.distributed only carries the 128-byte id,
+the barrier and the max-over-ranks of the timings).  The scene is replicated, the batches are dealt round-robin to the ranks
+(sample split, weak scaling: K batches per rank) and the product sums the three accumulation buffers onto rank 0 with one
+ncclReduce inside the timed region.  `e2e` goes through RendererPathTracing::render() with host buffers on every rank, and
+`frame` is the fixed 1024-spp frame (strong scaling: the frame's 64 batches split over the ranks), measured, not extrapolated.
 """
 import argparse
 import json
@@ -24,7 +27,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+from oracle import loader as oracle_loader  # noqa: E402  (cpu_baseline leg and --impl reference only)
+
 FRAME_SPP = 1024
+SHADING_RECORD_BYTES = 144  # vviewer_b200/csrc/lbvh.cuh::k_gather_shading
 
 
 def parse():
@@ -41,6 +47,8 @@ def parse():
     ap.add_argument("--texsize", type=int, default=1024)
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-frame", action="store_true", help="skip the measured 1024-spp frame (strong-scaling figure)")
+    ap.add_argument("--split", default="sample", choices=["sample", "tile"], help="how N > 1 GPUs partition the image")
     ap.add_argument("--cpu-spp", type=int, default=1, help="samples per pixel of one step of the reference arm (--impl reference)")
     ap.add_argument("--cpu-baseline-spp", type=int, default=12, help="samples per pixel of the cpu_baseline leg of the CUDA arm (about 10-15 s of CPU work)")
     return ap.parse_args()
@@ -110,9 +118,13 @@ def measured_peak():
     return 6650.0, "fallback"
 
 
-def build_engine(args, backend):
+def workload_name(args, ri):
+    return "C2 %s %dx%d batch %d depth %d (frame = %d spp)" % (args.scene, ri["width"], ri["height"], ri["batch_size"], ri["depth"], FRAME_SPP)
+
+
+def build_engine(args):
     from vviewer_b200 import capi
-    eng = capi.HostEngine(backend_lib=backend)
+    eng = capi.HostEngine()
     eng.build_scene(args.scene, texture_size=args.texsize, scale=args.scale)
     eng.set_render_info(width=args.width, height=args.height, batch_size=args.batch, depth=args.depth)
     return eng
@@ -124,9 +136,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from vviewer_b200 import capi
-    eng = build_engine(args, capi.ORACLE_LIB)
+    eng = build_engine(args)  # the host feeder only: the scene description is handed to the oracle below
     ri = eng.render_info()
-    oracle = capi.load_oracle()
+    oracle = oracle_loader.load_oracle()
     try:  # torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm uses ALL host cores whatever the environment says
         import ctypes
         ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(os.cpu_count()))
@@ -149,12 +161,11 @@ def run_reference(args, rank, world):
             ms += st["render_ms"]
     cores = os.cpu_count()
     value = seg / ms / 1e3 if ms > 0 else 0.0
-    sample = "%dx%d x %d spp per step (a full step is %d spp)" % (ri["width"], ri["height"], spp, ri["batch_size"])
+    sample = "%dx%d x %d spp per step (a bounded sample: a full step of this workload is %d spp)" % (ri["width"], ri["height"], spp, ri["batch_size"])
     line = {"impl": "reference", "metric": "Mpath-segments/s", "value": value, "unit": "Msegments/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2 %s %dx%d batch %d depth %d" % (args.scene, ri["width"], ri["height"], ri["batch_size"], ri["depth"]),
-                       "triangles": ctx.stats()["n_triangles"]},
+            "config": {"workload": workload_name(args, ri), "triangles": ctx.stats()["n_triangles"]},
             "cpu_baseline": {"value": value, "unit": "Msegments/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Msegments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -173,30 +184,38 @@ def run_cuda(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    def share_id(make):
+        """128 opaque bytes from rank 0 to everyone: the only thing torch.distributed carries for the product's communicator"""
+        box = [make() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
     cuda = capi.load_cuda()
-    eng = build_engine(args, capi.CUDA_LIB)
+    eng = build_engine(args)
     if not eng.backend_ok():
         raise RuntimeError("CUDA backend failed: " + eng.last_error())
     ri = eng.render_info()
     W, H, B, D = ri["width"], ri["height"], ri["batch_size"], ri["depth"]
     desc = eng.scene_desc()
     ctx = capi.Context(cuda, device=local_rank)
+    if world > 1:
+        ctx.comm_init_rank(share_id(ctx.unique_id), rank, world)   # device-timed leg
+        eng.comm_init_rank(share_id(eng.comm_unique_id), rank, world)  # plugin leg
+        eng.set_render_options(split=args.split)
     ctx.upload_scene(desc)
     ctx.build_accel()
     build_stats = ctx.stats()
-
-    # device-resident accumulation targets (torch owns the memory so NCCL can reduce them)
-    acc = torch.zeros((3, H, W, 4), dtype=torch.float32, device="cuda")
-    ptrs = [acc[i].data_ptr() for i in range(3)]
+    split_mode = capi.PTC_SPLIT_TILE if args.split == "tile" else capi.PTC_SPLIT_SAMPLE
 
     def render(n_batches, flags=0):
+        """n_batches per rank; with a communicator the product partitions the render and reduces onto rank 0 (device timed)"""
         rp = eng.render_params()
         rp.samples = n_batches * B * world
         rp.batch_size = B
         rp.flags = flags
         if world > 1:
-            rp.split_mode, rp.rank, rp.world = capi.PTC_SPLIT_SAMPLE, rank, world
-        ctx.render_device(rp, *ptrs)
+            rp.split_mode = split_mode
+        ctx.render_device(rp, None, None, None)
         return ctx.stats()
 
     def sync():
@@ -205,115 +224,123 @@ def run_cuda(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     render(max(args.warmup, 3))
-    if dist is not None:
-        dist.reduce(acc, dst=0)
     sync()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     t0 = time.perf_counter()
-    st = render(args.steps)             # K batches on this rank, device-timed with CUDA events on the library's stream
-    ev0.record()
-    if dist is not None:
-        dist.reduce(acc, dst=0)         # sum of the accumulation buffers over NVLink (the only exchange of the path)
-    ev1.record()
+    st = render(args.steps)             # K batches on this rank + the product's ncclReduce, device-timed with CUDA events on the library's streams
     sync()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    dev_ms = st["render_ms"] + (ev0.elapsed_time(ev1) if dist is not None else 0.0)
+    dev_ms = st["render_ms"]            # max over this context's devices, reduce included
     clocks = sampler.stop() if rank == 0 else None
 
-    t = torch.tensor([dev_ms, float(st["segments"]), float(st["kernel_launches"]), wall_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        tmax = t.clone()
+    def over_ranks(values):
+        t = torch.tensor(values, dtype=torch.float64, device="cuda")
+        if dist is None:
+            return t.tolist(), t.tolist()
+        tmax, tsum = t.clone(), t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, wall_ms = float(tmax[0]), float(tmax[3])
-        segments, launches = float(tsum[1]), int(tsum[2])
-    else:
-        segments, launches = float(st["segments"]), int(st["kernel_launches"])
+        return tmax.tolist(), tsum.tolist()
+
+    mx, sm = over_ranks([dev_ms, float(st["segments"]), float(st["kernel_launches"]), wall_ms, st["reduce_ms"]])
+    dev_ms, wall_ms, reduce_ms = mx[0], mx[3], mx[4]
+    segments, launches = sm[1], int(sm[2])
+
+    # ---- end to end through the public API (RendererPathTracing::render via the C++ plugin) on EVERY rank: host scene in, host
+    # images out on rank 0; includes flatten, H2D upload of the scene, BVH build, render, the NCCL reduce and D2H of the 3 targets
+    out = [np.empty(W * H * 4, np.float32) for _ in range(3)]  # the caller's host images, reused by every call
+
+    def plugin_render(total_batches):
+        eng.set_render_info(samples=total_batches * B)
+        sync()
+        t = time.perf_counter()
+        eng.render_to_memory(out)
+        dt = time.perf_counter() - t
+        est = eng.stats()
+        mxs, sms = over_ranks([dt, float(est["segments"])])
+        return mxs[0], sms[1]
+
+    plugin_render(world)  # warm-up of the plugin path (allocations, communicator)
+    e2e_s, e2e_seg = plugin_render(args.steps * world)
+    d = desc.contents
+    # textures / environment are resident after the first call (ptc_texture.uid): not copied in the timed call
+    h2d = d.n_vertices * 68 + d.n_indices * 4 + d.n_instances * 176 + d.n_materials * 128 + d.n_light_instances * 64 + d.n_light_data * 64
+    d2h = 3 * W * H * 16
+    e2e = {"value": e2e_seg / e2e_s / 1e6, "unit": "Msegments/s", "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps / world),
+           "seconds": e2e_s,
+           "note": "one RendererPathTracing::render() call per rank, %d batches per rank: flatten + scene upload (geometry, instances, materials; textures and "
+                   "environment keep their device copies by identity, like the reference's import-time upload) + BVH build + render + NCCL reduce "
+                   "inside the product + readback on rank 0; h2d per rank, d2h on rank 0 divided over the ranks" % args.steps}
+    frame = None
+    if not args.no_frame:
+        f_s, f_seg = plugin_render(FRAME_SPP // B)  # the WHOLE frame, its batches split over the ranks: strong scaling, measured
+        frame = {"spp": FRAME_SPP, "seconds": f_s, "Msegments_per_s": f_seg / f_s / 1e6, "split": args.split if world > 1 else "none",
+                 "note": "fixed %dx%d x %d spp frame through RendererPathTracing::render() with host buffers (upload + build + render + reduce + readback)" % (W, H, FRAME_SPP)}
 
     if rank != 0:
         if dist is not None:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
     value = segments / dev_ms / 1e3  # Msegments/s, whole job
-    # ---- roofline of the dominant kernel (k_extend), timed live with CUDA events on the launching stream
-    stp = render(2, flags=capi.PTC_FLAG_TIME_KERNELS)
-    bytes_per_ray, bvh_depth = algorithmic_bytes_per_ray(build_stats["n_triangles"])
-    peak, peak_kind = measured_peak()
-    rays = stp["segments"]
-    avg_launch_ms = stp["trace_ms"] / max(stp["trace_launches"], 1)
-    achieved = rays * bytes_per_ray / (stp["trace_ms"] * 1e-3) / 1e9 if stp["trace_ms"] > 0 else 0.0
-    share = {"extend": stp["trace_ms"], "shade": stp["shade_ms"], "shadow_probe": stp["shadow_ms"]}
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("k_extend_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    # second kernel (k_shade, DRAM bound): algorithmic bytes per segment with the actual record sizes - queue id 4,
-    # hit + origin + direction + throughput read 64, new origin + direction + throughput written 48, shading record 144, three texture
-    # taps of 16 B (albedo, normal, roughness of the bench scene's materials)
-    shade_bytes = 4 + 64 + 48 + 144 + 3 * 16
-    shade_gbs = stp["segments"] * shade_bytes / (stp["shade_ms"] * 1e-3) / 1e9 if stp["shade_ms"] > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "bytes_per_ray": bytes_per_ray, "bvh_depth": bvh_depth,
-                "avg_launch_ms": avg_launch_ms, "kernel_ms_share": share,
-                "k_shade": {"achieved": shade_gbs, "frac": shade_gbs / peak, "bytes_per_segment": shade_bytes,
-                            "note": "algorithmic bytes; the DRAM traffic at 32 B sector granularity is about twice that (profiles/r1_v3_k_shade_full_raw.csv)"}}
-
-    # ---- end to end through the public API (RendererPathTracing::render via the C++ plugin): host scene in,
-    # host images out; includes flatten, H2D upload of the scene, BVH build, render and D2H of the 3 targets
-    e2e = None
+    roofline, cpu = None, None
     if world == 1:
-        eng.set_render_info(samples=args.steps * B)
-        out = [np.empty(W * H * 4, np.float32) for _ in range(3)]  # the caller's host images, reused by both calls
-        eng.render_to_memory(out)  # warm-up of the plugin path (allocations)
-        t0 = time.perf_counter()
-        eng.render_to_memory(out)
-        e2e_s = time.perf_counter() - t0
-        est = eng.stats()
-        d = desc.contents
-        # textures / environment are resident after the first call (ptc_texture.uid): not copied in the timed call
-        h2d = d.n_vertices * 68 + d.n_indices * 4 + d.n_instances * 176 + d.n_materials * 128 + d.n_light_instances * 64 + d.n_light_data * 64
-        d2h = 3 * W * H * 16
-        e2e = {"value": est["segments"] / e2e_s / 1e6, "unit": "Msegments/s", "h2d_bytes_per_step": int(h2d / args.steps),
-               "d2h_bytes_per_step": int(d2h / args.steps), "seconds": e2e_s, "note": "one render() call of %d batches: flatten + scene upload (geometry, instances, materials; textures and "
-                       "environment keep their device copies by identity, like the reference's import-time upload) + BVH build + render + readback" % args.steps}
-    else:
-        e2e = {"value": segments / wall_ms / 1e3, "unit": "Msegments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "multi-GPU: wall clock of render_device + NCCL reduce, scene resident"}
+        # ---- roofline of the dominant kernel (k_extend), timed live with CUDA events on the launching stream
+        stp = render(2, flags=capi.PTC_FLAG_TIME_KERNELS)
+        bytes_per_ray, bvh_depth = algorithmic_bytes_per_ray(build_stats["n_triangles"])
+        peak, peak_kind = measured_peak()
+        rays = stp["segments"]
+        avg_launch_ms = stp["trace_ms"] / max(stp["trace_launches"], 1)
+        achieved = rays * bytes_per_ray / (stp["trace_ms"] * 1e-3) / 1e9 if stp["trace_ms"] > 0 else 0.0
+        share = {"extend": stp["trace_ms"], "shade": stp["shade_ms"], "shadow_probe": stp["shadow_ms"]}
+        traffic, shade_traffic = None, None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                traffic = tj.get("k_extend_dram_bytes_per_launch")
+                shade_traffic = tj.get("k_shade_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        # second kernel (k_shade, DRAM bound): algorithmic bytes per segment with the actual record sizes - queue id 4,
+        # hit + origin + direction + throughput read 64, new origin + direction + throughput written 48, shading record, three texture
+        # taps of 16 B (albedo, normal, roughness of the bench scene's materials)
+        shade_bytes = 4 + 64 + 48 + SHADING_RECORD_BYTES + 3 * 16
+        shade_gbs = stp["segments"] * shade_bytes / (stp["shade_ms"] * 1e-3) / 1e9 if stp["shade_ms"] > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "bytes_per_ray": bytes_per_ray, "bvh_depth": bvh_depth,
+                    "avg_launch_ms": avg_launch_ms, "kernel_ms_share": share,
+                    "k_shade": {"achieved": shade_gbs, "frac": shade_gbs / peak, "bytes_per_segment": shade_bytes, "traffic": shade_traffic}}
 
-    # ---- CPU baseline: the oracle on the host cores, bounded sample of the same workload
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
-        octx = capi.Context(capi.load_oracle())
-        octx.upload_scene(desc)
-        octx.build_accel()
-        rp = eng.render_params()
-        rp.samples = rp.batch_size = max(1, args.cpu_baseline_spp)
-        octx.render(rp, want_aovs=False)
-        ost = octx.stats()
-        cpu = {"value": ost["segments"] / ost["render_ms"] / 1e3, "unit": "Msegments/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "%dx%d x %d spp (%d/%d of a step), %.1f s of all host cores (OpenMP over image rows)" % (W, H, rp.samples, rp.samples, B, ost["render_ms"] / 1e3)}
-        octx.close()
+        # ---- CPU baseline: the oracle on the host cores, bounded sample of the same workload
+        if not args.no_cpu_baseline:
+            octx = capi.Context(oracle_loader.load_oracle())
+            octx.upload_scene(desc)
+            octx.build_accel()
+            rp = eng.render_params()
+            rp.samples = rp.batch_size = max(1, args.cpu_baseline_spp)
+            octx.render(rp, want_aovs=False)
+            ost = octx.stats()
+            cpu = {"value": ost["segments"] / ost["render_ms"] / 1e3, "unit": "Msegments/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": "%dx%d x %d spp (%d/%d of a step), %.1f s of all host cores (OpenMP over image rows)" % (W, H, rp.samples, rp.samples, B, ost["render_ms"] / 1e3)}
+            octx.close()
 
     ms_per_step = dev_ms / args.steps
     line = {"metric": "Mpath-segments/s", "value": value, "unit": "Msegments/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2 %s %dx%d batch %d depth %d (frame = %d spp)" % (args.scene, W, H, B, D, FRAME_SPP),
+            "config": {"workload": workload_name(args, ri),
                        "triangles": build_stats["n_triangles"], "l2": "inputs larger than L2 (%.1f GB of path state streamed per step)" % (W * H * B * 192 / 1e9),
-                       "split": "sample" if world > 1 else "none"},
-            "s_per_frame": ms_per_step * (FRAME_SPP / B) / world / 1e3, "segments_per_path": segments / (args.steps * world * W * H * B),
-            "build_ms": build_stats["build_ms"], "wall_ms": wall_ms, "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
+                       "split": args.split if world > 1 else "none"},
+            "s_per_frame": frame["seconds"] if frame else None, "frame": frame, "segments_per_path": segments / (args.steps * world * W * H * B),
+            "build_ms": build_stats["build_ms"], "reduce_ms": reduce_ms, "wall_ms": wall_ms, "clocks": clocks, "gpu_launches": launches, "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e}
     print(json.dumps(line))
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -164,7 +164,8 @@ typedef struct ptc_render_params {
     uint32_t width, height;
     uint32_t camera_type; /* ptc_camera_type; orthographic = true parallel rays (documented deviation T10) */
     float ortho_width, ortho_height;
-    /* partition: this context renders only its share; the sum over ranks is the full image */
+    /* partition: this context renders only its share; the sum over ranks is the full image (alpha = 1 is written by rank 0
+     * only, so the sum keeps it).  A multi-device context / a context with a communicator sets rank and world itself. */
     uint32_t split_mode; /* ptc_split_mode */
     uint32_t rank, world;
     uint32_t tile_size;  /* tile edge in pixels for PTC_SPLIT_TILE (0 = 32) */
@@ -174,6 +175,10 @@ typedef struct ptc_render_params {
 
 #define PTC_FLAG_WORLD_ORIGIN_PROBE_PDF 1u /* use the world-space ray origin in the probe-ray pdf instead of reproducing rayNEE.rahit.glsl:122 */
 #define PTC_FLAG_SAMPLER_SOBOL 4u         /* low-discrepancy sampler (shuffled, Owen-scrambled Sobol; plays the role of the reference's optional PMJ02BN sampler, rng_pmj.glsl) instead of the default xorshift stream */
+/* The reference's optional sampler (SAMPLING_PMJ in defines_pt.glsl:1-5): pbrt-v4 style PMJ02BN, rng_pmj.glsl:20-107, with the
+ * reference's own tables (math/PMJSequences.cpp: 16 x 16384 x 2 floats; math/BlueNoise.cpp: 48 x 128 x 128 floats).  Start
+ * dimension pixel.y * width + pixel.y like raygen.rgen.glsl:59.  Integer-exact between the product and the oracle. */
+#define PTC_FLAG_SAMPLER_PMJ 16u
 /* Extension, off for parity: the reference never light-samples the environment (lightSampling.glsl:101-106 is a TODO, trap T3).
  * With this flag an HDRI environment (type 1 or 2) becomes one more light of the uniform light pick: directions are drawn from a
  * 512 x 256 luminance x cos(latitude) table over the equirectangular domain, the shadow chain decides visibility, and both this
@@ -200,13 +205,30 @@ typedef struct ptc_stats {
     uint64_t n_bvh_nodes;
     uint64_t scene_bytes;     /* device bytes held by scene + accel */
     uint64_t reserved[4];
+    uint64_t upload_bytes;    /* host -> device bytes of the last ptc_upload_scene, per device (textures / the environment that stayed
+                                 resident by uid are not copied and not counted) */
+    double reduce_ms;         /* multi-GPU: the NCCL reduce of the accumulation buffers inside the last render */
 } ptc_stats;
 
 typedef struct ptc_ctx ptc_ctx;
 
 /* ---------------------------------------------------------------- lifecycle */
+/* device_ids == NULL / n_devices == 0: the calling thread's current device.
+ * n_devices > 1: ONE context drives several GPUs of the box: one worker thread + streams per GPU and an NCCL
+ * communicator over them (ncclCommInitAll).  ptc_upload_scene / ptc_build_accel then replicate the scene and its acceleration
+ * structure on every GPU (the build is deterministic), and ptc_render* partition the render over the GPUs - by tiles
+ * (PTC_SPLIT_TILE) or by sample batches (PTC_SPLIT_SAMPLE; also what PTC_SPLIT_NONE selects) - and sum the accumulation buffers
+ * onto the first device with one ncclReduce per GPU over NVLink; rank / world of ptc_render_params are filled in by the context. */
 PTC_API int ptc_create(ptc_ctx **out, const int *device_ids, int n_devices);
 PTC_API void ptc_destroy(ptc_ctx *ctx);
+PTC_API int ptc_device_count(const ptc_ctx *ctx);
+/* One process per GPU (torchrun, MPI): every rank creates a single-device context; ONE rank obtains 128 opaque bytes from
+ * ptc_comm_unique_id (ncclGetUniqueId) and the launcher hands them to all ranks, which each call ptc_comm_init_rank
+ * (ncclCommInitRank; collective).  From then on ptc_render* of every rank take part in one partitioned render: the context fills
+ * in rank / world, the buffers are reduced onto rank 0, and only rank 0's output pointers are written (others may pass NULL).
+ * The oracle has no communicator: both return non-zero there. */
+PTC_API int ptc_comm_unique_id(uint8_t *out128);
+PTC_API int ptc_comm_init_rank(ptc_ctx *ctx, const uint8_t *id128, int rank, int world);
 PTC_API const char *ptc_last_error(const ptc_ctx *ctx);
 PTC_API const char *ptc_backend_name(void); /* "cuda-sm_100a" or "cpu-oracle" */
 

@@ -925,6 +925,9 @@ PTC_API int ptc_create(ptc_ctx **out, const int *, int) {
     return 0;
 }
 PTC_API void ptc_destroy(ptc_ctx *ctx) { delete ctx; }
+PTC_API int ptc_device_count(const ptc_ctx *ctx) { return ctx ? 1 : 0; }
+PTC_API int ptc_comm_unique_id(uint8_t *) { return 1; } /* the oracle has no communicator */
+PTC_API int ptc_comm_init_rank(ptc_ctx *c, const uint8_t *, int, int) { return fail(c, "the CPU oracle has no communicator"); }
 PTC_API const char *ptc_last_error(const ptc_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *s) {
@@ -1020,11 +1023,13 @@ PTC_API int ptc_render(ptc_ctx *c, const ptc_render_params *rp, float *radiance,
     c->progress = 0.0f;
     auto t0 = std::chrono::steady_clock::now();
     const size_t npx = (size_t)W * H;
+    /* alpha = 1 is written by ONE rank of a partitioned render (include/ptc.h: the parts are summed) */
+    const float alpha = (rp->split_mode == PTC_SPLIT_NONE || world <= 1 || rp->rank == 0) ? 1.0f : 0.0f;
     for (float *buf : {radiance, albedo, normal})
         if (buf)
             for (size_t i = 0; i < npx; i++) {
                 buf[i * 4 + 0] = buf[i * 4 + 1] = buf[i * 4 + 2] = 0.0f;
-                buf[i * 4 + 3] = 1.0f;
+                buf[i * 4 + 3] = alpha;
             }
     Stats total;
     std::atomic<uint32_t> rowsDone{0};

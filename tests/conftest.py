@@ -7,6 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+from oracle import loader as oracle_loader  # noqa: E402
+
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 REF_IMAGES = os.path.join(GOLDEN_DIR, "reference_images")
 
@@ -19,7 +21,7 @@ def pytest_configure(config):
 def built():
     """Make sure the native libraries exist (the driver runs build() first; this covers a bare pytest)."""
     from vviewer_b200 import capi
-    need = [capi.HOST_LIB, capi.CUDA_LIB, capi.ORACLE_LIB]
+    need = [capi.HOST_LIB, capi.CUDA_LIB, oracle_loader.ORACLE_LIB]
     if not all(os.path.exists(p) for p in need):
         import __graft_entry__
         __graft_entry__.build()
@@ -33,7 +35,7 @@ def capi(built):
 
 @pytest.fixture(scope="session")
 def oracle_lib(capi):
-    return capi.load_oracle()
+    return oracle_loader.load_oracle()
 
 
 @pytest.fixture(scope="session")

@@ -48,7 +48,7 @@ def main():
     out_path = os.path.join(HERE, "oracle_vs_reference.json" if backend == "oracle" else "cuda_vs_reference.json")
     results = json.load(open(out_path)) if os.path.exists(out_path) else {}
     for name in names:
-        eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB) if backend == "oracle" else capi.HostEngine()
+        eng = capi.HostEngine() if backend == "oracle" else capi.HostEngine()
         eng.build_scene(name)
         ri = eng.render_info()
         spp = max(ri["batch_size"], int(ri["samples"] * scale) // ri["batch_size"] * ri["batch_size"])

@@ -42,3 +42,22 @@ def p99_rel_err(a, b, floor=0.02):
     la, lb = luminance(box3(a[..., :3])), luminance(box3(b[..., :3]))
     rel = np.abs(la - lb) / np.maximum(lb, floor)
     return float(np.percentile(rel, 99))
+
+
+def firefly_mask(ref, factor=3.0, floor=0.25):
+    """Pixels of a (golden) image that are isolated spikes: luminance above `factor` times the median of their 3x3
+    neighbourhood and more than `floor` above it.  A converged render has none; a 1024-2048 spp golden with a point light inside
+    a scattering medium has a few hundred (paths that scatter next to the light: the 1 / d^2 of lightSampling.glsl:20-31)."""
+    lum = luminance(np.asarray(ref[..., :3], np.float64))
+    p = np.pad(lum, 1, mode="edge")
+    h, w = lum.shape
+    stack = np.stack([p[dy:dy + h, dx:dx + w] for dy in range(3) for dx in range(3)])
+    med = np.median(stack, axis=0)
+    return (lum > factor * med) & (lum - med > floor)
+
+
+def mse_masked(a, b, mask):
+    """MSE over the pixels NOT in mask"""
+    d = (np.asarray(a[..., :3], np.float64) - np.asarray(b[..., :3], np.float64)) ** 2
+    keep = ~mask
+    return float(d[keep].mean()) if keep.any() else 0.0

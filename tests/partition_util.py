@@ -1,7 +1,7 @@
-"""Multi-GPU partitioning of one render: the scene is replicated, the image is cut into tiles or the
-sample batches are dealt round-robin, and the per-rank accumulation buffers are SUMMED (tiles are disjoint, so one
-reduce serves both modes).  One process per GPU; `torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is plumbing."""
-from . import capi
+"""Hand partition of one render over `world` ranks through the plain C-ABI fields (include/ptc.h: split_mode, rank, world,
+tile_size) - what a launcher without a communicator does; contexts that own several GPUs or a communicator fill these in
+themselves (ptc_create with n_devices > 1, ptc_comm_init_rank)."""
+from vviewer_b200 import capi
 
 MODES = {"none": capi.PTC_SPLIT_NONE, "tile": capi.PTC_SPLIT_TILE, "sample": capi.PTC_SPLIT_SAMPLE}
 
@@ -22,9 +22,3 @@ def batches_of_rank(samples, batch_size, rank, world, mode):
     if mode != "sample" or world <= 1:
         return batches
     return len(range(rank, batches, world))
-
-
-def reduce_to_root(dist, tensor, root=0):
-    """Sum the accumulation buffers onto the root (NCCL reduce over NVLink on GPUs)."""
-    dist.reduce(tensor, dst=root)
-    return tensor

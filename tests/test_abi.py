@@ -4,6 +4,7 @@ import os
 import re
 
 import pytest
+from oracle import loader as oracle_loader
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -20,7 +21,7 @@ def test_header_symbols_listed(capi):
 
 @pytest.mark.parametrize("which", ["cuda", "oracle"])
 def test_ptc_library_exports(capi, which):
-    path = capi.CUDA_LIB if which == "cuda" else capi.ORACLE_LIB
+    path = capi.CUDA_LIB if which == "cuda" else oracle_loader.ORACLE_LIB
     lib = ctypes.CDLL(path)
     for sym in capi.PTC_SYMBOLS:
         assert hasattr(lib, sym), "%s does not export %s" % (path, sym)
@@ -56,8 +57,10 @@ def test_cuda_library_fails_loudly_without_gpu(capi):
 
 
 def test_product_does_not_reference_oracle():
-    """The product sources (package + include) must never include, link or load anything under oracle/."""
+    """The product (package, headers, its binaries' sources) must never include, link, name or load anything under oracle/,
+    and must not be steerable to another backend: no path string, no ctypes / dlopen of a caller-named library, no --backend."""
     bad = []
+    word = re.compile(r"oracle", re.I)
     for base in ("vviewer_b200", "include"):
         for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
             if "_lib" in dirpath or "__pycache__" in dirpath:
@@ -65,9 +68,31 @@ def test_product_does_not_reference_oracle():
             for f in files:
                 if not f.endswith((".cu", ".cuh", ".cpp", ".hpp", ".h", ".py")):
                     continue
-                text = open(os.path.join(dirpath, f), errors="ignore").read()
-                for line in text.splitlines():
+                path = os.path.join(dirpath, f)
+                for ln, line in enumerate(open(path, errors="ignore").read().splitlines(), 1):
                     s = line.strip()
-                    if ("#include" in s and "oracle" in s) or "dlopen(\"oracle" in s:
-                        bad.append((f, s))
+                    code = s.split("//")[0]
+                    in_comment = s.startswith(("/*", "*", "//", "#", '"""')) or "/*" in s and s.index("/*") < (s.lower().index("oracle") if "oracle" in s.lower() else 0)
+                    # 1. the word may appear in prose (comments / docstrings explaining what the tests check), never in code or strings
+                    if word.search(code) and not in_comment and not (f.endswith(".py") and (s.startswith(("#", '"', "'")) or '"""' in s)):
+                        if re.search(r"[\"'][^\"']*oracle[^\"']*[\"']", s, re.I) or "#include" in s or "import" in s or "load" in s.lower():
+                            bad.append((path, ln, s))
+                    # 2. no run-time loading of a library the caller names
+                    if "dlopen(" in code and not any(k in code for k in ("libPath.c_str()", "(n, RTLD")):
+                        bad.append((path, ln, s))
+                    if "--backend" in s and "unknown" not in s:
+                        bad.append((path, ln, s))
+                    if f.endswith(".py") and re.search(r"CDLL\(|cdll\.LoadLibrary", code) and "path" not in code and "HOST_LIB" not in code:
+                        bad.append((path, ln, s))
     assert not bad, bad
+    # the two dlopen sites that exist open FIXED names: the CUDA core next to the host library, and NCCL
+    host = open(os.path.join(ROOT, "vviewer_b200", "host", "vengine.cpp")).read()
+    assert 'm_backend.load(selfDir() + "/libptc_cuda.so"' in host and host.count("dlopen(") == 1
+    core = open(os.path.join(ROOT, "vviewer_b200", "csrc", "ptc_cuda.cu")).read()
+    assert core.count("dlopen(") == 1 and '"libnccl.so.2"' in core
+    # the Python package exposes no oracle loader and the engine takes no backend argument
+    from vviewer_b200 import capi
+    assert not hasattr(capi, "ORACLE_LIB") and not hasattr(capi, "load_oracle")
+    import inspect
+    assert "backend" not in inspect.signature(capi.HostEngine.__init__).parameters
+    assert "backend_lib" not in open(os.path.join(ROOT, "include", "vengine_host.h")).read()

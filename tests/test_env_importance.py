@@ -15,7 +15,7 @@ from test_oracle_units import look_down_params, make_quad_scene
 
 @pytest.fixture(scope="module")
 def env_ctx(capi, oracle_lib):
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     eng.build_scene("EnvironmentMapLambert")
     ctx = capi.Context(oracle_lib)
     ctx.upload_scene(eng.scene_desc())
@@ -76,7 +76,7 @@ EXPECT = [("EnvironmentMapLambert", 1, (-0.01, 0.01)), ("EnvironmentMapLambert",
 
 @pytest.mark.parametrize("scene,env_type,band", EXPECT)
 def test_flag_keeps_the_expectation(capi, oracle_lib, scene, env_type, band):
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     eng.build_scene(scene)
     eng.set_render_info(width=64, height=64, samples=512, batch_size=64)
     rp = eng.render_params()

@@ -9,6 +9,7 @@ import pytest
 
 from imgmetrics import mean_lum_ratio, mse, p99_rel_err, rgbe_roundtrip
 from test_oracle_units import HIERARCHIES, check_lbvh, check_wide_bvh, look_down_params, make_quad_scene
+from oracle import loader as oracle_loader
 
 pytestmark = pytest.mark.gpu
 
@@ -31,7 +32,7 @@ def engine(capi):
 
 def both(capi, desc, hierarchy=None):
     out = {}
-    for label, lib in (("cuda", capi.load_cuda()), ("oracle", capi.load_oracle())):
+    for label, lib in (("cuda", capi.load_cuda()), ("oracle", oracle_loader.load_oracle())):
         ctx = capi.Context(lib)
         ctx.upload_scene(desc)
         ctx.build_accel(hierarchy)
@@ -146,7 +147,7 @@ def test_ray_set_parity(capi, engine, scene, kw, box, coplanar, hierarchy):
 
 # ---------------------------------------------------------------- (3) BSDF: 1e-5 relative on 1e5 random configurations
 def test_bsdf_parity(capi):
-    cu, orc = capi.Context(capi.load_cuda()), capi.Context(capi.load_oracle())
+    cu, orc = capi.Context(capi.load_cuda()), capi.Context(oracle_loader.load_oracle())
     rng = np.random.default_rng(5)
     n = 100000
     def dirs():
@@ -201,7 +202,7 @@ def test_env_lookup_parity(capi, engine):
 # ---------------------------------------------------------------- (5) renders: CUDA vs oracle at matched samples (same RNG streams)
 def test_sampler_points_bit_exact(capi):
     """Both samplers (default xorshift stream, shuffled Owen-scrambled Sobol) are integer arithmetic: identical on both sides."""
-    cu, orc = capi.Context(capi.load_cuda()), capi.Context(capi.load_oracle())
+    cu, orc = capi.Context(capi.load_cuda()), capi.Context(oracle_loader.load_oracle())
     for flags in (0, capi.PTC_FLAG_SAMPLER_SOBOL):
         for (px, py, w, first, count, dim) in [(0, 0, 256, 0, 1024, 0), (1919, 1079, 1920, 4000, 96, 7), (5, 9, 64, 1 << 20, 33, 40)]:
             a = cu.sampler_points(px, py, w, first, count, dim, flags)
@@ -492,7 +493,7 @@ def test_texture_identity_cache(capi):
 
 @pytest.mark.parametrize("mode", ["tile", "sample"])
 def test_partition_sums_to_full_render(capi, engine, mode):
-    from vviewer_b200 import parallel
+    import partition_util as parallel
     engine.build_scene("MeshLight")
     engine.set_render_info(width=160, height=96, samples=16, batch_size=4)
     cu = capi.Context(capi.load_cuda())
@@ -506,10 +507,11 @@ def test_partition_sums_to_full_render(capi, engine, mode):
     for r in range(world):
         rp = parallel.partition(engine.render_params(), r, world, mode, tile_size=32)
         part = np.stack(cu.render(rp))
-        total[..., :3] += part[..., :3]
+        total += part
         seg += cu.stats()["segments"]
     assert seg == seg_full
     assert np.allclose(total[..., :3], full[..., :3], rtol=1e-5, atol=1e-6)
+    assert np.all(total[..., 3] == 1.0) and np.all(full[..., 3] == 1.0)  # alpha is written by rank 0 alone: the sum keeps it
     cu.close()
 
 

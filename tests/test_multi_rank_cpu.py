@@ -6,6 +6,7 @@ import sys
 
 import numpy as np
 import pytest
+from oracle import loader as oracle_loader
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -22,21 +23,23 @@ def _worker(rank, world, port, mode, out_dir):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
-    from vviewer_b200 import capi, parallel
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from vviewer_b200 import capi
+    import partition_util as parallel
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     eng.build_scene("Cornell")
     eng.set_render_info(width=48, height=40, samples=8, batch_size=2, depth=5)
-    ctx = capi.Context(capi.load_oracle())
+    ctx = capi.Context(oracle_loader.load_oracle())
     ctx.upload_scene(eng.scene_desc())
     ctx.build_accel()
     rp = parallel.partition(eng.render_params(), rank, world, mode, tile_size=16)
     rad, alb, nrm = ctx.render(rp)
-    t = torch.from_numpy(np.stack([rad, alb, nrm])[..., :3].copy())
+    t = torch.from_numpy(np.stack([rad, alb, nrm]).copy())
     seg = torch.tensor([ctx.stats()["segments"]], dtype=torch.int64)
-    parallel.reduce_to_root(dist, t, 0)
+    dist.reduce(t, dst=0)  # the sum of the parts IS the image, alpha included (rank 0 alone writes the 1)
     dist.reduce(seg, dst=0)
     if rank == 0:
         np.save(os.path.join(out_dir, "sum_%s.npy" % mode), t.numpy())
@@ -54,14 +57,15 @@ def test_two_ranks_sum_to_full_image(capi, tmp_path, mode):
     total = np.load(str(tmp_path / ("sum_%s.npy" % mode)))
     seg = int(np.load(str(tmp_path / ("seg_%s.npy" % mode)))[0])
     # single-rank reference
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     eng.build_scene("Cornell")
     eng.set_render_info(width=48, height=40, samples=8, batch_size=2, depth=5)
-    ctx = capi.Context(capi.load_oracle())
+    ctx = capi.Context(oracle_loader.load_oracle())
     ctx.upload_scene(eng.scene_desc())
     ctx.build_accel()
     rad, alb, nrm = ctx.render(eng.render_params())
-    full = np.stack([rad, alb, nrm])[..., :3]
+    full = np.stack([rad, alb, nrm])
+    assert np.all(total[..., 3] == 1.0) and np.all(full[..., 3] == 1.0)  # alpha survives the sum
     assert seg == ctx.stats()["segments"]
     # same samples, only the floating-point summation order differs
     assert np.allclose(total, full, rtol=1e-5, atol=1e-6)
@@ -70,7 +74,7 @@ def test_two_ranks_sum_to_full_image(capi, tmp_path, mode):
 
 
 def test_batches_of_rank():
-    from vviewer_b200 import parallel
+    import partition_util as parallel
     assert [parallel.batches_of_rank(1024, 16, r, 8, "sample") for r in range(8)] == [8] * 8
     assert [parallel.batches_of_rank(70, 16, r, 3, "sample") for r in range(3)] == [2, 1, 1]
     assert parallel.batches_of_rank(70, 16, 1, 3, "tile") == 4

@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 from imgmetrics import mean_lum_ratio, mse, p99_rel_err, rgbe_roundtrip
+from oracle import loader as oracle_loader
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_DIR = os.path.join(ROOT, "tests", "golden", "reference_images")
@@ -45,11 +46,11 @@ def test_every_reference_golden_is_accounted_for():
 
 @pytest.mark.parametrize("scene,spp_div", [("EnvironmentMapPBR01", 1), ("EnvironmentMapLambert", 1), ("NormalMap", 1), ("FurnaceLambert", 4)])
 def test_oracle_rerender_matches_golden(capi, scene, spp_div):
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     eng.build_scene(scene)
     ri = eng.render_info()
     eng.set_render_info(samples=ri["samples"] // spp_div)
-    rad = eng.render_to_memory()[0]
+    rad = oracle_loader.oracle_render(eng)[0]
     eng.close()
     ref = capi.read_hdr(os.path.join(REF_DIR, scene + "_ref.hdr"))
     q = rgbe_roundtrip(rad)

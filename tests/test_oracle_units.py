@@ -296,7 +296,7 @@ HIERARCHIES = [0, 1]  # PTC_HIERARCHY_LBVH (Karras), PTC_HIERARCHY_PLOC
 @pytest.mark.parametrize("hierarchy", HIERARCHIES)
 @pytest.mark.parametrize("scene,bits", [("Volume5", 10), ("EnvironmentMap", 10)])
 def test_oracle_lbvh_invariants(capi, oracle_lib, scene, bits, hierarchy):
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     eng.build_scene(scene)
     ctx = capi.Context(oracle_lib)
     ctx.upload_scene(eng.scene_desc())
@@ -310,7 +310,7 @@ def test_oracle_lbvh_invariants(capi, oracle_lib, scene, bits, hierarchy):
 
 @pytest.mark.parametrize("hierarchy", HIERARCHIES)
 def test_oracle_lbvh_63bit_for_large_scenes(capi, oracle_lib, hierarchy):
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     eng.build_scene("Atrium", texture_size=4, scale=0.3)
     ctx = capi.Context(oracle_lib)
     ctx.upload_scene(eng.scene_desc())
@@ -386,7 +386,7 @@ def check_wide_bvh(W, L):
 @pytest.mark.parametrize("hierarchy", HIERARCHIES)
 @pytest.mark.parametrize("scene,kw", [("Volume5", {}), ("Cornell", {}), ("Hierarchy", {}), ("Atrium", dict(texture_size=4, scale=0.05))])
 def test_oracle_wide_bvh_invariants(capi, oracle_lib, scene, kw, hierarchy):
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     eng.build_scene(scene, **kw)
     ctx = capi.Context(oracle_lib)
     ctx.upload_scene(eng.scene_desc())
@@ -413,7 +413,7 @@ def sah_cost(L):
 
 def test_ploc_hierarchy_is_better_than_karras(capi, oracle_lib):
     """PLOC exists to lower the traversal cost: its SAH cost on the atrium must be clearly below the Karras tree's."""
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     eng.build_scene("Atrium", texture_size=4, scale=0.1)
     ctx = capi.Context(oracle_lib)
     ctx.upload_scene(eng.scene_desc())
@@ -454,7 +454,7 @@ def test_morton_bit_expansion_reference():
 
 def test_env_cubemap_lookup_matches_equirect(capi, oracle_lib):
     """createCubemap semantics: cubemap(dir) == bilinear equirect(sampleEquirectangularMap(dir)) up to resampling blur."""
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     eng.build_scene("EnvironmentMapLambert")
     d = eng.scene_desc().contents
     W, H = d.env.width, d.env.height
@@ -513,7 +513,7 @@ def test_sobol_sampler_points_are_scrambled_nets(octx, capi):
 def test_sobol_sampler_lowers_the_error_of_a_render(capi, oracle_lib):
     """Same estimator, same sample count: the low-discrepancy points must beat the default stream on a smooth integrand
     (environment-lit diffuse sphere), measured against a high sample count render."""
-    eng = capi.HostEngine(backend_lib=capi.ORACLE_LIB)
+    eng = capi.HostEngine()
     eng.build_scene("EnvironmentMapLambert")
     eng.set_render_info(width=48, height=48, samples=16, batch_size=16, depth=3)
     ctx = capi.Context(oracle_lib)

@@ -3,11 +3,12 @@ import sys, time, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vviewer_b200 import capi
+from oracle import loader as oracle_loader
 
 names = sys.argv[1:] or ["FurnaceLambert", "EnvironmentMap", "MeshLight", "Volume5", "Transparency"]
 cuda = capi.load_cuda()
-orc = capi.load_oracle()
-eng = capi.HostEngine(backend_lib=capi.CUDA_LIB)
+orc = oracle_loader.load_oracle()
+eng = capi.HostEngine()
 print("backend ok:", eng.backend_ok(), eng.last_error())
 for name in names:
     eng.build_scene(name)

@@ -2,6 +2,7 @@ import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vviewer_b200 import capi
+from oracle import loader as oracle_loader
 eng = capi.HostEngine()
 scene = sys.argv[1] if len(sys.argv) > 1 else "GLTF"
 flags = int(sys.argv[2]) if len(sys.argv) > 2 else 0
@@ -14,7 +15,7 @@ else:
 desc, rp = eng.scene_desc(), eng.render_params()
 rp.flags |= flags
 res = {}
-for label, lib in (("cuda", capi.load_cuda()), ("oracle", capi.load_oracle())):
+for label, lib in (("cuda", capi.load_cuda()), ("oracle", oracle_loader.load_oracle())):
     ctx = capi.Context(lib); ctx.upload_scene(desc); ctx.build_accel(); res[label] = ctx.render(rp); print(label, ctx.stats()["segments"]); ctx.close()
 for k, nm in enumerate(["radiance", "albedo", "normal"]):
     a, b = res["cuda"][k][..., :3], res["oracle"][k][..., :3]

@@ -5,8 +5,7 @@
 
 Nothing here computes anything: it only declares structures / prototypes and loads shared libraries.
 The product library is ``vviewer_b200/_lib/libptc_cuda.so``; loading it fails loudly when it is missing
-(there is no CPU fallback).  The oracle library is loaded only by tests, smoke() and bench.py's CPU legs
-through :func:`load_oracle`.
+(there is no CPU fallback, and nothing in this package knows where the test oracle lives).
 """
 import ctypes as C
 import os
@@ -17,7 +16,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_DIR = os.path.join(ROOT, "vviewer_b200", "_lib")
 CUDA_LIB = os.path.join(LIB_DIR, "libptc_cuda.so")
 HOST_LIB = os.path.join(LIB_DIR, "libvengine_host.so")
-ORACLE_LIB = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
 
 f32 = C.c_float
 u32 = C.c_uint32
@@ -82,7 +80,8 @@ class ptc_stats(C.Structure):
     _fields_ = [("segments", u64), ("path_rays", u64), ("shadow_rays", u64), ("shadow_hops", u64), ("probe_rays", u64),
                 ("probe_hops", u64), ("render_ms", C.c_double), ("trace_ms", C.c_double), ("shade_ms", C.c_double),
                 ("shadow_ms", C.c_double), ("build_ms", C.c_double), ("trace_launches", u64), ("kernel_launches", u64),
-                ("n_triangles", u64), ("n_bvh_nodes", u64), ("scene_bytes", u64), ("reserved", u64 * 4)]
+                ("n_triangles", u64), ("n_bvh_nodes", u64), ("scene_bytes", u64), ("reserved", u64 * 4),
+                ("upload_bytes", u64), ("reduce_ms", C.c_double)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -91,17 +90,19 @@ class ptc_stats(C.Structure):
 
 
 PTC_SPLIT_NONE, PTC_SPLIT_TILE, PTC_SPLIT_SAMPLE = 0, 1, 2
+PTC_CAMERA_PERSPECTIVE, PTC_CAMERA_ORTHOGRAPHIC = 0, 1
 PTC_FLAG_WORLD_ORIGIN_PROBE_PDF = 1
 PTC_FLAG_TIME_KERNELS = 2
 PTC_FLAG_SAMPLER_SOBOL = 4
 PTC_FLAG_ENV_IMPORTANCE = 8
+PTC_FLAG_SAMPLER_PMJ = 16
 PTC_HIERARCHY_LBVH, PTC_HIERARCHY_PLOC = 0, 1
 
 # every symbol include/ptc.h declares
-PTC_SYMBOLS = ["ptc_create", "ptc_destroy", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_set_build_options", "ptc_build_accel", "ptc_render",
+PTC_SYMBOLS = ["ptc_create", "ptc_destroy", "ptc_device_count", "ptc_comm_unique_id", "ptc_comm_init_rank", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_set_build_options", "ptc_build_accel", "ptc_render",
                "ptc_render_device", "ptc_progress", "ptc_get_stats", "ptc_trace_closest", "ptc_get_lbvh", "ptc_get_wide_bvh", "ptc_bsdf_eval",
                "ptc_bsdf_sample", "ptc_sampler_points", "ptc_env_lookup", "ptc_env_sample", "ptc_env_pdf"]
-VH_SYMBOLS = ["vh_engine_create", "vh_engine_destroy", "vh_backend_ok", "vh_last_error", "vh_scene_list", "vh_build_scene",
+VH_SYMBOLS = ["vh_set_sequence_frame", "vh_set_output", "vh_write_image", "vh_set_devices", "vh_device_count", "vh_comm_unique_id", "vh_comm_init_rank", "vh_set_render_options", "vh_engine_create", "vh_engine_destroy", "vh_backend_ok", "vh_last_error", "vh_scene_list", "vh_build_scene",
               "vh_set_render_info", "vh_get_render_info", "vh_scene_desc", "vh_render_params", "vh_render_to_memory", "vh_render",
               "vh_get_stats", "vh_read_hdr", "vh_write_hdr", "vh_import_model", "vh_add_model", "vh_import_scene", "vh_export_scene",
               "vh_describe", "vh_decode_image", "vh_render_progress"]
@@ -118,6 +119,12 @@ def _declare_ptc(lib):
     lib.ptc_destroy.restype = None
     lib.ptc_last_error.argtypes = [vp]
     lib.ptc_last_error.restype = C.c_char_p
+    lib.ptc_device_count.argtypes = [vp]
+    lib.ptc_device_count.restype = C.c_int
+    lib.ptc_comm_unique_id.argtypes = [vp]
+    lib.ptc_comm_unique_id.restype = C.c_int
+    lib.ptc_comm_init_rank.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.ptc_comm_init_rank.restype = C.c_int
     lib.ptc_backend_name.argtypes = []
     lib.ptc_backend_name.restype = C.c_char_p
     lib.ptc_upload_scene.argtypes = [vp, C.POINTER(ptc_scene_desc)]
@@ -157,7 +164,23 @@ def _declare_ptc(lib):
 
 def _declare_vh(lib):
     vp = C.c_void_p
-    lib.vh_engine_create.argtypes = [C.c_char_p, C.c_char_p]
+    lib.vh_set_devices.argtypes = [vp, _ip, C.c_int]
+    lib.vh_set_devices.restype = C.c_int
+    lib.vh_device_count.argtypes = [vp]
+    lib.vh_device_count.restype = C.c_int
+    lib.vh_comm_unique_id.argtypes = [vp, vp]
+    lib.vh_comm_unique_id.restype = C.c_int
+    lib.vh_comm_init_rank.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.vh_comm_init_rank.restype = C.c_int
+    lib.vh_set_render_options.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    lib.vh_set_render_options.restype = None
+    lib.vh_set_sequence_frame.argtypes = [vp, C.c_int]
+    lib.vh_set_sequence_frame.restype = C.c_int
+    lib.vh_set_output.argtypes = [vp, C.c_int, f32, C.c_int, C.c_int]
+    lib.vh_set_output.restype = None
+    lib.vh_write_image.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, vp, C.c_int, f32]
+    lib.vh_write_image.restype = C.c_int
+    lib.vh_engine_create.argtypes = [C.c_char_p]
     lib.vh_engine_create.restype = vp
     lib.vh_engine_destroy.argtypes = [vp]
     lib.vh_engine_destroy.restype = None
@@ -212,7 +235,6 @@ def load_ptc(path):
 
 _cuda = None
 _host = None
-_oracle = None
 
 
 def load_cuda():
@@ -221,14 +243,6 @@ def load_cuda():
     if _cuda is None:
         _cuda = load_ptc(CUDA_LIB)
     return _cuda
-
-
-def load_oracle():
-    """CPU restatement of the reference. TEST INFRASTRUCTURE: tests, smoke() and bench CPU legs only."""
-    global _oracle
-    if _oracle is None:
-        _oracle = load_ptc(ORACLE_LIB)
-    return _oracle
 
 
 def load_host():
@@ -248,13 +262,15 @@ class Context:
     """RAII wrapper of a ptc_ctx of one backend library."""
 
     def __init__(self, lib, device=None):
+        """device: None (current device), an index, or a list of indices (one context driving several GPUs over NCCL)"""
         self.lib = lib
         self.ctx = C.c_void_p()
         if device is None:
             rc = lib.ptc_create(C.byref(self.ctx), None, 0)
         else:
-            d = (C.c_int * 1)(int(device))
-            rc = lib.ptc_create(C.byref(self.ctx), d, 1)
+            ids = [int(device)] if isinstance(device, int) else [int(x) for x in device]
+            d = (C.c_int * len(ids))(*ids)
+            rc = lib.ptc_create(C.byref(self.ctx), d, len(ids))
         if rc != 0 or not self.ctx:
             msg = lib.ptc_last_error(self.ctx).decode() if self.ctx else "no context"
             raise RuntimeError("ptc_create failed (%s): %s" % (lib.ptc_backend_name().decode(), msg))
@@ -273,6 +289,20 @@ class Context:
     def _check(self, rc, what):
         if rc != 0:
             raise RuntimeError("%s failed: %s" % (what, self.lib.ptc_last_error(self.ctx).decode()))
+
+    def device_count(self):
+        return int(self.lib.ptc_device_count(self.ctx))
+
+    def unique_id(self):
+        """128 opaque bytes (ncclGetUniqueId) to hand to every rank's comm_init_rank"""
+        buf = (C.c_uint8 * 128)()
+        if self.lib.ptc_comm_unique_id(buf) != 0:
+            raise RuntimeError("ptc_comm_unique_id failed (no NCCL library?)")
+        return bytes(buf)
+
+    def comm_init_rank(self, id_bytes, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(id_bytes)
+        self._check(self.lib.ptc_comm_init_rank(self.ctx, buf, int(rank), int(world)), "ptc_comm_init_rank")
 
     def upload_scene(self, desc_ptr):
         self._check(self.lib.ptc_upload_scene(self.ctx, desc_ptr), "ptc_upload_scene")
@@ -391,11 +421,39 @@ class Context:
 class HostEngine:
     """The C++ vengine host library: scene recipes, flattening, RendererPathTracing."""
 
-    def __init__(self, backend_lib=None, asset_root=None):
+    def __init__(self, asset_root=None, devices=None):
+        """devices: None = the current device; a list of indices = one engine driving several GPUs (NCCL inside the core)"""
         self.lib = load_host()
-        b = (backend_lib or CUDA_LIB).encode()
         a = (asset_root or ROOT).encode()
-        self.h = C.c_void_p(self.lib.vh_engine_create(b, a))
+        self.h = C.c_void_p(self.lib.vh_engine_create(a))
+        if devices is not None and len(devices) > 1:
+            self.set_devices(devices)
+
+    def set_devices(self, devices):
+        ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+        if self.lib.vh_set_devices(self.h, ids, len(devices)) != 0:
+            raise RuntimeError("cannot use devices %s: %s" % (list(devices), self.last_error()))
+
+    def device_count(self):
+        return int(self.lib.vh_device_count(self.h))
+
+    def comm_unique_id(self):
+        buf = (C.c_uint8 * 128)()
+        if self.lib.vh_comm_unique_id(self.h, buf) != 0:
+            raise RuntimeError("vh_comm_unique_id failed")
+        return bytes(buf)
+
+    def comm_init_rank(self, id_bytes, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(id_bytes)
+        if self.lib.vh_comm_init_rank(self.h, buf, int(rank), int(world)) != 0:
+            raise RuntimeError("vh_comm_init_rank failed: %s" % self.last_error())
+
+    def set_render_options(self, split=None, sampler=None, env_importance=None):
+        """split: None | "default" | "tile" | "sample"; sampler: None | "default" | "sobol" | "pmj" """
+        sp = -1 if split is None else {"default": 0, "tile": 1, "sample": 2}[split]
+        sm = -1 if sampler is None else {"default": 0, "sobol": 1, "pmj": 2}[sampler]
+        ei = -1 if env_importance is None else int(bool(env_importance))
+        self.lib.vh_set_render_options(self.h, sp, sm, ei)
 
     def close(self):
         if self.h:
@@ -477,6 +535,16 @@ class HostEngine:
         shape = (ri["height"], ri["width"], 4)
         return rad.reshape(shape), alb.reshape(shape), nrm.reshape(shape)
 
+    def set_sequence_frame(self, frame):
+        if self.lib.vh_set_sequence_frame(self.h, int(frame)) != 0:
+            raise RuntimeError("no scene / camera")
+
+    def set_output(self, file_type=None, exposure=0.0, write_all_files=None, denoise=None):
+        """file_type: None | "hdr" | "png" """
+        ft = -1 if file_type is None else {"hdr": 0, "png": 1}[file_type]
+        self.lib.vh_set_output(self.h, ft, float(exposure), -1 if write_all_files is None else int(write_all_files),
+                               -1 if denoise is None else int(denoise))
+
     def render_progress(self):
         """RendererPathTracing::renderProgress(); safe to call from another thread while a render runs"""
         return float(self.lib.vh_render_progress(self.h))
@@ -513,6 +581,15 @@ def read_hdr(path):
     out = np.zeros((h.value, w.value, 4), np.float32)
     lib.vh_read_hdr(path.encode(), C.byref(w), C.byref(h), np_ptr(out))
     return out
+
+
+def write_image(path_no_ext, img, file_type="png", exposure=0.0):
+    """writeToDisk of the host library (+ applyExposure for PNG): <path>.png / <path>.hdr"""
+    lib = load_host()
+    img = np.ascontiguousarray(img, np.float32)
+    h, w, c = img.shape
+    if lib.vh_write_image(path_no_ext.encode(), w, h, c, np_ptr(img), {"hdr": 0, "png": 1}[file_type], float(exposure)) != 0:
+        raise RuntimeError("cannot write %s" % path_no_ext)
 
 
 def write_hdr(path, img):

@@ -18,7 +18,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <vector>
+
+#include <dlfcn.h>
+#include <nccl.h> /* types and prototypes only: the library is opened at run time (NcclApi) */
 
 namespace {
 
@@ -31,9 +37,9 @@ struct TextureClass {
 
 }  // namespace
 
-struct ptc_ctx {
+/* everything one GPU holds: scene, acceleration structure, wavefront state, streams */
+struct Dev {
     int device = 0;
-    std::string err;
     cudaStream_t stream = nullptr;
     int smCount = 148;
     wf::ExtendTune tune{EXTEND_MIN_ACTIVE, EXTEND_TRI_ENTER, EXTEND_TRI_LEAVE, EXTEND_BLOCKED};
@@ -61,7 +67,7 @@ struct ptc_ctx {
     lbvh::Build accel;
 
     /* render state */
-    DBuf<float4> accR, accA, accN;
+    DBuf<float4> acc; /* the three accumulation targets (radiance, albedo, normal), contiguous: ONE ncclReduce sums them */
     /* two wavefronts in flight (see renderImpl): each has its own path state, queues, counters and stream */
     struct WaveBufs {
         DBuf<float4> orgRng, dirFlags, beta, radiance, hit, aovA, aovN, shOrg, shDir, shContrib, prBeta;
@@ -69,7 +75,9 @@ struct ptc_ctx {
         DBuf<unsigned long long> stats;
         size_t capacity = 0;
     } wave[2];
-    DBuf<uint32_t> pixmap;
+    DBuf<uint32_t> pixmap, tileOffsets; /* tile split: local pixel -> global pixel, built on the device, kept across calls */
+    uint32_t pixmapKey[5] = {0, 0, 0, 0, 0}, pixmapCount = 0;
+    cudaEvent_t evStart = nullptr, evStop = nullptr; /* device time of one render */
     cudaStream_t stream2 = nullptr; /* second wavefront; c->stream carries the first and everything else */
     cudaEvent_t evA = nullptr, evB = nullptr, evAcc[2] = {nullptr, nullptr}, evFork = nullptr;
     static constexpr int RING = 8;
@@ -84,6 +92,7 @@ struct ptc_ctx {
 
     std::atomic<float> progress{0.0f};
     ptc_stats stats{};
+    std::string err; /* what went wrong on this device (collected by the context) */
 
     /* identity of what the texture arrays / the cubemap were built from (ptc_texture.uid, ptc_env.uid): an upload whose
      * textures are the same immutable objects keeps the device copies, like the reference, which uploads at import */
@@ -110,12 +119,14 @@ struct ptc_ctx {
         freeTextureClasses();
         freeCubemap();
     }
-    ~ptc_ctx() {
+    ~Dev() {
         cudaSetDevice(device);
         freeTextures();
         if (evA) cudaEventDestroy(evA);
         if (evB) cudaEventDestroy(evB);
         if (evFork) cudaEventDestroy(evFork);
+        if (evStart) cudaEventDestroy(evStart);
+        if (evStop) cudaEventDestroy(evStop);
         for (cudaEvent_t e : evAcc)
             if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : evItem)
@@ -126,11 +137,6 @@ struct ptc_ctx {
 };
 
 namespace {
-
-int fail(ptc_ctx *c, const std::string &msg) {
-    if (c) c->err = msg;
-    return 1;
-}
 
 /* 3x3 inverse of the upper-left block of a column-major 4x4; row-major output */
 void inverse3(const float *M, float *out) {
@@ -151,7 +157,7 @@ void inverse3(const float *M, float *out) {
     out[8] = (a * e - b * d) * id;
 }
 
-DScene makeDScene(ptc_ctx *c) {
+DScene makeDScene(Dev *c) {
     DScene s{};
     s.vertices = c->vertices.p;
     s.indices = c->indices.p;
@@ -186,7 +192,7 @@ DScene makeDScene(ptc_ctx *c) {
 /* Uploads the scene's 8-bit textures: every texture becomes RGBA8 (an R8 source reads back as (r, 0, 0, 1) like
  * VK_FORMAT_R8_UNORM), grouped into layered arrays by (width, height, sRGB).  Sampler = the reference's
  * (VulkanTexture.cpp:219-232): linear, REPEAT, normalised coordinates, sRGB decode before filtering. */
-void createTextures(ptc_ctx *c, const ptc_scene_desc *sd) {
+void createTextures(Dev *c, const ptc_scene_desc *sd) {
     const uint32_t n = sd->n_textures;
     std::vector<uint32_t> ref(n, 0);
     std::vector<std::vector<uint32_t>> members;
@@ -262,7 +268,7 @@ void createTextures(ptc_ctx *c, const ptc_scene_desc *sd) {
     CUDA_TRY(cudaStreamSynchronize(c->stream)); /* the host vectors die here */
 }
 
-void createCubemap(ptc_ctx *c, const ptc_env &env) {
+void createCubemap(Dev *c, const ptc_env &env) {
     if (!env.equirect_rgba || !env.width || !env.height) return;
     const uint32_t N = std::max(1u, std::min(env.width / 4u, 1080u)); /* VulkanRendererSkybox.cpp:100 */
     /* equirect as a float4 texture: linear, REPEAT, like the reference's sampler for the HDR image */
@@ -319,7 +325,7 @@ void createCubemap(ptc_ctx *c, const ptc_env &env) {
 /* L2 persistence for what every ray touches: the wide nodes (breadth first, so the top levels come first) and as much of
  * the triangle array as the persisting carve-out holds.  The path state streams through L2 (6 GB per batch at 1080p x 16)
  * and would otherwise keep evicting the BVH. */
-void setTraversalWindow(ptc_ctx *c) {
+void setTraversalWindow(Dev *c) {
     cudaStreamAttrValue attr{};
     cudaCtxResetPersistingL2Cache(); /* lines of a previous scene */
     const size_t bytes = c->accel.n ? c->accel.traversalBytes() : 0;
@@ -341,8 +347,8 @@ void setTraversalWindow(ptc_ctx *c) {
     CUDA_TRY(cudaStreamSetAttribute(c->stream2, cudaStreamAttributeAccessPolicyWindow, &attr));
 }
 
-void ensureWave(ptc_ctx *c, int k, size_t slots, uint32_t depth) {
-    ptc_ctx::WaveBufs &w = c->wave[k];
+void ensureWave(Dev *c, int k, size_t slots, uint32_t depth) {
+    Dev::WaveBufs &w = c->wave[k];
     if (slots > w.capacity) {
         w.orgRng.alloc(slots);
         w.dirFlags.alloc(slots);
@@ -365,8 +371,8 @@ void ensureWave(ptc_ctx *c, int k, size_t slots, uint32_t depth) {
     w.stats.alloc(wf::ST_COUNT);
 }
 
-wf::Wave makeWave(ptc_ctx *c, int k) {
-    ptc_ctx::WaveBufs &b = c->wave[k];
+wf::Wave makeWave(Dev *c, int k) {
+    Dev::WaveBufs &b = c->wave[k];
     wf::Wave w{};
     w.orgRng = b.orgRng.p;
     w.dirFlags = b.dirFlags.p;
@@ -388,7 +394,7 @@ wf::Wave makeWave(ptc_ctx *c, int k) {
     return w;
 }
 
-int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, float4 *dN) {
+int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, float4 *dN) {
     const uint32_t W = rp->width, H = rp->height;
     const uint32_t batches = rp->samples / rp->batch_size; /* VulkanRendererPathTracing.cpp:798-799 (T7) */
     const uint32_t totalSamples = batches * rp->batch_size;
@@ -398,19 +404,32 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     cudaStream_t s = c->stream;
     c->progress = 0.0f; /* renderProgress() restarts with every render (VulkanRendererPathTracing.cpp:228-231) */
 
-    /* pixel set of this rank */
+    /* pixel set of this rank: tiles dealt round-robin, enumerated tile by tile (a warp's 32 camera rays then cover a compact
+     * screen area).  The host only walks the rank's TILES for their offsets; k_tile_pixmap fills the pixels; the result is kept
+     * until the partition changes. */
     uint32_t nPixLocal = (uint32_t)nPix;
     const uint32_t *pixmapPtr = nullptr;
     if (rp->split_mode == PTC_SPLIT_TILE && world > 1) {
-        std::vector<uint32_t> pm;
-        pm.reserve(nPix / world + 1024);
-        const uint32_t tilesX = (W + tile - 1) / tile;
-        for (uint32_t y = 0; y < H; y++)
-            for (uint32_t x = 0; x < W; x++)
-                if (((y / tile) * tilesX + (x / tile)) % world == rp->rank) pm.push_back(y * W + x);
-        nPixLocal = (uint32_t)pm.size();
-        c->pixmap.upload(pm.data(), pm.size(), s);
-        CUDA_TRY(cudaStreamSynchronize(s));
+        const uint32_t key[5] = {W, H, tile, rp->rank, world};
+        if (memcmp(key, c->pixmapKey, sizeof(key)) != 0 || !c->pixmap.p) {
+            const uint32_t tilesX = (W + tile - 1) / tile, tilesY = (H + tile - 1) / tile, nTiles = tilesX * tilesY;
+            std::vector<uint32_t> offsets;
+            uint32_t total = 0;
+            for (uint32_t t = rp->rank; t < nTiles; t += world) {
+                const uint32_t tx = t % tilesX, ty = t / tilesX;
+                offsets.push_back(total);
+                total += std::min(tile, W - tx * tile) * std::min(tile, H - ty * tile);
+            }
+            offsets.push_back(total);
+            c->tileOffsets.upload(offsets.data(), offsets.size(), s);
+            c->pixmap.alloc(std::max<size_t>(total, 1));
+            const uint32_t nLocalTiles = (uint32_t)offsets.size() - 1u;
+            if (nLocalTiles) wf::k_tile_pixmap<<<nLocalTiles, 256, 0, s>>>(W, H, tile, rp->rank, world, c->tileOffsets.p, c->pixmap.p);
+            CUDA_TRY(cudaStreamSynchronize(s)); /* the host vector dies here */
+            memcpy(c->pixmapKey, key, sizeof(key));
+            c->pixmapCount = total;
+        }
+        nPixLocal = c->pixmapCount;
         pixmapPtr = c->pixmap.p;
     }
 
@@ -496,9 +515,7 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
         }
     };
 
-    cudaEvent_t evStart, evStop;
-    CUDA_TRY(cudaEventCreate(&evStart));
-    CUDA_TRY(cudaEventCreate(&evStop));
+    cudaEvent_t evStart = c->evStart, evStop = c->evStop; /* owned by the device state: nothing leaks when a call below throws */
     CUDA_TRY(cudaEventRecord(evStart, s));
     /* the second stream starts after the clears above */
     if (overlap) {
@@ -520,9 +537,9 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
                 cudaStream_t st = streams[k];
                 const wf::Wave &w = waves[k];
                 /* at most RING work items in flight; renderProgress() follows the completed ones without draining the pipeline */
-                if (item >= (uint64_t)ptc_ctx::RING) {
-                    CUDA_TRY(cudaEventSynchronize(c->evItem[item % ptc_ctx::RING]));
-                    c->progress = (float)(item - ptc_ctx::RING + 1) / (float)totalItems;
+                if (item >= (uint64_t)Dev::RING) {
+                    CUDA_TRY(cudaEventSynchronize(c->evItem[item % Dev::RING]));
+                    c->progress = (float)(item - Dev::RING + 1) / (float)totalItems;
                 }
                 const uint32_t ns = std::min(chunkSamples, rp->batch_size - s0);
                 const uint32_t nSlots = ns * nPixLocal;
@@ -548,7 +565,7 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
                 if (overlap && item > 0) CUDA_TRY(cudaStreamWaitEvent(st, c->evAcc[(item - 1) & 1u], 0));
                 wf::k_accumulate<<<(nPixLocal + 255) / 256, 256, 0, st>>>(w, rc, ns, dR, dA, dN);
                 if (overlap) CUDA_TRY(cudaEventRecord(c->evAcc[item & 1u], st));
-                CUDA_TRY(cudaEventRecord(c->evItem[item % ptc_ctx::RING], st));
+                CUDA_TRY(cudaEventRecord(c->evItem[item % Dev::RING], st));
                 launches += 2;
                 CUDA_TRY(cudaGetLastError());
             }
@@ -561,8 +578,6 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     CUDA_TRY(cudaStreamSynchronize(s));
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, evStart, evStop));
-    cudaEventDestroy(evStart);
-    cudaEventDestroy(evStop);
 
     unsigned long long hs[wf::ST_COUNT] = {};
     for (int k = 0; k < nWaves; k++) {
@@ -590,89 +605,154 @@ int renderImpl(ptc_ctx *c, const ptc_render_params *rp, float4 *dR, float4 *dA, 
     return 0;
 }
 
-__global__ void k_fill_alpha(float4 *a, float4 *b, float4 *cc, size_t n) {
-    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    a[i].w = 1.0f;
-    b[i].w = 1.0f;
-    cc[i].w = 1.0f;
-}
+/* ------------------------------------------------------------------ NCCL, resolved at run time
+ * The only exchange of the path is the sum (sample split) / gather (tile split: disjoint pixels, zeros elsewhere) of the
+ * accumulation buffers onto one GPU.  libnccl is opened on first use, so a single-GPU process needs no NCCL at
+ * all and a process that already holds one (torch) shares it. */
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool load() {
+        if (handle) return true;
+        const char *names[] = {getenv("PTC_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            if (!n || !*n) continue;
+            handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) {
+            error = std::string("cannot open libnccl.so.2: ") + dlerror();
+            return false;
+        }
+#define NCCL_SYM(field, sym)                                                        \
+    field = reinterpret_cast<decltype(field)>(dlsym(handle, #sym));                 \
+    if (!field) {                                                                   \
+        error = "libnccl lacks " #sym;                                              \
+        return false;                                                               \
+    }
+        NCCL_SYM(GetUniqueId, ncclGetUniqueId)
+        NCCL_SYM(CommInitRank, ncclCommInitRank)
+        NCCL_SYM(CommInitAll, ncclCommInitAll)
+        NCCL_SYM(CommDestroy, ncclCommDestroy)
+        NCCL_SYM(Reduce, ncclReduce)
+        NCCL_SYM(GroupStart, ncclGroupStart)
+        NCCL_SYM(GroupEnd, ncclGroupEnd)
+        NCCL_SYM(GetErrorString, ncclGetErrorString)
+#undef NCCL_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+std::mutex g_ncclMutex;
+#define NCCL_TRY(expr)                                                                                                                    \
+    do {                                                                                                                                  \
+        ncclResult_t _r = (expr);                                                                                                         \
+        if (_r != ncclSuccess) throw CudaError{std::string(#expr) + " -> " + g_nccl.GetErrorString(_r) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"}; \
+    } while (0)
 
 }  // namespace
 
-/* ====================================================================== C-ABI */
-#define PTC_GUARD_BEGIN try {
-#define PTC_GUARD_END(ctx)                          \
-    }                                               \
-    catch (const CudaError &e) {                    \
-        return fail(ctx, e.msg);                    \
-    }                                               \
-    catch (const std::exception &e) {               \
-        return fail(ctx, e.what());                 \
+/* The context: one Dev per GPU it drives.
+ *   one device                      the plain case
+ *   several devices, one process    ptc_create(.., ids, n > 1): one worker thread + streams per GPU, ncclCommInitAll over them;
+ *                                   upload / build run on all of them, a render is partitioned (tiles or sample batches) and the
+ *                                   buffers are reduced onto the first device
+ *   one device, several processes   ptc_comm_init_rank: this context is rank r of `world` single-device contexts (one process per
+ *                                   GPU under torchrun / MPI); ptc_render* reduce onto rank 0 */
+struct ptc_ctx {
+    std::vector<std::unique_ptr<Dev>> devs;
+    std::string err;
+    std::vector<ncclComm_t> comms; /* one per Dev (in-process group) or one (multi-process) */
+    int commRank = 0, commWorld = 1; /* multi-process mode */
+    ptc_stats stats{};
+    double reduceMs = 0.0;
+    ~ptc_ctx() {
+        for (ncclComm_t cm : comms)
+            if (cm && g_nccl.CommDestroy) g_nccl.CommDestroy(cm);
     }
+};
 
-extern "C" {
+namespace {
 
-PTC_API const char *ptc_backend_name(void) { return "cuda-sm_100a"; }
+int fail(ptc_ctx *c, const std::string &msg) {
+    if (c) c->err = msg;
+    return 1;
+}
+Dev *dev0(ptc_ctx *ctx) { return (ctx && !ctx->devs.empty()) ? ctx->devs[0].get() : nullptr; }
 
-PTC_API int ptc_create(ptc_ctx **out, const int *device_ids, int n_devices) {
-    if (!out) return 1;
-    *out = nullptr;
-    ptc_ctx *c = new ptc_ctx();
-    *out = c; /* returned even on failure so that ptc_last_error can explain */
-    PTC_GUARD_BEGIN
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0)
-        return fail(c, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
-    c->device = (device_ids && n_devices > 0) ? device_ids[0] : 0;
-    if (!(device_ids && n_devices > 0)) {
-        int cur = 0;
-        if (cudaGetDevice(&cur) == cudaSuccess) c->device = cur;
+/* runs fn(dev, index) for every device of the context, on one thread per device when there are several; the first error wins */
+template <class Fn>
+void forEachDev(ptc_ctx *ctx, Fn &&fn) {
+    const size_t n = ctx->devs.size();
+    std::vector<std::string> errs(n);
+    auto body = [&](size_t i) {
+        try {
+            CUDA_TRY(cudaSetDevice(ctx->devs[i]->device));
+            fn(ctx->devs[i].get(), (uint32_t)i);
+        } catch (const CudaError &e) {
+            errs[i] = e.msg;
+        } catch (const std::exception &e) {
+            errs[i] = e.what();
+        }
+    };
+    if (n == 1) {
+        body(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < n; i++) th.emplace_back(body, i);
+        for (auto &t : th) t.join();
     }
-    CUDA_TRY(cudaSetDevice(c->device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
-    if (prop.major != 10) return fail(c, std::string("device '") + prop.name + "' is not sm_100; this build targets B200 only");
-    c->smCount = prop.multiProcessorCount;
-    c->persistMax = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
-    c->windowMax = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
-    if (const char *h = getenv("PTC_HIERARCHY")) {
-        if (!strcmp(h, "lbvh")) c->accel.hierarchy = PTC_HIERARCHY_LBVH;
-        if (!strcmp(h, "ploc")) c->accel.hierarchy = PTC_HIERARCHY_PLOC;
-    }
-    if (const char *r = getenv("PTC_PLOC_RADIUS")) {
-        const int v = atoi(r);
-        if (v >= 1 && v <= PLOC_MAX_RADIUS) c->accel.plocRadius = (uint32_t)v;
-    }
-    if (const char *t = getenv("PTC_EXTEND_TUNE")) { /* "minActive,triEnter,triLeave,blocked" */
-        unsigned a, b, d, e;
-        if (sscanf(t, "%u,%u,%u,%u", &a, &b, &d, &e) == 4) c->tune = wf::ExtendTune{a, b, d, e};
-    }
-    if (const char *o = getenv("PTC_OVERLAP")) { /* "traceBlocksPerSM,shadeBlocksPerSM"; "0" = one wavefront at a time */
-        int a = 0, b = 0;
-        const int got = sscanf(o, "%d,%d", &a, &b);
-        if (got == 2 && a > 0 && b > 0) c->overlapTrace = a, c->overlapShade = b;
-        else if (got >= 1 && a == 0) c->overlapTrace = c->overlapShade = 0;
-    }
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreate(&c->evA));
-    CUDA_TRY(cudaEventCreate(&c->evB));
-    CUDA_TRY(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
-    for (cudaEvent_t &e : c->evAcc) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (cudaEvent_t &e : c->evItem) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    return 0;
-    PTC_GUARD_END(c)
+    for (size_t i = 0; i < n; i++)
+        if (!errs[i].empty()) throw CudaError{n > 1 ? "device " + std::to_string(ctx->devs[i]->device) + ": " + errs[i] : errs[i]};
 }
 
-PTC_API void ptc_destroy(ptc_ctx *ctx) { delete ctx; }
-PTC_API const char *ptc_last_error(const ptc_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+/* every index a kernel will follow unchecked is checked here, once, on the host (a malformed description must fail with a message,
+ * not read out of bounds on the device) */
+void validateScene(const ptc_scene_desc *sd) {
+    if ((sd->n_vertices && !sd->vertices) || (sd->n_indices && !sd->indices) || (sd->n_meshes && !sd->meshes) || (sd->n_instances && !sd->instances) ||
+        (sd->n_materials && !sd->materials) || (sd->n_light_data && !sd->light_data) || (sd->n_light_instances && !sd->light_instances) ||
+        (sd->n_textures && !sd->textures))
+        throw CudaError{"scene array is null but its count is not"};
+    std::vector<uint8_t> meshChecked(sd->n_meshes, 0);
+    auto volumeIndexOk = [&](float v) { return v == -1.0f || (v >= 0.0f && v < (float)sd->n_materials && v <= 65535.0f && v == floorf(v)); };
+    for (uint32_t i = 0; i < sd->n_instances; i++) {
+        const ptc_instance &in = sd->instances[i];
+        if (in.mesh_index >= sd->n_meshes) throw CudaError{"instance mesh index out of range"};
+        if (in.material_index >= sd->n_materials) throw CudaError{"instance material index out of range"};
+        const ptc_mesh &m = sd->meshes[in.mesh_index];
+        if (in.num_triangles != m.tri_count) throw CudaError{"instance num_triangles differs from its mesh's tri_count"};
+        if (!volumeIndexOk(in.id[1]) || !volumeIndexOk(in.id[2])) throw CudaError{"instance volume material index out of range (must be -1 or a material index below 65536)"};
+        if (meshChecked[in.mesh_index]) continue;
+        meshChecked[in.mesh_index] = 1;
+        if ((uint64_t)m.first_index + 3ull * m.tri_count > sd->n_indices) throw CudaError{"mesh index range out of bounds"};
+        if ((uint64_t)m.first_vertex + m.vertex_count > sd->n_vertices) throw CudaError{"mesh vertex range out of bounds"};
+        const uint32_t *ind = sd->indices + m.first_index;
+        uint32_t mx = 0;
+        for (uint64_t k = 0; k < 3ull * m.tri_count; k++) mx = std::max(mx, ind[k]);
+        if (m.tri_count && mx >= m.vertex_count) throw CudaError{"mesh index exceeds its vertex count"};
+    }
+    for (uint32_t i = 0; i < sd->n_light_instances; i++) {
+        const ptc_light_instance &L = sd->light_instances[i];
+        if (L.info[3] > 2u) throw CudaError{"light instance type must be 0, 1 or 2"};
+        if (L.info[3] == 2u) {
+            if (L.info[1] >= sd->n_instances) throw CudaError{"mesh light instance index out of range"};
+            if (sd->instances[L.info[1]].num_triangles == 0u) throw CudaError{"mesh light without triangles"};
+        } else if (L.info[0] >= sd->n_light_data) {
+            throw CudaError{"light data index out of range"};
+        }
+    }
+}
 
-PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
-    if (!c || !sd) return fail(c, "null argument");
-    if (!c->stream) return fail(c, "context has no CUDA device");
-    PTC_GUARD_BEGIN
+/* ptc_upload_scene on one device */
+void uploadSceneDev(Dev *c, const ptc_scene_desc *sd) {
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     c->sceneUploaded = false;
@@ -695,8 +775,8 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
     c->anyEmissive = c->anyTransparent = c->anyVolumeChange = false;
     for (uint32_t i = 0; i < sd->n_instances; i++) {
         const ptc_instance &in = sd->instances[i];
-        if (in.mesh_index >= sd->n_meshes) return fail(c, "instance mesh index out of range");
-        if (in.material_index >= sd->n_materials) return fail(c, "instance material index out of range");
+        if (in.mesh_index >= sd->n_meshes) throw CudaError{"instance mesh index out of range"};
+        if (in.material_index >= sd->n_materials) throw CudaError{"instance material index out of range"};
         const ptc_mesh &m = sd->meshes[in.mesh_index];
         DInstance &d = inst[i];
         const float *M = in.model;
@@ -725,7 +805,7 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
              * instance transform, padded against the rounding of the device's own transform */
             nEmissiveInst++;
             if (m.vertex_count > 0) {
-                if ((uint64_t)m.first_vertex + m.vertex_count > sd->n_vertices) return fail(c, "mesh vertex range out of bounds");
+                if ((uint64_t)m.first_vertex + m.vertex_count > sd->n_vertices) throw CudaError{"mesh vertex range out of bounds"};
                 auto it = meshBox.find(in.mesh_index);
                 if (it == meshBox.end()) {
                     std::array<float, 6> ob = {1e30f, 1e30f, 1e30f, -1e30f, -1e30f, -1e30f};
@@ -764,7 +844,7 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
         if (mat.metallic_roughness_ao[3] > 0.0f) c->anyTransparent = true;
         if (in.id[1] != in.id[2]) c->anyVolumeChange = true;
     }
-    if (tri >= 0x7fffffffull) return fail(c, "more than 2^31 world triangles");
+    if (tri >= 0x7fffffffull) throw CudaError{"more than 2^31 world triangles"};
     c->nWorldTris = (uint32_t)tri;
     c->instances.upload(inst.data(), inst.size(), s);
     /* few emitters: one box each; many: the box around all of them */
@@ -780,23 +860,28 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
     bool allIdentified = sd->n_textures > 0;
     for (uint32_t t = 0; t < sd->n_textures; t++) {
         const ptc_texture &in = sd->textures[t];
-        if (in.channels != 1 && in.channels != 4) return fail(c, "texture channels must be 1 or 4");
-        if (!in.data || !in.width || !in.height) return fail(c, "texture without data");
+        if (in.channels != 1 && in.channels != 4) throw CudaError{"texture channels must be 1 or 4"};
+        if (!in.data || !in.width || !in.height) throw CudaError{"texture without data"};
         allIdentified = allIdentified && in.uid != 0;
         sig.push_back(in.uid);
         sig.push_back(((uint64_t)in.width << 32) | in.height);
         sig.push_back(((uint64_t)in.channels << 32) | in.srgb);
     }
+    uint64_t uploadBytes = sd->n_vertices * sizeof(ptc_vertex) + sd->n_indices * 4ull + (uint64_t)sd->n_materials * sizeof(ptc_material) +
+                           (uint64_t)sd->n_light_data * sizeof(ptc_light_data) + (uint64_t)sd->n_light_instances * sizeof(ptc_light_instance) +
+                           (uint64_t)sd->n_instances * sizeof(DInstance);
     if (!(allIdentified && sig == c->texSignature && c->nTextures == sd->n_textures)) {
         c->freeTextureClasses();
         createTextures(c, sd);
         if (allIdentified) c->texSignature = sig;
+        for (uint32_t t = 0; t < sd->n_textures; t++) uploadBytes += (uint64_t)sd->textures[t].width * sd->textures[t].height * sd->textures[t].channels;
     }
     const ptc_env &env = sd->env;
     const bool hasEnv = env.equirect_rgba && env.width && env.height;
     if (!(hasEnv && env.uid != 0 && c->cubeTex && c->envSignature[0] == env.uid && c->envSignature[1] == env.width && c->envSignature[2] == env.height)) {
         c->freeCubemap();
         createCubemap(c, env);
+        if (hasEnv) uploadBytes += (uint64_t)env.width * env.height * 16ull;
         if (hasEnv && env.uid != 0) {
             c->envSignature[0] = env.uid;
             c->envSignature[1] = env.width;
@@ -804,100 +889,344 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *sd) {
         }
     }
     CUDA_TRY(cudaStreamSynchronize(s));
+    c->stats.upload_bytes = uploadBytes;
     c->sceneUploaded = true;
-    return 0;
-    PTC_GUARD_END(c)
 }
 
-PTC_API int ptc_set_build_options(ptc_ctx *c, uint32_t hierarchy, uint32_t ploc_radius) {
-    if (!c) return 1;
-    if (hierarchy != PTC_HIERARCHY_LBVH && hierarchy != PTC_HIERARCHY_PLOC) return fail(c, "unknown hierarchy");
-    if (ploc_radius > PLOC_MAX_RADIUS) return fail(c, "ploc_radius must be <= 32");
-    c->accel.hierarchy = hierarchy;
-    c->accel.plocRadius = ploc_radius ? ploc_radius : 16u;
-    c->accelBuilt = false;
-    return 0;
+
+__global__ void k_fill_alpha(float4 *a, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) a[i].w = 1.0f;
 }
 
-PTC_API int ptc_build_accel(ptc_ctx *c) {
-    if (!c) return 1;
-    if (!c->sceneUploaded) return fail(c, "ptc_upload_scene has not been called");
-    PTC_GUARD_BEGIN
-    CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaEventRecord(c->evA, c->stream));
-    c->accel.run(c->vertices.p, c->indices.p, c->instances.p, c->nInstances, c->nWorldTris, c->stream);
-    CUDA_TRY(cudaEventRecord(c->evB, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    float ms = 0;
-    CUDA_TRY(cudaEventElapsedTime(&ms, c->evA, c->evB));
-    c->accelBuilt = true;
-    setTraversalWindow(c);
-    c->stats.build_ms = ms;
-    c->stats.n_triangles = c->nWorldTris;
-    c->stats.n_bvh_nodes = c->accel.nWide;
-    c->stats.scene_bytes = c->accel.bytes() + c->vertices.bytes() + c->indices.bytes() + c->instances.bytes() + c->materials.bytes();
-    return 0;
-    PTC_GUARD_END(c)
+/* render settings a backend cannot run */
+void checkRenderParams(ptc_ctx *ctx, const ptc_render_params *rp) {
+    for (auto &d : ctx->devs)
+        if (!d->accelBuilt) throw CudaError{"ptc_build_accel has not been called"};
+    if (rp->batch_size == 0 || rp->width == 0 || rp->height == 0 || rp->depth == 0) throw CudaError{"bad render params"};
+    if (rp->depth > 255) throw CudaError{"depth must be <= 255"};
+    if ((uint64_t)rp->width * rp->height >= 0x7fffffffull) throw CudaError{"image too large"};
+    const float cv = rp->scene.volumes[0];
+    if (!(cv == -1.0f || (cv >= 0.0f && cv < (float)ctx->devs[0]->nMaterials && cv <= 65535.0f && cv == floorf(cv))))
+        throw CudaError{"camera volume material index out of range"};
+    if (rp->split_mode > PTC_SPLIT_SAMPLE) throw CudaError{"unknown split mode"};
+    if (rp->split_mode != PTC_SPLIT_NONE && rp->world > 1 && rp->rank >= rp->world) throw CudaError{"rank must be below world"};
 }
 
-static int renderChecked(ptc_ctx *c, const ptc_render_params *rp) {
-    if (!c || !rp) return fail(c, "null argument");
-    if (!c->accelBuilt) return fail(c, "ptc_build_accel has not been called");
-    if (rp->batch_size == 0 || rp->width == 0 || rp->height == 0 || rp->depth == 0) return fail(c, "bad render params");
-    if (rp->depth > 255) return fail(c, "depth must be <= 255");
-    if ((uint64_t)rp->width * rp->height >= 0x7fffffffull) return fail(c, "image too large");
-    return 0;
-}
-
-PTC_API int ptc_render_device(ptc_ctx *c, const ptc_render_params *rp, void *dR, void *dA, void *dN) {
-    if (int rcode = renderChecked(c, rp)) return rcode;
-    PTC_GUARD_BEGIN
-    CUDA_TRY(cudaSetDevice(c->device));
+/* The partitioned render of a context: every device renders its share into its own three targets (one allocation), the targets are
+ * summed onto the root with ONE ncclReduce per device (tiles are disjoint and zero elsewhere, so the sum serves both split modes),
+ * and the root writes alpha = 1 behind the reduce.  dOut (optional, device pointers on the root's device) / hOut (optional, host)
+ * receive the three images.  Returns false on a non-root rank of a multi-process group (no image there). */
+bool renderAll(ptc_ctx *ctx, const ptc_render_params *rp, void *const dOut[3], float *const hOut[3]) {
+    checkRenderParams(ctx, rp);
     const size_t nPix = (size_t)rp->width * rp->height;
-    float4 *r = (float4 *)dR, *a = (float4 *)dA, *n = (float4 *)dN;
-    if (!r) { c->accR.alloc(nPix); r = c->accR.p; }
-    if (!a) { c->accA.alloc(nPix); a = c->accA.p; }
-    if (!n) { c->accN.alloc(nPix); n = c->accN.p; }
-    int rcode = renderImpl(c, rp, r, a, n);
-    if (rcode) return rcode;
-    if (rp->split_mode == PTC_SPLIT_NONE || rp->rank == 0) {
-        k_fill_alpha<<<(unsigned)((nPix + 255) / 256), 256, 0, c->stream>>>(r, a, n, nPix);
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const uint32_t nDev = (uint32_t)ctx->devs.size();
+    const bool group = nDev > 1, ranks = ctx->commWorld > 1;
+    ptc_render_params base = *rp;
+    if (group || ranks) {
+        /* the context knows the partition; the caller only chooses the mode (none = sample batches: any batch count balances) */
+        if (base.split_mode == PTC_SPLIT_NONE) base.split_mode = PTC_SPLIT_SAMPLE;
+        base.world = group ? nDev : (uint32_t)ctx->commWorld;
+    }
+    const bool isRoot = !ranks || ctx->commRank == 0;
+    /* device targets: the caller's (single device, device pointers given) or the device's own contiguous triple */
+    std::vector<float4 *> target(nDev, nullptr);
+    const bool callerTargets = dOut && dOut[0] && dOut[1] && dOut[2] && !group && !ranks;
+    forEachDev(ctx, [&](Dev *c, uint32_t i) {
+        ptc_render_params mine = base;
+        if (group) mine.rank = i;
+        if (ranks) mine.rank = (uint32_t)ctx->commRank;
+        float4 *r, *a, *n;
+        if (callerTargets) {
+            r = (float4 *)dOut[0], a = (float4 *)dOut[1], n = (float4 *)dOut[2];
+        } else {
+            c->acc.alloc(3 * nPix);
+            r = c->acc.p, a = r + nPix, n = a + nPix;
+            target[i] = r;
+        }
+        renderImpl(c, &mine, r, a, n);
+    });
+    /* the exchange */
+    ctx->reduceMs = 0.0;
+    if (group || ranks) {
+        Dev *root = ctx->devs[0].get();
+        CUDA_TRY(cudaSetDevice(root->device));
+        CUDA_TRY(cudaEventRecord(root->evA, root->stream));
+        NCCL_TRY(g_nccl.GroupStart());
+        for (uint32_t i = 0; i < nDev; i++) {
+            Dev *c = ctx->devs[i].get();
+            CUDA_TRY(cudaSetDevice(c->device));
+            NCCL_TRY(g_nccl.Reduce(target[i], target[i], 3 * nPix * 4, ncclFloat, ncclSum, 0, ctx->comms[i], c->stream));
+        }
+        NCCL_TRY(g_nccl.GroupEnd());
+        CUDA_TRY(cudaSetDevice(root->device));
+        CUDA_TRY(cudaEventRecord(root->evB, root->stream));
+        for (uint32_t i = 0; i < nDev; i++) {
+            CUDA_TRY(cudaSetDevice(ctx->devs[i]->device));
+            CUDA_TRY(cudaStreamSynchronize(ctx->devs[i]->stream));
+        }
+        CUDA_TRY(cudaSetDevice(root->device));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, root->evA, root->evB));
+        ctx->reduceMs = ms;
+    }
+    /* statistics of the whole context */
+    ptc_stats st{};
+    const ptc_stats &b0 = ctx->devs[0]->stats;
+    st.build_ms = b0.build_ms, st.n_triangles = b0.n_triangles, st.n_bvh_nodes = b0.n_bvh_nodes, st.scene_bytes = b0.scene_bytes;
+    st.upload_bytes = b0.upload_bytes;
+    st.reduce_ms = ctx->reduceMs;
+    for (auto &d : ctx->devs) {
+        const ptc_stats &x = d->stats;
+        st.segments += x.segments, st.path_rays += x.path_rays, st.shadow_rays += x.shadow_rays, st.shadow_hops += x.shadow_hops;
+        st.probe_rays += x.probe_rays, st.probe_hops += x.probe_hops, st.trace_launches += x.trace_launches, st.kernel_launches += x.kernel_launches;
+        st.render_ms = std::max(st.render_ms, x.render_ms), st.trace_ms = std::max(st.trace_ms, x.trace_ms);
+        st.shade_ms = std::max(st.shade_ms, x.shade_ms), st.shadow_ms = std::max(st.shadow_ms, x.shadow_ms);
+        st.build_ms = std::max(st.build_ms, x.build_ms);
+        for (int k = 0; k < 4; k++) st.reserved[k] += x.reserved[k];
+    }
+    st.render_ms += ctx->reduceMs;
+    ctx->stats = st;
+    if (!isRoot) return false;
+    /* alpha = 1 is written in ONE place: here on the image's owner, or - for a caller who partitions by hand and sums the parts
+     * himself (rank / world given, no communicator) - on rank 0 only */
+    Dev *root = ctx->devs[0].get();
+    CUDA_TRY(cudaSetDevice(root->device));
+    const bool manualPart = !group && !ranks && rp->split_mode != PTC_SPLIT_NONE && rp->world > 1;
+    float4 *img[3];
+    for (int k = 0; k < 3; k++) img[k] = callerTargets ? (float4 *)dOut[k] : target[0] + (size_t)k * nPix;
+    if (!manualPart || rp->rank == 0)
+        for (int k = 0; k < 3; k++) k_fill_alpha<<<(unsigned)((nPix + 255) / 256), 256, 0, root->stream>>>(img[k], nPix);
+    if (!callerTargets && dOut)
+        for (int k = 0; k < 3; k++)
+            if (dOut[k]) CUDA_TRY(cudaMemcpyAsync(dOut[k], img[k], nPix * 16, cudaMemcpyDeviceToDevice, root->stream));
+    /* readback like getRenderTargetData x3 (…PathTracing.cpp:890-893) */
+    if (hOut)
+        for (int k = 0; k < 3; k++)
+            if (hOut[k]) CUDA_TRY(cudaMemcpyAsync(hOut[k], img[k], nPix * 16, cudaMemcpyDeviceToHost, root->stream));
+    CUDA_TRY(cudaStreamSynchronize(root->stream));
+    return true;
+}
+
+}  // namespace
+
+/* ====================================================================== C-ABI */
+#define PTC_GUARD_BEGIN try {
+#define PTC_GUARD_END(ctx)                          \
+    }                                               \
+    catch (const CudaError &e) {                    \
+        return fail(ctx, e.msg);                    \
+    }                                               \
+    catch (const std::exception &e) {               \
+        return fail(ctx, e.what());                 \
+    }
+
+extern "C" {
+
+PTC_API const char *ptc_backend_name(void) { return "cuda-sm_100a"; }
+
+static void createDev(Dev *c, int device) {
+    c->device = device;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major != 10) throw CudaError{std::string("device '") + prop.name + "' is not sm_100; this build targets B200 only"};
+    c->smCount = prop.multiProcessorCount;
+    c->persistMax = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
+    c->windowMax = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
+    if (const char *h = getenv("PTC_HIERARCHY")) {
+        if (!strcmp(h, "lbvh")) c->accel.hierarchy = PTC_HIERARCHY_LBVH;
+        if (!strcmp(h, "ploc")) c->accel.hierarchy = PTC_HIERARCHY_PLOC;
+    }
+    if (const char *r = getenv("PTC_PLOC_RADIUS")) {
+        const int v = atoi(r);
+        if (v >= 1 && v <= PLOC_MAX_RADIUS) c->accel.plocRadius = (uint32_t)v;
+    }
+    if (const char *t = getenv("PTC_EXTEND_TUNE")) { /* "minActive,triEnter,triLeave,blocked" */
+        unsigned a, b, d, e;
+        if (sscanf(t, "%u,%u,%u,%u", &a, &b, &d, &e) == 4) c->tune = wf::ExtendTune{a, b, d, e};
+    }
+    if (const char *o = getenv("PTC_OVERLAP")) { /* "traceBlocksPerSM,shadeBlocksPerSM"; "0" = one wavefront at a time */
+        int a = 0, b = 0;
+        const int got = sscanf(o, "%d,%d", &a, &b);
+        if (got == 2 && a > 0 && b > 0) c->overlapTrace = a, c->overlapShade = b;
+        else if (got >= 1 && a == 0) c->overlapTrace = c->overlapShade = 0;
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&c->evA));
+    CUDA_TRY(cudaEventCreate(&c->evB));
+    CUDA_TRY(cudaEventCreate(&c->evStart));
+    CUDA_TRY(cudaEventCreate(&c->evStop));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+    for (cudaEvent_t &e : c->evAcc) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (cudaEvent_t &e : c->evItem) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+}
+
+PTC_API int ptc_create(ptc_ctx **out, const int *device_ids, int n_devices) {
+    if (!out) return 1;
+    *out = nullptr;
+    ptc_ctx *ctx = new ptc_ctx();
+    *out = ctx; /* returned even on failure so that ptc_last_error can explain */
+    PTC_GUARD_BEGIN
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(ctx, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    std::vector<int> ids;
+    if (device_ids && n_devices > 0) {
+        ids.assign(device_ids, device_ids + n_devices);
+    } else {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
+        ids.push_back(cur);
+    }
+    for (size_t i = 0; i < ids.size(); i++) {
+        if (ids[i] < 0 || ids[i] >= count) return fail(ctx, "device id " + std::to_string(ids[i]) + " out of range (" + std::to_string(count) + " devices)");
+        for (size_t j = 0; j < i; j++)
+            if (ids[j] == ids[i]) return fail(ctx, "device id " + std::to_string(ids[i]) + " listed twice");
+    }
+    for (int id : ids) {
+        ctx->devs.emplace_back(new Dev());
+        createDev(ctx->devs.back().get(), id);
+    }
+    if (ids.size() > 1) { /* one process, several GPUs: ncclCommInitAll */
+        std::lock_guard<std::mutex> lock(g_ncclMutex);
+        if (!g_nccl.load()) return fail(ctx, g_nccl.error);
+        ctx->comms.assign(ids.size(), nullptr);
+        NCCL_TRY(g_nccl.CommInitAll(ctx->comms.data(), (int)ids.size(), ids.data()));
+    }
+    CUDA_TRY(cudaSetDevice(ids[0]));
+    return 0;
+    PTC_GUARD_END(ctx)
+}
+
+PTC_API void ptc_destroy(ptc_ctx *ctx) { delete ctx; }
+PTC_API const char *ptc_last_error(const ptc_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+PTC_API int ptc_device_count(const ptc_ctx *ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+PTC_API int ptc_comm_unique_id(uint8_t *out128) {
+    if (!out128) return 1;
+    std::lock_guard<std::mutex> lock(g_ncclMutex);
+    if (!g_nccl.load()) return 1;
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ptc_comm_unique_id hands out 128 bytes");
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return 1;
+    memcpy(out128, &id, 128);
+    return 0;
+}
+
+PTC_API int ptc_comm_init_rank(ptc_ctx *ctx, const uint8_t *id128, int rank, int world) {
+    if (!ctx || !id128) return fail(ctx, "null argument");
+    if (ctx->devs.size() != 1) return fail(ctx, "ptc_comm_init_rank needs a single-device context (one process per GPU)");
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, "bad rank / world");
+    if (!ctx->comms.empty()) return fail(ctx, "context already has a communicator");
+    PTC_GUARD_BEGIN
+    {
+        std::lock_guard<std::mutex> lock(g_ncclMutex);
+        if (!g_nccl.load()) return fail(ctx, g_nccl.error);
+    }
+    if (world == 1) return 0;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    CUDA_TRY(cudaSetDevice(ctx->devs[0]->device));
+    ctx->comms.assign(1, nullptr);
+    NCCL_TRY(g_nccl.CommInitRank(&ctx->comms[0], world, id, rank));
+    ctx->commRank = rank;
+    ctx->commWorld = world;
+    return 0;
+    PTC_GUARD_END(ctx)
+}
+
+PTC_API int ptc_upload_scene(ptc_ctx *ctx, const ptc_scene_desc *sd) {
+    if (!ctx || !sd) return fail(ctx, "null argument");
+    if (ctx->devs.empty()) return fail(ctx, "context has no CUDA device");
+    PTC_GUARD_BEGIN
+    for (auto &d : ctx->devs) d->sceneUploaded = d->accelBuilt = false;
+    validateScene(sd);
+    /* the scene is replicated: every device gets its own copy */
+    forEachDev(ctx, [&](Dev *c, uint32_t) { uploadSceneDev(c, sd); });
+    ctx->stats.upload_bytes = ctx->devs[0]->stats.upload_bytes;
+    return 0;
+    PTC_GUARD_END(ctx)
+}
+
+PTC_API int ptc_set_build_options(ptc_ctx *ctx, uint32_t hierarchy, uint32_t ploc_radius) {
+    if (!ctx) return 1;
+    if (hierarchy != PTC_HIERARCHY_LBVH && hierarchy != PTC_HIERARCHY_PLOC) return fail(ctx, "unknown hierarchy");
+    if (ploc_radius > PLOC_MAX_RADIUS) return fail(ctx, "ploc_radius must be <= 32");
+    for (auto &c : ctx->devs) {
+        c->accel.hierarchy = hierarchy;
+        c->accel.plocRadius = ploc_radius ? ploc_radius : 16u;
+        c->accelBuilt = false;
     }
     return 0;
-    PTC_GUARD_END(c)
 }
 
-PTC_API int ptc_render(ptc_ctx *c, const ptc_render_params *rp, float *radiance, float *albedo, float *normal) {
-    if (int rcode = renderChecked(c, rp)) return rcode;
+PTC_API int ptc_build_accel(ptc_ctx *ctx) {
+    if (!ctx) return 1;
+    if (ctx->devs.empty()) return fail(ctx, "context has no CUDA device");
+    for (auto &d : ctx->devs)
+        if (!d->sceneUploaded) return fail(ctx, "ptc_upload_scene has not been called");
     PTC_GUARD_BEGIN
-    CUDA_TRY(cudaSetDevice(c->device));
-    const size_t nPix = (size_t)rp->width * rp->height;
-    c->accR.alloc(nPix);
-    c->accA.alloc(nPix);
-    c->accN.alloc(nPix);
-    int rcode = renderImpl(c, rp, c->accR.p, c->accA.p, c->accN.p);
-    if (rcode) return rcode;
-    k_fill_alpha<<<(unsigned)((nPix + 255) / 256), 256, 0, c->stream>>>(c->accR.p, c->accA.p, c->accN.p, nPix);
-    /* readback like getRenderTargetData x3 (…PathTracing.cpp:890-893) */
-    if (radiance) CUDA_TRY(cudaMemcpyAsync(radiance, c->accR.p, nPix * 16, cudaMemcpyDeviceToHost, c->stream));
-    if (albedo) CUDA_TRY(cudaMemcpyAsync(albedo, c->accA.p, nPix * 16, cudaMemcpyDeviceToHost, c->stream));
-    if (normal) CUDA_TRY(cudaMemcpyAsync(normal, c->accN.p, nPix * 16, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    /* every device builds its own copy from the same input: the build is deterministic, so the copies are identical */
+    forEachDev(ctx, [&](Dev *c, uint32_t) {
+        CUDA_TRY(cudaEventRecord(c->evA, c->stream));
+        c->accel.run(c->vertices.p, c->indices.p, c->instances.p, c->nInstances, c->nWorldTris, c->stream);
+        CUDA_TRY(cudaEventRecord(c->evB, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, c->evA, c->evB));
+        c->accelBuilt = true;
+        setTraversalWindow(c);
+        c->stats.build_ms = ms;
+        c->stats.n_triangles = c->nWorldTris;
+        c->stats.n_bvh_nodes = c->accel.nWide;
+        c->stats.scene_bytes = c->accel.bytes() + c->vertices.bytes() + c->indices.bytes() + c->instances.bytes() + c->materials.bytes();
+    });
+    const ptc_stats &b0 = ctx->devs[0]->stats;
+    ctx->stats.build_ms = b0.build_ms, ctx->stats.n_triangles = b0.n_triangles, ctx->stats.n_bvh_nodes = b0.n_bvh_nodes, ctx->stats.scene_bytes = b0.scene_bytes;
+    for (auto &d : ctx->devs) ctx->stats.build_ms = std::max(ctx->stats.build_ms, d->stats.build_ms);
     return 0;
-    PTC_GUARD_END(c)
+    PTC_GUARD_END(ctx)
 }
 
-PTC_API float ptc_progress(const ptc_ctx *c) { return c ? c->progress.load() : 0.0f; }
-PTC_API int ptc_get_stats(ptc_ctx *c, ptc_stats *out) {
-    if (!c || !out) return 1;
-    *out = c->stats;
+PTC_API int ptc_render_device(ptc_ctx *ctx, const ptc_render_params *rp, void *dR, void *dA, void *dN) {
+    if (!ctx || !rp) return fail(ctx, "null argument");
+    if (ctx->devs.empty()) return fail(ctx, "context has no CUDA device");
+    PTC_GUARD_BEGIN
+    void *const d[3] = {dR, dA, dN};
+    renderAll(ctx, rp, d, nullptr);
+    return 0;
+    PTC_GUARD_END(ctx)
+}
+
+PTC_API int ptc_render(ptc_ctx *ctx, const ptc_render_params *rp, float *radiance, float *albedo, float *normal) {
+    if (!ctx || !rp) return fail(ctx, "null argument");
+    if (ctx->devs.empty()) return fail(ctx, "context has no CUDA device");
+    PTC_GUARD_BEGIN
+    float *const h[3] = {radiance, albedo, normal};
+    renderAll(ctx, rp, nullptr, h);
+    return 0;
+    PTC_GUARD_END(ctx)
+}
+
+PTC_API float ptc_progress(const ptc_ctx *ctx) {
+    if (!ctx || ctx->devs.empty()) return 0.0f;
+    float p = 0.0f;
+    for (auto &d : ctx->devs) p += d->progress.load();
+    return p / (float)ctx->devs.size();
+}
+PTC_API int ptc_get_stats(ptc_ctx *ctx, ptc_stats *out) {
+    if (!ctx || !out) return 1;
+    *out = ctx->stats;
     return 0;
 }
 
-PTC_API int ptc_trace_closest(ptc_ctx *c, const float *rays, int n, int *inst, int *prim, float *t, float *u, float *v) {
-    if (!c || !rays) return fail(c, "null argument");
-    if (!c->accelBuilt) return fail(c, "ptc_build_accel has not been called");
+PTC_API int ptc_trace_closest(ptc_ctx *ctx, const float *rays, int n, int *inst, int *prim, float *t, float *u, float *v) {
+    Dev *c = dev0(ctx);
+    if (!c || !rays) return fail(ctx, "null argument");
+    if (!c->accelBuilt) return fail(ctx, "ptc_build_accel has not been called");
     if (n <= 0) return 0;
     PTC_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
@@ -916,13 +1245,14 @@ PTC_API int ptc_trace_closest(ptc_ctx *c, const float *rays, int n, int *inst, i
     if (v) CUDA_TRY(cudaMemcpyAsync(v, dV.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return 0;
-    PTC_GUARD_END(c)
+    PTC_GUARD_END(ctx)
 }
 
-PTC_API int ptc_get_lbvh(ptc_ctx *c, uint64_t *n_out, uint64_t *morton, uint32_t *order, int32_t *parent, int32_t *left, int32_t *right,
+PTC_API int ptc_get_lbvh(ptc_ctx *ctx, uint64_t *n_out, uint64_t *morton, uint32_t *order, int32_t *parent, int32_t *left, int32_t *right,
                          float *aabb) {
+    Dev *c = dev0(ctx);
     if (!c) return 1;
-    if (!c->accelBuilt) return fail(c, "ptc_build_accel has not been called");
+    if (!c->accelBuilt) return fail(ctx, "ptc_build_accel has not been called");
     PTC_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
     const lbvh::Build &B = c->accel;
@@ -945,12 +1275,13 @@ PTC_API int ptc_get_lbvh(ptc_ctx *c, uint64_t *n_out, uint64_t *morton, uint32_t
         }
     }
     return 0;
-    PTC_GUARD_END(c)
+    PTC_GUARD_END(ctx)
 }
 
-PTC_API int ptc_get_wide_bvh(ptc_ctx *c, uint64_t *n_nodes_out, uint64_t *n_tris_out, uint32_t *node_words, uint32_t *tri_order) {
+PTC_API int ptc_get_wide_bvh(ptc_ctx *ctx, uint64_t *n_nodes_out, uint64_t *n_tris_out, uint32_t *node_words, uint32_t *tri_order) {
+    Dev *c = dev0(ctx);
     if (!c) return 1;
-    if (!c->accelBuilt) return fail(c, "ptc_build_accel has not been called");
+    if (!c->accelBuilt) return fail(ctx, "ptc_build_accel has not been called");
     PTC_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
     const lbvh::Build &B = c->accel;
@@ -960,11 +1291,12 @@ PTC_API int ptc_get_wide_bvh(ptc_ctx *c, uint64_t *n_nodes_out, uint64_t *n_tris
     if (node_words) CUDA_TRY(cudaMemcpy(node_words, B.wideNodes(), (size_t)B.nWide * 80, cudaMemcpyDeviceToHost));
     if (tri_order) CUDA_TRY(cudaMemcpy(tri_order, B.wideOrder.p, (size_t)B.n * 4, cudaMemcpyDeviceToHost));
     return 0;
-    PTC_GUARD_END(c)
+    PTC_GUARD_END(ctx)
 }
 
-PTC_API int ptc_bsdf_eval(ptc_ctx *c, int n, const float *params, const float *wi, const float *wo, float *out_f, float *out_pdf) {
-    if (!c || !c->stream) return fail(c, "context has no CUDA device");
+PTC_API int ptc_bsdf_eval(ptc_ctx *ctx, int n, const float *params, const float *wi, const float *wo, float *out_f, float *out_pdf) {
+    Dev *c = dev0(ctx);
+    if (!c || !c->stream) return fail(ctx, "context has no CUDA device");
     if (n <= 0) return 0;
     PTC_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
@@ -981,12 +1313,13 @@ PTC_API int ptc_bsdf_eval(ptc_ctx *c, int n, const float *params, const float *w
     CUDA_TRY(cudaMemcpyAsync(out_pdf, dPdf.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return 0;
-    PTC_GUARD_END(c)
+    PTC_GUARD_END(ctx)
 }
 
-PTC_API int ptc_bsdf_sample(ptc_ctx *c, int n, const float *params, const float *wo, const float *u, float *out_wi, float *out_f,
+PTC_API int ptc_bsdf_sample(ptc_ctx *ctx, int n, const float *params, const float *wo, const float *u, float *out_wi, float *out_f,
                             float *out_pdf) {
-    if (!c || !c->stream) return fail(c, "context has no CUDA device");
+    Dev *c = dev0(ctx);
+    if (!c || !c->stream) return fail(ctx, "context has no CUDA device");
     if (n <= 0) return 0;
     PTC_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1005,14 +1338,15 @@ PTC_API int ptc_bsdf_sample(ptc_ctx *c, int n, const float *params, const float 
     CUDA_TRY(cudaMemcpyAsync(out_pdf, dPdf.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return 0;
-    PTC_GUARD_END(c)
+    PTC_GUARD_END(ctx)
 }
 
-PTC_API int ptc_sampler_points(ptc_ctx *c, uint32_t px, uint32_t py, uint32_t width, uint32_t first_index, uint32_t count, uint32_t dimension,
+PTC_API int ptc_sampler_points(ptc_ctx *ctx, uint32_t px, uint32_t py, uint32_t width, uint32_t first_index, uint32_t count, uint32_t dimension,
                                uint32_t flags, float *out_xy) {
-    if (!c || !c->stream) return fail(c, "context has no CUDA device");
+    Dev *c = dev0(ctx);
+    if (!c || !c->stream) return fail(ctx, "context has no CUDA device");
     if (count == 0) return 0;
-    if (!out_xy) return fail(c, "null argument");
+    if (!out_xy) return fail(ctx, "null argument");
     PTC_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
     DBuf<float> dO;
@@ -1022,11 +1356,12 @@ PTC_API int ptc_sampler_points(ptc_ctx *c, uint32_t px, uint32_t py, uint32_t wi
     CUDA_TRY(cudaMemcpyAsync(out_xy, dO.p, (size_t)count * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
-    PTC_GUARD_END(c)
+    PTC_GUARD_END(ctx)
 }
 
-PTC_API int ptc_env_lookup(ptc_ctx *c, int n, const float *dirs, float *out_rgb) {
-    if (!c || !c->stream) return fail(c, "context has no CUDA device");
+PTC_API int ptc_env_lookup(ptc_ctx *ctx, int n, const float *dirs, float *out_rgb) {
+    Dev *c = dev0(ctx);
+    if (!c || !c->stream) return fail(ctx, "context has no CUDA device");
     if (n <= 0) return 0;
     PTC_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1040,12 +1375,13 @@ PTC_API int ptc_env_lookup(ptc_ctx *c, int n, const float *dirs, float *out_rgb)
     CUDA_TRY(cudaMemcpyAsync(out_rgb, dO.p, (size_t)n * 12, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return 0;
-    PTC_GUARD_END(c)
+    PTC_GUARD_END(ctx)
 }
 
-PTC_API int ptc_env_sample(ptc_ctx *c, int n, const float *u01, float *out_dirs, float *out_pdf) {
-    if (!c || !c->stream) return fail(c, "context has no CUDA device");
-    if (!c->cubeTex || !c->envCdfV.p) return fail(c, "no environment");
+PTC_API int ptc_env_sample(ptc_ctx *ctx, int n, const float *u01, float *out_dirs, float *out_pdf) {
+    Dev *c = dev0(ctx);
+    if (!c || !c->stream) return fail(ctx, "context has no CUDA device");
+    if (!c->cubeTex || !c->envCdfV.p) return fail(ctx, "no environment");
     if (n <= 0) return 0;
     PTC_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1060,12 +1396,13 @@ PTC_API int ptc_env_sample(ptc_ctx *c, int n, const float *u01, float *out_dirs,
     CUDA_TRY(cudaMemcpyAsync(out_pdf, dP.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return 0;
-    PTC_GUARD_END(c)
+    PTC_GUARD_END(ctx)
 }
 
-PTC_API int ptc_env_pdf(ptc_ctx *c, int n, const float *dirs, float *out_pdf) {
-    if (!c || !c->stream) return fail(c, "context has no CUDA device");
-    if (!c->cubeTex || !c->envCdfV.p) return fail(c, "no environment");
+PTC_API int ptc_env_pdf(ptc_ctx *ctx, int n, const float *dirs, float *out_pdf) {
+    Dev *c = dev0(ctx);
+    if (!c || !c->stream) return fail(ctx, "context has no CUDA device");
+    if (!c->cubeTex || !c->envCdfV.p) return fail(ctx, "no environment");
     if (n <= 0) return 0;
     PTC_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1078,7 +1415,7 @@ PTC_API int ptc_env_pdf(ptc_ctx *c, int n, const float *dirs, float *out_pdf) {
     CUDA_TRY(cudaMemcpyAsync(out_pdf, dP.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return 0;
-    PTC_GUARD_END(c)
+    PTC_GUARD_END(ctx)
 }
 
 } /* extern "C" */

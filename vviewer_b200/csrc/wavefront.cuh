@@ -1103,10 +1103,23 @@ __global__ void __launch_bounds__(256) k_accumulate(Wave w, const __grid_constan
         cn += f3(ldS(&w.aovNormal[slot])) / total;
     }
     const uint32_t pixel = rc.pixmap ? rc.pixmap[p] : p;
+    /* alpha is not touched here: partitioned renders are SUMMED over ranks, so exactly one place writes the 1 (k_fill_alpha, after
+     * the reduce / on the rank that owns the image) */
     float4 r = accR[pixel], a = accA[pixel], n = accN[pixel];
-    accR[pixel] = make_float4(r.x + cr.x, r.y + cr.y, r.z + cr.z, 1.0f);
-    accA[pixel] = make_float4(a.x + ca.x, a.y + ca.y, a.z + ca.z, 1.0f);
-    accN[pixel] = make_float4(n.x + cn.x, n.y + cn.y, n.z + cn.z, 1.0f);
+    accR[pixel] = make_float4(r.x + cr.x, r.y + cr.y, r.z + cr.z, r.w);
+    accA[pixel] = make_float4(a.x + ca.x, a.y + ca.y, a.z + ca.z, a.w);
+    accN[pixel] = make_float4(n.x + cn.x, n.y + cn.y, n.z + cn.z, n.w);
+}
+
+/* tile split: block k fills the pixels of this rank's k-th tile (tiles rank, rank + world, ... in row-major tile order), tile by
+ * tile, row-major inside the tile; offsets[k] = first local pixel index of tile k (edge tiles are smaller) */
+__global__ void __launch_bounds__(256) k_tile_pixmap(uint32_t W, uint32_t H, uint32_t tile, uint32_t rank, uint32_t world, const uint32_t *__restrict__ offsets,
+                                                     uint32_t *__restrict__ pixmap) {
+    const uint32_t tilesX = (W + tile - 1) / tile;
+    const uint32_t t = rank + blockIdx.x * world, tx = t % tilesX, ty = t / tilesX;
+    const uint32_t x0 = tx * tile, y0 = ty * tile, tw = min(tile, W - x0), th = min(tile, H - y0);
+    const uint32_t base = offsets[blockIdx.x];
+    for (uint32_t i = threadIdx.x; i < tw * th; i += blockDim.x) pixmap[base + i] = (y0 + i / tw) * W + x0 + i % tw;
 }
 
 /* sums the per-bounce queue counters into the statistics block */

@@ -37,9 +37,9 @@ static std::string hex64(uint64_t v) {
 
 extern "C" {
 
-PTC_API vh_engine *vh_engine_create(const char *backend_lib, const char *asset_root) {
+PTC_API vh_engine *vh_engine_create(const char *asset_root) {
     auto *h = new vh_engine();
-    h->engine = std::make_unique<Engine>("vh", backend_lib ? backend_lib : "", asset_root ? asset_root : "");
+    h->engine = std::make_unique<Engine>("vh", asset_root ? asset_root : "");
     h->engine->initResources();
     return h;
 }
@@ -305,6 +305,31 @@ PTC_API void vh_set_render_info(vh_engine *h, int width, int height, int samples
     if (depth > 0) ri.depth = (uint32_t)depth;
 }
 
+PTC_API int vh_set_devices(vh_engine *h, const int *device_ids, int n_devices) {
+    if (!h) return 1;
+    std::vector<int> ids;
+    if (device_ids && n_devices > 0) ids.assign(device_ids, device_ids + n_devices);
+    return h->engine->renderer().rendererPathTracing().setDevices(ids) ? 0 : 2;
+}
+PTC_API int vh_device_count(vh_engine *h) { return h ? h->engine->renderer().rendererPathTracing().deviceCount() : 0; }
+PTC_API int vh_comm_unique_id(vh_engine *h, uint8_t *out128) {
+    if (!h || !out128) return 1;
+    return h->engine->renderer().rendererPathTracing().commUniqueId(out128) ? 0 : 2;
+}
+PTC_API int vh_comm_init_rank(vh_engine *h, const uint8_t *id128, int rank, int world) {
+    if (!h || !id128) return 1;
+    return h->engine->renderer().rendererPathTracing().commInitRank(id128, rank, world) ? 0 : 2;
+}
+PTC_API void vh_set_render_options(vh_engine *h, int multi_gpu_split, int sampler, int env_importance) {
+    auto &ri = h->engine->renderer().rendererPathTracing().renderInfo();
+    if (multi_gpu_split >= 0) ri.multiGpuSplit = (uint32_t)multi_gpu_split;
+    if (sampler >= 0) {
+        ri.lowDiscrepancySampler = sampler == 1;
+        ri.pmjSampler = sampler == 2;
+    }
+    if (env_importance >= 0) ri.environmentImportanceSampling = env_importance != 0;
+}
+
 PTC_API void vh_get_render_info(vh_engine *h, int *width, int *height, int *samples, int *batch_size, int *depth) {
     auto &ri = h->engine->renderer().rendererPathTracing().renderInfo();
     if (width) *width = (int)ri.width;
@@ -340,6 +365,34 @@ PTC_API int vh_render(vh_engine *h, const char *filename) {
     if (filename) pt.renderInfo().filename = filename;
     if (!pt.isRayTracingEnabled()) return 2;
     pt.render();
+    return 0;
+}
+
+/* frame `frame` of the BallOnPlane render sequence (PtSceneBallOnPlane.cpp:44-55): only the camera moves */
+PTC_API int vh_set_sequence_frame(vh_engine *h, int frame) {
+    if (!h || !h->engine->scene().camera()) return 1;
+    scenes::ballOnPlaneFrame(*h->engine, frame);
+    h->flatValid = false;
+    return 0;
+}
+
+/* the output half of RenderInfo (core/Renderer.hpp:14-28): file type, PNG exposure, AOV files, denoise flag; negative keeps */
+PTC_API void vh_set_output(vh_engine *h, int file_type, float exposure, int write_all_files, int denoise) {
+    auto &ri = h->engine->renderer().rendererPathTracing().renderInfo();
+    if (file_type >= 0) ri.fileType = file_type == 1 ? FileType::PNG : FileType::HDR;
+    ri.exposure = exposure;
+    if (write_all_files >= 0) ri.writeAllFiles = write_all_files != 0;
+    if (denoise >= 0) ri.denoise = denoise != 0;
+}
+
+/* storeToDisk's last step on a caller's image (VulkanRendererPathTracing.cpp:958-975 + core/ImageUtils.cpp:34-76): PNG gets
+ * v * 2^exposure when exposure != 0, clamp, linear -> sRGB, uchar(255 x) truncation; HDR is written as RGBE */
+PTC_API int vh_write_image(const char *filename_no_ext, int w, int h, int channels, const float *data, int file_type, float exposure) {
+    if (!filename_no_ext || !data || w <= 0 || h <= 0 || channels <= 0) return 1;
+    std::vector<float> img(data, data + (size_t)w * h * channels);
+    const FileType ft = file_type == 1 ? FileType::PNG : FileType::HDR;
+    if (ft == FileType::PNG && exposure != 0.0f) applyExposure(img, exposure, (uint32_t)channels);
+    writeToDisk(img, filename_no_ext, ft, (uint32_t)w, (uint32_t)h, (uint32_t)channels);
     return 0;
 }
 

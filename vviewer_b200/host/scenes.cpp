@@ -330,6 +330,39 @@ static void depthOfField(Engine &e) {
     testRenderInfo(e, "DepthOfField", 2048, 4);
 }
 
+/* src/bin/offlinerender/PtSceneBallOnPlane.cpp:8-32 (create) */
+static void ballOnPlane(Engine &e) {
+    Scene &scene = e.scene();
+    auto camera = makeCamera(scene, vec3(0, 3, 10), vec3(vm::radians(-15.0f), 0, 0));
+    camera->fov() = 60.0f;
+    camera->lensRadius() = 0.03f;
+    camera->focalDistance() = 7.0f;
+    BaseMeshes bm = baseMeshes(e);
+    Material *def = e.materials().get("defaultMaterial");
+    addMeshObject(scene, "plane", Transform({0, -3, 0}, {10, 10, 10}), bm.plane, def);
+    addMeshObject(scene, "uvsphere", Transform({0, 0, 0}, {3, 3, 3}), bm.sphere, def);
+    scene.addSceneObject("light", Transform({4, 1.5f, 0}))->add<ComponentLight>().setLight(e.lightsMap().get("defaultPointLight"));
+    scene.environmentIntensity() = 1.0f;
+    scene.update();
+    /* PtSceneBallOnPlane.cpp:38-42 (the reference also denoises, which is out of scope: OIDN) */
+    RI &ri = info(e);
+    ri = RI();
+    ri.filename = "0";
+    ri.samples = 64;
+    ri.batchSize = 64;
+    ri.fileType = FileType::PNG;
+    ri.denoise = false;
+    ri.writeAllFiles = false;
+}
+
+/* PtSceneBallOnPlane.cpp:44-55: frame i of the render sequence - the camera orbits the ball in 45 degree steps */
+void ballOnPlaneFrame(Engine &e, int frame) {
+    const float height = 1.0f, radius = 10.0f, a = vm::radians(45.0f) * (float)frame;
+    e.renderer().rendererPathTracing().renderInfo().filename = std::to_string(frame);
+    e.scene().camera()->transform().position() = vec3(radius * std::sin(a), height, radius * std::cos(a));
+    e.scene().camera()->transform().setRotationEuler(0, a, 0);
+}
+
 /* RenderTests.cpp:969-1031 */
 static void sharedComponents(Engine &e) {
     Scene &scene = e.scene();
@@ -975,7 +1008,7 @@ std::vector<std::string> list() {
     return {"FurnacePBR", "FurnaceLambert", "EnvironmentMap", "EnvironmentMapPBR00", "EnvironmentMapPBR01", "EnvironmentMapPBR10", "EnvironmentMapPBR11",
             "EnvironmentMapLambert", "Volume0", "Volume1", "Volume2", "Volume3", "Volume4", "Volume5", "Volume6", "Volume7", "Volume8", "Volume9",
             "PointLight", "DirectionalLight", "MeshLight", "Transparency", "NormalMap", "GLTF", "Hierarchy", "DepthOfField", "SharedComponents", "Denoise",
-            "Cornell", "Atrium", "Fog", "Instanced", "Progressive"};
+            "Cornell", "Atrium", "Fog", "Instanced", "Progressive", "BallOnPlane"};
 }
 
 bool build(Engine &e, const std::string &name, const Options &opt) {
@@ -1001,6 +1034,7 @@ bool build(Engine &e, const std::string &name, const Options &opt) {
     else if (name == "Fog") atrium(e, opt, true);
     else if (name == "Progressive") progressive(e, opt);
     else if (name == "Instanced") instanced(e, opt);
+    else if (name == "BallOnPlane") ballOnPlane(e);
     else return false;
     return true;
 }

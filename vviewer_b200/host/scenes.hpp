@@ -23,6 +23,10 @@ std::vector<std::string> list();
 /* Clears the engine's scene, builds `name`, calls scene.update() and fills renderInfo() with the recipe's
  * settings (resolution, samples, batch size, depth, file name). Returns false for an unknown name. */
 bool build(Engine &engine, const std::string &name, const Options &opt = Options());
+/* the render sequence of the reference's BallOnPlane demo (src/bin/offlinerender/PtSceneBallOnPlane.cpp:44-55): moves the
+ * camera of an already built "BallOnPlane" scene to frame 0..7 of its orbit and names the output file after the frame */
+constexpr int kBallOnPlaneFrames = 8;
+void ballOnPlaneFrame(Engine &engine, int frame);
 
 }  // namespace scenes
 }  // namespace vengine

@@ -336,9 +336,7 @@ static std::string selfDir() {
     return ".";
 }
 
-Engine::Engine(const std::string &name, const std::string &backendLib, const std::string &assetRoot)
-    : m_name(name), m_backendLib(backendLib), m_assetRoot(assetRoot) {
-    if (m_backendLib.empty()) m_backendLib = selfDir() + "/libptc_cuda.so";
+Engine::Engine(const std::string &name, const std::string &assetRoot) : m_name(name), m_assetRoot(assetRoot) {
     if (m_assetRoot.empty()) {
         const char *env = std::getenv("VVIEWER_ASSETS");
         m_assetRoot = env ? env : (selfDir() + "/../..");
@@ -346,7 +344,7 @@ Engine::Engine(const std::string &name, const std::string &backendLib, const std
     m_textures = std::make_unique<Textures>();
     m_materials = std::make_unique<Materials>(*m_textures);
     m_scene = std::make_unique<Scene>(*this);
-    m_renderer = std::make_unique<Renderer>(std::make_unique<CudaRendererPathTracing>(*this, m_backendLib));
+    m_renderer = std::make_unique<Renderer>(std::make_unique<CudaRendererPathTracing>(*this));
 }
 Engine::~Engine() {}
 
@@ -611,14 +609,17 @@ bool PtcBackend::load(const std::string &libPath, std::string *err) {
     PTC_SYM(render, ptc_render)
     PTC_SYM(progress, ptc_progress)
     PTC_SYM(get_stats, ptc_get_stats)
+    PTC_SYM(device_count, ptc_device_count)
+    PTC_SYM(comm_unique_id, ptc_comm_unique_id)
+    PTC_SYM(comm_init_rank, ptc_comm_init_rank)
 #undef PTC_SYM
     return true;
 }
 
-CudaRendererPathTracing::CudaRendererPathTracing(Engine &engine, const std::string &backendLib) : m_engine(engine) {
+CudaRendererPathTracing::CudaRendererPathTracing(Engine &engine) : m_engine(engine) {
     /* like VulkanRendererPathTracing::initResources (…PathTracing.cpp:45-91) a failure leaves
      * isRayTracingEnabled() == false; render() then reports the error and returns */
-    if (!m_backend.load(backendLib, &m_error)) {
+    if (!m_backend.load(selfDir() + "/libptc_cuda.so", &m_error)) {
         std::fprintf(stderr, "CudaRendererPathTracing: %s\n", m_error.c_str());
         return;
     }
@@ -632,6 +633,37 @@ CudaRendererPathTracing::CudaRendererPathTracing(Engine &engine, const std::stri
 
 CudaRendererPathTracing::~CudaRendererPathTracing() {
     if (m_ctx) m_backend.destroy(m_ctx);
+}
+
+bool CudaRendererPathTracing::setDevices(const std::vector<int> &deviceIds) {
+    if (!m_backend.create || m_renderInProgress) return false;
+    ptc_ctx *fresh = nullptr;
+    if (m_backend.create(&fresh, deviceIds.empty() ? nullptr : deviceIds.data(), (int)deviceIds.size()) != 0 || !fresh) {
+        m_error = std::string("ptc_create failed: ") + (fresh ? m_backend.last_error(fresh) : "no context");
+        if (fresh) m_backend.destroy(fresh);
+        std::fprintf(stderr, "CudaRendererPathTracing::setDevices(): %s\n", m_error.c_str());
+        return false;
+    }
+    if (m_ctx) m_backend.destroy(m_ctx);
+    m_ctx = fresh;
+    m_commRank = 0;
+    m_commWorld = 1;
+    m_isInitialized = true;
+    return true;
+}
+
+bool CudaRendererPathTracing::commUniqueId(uint8_t out128[128]) { return m_backend.comm_unique_id && m_backend.comm_unique_id(out128) == 0; }
+
+bool CudaRendererPathTracing::commInitRank(const uint8_t id128[128], int rank, int world) {
+    if (!m_isInitialized) return false;
+    if (m_backend.comm_init_rank(m_ctx, id128, rank, world) != 0) {
+        m_error = m_backend.last_error(m_ctx);
+        std::fprintf(stderr, "CudaRendererPathTracing::commInitRank(): %s\n", m_error.c_str());
+        return false;
+    }
+    m_commRank = rank;
+    m_commWorld = world;
+    return true;
 }
 
 float CudaRendererPathTracing::renderProgress() { return (m_ctx && m_isInitialized) ? m_backend.progress(m_ctx) : 0.0f; }
@@ -674,10 +706,12 @@ ptc_render_params CudaRendererPathTracing::makeRenderParams() {
     rp.depth = renderInfo().depth;
     rp.width = width;
     rp.height = height;
-    rp.split_mode = PTC_SPLIT_NONE;
+    /* several GPUs: the core fills in rank / world itself; the caller only chooses how the image is cut */
+    rp.split_mode = renderInfo().multiGpuSplit == 1u ? PTC_SPLIT_TILE : (renderInfo().multiGpuSplit == 2u ? PTC_SPLIT_SAMPLE : PTC_SPLIT_NONE);
     rp.rank = 0;
     rp.world = 1;
     rp.flags = renderInfo().lowDiscrepancySampler ? PTC_FLAG_SAMPLER_SOBOL : 0u;
+    if (renderInfo().pmjSampler) rp.flags = (rp.flags & ~PTC_FLAG_SAMPLER_SOBOL) | PTC_FLAG_SAMPLER_PMJ;
     if (renderInfo().environmentImportanceSampling) rp.flags |= PTC_FLAG_ENV_IMPORTANCE;
     return rp;
 }
@@ -737,6 +771,7 @@ void CudaRendererPathTracing::render() {
     auto t0 = std::chrono::steady_clock::now();
     std::vector<float> radiance, albedo, normal;
     if (!renderToMemory(radiance, albedo, normal)) return;
+    if (m_commRank != 0) return; /* one process per GPU: the image lives on rank 0 */
     /* storeToDisk, …PathTracing.cpp:958-1027 (OIDN is out of scope: denoise == true writes the
      * un-denoised radiance and, with writeAllFiles, the _radiance AOV) */
     const RenderInfo &ri = renderInfo();

@@ -698,6 +698,11 @@ public:
         /* extension, off for parity (the reference never light-samples the environment, lightSampling.glsl:101-106):
          * luminance importance sampling of the HDRI environment + MIS (PTC_FLAG_ENV_IMPORTANCE) */
         bool environmentImportanceSampling = false;
+        /* extension: how a renderer that drives several GPUs partitions the image: 0 = backend default (sample
+         * batches), 1 = image tiles (ptc_split_mode PTC_SPLIT_TILE), 2 = sample batches.  Ignored on one GPU. */
+        uint32_t multiGpuSplit = 0u;
+        /* extension: the reference's optional PMJ02BN sampler (rng_pmj.glsl; tables of math/PMJSequences.cpp, BlueNoise.cpp) */
+        bool pmjSampler = false;
     };
     virtual ~RendererPathTracing() {}
     RenderInfo &renderInfo() { return m_renderInfo; }
@@ -709,7 +714,8 @@ private:
     RenderInfo m_renderInfo;
 };
 
-/* the backend function table, resolved from a shared library that exports include/ptc.h */
+/* the function table of the CUDA path-tracing core (libptc_cuda.so next to this library; include/ptc.h).  The host library
+ * resolves it at run time so that it links no CUDA itself; there is no other backend and no CPU fallback. */
 struct PtcBackend {
     void *handle = nullptr;
     std::string path;
@@ -722,13 +728,16 @@ struct PtcBackend {
     decltype(&ptc_render) render = nullptr;
     decltype(&ptc_progress) progress = nullptr;
     decltype(&ptc_get_stats) get_stats = nullptr;
+    decltype(&ptc_device_count) device_count = nullptr;
+    decltype(&ptc_comm_unique_id) comm_unique_id = nullptr;
+    decltype(&ptc_comm_init_rank) comm_init_rank = nullptr;
     bool load(const std::string &libPath, std::string *err);
 };
 
 /* B200 implementation of the boundary: replaces VulkanRendererPathTracing (…PathTracing.cpp:121-226, 791-1027) */
 class CudaRendererPathTracing : public RendererPathTracing {
 public:
-    CudaRendererPathTracing(Engine &engine, const std::string &backendLib);
+    explicit CudaRendererPathTracing(Engine &engine);
     ~CudaRendererPathTracing() override;
     bool isRayTracingEnabled() const override { return m_isInitialized; }
     void render() override;
@@ -741,6 +750,16 @@ public:
     const ptc_stats &lastStats() const { return m_stats; }
     const std::string &lastError() const { return m_error; }
     const char *backendName() const { return m_backend.backend_name ? m_backend.backend_name() : "none"; }
+    /* multi-GPU.  setDevices: this renderer drives the listed GPUs of the box from one process (NCCL communicator
+     * inside the core); the scene is re-uploaded by the next render().  commUniqueId / commInitRank: one process per GPU
+     * (torchrun, MPI) - every rank's renderer joins one communicator; render() is then collective and only rank 0 gets /
+     * writes the image. */
+    bool setDevices(const std::vector<int> &deviceIds);
+    int deviceCount() const { return (m_ctx && m_backend.device_count) ? m_backend.device_count(m_ctx) : 0; }
+    bool commUniqueId(uint8_t out128[128]);
+    bool commInitRank(const uint8_t id128[128], int rank, int world);
+    int commRank() const { return m_commRank; }
+    int commWorld() const { return m_commWorld; }
 
 private:
     Engine &m_engine;
@@ -748,6 +767,7 @@ private:
     ptc_ctx *m_ctx = nullptr;
     bool m_isInitialized = false;
     bool m_renderInProgress = false;
+    int m_commRank = 0, m_commWorld = 1;
     ptc_stats m_stats{};
     std::string m_error;
 };
@@ -763,9 +783,9 @@ private:
 /* ------------------------------------------------------------------ core/Engine.hpp + vulkan/VulkanEngine.cpp */
 class Engine {
 public:
-    /* backendLib: path of a shared library exporting include/ptc.h. Empty = the CUDA product library next
-     * to this one (vviewer_b200/_lib/libptc_cuda.so). There is no CPU fallback. */
-    explicit Engine(const std::string &name, const std::string &backendLib = "", const std::string &assetRoot = "");
+    /* The path tracer is the CUDA core next to this library (vviewer_b200/_lib/libptc_cuda.so): no other backend, no CPU
+     * fallback.  assetRoot: directory that contains assets/ (empty = $VVIEWER_ASSETS or the repository root). */
+    explicit Engine(const std::string &name, const std::string &assetRoot = "");
     ~Engine();
     void initResources(); /* VulkanEngine.cpp:32-48 + initDefaultData :331-391 */
     void releaseResources() {}
@@ -789,7 +809,7 @@ public:
     void flatten(FlatScene &out);
 
 private:
-    std::string m_name, m_backendLib, m_assetRoot;
+    std::string m_name, m_assetRoot;
     std::unique_ptr<Textures> m_textures;
     std::unique_ptr<Materials> m_materials;
     std::unique_ptr<Scene> m_scene;
