@@ -208,6 +208,7 @@ typedef struct ptc_stats {
     uint64_t upload_bytes;    /* host -> device bytes of the last ptc_upload_scene, per device (textures / the environment that stayed
                                  resident by uid are not copied and not counted) */
     double reduce_ms;         /* multi-GPU: the NCCL reduce of the accumulation buffers inside the last render */
+    double bin_ms;            /* time inside the ray-binning kernel (PTC_FLAG_TIME_KERNELS) */
 } ptc_stats;
 
 typedef struct ptc_ctx ptc_ctx;
@@ -238,6 +239,12 @@ PTC_API const char *ptc_backend_name(void); /* "cuda-sm_100a" or "cpu-oracle" */
 PTC_API int ptc_upload_scene(ptc_ctx *ctx, const ptc_scene_desc *scene);
 /* replaces the driver BLAS/TLAS builds: on-device LBVH over world-space triangles */
 PTC_API int ptc_build_accel(ptc_ctx *ctx);
+
+/* The tables of the reference's optional PMJ02BN sampler (PTC_FLAG_SAMPLER_PMJ), copied during the call: pmj =
+ * [n_sequences = 16][n_samples = 16384][2] floats (math/PMJSequences.cpp), blue = [n_textures = 48][resolution = 128][128] floats
+ * (math/BlueNoise.cpp).  Replaces VulkanRandom::createBuffers (vulkan/resources/VulkanRandom.cpp:40-72). */
+PTC_API int ptc_set_sampler_tables(ptc_ctx *ctx, const float *pmj, uint32_t n_sequences, uint32_t n_samples, const float *blue, uint32_t n_textures,
+                                   uint32_t resolution);
 
 /* Hierarchy over the Morton-sorted triangles, before the collapse to the 8-wide compressed BVH:
  *   PTC_HIERARCHY_LBVH  Karras 2012 radix tree (splits at the highest differing Morton bit)
@@ -286,8 +293,10 @@ PTC_API int ptc_bsdf_sample(ptc_ctx *ctx, int n, const float *params, const floa
                             float *out_f, float *out_pdf);
 
 /* Sampler parity hook: the rand2D() points (x, y interleaved in out_xy[2 * count]) that the sampler selected by `flags`
- * (PTC_FLAG_SAMPLER_SOBOL or 0) hands to pixel (px, py) of an image `width` wide at dimension `dimension`, for the global
- * sample indices first_index .. first_index + count - 1. */
+ * (PTC_FLAG_SAMPLER_SOBOL, PTC_FLAG_SAMPLER_PMJ or 0) hands to pixel (px, py) of an image `width` wide at dimension `dimension`, for
+ * the global sample indices first_index .. first_index + count - 1.  PMJ02BN: `dimension` counts from the sample's start dimension
+ * (pixel.y * width + pixel.y, raygen.rgen.glsl:59) and samplesPerPixel = first_index + count. */
+#define PTC_SAMPLER_HOOK_1D 0x80000000u /* in `flags` of ptc_sampler_points: out_xy holds two consecutive rand1D() draws instead of one rand2D() */
 PTC_API int ptc_sampler_points(ptc_ctx *ctx, uint32_t px, uint32_t py, uint32_t width, uint32_t first_index, uint32_t count,
                                uint32_t dimension, uint32_t flags, float *out_xy);
 

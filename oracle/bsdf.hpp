@@ -78,18 +78,91 @@ inline uint32_t sobolDim1(uint32_t i) {
     }
     return r;
 }
+/* ---- the reference's optional PMJ02BN sampler, include/rng/rng_pmj.glsl:20-107 (pbrt-v4 style) */
+struct PmjTables { /* the two storage buffers of vulkan/resources/VulkanRandom.cpp:40-72 */
+    const float *pmj = nullptr;  /* [PMJ_N_SEQUENCES][PMJ_N_SAMPLES][2] */
+    const float *blue = nullptr; /* [BLUE_NOISE_TEXTURES][BLUE_NOISE_RESOLUTION][BLUE_NOISE_RESOLUTION] */
+};
+static constexpr uint32_t PMJ_N_SEQUENCES = 16, PMJ_N_SAMPLES = 16384, BLUE_NOISE_TEXTURES = 48, BLUE_NOISE_RESOLUTION = 128; /* rng_pmj_defines.glsl, bluenoise_defines.glsl */
+static constexpr uint32_t PMJ_SEED = 2873468793u;
+static constexpr float ONEMINUSEPSILON = 0.999999f; /* include/constants.glsl:2 */
+inline uint64_t mixBits(uint64_t v) { /* rng_pmj.glsl:30-37 */
+    v ^= (v >> 31);
+    v *= 9202493588570546565ull;
+    v ^= (v >> 27);
+    v *= 9357036318526133325ull;
+    v ^= (v >> 33);
+    return v;
+}
+inline uint32_t permutationElement(uint32_t i, uint32_t l, uint32_t p) { /* rng_pmj.glsl:39-69 */
+    uint32_t w = l - 1;
+    w |= w >> 1;
+    w |= w >> 2;
+    w |= w >> 4;
+    w |= w >> 8;
+    w |= w >> 16;
+    do {
+        i ^= p;
+        i *= 0xe170893du;
+        i ^= p >> 16;
+        i ^= (i & w) >> 4;
+        i ^= p >> 8;
+        i *= 0x0929eb3fu;
+        i ^= p >> 23;
+        i ^= (i & w) >> 1;
+        i *= 1u | p >> 27;
+        i *= 0x6935fa69u;
+        i ^= (i & w) >> 11;
+        i *= 0x74dcb303u;
+        i ^= (i & w) >> 2;
+        i *= 0x9e501cc3u;
+        i ^= (i & w) >> 2;
+        i *= 0xc860a3dfu;
+        i &= w;
+        i ^= i >> 5;
+    } while (i >= l);
+    return (i + p) % l;
+}
+inline uint32_t pmjHash(uint32_t px, uint32_t py, uint32_t dimension) { /* rng_pmj.glsl:73-74, 92-94 */
+    return (uint32_t)mixBits(((uint64_t)px << 48) ^ ((uint64_t)py << 32) ^ ((uint64_t)dimension << 16) ^ (uint64_t)PMJ_SEED);
+}
+inline float blueNoise(const PmjTables &t, uint32_t texture, uint32_t px, uint32_t py) { /* include/rng/bluenoise.glsl:1-8: [texture][x][y] */
+    return t.blue[((size_t)(texture % BLUE_NOISE_TEXTURES) * BLUE_NOISE_RESOLUTION + px % BLUE_NOISE_RESOLUTION) * BLUE_NOISE_RESOLUTION + py % BLUE_NOISE_RESOLUTION];
+}
+
 struct Rng {
     uint32_t state;         /* xorshift state, or the next dimension */
     uint32_t pixelSeed = 0; /* low discrepancy only */
     uint32_t index = 0;     /* global sample index */
     bool ld = false;
-    void init(uint32_t px, uint32_t py, uint32_t resx, uint32_t sampleIndex, bool lowDiscrepancy) {
+    /* PMJ02BN (PTC_FLAG_SAMPLER_PMJ): state = dimension, index = sampleIndex */
+    bool pmj = false;
+    uint32_t px = 0, py = 0, spp = 1;
+    PmjTables tables;
+    void init(uint32_t px_, uint32_t py_, uint32_t resx, uint32_t sampleIndex, bool lowDiscrepancy) {
         ld = lowDiscrepancy;
         index = sampleIndex;
-        pixelSeed = jenkinsHash(px * resx + py);
-        state = ld ? 0u : initRNG(px, py, resx, sampleIndex);
+        pixelSeed = jenkinsHash(px_ * resx + py_);
+        state = ld ? 0u : initRNG(px_, py_, resx, sampleIndex);
+    }
+    /* raygen.rgen.glsl:30-33, 41-43, 57-61: per sample the dimension restarts at pixel.y * width + pixel.y (sic) */
+    void initPmj(uint32_t px_, uint32_t py_, uint32_t resx, uint32_t sampleIndex, uint32_t samplesPerPixel, const PmjTables &t) {
+        pmj = true;
+        ld = false;
+        px = px_;
+        py = py_;
+        spp = samplesPerPixel;
+        tables = t;
+        index = sampleIndex;
+        state = py_ * resx + py_;
     }
     float rand1D() {
+        if (pmj) { /* rng_pmj.glsl:71-83 */
+            const uint32_t idx = permutationElement(index, spp, pmjHash(px, py, state));
+            const float delta = blueNoise(tables, state, px, py);
+            state++;
+            return std::min(((float)idx + delta) / (float)spp, ONEMINUSEPSILON);
+        }
         if (ld) {
             uint32_t seed = jenkinsHash(hashCombine(pixelSeed, state));
             state += 1;
@@ -99,6 +172,14 @@ struct Rng {
         return uintToFloat(xorshift(state));
     }
     vec2 rand2D() {
+        if (pmj) { /* rng_pmj.glsl:85-107 (BLUE_NOISE_2D is not defined) */
+            uint32_t idx = index;
+            const uint32_t inst = state / 2u;
+            if (inst >= PMJ_N_SEQUENCES) idx = permutationElement(index, spp, pmjHash(px, py, state));
+            const float *u = tables.pmj + ((size_t)(inst % PMJ_N_SEQUENCES) * PMJ_N_SAMPLES + idx % PMJ_N_SAMPLES) * 2;
+            state += 2u;
+            return {std::min(u[0], ONEMINUSEPSILON), std::min(u[1], ONEMINUSEPSILON)};
+        }
         if (ld) {
             uint32_t seed = jenkinsHash(hashCombine(pixelSeed, state));
             state += 2;

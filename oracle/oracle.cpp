@@ -97,6 +97,7 @@ struct ptc_ctx {
     uint32_t cubeN = 0;
     std::vector<float> cube;
     envdist::Tables envTables; /* PTC_FLAG_ENV_IMPORTANCE */
+    std::vector<float> pmjTable, blueTable; /* ptc_set_sampler_tables (PTC_FLAG_SAMPLER_PMJ) */
     /* accel */
     std::vector<WorldTri> tris;
     std::vector<uint64_t> instFirstTri;
@@ -833,7 +834,10 @@ struct Tracer {
     /* raygen.rgen.glsl:55-129 for one sample of one pixel */
     void samplePixel(uint32_t px, uint32_t py, uint32_t sampleIndex, vec3 &radiance, vec3 &albedo, vec3 &normal) {
         Payload P;
-        P.rng.init(px, py, rp->width, sampleIndex, (rp->flags & PTC_FLAG_SAMPLER_SOBOL) != 0u);
+        if (rp->flags & PTC_FLAG_SAMPLER_PMJ)
+            P.rng.initPmj(px, py, rp->width, sampleIndex, (rp->samples / rp->batch_size) * rp->batch_size, PmjTables{c->pmjTable.data(), c->blueTable.data()});
+        else
+            P.rng.init(px, py, rp->width, sampleIndex, (rp->flags & PTC_FLAG_SAMPLER_SOBOL) != 0u);
         const mat4 projInv = mat4_from(rp->scene.projection_inverse);
         const mat4 viewInv = mat4_from(rp->scene.view_inverse);
         float lensRadius = rp->scene.exposure[2];
@@ -1015,6 +1019,7 @@ PTC_API int ptc_render(ptc_ctx *c, const ptc_render_params *rp, float *radiance,
     if (!c || !rp) return fail(c, "null argument");
     if (!c->accelBuilt) return fail(c, "ptc_build_accel has not been called");
     if (rp->batch_size == 0 || rp->width == 0 || rp->height == 0) return fail(c, "bad render params");
+    if ((rp->flags & PTC_FLAG_SAMPLER_PMJ) && c->pmjTable.empty()) return fail(c, "PTC_FLAG_SAMPLER_PMJ needs ptc_set_sampler_tables");
     const uint32_t W = rp->width, H = rp->height;
     const uint32_t batches = rp->samples / rp->batch_size; /* VulkanRendererPathTracing.cpp:798-799 (T7) */
     const uint32_t totalSamples = batches * rp->batch_size;
@@ -1200,16 +1205,47 @@ PTC_API int ptc_bsdf_sample(ptc_ctx *, int n, const float *params, const float *
     }
     return 0;
 }
-PTC_API int ptc_sampler_points(ptc_ctx *, uint32_t px, uint32_t py, uint32_t width, uint32_t first_index, uint32_t count, uint32_t dimension,
+PTC_API int ptc_set_sampler_tables(ptc_ctx *c, const float *pmj, uint32_t n_sequences, uint32_t n_samples, const float *blue, uint32_t n_textures,
+                                   uint32_t resolution) {
+    if (!c || !pmj || !blue) return fail(c, "null argument");
+    if (n_sequences != PMJ_N_SEQUENCES || n_samples != PMJ_N_SAMPLES || n_textures != BLUE_NOISE_TEXTURES || resolution != BLUE_NOISE_RESOLUTION)
+        return fail(c, "sampler tables must be 16 x 16384 x 2 and 48 x 128 x 128 (rng_pmj_defines.glsl, bluenoise_defines.glsl)");
+    c->pmjTable.assign(pmj, pmj + (size_t)n_sequences * n_samples * 2);
+    c->blueTable.assign(blue, blue + (size_t)n_textures * resolution * resolution);
+    return 0;
+}
+
+PTC_API int ptc_sampler_points(ptc_ctx *c, uint32_t px, uint32_t py, uint32_t width, uint32_t first_index, uint32_t count, uint32_t dimension,
                                uint32_t flags, float *out_xy) {
+    if ((flags & PTC_FLAG_SAMPLER_PMJ) && (!c || c->pmjTable.empty())) return fail(c, "ptc_set_sampler_tables has not been called");
     for (uint32_t i = 0; i < count; i++) {
         Rng r;
+        if (flags & PTC_FLAG_SAMPLER_PMJ) {
+            r.initPmj(px, py, width, first_index + i, first_index + count, PmjTables{c->pmjTable.data(), c->blueTable.data()});
+            r.state += dimension;
+            vec2 p;
+            if (flags & PTC_SAMPLER_HOOK_1D) {
+                p.x = r.rand1D();
+                p.y = r.rand1D();
+            } else {
+                p = r.rand2D();
+            }
+            out_xy[2 * i] = p.x;
+            out_xy[2 * i + 1] = p.y;
+            continue;
+        }
         r.init(px, py, width, first_index + i, (flags & PTC_FLAG_SAMPLER_SOBOL) != 0u);
         if (r.ld)
             r.state = dimension;
         else
             for (uint32_t k = 0; k < dimension; k++) r.rand1D();
-        vec2 p = r.rand2D();
+        vec2 p;
+        if (flags & PTC_SAMPLER_HOOK_1D) {
+            p.x = r.rand1D();
+            p.y = r.rand1D();
+        } else {
+            p = r.rand2D();
+        }
         out_xy[2 * i] = p.x;
         out_xy[2 * i + 1] = p.y;
     }

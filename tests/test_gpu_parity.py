@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from imgmetrics import mean_lum_ratio, mse, p99_rel_err, rgbe_roundtrip
+from imgmetrics import firefly_mask, mean_lum_ratio, mse, mse_masked, p99_rel_err, rgbe_roundtrip
 from test_oracle_units import HIERARCHIES, check_lbvh, check_wide_bvh, look_down_params, make_quad_scene
 from oracle import loader as oracle_loader
 
@@ -245,38 +245,54 @@ def test_render_matches_oracle(capi, engine, scene, sobol):
 
 # ---------------------------------------------------------------- (6) renders: CUDA vs the reference's golden images
 GOLDEN_LIMITS = {"mse": 2e-4, "lum": 0.01, "p99": 0.05}
+GOLDEN_SPP_FACTOR = 8  # "render at >= 8x the golden's spp"
 # low-variance scenes (delta or small lights) must do much better
 TIGHT = {"PointLight": 1e-5, "DirectionalLight": 1e-5, "FurnaceLambert": 5e-6, "SharedComponents": 1e-5}
-# scenes whose golden itself carries fireflies from the point light inside the medium: luminance and structure only
-NOISY_GOLDEN = {"Volume4": 4e-3, "Volume8": 2e-3, "Volume5": 1e-3, "Volume9": 1.5e-3}
+# Goldens that are themselves far from converged at their 2048 spp: a point light / an emissive plane INSIDE a scattering medium
+# (1 / d^2 of lightSampling.glsl:20-31 next to the light).  profiles/r2_golden_fireflies.json: at 8x the samples 69 % (Volume4) and
+# 89 % (Volume8) of the whole squared error sits in 4-5 isolated spike pixels OF THE GOLDEN, and what remains equals the noise a
+# 2048-spp render of this estimator carries (our own 1x render against our own 8x render).  So these four are held to the SAME
+# 2e-4 / 5 % limits after (a) dropping the golden's spike pixels (imgmetrics.firefly_mask) and (b) never asking for less than 1.5x
+# that measured noise floor; the mean luminance must still agree within 1 % (it did not need loosening).
+NOISY_GOLDEN = {"Volume4", "Volume5", "Volume8", "Volume9"}
 
 
 @pytest.mark.parametrize("scene", GOLDEN_SCENES)
 def test_render_matches_reference_golden(capi, engine, scene, tmp_path):
-    """Same recipe as the reference's TEST_F (RenderTests.cpp), rendered through RendererPathTracing::render() at 4x the golden's
+    """Same recipe as the reference's TEST_F (RenderTests.cpp), rendered through RendererPathTracing::render() at 8x the golden's
     samples, compared with assets/unittests/<scene>_ref.hdr after the same RGBE quantisation."""
     engine.build_scene(scene)
     ri = engine.render_info()
-    engine.set_render_info(samples=4 * ri["samples"])
+    engine.set_render_info(samples=GOLDEN_SPP_FACTOR * ri["samples"])
     out = str(tmp_path / (scene + "_test"))
     engine.render(out)  # writes <out>.hdr like the reference
     img = capi.read_hdr(out + ".hdr")
     ref = capi.read_hdr(os.path.join(REF_DIR, scene + "_ref.hdr"))
     # the RGBE writer turns a NaN into a number: the images handed back in memory must be finite too
     assert all(np.isfinite(x).all() for x in engine.render_to_memory()), "non-finite pixel"
-    m, lum, p99 = mse(img, ref), mean_lum_ratio(img, ref), p99_rel_err(img, ref)
-    limit = TIGHT.get(scene, NOISY_GOLDEN.get(scene, GOLDEN_LIMITS["mse"]))
+    lum, p99 = mean_lum_ratio(img, ref), p99_rel_err(img, ref)
+    assert abs(lum - 1) <= GOLDEN_LIMITS["lum"], "mean luminance ratio %.4f" % lum
+    if scene in NOISY_GOLDEN:
+        engine.set_render_info(samples=ri["samples"])
+        own = rgbe_roundtrip(engine.render_to_memory()[0])  # this estimator at the golden's own sample count
+        floor_mse, floor_p99 = mse(own, img), p99_rel_err(own, img)
+        spikes = firefly_mask(ref)
+        assert spikes.sum() <= 16, "the golden's spikes are a handful of pixels, not a region (%d)" % int(spikes.sum())
+        m = mse_masked(img, ref, spikes)
+        assert m <= max(GOLDEN_LIMITS["mse"], 1.5 * floor_mse), "MSE %.3e (noise floor of a %d-spp render: %.3e)" % (m, ri["samples"], floor_mse)
+        assert p99 <= max(GOLDEN_LIMITS["p99"], 1.5 * floor_p99), "p99 rel err %.4f (noise floor %.4f)" % (p99, floor_p99)
+        return
+    m = mse(img, ref)
+    limit = TIGHT.get(scene, GOLDEN_LIMITS["mse"])
     assert m <= limit, "MSE %.3e > %.1e" % (m, limit)
-    assert abs(lum - 1) <= (0.02 if scene in NOISY_GOLDEN else GOLDEN_LIMITS["lum"]), "mean luminance ratio %.4f" % lum
-    if scene not in NOISY_GOLDEN:
-        assert p99 <= GOLDEN_LIMITS["p99"] * (2 if scene in ("Transparency", "NormalMap", "GLTF", "DepthOfField", "EnvironmentMap") else 1), "p99 rel err %.4f" % p99
+    assert p99 <= GOLDEN_LIMITS["p99"] * (2 if scene in ("Transparency", "NormalMap", "GLTF", "DepthOfField", "EnvironmentMap") else 1), "p99 rel err %.4f" % p99
 
 
 def test_denoise_aovs_match_reference(capi, engine, tmp_path):
     """Denoise_ref_{radiance,albedo,normal}.hdr pin the AOV conventions (first-hit albedo, n*0.5+0.5, background albedo = env)."""
     engine.build_scene("Denoise")
     ri = engine.render_info()
-    engine.set_render_info(samples=4 * ri["samples"])
+    engine.set_render_info(samples=GOLDEN_SPP_FACTOR * ri["samples"])
     out = str(tmp_path / "Denoise_test")
     engine.render(out)
     for suffix, lim in (("_radiance", 2e-4), ("_albedo", 2e-4), ("_normal", 5e-5)):

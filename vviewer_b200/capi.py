@@ -81,7 +81,7 @@ class ptc_stats(C.Structure):
                 ("probe_hops", u64), ("render_ms", C.c_double), ("trace_ms", C.c_double), ("shade_ms", C.c_double),
                 ("shadow_ms", C.c_double), ("build_ms", C.c_double), ("trace_launches", u64), ("kernel_launches", u64),
                 ("n_triangles", u64), ("n_bvh_nodes", u64), ("scene_bytes", u64), ("reserved", u64 * 4),
-                ("upload_bytes", u64), ("reduce_ms", C.c_double)]
+                ("upload_bytes", u64), ("reduce_ms", C.c_double), ("bin_ms", C.c_double)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -96,10 +96,11 @@ PTC_FLAG_TIME_KERNELS = 2
 PTC_FLAG_SAMPLER_SOBOL = 4
 PTC_FLAG_ENV_IMPORTANCE = 8
 PTC_FLAG_SAMPLER_PMJ = 16
+PTC_SAMPLER_HOOK_1D = 0x80000000
 PTC_HIERARCHY_LBVH, PTC_HIERARCHY_PLOC = 0, 1
 
 # every symbol include/ptc.h declares
-PTC_SYMBOLS = ["ptc_create", "ptc_destroy", "ptc_device_count", "ptc_comm_unique_id", "ptc_comm_init_rank", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_set_build_options", "ptc_build_accel", "ptc_render",
+PTC_SYMBOLS = ["ptc_set_sampler_tables", "ptc_create", "ptc_destroy", "ptc_device_count", "ptc_comm_unique_id", "ptc_comm_init_rank", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_set_build_options", "ptc_build_accel", "ptc_render",
                "ptc_render_device", "ptc_progress", "ptc_get_stats", "ptc_trace_closest", "ptc_get_lbvh", "ptc_get_wide_bvh", "ptc_bsdf_eval",
                "ptc_bsdf_sample", "ptc_sampler_points", "ptc_env_lookup", "ptc_env_sample", "ptc_env_pdf"]
 VH_SYMBOLS = ["vh_set_sequence_frame", "vh_set_output", "vh_write_image", "vh_set_devices", "vh_device_count", "vh_comm_unique_id", "vh_comm_init_rank", "vh_set_render_options", "vh_engine_create", "vh_engine_destroy", "vh_backend_ok", "vh_last_error", "vh_scene_list", "vh_build_scene",
@@ -119,6 +120,8 @@ def _declare_ptc(lib):
     lib.ptc_destroy.restype = None
     lib.ptc_last_error.argtypes = [vp]
     lib.ptc_last_error.restype = C.c_char_p
+    lib.ptc_set_sampler_tables.argtypes = [vp, vp, u32, u32, vp, u32, u32]
+    lib.ptc_set_sampler_tables.restype = C.c_int
     lib.ptc_device_count.argtypes = [vp]
     lib.ptc_device_count.restype = C.c_int
     lib.ptc_comm_unique_id.argtypes = [vp]
@@ -254,6 +257,14 @@ def load_host():
     return _host
 
 
+def load_sampler_tables(root=None):
+    """assets/tables/pmj02bn.f32 + bluenoise.u16 -> (float32 [16, 16384, 2], float32 [48, 128, 128])"""
+    d = os.path.join(root or ROOT, "assets", "tables")
+    pmj = np.fromfile(os.path.join(d, "pmj02bn.f32"), "<f4").reshape(16, 16384, 2).copy()
+    blue = (np.fromfile(os.path.join(d, "bluenoise.u16"), "<u2").astype(np.float32) / np.float32(65536.0)).reshape(48, 128, 128).copy()
+    return pmj, blue
+
+
 def np_ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -303,6 +314,12 @@ class Context:
     def comm_init_rank(self, id_bytes, rank, world):
         buf = (C.c_uint8 * 128).from_buffer_copy(id_bytes)
         self._check(self.lib.ptc_comm_init_rank(self.ctx, buf, int(rank), int(world)), "ptc_comm_init_rank")
+
+    def set_sampler_tables(self, tables=None):
+        """the PMJ02BN / blue-noise tables (default: assets/tables, extracted from the reference by tools/extract_sampler_tables.py)"""
+        pmj, blue = tables or load_sampler_tables()
+        self._tables = (pmj, blue)
+        self._check(self.lib.ptc_set_sampler_tables(self.ctx, np_ptr(pmj), 16, 16384, np_ptr(blue), 48, 128), "ptc_set_sampler_tables")
 
     def upload_scene(self, desc_ptr):
         self._check(self.lib.ptc_upload_scene(self.ctx, desc_ptr), "ptc_upload_scene")

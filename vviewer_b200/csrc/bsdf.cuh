@@ -38,10 +38,82 @@ PTC_HD uint32_t rngSeed(uint32_t px, uint32_t py, uint32_t width, uint32_t sampl
  * rnd() = rand1D, rnd2() = rand2D of the reference; both modes draw in the same program order. */
 struct Rng {
     uint32_t s;         /* xorshift state, or the next dimension */
-    uint32_t pixelSeed; /* low discrepancy only */
+    uint32_t pixelSeed; /* low discrepancy only; PMJ02BN: pixel.x | pixel.y << 16 */
     uint32_t index;     /* global sample index of the path (batch * batchSize + s) */
-    uint32_t ld;
+    uint32_t ld;        /* 0 xorshift stream, 1 Owen-scrambled Sobol, 2 PMJ02BN (rng_pmj.glsl) */
 };
+
+/* ---- the reference's optional PMJ02BN sampler (include/rng/rng_pmj.glsl:20-107).  The two tables are the reference's storage
+ * buffers (vulkan/resources/VulkanRandom.cpp:40-72), handed over through ptc_set_sampler_tables; one render uses one
+ * samplesPerPixel (raygen.rgen.glsl:30-33), so tables + count sit in constant memory for the kernels of that render. */
+struct PmjConst {
+    const float *pmj;  /* [16][16384][2] */
+    const float *blue; /* [48][128][128] */
+    uint32_t spp;
+};
+__constant__ PmjConst g_pmj;
+#define PMJ_N_SEQUENCES 16u
+#define PMJ_N_SAMPLES 16384u
+#define BLUE_NOISE_TEXTURES 48u
+#define BLUE_NOISE_RESOLUTION 128u
+#define PMJ_SEED 2873468793u
+#define ONEMINUSEPSILON 0.999999f
+PTC_D uint64_t mixBits(uint64_t v) { /* rng_pmj.glsl:30-37 */
+    v ^= (v >> 31);
+    v *= 9202493588570546565ull;
+    v ^= (v >> 27);
+    v *= 9357036318526133325ull;
+    v ^= (v >> 33);
+    return v;
+}
+PTC_D uint32_t permutationElement(uint32_t i, uint32_t l, uint32_t p) { /* rng_pmj.glsl:39-69 */
+    uint32_t w = l - 1u;
+    w |= w >> 1;
+    w |= w >> 2;
+    w |= w >> 4;
+    w |= w >> 8;
+    w |= w >> 16;
+    do {
+        i ^= p;
+        i *= 0xe170893du;
+        i ^= p >> 16;
+        i ^= (i & w) >> 4;
+        i ^= p >> 8;
+        i *= 0x0929eb3fu;
+        i ^= p >> 23;
+        i ^= (i & w) >> 1;
+        i *= 1u | p >> 27;
+        i *= 0x6935fa69u;
+        i ^= (i & w) >> 11;
+        i *= 0x74dcb303u;
+        i ^= (i & w) >> 2;
+        i *= 0x9e501cc3u;
+        i ^= (i & w) >> 2;
+        i *= 0xc860a3dfu;
+        i &= w;
+        i ^= i >> 5;
+    } while (i >= l);
+    return (i + p) % l;
+}
+PTC_D uint32_t pmjHash(uint32_t px, uint32_t py, uint32_t dimension) { /* rng_pmj.glsl:73-74, 92-94 */
+    return (uint32_t)mixBits(((uint64_t)px << 48) ^ ((uint64_t)py << 32) ^ ((uint64_t)dimension << 16) ^ (uint64_t)PMJ_SEED);
+}
+PTC_D float pmjRand1D(Rng &r) { /* rng_pmj.glsl:71-83 */
+    const uint32_t px = r.pixelSeed & 0xffffu, py = r.pixelSeed >> 16;
+    const uint32_t idx = permutationElement(r.index, g_pmj.spp, pmjHash(px, py, r.s));
+    /* include/rng/bluenoise.glsl:1-8: data[texture][pixel.x][pixel.y] */
+    const float delta = __ldg(g_pmj.blue + ((size_t)(r.s % BLUE_NOISE_TEXTURES) * BLUE_NOISE_RESOLUTION + px % BLUE_NOISE_RESOLUTION) * BLUE_NOISE_RESOLUTION + py % BLUE_NOISE_RESOLUTION);
+    r.s += 1u;
+    return fminf(__fdiv_rn(__fadd_rn((float)idx, delta), (float)g_pmj.spp), ONEMINUSEPSILON);
+}
+PTC_D float2 pmjRand2D(Rng &r) { /* rng_pmj.glsl:85-107 (BLUE_NOISE_2D is not defined) */
+    uint32_t idx = r.index;
+    const uint32_t inst = r.s / 2u;
+    if (inst >= PMJ_N_SEQUENCES) idx = permutationElement(r.index, g_pmj.spp, pmjHash(r.pixelSeed & 0xffffu, r.pixelSeed >> 16, r.s));
+    const float2 u = __ldg((const float2 *)g_pmj.pmj + (size_t)(inst % PMJ_N_SEQUENCES) * PMJ_N_SAMPLES + idx % PMJ_N_SAMPLES);
+    r.s += 2u;
+    return make_float2(fminf(u.x, ONEMINUSEPSILON), fminf(u.y, ONEMINUSEPSILON));
+}
 PTC_HD uint32_t hashCombine(uint32_t seed, uint32_t v) { return seed ^ (v + (seed << 6) + (seed >> 2)); }
 PTC_HD uint32_t reverseBits32(uint32_t x) {
 #ifdef __CUDA_ARCH__
@@ -81,15 +153,29 @@ PTC_HD float bitsToUnitFloat(uint32_t x) {
     return f - 1.0f;
 #endif
 }
-PTC_D Rng rngInit(uint32_t px, uint32_t py, uint32_t width, uint32_t sampleIndex, bool lowDiscrepancy) {
+/* sampler: 0 default xorshift stream, 1 Sobol, 2 PMJ02BN */
+PTC_D uint32_t samplerOfFlags(uint32_t flags) { return (flags & PTC_FLAG_SAMPLER_PMJ) ? 2u : ((flags & PTC_FLAG_SAMPLER_SOBOL) ? 1u : 0u); }
+PTC_D Rng rngInit(uint32_t px, uint32_t py, uint32_t width, uint32_t sampleIndex, uint32_t sampler) {
     Rng r;
-    r.ld = lowDiscrepancy ? 1u : 0u;
+    r.ld = sampler;
     r.index = sampleIndex;
+    if (sampler == 2u) { /* raygen.rgen.glsl:57-61: every sample starts at dimension pixel.y * width + pixel.y (sic) */
+        r.pixelSeed = (px & 0xffffu) | (py << 16);
+        r.s = py * width + py;
+        return r;
+    }
     r.pixelSeed = jenkins(px * width + py);
-    r.s = lowDiscrepancy ? 0u : rngSeed(px, py, width, sampleIndex);
+    r.s = sampler ? 0u : rngSeed(px, py, width, sampleIndex);
     return r;
 }
+/* the per-path part of the state that is not stored in the slot (everything but `s`) is a function of (pixel, sample index) */
+PTC_D void rngRestore(Rng &r, uint32_t sampler, uint32_t px, uint32_t py, uint32_t width, uint32_t sampleIndex) {
+    r.ld = sampler;
+    r.index = sampleIndex;
+    r.pixelSeed = sampler == 2u ? ((px & 0xffffu) | (py << 16)) : (sampler == 1u ? jenkins(px * width + py) : 0u);
+}
 PTC_D float rnd(Rng &r) {
+    if (r.ld == 2u) return pmjRand1D(r);
     if (r.ld) {
         const uint32_t seed = jenkins(hashCombine(r.pixelSeed, r.s));
         r.s += 1u;
@@ -102,6 +188,7 @@ PTC_D float rnd(Rng &r) {
     return __uint_as_float(0x3f800000u | (r.s >> 9)) - 1.0f;
 }
 PTC_D float2 rnd2(Rng &r) {
+    if (r.ld == 2u) return pmjRand2D(r);
     if (r.ld) {
         const uint32_t seed = jenkins(hashCombine(r.pixelSeed, r.s));
         r.s += 2u;

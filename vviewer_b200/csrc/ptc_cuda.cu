@@ -59,6 +59,7 @@ struct Dev {
     cudaTextureObject_t cubeTex = 0;
     uint32_t cubeN = 0;
     DBuf<float> envCdfV, envCdfU; /* PTC_FLAG_ENV_IMPORTANCE tables, valid while cubeTex is */
+    DBuf<float> pmjTable, blueTable; /* ptc_set_sampler_tables (PTC_FLAG_SAMPLER_PMJ) */
     DBuf<float4> emissiveBoxes;   /* DScene::emissiveBoxes */
     uint32_t nEmissiveBoxes = 0;
     uint32_t nInstances = 0, nMaterials = 0, nLightInstances = 0, nTextures = 0, nWorldTris = 0;
@@ -72,6 +73,7 @@ struct Dev {
     struct WaveBufs {
         DBuf<float4> orgRng, dirFlags, beta, radiance, hit, aovA, aovN, shOrg, shDir, shContrib, prBeta;
         DBuf<uint32_t> queue0, queue1, qShadow, qProbe, counters;
+        DBuf<uint16_t> qKey;
         DBuf<unsigned long long> stats;
         size_t capacity = 0;
     } wave[2];
@@ -89,6 +91,9 @@ struct Dev {
      * 2069 Mseg/s alone (profiles/r1_v4_kernel_experiments.log) - k_shade needs >= 3 blocks per SM to keep DRAM busy and k_extend
      * loses as much with 4 as the overlap wins.  PTC_OVERLAP=t,s / PTC_OVERLAP=0 for experiments. */
     int overlapTrace = 64, overlapShade = 64;
+    uint32_t binMode = 0;   /* PTC_BIN: ray binning between bounces (wf::k_bin_window) */
+    uint32_t tileOrder = 0; /* PTC_TILE_ORDER: tile edge of the single-rank pixel walk, 0 = row major */
+    float sceneLo[3] = {0, 0, 0}, sceneHi[3] = {0, 0, 0}; /* world box of the scene (from the build) */
 
     std::atomic<float> progress{0.0f};
     ptc_stats stats{};
@@ -365,6 +370,7 @@ void ensureWave(Dev *c, int k, size_t slots, uint32_t depth) {
         w.queue1.alloc(slots);
         w.qShadow.alloc(slots);
         w.qProbe.alloc(slots);
+        w.qKey.alloc(slots);
         w.capacity = slots;
     }
     w.counters.alloc((size_t)(depth + 2) * wf::CNT_STRIDE);
@@ -389,6 +395,7 @@ wf::Wave makeWave(Dev *c, int k) {
     w.queue[1] = b.queue1.p;
     w.qShadow = b.qShadow.p;
     w.qProbe = b.qProbe.p;
+    w.qKey = b.qKey.p;
     w.counters = b.counters.p;
     w.stats = b.stats.p;
     return w;
@@ -409,13 +416,19 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
      * until the partition changes. */
     uint32_t nPixLocal = (uint32_t)nPix;
     const uint32_t *pixmapPtr = nullptr;
-    if (rp->split_mode == PTC_SPLIT_TILE && world > 1) {
-        const uint32_t key[5] = {W, H, tile, rp->rank, world};
+    /* a single rank walks the image in small tiles too (PTC_TILE_ORDER = tile edge, 0 = row major): the 32 camera rays of a warp and the
+     * entries of a queue window then cover a compact screen area */
+    const bool tileSplit = rp->split_mode == PTC_SPLIT_TILE && world > 1;
+    const uint32_t orderTile = tileSplit ? 0u : c->tileOrder;
+    if (tileSplit || orderTile > 0u) {
+        const uint32_t tile = tileSplit ? (rp->tile_size ? rp->tile_size : 32u) : orderTile;
+        const uint32_t world = tileSplit ? (rp->world ? rp->world : 1u) : 1u;
+        const uint32_t key[5] = {W, H, tile, tileSplit ? rp->rank : 0u, world};
         if (memcmp(key, c->pixmapKey, sizeof(key)) != 0 || !c->pixmap.p) {
             const uint32_t tilesX = (W + tile - 1) / tile, tilesY = (H + tile - 1) / tile, nTiles = tilesX * tilesY;
             std::vector<uint32_t> offsets;
             uint32_t total = 0;
-            for (uint32_t t = rp->rank; t < nTiles; t += world) {
+            for (uint32_t t = key[3]; t < nTiles; t += world) {
                 const uint32_t tx = t % tilesX, ty = t / tilesX;
                 offsets.push_back(total);
                 total += std::min(tile, W - tx * tile) * std::min(tile, H - ty * tile);
@@ -424,7 +437,7 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
             c->tileOffsets.upload(offsets.data(), offsets.size(), s);
             c->pixmap.alloc(std::max<size_t>(total, 1));
             const uint32_t nLocalTiles = (uint32_t)offsets.size() - 1u;
-            if (nLocalTiles) wf::k_tile_pixmap<<<nLocalTiles, 256, 0, s>>>(W, H, tile, rp->rank, world, c->tileOffsets.p, c->pixmap.p);
+            if (nLocalTiles) wf::k_tile_pixmap<<<nLocalTiles, 256, 0, s>>>(W, H, tile, key[3], world, c->tileOffsets.p, c->pixmap.p);
             CUDA_TRY(cudaStreamSynchronize(s)); /* the host vector dies here */
             memcpy(c->pixmapKey, key, sizeof(key));
             c->pixmapCount = total;
@@ -461,6 +474,12 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
         CUDA_TRY(cudaMemsetAsync(c->wave[k].stats.p, 0, wf::ST_COUNT * sizeof(unsigned long long), s));
     }
 
+    if (rp->flags & PTC_FLAG_SAMPLER_PMJ) {
+        if (!c->pmjTable.p || !c->blueTable.p) throw CudaError{"PTC_FLAG_SAMPLER_PMJ needs ptc_set_sampler_tables"};
+        if (W > 65535u || H > 65535u) throw CudaError{"the PMJ02BN sampler packs pixel coordinates into 16 bits"};
+        const PmjConst pc{c->pmjTable.p, c->blueTable.p, totalSamples};
+        CUDA_TRY(cudaMemcpyToSymbolAsync(g_pmj, &pc, sizeof(pc), 0, cudaMemcpyHostToDevice, s));
+    }
     wf::RenderConst rc{};
     rc.sd = rp->scene;
     rc.width = W;
@@ -476,6 +495,12 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
     rc.flags = rp->flags;
     rc.nPixLocal = nPixLocal;
     rc.pixmap = pixmapPtr;
+    rc.binMode = c->accel.n > 0 ? c->binMode : 0u;
+    for (int a = 0; a < 3; a++) {
+        rc.binLo[a] = c->sceneLo[a];
+        const float ext = c->sceneHi[a] - c->sceneLo[a];
+        rc.binScale[a] = ext > 0.0f ? 8.0f / ext : 0.0f;
+    }
     DScene sc = makeDScene(c);
 
     /* persistent kernels: exactly as many blocks as are resident at once (multiples of the SM count) */
@@ -502,7 +527,15 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
     const int gridShadow = residentGrid((const void *)shadowFn, TRV_BLOCK, capTrace);
     const int gridProbe = residentGrid((const void *)wf::k_probe, TRV_BLOCK, capTrace);
     uint64_t launches = 0, traceLaunches = 0;
-    double traceMs = 0, shadeMs = 0, shadowMs = 0;
+    double traceMs = 0, shadeMs = 0, shadowMs = 0, binMs = 0;
+    const size_t binSmemBytes = ((size_t)(1u << BIN_KEY_BITS) + BIN_WINDOW) * 4 + (size_t)BIN_WINDOW * 2;
+    int gridBin = c->smCount;
+    if (rc.binMode != 0u) {
+        CUDA_TRY(cudaFuncSetAttribute((const void *)wf::k_bin_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)binSmemBytes));
+        int perSm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (const void *)wf::k_bin_window, BIN_THREADS, binSmemBytes) != cudaSuccess || perSm < 1) perSm = 1;
+        gridBin = c->smCount * perSm;
+    }
     auto timed = [&](double &acc, cudaStream_t st, auto &&launch) {
         if (timeKernels) CUDA_TRY(cudaEventRecord(c->evA, st));
         launch();
@@ -559,6 +592,12 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
                         timed(shadowMs, st, [&] { wf::k_probe<<<gridProbe, TRV_BLOCK, 0, st>>>(w, sc, rc, d, c->tune); });
                         launches++;
                     }
+                    if (rc.binMode != 0u && d + 1 < rp->depth) { /* regroup the survivors before they are traced */
+                        timed(binMs, st, [&] {
+                            wf::k_bin_window<<<gridBin, BIN_THREADS, binSmemBytes, st>>>(w.queue[(d + 1) & 1u], w.qKey, &w.counters[(d + 1) * wf::CNT_STRIDE + wf::CNT_ACTIVE]);
+                        });
+                        launches++;
+                    }
                 }
                 wf::k_collect_stats<<<1, 32, 0, st>>>(w, rp->depth);
                 /* accumulate in item order: item i adds after item i - 1 (which ran on the other stream) */
@@ -599,6 +638,7 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
     c->stats.trace_ms = traceMs;
     c->stats.shade_ms = shadeMs;
     c->stats.shadow_ms = shadowMs;
+    c->stats.bin_ms = binMs;
     c->stats.trace_launches = traceLaunches;
     c->stats.kernel_launches = launches;
     c->progress = 1.0f;
@@ -982,6 +1022,7 @@ bool renderAll(ptc_ctx *ctx, const ptc_render_params *rp, void *const dOut[3], f
         st.probe_rays += x.probe_rays, st.probe_hops += x.probe_hops, st.trace_launches += x.trace_launches, st.kernel_launches += x.kernel_launches;
         st.render_ms = std::max(st.render_ms, x.render_ms), st.trace_ms = std::max(st.trace_ms, x.trace_ms);
         st.shade_ms = std::max(st.shade_ms, x.shade_ms), st.shadow_ms = std::max(st.shadow_ms, x.shadow_ms);
+        st.bin_ms = std::max(st.bin_ms, x.bin_ms);
         st.build_ms = std::max(st.build_ms, x.build_ms);
         for (int k = 0; k < 4; k++) st.reserved[k] += x.reserved[k];
     }
@@ -1046,6 +1087,8 @@ static void createDev(Dev *c, int device) {
         unsigned a, b, d, e;
         if (sscanf(t, "%u,%u,%u,%u", &a, &b, &d, &e) == 4) c->tune = wf::ExtendTune{a, b, d, e};
     }
+    if (const char *b = getenv("PTC_BIN")) c->binMode = (uint32_t)std::min(2, std::max(0, atoi(b)));
+    if (const char *t = getenv("PTC_TILE_ORDER")) c->tileOrder = (uint32_t)std::min(64, std::max(0, atoi(t)));
     if (const char *o = getenv("PTC_OVERLAP")) { /* "traceBlocksPerSM,shadeBlocksPerSM"; "0" = one wavefront at a time */
         int a = 0, b = 0;
         const int got = sscanf(o, "%d,%d", &a, &b);
@@ -1151,6 +1194,23 @@ PTC_API int ptc_upload_scene(ptc_ctx *ctx, const ptc_scene_desc *sd) {
     PTC_GUARD_END(ctx)
 }
 
+/* replaces VulkanRandom::createBuffers (vulkan/resources/VulkanRandom.cpp:40-72): the two sampler tables as device arrays */
+PTC_API int ptc_set_sampler_tables(ptc_ctx *ctx, const float *pmj, uint32_t n_sequences, uint32_t n_samples, const float *blue, uint32_t n_textures,
+                                   uint32_t resolution) {
+    if (!ctx || !pmj || !blue) return fail(ctx, "null argument");
+    if (ctx->devs.empty()) return fail(ctx, "context has no CUDA device");
+    if (n_sequences != PMJ_N_SEQUENCES || n_samples != PMJ_N_SAMPLES || n_textures != BLUE_NOISE_TEXTURES || resolution != BLUE_NOISE_RESOLUTION)
+        return fail(ctx, "sampler tables must be 16 x 16384 x 2 and 48 x 128 x 128 (rng_pmj_defines.glsl, bluenoise_defines.glsl)");
+    PTC_GUARD_BEGIN
+    forEachDev(ctx, [&](Dev *c, uint32_t) {
+        c->pmjTable.upload(pmj, (size_t)n_sequences * n_samples * 2, c->stream);
+        c->blueTable.upload(blue, (size_t)n_textures * resolution * resolution, c->stream);
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    });
+    return 0;
+    PTC_GUARD_END(ctx)
+}
+
 PTC_API int ptc_set_build_options(ptc_ctx *ctx, uint32_t hierarchy, uint32_t ploc_radius) {
     if (!ctx) return 1;
     if (hierarchy != PTC_HIERARCHY_LBVH && hierarchy != PTC_HIERARCHY_PLOC) return fail(ctx, "unknown hierarchy");
@@ -1178,6 +1238,11 @@ PTC_API int ptc_build_accel(ptc_ctx *ctx) {
         float ms = 0;
         CUDA_TRY(cudaEventElapsedTime(&ms, c->evA, c->evB));
         c->accelBuilt = true;
+        if (c->accel.n > 0) {
+            uint32_t sb[6];
+            CUDA_TRY(cudaMemcpy(sb, c->accel.sceneBounds.p, sizeof(sb), cudaMemcpyDeviceToHost));
+            for (int a = 0; a < 3; a++) c->sceneLo[a] = lbvh::floatUnflip(sb[a]), c->sceneHi[a] = lbvh::floatUnflip(sb[3 + a]);
+        }
         setTraversalWindow(c);
         c->stats.build_ms = ms;
         c->stats.n_triangles = c->nWorldTris;
@@ -1349,6 +1414,11 @@ PTC_API int ptc_sampler_points(ptc_ctx *ctx, uint32_t px, uint32_t py, uint32_t 
     if (!out_xy) return fail(ctx, "null argument");
     PTC_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
+    if (flags & PTC_FLAG_SAMPLER_PMJ) {
+        if (!c->pmjTable.p || !c->blueTable.p) return fail(ctx, "ptc_set_sampler_tables has not been called");
+        const PmjConst pc{c->pmjTable.p, c->blueTable.p, first_index + count};
+        CUDA_TRY(cudaMemcpyToSymbolAsync(g_pmj, &pc, sizeof(pc), 0, cudaMemcpyHostToDevice, c->stream));
+    }
     DBuf<float> dO;
     dO.alloc((size_t)count * 2);
     wf::k_sampler_points<<<(count + 255) / 256, 256, 0, c->stream>>>(px, py, width, first_index, count, dimension, flags, dO.p);

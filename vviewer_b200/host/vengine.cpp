@@ -612,6 +612,7 @@ bool PtcBackend::load(const std::string &libPath, std::string *err) {
     PTC_SYM(device_count, ptc_device_count)
     PTC_SYM(comm_unique_id, ptc_comm_unique_id)
     PTC_SYM(comm_init_rank, ptc_comm_init_rank)
+    PTC_SYM(set_sampler_tables, ptc_set_sampler_tables)
 #undef PTC_SYM
     return true;
 }
@@ -646,6 +647,7 @@ bool CudaRendererPathTracing::setDevices(const std::vector<int> &deviceIds) {
     }
     if (m_ctx) m_backend.destroy(m_ctx);
     m_ctx = fresh;
+    m_samplerTablesSet = false;
     m_commRank = 0;
     m_commWorld = 1;
     m_isInitialized = true;
@@ -663,6 +665,44 @@ bool CudaRendererPathTracing::commInitRank(const uint8_t id128[128], int rank, i
     }
     m_commRank = rank;
     m_commWorld = world;
+    return true;
+}
+
+/* VulkanRandom::initResources / createBuffers (vulkan/resources/VulkanRandom.cpp:15-72): the PMJ02BN sequences and the blue-noise
+ * textures as device tables.  The numbers are the reference's (math/PMJSequences.cpp, math/BlueNoise.cpp), kept as binary files under
+ * assets/tables (tools/extract_sampler_tables.py); they are only loaded when the PMJ sampler is asked for. */
+bool CudaRendererPathTracing::ensureSamplerTables() {
+    if (m_samplerTablesSet) return true;
+    auto readAll = [](const std::string &path, std::vector<uint8_t> &out) {
+        FILE *f = std::fopen(path.c_str(), "rb");
+        if (!f) return false;
+        std::fseek(f, 0, SEEK_END);
+        const long n = std::ftell(f);
+        std::fseek(f, 0, SEEK_SET);
+        if (n < 0) {
+            std::fclose(f);
+            return false;
+        }
+        out.resize((size_t)n);
+        const bool ok = std::fread(out.data(), 1, out.size(), f) == out.size();
+        std::fclose(f);
+        return ok;
+    };
+    std::vector<uint8_t> pmjBytes, blueBytes;
+    const size_t nPmj = (size_t)16 * 16384 * 2, nBlue = (size_t)48 * 128 * 128;
+    if (!readAll(m_engine.assetPath("assets/tables/pmj02bn.f32"), pmjBytes) || pmjBytes.size() != nPmj * 4 ||
+        !readAll(m_engine.assetPath("assets/tables/bluenoise.u16"), blueBytes) || blueBytes.size() != nBlue * 2) {
+        m_error = "PMJ02BN sampler tables not found under assets/tables (tools/extract_sampler_tables.py writes them)";
+        return false;
+    }
+    std::vector<float> pmj(nPmj), blue(nBlue);
+    std::memcpy(pmj.data(), pmjBytes.data(), nPmj * 4);
+    for (size_t i = 0; i < nBlue; i++) blue[i] = (float)((uint32_t)blueBytes[2 * i] | ((uint32_t)blueBytes[2 * i + 1] << 8)) / 65536.0f;
+    if (m_backend.set_sampler_tables(m_ctx, pmj.data(), 16, 16384, blue.data(), 48, 128) != 0) {
+        m_error = m_backend.last_error(m_ctx);
+        return false;
+    }
+    m_samplerTablesSet = true;
     return true;
 }
 
@@ -737,7 +777,7 @@ bool CudaRendererPathTracing::renderToBuffers(float *radiance, float *albedo, fl
         return false;
     }
     m_renderInProgress = true;
-    bool ok = false;
+    bool ok = false, tablesFailed = false;
     const bool verbose = std::getenv("PTC_VERBOSE") != nullptr;
     auto tick = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) {
@@ -750,6 +790,10 @@ bool CudaRendererPathTracing::renderToBuffers(float *radiance, float *albedo, fl
         m_engine.flatten(flat);
         lap("flatten");
         ptc_render_params rp = makeRenderParams();
+        if ((rp.flags & PTC_FLAG_SAMPLER_PMJ) && !ensureSamplerTables()) {
+            tablesFailed = true;
+            break;
+        }
         if (m_backend.upload_scene(m_ctx, &flat.desc) != 0) break;
         lap("upload");
         if (m_backend.build_accel(m_ctx) != 0) break;
@@ -760,7 +804,7 @@ bool CudaRendererPathTracing::renderToBuffers(float *radiance, float *albedo, fl
         ok = true;
     } while (false);
     if (!ok) {
-        m_error = m_backend.last_error(m_ctx);
+        if (!tablesFailed) m_error = m_backend.last_error(m_ctx);
         std::fprintf(stderr, "CudaRendererPathTracing::render(): %s\n", m_error.c_str());
     }
     m_renderInProgress = false;

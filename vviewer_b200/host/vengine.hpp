@@ -731,6 +731,7 @@ struct PtcBackend {
     decltype(&ptc_device_count) device_count = nullptr;
     decltype(&ptc_comm_unique_id) comm_unique_id = nullptr;
     decltype(&ptc_comm_init_rank) comm_init_rank = nullptr;
+    decltype(&ptc_set_sampler_tables) set_sampler_tables = nullptr;
     bool load(const std::string &libPath, std::string *err);
 };
 
@@ -768,6 +769,8 @@ private:
     bool m_isInitialized = false;
     bool m_renderInProgress = false;
     int m_commRank = 0, m_commWorld = 1;
+    bool m_samplerTablesSet = false; /* VulkanRandom's two tables were handed to the current context */
+    bool ensureSamplerTables();
     ptc_stats m_stats{};
     std::string m_error;
 };
