@@ -42,7 +42,7 @@ $(LIBDIR)/libptc_cuda_stats.so: $(CUDA_SRCS) $(CUDA_HDRS)
 
 # -ffp-contract=off: the world-space flatten and the LBVH reference build must round exactly like the
 # device kernels, which use explicit __fmul_rn/__fadd_rn
-$(ORCDIR)/liboracle.so: oracle/oracle.cpp oracle/omath.hpp oracle/bsdf.hpp oracle/accel.hpp include/ptc.h
+$(ORCDIR)/liboracle.so: oracle/oracle.cpp oracle/omath.hpp oracle/bsdf.hpp oracle/accel.hpp oracle/envdist.hpp oracle/srgb_table.h include/ptc.h
 	@mkdir -p $(ORCDIR)
 	$(CXX) -O3 -std=c++17 -fPIC -fvisibility=hidden -ffp-contract=off -fopenmp -Wall -Iinclude -shared -o $@ oracle/oracle.cpp
 

@@ -300,6 +300,12 @@ PTC_API int ptc_bsdf_sample(ptc_ctx *ctx, int n, const float *params, const floa
 PTC_API int ptc_sampler_points(ptc_ctx *ctx, uint32_t px, uint32_t py, uint32_t width, uint32_t first_index, uint32_t count,
                                uint32_t dimension, uint32_t flags, float *out_xy);
 
+/* sRGB decode parity hook: out256[i] = what a texture fetch returns for the 8-bit sRGB code i (VK_FORMAT_R8G8B8A8_SRGB texels are
+ * decoded before filtering, VulkanUtils.cpp:535-554).  Texture units do this with a fixed table whose entries differ from the
+ * analytic curve by up to 1.2e-3 relative; the oracle carries a copy of the table (oracle/srgb_table.h), this hook is how it was
+ * read and how tests/test_gpu_parity.py keeps the copy honest. */
+PTC_API int ptc_srgb_table(ptc_ctx *ctx, float *out256);
+
 /* Environment lookup parity hook: n directions (xyz) -> rgb of the backend's cubemap at LOD 0. */
 PTC_API int ptc_env_lookup(ptc_ctx *ctx, int n, const float *dirs, float *out_rgb);
 

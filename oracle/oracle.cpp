@@ -77,7 +77,7 @@ mat4 inverseAffine(const mat4 &M) {
     return R;
 }
 
-float srgbToLinear(float c) { return c <= 0.04045f ? c / 12.92f : std::pow((c + 0.055f) / 1.055f, 2.4f); }
+#include "srgb_table.h" /* kSrgbToLinear: the texture unit's decode table (hardware-defined) */
 
 }  // namespace
 
@@ -971,7 +971,7 @@ PTC_API int ptc_upload_scene(ptc_ctx *c, const ptc_scene_desc *s) {
             float v[4] = {0, 0, 0, 1};
             for (uint32_t k = 0; k < in.channels; k++) {
                 float f = in.data[p * in.channels + k] / 255.0f;
-                if (in.srgb && k < 3) f = srgbToLinear(f);
+                if (in.srgb && k < 3) f = kSrgbToLinear[in.data[p * in.channels + k]]; /* VK_FORMAT_R8G8B8A8_SRGB: decoded before filtering */
                 v[k] = f;
             }
             for (int k = 0; k < 4; k++) T.px[p * 4 + k] = v[k];
@@ -1249,6 +1249,12 @@ PTC_API int ptc_sampler_points(ptc_ctx *c, uint32_t px, uint32_t py, uint32_t wi
         out_xy[2 * i] = p.x;
         out_xy[2 * i + 1] = p.y;
     }
+    return 0;
+}
+
+PTC_API int ptc_srgb_table(ptc_ctx *, float *out256) {
+    if (!out256) return 1;
+    for (int i = 0; i < 256; i++) out256[i] = kSrgbToLinear[i];
     return 0;
 }
 

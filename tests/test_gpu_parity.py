@@ -199,6 +199,21 @@ def test_env_lookup_parity(capi, engine):
     orc.close()
 
 
+def test_srgb_table_is_the_hardware_s(capi):
+    """sRGB texels are decoded by the texture unit with a fixed table (hardware-defined) that differs from the analytic
+    curve by up to 5e-3 relative; the oracle carries a copy (oracle/srgb_table.h, read through this hook): it must be what the
+    device does, bit for bit, and stay a plausible sRGB curve"""
+    cu, orc = capi.Context(capi.load_cuda()), capi.Context(oracle_loader.load_oracle())
+    a, b = cu.srgb_table(), orc.srgb_table()
+    assert np.array_equal(a, b)
+    c = np.arange(256) / 255.0
+    analytic = np.where(c <= 0.04045, c / 12.92, ((c + 0.055) / 1.055) ** 2.4)
+    assert a[0] == 0.0 and a[255] == 1.0 and np.all(np.diff(a) > 0)
+    assert np.max(np.abs(a - analytic) / np.maximum(analytic, 1e-3)) < 1e-2
+    cu.close()
+    orc.close()
+
+
 # ---------------------------------------------------------------- (5) renders: CUDA vs oracle at matched samples (same RNG streams)
 def test_sampler_points_bit_exact(capi):
     """Both samplers (default xorshift stream, shuffled Owen-scrambled Sobol) are integer arithmetic: identical on both sides."""

@@ -100,7 +100,7 @@ PTC_SAMPLER_HOOK_1D = 0x80000000
 PTC_HIERARCHY_LBVH, PTC_HIERARCHY_PLOC = 0, 1
 
 # every symbol include/ptc.h declares
-PTC_SYMBOLS = ["ptc_set_sampler_tables", "ptc_create", "ptc_destroy", "ptc_device_count", "ptc_comm_unique_id", "ptc_comm_init_rank", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_set_build_options", "ptc_build_accel", "ptc_render",
+PTC_SYMBOLS = ["ptc_srgb_table", "ptc_set_sampler_tables", "ptc_create", "ptc_destroy", "ptc_device_count", "ptc_comm_unique_id", "ptc_comm_init_rank", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_set_build_options", "ptc_build_accel", "ptc_render",
                "ptc_render_device", "ptc_progress", "ptc_get_stats", "ptc_trace_closest", "ptc_get_lbvh", "ptc_get_wide_bvh", "ptc_bsdf_eval",
                "ptc_bsdf_sample", "ptc_sampler_points", "ptc_env_lookup", "ptc_env_sample", "ptc_env_pdf"]
 VH_SYMBOLS = ["vh_set_sequence_frame", "vh_set_output", "vh_write_image", "vh_set_devices", "vh_device_count", "vh_comm_unique_id", "vh_comm_init_rank", "vh_set_render_options", "vh_engine_create", "vh_engine_destroy", "vh_backend_ok", "vh_last_error", "vh_scene_list", "vh_build_scene",
@@ -120,6 +120,8 @@ def _declare_ptc(lib):
     lib.ptc_destroy.restype = None
     lib.ptc_last_error.argtypes = [vp]
     lib.ptc_last_error.restype = C.c_char_p
+    lib.ptc_srgb_table.argtypes = [vp, vp]
+    lib.ptc_srgb_table.restype = C.c_int
     lib.ptc_set_sampler_tables.argtypes = [vp, vp, u32, u32, vp, u32, u32]
     lib.ptc_set_sampler_tables.restype = C.c_int
     lib.ptc_device_count.argtypes = [vp]
@@ -320,6 +322,11 @@ class Context:
         pmj, blue = tables or load_sampler_tables()
         self._tables = (pmj, blue)
         self._check(self.lib.ptc_set_sampler_tables(self.ctx, np_ptr(pmj), 16, 16384, np_ptr(blue), 48, 128), "ptc_set_sampler_tables")
+
+    def srgb_table(self):
+        out = np.zeros(256, np.float32)
+        self._check(self.lib.ptc_srgb_table(self.ctx, np_ptr(out)), "ptc_srgb_table")
+        return out
 
     def upload_scene(self, desc_ptr):
         self._check(self.lib.ptc_upload_scene(self.ctx, desc_ptr), "ptc_upload_scene")

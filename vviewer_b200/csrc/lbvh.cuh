@@ -8,7 +8,7 @@
  *   k_flatten   instance x primitive -> world triangle (v0, e1, e2) + bounds      [__f*_rn: no FMA contraction]
  *   k_bounds    scene AABB (order-preserving uint atomics: exact, order independent)
  *   k_morton    30-bit (<= 65 536 triangles) or 63-bit Morton code of the bounds centre
- *   radix sort  stable LSD sort of (code, triangle id) pairs
+ *   radix sort  stable LSD sort of (code, triangle id) pairs (radix.cuh: hand written, 8-bit digits)
  *   hierarchy   (a) PTC_HIERARCHY_LBVH: k_karras (Karras 2012, ties broken by sorted index) + k_fit (bottom-up AABB fit
  *               with per-node arrival counters);  (b) PTC_HIERARCHY_PLOC (default): parallel locally-ordered clustering
  *               over the same Morton order (Meister & Bittner 2018): every round each cluster finds the neighbour within
@@ -21,13 +21,17 @@
  *               deterministic (breadth first); layout after Ylitie, Karras, Laine 2017
  *   k_gather    triangles in wide-node order
  *
+ * The PLOC rounds and the collapse levels are data dependent loops (about 50 rounds / 10 levels): each runs inside ONE cooperative
+ * kernel that keeps its counts on the device and separates its phases with grid-wide barriers, so the whole build needs two host
+ * round trips (the node bound before the collapse buffers are sized, the final node count) instead of one per round and level.
+ *
  * Every step is bit-exact against the CPU reference build in oracle/accel.hpp
  * (tests/test_gpu_parity.py::test_lbvh_bit_exact, ::test_wide_bvh_bit_exact).
  */
 #pragma once
 #include "common.cuh"
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
+#include "radix.cuh"
+#include <cooperative_groups.h>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -272,79 +276,177 @@ __global__ void k_ploc_init(uint32_t n, const uint32_t *__restrict__ order, cons
 
 #define PLOC_BLOCK 256
 #define PLOC_MAX_RADIUS 32
-__global__ void __launch_bounds__(PLOC_BLOCK) k_ploc_nn(uint32_t c, int radius, const float4 *__restrict__ cLo, const float4 *__restrict__ cHi,
-                                                        uint32_t *__restrict__ nn) {
-    __shared__ float4 sLo[PLOC_BLOCK + 2 * PLOC_MAX_RADIUS], sHi[PLOC_BLOCK + 2 * PLOC_MAX_RADIUS];
-    const int64_t base = (int64_t)blockIdx.x * PLOC_BLOCK - radius;
-    for (int k = threadIdx.x; k < PLOC_BLOCK + 2 * radius; k += PLOC_BLOCK) {
-        const int64_t g = base + k;
-        if (g >= 0 && g < (int64_t)c) {
-            sLo[k] = cLo[g];
-            sHi[k] = cHi[g];
-        }
+
+/* block-wide exclusive scan of two counters per thread (creates / survives, internal children / triangles); returns the block totals */
+PTC_D void blockScan2(uint32_t a, uint32_t b, uint32_t &exA, uint32_t &exB, uint32_t &totA, uint32_t &totB, uint32_t *warpA, uint32_t *warpB) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+    uint32_t ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+        if ((int)lane >= o) ia += ta, ib += tb;
     }
+    __syncthreads(); /* the arrays may still be read by the previous call */
+    if (lane == 31u) warpA[warp] = ia, warpB[warp] = ib;
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * PLOC_BLOCK + threadIdx.x;
-    if (i >= (int64_t)c) return;
-    const float4 lo = sLo[threadIdx.x + radius], hi = sHi[threadIdx.x + radius];
-    float bestA = 0.0f;
-    int64_t best = -1;
-    for (int dj = -radius; dj <= radius; dj++) {
-        const int64_t j = i + dj;
-        if (dj == 0 || j < 0 || j >= (int64_t)c) continue;
-        const float a = mergedHalfArea(lo, hi, sLo[threadIdx.x + radius + dj], sHi[threadIdx.x + radius + dj]);
-        if (best < 0 || a < bestA) { /* ascending j and strict <: the smallest position wins ties */
-            bestA = a;
-            best = j;
+    uint32_t baseA = 0, baseB = 0;
+    totA = totB = 0;
+    for (uint32_t w = 0; w < nWarps; w++) {
+        const uint32_t va = warpA[w], vb = warpB[w];
+        if (w < warp) baseA += va, baseB += vb;
+        totA += va, totB += vb;
+    }
+    exA = baseA + ia - a;
+    exB = baseB + ib - b;
+}
+
+/* sums blockSums[0 .. gridDim.x) (two counters each): prefix of the blocks before this one and the grid total, by every block */
+PTC_D void gridPrefix2(const uint2 *__restrict__ blockSums, uint32_t &preA, uint32_t &preB, uint32_t &totA, uint32_t &totB, uint32_t *shA, uint32_t *shB) {
+    uint32_t pa = 0, pb = 0, ta = 0, tb = 0;
+    for (uint32_t k = threadIdx.x; k < gridDim.x; k += blockDim.x) {
+        const uint2 v = __ldcg(&blockSums[k]);
+        if (k < blockIdx.x) pa += v.x, pb += v.y;
+        ta += v.x, tb += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        pa += __shfl_xor_sync(0xffffffffu, pa, o), pb += __shfl_xor_sync(0xffffffffu, pb, o);
+        ta += __shfl_xor_sync(0xffffffffu, ta, o), tb += __shfl_xor_sync(0xffffffffu, tb, o);
+    }
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nWarps = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0u) shA[warp] = pa, shB[warp] = pb, shA[32 + warp] = ta, shB[32 + warp] = tb;
+    __syncthreads();
+    preA = preB = totA = totB = 0;
+    for (uint32_t w = 0; w < nWarps; w++) preA += shA[w], preB += shB[w], totA += shA[32 + w], totB += shB[32 + w];
+    __syncthreads();
+}
+
+struct PlocResult {
+    uint32_t rounds, nodes, failed, pad;
+};
+
+/* The whole clustering in one cooperative launch.  Per round: (A) nearest neighbour of every cluster within +-radius positions
+ * (shared-memory tile + halo), (B) mutual pairs: position i creates a node when nn[nn[i]] == i and i < nn[i], and survives unless it
+ * is the larger position of a mutual pair; every block sums the flags of its contiguous chunk, (C) exclusive prefix over the blocks
+ * + scan inside the chunk = node numbers (creation order = position order) and compacted positions; the pairs become nodes.  The
+ * cluster count and the node counter live in registers of every thread (all blocks compute the same totals). */
+__global__ void __launch_bounds__(PLOC_BLOCK) k_ploc_all(uint32_t n, int radius, int32_t *cid0, int32_t *cid1, float4 *cLo0, float4 *cLo1, float4 *cHi0, float4 *cHi1,
+                                                         uint32_t *__restrict__ nn, int32_t *__restrict__ parent, int32_t *__restrict__ left, int32_t *__restrict__ right,
+                                                         uint32_t *__restrict__ subCount, float4 *__restrict__ nodeLo, float4 *__restrict__ nodeHi, uint32_t *__restrict__ bigNodes,
+                                                         uint2 *__restrict__ blockSums, PlocResult *__restrict__ result) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float4 sLo[PLOC_BLOCK + 2 * PLOC_MAX_RADIUS], sHi[PLOC_BLOCK + 2 * PLOC_MAX_RADIUS];
+    __shared__ uint32_t shA[64], shB[64];
+    uint32_t c = n, nextNode = 0, rounds = 0, failed = 0;
+    int cur = 0;
+    while (c > 1u) {
+        const float4 *__restrict__ cLo = cur ? cLo1 : cLo0, *__restrict__ cHi = cur ? cHi1 : cHi0;
+        const int32_t *__restrict__ cid = cur ? cid1 : cid0;
+        float4 *__restrict__ cLoOut = cur ? cLo0 : cLo1, *__restrict__ cHiOut = cur ? cHi0 : cHi1;
+        int32_t *__restrict__ cidOut = cur ? cid0 : cid1;
+        /* (A) */
+        const uint32_t tiles = (c + PLOC_BLOCK - 1) / PLOC_BLOCK;
+        for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int64_t base = (int64_t)tile * PLOC_BLOCK - radius;
+            for (int k = threadIdx.x; k < PLOC_BLOCK + 2 * radius; k += PLOC_BLOCK) {
+                const int64_t g = base + k;
+                if (g >= 0 && g < (int64_t)c) {
+                    sLo[k] = __ldcg(&cLo[g]);
+                    sHi[k] = __ldcg(&cHi[g]);
+                }
+            }
+            __syncthreads();
+            const int64_t i = (int64_t)tile * PLOC_BLOCK + threadIdx.x;
+            if (i < (int64_t)c) {
+                const float4 lo = sLo[threadIdx.x + radius], hi = sHi[threadIdx.x + radius];
+                float bestA = 0.0f;
+                int64_t best = -1;
+                for (int dj = -radius; dj <= radius; dj++) {
+                    const int64_t j = i + dj;
+                    if (dj == 0 || j < 0 || j >= (int64_t)c) continue;
+                    const float a = mergedHalfArea(lo, hi, sLo[threadIdx.x + radius + dj], sHi[threadIdx.x + radius + dj]);
+                    if (best < 0 || a < bestA) { /* ascending j and strict <: the smallest position wins ties */
+                        bestA = a;
+                        best = j;
+                    }
+                }
+                nn[i] = (uint32_t)best;
+            }
+            __syncthreads();
         }
+        grid.sync();
+        /* (B) chunk sums; block b owns positions [b * chunk, (b + 1) * chunk) */
+        const uint32_t chunk = ((c + gridDim.x - 1) / gridDim.x + PLOC_BLOCK - 1) / PLOC_BLOCK * PLOC_BLOCK;
+        const uint32_t begin = min(blockIdx.x * chunk, c), end = min(begin + chunk, c);
+        {
+            uint32_t creates = 0, survives = 0;
+            for (uint32_t i = begin + threadIdx.x; i < end; i += PLOC_BLOCK) {
+                const uint32_t j = __ldcg(&nn[i]);
+                const bool mutual = __ldcg(&nn[j]) == i;
+                creates += (mutual && i < j) ? 1u : 0u;
+                survives += (mutual && i > j) ? 0u : 1u;
+            }
+            uint32_t ea, eb, ta, tb;
+            blockScan2(creates, survives, ea, eb, ta, tb, shA, shB);
+            if (threadIdx.x == 0) blockSums[blockIdx.x] = make_uint2(ta, tb);
+        }
+        grid.sync();
+        /* (C) */
+        uint32_t preCreate, preSurvive, totCreate, totSurvive;
+        gridPrefix2(blockSums, preCreate, preSurvive, totCreate, totSurvive, shA, shB);
+        for (uint32_t piece = begin; piece < end; piece += PLOC_BLOCK) {
+            const uint32_t i = piece + threadIdx.x;
+            uint32_t j = 0, creates = 0, survives = 0;
+            if (i < end) {
+                j = __ldcg(&nn[i]);
+                const bool mutual = __ldcg(&nn[j]) == i;
+                creates = (mutual && i < j) ? 1u : 0u;
+                survives = (mutual && i > j) ? 0u : 1u;
+            }
+            uint32_t exCreate, exSurvive, tc, ts;
+            blockScan2(creates, survives, exCreate, exSurvive, tc, ts, shA, shB);
+            if (i < end && survives) {
+                const uint32_t pos = preSurvive + exSurvive;
+                if (creates) {
+                    const int32_t id = (int32_t)(nextNode + preCreate + exCreate);
+                    const int32_t L = __ldcg(&cid[i]), R = __ldcg(&cid[j]);
+                    const float4 alo = __ldcg(&cLo[i]), ahi = __ldcg(&cHi[i]), blo = __ldcg(&cLo[j]), bhi = __ldcg(&cHi[j]);
+                    const float4 lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
+                    const float4 hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+                    const uint32_t cnt = (L >= (int32_t)(n - 1) ? 1u : __ldcg(&subCount[L])) + (R >= (int32_t)(n - 1) ? 1u : __ldcg(&subCount[R]));
+                    left[id] = L;
+                    right[id] = R;
+                    parent[L] = id;
+                    parent[R] = id;
+                    subCount[id] = cnt;
+                    nodeLo[id] = lo;
+                    nodeHi[id] = hi;
+                    if (cnt > WIDE_LEAF_TRIS) atomicAdd(bigNodes, 1u);
+                    cidOut[pos] = id;
+                    cLoOut[pos] = lo;
+                    cHiOut[pos] = hi;
+                } else {
+                    cidOut[pos] = __ldcg(&cid[i]);
+                    cLoOut[pos] = __ldcg(&cLo[i]);
+                    cHiOut[pos] = __ldcg(&cHi[i]);
+                }
+            }
+            preCreate += tc;
+            preSurvive += ts;
+        }
+        if (totCreate == 0u) { /* cannot happen (the globally closest pair is always mutual); never spin */
+            failed = 1;
+            break;
+        }
+        nextNode += totCreate;
+        c = totSurvive;
+        cur ^= 1;
+        rounds++;
+        grid.sync();
     }
-    nn[i] = (uint32_t)best;
-}
-
-/* low word: 1 when position i creates a node (mutual pair, i is the smaller position); high word: 1 when i survives */
-__global__ void k_ploc_flags(uint32_t c, const uint32_t *__restrict__ nn, unsigned long long *__restrict__ counts) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c) return;
-    const uint32_t j = nn[i];
-    const bool mutual = nn[j] == i;
-    const unsigned long long creates = (mutual && i < j) ? 1ull : 0ull, survives = (mutual && i > j) ? 0ull : 1ull;
-    counts[i] = creates | (survives << 32);
-}
-
-__global__ void k_ploc_apply(uint32_t c, uint32_t nextNode, const uint32_t *__restrict__ nn, const unsigned long long *__restrict__ counts,
-                             const unsigned long long *__restrict__ inclusive, const int32_t *__restrict__ cid, const float4 *__restrict__ cLo,
-                             const float4 *__restrict__ cHi, int32_t *__restrict__ cidOut, float4 *__restrict__ cLoOut, float4 *__restrict__ cHiOut,
-                             uint32_t n, int32_t *__restrict__ parent, int32_t *__restrict__ left, int32_t *__restrict__ right,
-                             uint32_t *__restrict__ subCount, float4 *__restrict__ nodeLo, float4 *__restrict__ nodeHi, uint32_t *__restrict__ bigNodes) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c) return;
-    const unsigned long long own = counts[i], excl = inclusive[i] - own;
-    if ((own >> 32) == 0ull) return; /* merged into its partner */
-    const uint32_t pos = (uint32_t)(excl >> 32);
-    if (own & 1ull) {
-        const uint32_t j = nn[i];
-        const int32_t id = (int32_t)(nextNode + (uint32_t)(excl & 0xffffffffull));
-        const int32_t L = cid[i], R = cid[j];
-        const float4 alo = cLo[i], ahi = cHi[i], blo = cLo[j], bhi = cHi[j];
-        const float4 lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
-        const float4 hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
-        const uint32_t cnt = subTris(L, n, subCount) + subTris(R, n, subCount);
-        left[id] = L;
-        right[id] = R;
-        parent[L] = id;
-        parent[R] = id;
-        subCount[id] = cnt;
-        nodeLo[id] = lo;
-        nodeHi[id] = hi;
-        if (cnt > WIDE_LEAF_TRIS) atomicAdd(bigNodes, 1u);
-        cidOut[pos] = id;
-        cLoOut[pos] = lo;
-        cHiOut[pos] = hi;
-    } else {
-        cidOut[pos] = cid[i];
-        cLoOut[pos] = cLo[i];
-        cHiOut[pos] = cHi[i];
-    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *result = PlocResult{rounds, nextNode, failed, 0u};
 }
 
 /* ------------------------------------------------------------------ collapse to the 8-wide compressed BVH
@@ -372,12 +474,8 @@ PTC_D float halfArea(float4 lo, float4 hi) {
 }
 
 /* one thread per wide node of the current level: choose children and slots, count internal children / triangles */
-__global__ void k_wide_select(uint32_t n, uint32_t count, uint32_t levelBase, const int32_t *__restrict__ rootOf, const int32_t *__restrict__ left,
-                              const int32_t *__restrict__ right, const uint32_t *__restrict__ subCount, const float4 *__restrict__ nodeLo,
-                              const float4 *__restrict__ nodeHi, WideTmp *__restrict__ tmp, unsigned long long *__restrict__ counts) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= count) return;
-    const int32_t root = rootOf[levelBase + k];
+PTC_D uint2 wideSelect(uint32_t n, int32_t root, const int32_t *__restrict__ left, const int32_t *__restrict__ right, const uint32_t *__restrict__ subCount,
+                       const float4 *__restrict__ nodeLo, const float4 *__restrict__ nodeHi, WideTmp &t) {
     int32_t list[8];
     uint32_t tris[8];
     float area[8];
@@ -439,7 +537,6 @@ __global__ void k_wide_select(uint32_t n, uint32_t count, uint32_t levelBase, co
         slotChild[bs] = list[bc];
     }
     uint32_t nInternal = 0, nTris = 0;
-    WideTmp t;
     for (int sl = 0; sl < 8; sl++) {
         const int32_t c = slotChild[sl];
         t.slotChild[sl] = c;
@@ -447,8 +544,7 @@ __global__ void k_wide_select(uint32_t n, uint32_t count, uint32_t levelBase, co
         const uint32_t ct = subTris(c, n, subCount);
         if (ct > (uint32_t)WIDE_LEAF_TRIS) nInternal++; else nTris += ct;
     }
-    tmp[levelBase + k] = t;
-    counts[k] = (unsigned long long)nInternal | ((unsigned long long)nTris << 32);
+    return make_uint2(nInternal, nTris);
 }
 
 /* biased exponent byte e with extent <= 255 * 2^(e - 127) */
@@ -463,19 +559,11 @@ PTC_D uint32_t wideExponent(float extent) {
 }
 PTC_D float pow2Biased(uint32_t e) { return __uint_as_float(e << 23); }
 
-__global__ void k_wide_emit(uint32_t n, uint32_t count, uint32_t levelBase, uint32_t nextBase, uint32_t levelTriBase, int32_t *__restrict__ rootOf,
-                            const int32_t *__restrict__ left, const int32_t *__restrict__ right, const uint32_t *__restrict__ subCount,
-                            const float4 *__restrict__ nodeLo, const float4 *__restrict__ nodeHi,
-                            const WideTmp *__restrict__ tmp, const unsigned long long *__restrict__ counts,
-                            const unsigned long long *__restrict__ inclusive, uint4 *__restrict__ wide, uint32_t *__restrict__ triMap) {
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= count) return;
-    const unsigned long long excl = inclusive[k] - counts[k];
-    const uint32_t childBase = nextBase + (uint32_t)(excl & 0xffffffffull);
-    const uint32_t triBase = levelTriBase + (uint32_t)(excl >> 32);
-    const uint32_t id = levelBase + k;
-    const int32_t root = rootOf[id];
-    const WideTmp t = tmp[id];
+/* writes wide node `id` (rooted at binary node `root`, children chosen by wideSelect): its internal children are numbered from
+ * childBase (their binary roots go to rootOf), the triangles of its leaf children from triBase */
+PTC_D void wideEmit(uint32_t n, uint32_t id, int32_t root, const WideTmp &t, uint32_t childBase, uint32_t triBase, int32_t *__restrict__ rootOf,
+                    const int32_t *__restrict__ left, const int32_t *__restrict__ right, const uint32_t *__restrict__ subCount,
+                    const float4 *__restrict__ nodeLo, const float4 *__restrict__ nodeHi, uint4 *__restrict__ wide, uint32_t *__restrict__ triMap) {
     const float4 lo = nodeLo[root], hi = nodeHi[root];
     const float plo[3] = {lo.x, lo.y, lo.z}, phi[3] = {hi.x, hi.y, hi.z};
     uint32_t e[3];
@@ -547,6 +635,72 @@ __global__ void k_wide_emit(uint32_t n, uint32_t count, uint32_t levelBase, uint
     out[4] = w4;
 }
 
+struct WideResult {
+    uint32_t nWide, nTris, levels, failed;
+};
+#define WIDE_BLOCK 128
+/* The whole collapse in one cooperative launch, level by level (numbering stays breadth first and deterministic).  Per level:
+ * (1) every wide node of the level chooses its children (wideSelect); blocks own contiguous chunks and sum their (internal
+ * children, triangles); (2) prefix over the blocks + scan inside the chunk = first child index / first triangle position of every
+ * node; wideEmit writes the nodes and the roots of the next level. */
+__global__ void __launch_bounds__(WIDE_BLOCK) k_wide_all(uint32_t n, int32_t binaryRoot, uint32_t maxWide, int32_t *__restrict__ rootOf, const int32_t *__restrict__ left,
+                                                         const int32_t *__restrict__ right, const uint32_t *__restrict__ subCount, const float4 *__restrict__ nodeLo,
+                                                         const float4 *__restrict__ nodeHi, WideTmp *__restrict__ tmp, uint2 *__restrict__ counts, uint4 *__restrict__ wide,
+                                                         uint32_t *__restrict__ triMap, uint2 *__restrict__ blockSums, WideResult *__restrict__ result) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t shA[64], shB[64];
+    if (blockIdx.x == 0 && threadIdx.x == 0) rootOf[0] = binaryRoot;
+    grid.sync();
+    uint32_t levelBase = 0, levelCount = 1, triBase = 0, levels = 0, failed = 0;
+    while (levelCount > 0u) {
+        if ((size_t)levelBase + levelCount > maxWide) {
+            failed = 1;
+            break;
+        }
+        const uint32_t chunk = ((levelCount + gridDim.x - 1) / gridDim.x + WIDE_BLOCK - 1) / WIDE_BLOCK * WIDE_BLOCK;
+        const uint32_t begin = min(blockIdx.x * chunk, levelCount), end = min(begin + chunk, levelCount);
+        {
+            uint32_t a = 0, b = 0;
+            for (uint32_t k = begin + threadIdx.x; k < end; k += WIDE_BLOCK) {
+                WideTmp t;
+                const uint2 cnt = wideSelect(n, __ldcg(&rootOf[levelBase + k]), left, right, subCount, nodeLo, nodeHi, t);
+                tmp[levelBase + k] = t;
+                counts[k] = cnt;
+                a += cnt.x;
+                b += cnt.y;
+            }
+            uint32_t ea, eb, ta, tb;
+            blockScan2(a, b, ea, eb, ta, tb, shA, shB);
+            if (threadIdx.x == 0) blockSums[blockIdx.x] = make_uint2(ta, tb);
+        }
+        grid.sync();
+        uint32_t preInner, preTris, totInner, totTris;
+        gridPrefix2(blockSums, preInner, preTris, totInner, totTris, shA, shB);
+        const uint32_t nextBase = levelBase + levelCount;
+        for (uint32_t piece = begin; piece < end; piece += WIDE_BLOCK) {
+            const uint32_t k = piece + threadIdx.x;
+            uint2 cnt = make_uint2(0u, 0u);
+            if (k < end) cnt = counts[k];
+            uint32_t exInner, exTris, ti, tt;
+            blockScan2(cnt.x, cnt.y, exInner, exTris, ti, tt, shA, shB);
+            if (k < end) {
+                const uint32_t id = levelBase + k;
+                const WideTmp t = tmp[id];
+                wideEmit(n, id, __ldcg(&rootOf[id]), t, nextBase + preInner + exInner, triBase + preTris + exTris, rootOf, left, right, subCount, nodeLo, nodeHi, wide, triMap);
+            }
+            preInner += ti;
+            preTris += tt;
+        }
+        triBase += totTris;
+        levelBase = nextBase;
+        levelCount = totInner;
+        levels++;
+        grid.sync();
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *result = WideResult{levelBase, triBase, levels, failed};
+}
+
 /* triangles in wide-node order: position k holds sorted triangle triMap[k] = world triangle order[triMap[k]] */
 __global__ void k_gather_tris(uint32_t n, const uint32_t *__restrict__ triMap, const uint32_t *__restrict__ order, const float4 *__restrict__ in,
                               float4 *__restrict__ out, uint32_t *__restrict__ wideOrder) {
@@ -594,34 +748,47 @@ struct Build {
                                       [5 x float4 per wide node, breadth first][3 x float4 per triangle, wide-node order] */
     DBuf<uint4> wide;              /* collapse output before compaction (sized by the node bound) */
     DBuf<uint64_t> keys, keysSorted;
-    DBuf<uint32_t> ids, order, arrivals, sceneBounds, triMap, wideOrder, bigNodes;
+    DBuf<uint32_t> ids, order, arrivals, sceneBounds, triMap, wideOrder, bigNodes, radixTable;
     DBuf<int32_t> parent, left, right, rootOf, cid[2];
     DBuf<uint32_t> subCount, nnIdx;
     DBuf<float4> cLo[2], cHi[2];
+    DBuf<uint2> blockSums, wideCounts;
+    DBuf<PlocResult> plocResult;
+    DBuf<WideResult> wideResult;
     int32_t binaryRoot = 0;
     uint32_t hierarchy = PTC_HIERARCHY_PLOC, plocRadius = 16, plocRounds = 0;
     DBuf<WideTmp> wideTmp;
-    DBuf<unsigned long long> counts, inclusive;
-    DBuf<uint8_t> sortTemp, scanTemp;
     uint32_t n = 0;
     uint32_t nWide = 0, wideLevels = 0;
     int bits = 0;
+    int hostSyncs = 0; /* host round trips of the last build */
 
     size_t bytes() const {
         return trisUnsorted.bytes() + trav.bytes() + shading.bytes() + triLo.bytes() + triHi.bytes() + nodeLo.bytes() + nodeHi.bytes() + wide.bytes() +
                keys.bytes() + keysSorted.bytes() + ids.bytes() + order.bytes() + arrivals.bytes() + parent.bytes() + left.bytes() +
-               right.bytes() + sortTemp.bytes() + triMap.bytes() + wideOrder.bytes() + subCount.bytes() + rootOf.bytes() + wideTmp.bytes() +
-               counts.bytes() + inclusive.bytes() + scanTemp.bytes();
+               right.bytes() + radixTable.bytes() + triMap.bytes() + wideOrder.bytes() + subCount.bytes() + rootOf.bytes() + wideTmp.bytes() +
+               wideCounts.bytes() + cid[0].bytes() + cid[1].bytes() + cLo[0].bytes() + cLo[1].bytes() + cHi[0].bytes() + cHi[1].bytes() + nnIdx.bytes();
     }
     size_t traversalBytes() const { return (size_t)nWide * 80 + (size_t)n * 48; }
     const float4 *wideNodes() const { return trav.p; }
     const float4 *sortedTris() const { return trav.p ? trav.p + 5 * (size_t)nWide : nullptr; }
+
+    /* blocks of a cooperative launch: all of them must be resident */
+    static int cooperativeGrid(const void *kernel, int block, int capPerSm) {
+        int dev = 0, sms = 0, perSm = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, block, 0));
+        if (perSm < 1) throw CudaError{"cooperative kernel does not fit on an SM"};
+        return sms * std::min(perSm, capPerSm);
+    }
 
     /* returns the number of kernel launches */
     int run(const ptc_vertex *vertices, const uint32_t *indices, const DInstance *instances, uint32_t nInstances, uint32_t nTris,
             cudaStream_t s) {
         n = nTris;
         nWide = wideLevels = 0;
+        hostSyncs = 0;
         if (n == 0) return 0;
         const bool verbose = getenv("PTC_VERBOSE") != nullptr;
         auto now = [&] {
@@ -653,6 +820,7 @@ struct Build {
         wideOrder.alloc(n);
         sceneBounds.alloc(6);
         bigNodes.alloc(1);
+        radixTable.alloc(radix::tableEntries(n));
         uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
         CUDA_TRY(cudaMemcpyAsync(sceneBounds.p, init, sizeof(init), cudaMemcpyHostToDevice, s));
         CUDA_TRY(cudaMemsetAsync(parent.p, 0xff, nn * sizeof(int32_t), s));
@@ -666,16 +834,22 @@ struct Build {
         bits = mortonBitsPerAxis(n);
         k_morton<<<G, B, 0, s>>>(triLo.p, triHi.p, sceneBounds.p, n, bits, keys.p, ids.p);
         launches++;
-        size_t tempBytes = 0;
-        int endBit = bits * 3;
-        cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, keys.p, keysSorted.p, ids.p, order.p, (int)n, 0, endBit, s);
-        sortTemp.alloc(tempBytes);
-        CUDA_TRY(cub::DeviceRadixSort::SortPairs(sortTemp.p, tempBytes, keys.p, keysSorted.p, ids.p, order.p, (int)n, 0, endBit, s));
-        launches += (endBit + 7) / 8 * 2 + 1;
+        /* (code, id) pairs in ascending order: the sorted keys must end in keysSorted and the ids in order */
+        const int endBit = bits * 3;
+        const int passes = (endBit + 7) / 8;
+        uint64_t *kA = keys.p, *kB = keysSorted.p;
+        uint32_t *vA = ids.p, *vB = order.p;
+        if (passes % 2 == 0) { /* an even number of passes ends in the buffers it started from: start from the final ones */
+            CUDA_TRY(cudaMemcpyAsync(keysSorted.p, keys.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(order.p, ids.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+            kA = keysSorted.p, kB = keys.p, vA = order.p, vB = ids.p;
+        }
+        radix::sortPairs(kA, vA, kB, vB, radixTable.p, n, endBit, s, &launches);
         const auto tSorted = now();
-        size_t scanBytes = 0;
         binaryRoot = 0;
         plocRounds = 0;
+        const uint32_t blockSumEntries = 148u * 16u;
+        blockSums.alloc(blockSumEntries);
         if (hierarchy == PTC_HIERARCHY_LBVH || n == 1) {
             if (n > 1) {
                 k_karras<<<(n - 1 + B - 1) / B, B, 0, s>>>(keysSorted.p, n, parent.p, left.p, right.p, subCount.p, bigNodes.p);
@@ -684,81 +858,67 @@ struct Build {
             k_fit<<<G, B, 0, s>>>(n, order.p, triLo.p, triHi.p, parent.p, left.p, right.p, nodeLo.p, nodeHi.p, arrivals.p);
             launches++;
         } else {
-            const int radius = (int)std::min<uint32_t>(std::max<uint32_t>(plocRadius, 1u), PLOC_MAX_RADIUS);
+            int radius = (int)std::min<uint32_t>(std::max<uint32_t>(plocRadius, 1u), PLOC_MAX_RADIUS);
             for (int k = 0; k < 2; k++) {
                 cid[k].alloc(n);
                 cLo[k].alloc(n);
                 cHi[k].alloc(n);
             }
             nnIdx.alloc(n);
-            counts.alloc(n);
-            inclusive.alloc(n);
-            cub::DeviceScan::InclusiveSum(nullptr, scanBytes, counts.p, inclusive.p, (int)n, s);
-            scanTemp.alloc(scanBytes);
+            plocResult.alloc(1);
             k_ploc_init<<<G, B, 0, s>>>(n, order.p, triLo.p, triHi.p, nodeLo.p, nodeHi.p, cid[0].p, cLo[0].p, cHi[0].p);
             launches++;
-            uint32_t c = n, nextNode = 0;
-            int cur = 0;
-            while (c > 1) {
-                const uint32_t g = (c + PLOC_BLOCK - 1) / PLOC_BLOCK;
-                k_ploc_nn<<<g, PLOC_BLOCK, 0, s>>>(c, radius, cLo[cur].p, cHi[cur].p, nnIdx.p);
-                k_ploc_flags<<<g, PLOC_BLOCK, 0, s>>>(c, nnIdx.p, counts.p);
-                size_t sb = scanBytes;
-                CUDA_TRY(cub::DeviceScan::InclusiveSum(scanTemp.p, sb, counts.p, inclusive.p, (int)c, s));
-                k_ploc_apply<<<g, PLOC_BLOCK, 0, s>>>(c, nextNode, nnIdx.p, counts.p, inclusive.p, cid[cur].p, cLo[cur].p, cHi[cur].p, cid[cur ^ 1].p,
-                                                       cLo[cur ^ 1].p, cHi[cur ^ 1].p, n, parent.p, left.p, right.p, subCount.p, nodeLo.p, nodeHi.p,
-                                                       bigNodes.p);
-                launches += 4;
-                unsigned long long total = 0;
-                CUDA_TRY(cudaMemcpyAsync(&total, inclusive.p + (c - 1), sizeof(total), cudaMemcpyDeviceToHost, s));
-                CUDA_TRY(cudaStreamSynchronize(s));
-                const uint32_t merges = (uint32_t)(total & 0xffffffffull);
-                if (merges == 0) throw CudaError{"PLOC round without a merge"};
-                nextNode += merges;
-                c = (uint32_t)(total >> 32);
-                cur ^= 1;
-                plocRounds++;
-            }
-            if (nextNode != n - 1) throw CudaError{"PLOC built a wrong number of nodes"};
+            /* few resident blocks per SM keep the grid barriers cheap; small inputs need no more than one block per tile */
+            int grid = cooperativeGrid((const void *)k_ploc_all, PLOC_BLOCK, n > (2u << 20) ? 8 : 4);
+            grid = std::max(1, std::min<int>(grid, (int)((n + PLOC_BLOCK - 1) / PLOC_BLOCK)));
+            if ((uint32_t)grid > blockSumEntries) grid = (int)blockSumEntries;
+            uint32_t nArg = n;
+            void *args[] = {&nArg, &radius, &cid[0].p, &cid[1].p, &cLo[0].p, &cLo[1].p, &cHi[0].p, &cHi[1].p, &nnIdx.p, &parent.p, &left.p, &right.p,
+                            &subCount.p, &nodeLo.p, &nodeHi.p, &bigNodes.p, &blockSums.p, &plocResult.p};
+            CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_ploc_all, dim3(grid), dim3(PLOC_BLOCK), args, 0, s));
+            launches++;
             binaryRoot = (int32_t)(n - 2);
         }
 
         const auto tHierarchy = now();
-        /* ---- collapse, one level at a time */
+        /* ---- first host round trip: the bound of the wide node count sizes the collapse buffers (and the PLOC verdict rides along) */
         uint32_t big = 0;
+        PlocResult pr{};
         CUDA_TRY(cudaMemcpyAsync(&big, bigNodes.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (hierarchy == PTC_HIERARCHY_PLOC && n > 1) CUDA_TRY(cudaMemcpyAsync(&pr, plocResult.p, sizeof(pr), cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
+        hostSyncs++;
+        if (hierarchy == PTC_HIERARCHY_PLOC && n > 1) {
+            if (pr.failed) throw CudaError{"PLOC round without a merge"};
+            if (pr.nodes != n - 1) throw CudaError{"PLOC built a wrong number of nodes"};
+            plocRounds = pr.rounds;
+        }
         const size_t maxWide = (size_t)big + 1; /* every wide node but the root is rooted at a distinct binary node with > 3 triangles */
         wide.alloc(5 * maxWide);
         wideTmp.alloc(maxWide);
         rootOf.alloc(maxWide);
-        counts.alloc(maxWide);
-        inclusive.alloc(maxWide);
-        cub::DeviceScan::InclusiveSum(nullptr, scanBytes, counts.p, inclusive.p, (int)maxWide, s);
-        scanTemp.alloc(scanBytes);
-        /* Karras: internal node 0 is the root; PLOC: the last node created; a single triangle is leaf node 0 = n - 1 */
-        CUDA_TRY(cudaMemcpyAsync(rootOf.p, &binaryRoot, sizeof(int32_t), cudaMemcpyHostToDevice, s));
-        uint32_t levelBase = 0, levelCount = 1, triBase = 0;
-        while (levelCount > 0) {
-            if ((size_t)levelBase + levelCount > maxWide) throw CudaError{"wide BVH collapse exceeded its node bound"};
-            const uint32_t g = (levelCount + 127) / 128;
-            k_wide_select<<<g, 128, 0, s>>>(n, levelCount, levelBase, rootOf.p, left.p, right.p, subCount.p, nodeLo.p, nodeHi.p, wideTmp.p, counts.p);
-            size_t sb = scanBytes;
-            CUDA_TRY(cub::DeviceScan::InclusiveSum(scanTemp.p, sb, counts.p, inclusive.p, (int)levelCount, s));
-            const uint32_t nextBase = levelBase + levelCount;
-            k_wide_emit<<<g, 128, 0, s>>>(n, levelCount, levelBase, nextBase, triBase, rootOf.p, left.p, right.p, subCount.p, nodeLo.p, nodeHi.p, wideTmp.p, counts.p,
-                                         inclusive.p, wide.p, triMap.p);
-            launches += 3;
-            unsigned long long total = 0;
-            CUDA_TRY(cudaMemcpyAsync(&total, inclusive.p + (levelCount - 1), sizeof(total), cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaStreamSynchronize(s));
-            triBase += (uint32_t)(total >> 32);
-            levelBase = nextBase;
-            levelCount = (uint32_t)(total & 0xffffffffull);
-            wideLevels++;
+        wideCounts.alloc(maxWide);
+        wideResult.alloc(1);
+        {
+            /* Karras: internal node 0 is the root; PLOC: the last node created; a single triangle is leaf node 0 = n - 1 */
+            int grid = cooperativeGrid((const void *)k_wide_all, WIDE_BLOCK, n > (2u << 20) ? 16 : 4);
+            grid = std::max(1, std::min<int>(grid, (int)((maxWide + WIDE_BLOCK - 1) / WIDE_BLOCK)));
+            if ((uint32_t)grid > blockSumEntries) grid = (int)blockSumEntries;
+            uint32_t nArg = n, maxWideArg = (uint32_t)maxWide;
+            void *args[] = {&nArg, &binaryRoot, &maxWideArg, &rootOf.p, &left.p, &right.p, &subCount.p, &nodeLo.p, &nodeHi.p, &wideTmp.p, &wideCounts.p,
+                            &wide.p, &triMap.p, &blockSums.p, &wideResult.p};
+            CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_wide_all, dim3(grid), dim3(WIDE_BLOCK), args, 0, s));
+            launches++;
         }
-        nWide = levelBase;
-        if (triBase != n) throw CudaError{"wide BVH collapse lost triangles"};
+        /* ---- second host round trip: the node count sizes the traversal buffer */
+        WideResult wr{};
+        CUDA_TRY(cudaMemcpyAsync(&wr, wideResult.p, sizeof(wr), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        hostSyncs++;
+        if (wr.failed) throw CudaError{"wide BVH collapse exceeded its node bound"};
+        if (wr.nTris != n) throw CudaError{"wide BVH collapse lost triangles"};
+        nWide = wr.nWide;
+        wideLevels = wr.levels;
         const auto tCollapsed = now();
         trav.alloc(5 * (size_t)nWide + 3 * (size_t)n);
         CUDA_TRY(cudaMemcpyAsync(trav.p, wide.p, (size_t)nWide * 80, cudaMemcpyDeviceToDevice, s));
@@ -770,9 +930,9 @@ struct Build {
         CUDA_TRY(cudaGetLastError());
         if (verbose) {
             const auto tEnd = now();
-            fprintf(stderr, "[ptc] build: %u triangles | alloc+flatten+morton+sort %.2f ms | hierarchy %.2f ms (%s, %u rounds) | collapse %.2f ms (%u levels, %u wide nodes) | gather %.2f ms\n",
+            fprintf(stderr, "[ptc] build: %u triangles | alloc+flatten+morton+sort %.2f ms | hierarchy %.2f ms (%s, %u rounds) | collapse %.2f ms (%u levels, %u wide nodes) | gather %.2f ms | %d host syncs\n",
                     n, msSince(tStart, tSorted), msSince(tSorted, tHierarchy), hierarchy == PTC_HIERARCHY_PLOC ? "PLOC" : "Karras", plocRounds,
-                    msSince(tHierarchy, tCollapsed), wideLevels, nWide, msSince(tCollapsed, tEnd));
+                    msSince(tHierarchy, tCollapsed), wideLevels, nWide, msSince(tCollapsed, tEnd), hostSyncs);
         }
         return launches;
     }

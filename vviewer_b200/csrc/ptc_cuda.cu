@@ -406,7 +406,6 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
     const uint32_t batches = rp->samples / rp->batch_size; /* VulkanRendererPathTracing.cpp:798-799 (T7) */
     const uint32_t totalSamples = batches * rp->batch_size;
     const uint32_t world = rp->world ? rp->world : 1u;
-    const uint32_t tile = rp->tile_size ? rp->tile_size : 32u;
     const size_t nPix = (size_t)W * H;
     cudaStream_t s = c->stream;
     c->progress = 0.0f; /* renderProgress() restarts with every render (VulkanRendererPathTracing.cpp:228-231) */
@@ -1425,6 +1424,50 @@ PTC_API int ptc_sampler_points(ptc_ctx *ctx, uint32_t px, uint32_t py, uint32_t 
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out_xy, dO.p, (size_t)count * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+    PTC_GUARD_END(ctx)
+}
+
+PTC_API int ptc_srgb_table(ptc_ctx *ctx, float *out256) {
+    Dev *c = dev0(ctx);
+    if (!c || !c->stream || !out256) return fail(ctx, "context has no CUDA device");
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    /* a 256 x 1 sRGB texture whose texel i holds the code i, created exactly like the scene's textures (createTextures) */
+    cudaArray_t arr = nullptr;
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+    CUDA_TRY(cudaMalloc3DArray(&arr, &fmt, make_cudaExtent(256, 1, 1), cudaArrayLayered));
+    std::vector<uint8_t> px(256 * 4);
+    for (int i = 0; i < 256; i++) px[4 * i] = px[4 * i + 1] = px[4 * i + 2] = (uint8_t)i, px[4 * i + 3] = 255;
+    cudaMemcpy3DParms cp{};
+    cp.srcPtr = make_cudaPitchedPtr(px.data(), 256 * 4, 256, 1);
+    cp.dstArray = arr;
+    cp.extent = make_cudaExtent(256, 1, 1);
+    cp.kind = cudaMemcpyHostToDevice;
+    cudaError_t e = cudaMemcpy3D(&cp);
+    cudaTextureObject_t tex = 0;
+    if (e == cudaSuccess) {
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeWrap;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 1;
+        td.sRGB = 1;
+        e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+    }
+    DBuf<float> dO;
+    if (e == cudaSuccess) {
+        dO.alloc(256);
+        wf::k_srgb_table<<<1, 256, 0, c->stream>>>(tex, dO.p);
+        e = cudaMemcpyAsync(out256, dO.p, 256 * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    }
+    if (tex) cudaDestroyTextureObject(tex);
+    cudaFreeArray(arr);
+    CUDA_TRY(e);
     return 0;
     PTC_GUARD_END(ctx)
 }

@@ -1308,6 +1308,10 @@ __global__ void k_sampler_points(uint32_t px, uint32_t py, uint32_t width, uint3
     out[2 * i] = p.x;
     out[2 * i + 1] = p.y;
 }
+__global__ void k_srgb_table(cudaTextureObject_t tex, float *__restrict__ out) {
+    const uint32_t i = threadIdx.x;
+    out[i] = tex2DLayered<float4>(tex, ((float)i + 0.5f) / 256.0f, 0.5f, 0).x;
+}
 __global__ void k_env_lookup(const __grid_constant__ DScene sc, int n, const float *dirs, float *out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
