@@ -209,6 +209,8 @@ typedef struct ptc_stats {
                                  resident by uid are not copied and not counted) */
     double reduce_ms;         /* multi-GPU: the NCCL reduce of the accumulation buffers inside the last render */
     double bin_ms;            /* time inside the ray-binning kernel (PTC_FLAG_TIME_KERNELS) */
+    uint64_t accel_levels;    /* 1 = one tree over world triangles, 2 = per-mesh trees under an instance tree */
+    uint64_t traversal_bytes; /* nodes + triangles the traversal kernels read */
 } ptc_stats;
 
 typedef struct ptc_ctx ptc_ctx;
@@ -254,6 +256,23 @@ PTC_API int ptc_set_sampler_tables(ptc_ctx *ctx, const float *pmj, uint32_t n_se
  * ray); the environment variable PTC_HIERARCHY=lbvh|ploc overrides the default at ptc_create.  Call before ptc_build_accel. */
 enum ptc_hierarchy { PTC_HIERARCHY_LBVH = 0, PTC_HIERARCHY_PLOC = 1 };
 PTC_API int ptc_set_build_options(ptc_ctx *ctx, uint32_t hierarchy, uint32_t ploc_radius);
+
+/* One level or two?  The reference's driver builds a BLAS per mesh and one TLAS over the instances (VulkanScene.cpp:306-381).
+ *   PTC_ACCEL_FLAT       one tree over world-space triangles (instances flattened): no per-ray transform, no overlapping instance
+ *                        boxes - fastest while the traversal data fits the caches
+ *   PTC_ACCEL_TWO_LEVEL  one tree per mesh in object space + one tree over the instances' world boxes; rays are transformed with the
+ *                        instance's world->object matrix on the way in - for heavily instanced scenes (BASELINE C4: 42.5 M world
+ *                        triangles, 0.6 M unique ones)
+ *   PTC_ACCEL_AUTO       (default) two levels when the world triangles exceed 4 M and are at least 4 times the unique ones
+ * Call before ptc_build_accel.  Hits are the same up to the rounding of the object-space intersection. */
+enum ptc_accel_mode { PTC_ACCEL_AUTO = 0, PTC_ACCEL_FLAT = 1, PTC_ACCEL_TWO_LEVEL = 2 };
+PTC_API int ptc_set_accel_mode(ptc_ctx *ctx, uint32_t mode);
+/* Two-level dump for the bit-exact build check: level -1 = top-level tree (primitives = instances), level m >= 0 = tree of mesh m
+ * (primitives = the mesh's triangles).  node_words[n_nodes * 20] with child / primitive indices relative to the tree, prim_order[n_prims]
+ * (tree position -> primitive), box6 = the tree's bounds (lo xyz, hi xyz).  NULL arrays query the counts.  Error on a single-level
+ * structure. */
+PTC_API int ptc_get_accel_level(ptc_ctx *ctx, int32_t level, uint64_t *n_nodes_out, uint64_t *n_prims_out, uint32_t *node_words, uint32_t *prim_order,
+                                float *box6);
 
 /* ---------------------------------------------------------------- render */
 /* replaces render(VkDescriptorSet) batch loop + readback (VulkanRendererPathTracing.cpp:791-956).

@@ -247,16 +247,18 @@ struct LBVH {
     }
 
     void build(const std::vector<WorldTri> &tris) {
-        n = tris.size();
+        std::vector<AABB> tb(tris.size());
+        for (size_t i = 0; i < tris.size(); i++) tb[i] = triBounds(tris[i]);
+        buildBounds(tb);
+    }
+    /* the build only ever looks at the primitives' boxes: triangles (single level, bottom level) or instances (top level) */
+    void buildBounds(const std::vector<AABB> &tb) {
+        n = tb.size();
         morton.assign(n, 0);
         order.resize(n);
         if (n == 0) return;
-        std::vector<AABB> tb(n);
         scene = AABB();
-        for (uint64_t i = 0; i < n; i++) {
-            tb[i] = triBounds(tris[i]);
-            scene.grow(tb[i]);
-        }
+        for (uint64_t i = 0; i < n; i++) scene.grow(tb[i]);
         vec3 ext = scene.hi - scene.lo;
         vec3 inv(ext.x > 0 ? 1.0f / ext.x : 0.0f, ext.y > 0 ? 1.0f / ext.y : 0.0f, ext.z > 0 ? 1.0f / ext.z : 0.0f);
         int bits = mortonBitsPerAxis(n);

@@ -1164,6 +1164,74 @@ PTC_API int ptc_get_lbvh(ptc_ctx *c, uint64_t *n_out, uint64_t *morton, uint32_t
     return 0;
 }
 
+PTC_API int ptc_set_accel_mode(ptc_ctx *c, uint32_t mode) {
+    if (!c) return 1;
+    if (mode > PTC_ACCEL_TWO_LEVEL) return fail(c, "unknown acceleration-structure mode");
+    return 0; /* the oracle's own queries are structure independent (brute force / its median-split tree over world triangles) */
+}
+
+/* CPU restatement of the two-level build (vviewer_b200/csrc/lbvh.cuh::TwoLevel; the reference's driver builds one BLAS per mesh and a
+ * TLAS over the instances, VulkanScene.cpp:306-381): level m >= 0 = the tree over mesh m's OBJECT-space triangles (v0, v1 - v0, v2 - v0),
+ * empty when no instance uses the mesh; level -1 = the tree over the instances' world boxes, each the bounds of the 8 corners of its
+ * mesh's box through the instance matrix (same fixed operation order as the flatten). */
+PTC_API int ptc_get_accel_level(ptc_ctx *c, int32_t level, uint64_t *n_nodes_out, uint64_t *n_prims_out, uint32_t *node_words, uint32_t *prim_order,
+                                float *box6) {
+    if (!c) return 1;
+    if (level < -1 || level >= (int32_t)c->meshes.size()) return fail(c, "no such level");
+    std::vector<uint8_t> used(c->meshes.size(), 0);
+    for (const InstanceX &I : c->instances) used[I.d.mesh_index] = 1;
+    auto v3 = [](const float *p) { return vec3(p[0], p[1], p[2]); };
+    auto meshBounds = [&](uint32_t m, std::vector<AABB> &tb) {
+        const ptc_mesh &M = c->meshes[m];
+        tb.clear();
+        if (!used[m]) return;
+        tb.resize(M.tri_count);
+        for (uint32_t p = 0; p < M.tri_count; p++) {
+            const uint32_t *ind = &c->indices[M.first_index + 3 * (size_t)p];
+            vec3 a = v3(c->vertices[M.first_vertex + ind[0]].position), b = v3(c->vertices[M.first_vertex + ind[1]].position),
+                 cc = v3(c->vertices[M.first_vertex + ind[2]].position);
+            tb[p] = triBounds(WorldTri{a, b - a, cc - a, 0u, p});
+        }
+    };
+    std::vector<AABB> boxes;
+    if (level >= 0) {
+        meshBounds((uint32_t)level, boxes);
+    } else {
+        std::vector<AABB> meshBox(c->meshes.size());
+        std::vector<AABB> tb;
+        for (uint32_t m = 0; m < c->meshes.size(); m++) {
+            meshBounds(m, tb);
+            AABB b;
+            for (const AABB &t : tb) b.grow(t);
+            meshBox[m] = b;
+        }
+        boxes.resize(c->instances.size());
+        for (size_t i = 0; i < c->instances.size(); i++) {
+            const InstanceX &I = c->instances[i];
+            const AABB &mb = meshBox[I.d.mesh_index];
+            AABB w;
+            for (int corner = 0; corner < 8; corner++)
+                w.grow(xform_point(I.model, vec3((corner & 1) ? mb.hi.x : mb.lo.x, (corner & 2) ? mb.hi.y : mb.lo.y, (corner & 4) ? mb.hi.z : mb.lo.z)));
+            boxes[i] = w;
+        }
+    }
+    LBVH L;
+    L.hierarchy = c->hierarchy;
+    L.plocRadius = c->plocRadius;
+    L.buildBounds(boxes);
+    WideBVH W;
+    W.build(L);
+    if (n_nodes_out) *n_nodes_out = L.n ? W.nNodes : 0;
+    if (n_prims_out) *n_prims_out = L.n;
+    if (box6 && L.n) {
+        box6[0] = L.scene.lo.x; box6[1] = L.scene.lo.y; box6[2] = L.scene.lo.z;
+        box6[3] = L.scene.hi.x; box6[4] = L.scene.hi.y; box6[5] = L.scene.hi.z;
+    }
+    if (node_words && L.n) memcpy(node_words, W.words.data(), W.words.size() * 4);
+    if (prim_order && L.n) memcpy(prim_order, W.triOrder.data(), W.triOrder.size() * 4);
+    return 0;
+}
+
 PTC_API int ptc_get_wide_bvh(ptc_ctx *c, uint64_t *n_nodes_out, uint64_t *n_tris_out, uint32_t *node_words, uint32_t *tri_order) {
     if (!c) return 1;
     if (c->lbvh.n != c->tris.size() || c->lbvh.morton.empty()) {

@@ -61,6 +61,13 @@ WORKLOADS = [
     ("Instanced", dict(scale=0.004, texture_size=64), 160, 90, 8, 4),  # C4: alpha-tested foliage + directional light
     ("Cornell", {}, 96, 96, 16, 8),                                    # C1
 ]
+# Scenes whose paths bounce off glossy, finely textured surfaces many times.  Product and oracle draw the same random numbers, but a
+# sampled direction already differs in its last bits (sincos of libdevice vs glibc, test_bsdf_parity: 2e-4), a glossy lobe amplifies
+# that, and after two or three such bounces the two paths land on different texels / triangles: from then on they are two independent
+# samples of the same estimator (profiles/r2_atrium_parity_diag.log: 0.05 % of the pixels differ at depth 2, 7.5 % at depth 4, 17 % at
+# depth 9; the first-hit AOVs agree to 5e-5).  These configs are therefore held to the per-pixel limits at depth 2, where the paths
+# still coincide, and to STATISTICAL limits at their full depth with 16 times the samples.
+CHAOTIC = ("Atrium", "Fog")
 
 
 @pytest.mark.parametrize("scene,kw,w,h,spp,batch", WORKLOADS, ids=["C2-Atrium", "C3-Fog", "C5-persp", "C5-ortho", "C4-Instanced", "C1-Cornell"])
@@ -73,11 +80,40 @@ def test_workload_configs_match_oracle(capi, engine, scene, kw, w, h, spp, batch
         assert full["depth"] == 32 and rp.scene.volumes[0] >= 0 and rp.scene.exposure[2] > 0  # medium + depth of field are really on
     if kw.get("camera") == 1:
         assert rp.camera_type == capi.PTC_CAMERA_ORTHOGRAPHIC and rp.ortho_width > 0
-    # magnified procedural textures: the texture unit's 8-bit filter weights; foliage: alpha-tested silhouettes
-    loose = scene in ("Atrium", "Fog", "Instanced")
+    if scene in CHAOTIC:
+        rp.depth = 2
+        compare_with_oracle(capi, engine, rp)  # the strict limits of every other scene
+        return
+    loose = scene == "Instanced"  # alpha-tested silhouettes of magnified 64 x 64 leaf cards
     ra, rb, sa, sb = compare_with_oracle(capi, engine, rp, pixel_limit=0.03 if loose else 0.01, mean_limit=5e-3 if loose else 2e-3,
                                          aov_limit=0.03 if loose else 0.01)
     assert rb[..., :3].mean() > 1e-4
+
+
+@pytest.mark.parametrize("scene,kw", [("Atrium", dict(scale=0.1, texture_size=64)), ("Fog", dict(scale=0.05, texture_size=32))], ids=["C2-Atrium", "C3-Fog"])
+def test_deep_glossy_configs_match_oracle_statistically(capi, engine, scene, kw):
+    """full depth (9 / 32 with roulette), 128 spp at 64 x 36: means, block means and segment counts of two converging estimates"""
+    engine.build_scene(scene, **kw)
+    engine.set_render_info(width=64, height=36, samples=128, batch_size=16)
+    desc, rp = engine.scene_desc(), engine.render_params()
+    res = {}
+    for label, lib in (("cuda", capi.load_cuda()), ("oracle", oracle_loader.load_oracle())):
+        ctx = capi.Context(lib)
+        ctx.upload_scene(desc)
+        ctx.build_accel()
+        res[label] = (ctx.render(rp), ctx.stats())
+        ctx.close()
+    (ra, aa, na), sa = res["cuda"]
+    (rb, ab, nb), sb = res["oracle"]
+    assert np.isfinite(ra).all() and np.all(ra[..., 3] == 1.0)
+    # first-hit AOVs do not depend on the later bounces: per pixel
+    assert np.mean(np.abs(aa - ab).max(axis=-1) > 1e-3) < 0.01 and np.mean(np.abs(na - nb).max(axis=-1) > 1e-3) < 0.01
+    assert abs(sa["segments"] / sb["segments"] - 1) < 2e-3       # path lengths (roulette, misses) have the same distribution
+    assert abs(ra[..., :3].mean() / rb[..., :3].mean() - 1) < 0.01  # 295 k paths each: the means of two independent estimates agree to ~0.3 %
+    blocks = lambda x: x[..., :3].reshape(9, 4, 16, 4, 3).mean(axis=(1, 3, 4))  # noqa: E731  4 x 4 pixel block luminance
+    ba, bb = blocks(ra), blocks(rb)
+    rel = np.abs(ba - bb) / np.maximum(bb, 0.05 * bb.mean())
+    assert np.median(rel) < 0.05 and np.percentile(rel, 95) < 0.2, (float(np.median(rel)), float(np.percentile(rel, 95)))
 
 
 def test_orthographic_rays_are_parallel(capi, engine):
@@ -273,3 +309,119 @@ def test_one_process_per_gpu_communicator(capi, tmp_path):
     assert single.stats()["segments"] in (seg, seg // world)  # every rank reports the group's statistics or its own share
     assert np.allclose(a[..., :3], img[..., :3], rtol=1e-5, atol=1e-6) and np.all(img[..., 3] == 1.0)
     single.close()
+
+
+# ---------------------------------------------------------------- two-level acceleration structure (VulkanScene.cpp:306-381)
+def _instanced(engine, **kw):
+    engine.build_scene("Instanced", **kw)
+    return engine.scene_desc()
+
+
+def test_two_level_build_bit_exact(capi, engine):
+    """every tree of the two-level structure - one per mesh over object-space triangles, one over the instances' world boxes - equals the
+    oracle's restatement byte for byte: node words, primitive order, bounds"""
+    desc = _instanced(engine, texture_size=16, scale=0.01)
+    d = desc.contents
+    cu, orc = capi.Context(capi.load_cuda()), capi.Context(oracle_loader.load_oracle())
+    for ctx in (cu, orc):
+        ctx.upload_scene(desc)
+        ctx.set_accel_mode(capi.PTC_ACCEL_TWO_LEVEL)
+        ctx.build_accel()
+    assert cu.stats()["accel_levels"] == 2
+    seen_tris = 0
+    for level in [-1] + list(range(d.n_meshes)):
+        a, b = cu.get_accel_level(level), orc.get_accel_level(level)
+        assert a["n_prims"] == b["n_prims"] and a["n_nodes"] == b["n_nodes"], level
+        if a["n_prims"] == 0:
+            continue
+        assert np.array_equal(a["order"], b["order"]), level
+        assert np.array_equal(a["words"], b["words"]), "level %d: %d nodes differ" % (level, int(np.any(a["words"] != b["words"], axis=1).sum()))
+        assert np.array_equal(a["box"], b["box"]), level
+        assert sorted(a["order"]) == list(range(a["n_prims"]))
+        if level >= 0:
+            seen_tris += a["n_prims"]
+    assert cu.get_accel_level(-1)["n_prims"] == d.n_instances
+    used = {d.instances[i].mesh_index for i in range(d.n_instances)}
+    assert seen_tris == sum(d.meshes[m].tri_count for m in used)
+    with pytest.raises(RuntimeError, match="two levels"):
+        cu.get_wide_bvh()
+    cu.close()
+    orc.close()
+
+
+@pytest.mark.parametrize("scene,kw,box", [("Instanced", dict(texture_size=16, scale=0.01), 60.0), ("SharedComponents", {}, 60.0), ("Hierarchy", {}, 12.0)])
+def test_two_level_ray_sets_match_oracle(capi, engine, scene, kw, box):
+    """closest hits through instance transforms: ids identical to the oracle's world-space queries, |dt| <= 1e-4 max(1, t)"""
+    from test_gpu_parity import ray_set
+    engine.build_scene(scene, **kw)
+    desc = engine.scene_desc()
+    cu, orc = capi.Context(capi.load_cuda()), capi.Context(oracle_loader.load_oracle())
+    for ctx in (cu, orc):
+        ctx.upload_scene(desc)
+        ctx.set_accel_mode(capi.PTC_ACCEL_TWO_LEVEL)
+        ctx.build_accel()
+    rng = np.random.default_rng(21)
+    rays = np.concatenate([ray_set(rng, 30000, -box, box), ray_set(rng, 30000, -box, box, aim=(-box / 4, box / 4))])
+    ia, pa, ta, ua, va = cu.trace_closest(rays)
+    ib, pb, tb, ub, vb = orc.trace_closest(rays)
+    assert (ib >= 0).mean() > 0.1
+    bad = ~((ia == ib) & (pa == pb))
+    # object-space vs world-space intersection: a different rounding can flip the winner only on shared edges / coplanar overlaps
+    assert bad.mean() <= 2e-3, "id mismatches: %d" % int(bad.sum())
+    if bad.any():
+        assert np.all(np.abs(ta[bad] - tb[bad]) <= 1e-3 * np.maximum(1.0, tb[bad]))
+    hit = ~bad & (ib >= 0)
+    assert np.all(np.abs(ta[hit] - tb[hit]) <= 1e-4 * np.maximum(1.0, tb[hit]))
+    db = np.maximum(np.abs(ua[hit] - ub[hit]), np.abs(va[hit] - vb[hit]))
+    assert np.percentile(db, 99.9) <= 1e-3
+    # and the flat structure of the same scene answers the same
+    flat = capi.Context(capi.load_cuda())
+    flat.upload_scene(desc)
+    flat.set_accel_mode(capi.PTC_ACCEL_FLAT)
+    flat.build_accel()
+    assert flat.stats()["accel_levels"] == 1
+    ic, pc, tc, _, _ = flat.trace_closest(rays)
+    assert np.mean((ia != ic) | (pa != pc)) <= 2e-3
+    for c in (cu, orc, flat):
+        c.close()
+
+
+@pytest.mark.parametrize("scene,kw", [("Instanced", dict(texture_size=64, scale=0.004)), ("SharedComponents", {}), ("MeshLight", {}), ("Volume5", {}),
+                                      ("Transparency", {})])
+def test_two_level_render_matches_oracle(capi, engine, scene, kw):
+    """the whole pipeline (path rays, shadow chains incl. the all-hits foliage mode, probes, media) over the two-level structure"""
+    engine.build_scene(scene, **kw)
+    engine.set_render_info(width=128, height=96, samples=8, batch_size=4)
+    desc, rp = engine.scene_desc(), engine.render_params()
+    cu = capi.Context(capi.load_cuda())
+    cu.upload_scene(desc)
+    cu.set_accel_mode(capi.PTC_ACCEL_TWO_LEVEL)
+    cu.build_accel()
+    ra, aa, na = cu.render(rp)
+    sa = cu.stats()
+    assert sa["accel_levels"] == 2
+    cu.close()
+    orc = oracle_loader.oracle_context(engine)
+    rb, ab, nb = orc.render(rp)
+    sb = orc.stats()
+    orc.close()
+    loose = scene in ("Instanced", "Transparency")
+    d = np.abs(ra[..., :3] - rb[..., :3]).max(axis=-1)
+    assert np.mean(d > 1e-3 * np.maximum(1.0, rb[..., :3].max(axis=-1))) < (0.03 if loose else 0.01)
+    assert abs(ra[..., :3].mean() / rb[..., :3].mean() - 1) < (5e-3 if loose else 2e-3)
+    assert np.mean(np.abs(aa - ab).max(axis=-1) > 1e-3) < (0.03 if loose else 0.01) and np.mean(np.abs(na - nb).max(axis=-1) > 1e-3) < (0.03 if loose else 0.01)
+    assert abs(sa["segments"] - sb["segments"]) <= 2e-3 * sb["segments"] and np.all(ra[..., 3] == 1.0)
+
+
+def test_accel_mode_auto_picks_two_levels_for_heavy_instancing(capi, engine):
+    desc = _instanced(engine, texture_size=16, scale=0.12)  # ~5 M world triangles of a few unique meshes
+    cu = capi.Context(capi.load_cuda())
+    cu.upload_scene(desc)
+    cu.build_accel()
+    st = cu.stats()
+    assert st["n_triangles"] > 4 << 20 and st["accel_levels"] == 2 and st["traversal_bytes"] < 0.25 * st["n_triangles"] * 48
+    engine.build_scene("Atrium", texture_size=4, scale=0.3)
+    cu.upload_scene(engine.scene_desc())
+    cu.build_accel()
+    assert cu.stats()["accel_levels"] == 1
+    cu.close()

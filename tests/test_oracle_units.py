@@ -5,6 +5,8 @@ import ctypes as C
 import numpy as np
 import pytest
 
+from oracle import loader as oracle_loader
+
 
 @pytest.fixture(scope="module")
 def octx(capi, oracle_lib):
@@ -544,3 +546,28 @@ def test_power_heuristic_does_not_overflow_to_nan(capi, oracle_lib):
     rad = ctx.render(rp)[0]
     assert np.isfinite(rad).all()
     ctx.close()
+
+
+def test_two_level_restatement_is_consistent(capi):
+    """oracle side of ptc_get_accel_level: every tree is a permutation of its primitives, the instance tree has one entry per instance,
+    unused meshes are empty, and the top-level bounds contain every instance box"""
+    eng = capi.HostEngine()
+    eng.build_scene("Instanced", texture_size=8, scale=0.004)
+    d = eng.scene_desc().contents
+    ctx = capi.Context(oracle_loader.load_oracle())
+    ctx.upload_scene(eng.scene_desc())
+    ctx.build_accel()
+    top = ctx.get_accel_level(-1)
+    assert top["n_prims"] == d.n_instances and sorted(top["order"]) == list(range(d.n_instances)) and top["n_nodes"] >= 1
+    used = {d.instances[i].mesh_index for i in range(d.n_instances)}
+    for m in range(d.n_meshes):
+        lv = ctx.get_accel_level(m)
+        if m not in used:
+            assert lv["n_prims"] == 0
+            continue
+        assert lv["n_prims"] == d.meshes[m].tri_count and sorted(lv["order"]) == list(range(lv["n_prims"]))
+        assert np.all(lv["box"][:3] <= lv["box"][3:])
+    with pytest.raises(RuntimeError, match="no such level"):
+        ctx.get_accel_level(d.n_meshes)
+    ctx.close()
+    eng.close()

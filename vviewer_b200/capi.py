@@ -81,7 +81,7 @@ class ptc_stats(C.Structure):
                 ("probe_hops", u64), ("render_ms", C.c_double), ("trace_ms", C.c_double), ("shade_ms", C.c_double),
                 ("shadow_ms", C.c_double), ("build_ms", C.c_double), ("trace_launches", u64), ("kernel_launches", u64),
                 ("n_triangles", u64), ("n_bvh_nodes", u64), ("scene_bytes", u64), ("reserved", u64 * 4),
-                ("upload_bytes", u64), ("reduce_ms", C.c_double), ("bin_ms", C.c_double)]
+                ("upload_bytes", u64), ("reduce_ms", C.c_double), ("bin_ms", C.c_double), ("accel_levels", u64), ("traversal_bytes", u64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -98,9 +98,10 @@ PTC_FLAG_ENV_IMPORTANCE = 8
 PTC_FLAG_SAMPLER_PMJ = 16
 PTC_SAMPLER_HOOK_1D = 0x80000000
 PTC_HIERARCHY_LBVH, PTC_HIERARCHY_PLOC = 0, 1
+PTC_ACCEL_AUTO, PTC_ACCEL_FLAT, PTC_ACCEL_TWO_LEVEL = 0, 1, 2
 
 # every symbol include/ptc.h declares
-PTC_SYMBOLS = ["ptc_srgb_table", "ptc_set_sampler_tables", "ptc_create", "ptc_destroy", "ptc_device_count", "ptc_comm_unique_id", "ptc_comm_init_rank", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_set_build_options", "ptc_build_accel", "ptc_render",
+PTC_SYMBOLS = ["ptc_set_accel_mode", "ptc_get_accel_level", "ptc_srgb_table", "ptc_set_sampler_tables", "ptc_create", "ptc_destroy", "ptc_device_count", "ptc_comm_unique_id", "ptc_comm_init_rank", "ptc_last_error", "ptc_backend_name", "ptc_upload_scene", "ptc_set_build_options", "ptc_build_accel", "ptc_render",
                "ptc_render_device", "ptc_progress", "ptc_get_stats", "ptc_trace_closest", "ptc_get_lbvh", "ptc_get_wide_bvh", "ptc_bsdf_eval",
                "ptc_bsdf_sample", "ptc_sampler_points", "ptc_env_lookup", "ptc_env_sample", "ptc_env_pdf"]
 VH_SYMBOLS = ["vh_set_sequence_frame", "vh_set_output", "vh_write_image", "vh_set_devices", "vh_device_count", "vh_comm_unique_id", "vh_comm_init_rank", "vh_set_render_options", "vh_engine_create", "vh_engine_destroy", "vh_backend_ok", "vh_last_error", "vh_scene_list", "vh_build_scene",
@@ -120,6 +121,10 @@ def _declare_ptc(lib):
     lib.ptc_destroy.restype = None
     lib.ptc_last_error.argtypes = [vp]
     lib.ptc_last_error.restype = C.c_char_p
+    lib.ptc_set_accel_mode.argtypes = [vp, u32]
+    lib.ptc_set_accel_mode.restype = C.c_int
+    lib.ptc_get_accel_level.argtypes = [vp, C.c_int32, C.POINTER(u64), C.POINTER(u64), vp, vp, vp]
+    lib.ptc_get_accel_level.restype = C.c_int
     lib.ptc_srgb_table.argtypes = [vp, vp]
     lib.ptc_srgb_table.restype = C.c_int
     lib.ptc_set_sampler_tables.argtypes = [vp, vp, u32, u32, vp, u32, u32]
@@ -333,6 +338,19 @@ class Context:
 
     def set_build_options(self, hierarchy, ploc_radius=0):
         self._check(self.lib.ptc_set_build_options(self.ctx, hierarchy, ploc_radius), "ptc_set_build_options")
+
+    def set_accel_mode(self, mode):
+        self._check(self.lib.ptc_set_accel_mode(self.ctx, int(mode)), "ptc_set_accel_mode")
+
+    def get_accel_level(self, level):
+        """two-level structure: level -1 = instance tree, m >= 0 = tree of mesh m"""
+        nn, npr = u64(), u64()
+        box = np.zeros(6, np.float32)
+        self._check(self.lib.ptc_get_accel_level(self.ctx, int(level), C.byref(nn), C.byref(npr), None, None, np_ptr(box)), "ptc_get_accel_level")
+        words = np.zeros((max(nn.value, 1), 20), np.uint32)
+        order = np.zeros(max(npr.value, 1), np.uint32)
+        self._check(self.lib.ptc_get_accel_level(self.ctx, int(level), C.byref(nn), C.byref(npr), np_ptr(words), np_ptr(order), None), "ptc_get_accel_level")
+        return {"n_nodes": nn.value, "n_prims": npr.value, "words": words[:nn.value], "order": order[:npr.value], "box": box}
 
     def build_accel(self, hierarchy=None, ploc_radius=0):
         if hierarchy is not None:

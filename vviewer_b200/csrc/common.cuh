@@ -55,7 +55,7 @@ struct DInstance {
     uint32_t firstVertex; /* into the vertex pool */
     uint32_t numTriangles;
     uint32_t firstWorldTri; /* prefix of world triangles */
-    uint32_t pad;
+    uint32_t mesh;          /* index of the instance's mesh (two-level acceleration structure: which bottom-level tree) */
 };
 
 #define PTC_MAX_EMISSIVE_BOXES 16
@@ -81,6 +81,12 @@ struct DScene {
     uint32_t nTris;
     uint32_t nWideNodes;
     uint32_t prmtMagic; /* 0x47000000, see traverse.cuh::byteToFloat */
+    /* two-level structure (lbvh.cuh::TwoLevel; twoLevel != 0): bvhNodes starts with the top-level tree over the instances' world boxes
+     * (node 0 = its root), followed by one bottom-level tree per mesh over object-space triangles; tris / shading hold the meshes'
+     * triangles in bottom-level order; a top-level leaf entry p is instance tlasInst[p]; meshRoot[m] = root node of mesh m's tree */
+    uint32_t twoLevel;
+    const uint32_t *tlasInst;
+    const uint32_t *meshRoot;
     /* scene-level switches that let whole ray types be skipped without changing any result */
     uint32_t anyEmissive;    /* some instanced material can pass the probe's emissive test */
     /* world boxes (lo, hi pairs) of the instances whose material can pass that test, when there are at most PTC_MAX_EMISSIVE_BOXES of

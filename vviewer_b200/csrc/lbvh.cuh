@@ -33,6 +33,8 @@
 #include "radix.cuh"
 #include <cooperative_groups.h>
 #include <chrono>
+#include <memory>
+#include <vector>
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
@@ -112,6 +114,77 @@ __global__ void k_flatten(const ptc_vertex *__restrict__ vertices, const uint32_
         atomicMax(&sceneBounds[4], floatFlip(hi.y));
         atomicMax(&sceneBounds[5], floatFlip(hi.z));
     }
+}
+
+/* warp reduce of a box, then one atomic per warp and component into the order-preserving scene bounds */
+PTC_D void boundsAtomic(float3 lo, float3 hi, uint32_t *__restrict__ sceneBounds) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o));
+        lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o));
+        hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o));
+        hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo.x <= hi.x) {
+        atomicMin(&sceneBounds[0], floatFlip(lo.x));
+        atomicMin(&sceneBounds[1], floatFlip(lo.y));
+        atomicMin(&sceneBounds[2], floatFlip(lo.z));
+        atomicMax(&sceneBounds[3], floatFlip(hi.x));
+        atomicMax(&sceneBounds[4], floatFlip(hi.y));
+        atomicMax(&sceneBounds[5], floatFlip(hi.z));
+    }
+}
+
+/* bottom level of the two-level structure: the triangles of ONE mesh in object space, (v0, e1 = v1 - v0, e2 = v2 - v0) + bounds */
+__global__ void k_mesh_tris(const ptc_vertex *__restrict__ vertices, const uint32_t *__restrict__ indices, uint32_t firstIndex, uint32_t firstVertex,
+                            uint32_t nTris, float4 *__restrict__ triOut, float4 *__restrict__ boundsLo, float4 *__restrict__ boundsHi,
+                            uint32_t *__restrict__ sceneBounds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 lo = f3(3.4e38f), hi = f3(-3.4e38f);
+    if (i < nTris) {
+        const uint32_t *ind = indices + firstIndex + 3 * (size_t)i;
+        float3 p[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const ptc_vertex &v = vertices[firstVertex + ind[k]];
+            p[k] = f3(v.position[0], v.position[1], v.position[2]);
+        }
+        const float3 e1 = f3(__fsub_rn(p[1].x, p[0].x), __fsub_rn(p[1].y, p[0].y), __fsub_rn(p[1].z, p[0].z));
+        const float3 e2 = f3(__fsub_rn(p[2].x, p[0].x), __fsub_rn(p[2].y, p[0].y), __fsub_rn(p[2].z, p[0].z));
+        triOut[3 * (size_t)i + 0] = make_float4(p[0].x, p[0].y, p[0].z, 0.0f);
+        triOut[3 * (size_t)i + 1] = make_float4(e1.x, e1.y, e1.z, __uint_as_float(i));
+        triOut[3 * (size_t)i + 2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+        const float3 q1 = f3(__fadd_rn(p[0].x, e1.x), __fadd_rn(p[0].y, e1.y), __fadd_rn(p[0].z, e1.z));
+        const float3 q2 = f3(__fadd_rn(p[0].x, e2.x), __fadd_rn(p[0].y, e2.y), __fadd_rn(p[0].z, e2.z));
+        lo = fmin3(p[0], fmin3(q1, q2));
+        hi = fmax3(p[0], fmax3(q1, q2));
+        boundsLo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+        boundsHi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    }
+    boundsAtomic(lo, hi, sceneBounds);
+}
+
+/* top level: the world box of every instance = bounds of the 8 transformed corners of its mesh's object-space box (corner order
+ * x fastest, then y, then z; same fixed operation order as the flatten) */
+__global__ void k_instance_boxes(const DInstance *__restrict__ instances, uint32_t nInstances, const float4 *__restrict__ meshLo, const float4 *__restrict__ meshHi,
+                                 float4 *__restrict__ boundsLo, float4 *__restrict__ boundsHi, uint32_t *__restrict__ sceneBounds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float3 lo = f3(3.4e38f), hi = f3(-3.4e38f);
+    if (i < nInstances) {
+        const DInstance &I = instances[i];
+        const float4 ml = meshLo[I.mesh], mh = meshHi[I.mesh];
+        for (int corner = 0; corner < 8; corner++) {
+            const float x = (corner & 1) ? mh.x : ml.x, y = (corner & 2) ? mh.y : ml.y, z = (corner & 4) ? mh.z : ml.z;
+            const float3 w = f3(xformRow(I.m, x, y, z), xformRow(I.m + 4, x, y, z), xformRow(I.m + 8, x, y, z));
+            lo = fmin3(lo, w);
+            hi = fmax3(hi, w);
+        }
+        boundsLo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
+        boundsHi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    }
+    boundsAtomic(lo, hi, sceneBounds);
 }
 
 PTC_HD uint64_t expandBits21(uint64_t v) {
@@ -783,26 +856,14 @@ struct Build {
         return sms * std::min(perSm, capPerSm);
     }
 
-    /* returns the number of kernel launches */
-    int run(const ptc_vertex *vertices, const uint32_t *indices, const DInstance *instances, uint32_t nInstances, uint32_t nTris,
-            cudaStream_t s) {
-        n = nTris;
+    /* phase 1: buffers for n primitives, cleared state */
+    void begin(uint32_t nPrims, bool needTris, cudaStream_t s) {
+        n = nPrims;
         nWide = wideLevels = 0;
         hostSyncs = 0;
-        if (n == 0) return 0;
-        const bool verbose = getenv("PTC_VERBOSE") != nullptr;
-        auto now = [&] {
-            if (verbose) cudaStreamSynchronize(s);
-            return std::chrono::steady_clock::now();
-        };
-        auto msSince = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
-            return std::chrono::duration<double, std::milli>(b - a).count();
-        };
-        const auto tStart = now();
-        const int B = 256;
-        const uint32_t G = (n + B - 1) / B;
+        if (n == 0) return;
         size_t nn = 2 * (size_t)n - 1;
-        trisUnsorted.alloc(3 * (size_t)n);
+        if (needTris) trisUnsorted.alloc(3 * (size_t)n);
         triLo.alloc(n);
         triHi.alloc(n);
         keys.alloc(n);
@@ -828,9 +889,15 @@ struct Build {
         CUDA_TRY(cudaMemsetAsync(right.p, 0xff, nn * sizeof(int32_t), s));
         CUDA_TRY(cudaMemsetAsync(arrivals.p, 0, n * sizeof(uint32_t), s));
         CUDA_TRY(cudaMemsetAsync(bigNodes.p, 0, sizeof(uint32_t), s));
+    }
+
+    /* phase 2 (after a prepare kernel has filled triLo / triHi / sceneBounds): Morton codes, sort, hierarchy, collapse.  Leaves the wide
+     * nodes in `wide` (nWide of them, indices relative to this tree) and the primitive order in triMap / order.  Two host round trips. */
+    int buildFromBounds(cudaStream_t s) {
+        if (n == 0) return 0;
+        const int B = 256;
+        const uint32_t G = (n + B - 1) / B;
         int launches = 0;
-        k_flatten<<<G, B, 0, s>>>(vertices, indices, instances, nInstances, n, trisUnsorted.p, triLo.p, triHi.p, sceneBounds.p);
-        launches++;
         bits = mortonBitsPerAxis(n);
         k_morton<<<G, B, 0, s>>>(triLo.p, triHi.p, sceneBounds.p, n, bits, keys.p, ids.p);
         launches++;
@@ -845,7 +912,6 @@ struct Build {
             kA = keysSorted.p, kB = keys.p, vA = order.p, vB = ids.p;
         }
         radix::sortPairs(kA, vA, kB, vB, radixTable.p, n, endBit, s, &launches);
-        const auto tSorted = now();
         binaryRoot = 0;
         plocRounds = 0;
         const uint32_t blockSumEntries = 148u * 16u;
@@ -879,8 +945,6 @@ struct Build {
             launches++;
             binaryRoot = (int32_t)(n - 2);
         }
-
-        const auto tHierarchy = now();
         /* ---- first host round trip: the bound of the wide node count sizes the collapse buffers (and the PLOC verdict rides along) */
         uint32_t big = 0;
         PlocResult pr{};
@@ -919,6 +983,29 @@ struct Build {
         if (wr.nTris != n) throw CudaError{"wide BVH collapse lost triangles"};
         nWide = wr.nWide;
         wideLevels = wr.levels;
+        return launches;
+    }
+
+    /* the single-level structure over world-space triangles; returns the number of kernel launches */
+    int run(const ptc_vertex *vertices, const uint32_t *indices, const DInstance *instances, uint32_t nInstances, uint32_t nTris,
+            cudaStream_t s) {
+        const bool verbose = getenv("PTC_VERBOSE") != nullptr;
+        auto now = [&] {
+            if (verbose) cudaStreamSynchronize(s);
+            return std::chrono::steady_clock::now();
+        };
+        auto msSince = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        const auto tStart = now();
+        begin(nTris, true, s);
+        if (n == 0) return 0;
+        const int B = 256;
+        const uint32_t G = (n + B - 1) / B;
+        int launches = 0;
+        k_flatten<<<G, B, 0, s>>>(vertices, indices, instances, nInstances, n, trisUnsorted.p, triLo.p, triHi.p, sceneBounds.p);
+        launches++;
+        launches += buildFromBounds(s);
         const auto tCollapsed = now();
         trav.alloc(5 * (size_t)nWide + 3 * (size_t)n);
         CUDA_TRY(cudaMemcpyAsync(trav.p, wide.p, (size_t)nWide * 80, cudaMemcpyDeviceToDevice, s));
@@ -930,10 +1017,188 @@ struct Build {
         CUDA_TRY(cudaGetLastError());
         if (verbose) {
             const auto tEnd = now();
-            fprintf(stderr, "[ptc] build: %u triangles | alloc+flatten+morton+sort %.2f ms | hierarchy %.2f ms (%s, %u rounds) | collapse %.2f ms (%u levels, %u wide nodes) | gather %.2f ms | %d host syncs\n",
-                    n, msSince(tStart, tSorted), msSince(tSorted, tHierarchy), hierarchy == PTC_HIERARCHY_PLOC ? "PLOC" : "Karras", plocRounds,
-                    msSince(tHierarchy, tCollapsed), wideLevels, nWide, msSince(tCollapsed, tEnd), hostSyncs);
+            fprintf(stderr, "[ptc] build: %u triangles | flatten + morton + sort + hierarchy (%s, %u rounds) + collapse (%u levels, %u wide nodes) %.2f ms | gather %.2f ms | %d host syncs\n",
+                    n, hierarchy == PTC_HIERARCHY_PLOC ? "PLOC" : "Karras", plocRounds, wideLevels, nWide, msSince(tStart, tCollapsed), msSince(tCollapsed, tEnd), hostSyncs);
         }
+        return launches;
+    }
+};
+
+/* ------------------------------------------------------------------ two-level structure (VulkanScene.cpp:306-381: one TLAS over instances with
+ * 3x4 transforms, one BLAS per mesh in object space).  Chosen for heavily instanced scenes: C4's 1 250 instances of 24 meshes are
+ * 42.5 M world triangles (2.5 GB of traversal data that no cache holds) but 0.6 M unique ones (30 MB, L2 resident).
+ *   bottom level  per mesh: k_mesh_tris -> the same Morton / sort / hierarchy / collapse as above, over object-space triangles
+ *   top level     k_instance_boxes (world box of every instance from its mesh's box) -> the same pipeline over the boxes; a leaf entry
+ *                 is an instance
+ *   assembly      one traversal buffer: [top-level nodes][nodes of mesh 0][mesh 1]...[triangles of mesh 0][mesh 1]...; child and triangle
+ *                 indices of the bottom-level nodes are rebased to absolute positions (k_rebase_nodes), so the traversal needs no
+ *                 per-tree offsets
+ * Every tree is bit-exact against the oracle's restatement (oracle/accel.hpp, ptc_get_accel_level). */
+__global__ void k_rebase_nodes(uint4 *__restrict__ nodes, uint32_t count, uint32_t nodeBase, uint32_t triBase) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    uint4 w1 = nodes[5 * (size_t)k + 1];
+    w1.x += nodeBase;
+    w1.y += triBase;
+    nodes[5 * (size_t)k + 1] = w1;
+}
+/* bottom-level triangles in tree order: (v0, .) (e1, primitive) (e2, .) */
+__global__ void k_gather_mesh_tris(uint32_t n, const uint32_t *__restrict__ triMap, const uint32_t *__restrict__ order, const float4 *__restrict__ in,
+                                   float4 *__restrict__ out, uint32_t *__restrict__ wideOrder) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t t = order[triMap[k]];
+    out[3 * (size_t)k + 0] = in[3 * (size_t)t + 0];
+    out[3 * (size_t)k + 1] = in[3 * (size_t)t + 1];
+    out[3 * (size_t)k + 2] = in[3 * (size_t)t + 2];
+    wideOrder[k] = t;
+}
+/* shading records of a mesh's triangles in tree order (same 144 bytes as k_gather_shading; the instance word is not used: the hit
+ * carries the instance) */
+__global__ void k_gather_mesh_shading(uint32_t n, const uint32_t *__restrict__ wideOrder, const ptc_vertex *__restrict__ vertices,
+                                      const uint32_t *__restrict__ indices, uint32_t firstIndex, uint32_t firstVertex, float4 *__restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t prim = wideOrder[k];
+    const uint32_t *ind = indices + firstIndex + 3 * (size_t)prim;
+    const ptc_vertex &a = vertices[firstVertex + ind[0]], &b = vertices[firstVertex + ind[1]], &c = vertices[firstVertex + ind[2]];
+    float4 *r = out + 9 * (size_t)k;
+    r[0] = make_float4(a.position[0], a.position[1], a.position[2], a.uv[0]);
+    r[1] = make_float4(b.position[0], b.position[1], b.position[2], a.uv[1]);
+    r[2] = make_float4(c.position[0], c.position[1], c.position[2], b.uv[0]);
+    r[3] = make_float4(a.normal[0], a.normal[1], a.normal[2], b.uv[1]);
+    r[4] = make_float4(b.normal[0], b.normal[1], b.normal[2], c.uv[0]);
+    r[5] = make_float4(c.normal[0], c.normal[1], c.normal[2], c.uv[1]);
+    r[6] = make_float4(a.tangent[0], a.tangent[1], a.tangent[2], __uint_as_float(0xffffffffu));
+    r[7] = make_float4(b.tangent[0], b.tangent[1], b.tangent[2], __uint_as_float(prim));
+    r[8] = make_float4(c.tangent[0], c.tangent[1], c.tangent[2], 0.0f);
+}
+__global__ void k_tlas_instances(uint32_t n, const uint32_t *__restrict__ triMap, const uint32_t *__restrict__ order, uint32_t *__restrict__ out) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = order[triMap[k]];
+}
+
+struct MeshRange { /* one mesh of the scene description */
+    uint32_t firstIndex, triCount, firstVertex;
+};
+
+struct TwoLevel {
+    struct Tree { /* one built tree, kept until assembly (and for the parity dump) */
+        DBuf<uint4> nodes;      /* relative indices */
+        DBuf<float4> tris;      /* bottom level only */
+        DBuf<float4> shading;   /* bottom level only */
+        DBuf<uint32_t> order;   /* tree position -> primitive (triangle of the mesh / instance) */
+        uint32_t nNodes = 0, nPrims = 0, nodeBase = 0, triBase = 0;
+        float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    };
+    Build work; /* scratch of every tree build */
+    std::vector<std::unique_ptr<Tree>> blas;
+    Tree tlas;
+    DBuf<float4> trav, shading, meshLo, meshHi;
+    DBuf<uint32_t> tlasInst, meshRoot;
+    uint32_t nNodes = 0, nTris = 0;
+    int hostSyncs = 0;
+
+    size_t traversalBytes() const { return (size_t)nNodes * 80 + (size_t)nTris * 48; }
+    size_t bytes() const { return trav.bytes() + shading.bytes() + tlasInst.bytes() + meshRoot.bytes() + work.bytes(); }
+    const float4 *nodes() const { return trav.p; }
+    const float4 *tris() const { return trav.p ? trav.p + 5 * (size_t)nNodes : nullptr; }
+
+    void keep(Tree &t, bool bottom, cudaStream_t s) {
+        t.nNodes = work.nWide;
+        t.nPrims = work.n;
+        t.nodes.alloc(5 * (size_t)std::max(1u, t.nNodes));
+        CUDA_TRY(cudaMemcpyAsync(t.nodes.p, work.wide.p, (size_t)t.nNodes * 80, cudaMemcpyDeviceToDevice, s));
+        t.order.alloc(std::max(1u, t.nPrims));
+        uint32_t sb[6];
+        CUDA_TRY(cudaMemcpyAsync(sb, work.sceneBounds.p, sizeof(sb), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        for (int a = 0; a < 3; a++) t.lo[a] = floatUnflip(sb[a]), t.hi[a] = floatUnflip(sb[3 + a]);
+        (void)bottom;
+    }
+
+    int run(const ptc_vertex *vertices, const uint32_t *indices, const DInstance *instances, uint32_t nInstances, const std::vector<MeshRange> &meshes,
+            uint32_t hierarchy, uint32_t plocRadius, cudaStream_t s) {
+        const int B = 256;
+        int launches = 0;
+        hostSyncs = 0;
+        work.hierarchy = hierarchy;
+        work.plocRadius = plocRadius;
+        blas.clear();
+        std::vector<float4> hLo(meshes.size()), hHi(meshes.size());
+        uint32_t nodeTotal = 0, triTotal = 0;
+        /* ---- bottom level */
+        for (size_t m = 0; m < meshes.size(); m++) {
+            blas.emplace_back(new Tree());
+            Tree &t = *blas.back();
+            const MeshRange &mr = meshes[m];
+            work.begin(mr.triCount, true, s);
+            if (mr.triCount == 0) {
+                hLo[m] = make_float4(0, 0, 0, 0), hHi[m] = make_float4(0, 0, 0, 0);
+                continue;
+            }
+            const uint32_t G = (mr.triCount + B - 1) / B;
+            k_mesh_tris<<<G, B, 0, s>>>(vertices, indices, mr.firstIndex, mr.firstVertex, mr.triCount, work.trisUnsorted.p, work.triLo.p, work.triHi.p, work.sceneBounds.p);
+            launches += 1 + work.buildFromBounds(s);
+            keep(t, true, s);
+            t.tris.alloc(3 * (size_t)t.nPrims);
+            k_gather_mesh_tris<<<G, B, 0, s>>>(t.nPrims, work.triMap.p, work.order.p, work.trisUnsorted.p, t.tris.p, t.order.p);
+            t.shading.alloc(9 * (size_t)t.nPrims);
+            k_gather_mesh_shading<<<G, B, 0, s>>>(t.nPrims, t.order.p, vertices, indices, mr.firstIndex, mr.firstVertex, t.shading.p);
+            launches += 2;
+            hostSyncs += work.hostSyncs + 1;
+            hLo[m] = make_float4(t.lo[0], t.lo[1], t.lo[2], 0.0f);
+            hHi[m] = make_float4(t.hi[0], t.hi[1], t.hi[2], 0.0f);
+            nodeTotal += t.nNodes;
+            triTotal += t.nPrims;
+        }
+        /* ---- top level over the instances' world boxes */
+        meshLo.upload(hLo.data(), hLo.size(), s);
+        meshHi.upload(hHi.data(), hHi.size(), s);
+        work.begin(nInstances, false, s);
+        if (nInstances) {
+            k_instance_boxes<<<(nInstances + B - 1) / B, B, 0, s>>>(instances, nInstances, meshLo.p, meshHi.p, work.triLo.p, work.triHi.p, work.sceneBounds.p);
+            launches += 1 + work.buildFromBounds(s);
+            keep(tlas, false, s);
+            k_tlas_instances<<<(nInstances + B - 1) / B, B, 0, s>>>(nInstances, work.triMap.p, work.order.p, tlas.order.p);
+            launches++;
+            hostSyncs += work.hostSyncs + 1;
+        } else {
+            tlas.nNodes = tlas.nPrims = 0;
+        }
+        /* ---- assembly */
+        nNodes = tlas.nNodes + nodeTotal;
+        nTris = triTotal;
+        trav.alloc(std::max<size_t>(1, 5 * (size_t)nNodes + 3 * (size_t)nTris));
+        shading.alloc(std::max<size_t>(1, 9 * (size_t)nTris));
+        tlasInst.alloc(std::max(1u, nInstances));
+        if (tlas.nNodes) CUDA_TRY(cudaMemcpyAsync(trav.p, tlas.nodes.p, (size_t)tlas.nNodes * 80, cudaMemcpyDeviceToDevice, s));
+        if (nInstances) CUDA_TRY(cudaMemcpyAsync(tlasInst.p, tlas.order.p, (size_t)nInstances * 4, cudaMemcpyDeviceToDevice, s));
+        std::vector<uint32_t> roots(std::max<size_t>(1, meshes.size()), 0u);
+        uint32_t nodeBase = tlas.nNodes, triBase = 0;
+        for (size_t m = 0; m < meshes.size(); m++) {
+            Tree &t = *blas[m];
+            t.nodeBase = nodeBase;
+            t.triBase = triBase;
+            roots[m] = nodeBase;
+            if (t.nNodes) {
+                float4 *dstNodes = trav.p + 5 * (size_t)nodeBase;
+                CUDA_TRY(cudaMemcpyAsync(dstNodes, t.nodes.p, (size_t)t.nNodes * 80, cudaMemcpyDeviceToDevice, s));
+                k_rebase_nodes<<<(t.nNodes + B - 1) / B, B, 0, s>>>((uint4 *)dstNodes, t.nNodes, nodeBase, triBase);
+                CUDA_TRY(cudaMemcpyAsync(trav.p + 5 * (size_t)nNodes + 3 * (size_t)triBase, t.tris.p, (size_t)t.nPrims * 48, cudaMemcpyDeviceToDevice, s));
+                CUDA_TRY(cudaMemcpyAsync(shading.p + 9 * (size_t)triBase, t.shading.p, (size_t)t.nPrims * 144, cudaMemcpyDeviceToDevice, s));
+                launches++;
+            }
+            nodeBase += t.nNodes;
+            triBase += t.nPrims;
+        }
+        meshRoot.upload(roots.data(), roots.size(), s);
+        CUDA_TRY(cudaStreamSynchronize(s)); /* the host vectors die here */
+        hostSyncs++;
+        CUDA_TRY(cudaGetLastError());
+        if (getenv("PTC_VERBOSE"))
+            fprintf(stderr, "[ptc] two-level build: %zu meshes (%u triangles, %u nodes), %u instances (%u top-level nodes), traversal set %.1f MB, %d host syncs\n",
+                    meshes.size(), nTris, nodeTotal, nInstances, tlas.nNodes, traversalBytes() / 1e6, hostSyncs);
         return launches;
     }
 };

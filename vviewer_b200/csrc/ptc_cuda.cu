@@ -66,13 +66,21 @@ struct Dev {
     bool anyEmissive = false, anyTransparent = false, anyVolumeChange = false;
     bool sceneUploaded = false, accelBuilt = false;
     lbvh::Build accel;
+    /* two-level alternative (one tree per mesh + one over the instances), for heavily instanced scenes */
+    lbvh::TwoLevel accel2;
+    std::vector<lbvh::MeshRange> meshes; /* of the uploaded scene */
+    uint64_t uniqueTris = 0;             /* triangles of the meshes that are instanced at least once */
+    uint32_t accelMode = PTC_ACCEL_AUTO;
+    bool twoLevel = false;               /* what the last build produced */
+    size_t travBytes() const { return twoLevel ? accel2.traversalBytes() : (accel.n ? accel.traversalBytes() : 0); }
+    const void *travBase() const { return twoLevel ? (const void *)accel2.trav.p : (const void *)accel.trav.p; }
 
     /* render state */
     DBuf<float4> acc; /* the three accumulation targets (radiance, albedo, normal), contiguous: ONE ncclReduce sums them */
     /* two wavefronts in flight (see renderImpl): each has its own path state, queues, counters and stream */
     struct WaveBufs {
         DBuf<float4> orgRng, dirFlags, beta, radiance, hit, aovA, aovN, shOrg, shDir, shContrib, prBeta;
-        DBuf<uint32_t> queue0, queue1, qShadow, qProbe, counters;
+        DBuf<uint32_t> queue0, queue1, qShadow, qProbe, counters, hitInst;
         DBuf<uint16_t> qKey;
         DBuf<unsigned long long> stats;
         size_t capacity = 0;
@@ -172,7 +180,7 @@ DScene makeDScene(Dev *c) {
     s.lightInstances = c->lightInstances.p;
     s.texClasses = c->texClassTable.p;
     s.texRef = c->texRef.p;
-    s.shading = c->accel.shading.p;
+    s.shading = c->twoLevel ? c->accel2.shading.p : c->accel.shading.p;
     s.cubemap = c->cubeTex;
     s.envCdfV = c->cubeTex ? c->envCdfV.p : nullptr;
     s.envCdfU = c->cubeTex ? c->envCdfU.p : nullptr;
@@ -181,10 +189,22 @@ DScene makeDScene(Dev *c) {
     s.nLightInstances = c->nLightInstances;
     s.nTextures = c->nTextures;
     s.hasCubemap = c->cubeTex ? 1u : 0u;
-    s.bvhNodes = c->accel.wideNodes();
-    s.tris = c->accel.sortedTris();
-    s.nTris = c->accelBuilt ? c->accel.n : 0u;
-    s.nWideNodes = c->accel.nWide;
+    s.twoLevel = c->twoLevel ? 1u : 0u;
+    if (c->twoLevel) {
+        s.bvhNodes = c->accel2.nodes();
+        s.tris = c->accel2.tris();
+        s.nTris = (c->accelBuilt && c->accel2.tlas.nNodes) ? c->accel2.nTris : 0u; /* 0 = nothing to hit */
+        s.nWideNodes = c->accel2.nNodes;
+        s.tlasInst = c->accel2.tlasInst.p;
+        s.meshRoot = c->accel2.meshRoot.p;
+    } else {
+        s.bvhNodes = c->accel.wideNodes();
+        s.tris = c->accel.sortedTris();
+        s.nTris = c->accelBuilt ? c->accel.n : 0u;
+        s.nWideNodes = c->accel.nWide;
+        s.tlasInst = nullptr;
+        s.meshRoot = nullptr;
+    }
     s.prmtMagic = 0x47000000u;
     s.anyEmissive = c->anyEmissive ? 1u : 0u;
     s.emissiveBoxes = c->emissiveBoxes.p;
@@ -333,7 +353,7 @@ void createCubemap(Dev *c, const ptc_env &env) {
 void setTraversalWindow(Dev *c) {
     cudaStreamAttrValue attr{};
     cudaCtxResetPersistingL2Cache(); /* lines of a previous scene */
-    const size_t bytes = c->accel.n ? c->accel.traversalBytes() : 0;
+    const size_t bytes = c->travBytes();
     if (bytes == 0 || c->persistMax == 0 || c->windowMax == 0) {
         attr.accessPolicyWindow.num_bytes = 0;
         cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
@@ -343,7 +363,7 @@ void setTraversalWindow(Dev *c) {
     const size_t carve = std::min(c->persistMax, bytes);
     CUDA_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
     const size_t window = std::min(bytes, c->windowMax);
-    attr.accessPolicyWindow.base_ptr = (void *)c->accel.trav.p;
+    attr.accessPolicyWindow.base_ptr = const_cast<void *>(c->travBase());
     attr.accessPolicyWindow.num_bytes = window;
     attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)window);
     attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -354,6 +374,7 @@ void setTraversalWindow(Dev *c) {
 
 void ensureWave(Dev *c, int k, size_t slots, uint32_t depth) {
     Dev::WaveBufs &w = c->wave[k];
+    if (c->twoLevel && w.hitInst.n < std::max(slots, w.capacity)) w.hitInst.alloc(std::max(slots, w.capacity));
     if (slots > w.capacity) {
         w.orgRng.alloc(slots);
         w.dirFlags.alloc(slots);
@@ -371,6 +392,7 @@ void ensureWave(Dev *c, int k, size_t slots, uint32_t depth) {
         w.qShadow.alloc(slots);
         w.qProbe.alloc(slots);
         w.qKey.alloc(slots);
+        if (c->twoLevel) w.hitInst.alloc(slots);
         w.capacity = slots;
     }
     w.counters.alloc((size_t)(depth + 2) * wf::CNT_STRIDE);
@@ -396,6 +418,7 @@ wf::Wave makeWave(Dev *c, int k) {
     w.qShadow = b.qShadow.p;
     w.qProbe = b.qProbe.p;
     w.qKey = b.qKey.p;
+    w.hitInst = b.hitInst.p;
     w.counters = b.counters.p;
     w.stats = b.stats.p;
     return w;
@@ -494,7 +517,7 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
     rc.flags = rp->flags;
     rc.nPixLocal = nPixLocal;
     rc.pixmap = pixmapPtr;
-    rc.binMode = c->accel.n > 0 ? c->binMode : 0u;
+    rc.binMode = c->nWorldTris > 0 ? c->binMode : 0u;
     for (int a = 0; a < 3; a++) {
         rc.binLo[a] = c->sceneLo[a];
         const float ext = c->sceneHi[a] - c->sceneLo[a];
@@ -512,7 +535,9 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
     const int capTrace = overlap ? c->overlapTrace : 0, capShade = overlap ? c->overlapShade : 0;
     using ExtendFn = void (*)(wf::Wave, const DScene, uint32_t, wf::ExtendTune);
     const bool mediaInScene = c->anyVolumeChange || rp->scene.volumes[0] != -1.0f; /* = hasVolumes below: k_shade<*, true> writes the next tmax */
-    const ExtendFn extendFn = mediaInScene ? (ExtendFn)wf::k_extend<true> : (ExtendFn)wf::k_extend<false>;
+    const bool TL = c->twoLevel;
+    const ExtendFn extendFn = mediaInScene ? (TL ? (ExtendFn)wf::k_extend<true, true> : (ExtendFn)wf::k_extend<true, false>)
+                                           : (TL ? (ExtendFn)wf::k_extend<false, true> : (ExtendFn)wf::k_extend<false, false>);
     const int gridExtend = residentGrid((const void *)extendFn, TRV_BLOCK, capTrace);
     /* k_shade specialisation (wavefront.cuh): lights in the pick / media reachable */
     const bool hasLights = rc.totalLights > 0, hasVolumes = c->anyVolumeChange || rp->scene.volumes[0] != -1.0f;
@@ -522,9 +547,11 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
                                       : (hasVolumes ? (ShadeFn)wf::k_shade<false, true> : (ShadeFn)wf::k_shade<false, false>);
     const int gridShade = residentGrid((const void *)shadeFn, 128, capShade);
     using ChainFn = void (*)(wf::Wave, const DScene, const wf::RenderConst, uint32_t, wf::ExtendTune);
-    const ChainFn shadowFn = c->anyTransparent ? (ChainFn)wf::k_shadow<false> : (ChainFn)wf::k_shadow<true>;
+    const ChainFn shadowFn = c->anyTransparent ? (TL ? (ChainFn)wf::k_shadow<false, true> : (ChainFn)wf::k_shadow<false, false>)
+                                               : (TL ? (ChainFn)wf::k_shadow<true, true> : (ChainFn)wf::k_shadow<true, false>);
+    const ChainFn probeFn = TL ? (ChainFn)wf::k_probe<true> : (ChainFn)wf::k_probe<false>;
     const int gridShadow = residentGrid((const void *)shadowFn, TRV_BLOCK, capTrace);
-    const int gridProbe = residentGrid((const void *)wf::k_probe, TRV_BLOCK, capTrace);
+    const int gridProbe = residentGrid((const void *)probeFn, TRV_BLOCK, capTrace);
     uint64_t launches = 0, traceLaunches = 0;
     double traceMs = 0, shadeMs = 0, shadowMs = 0, binMs = 0;
     const size_t binSmemBytes = ((size_t)(1u << BIN_KEY_BITS) + BIN_WINDOW) * 4 + (size_t)BIN_WINDOW * 2;
@@ -588,7 +615,7 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
                         launches++;
                     }
                     if (c->anyEmissive) {
-                        timed(shadowMs, st, [&] { wf::k_probe<<<gridProbe, TRV_BLOCK, 0, st>>>(w, sc, rc, d, c->tune); });
+                        timed(shadowMs, st, [&] { probeFn<<<gridProbe, TRV_BLOCK, 0, st>>>(w, sc, rc, d, c->tune); });
                         launches++;
                     }
                     if (rc.binMode != 0u && d + 1 < rp->depth) { /* regroup the survivors before they are traced */
@@ -834,7 +861,7 @@ void uploadSceneDev(Dev *c, const ptc_scene_desc *sd) {
         d.firstVertex = m.first_vertex;
         d.numTriangles = in.num_triangles;
         d.firstWorldTri = (uint32_t)tri;
-        d.pad = 0;
+        d.mesh = in.mesh_index;
         tri += m.tri_count;
         const ptc_material &mat = sd->materials[in.material_index];
         const float ei = mat.emissive[3];
@@ -886,6 +913,17 @@ void uploadSceneDev(Dev *c, const ptc_scene_desc *sd) {
     if (tri >= 0x7fffffffull) throw CudaError{"more than 2^31 world triangles"};
     c->nWorldTris = (uint32_t)tri;
     c->instances.upload(inst.data(), inst.size(), s);
+    c->meshes.resize(sd->n_meshes);
+    {
+        std::vector<uint8_t> used(sd->n_meshes, 0);
+        for (uint32_t i = 0; i < sd->n_instances; i++) used[sd->instances[i].mesh_index] = 1;
+        c->uniqueTris = 0;
+        for (uint32_t m = 0; m < sd->n_meshes; m++) {
+            /* a mesh no instance refers to gets an empty tree */
+            c->meshes[m] = lbvh::MeshRange{sd->meshes[m].first_index, used[m] ? sd->meshes[m].tri_count : 0u, sd->meshes[m].first_vertex};
+            if (used[m]) c->uniqueTris += sd->meshes[m].tri_count;
+        }
+    }
     /* few emitters: one box each; many: the box around all of them */
     if (nEmissiveInst > PTC_MAX_EMISSIVE_BOXES) {
         emBoxes.clear();
@@ -1014,6 +1052,7 @@ bool renderAll(ptc_ctx *ctx, const ptc_render_params *rp, void *const dOut[3], f
     const ptc_stats &b0 = ctx->devs[0]->stats;
     st.build_ms = b0.build_ms, st.n_triangles = b0.n_triangles, st.n_bvh_nodes = b0.n_bvh_nodes, st.scene_bytes = b0.scene_bytes;
     st.upload_bytes = b0.upload_bytes;
+    st.accel_levels = b0.accel_levels, st.traversal_bytes = b0.traversal_bytes;
     st.reduce_ms = ctx->reduceMs;
     for (auto &d : ctx->devs) {
         const ptc_stats &x = d->stats;
@@ -1085,6 +1124,10 @@ static void createDev(Dev *c, int device) {
     if (const char *t = getenv("PTC_EXTEND_TUNE")) { /* "minActive,triEnter,triLeave,blocked" */
         unsigned a, b, d, e;
         if (sscanf(t, "%u,%u,%u,%u", &a, &b, &d, &e) == 4) c->tune = wf::ExtendTune{a, b, d, e};
+    }
+    if (const char *a = getenv("PTC_ACCEL")) { /* flat | two | auto: default mode of ptc_set_accel_mode, for tuning runs */
+        if (!strcmp(a, "flat")) c->accelMode = PTC_ACCEL_FLAT;
+        if (!strcmp(a, "two")) c->accelMode = PTC_ACCEL_TWO_LEVEL;
     }
     if (const char *b = getenv("PTC_BIN")) c->binMode = (uint32_t)std::min(2, std::max(0, atoi(b)));
     if (const char *t = getenv("PTC_TILE_ORDER")) c->tileOrder = (uint32_t)std::min(64, std::max(0, atoi(t)));
@@ -1222,6 +1265,16 @@ PTC_API int ptc_set_build_options(ptc_ctx *ctx, uint32_t hierarchy, uint32_t plo
     return 0;
 }
 
+PTC_API int ptc_set_accel_mode(ptc_ctx *ctx, uint32_t mode) {
+    if (!ctx) return 1;
+    if (mode > PTC_ACCEL_TWO_LEVEL) return fail(ctx, "unknown acceleration-structure mode");
+    for (auto &c : ctx->devs) {
+        c->accelMode = mode;
+        c->accelBuilt = false;
+    }
+    return 0;
+}
+
 PTC_API int ptc_build_accel(ptc_ctx *ctx) {
     if (!ctx) return 1;
     if (ctx->devs.empty()) return fail(ctx, "context has no CUDA device");
@@ -1231,13 +1284,24 @@ PTC_API int ptc_build_accel(ptc_ctx *ctx) {
     /* every device builds its own copy from the same input: the build is deterministic, so the copies are identical */
     forEachDev(ctx, [&](Dev *c, uint32_t) {
         CUDA_TRY(cudaEventRecord(c->evA, c->stream));
-        c->accel.run(c->vertices.p, c->indices.p, c->instances.p, c->nInstances, c->nWorldTris, c->stream);
+        /* One tree over world-space triangles, or one per mesh below one over the instances (VulkanScene.cpp:306-381)?  Flattening wins
+         * until instancing multiplies the triangles far beyond what the caches hold: two levels when the world triangles are at least
+         * PTC_TWO_LEVEL_RATIO (4) times the unique ones and more than PTC_TWO_LEVEL_MIN_TRIS (4 M). */
+        bool two = c->accelMode == PTC_ACCEL_TWO_LEVEL;
+        if (c->accelMode == PTC_ACCEL_AUTO) two = c->nWorldTris > (4u << 20) && (uint64_t)c->nWorldTris >= 4ull * std::max<uint64_t>(c->uniqueTris, 1);
+        c->twoLevel = two;
+        if (two)
+            c->accel2.run(c->vertices.p, c->indices.p, c->instances.p, c->nInstances, c->meshes, c->accel.hierarchy, c->accel.plocRadius, c->stream);
+        else
+            c->accel.run(c->vertices.p, c->indices.p, c->instances.p, c->nInstances, c->nWorldTris, c->stream);
         CUDA_TRY(cudaEventRecord(c->evB, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         float ms = 0;
         CUDA_TRY(cudaEventElapsedTime(&ms, c->evA, c->evB));
         c->accelBuilt = true;
-        if (c->accel.n > 0) {
+        if (two) {
+            for (int a = 0; a < 3; a++) c->sceneLo[a] = c->accel2.tlas.lo[a], c->sceneHi[a] = c->accel2.tlas.hi[a];
+        } else if (c->accel.n > 0) {
             uint32_t sb[6];
             CUDA_TRY(cudaMemcpy(sb, c->accel.sceneBounds.p, sizeof(sb), cudaMemcpyDeviceToHost));
             for (int a = 0; a < 3; a++) c->sceneLo[a] = lbvh::floatUnflip(sb[a]), c->sceneHi[a] = lbvh::floatUnflip(sb[3 + a]);
@@ -1245,11 +1309,14 @@ PTC_API int ptc_build_accel(ptc_ctx *ctx) {
         setTraversalWindow(c);
         c->stats.build_ms = ms;
         c->stats.n_triangles = c->nWorldTris;
-        c->stats.n_bvh_nodes = c->accel.nWide;
-        c->stats.scene_bytes = c->accel.bytes() + c->vertices.bytes() + c->indices.bytes() + c->instances.bytes() + c->materials.bytes();
+        c->stats.n_bvh_nodes = two ? c->accel2.nNodes : c->accel.nWide;
+        c->stats.accel_levels = two ? 2u : 1u;
+        c->stats.traversal_bytes = c->travBytes();
+        c->stats.scene_bytes = (two ? c->accel2.bytes() : c->accel.bytes()) + c->vertices.bytes() + c->indices.bytes() + c->instances.bytes() + c->materials.bytes();
     });
     const ptc_stats &b0 = ctx->devs[0]->stats;
     ctx->stats.build_ms = b0.build_ms, ctx->stats.n_triangles = b0.n_triangles, ctx->stats.n_bvh_nodes = b0.n_bvh_nodes, ctx->stats.scene_bytes = b0.scene_bytes;
+    ctx->stats.accel_levels = b0.accel_levels, ctx->stats.traversal_bytes = b0.traversal_bytes;
     for (auto &d : ctx->devs) ctx->stats.build_ms = std::max(ctx->stats.build_ms, d->stats.build_ms);
     return 0;
     PTC_GUARD_END(ctx)
@@ -1297,10 +1364,17 @@ PTC_API int ptc_trace_closest(ptc_ctx *ctx, const float *rays, int n, int *inst,
     cudaStream_t s = c->stream;
     DBuf<float> dRays, dT, dU, dV;
     DBuf<int> dInst, dPrim;
+    DBuf<uint32_t> dCounter;
     dRays.upload(rays, (size_t)n * 8, s);
     dT.alloc(n); dU.alloc(n); dV.alloc(n); dInst.alloc(n); dPrim.alloc(n);
+    dCounter.alloc(1);
+    CUDA_TRY(cudaMemsetAsync(dCounter.p, 0, 4, s));
     DScene sc = makeDScene(c);
-    wf::k_trace_closest<<<(n + TRV_BLOCK - 1) / TRV_BLOCK, TRV_BLOCK, 0, s>>>(sc, dRays.p, n, dInst.p, dPrim.p, dT.p, dU.p, dV.p);
+    const int grid = std::max(1, std::min((n + TRV_BLOCK - 1) / TRV_BLOCK, c->smCount * 4));
+    if (c->twoLevel)
+        wf::k_trace_closest<true><<<grid, TRV_BLOCK, 0, s>>>(sc, dRays.p, (uint32_t)n, dCounter.p, dInst.p, dPrim.p, dT.p, dU.p, dV.p, c->tune);
+    else
+        wf::k_trace_closest<false><<<grid, TRV_BLOCK, 0, s>>>(sc, dRays.p, (uint32_t)n, dCounter.p, dInst.p, dPrim.p, dT.p, dU.p, dV.p, c->tune);
     CUDA_TRY(cudaGetLastError());
     if (inst) CUDA_TRY(cudaMemcpyAsync(inst, dInst.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
     if (prim) CUDA_TRY(cudaMemcpyAsync(prim, dPrim.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
@@ -1312,6 +1386,27 @@ PTC_API int ptc_trace_closest(ptc_ctx *ctx, const float *rays, int n, int *inst,
     PTC_GUARD_END(ctx)
 }
 
+/* two-level structure dump: level -1 = the top-level tree (primitives = instances), level m >= 0 = the tree of mesh m (primitives =
+ * its triangles); node words with indices RELATIVE to the tree, like ptc_get_wide_bvh */
+PTC_API int ptc_get_accel_level(ptc_ctx *ctx, int32_t level, uint64_t *n_nodes_out, uint64_t *n_prims_out, uint32_t *node_words, uint32_t *prim_order, float *box6) {
+    Dev *c = dev0(ctx);
+    if (!c) return 1;
+    if (!c->accelBuilt) return fail(ctx, "ptc_build_accel has not been called");
+    if (!c->twoLevel) return fail(ctx, "the acceleration structure is single level (ptc_set_accel_mode)");
+    if (level < -1 || level >= (int32_t)c->accel2.blas.size()) return fail(ctx, "no such level");
+    PTC_GUARD_BEGIN
+    CUDA_TRY(cudaSetDevice(c->device));
+    const lbvh::TwoLevel::Tree &t = level < 0 ? c->accel2.tlas : *c->accel2.blas[level];
+    if (n_nodes_out) *n_nodes_out = t.nNodes;
+    if (n_prims_out) *n_prims_out = t.nPrims;
+    if (box6)
+        for (int a = 0; a < 3; a++) box6[a] = t.lo[a], box6[3 + a] = t.hi[a];
+    if (node_words && t.nNodes) CUDA_TRY(cudaMemcpy(node_words, t.nodes.p, (size_t)t.nNodes * 80, cudaMemcpyDeviceToHost));
+    if (prim_order && t.nPrims) CUDA_TRY(cudaMemcpy(prim_order, t.order.p, (size_t)t.nPrims * 4, cudaMemcpyDeviceToHost));
+    return 0;
+    PTC_GUARD_END(ctx)
+}
+
 PTC_API int ptc_get_lbvh(ptc_ctx *ctx, uint64_t *n_out, uint64_t *morton, uint32_t *order, int32_t *parent, int32_t *left, int32_t *right,
                          float *aabb) {
     Dev *c = dev0(ctx);
@@ -1319,6 +1414,7 @@ PTC_API int ptc_get_lbvh(ptc_ctx *ctx, uint64_t *n_out, uint64_t *morton, uint32
     if (!c->accelBuilt) return fail(ctx, "ptc_build_accel has not been called");
     PTC_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
+    if (c->twoLevel) return fail(ctx, "the acceleration structure has two levels: use ptc_get_accel_level");
     const lbvh::Build &B = c->accel;
     const size_t n = B.n;
     if (n_out) *n_out = n;
@@ -1348,6 +1444,7 @@ PTC_API int ptc_get_wide_bvh(ptc_ctx *ctx, uint64_t *n_nodes_out, uint64_t *n_tr
     if (!c->accelBuilt) return fail(ctx, "ptc_build_accel has not been called");
     PTC_GUARD_BEGIN
     CUDA_TRY(cudaSetDevice(c->device));
+    if (c->twoLevel) return fail(ctx, "the acceleration structure has two levels: use ptc_get_accel_level");
     const lbvh::Build &B = c->accel;
     if (n_nodes_out) *n_nodes_out = B.n ? B.nWide : 0;
     if (n_tris_out) *n_tris_out = B.n;

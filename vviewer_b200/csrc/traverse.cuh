@@ -33,6 +33,7 @@ struct HitRec {
     float t, u, v;
     int32_t pos;      /* position in the Morton-ordered triangle array, -1 = miss */
     uint32_t worldId; /* world triangle id (instance-major), the tie-break key */
+    uint32_t inst;    /* two-level structure only: the instance the hit triangle belongs to */
 };
 
 PTC_D bool intersectTri(const float4 v0, const float4 e1, const float4 e2, const float3 o, const float3 d, float &t, float &u, float &v) {
@@ -83,6 +84,17 @@ struct Stack {
     uint2 name##Spill[TRV_STACK];                                  \
     const trv::Stack name{name##Shared + threadIdx.x, name##Spill}
 
+/* Two-level structure (DScene::twoLevel, lbvh.cuh::TwoLevel).  The same node / triangle machinery walks the top-level tree in world
+ * space and the bottom-level tree of an instance in ITS object space: entering an instance replaces (o, d) by world->object * (o, d)
+ * - the direction is not renormalised, so t means the same on both levels and best.t keeps pruning - and leaving restores them.
+ * The stack then holds three kinds of entries:
+ *   node group       (first child, hits | imask)              y > 0x00ffffff
+ *   instance group   (first leaf entry | 0x80000000, mask)    the rest of a top-level leaf whose first instance is being visited
+ *   marker           (0xffffffff, 0)                          below it lies the top level: popping it leaves the instance
+ * TL is a compile-time switch of the kernels: the single-level instantiations never touch the extra state. */
+#define TRV_MARKER_X 0xffffffffu
+#define TRV_INSTANCE_FLAG 0x80000000u
+
 struct Trav {
     float3 o, d, idir;
     float tmin, tmax, t0;
@@ -91,6 +103,11 @@ struct Trav {
     uint2 ng, tg;
     uint32_t octinv4;
     int sp;
+    /* two-level state */
+    float3 wo, wd;          /* the world-space ray while the traversal is inside an instance */
+    uint2 ig;               /* pending instances of the current top-level leaf: (first leaf entry, mask) */
+    uint32_t inst, instFirstTri;
+    bool top;               /* walking the top level */
 
     PTC_D void init(const DScene &sc, const Ray &ray, float t0_, uint32_t id0_) {
         o = ray.o;
@@ -101,14 +118,18 @@ struct Trav {
         id0 = id0_;
         start(sc);
     }
-    /* (re)starts the query described by o, d, tmin, tmax, t0, id0 */
-    PTC_D void start(const DScene &sc) {
+    /* reciprocal direction and octant of the current (o, d) */
+    PTC_D void setDirection() {
         const float ooeps = 1e-20f;
         idir = f3(1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x)), 1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y)),
                   1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z)));
         /* octant of the direction signs; slot (oct) of every node is visited first */
         const uint32_t oct = (idir.x < 0.0f ? 4u : 0u) | (idir.y < 0.0f ? 2u : 0u) | (idir.z < 0.0f ? 1u : 0u);
         octinv4 = (7u - oct) * 0x01010101u;
+    }
+    /* (re)starts the query described by o, d, tmin, tmax, t0, id0 */
+    PTC_D void start(const DScene &sc) {
+        setDirection();
         best.t = tmax;
         best.u = best.v = 0.0f;
         best.pos = -1;
@@ -119,6 +140,55 @@ struct Trav {
         ng = sc.nTris == 0 ? make_uint2(0u, 0u) : make_uint2(0u, 0x80000000u);
         if (sc.nTris == 0) sp = -1;
     }
+    template <bool TL>
+    PTC_D void startLevel(const DScene &sc) {
+        start(sc);
+        if constexpr (TL) {
+            top = true;
+            ig = make_uint2(0u, 0u);
+            inst = 0xffffffffu;
+            instFirstTri = 0u;
+            best.inst = 0xffffffffu;
+            wo = o;
+            wd = d;
+        }
+    }
+    /* top level: visit the instance at leaf entry `entry` - transform the ray into its object space and start at its mesh's root */
+    PTC_D void enterInstance(const DScene &sc, uint32_t entry) {
+        inst = __ldg(&sc.tlasInst[entry]);
+        const DInstance *I = &sc.instances[inst];
+        const float *m = I->w2o;
+        o = f3(m[0] * wo.x + m[1] * wo.y + m[2] * wo.z + m[3], m[4] * wo.x + m[5] * wo.y + m[6] * wo.z + m[7], m[8] * wo.x + m[9] * wo.y + m[10] * wo.z + m[11]);
+        d = f3(m[0] * wd.x + m[1] * wd.y + m[2] * wd.z, m[4] * wd.x + m[5] * wd.y + m[6] * wd.z, m[8] * wd.x + m[9] * wd.y + m[10] * wd.z);
+        setDirection();
+        instFirstTri = I->firstWorldTri;
+        ng = make_uint2(__ldg(&sc.meshRoot[I->mesh]), I->numTriangles ? 0x80000000u : 0u);
+        tg = make_uint2(0u, 0u);
+        top = false;
+    }
+    PTC_D void leaveInstance() {
+        o = wo;
+        d = wd;
+        setDirection();
+        top = true;
+        inst = 0xffffffffu;
+    }
+    /* Two-level: the lane has no node work (and, on the top level, no pending instance): take the next stack entry.  canLeave = no
+     * triangle of the current instance is still waiting for its test (they need the object-space ray). */
+    PTC_D void popNext(const Stack &st, bool canLeave) {
+        const uint2 e = sp <= TRV_SHARED_STACK ? st.shared[(sp - 1) * TRV_BLOCK] : st.spill[sp - 1 - TRV_SHARED_STACK];
+        if (e.x == TRV_MARKER_X && e.y == 0u) {
+            if (!canLeave) return;
+            --sp;
+            leaveInstance();
+        } else if (e.y <= 0x00ffffffu) { /* instance group */
+            --sp;
+            ig = make_uint2(e.x & ~TRV_INSTANCE_FLAG, e.y);
+        } else {
+            --sp;
+            ng = e;
+        }
+    }
     PTC_D bool done() const { return sp < 0; }
     /* the stack: TRV_SHARED_STACK entries in a shared-memory column, deeper entries in the caller's local spill array
      * (kept OUT of this struct so that the traversal state itself stays in registers) */
@@ -126,11 +196,16 @@ struct Trav {
         --sp;
         return sp < TRV_SHARED_STACK ? st.shared[sp * TRV_BLOCK] : st.spill[sp - TRV_SHARED_STACK];
     }
+    /* (an entry beyond the spill array is dropped WITHOUT moving the stack pointer, so a later pop never reads past the array; the
+     * depth bound - shared + TRV_STACK entries against at most 63 + 32 binary levels collapsed eightfold, twice on two levels - makes
+     * this unreachable for any tree the build produces) */
     PTC_D void push(const Stack &st, uint2 v) {
         if (sp < TRV_SHARED_STACK)
             st.shared[sp * TRV_BLOCK] = v;
         else if (sp - TRV_SHARED_STACK < TRV_STACK)
             st.spill[sp - TRV_SHARED_STACK] = v;
+        else
+            return;
         ++sp;
     }
 
@@ -205,6 +280,7 @@ struct Trav {
     }
 
     /* tests the triangle at position pos of the traversal order; returns true when it became the best hit */
+    template <bool TL = false>
     PTC_D bool triTest(const DScene &sc, int32_t pos) {
         const float4 *__restrict__ tris = sc.tris;
         const float4 v0 = __ldg(&tris[3 * (size_t)pos + 0]);
@@ -212,7 +288,8 @@ struct Trav {
         const float4 e2 = __ldg(&tris[3 * (size_t)pos + 2]);
         float t, u, v;
         if (intersectTri(v0, e1, e2, o, d, t, u, v)) {
-            const uint32_t wid = __float_as_uint(e2.w);
+            /* world triangle id (the tie-break key): stored with the triangle, or instance prefix + primitive on two levels */
+            const uint32_t wid = TL ? instFirstTri + __float_as_uint(e1.w) : __float_as_uint(e2.w);
             const bool after = t > t0 || (t == t0 && id0 != 0xffffffffu && wid > id0);
             const bool inRange = after && t < tmax && t > tmin;
             if (inRange && (t < best.t || (t == best.t && wid < best.worldId))) {
@@ -221,46 +298,14 @@ struct Trav {
                 best.v = v;
                 best.pos = pos;
                 best.worldId = wid;
+                if constexpr (TL) best.inst = inst;
                 return true;
             }
         }
         return false;
     }
 
-    /* one step: node visit, the triangles it exposes, pop. Returns done(). */
-    template <bool ANY_HIT>
-    PTC_D bool advance(const DScene &sc, const Stack &stack) {
-        if (ng.y > 0x00ffffffu) tg = nodeStep(sc, stack);
-        while (tg.y != 0u) {
-            const uint32_t k = 31u - (uint32_t)__clz(tg.y);
-            tg.y &= ~(1u << k);
-            if (triTest(sc, (int32_t)(tg.x + k)) && ANY_HIT) {
-                sp = -1;
-                return true;
-            }
-        }
-        if (ng.y <= 0x00ffffffu) {
-            if (sp == 0) {
-                sp = -1;
-                return true;
-            }
-            ng = pop(stack);
-        }
-        return false;
-    }
 };
-
-/* run-to-completion wrappers (used by the chain kernels and the parity hooks) */
-template <bool ANY_HIT>
-PTC_D HitRec traverse(const DScene &sc, const Ray &ray, float t0, uint32_t id0, const Stack &stack) {
-    Trav tr;
-    tr.init(sc, ray, t0, id0);
-    while (!tr.done()) tr.advance<ANY_HIT>(sc, stack);
-    return tr.best;
-}
-PTC_D HitRec closestHit(const DScene &sc, const Ray &ray, const Stack &stack) { return traverse<false>(sc, ray, ray.tmin, 0xffffffffu, stack); }
-PTC_D HitRec nextHit(const DScene &sc, const Ray &ray, float t0, uint32_t id0, const Stack &stack) { return traverse<false>(sc, ray, t0, id0, stack); }
-PTC_D bool occluded(const DScene &sc, const Ray &ray, const Stack &stack) { return traverse<true>(sc, ray, ray.tmin, 0xffffffffu, stack).pos >= 0; }
 
 /* ------------------------------------------------------------------ persistent-warp work distribution */
 /* Each warp owns a chunk [pos, end) of the work list, refilled with ONE global atomic per chunk; lanes that need work

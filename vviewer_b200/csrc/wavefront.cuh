@@ -36,6 +36,7 @@ struct Wave {
     float4 *beta;      /* throughput.xyz */
     float4 *radiance;  /* rgb */
     float4 *hit;       /* t, u, v, triangle position (int bits, -1 = miss) */
+    uint32_t *hitInst; /* two-level structure: the instance of the hit (the triangle position alone names a mesh triangle) */
     float4 *aovAlbedo; /* first-hit albedo */
     float4 *aovNormal; /* first-hit normal * 0.5 + 0.5 */
     float4 *shOrgTmax; /* shadow request: origin.xyz, tmax */
@@ -149,11 +150,12 @@ struct Surf {
     float2 uv;
     float3 pos, n, t; /* world position, unnormalised->normalised world normal / tangent */
 };
-PTC_D void loadSurf(const DScene &sc, int32_t triPos, float u, float v, bool wantFrame, Surf &s) {
+/* hitInst: the instance the hit reported (two-level structure); single level: the record names its instance itself */
+PTC_D void loadSurf(const DScene &sc, int32_t triPos, uint32_t hitInst, float u, float v, bool wantFrame, Surf &s) {
     const float4 *__restrict__ r = sc.shading + 9 * (size_t)triPos;
     /* (plain cached loads: streaming the records past L1 with ld.global.cs was measured 1 % slower, 2054 vs 2074 Mseg/s) */
     const float4 r0 = __ldg(r + 0), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3), r4 = __ldg(r + 4), r5 = __ldg(r + 5), r6 = __ldg(r + 6);
-    const DInstance *I = &sc.instances[__float_as_uint(r6.w)];
+    const DInstance *I = &sc.instances[sc.twoLevel ? hitInst : __float_as_uint(r6.w)];
     s.inst = I;
     s.mat = &sc.materials[I->material];
     const float w0 = 1.0f - u - v, w1 = u, w2 = v;
@@ -174,7 +176,8 @@ PTC_D void loadSurf(const DScene &sc, int32_t triPos, float u, float v, bool wan
 
 /* material of the triangle at a traversal position without touching the rest of its record: the any-hit shaders of the shadow and
  * probe rays decide most candidates from the material alone (opaque and not emissive: the ray ends there) */
-PTC_D const ptc_material *hitMaterial(const DScene &sc, int32_t triPos) {
+PTC_D const ptc_material *hitMaterial(const DScene &sc, int32_t triPos, uint32_t hitInst) {
+    if (sc.twoLevel) return &sc.materials[sc.instances[hitInst].material];
     const float4 r6 = __ldg(sc.shading + 9 * (size_t)triPos + 6);
     return &sc.materials[sc.instances[__float_as_uint(r6.w)].material];
 }
@@ -412,11 +415,13 @@ PTC_D void testTriangle(const DScene &sc, Policy &pol, trv::Trav &tr, int32_t po
             const float4 *__restrict__ tris = sc.tris;
             const float4 v0 = __ldg(&tris[3 * (size_t)pos + 0]), e1 = __ldg(&tris[3 * (size_t)pos + 1]), e2 = __ldg(&tris[3 * (size_t)pos + 2]);
             float t, u, v;
-            if (tr.best.pos < 0 && trv::intersectTri(v0, e1, e2, tr.o, tr.d, t, u, v) && t > tr.tmin && t < tr.tmax && pol.candidate(pos, u, v)) tr.best.pos = pos;
+            if (tr.best.pos < 0 && trv::intersectTri(v0, e1, e2, tr.o, tr.d, t, u, v) && t > tr.tmin && t < tr.tmax &&
+                pol.candidate(pos, Policy::TWO_LEVEL ? tr.inst : 0xffffffffu, u, v))
+                tr.best.pos = pos;
             return;
         }
     }
-    tr.triTest(sc, pos);
+    tr.template triTest<Policy::TWO_LEVEL>(sc, pos);
 }
 
 template <class Policy>
@@ -440,12 +445,34 @@ PTC_D void traceLoop(const DScene &sc, Policy &pol, uint32_t count, uint32_t *fe
         }
         while (true) { /* warp-convergent: no lane leaves this loop alone */
             if (pending) {
-                tr.start(sc);
+                tr.template startLevel<Policy::TWO_LEVEL>(sc);
                 nStash = 0;
                 pending = false;
             }
+            if constexpr (Policy::TWO_LEVEL) {
+                /* out of node work: the next stack entry (more nodes, the rest of a top-level leaf, or the way out of the instance) */
+                if (active && tr.ng.y <= 0x00ffffffu && (!tr.top || tr.ig.y == 0u) && tr.sp > 0) tr.popNext(stack, tr.tg.y == 0u && nStash == 0u);
+                /* top level: step into the next instance of the current leaf */
+                if (active && tr.top && tr.ig.y != 0u && tr.ng.y <= 0x00ffffffu) {
+                    const uint32_t k = 31u - (uint32_t)__clz(tr.ig.y);
+                    tr.ig.y &= ~(1u << k);
+                    if (tr.ig.y != 0u) tr.push(stack, make_uint2(tr.ig.x | TRV_INSTANCE_FLAG, tr.ig.y));
+                    tr.push(stack, make_uint2(TRV_MARKER_X, 0u));
+                    tr.enterInstance(sc, tr.ig.x + k);
+                    tr.ig.y = 0u;
+                }
+            }
             TRV_COUNT(cnt.nodeIt);
-            if (active && tr.ng.y > 0x00ffffffu) {
+            if (Policy::TWO_LEVEL && active && tr.top && tr.ng.y > 0x00ffffffu) {
+                /* a top-level node: what it exposes are instances, visited before the node's remaining children */
+                TRV_COUNT(cnt.node);
+                const uint2 g = tr.nodeStep(sc, stack);
+                if (g.y != 0u) {
+                    if (tr.ng.y > 0x00ffffffu) tr.push(stack, tr.ng);
+                    tr.ng.y = 0u;
+                    tr.ig = g;
+                }
+            } else if (active && tr.ng.y > 0x00ffffffu) {
                 TRV_COUNT(cnt.node);
                 const uint2 g = tr.nodeStep(sc, stack);
                 if (g.y != 0u) {
@@ -462,9 +489,10 @@ PTC_D void traceLoop(const DScene &sc, Policy &pol, uint32_t count, uint32_t *fe
                     else
                         stash[(nStash++) * TRV_BLOCK] = g;
                 }
-                if (tr.ng.y <= 0x00ffffffu && tr.sp > 0) tr.ng = tr.pop(stack);
+                if (!Policy::TWO_LEVEL && tr.ng.y <= 0x00ffffffu && tr.sp > 0) tr.ng = tr.pop(stack);
             }
-            const bool hasNode = active && tr.ng.y > 0x00ffffffu;
+            /* (two levels: a lane with stack entries or pending instances still has work, it just takes it at the top of the loop) */
+            const bool hasNode = active && (tr.ng.y > 0x00ffffffu || (Policy::TWO_LEVEL && (tr.ig.y != 0u || (tr.sp > 0 && tr.tg.y == 0u))));
             bool hasTri = active && tr.tg.y != 0u;
             const unsigned mN = __ballot_sync(0xffffffffu, hasNode);
             unsigned mT = __ballot_sync(0xffffffffu, hasTri);
@@ -483,7 +511,11 @@ PTC_D void traceLoop(const DScene &sc, Policy &pol, uint32_t count, uint32_t *fe
                 } while (__popc(mT) >= tune.triLeave || (mT & ~mN) != 0u);
             }
             /* query complete: nothing left to visit, or an occlusion query that already has its answer */
-            if (active && ((!hasNode && !hasTri) || (pol.anyHit() && tr.best.pos >= 0))) {
+            const bool moreWork = tr.ng.y > 0x00ffffffu || hasTri || (Policy::TWO_LEVEL && (tr.sp > 0 || tr.ig.y != 0u));
+            if (active && (!moreWork || (pol.anyHit() && tr.best.pos >= 0))) {
+                if constexpr (Policy::TWO_LEVEL) {
+                    if (!tr.top) tr.leaveInstance(); /* an occlusion query may end inside an instance: the policy sees the world-space ray */
+                }
                 active = pending = pol.next(tr);
                 tr.ng.y = 0u;
                 tr.tg.y = 0u;
@@ -510,9 +542,10 @@ PTC_D void traceCountersFlush(const Wave &w, const TraceCounters &cnt) {
 /* VOLUMES: the scene has media.  A path inside a medium already knows how far it will fly (k_shade draws the free-flight distance of
  * the NEXT segment from a copy of the random stream and leaves 1e-3 + distance in the slot's hit record): the ray only needs to be traced
  * that far - a surface beyond the scattering point changes nothing (process_volume_hit.glsl:13-25). */
-template <bool VOLUMES>
+template <bool VOLUMES, bool TL>
 struct ExtendPolicy {
     static constexpr bool ALL_HITS = false;
+    static constexpr bool TWO_LEVEL = TL;
     const Wave &w;
     const uint32_t *__restrict__ q;
     uint32_t bounce, slot;
@@ -532,17 +565,21 @@ struct ExtendPolicy {
     PTC_D bool next(trv::Trav &tr) {
         const trv::HitRec &h = tr.best;
         stS(&w.hit[slot], make_float4(h.t, h.u, h.v, __int_as_float(h.pos)));
+        if constexpr (TL) w.hitInst[slot] = h.inst;
         return false;
     }
 };
 #ifndef TRV_EXTEND_MINBLOCKS
 #define TRV_EXTEND_MINBLOCKS 8
 #endif
-template <bool VOLUMES>
-__global__ void __launch_bounds__(TRV_BLOCK, TRV_EXTEND_MINBLOCKS) k_extend(Wave w, const __grid_constant__ DScene sc, uint32_t bounce, ExtendTune tune) {
+#ifndef TRV_TWO_LEVEL_MINBLOCKS
+#define TRV_TWO_LEVEL_MINBLOCKS 6 /* the two-level instantiations carry the world-space ray and the instance state */
+#endif
+template <bool VOLUMES, bool TL>
+__global__ void __launch_bounds__(TRV_BLOCK, TL ? TRV_TWO_LEVEL_MINBLOCKS : TRV_EXTEND_MINBLOCKS) k_extend(Wave w, const __grid_constant__ DScene sc, uint32_t bounce, ExtendTune tune) {
     TRV_DECLARE_STACK(stack);
     __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
-    ExtendPolicy<VOLUMES> pol(w, bounce);
+    ExtendPolicy<VOLUMES, TL> pol(w, bounce);
     TraceCounters cnt;
     traceLoop(sc, pol, w.counters[bounce * CNT_STRIDE + CNT_ACTIVE], &w.counters[bounce * CNT_STRIDE + CNT_FETCH], tune, stack, stashMem + threadIdx.x, cnt);
     traceCountersFlush(w, cnt);
@@ -656,7 +693,7 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
             Pbr pbr;
             bool lambert = false;
             if (!sampledMedium && triPos >= 0) {
-                loadSurf(sc, triPos, h.y, h.z, true, s);
+                loadSurf(sc, triPos, sc.twoLevel ? w.hitInst[slot] : 0u, h.y, h.z, true, s);
                 fr.n = s.n;
                 fr.t = s.t;
                 const bool flipped = fixFrame(fr, rayDir);
@@ -895,8 +932,9 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
 /* ------------------------------------------------------------------ k_shadow */
 /* lightSampling.glsl:108-144 + raySecondary.rahit/.rchit/.rmiss with nearest-first candidate order (trap T1), as a
  * per-lane state machine on top of traceLoop: one query = the next-nearest candidate of the current hop. */
-template <bool OPAQUE> /* OPAQUE: no material of the scene is transparent - every hit shadows, the candidate code is not compiled */
+template <bool OPAQUE, bool TL> /* OPAQUE: no material of the scene is transparent - every hit shadows, the candidate code is not compiled */
 struct ShadowPolicy {
+    static constexpr bool TWO_LEVEL = TL;
     /* Without media (no instance changes the volume, the camera is in none) the shadow chain is one ray whose transmittance is the
      * product of (1 - alpha) over the transparent surfaces it crosses, zero if any of them is opaque (raySecondary.rahit.glsl:31-72):
      * independent of the order, so one traversal that looks at every crossed triangle replaces one ordered query per surface. */
@@ -915,9 +953,9 @@ struct ShadowPolicy {
     PTC_D bool anyHit() const { return opaqueScene || everyHit; } /* every surface is opaque: any hit shadows; all-hits: a decided ray is marked hit */
     PTC_D bool allHits() const { return everyHit; }
     /* a triangle the ray crosses (all-hits mode): true = the ray is shadowed */
-    PTC_D bool candidate(int32_t pos, float u, float v) {
+    PTC_D bool candidate(int32_t pos, uint32_t hitInst, float u, float v) {
         const float4 *__restrict__ r = sc.shading + 9 * (size_t)pos;
-        const ptc_material *mat = &sc.materials[sc.instances[__float_as_uint(__ldg(r + 6).w)].material];
+        const ptc_material *mat = &sc.materials[sc.instances[TL ? hitInst : __float_as_uint(__ldg(r + 6).w)].material];
         if (!(__ldg(&mat->metallic_roughness_ao[3]) >= 0.99f)) return true; /* raySecondary.rahit.glsl:42-47 */
         const float w0 = 1.0f - u - v;
         const float uu = __ldg(r + 0).w * w0 + __ldg(r + 2).w * u + __ldg(r + 4).w * v, vv = __ldg(r + 1).w * w0 + __ldg(r + 3).w * u + __ldg(r + 5).w * v;
@@ -971,9 +1009,9 @@ struct ShadowPolicy {
             return finish(shadowed);
         }
         if (opaqueScene || everyHit) return finish(true);
-        if (!(__ldg(&hitMaterial(sc, h.pos)->metallic_roughness_ao[3]) >= 0.99f)) return finish(true); /* raySecondary.rahit.glsl:42-47 */
+        if (!(__ldg(&hitMaterial(sc, h.pos, h.inst)->metallic_roughness_ao[3]) >= 0.99f)) return finish(true); /* raySecondary.rahit.glsl:42-47 */
         Surf s;
-        loadSurf(sc, h.pos, h.u, h.v, false, s);
+        loadSurf(sc, h.pos, h.inst, h.u, h.v, false, s);
         const ptc_material *mat = s.mat;
         const float alpha =
             __ldg(&mat->albedo[3]) * texFetch(sc, __ldg(&mat->tex2[3]), s.uv.x * __ldg(&mat->uv_tiling[0]), s.uv.y * __ldg(&mat->uv_tiling[1])).x;
@@ -1004,12 +1042,12 @@ struct ShadowPolicy {
 #ifndef CHAIN_MINBLOCKS
 #define CHAIN_MINBLOCKS 7
 #endif
-template <bool OPAQUE>
-__global__ void __launch_bounds__(TRV_BLOCK, CHAIN_MINBLOCKS) k_shadow(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
+template <bool OPAQUE, bool TL>
+__global__ void __launch_bounds__(TRV_BLOCK, TL ? TRV_TWO_LEVEL_MINBLOCKS : CHAIN_MINBLOCKS) k_shadow(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
                                                       ExtendTune tune) {
     TRV_DECLARE_STACK(stack);
     __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
-    ShadowPolicy<OPAQUE> pol(w, sc, rc);
+    ShadowPolicy<OPAQUE, TL> pol(w, sc, rc);
     TraceCounters cnt;
     traceLoop(sc, pol, w.counters[bounce * CNT_STRIDE + CNT_SHADOW], &w.counters[bounce * CNT_STRIDE + CNT_FETCH_SHADOW], tune, stack,
               stashMem + threadIdx.x, cnt);
@@ -1018,7 +1056,9 @@ __global__ void __launch_bounds__(TRV_BLOCK, CHAIN_MINBLOCKS) k_shadow(Wave w, c
 
 /* ------------------------------------------------------------------ k_probe */
 /* next_event_estimation.glsl:1-33 + rayNEE.rahit/.rchit/.rmiss with nearest-first candidate order (trap T1) */
+template <bool TL>
 struct ProbePolicy {
+    static constexpr bool TWO_LEVEL = TL;
     static constexpr bool ALL_HITS = false; /* the probe's any-hit decisions depend on the order of the candidates */
     const Wave &w;
     const DScene &sc;
@@ -1069,11 +1109,11 @@ struct ProbePolicy {
         {
             /* rayNEE.rahit.glsl:44-54 decided from the material alone: the emissive texel is in [0, 1], so a material whose emissive
              * factor is already below the threshold cannot pass it, and an opaque one ends the ray (result-identical shortcut) */
-            const ptc_material *m0 = hitMaterial(sc, h.pos);
+            const ptc_material *m0 = hitMaterial(sc, h.pos, h.inst);
             if (!(__ldg(&m0->metallic_roughness_ao[3]) >= 0.99f) && isBlackEps(ld3(m0->emissive) * __ldg(&m0->emissive[3]), 0.05f)) return false;
         }
         Surf s;
-        loadSurf(sc, h.pos, h.u, h.v, false, s);
+        loadSurf(sc, h.pos, h.inst, h.u, h.v, false, s);
         const ptc_material *mat = s.mat;
         const float tu = s.uv.x * __ldg(&mat->uv_tiling[0]), tv = s.uv.y * __ldg(&mat->uv_tiling[1]);
         const float3 em = ld3(mat->emissive) * __ldg(&mat->emissive[3]) * f3(texFetch(sc, __ldg(&mat->tex2[0]), tu, tv));
@@ -1116,11 +1156,12 @@ struct ProbePolicy {
         return finish(em, pdf);
     }
 };
-__global__ void __launch_bounds__(TRV_BLOCK, CHAIN_MINBLOCKS) k_probe(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
+template <bool TL>
+__global__ void __launch_bounds__(TRV_BLOCK, TL ? TRV_TWO_LEVEL_MINBLOCKS : CHAIN_MINBLOCKS) k_probe(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
                                                      ExtendTune tune) {
     TRV_DECLARE_STACK(stack);
     __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
-    ProbePolicy pol(w, sc, rc);
+    ProbePolicy<TL> pol(w, sc, rc);
     TraceCounters cnt;
     traceLoop(sc, pol, w.counters[bounce * CNT_STRIDE + CNT_PROBE], &w.counters[bounce * CNT_STRIDE + CNT_FETCH_PROBE], tune, stack,
               stashMem + threadIdx.x, cnt);
@@ -1238,27 +1279,56 @@ __global__ void k_collect_stats(Wave w, uint32_t depth) {
 }
 
 /* ------------------------------------------------------------------ parity-hook kernels */
-__global__ void __launch_bounds__(TRV_BLOCK) k_trace_closest(const __grid_constant__ DScene sc, const float *__restrict__ rays, int n, int *inst, int *prim,
-                                                             float *t, float *u, float *v) {
-    TRV_DECLARE_STACK(stack);
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float *r = rays + (size_t)i * 8;
-    trv::Ray ray{f3(r[0], r[1], r[2]), f3(r[4], r[5], r[6]), r[3], r[7]};
-    trv::HitRec h = trv::closestHit(sc, ray, stack);
-    if (h.pos >= 0) {
-        inst[i] = (int)__float_as_uint(sc.tris[3 * (size_t)h.pos + 0].w);
-        prim[i] = (int)__float_as_uint(sc.tris[3 * (size_t)h.pos + 1].w);
-        t[i] = h.t;
-        u[i] = h.u;
-        v[i] = h.v;
-    } else {
-        inst[i] = -1;
-        prim[i] = -1;
-        t[i] = r[7];
-        u[i] = 0.0f;
-        v[i] = 0.0f;
+/* closest hits of a caller's ray set, through the same warp-persistent loop as the render */
+template <bool TL>
+struct RaySetPolicy {
+    static constexpr bool ALL_HITS = false;
+    static constexpr bool TWO_LEVEL = TL;
+    const DScene &sc;
+    const float *__restrict__ rays;
+    int *inst, *prim;
+    float *t, *u, *v;
+    uint32_t i;
+    float tmaxRay;
+    PTC_D RaySetPolicy(const DScene &sc_, const float *rays_, int *inst_, int *prim_, float *t_, float *u_, float *v_)
+        : sc(sc_), rays(rays_), inst(inst_), prim(prim_), t(t_), u(u_), v(v_), i(0), tmaxRay(0.0f) {}
+    PTC_D bool anyHit() const { return false; }
+    PTC_D bool begin(uint32_t index, trv::Trav &tr) {
+        i = index;
+        const float *r = rays + (size_t)i * 8;
+        tr.o = f3(r[0], r[1], r[2]);
+        tr.d = f3(r[4], r[5], r[6]);
+        tr.tmin = tr.t0 = r[3];
+        tr.tmax = tmaxRay = r[7];
+        tr.id0 = 0xffffffffu;
+        return true;
     }
+    PTC_D bool next(trv::Trav &tr) {
+        const trv::HitRec &h = tr.best;
+        if (h.pos >= 0) {
+            inst[i] = TL ? (int)h.inst : (int)__float_as_uint(sc.tris[3 * (size_t)h.pos + 0].w);
+            prim[i] = (int)__float_as_uint(sc.tris[3 * (size_t)h.pos + 1].w);
+            t[i] = h.t;
+            u[i] = h.u;
+            v[i] = h.v;
+        } else {
+            inst[i] = -1;
+            prim[i] = -1;
+            t[i] = tmaxRay;
+            u[i] = 0.0f;
+            v[i] = 0.0f;
+        }
+        return false;
+    }
+};
+template <bool TL>
+__global__ void __launch_bounds__(TRV_BLOCK) k_trace_closest(const __grid_constant__ DScene sc, const float *__restrict__ rays, uint32_t n, uint32_t *fetchCounter, int *inst,
+                                                             int *prim, float *t, float *u, float *v, ExtendTune tune) {
+    TRV_DECLARE_STACK(stack);
+    __shared__ uint2 stashMem[EXTEND_STASH * TRV_BLOCK];
+    RaySetPolicy<TL> pol(sc, rays, inst, prim, t, u, v);
+    TraceCounters cnt;
+    traceLoop(sc, pol, n, fetchCounter, tune, stack, stashMem + threadIdx.x, cnt);
 }
 
 __global__ void k_bsdf_eval(int n, const float *params, const float *wi, const float *wo, float *outF, float *outPdf) {
