@@ -263,7 +263,9 @@ PTC_API int ptc_set_build_options(ptc_ctx *ctx, uint32_t hierarchy, uint32_t plo
  *   PTC_ACCEL_TWO_LEVEL  one tree per mesh in object space + one tree over the instances' world boxes; rays are transformed with the
  *                        instance's world->object matrix on the way in - for heavily instanced scenes (BASELINE C4: 42.5 M world
  *                        triangles, 0.6 M unique ones)
- *   PTC_ACCEL_AUTO       (default) two levels when the world triangles exceed 4 M and are at least 4 times the unique ones
+ *   PTC_ACCEL_AUTO       (default) flat, unless the flattened data would take more than a quarter of the device memory and the scene
+ *                        instances its meshes at least twice on average (measured on C4: flat 1025 Mseg/s, two levels 648 - a forest's
+ *                        instance boxes overlap; what two levels buy is memory, 8.6 GB -> 0.13 GB)
  * Call before ptc_build_accel.  Hits are the same up to the rounding of the object-space intersection. */
 enum ptc_accel_mode { PTC_ACCEL_AUTO = 0, PTC_ACCEL_FLAT = 1, PTC_ACCEL_TWO_LEVEL = 2 };
 PTC_API int ptc_set_accel_mode(ptc_ctx *ctx, uint32_t mode);

@@ -413,14 +413,26 @@ def test_two_level_render_matches_oracle(capi, engine, scene, kw):
     assert abs(sa["segments"] - sb["segments"]) <= 2e-3 * sb["segments"] and np.all(ra[..., 3] == 1.0)
 
 
-def test_accel_mode_auto_picks_two_levels_for_heavy_instancing(capi, engine):
-    desc = _instanced(engine, texture_size=16, scale=0.12)  # ~5 M world triangles of a few unique meshes
+def test_accel_mode_auto(capi, engine):
+    """AUTO flattens (measured faster, profiles/r2_c4_flat_vs_two_level.log) until the flattened data would not fit a quarter of the
+    device memory; the threshold is overridable, which is how this test reaches the other branch with a small scene"""
+    desc = _instanced(engine, texture_size=16, scale=0.02)
     cu = capi.Context(capi.load_cuda())
     cu.upload_scene(desc)
     cu.build_accel()
-    st = cu.stats()
-    assert st["n_triangles"] > 4 << 20 and st["accel_levels"] == 2 and st["traversal_bytes"] < 0.25 * st["n_triangles"] * 48
-    engine.build_scene("Atrium", texture_size=4, scale=0.3)
+    flat = cu.stats()
+    assert flat["accel_levels"] == 1
+    cu.close()
+    os.environ["PTC_TWO_LEVEL_MIN_BYTES"] = "1000000"
+    try:
+        cu = capi.Context(capi.load_cuda())
+    finally:
+        del os.environ["PTC_TWO_LEVEL_MIN_BYTES"]
+    cu.upload_scene(desc)
+    cu.build_accel()
+    two = cu.stats()
+    assert two["accel_levels"] == 2 and two["n_triangles"] == flat["n_triangles"] and two["traversal_bytes"] < 0.5 * flat["traversal_bytes"]
+    engine.build_scene("Atrium", texture_size=4, scale=0.3)  # hardly any instancing: stays flat whatever the size
     cu.upload_scene(engine.scene_desc())
     cu.build_accel()
     assert cu.stats()["accel_levels"] == 1

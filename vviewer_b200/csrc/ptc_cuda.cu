@@ -71,6 +71,7 @@ struct Dev {
     std::vector<lbvh::MeshRange> meshes; /* of the uploaded scene */
     uint64_t uniqueTris = 0;             /* triangles of the meshes that are instanced at least once */
     uint32_t accelMode = PTC_ACCEL_AUTO;
+    uint64_t twoLevelMinBytes = ~0ull;   /* AUTO: flattened bytes above which two levels are taken (a quarter of the device memory) */
     bool twoLevel = false;               /* what the last build produced */
     size_t travBytes() const { return twoLevel ? accel2.traversalBytes() : (accel.n ? accel.traversalBytes() : 0); }
     const void *travBase() const { return twoLevel ? (const void *)accel2.trav.p : (const void *)accel.trav.p; }
@@ -1125,6 +1126,8 @@ static void createDev(Dev *c, int device) {
         unsigned a, b, d, e;
         if (sscanf(t, "%u,%u,%u,%u", &a, &b, &d, &e) == 4) c->tune = wf::ExtendTune{a, b, d, e};
     }
+    c->twoLevelMinBytes = (uint64_t)prop.totalGlobalMem / 4;
+    if (const char *b = getenv("PTC_TWO_LEVEL_MIN_BYTES")) c->twoLevelMinBytes = (uint64_t)atoll(b);
     if (const char *a = getenv("PTC_ACCEL")) { /* flat | two | auto: default mode of ptc_set_accel_mode, for tuning runs */
         if (!strcmp(a, "flat")) c->accelMode = PTC_ACCEL_FLAT;
         if (!strcmp(a, "two")) c->accelMode = PTC_ACCEL_TWO_LEVEL;
@@ -1284,11 +1287,16 @@ PTC_API int ptc_build_accel(ptc_ctx *ctx) {
     /* every device builds its own copy from the same input: the build is deterministic, so the copies are identical */
     forEachDev(ctx, [&](Dev *c, uint32_t) {
         CUDA_TRY(cudaEventRecord(c->evA, c->stream));
-        /* One tree over world-space triangles, or one per mesh below one over the instances (VulkanScene.cpp:306-381)?  Flattening wins
-         * until instancing multiplies the triangles far beyond what the caches hold: two levels when the world triangles are at least
-         * PTC_TWO_LEVEL_RATIO (4) times the unique ones and more than PTC_TWO_LEVEL_MIN_TRIS (4 M). */
+        /* One tree over world-space triangles, or one per mesh below one over the instances (VulkanScene.cpp:306-381)?  Measured on C4
+         * (42.5 M world / 0.6 M unique triangles, profiles/r2_c4_flat_vs_two_level.log): flat 1025 Mseg/s, two levels 648 - the boxes of
+         * a forest's instances overlap, a ray enters many bottom-level trees, and 180 GB of HBM hold the flattened 8 GB easily.  Two
+         * levels buy MEMORY (traversal + shading data 8.6 GB -> 0.13 GB), so AUTO takes them only when the flattened data would exceed a
+         * quarter of the device memory (PTC_TWO_LEVEL_MIN_BYTES overrides the threshold). */
         bool two = c->accelMode == PTC_ACCEL_TWO_LEVEL;
-        if (c->accelMode == PTC_ACCEL_AUTO) two = c->nWorldTris > (4u << 20) && (uint64_t)c->nWorldTris >= 4ull * std::max<uint64_t>(c->uniqueTris, 1);
+        if (c->accelMode == PTC_ACCEL_AUTO) {
+            const uint64_t flatBytes = (uint64_t)c->nWorldTris * (48 + 144 + 14); /* triangles + shading records + ~0.17 nodes of 80 B each */
+            two = flatBytes > c->twoLevelMinBytes && (uint64_t)c->nWorldTris >= 2ull * std::max<uint64_t>(c->uniqueTris, 1);
+        }
         c->twoLevel = two;
         if (two)
             c->accel2.run(c->vertices.p, c->indices.p, c->instances.p, c->nInstances, c->meshes, c->accel.hierarchy, c->accel.plocRadius, c->stream);
