@@ -168,7 +168,7 @@ typedef struct ptc_render_params {
      * only, so the sum keeps it).  A multi-device context / a context with a communicator sets rank and world itself. */
     uint32_t split_mode; /* ptc_split_mode */
     uint32_t rank, world;
-    uint32_t tile_size;  /* tile edge in pixels for PTC_SPLIT_TILE (0 = 32) */
+    uint32_t tile_size;  /* tile edge in pixels for PTC_SPLIT_TILE (0 = 32); tile (tx, ty) belongs to rank (tx + ty) mod world */
     uint32_t flags;      /* PTC_FLAG_* */
     uint32_t reserved[7];
 } ptc_render_params;

@@ -1053,9 +1053,7 @@ PTC_API int ptc_render(ptc_ctx *c, const ptc_render_params *rp, float *radiance,
         for (int y = 0; y < (int)H; y++) {
             for (uint32_t x = 0; x < W; x++) {
                 if (rp->split_mode == PTC_SPLIT_TILE) {
-                    uint32_t tilesX = (W + tile - 1) / tile;
-                    uint32_t tid = (y / tile) * tilesX + (x / tile);
-                    if (tid % world != rp->rank) continue;
+                    if (((uint32_t)y / tile + x / tile) % world != rp->rank) continue; /* diagonal stripes of tiles, like the product */
                 }
                 vec3 sumR(0.0f), sumA(0.0f), sumN(0.0f);
                 for (uint32_t b = 0; b < batches; b++) {

@@ -86,7 +86,7 @@ struct Dev {
         DBuf<unsigned long long> stats;
         size_t capacity = 0;
     } wave[2];
-    DBuf<uint32_t> pixmap, tileOffsets; /* tile split: local pixel -> global pixel, built on the device, kept across calls */
+    DBuf<uint32_t> pixmap, tileOffsets, tileIds; /* tile split: local pixel -> global pixel, built on the device, kept across calls */
     uint32_t pixmapKey[5] = {0, 0, 0, 0, 0}, pixmapCount = 0;
     cudaEvent_t evStart = nullptr, evStop = nullptr; /* device time of one render */
     cudaStream_t stream2 = nullptr; /* second wavefront; c->stream carries the first and everything else */
@@ -449,18 +449,25 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
         const uint32_t key[5] = {W, H, tile, tileSplit ? rp->rank : 0u, world};
         if (memcmp(key, c->pixmapKey, sizeof(key)) != 0 || !c->pixmap.p) {
             const uint32_t tilesX = (W + tile - 1) / tile, tilesY = (H + tile - 1) / tile, nTiles = tilesX * tilesY;
-            std::vector<uint32_t> offsets;
+            /* tile (tx, ty) belongs to rank (tx + ty) mod world: diagonal stripes, so that neither the columns of a colonnade nor the
+             * horizon of a landscape line up with one rank's share (plain t mod world with a tile count per row that is a multiple of
+             * world gave vertical stripes) */
+            std::vector<uint32_t> offsets, tileIds;
             uint32_t total = 0;
-            for (uint32_t t = key[3]; t < nTiles; t += world) {
+            for (uint32_t t = 0; t < nTiles; t++) {
                 const uint32_t tx = t % tilesX, ty = t / tilesX;
+                if ((tx + ty) % world != key[3]) continue;
                 offsets.push_back(total);
+                tileIds.push_back(t);
                 total += std::min(tile, W - tx * tile) * std::min(tile, H - ty * tile);
             }
             offsets.push_back(total);
             c->tileOffsets.upload(offsets.data(), offsets.size(), s);
+            c->tileIds.alloc(std::max<size_t>(tileIds.size(), 1));
+            if (!tileIds.empty()) c->tileIds.upload(tileIds.data(), tileIds.size(), s);
             c->pixmap.alloc(std::max<size_t>(total, 1));
-            const uint32_t nLocalTiles = (uint32_t)offsets.size() - 1u;
-            if (nLocalTiles) wf::k_tile_pixmap<<<nLocalTiles, 256, 0, s>>>(W, H, tile, key[3], world, c->tileOffsets.p, c->pixmap.p);
+            const uint32_t nLocalTiles = (uint32_t)tileIds.size();
+            if (nLocalTiles) wf::k_tile_pixmap<<<nLocalTiles, 256, 0, s>>>(W, H, tile, c->tileIds.p, c->tileOffsets.p, c->pixmap.p);
             CUDA_TRY(cudaStreamSynchronize(s)); /* the host vector dies here */
             memcpy(c->pixmapKey, key, sizeof(key));
             c->pixmapCount = total;
@@ -486,9 +493,21 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
     const int nWaves = overlap ? 2 : 1;
     size_t maxSlots = (size_t)1 << (overlap ? 25 : 26);
     if (const char *ms = getenv("PTC_MAX_SLOTS")) maxSlots = std::max<size_t>(1, (size_t)atoll(ms)); /* tests: force chunking */
-    uint32_t chunkSamples = rp->batch_size;
-    if (nPixLocal > 0) chunkSamples = (uint32_t)std::max<size_t>(1, std::min<size_t>(rp->batch_size, maxSlots / nPixLocal));
-    if (overlap && chunkSamples == rp->batch_size && rp->batch_size >= 2) chunkSamples = (rp->batch_size + 1) / 2;
+    /* Small wavefronts waste the GPU (every bounce is a handful of persistent-kernel launches whose tails and late, nearly empty
+     * bounces cost the same whatever the ray count): a rank that renders an eighth of a 4K image in batches of 8 samples ran 21 %
+     * below the full render's rate (profiles/r2_partition_probe.log).  So when one batch fills less than half a wavefront, consecutive
+     * batches are rendered as ONE work item (the sample index is global, so nothing but the grouping of the float additions into the
+     * accumulators changes).  Sample split keeps its batches apart: rank r owns every world-th batch. */
+    uint32_t mergeBatches = 1;
+    if (nPixLocal > 0 && batches > 1 && !(rp->split_mode == PTC_SPLIT_SAMPLE && world > 1) && getenv("PTC_NO_BATCH_MERGE") == nullptr) {
+        const size_t perBatch = (size_t)nPixLocal * rp->batch_size;
+        /* (at least 8 work items stay, so that renderProgress() keeps moving like the reference's batch counter) */
+        if (perBatch * 2 <= maxSlots) mergeBatches = (uint32_t)std::min<size_t>(std::max<uint32_t>(1u, batches / 8u), std::max<size_t>(1, (maxSlots * (size_t)nWaves) / perBatch));
+    }
+    const uint32_t itemSamplesMax = rp->batch_size * mergeBatches; /* samples of one work item */
+    uint32_t chunkSamples = itemSamplesMax;
+    if (nPixLocal > 0) chunkSamples = (uint32_t)std::max<size_t>(1, std::min<size_t>(itemSamplesMax, maxSlots / nPixLocal));
+    if (overlap && chunkSamples == itemSamplesMax && itemSamplesMax >= 2) chunkSamples = (itemSamplesMax + 1) / 2;
     wf::Wave waves[2];
     cudaStream_t streams[2] = {s, c->stream2};
     for (int k = 0; k < nWaves; k++) {
@@ -585,14 +604,20 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
     uint32_t myBatches = 0;
     for (uint32_t b = 0; b < batches; b++)
         if (!(rp->split_mode == PTC_SPLIT_SAMPLE && world > 1 && (b % world) != rp->rank)) myBatches++;
-    const uint32_t chunksPerBatch = (rp->batch_size + chunkSamples - 1) / chunkSamples;
-    const uint64_t totalItems = (uint64_t)myBatches * chunksPerBatch;
+    uint64_t totalItems = 0;
+    for (uint32_t b = 0; b < batches; b += mergeBatches) {
+        if (rp->split_mode == PTC_SPLIT_SAMPLE && world > 1 && (b % world) != rp->rank) continue;
+        const uint32_t itemSamples = std::min(mergeBatches, batches - b) * rp->batch_size;
+        totalItems += (itemSamples + chunkSamples - 1) / chunkSamples;
+    }
+    (void)myBatches;
 
     uint64_t item = 0;
     if (nPixLocal > 0) {
-        for (uint32_t b = 0; b < batches; b++) {
+        for (uint32_t b = 0; b < batches; b += mergeBatches) {
             if (rp->split_mode == PTC_SPLIT_SAMPLE && world > 1 && (b % world) != rp->rank) continue;
-            for (uint32_t s0 = 0; s0 < rp->batch_size; s0 += chunkSamples, item++) {
+            const uint32_t itemSamples = std::min(mergeBatches, batches - b) * rp->batch_size;
+            for (uint32_t s0 = 0; s0 < itemSamples; s0 += chunkSamples, item++) {
                 const int k = (int)(item % (uint64_t)nWaves);
                 cudaStream_t st = streams[k];
                 const wf::Wave &w = waves[k];
@@ -601,7 +626,7 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
                     CUDA_TRY(cudaEventSynchronize(c->evItem[item % Dev::RING]));
                     c->progress = (float)(item - Dev::RING + 1) / (float)totalItems;
                 }
-                const uint32_t ns = std::min(chunkSamples, rp->batch_size - s0);
+                const uint32_t ns = std::min(chunkSamples, itemSamples - s0);
                 const uint32_t nSlots = ns * nPixLocal;
                 CUDA_TRY(cudaMemsetAsync(w.counters, 0, (size_t)(rp->depth + 2) * wf::CNT_STRIDE * sizeof(uint32_t), st));
                 wf::k_raygen<<<(nSlots + 255) / 256, 256, 0, st>>>(w, rc, nSlots, b * rp->batch_size + s0);

@@ -1253,12 +1253,12 @@ __global__ void __launch_bounds__(256) k_accumulate(Wave w, const __grid_constan
     accN[pixel] = make_float4(n.x + cn.x, n.y + cn.y, n.z + cn.z, n.w);
 }
 
-/* tile split: block k fills the pixels of this rank's k-th tile (tiles rank, rank + world, ... in row-major tile order), tile by
- * tile, row-major inside the tile; offsets[k] = first local pixel index of tile k (edge tiles are smaller) */
-__global__ void __launch_bounds__(256) k_tile_pixmap(uint32_t W, uint32_t H, uint32_t tile, uint32_t rank, uint32_t world, const uint32_t *__restrict__ offsets,
+/* tile split: block k fills the pixels of this rank's k-th tile (tileIds[k], row-major tile index), row-major inside the tile;
+ * offsets[k] = first local pixel index of tile k (edge tiles are smaller) */
+__global__ void __launch_bounds__(256) k_tile_pixmap(uint32_t W, uint32_t H, uint32_t tile, const uint32_t *__restrict__ tileIds, const uint32_t *__restrict__ offsets,
                                                      uint32_t *__restrict__ pixmap) {
     const uint32_t tilesX = (W + tile - 1) / tile;
-    const uint32_t t = rank + blockIdx.x * world, tx = t % tilesX, ty = t / tilesX;
+    const uint32_t t = tileIds[blockIdx.x], tx = t % tilesX, ty = t / tilesX;
     const uint32_t x0 = tx * tile, y0 = ty * tile, tw = min(tile, W - x0), th = min(tile, H - y0);
     const uint32_t base = offsets[blockIdx.x];
     for (uint32_t i = threadIdx.x; i < tw * th; i += blockDim.x) pixmap[base + i] = (y0 + i / tw) * W + x0 + i % tw;
