@@ -453,3 +453,112 @@ def test_offlinerender_without_gpu_fails_loudly(capi):
     r = subprocess.run([exe, "--scene", "Cornell", "--width", "8", "--height", "8", "--spp", "1", "--batch", "1"], stdout=subprocess.PIPE,
                        stderr=subprocess.PIPE, text=True, cwd=ROOT)
     assert r.returncode == 1 and "no CUDA device" in r.stderr
+
+
+# ---------------------------------------------------------------- PNG variants the bundled assets do not cover
+def _png(w, h, color_type, bit_depth, pixels, interlace=0, palette=None, trns=None):
+    """minimal PNG writer for the tests: `pixels[y][x]` = tuple of samples (raw sample values at the given bit depth); filter 0"""
+    import zlib
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+
+    nch = {0: 1, 2: 3, 3: 1, 4: 2, 6: 4}[color_type]
+
+    def rows(xs, ys):
+        out = bytearray()
+        for y in ys:
+            out.append(0)
+            bits, acc, nbits = [], 0, 0
+            row = bytearray()
+            for x in xs:
+                for sample in pixels[y][x][:nch]:
+                    if bit_depth == 16:
+                        row += struct.pack(">H", sample)
+                    elif bit_depth == 8:
+                        row.append(sample)
+                    else:
+                        acc = (acc << bit_depth) | sample
+                        nbits += bit_depth
+                        if nbits == 8:
+                            row.append(acc)
+                            acc = nbits = 0
+            if nbits:
+                row.append(acc << (8 - nbits))
+            out += row
+        return bytes(out)
+
+    if interlace:
+        raw = b""
+        for x0, y0, dx, dy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+            xs, ys = range(x0, w, dx), range(y0, h, dy)
+            if len(xs) and len(ys):
+                raw += rows(xs, ys)
+    else:
+        raw = rows(range(w), range(h))
+    data = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, bit_depth, color_type, 0, 0, interlace))
+    if palette is not None:
+        data += chunk(b"PLTE", bytes(v for rgb in palette for v in rgb))
+    if trns is not None:
+        data += chunk(b"tRNS", bytes(trns))
+    return data + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+
+
+PNG_VARIANTS = [(0, 1, 0), (0, 2, 0), (0, 4, 1), (0, 8, 1), (0, 16, 0), (2, 8, 1), (2, 16, 1), (3, 1, 0), (3, 2, 1), (3, 4, 0), (3, 8, 1), (4, 8, 1), (4, 16, 0),
+                (6, 8, 1), (6, 16, 1)]
+
+
+@pytest.mark.parametrize("color_type,bit_depth,interlace", PNG_VARIANTS)
+def test_png_variants_match_reference_decoder(capi, tmp_path, color_type, bit_depth, interlace):
+    """every colour type / bit depth stb_image accepts, plain and Adam7-interlaced, at a size that is no multiple of 8: decoded like
+    the reference's decoder (oracle/_ref/stb_decode when this container has it) and like PIL's independent one"""
+    import io
+    import subprocess
+    from PIL import Image
+    rng = np.random.default_rng(color_type * 100 + bit_depth)
+    w, h = 13, 11
+    maxv = (1 << bit_depth) - 1
+    pixels = [[tuple(int(v) for v in rng.integers(0, maxv + 1, 4)) for _ in range(w)] for _ in range(h)]
+    palette = [tuple(int(v) for v in rng.integers(0, 256, 3)) for _ in range(1 << min(bit_depth, 8))] if color_type == 3 else None
+    trns = [int(v) for v in rng.integers(0, 256, 5)] if color_type == 3 and bit_depth >= 4 else None
+    data = _png(w, h, color_type, bit_depth, pixels, interlace, palette, trns)
+    img, src_ch = capi.decode_image(data)
+    assert img.shape[:2] == (h, w)
+    # PIL as an independent decoder (16-bit samples: the high byte, like stb's conversion to 8 bits)
+    pil = Image.open(io.BytesIO(data))
+    if bit_depth == 16:
+        want = np.array([[[s >> 8 for s in px] for px in row] for row in pixels], np.uint8)
+        n = {0: 1, 2: 3, 4: 2, 6: 4}[color_type]
+        want = want[..., :n]
+        want = {1: lambda a: np.concatenate([a, a, a, np.full_like(a, 255)], -1), 2: lambda a: np.concatenate([a[..., :1]] * 3 + [a[..., 1:]], -1),
+                3: lambda a: np.concatenate([a, np.full_like(a[..., :1], 255)], -1), 4: lambda a: a}[n](want)
+    else:
+        want = np.asarray(pil.convert("RGBA"))
+    got = img if img.shape[2] == 4 else np.concatenate([img] * 3 + [np.full_like(img, 255)], -1)
+    assert np.array_equal(got, want), (color_type, bit_depth, interlace)
+    stb = os.path.join(ROOT, "oracle", "_ref", "stb_decode")
+    if os.path.exists(stb):  # the reference's own decoder, bit for bit (incl. the channel count it reports)
+        f = tmp_path / "v.png"
+        f.write_bytes(data)
+        r = subprocess.run([stb, str(f)], stdout=subprocess.PIPE, check=True).stdout
+        head, _, body = r.partition(b"\n")
+        sw, sh, sc = (int(x) for x in head.split())
+        ref = np.frombuffer(body, np.uint8).reshape(sh, sw, 4)
+        assert (sw, sh) == (w, h) and np.array_equal(got, ref) and src_ch == sc
+
+
+def test_malformed_png_is_rejected_not_trusted(capi):
+    good = _png(4, 4, 2, 8, [[(1, 2, 3, 4)] * 4] * 4)
+    assert capi.decode_image(good)[0].shape == (4, 4, 4)
+    sig = good[:8]
+
+    def ihdr(w, h, depth=8, ctype=2, length=13):
+        body = struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0)[:length]
+        return sig + struct.pack(">I", length) + b"IHDR" + body + b"\0\0\0\0" + good[33:]
+
+    bad = [good[:20], ihdr(4, 4, length=9), ihdr(1 << 20, 1 << 20), ihdr(0, 4), ihdr(4, 4, depth=3), ihdr(4, 4, ctype=5),
+           good[:8] + struct.pack(">I", 0x7fffffff) + good[12:], good[:33] + good[33 + 12:],  # absurd chunk length; IDAT header cut
+           sig + good[33:]]  # no IHDR
+    for k, b in enumerate(bad):
+        with pytest.raises(RuntimeError):
+            capi.decode_image(b)

@@ -21,6 +21,10 @@ static bool readFile(const std::string &path, std::vector<uint8_t> &out) {
     std::fseek(f, 0, SEEK_END);
     long n = std::ftell(f);
     std::fseek(f, 0, SEEK_SET);
+    if (n < 0) { /* not seekable / error */
+        std::fclose(f);
+        return false;
+    }
     out.resize((size_t)n);
     size_t got = n > 0 ? std::fread(out.data(), 1, (size_t)n, f) : 0;
     std::fclose(f);
@@ -42,30 +46,33 @@ static uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint3
 
 static const uint8_t kPngSignature[8] = {137, 80, 78, 71, 13, 10, 26, 10};
 
-/* PNG from memory; rows top first.  srcChannels = the channel count stbi reports for the file */
+/* PNG from memory; rows top first.  srcChannels = the channel count stbi reports for the file.  Accepts what the reference's decoder
+ * (stb_image) accepts: colour types 0 / 2 / 3 / 4 / 6, bit depths 1 / 2 / 4 / 8 / 16 (16 keeps the high byte, sub-byte grey is scaled
+ * to 0..255), Adam7 interlacing; like stb it does not verify chunk CRCs.  The file is not trusted: chunk lengths, the IHDR size, the
+ * image dimensions (w * h <= 2^28 pixels) and the inflated size are checked before anything is allocated or indexed. */
 static bool decodePNG(const uint8_t *bytes, size_t nBytes, ImageU8 &out, int *srcChannels) {
     if (nBytes < 33 || std::memcmp(bytes, kPngSignature, 8) != 0) return false;
-    struct View {
-        const uint8_t *d;
-        size_t n;
-        size_t size() const { return n; }
-        const uint8_t &operator[](size_t i) const { return d[i]; }
-    } file{bytes, nBytes};
     uint32_t w = 0, h = 0;
     int bitDepth = 0, colorType = 0, interlace = 0;
+    bool haveHeader = false;
     std::vector<uint8_t> idat, plte, trns;
     size_t pos = 8;
-    while (pos + 12 <= file.size()) {
-        uint32_t len = be32(&file[pos]);
-        const uint8_t *type = &file[pos + 4];
-        const uint8_t *data = &file[pos + 8];
-        if (pos + 12 + len > file.size()) return false;
+    while (pos + 12 <= nBytes) {
+        const uint32_t len = be32(bytes + pos);
+        const uint8_t *type = bytes + pos + 4;
+        const uint8_t *data = bytes + pos + 8;
+        if ((size_t)len > nBytes - pos - 12) return false;
         if (!std::memcmp(type, "IHDR", 4)) {
+            if (len != 13 || haveHeader) return false;
             w = be32(data);
             h = be32(data + 4);
             bitDepth = data[8];
             colorType = data[9];
+            if (data[10] != 0 || data[11] != 0) return false; /* compression / filter method */
             interlace = data[12];
+            haveHeader = true;
+        } else if (!haveHeader) {
+            return false; /* IHDR must come first */
         } else if (!std::memcmp(type, "PLTE", 4)) {
             plte.assign(data, data + len);
         } else if (!std::memcmp(type, "tRNS", 4)) {
@@ -75,66 +82,113 @@ static bool decodePNG(const uint8_t *bytes, size_t nBytes, ImageU8 &out, int *sr
         } else if (!std::memcmp(type, "IEND", 4)) {
             break;
         }
-        pos += 12 + len;
+        pos += 12 + (size_t)len;
     }
-    if (w == 0 || h == 0 || interlace != 0) return false;
-    if (bitDepth != 8 && bitDepth != 16) return false;
-    int srcCh = colorType == 0 ? 1 : colorType == 2 ? 3 : colorType == 3 ? 1 : colorType == 4 ? 2 : colorType == 6 ? 4 : 0;
+    if (!haveHeader || w == 0 || h == 0 || interlace > 1) return false;
+    if ((uint64_t)w * h > (1ull << 28)) return false;
+    const int srcCh = colorType == 0 ? 1 : colorType == 2 ? 3 : colorType == 3 ? 1 : colorType == 4 ? 2 : colorType == 6 ? 4 : 0;
     if (!srcCh) return false;
-    int bps = bitDepth / 8;
-    size_t stride = (size_t)w * srcCh * bps;
-    std::vector<uint8_t> raw((stride + 1) * h);
+    const bool depthOk = colorType == 0 ? (bitDepth == 1 || bitDepth == 2 || bitDepth == 4 || bitDepth == 8 || bitDepth == 16)
+                       : colorType == 3 ? (bitDepth == 1 || bitDepth == 2 || bitDepth == 4 || bitDepth == 8)
+                                        : (bitDepth == 8 || bitDepth == 16);
+    if (!depthOk) return false;
+    const int bitsPerPixel = srcCh * bitDepth;
+    const int bpp = std::max(1, bitsPerPixel / 8); /* filter distance in bytes */
+    /* the (sub-)images the stream holds: the whole image, or the seven Adam7 passes */
+    struct Pass {
+        uint32_t x0, y0, dx, dy, pw, ph;
+        size_t stride;
+    };
+    std::vector<Pass> passes;
+    if (interlace == 0) {
+        passes.push_back({0, 0, 1, 1, w, h, 0});
+    } else {
+        const uint32_t xo[7] = {0, 4, 0, 2, 0, 1, 0}, yo[7] = {0, 0, 4, 0, 2, 0, 1}, xs[7] = {8, 8, 4, 4, 2, 2, 1}, ys[7] = {8, 8, 8, 4, 4, 2, 2};
+        for (int k = 0; k < 7; k++) {
+            const uint32_t pw = w > xo[k] ? (w - xo[k] + xs[k] - 1) / xs[k] : 0, ph = h > yo[k] ? (h - yo[k] + ys[k] - 1) / ys[k] : 0;
+            if (pw && ph) passes.push_back({xo[k], yo[k], xs[k], ys[k], pw, ph, 0});
+        }
+    }
+    size_t rawSize = 0;
+    for (Pass &ps : passes) {
+        ps.stride = ((size_t)ps.pw * bitsPerPixel + 7) / 8;
+        rawSize += (ps.stride + 1) * ps.ph;
+    }
+    std::vector<uint8_t> raw(rawSize);
     uLongf rawLen = (uLongf)raw.size();
-    if (uncompress(raw.data(), &rawLen, idat.data(), (uLong)idat.size()) != Z_OK || rawLen != raw.size()) return false;
-    /* unfilter */
-    int bpp = srcCh * bps;
-    std::vector<uint8_t> img(stride * h);
-    for (uint32_t y = 0; y < h; y++) {
-        int ft = raw[y * (stride + 1)];
-        const uint8_t *src = &raw[y * (stride + 1) + 1];
-        uint8_t *dst = &img[y * stride];
-        const uint8_t *up = y ? &img[(y - 1) * stride] : nullptr;
-        for (size_t i = 0; i < stride; i++) {
-            int a = i >= (size_t)bpp ? dst[i - bpp] : 0;
-            int b = up ? up[i] : 0;
-            int c = (up && i >= (size_t)bpp) ? up[i - bpp] : 0;
-            int v = src[i];
-            switch (ft) {
-                case 0: break;
-                case 1: v += a; break;
-                case 2: v += b; break;
-                case 3: v += (a + b) >> 1; break;
-                case 4: {
-                    int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
-                    v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-                    break;
+    if (idat.empty() || uncompress(raw.data(), &rawLen, idat.data(), (uLong)idat.size()) != Z_OK || rawLen != raw.size()) return false;
+    /* unfilter every pass in place (row by row, previous row of the SAME pass), then scatter its samples: one byte per sample
+     * (the high byte of 16-bit samples, sub-byte samples unpacked) into img[h][w][srcCh] */
+    std::vector<uint8_t> img((size_t)w * h * srcCh);
+    std::vector<uint8_t> cur, prev;
+    size_t rp = 0;
+    const int greyScale = (colorType == 0 && bitDepth < 8) ? 255 / ((1 << bitDepth) - 1) : 1;
+    for (const Pass &ps : passes) {
+        cur.assign(ps.stride, 0);
+        prev.assign(ps.stride, 0);
+        for (uint32_t y = 0; y < ps.ph; y++) {
+            const int ft = raw[rp];
+            const uint8_t *src = &raw[rp + 1];
+            rp += ps.stride + 1;
+            for (size_t i = 0; i < ps.stride; i++) {
+                const int a = i >= (size_t)bpp ? cur[i - bpp] : 0;
+                const int b = y ? prev[i] : 0;
+                const int c = (y && i >= (size_t)bpp) ? prev[i - bpp] : 0;
+                int v = src[i];
+                switch (ft) {
+                    case 0: break;
+                    case 1: v += a; break;
+                    case 2: v += b; break;
+                    case 3: v += (a + b) >> 1; break;
+                    case 4: {
+                        const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+                        v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+                        break;
+                    }
+                    default: return false;
                 }
-                default: return false;
+                cur[i] = (uint8_t)v;
             }
-            dst[i] = (uint8_t)v;
+            const uint32_t oy = ps.y0 + y * ps.dy;
+            for (uint32_t x = 0; x < ps.pw; x++) {
+                uint8_t *dst = &img[((size_t)oy * w + (ps.x0 + x * ps.dx)) * srcCh];
+                for (int ch = 0; ch < srcCh; ch++) {
+                    const size_t sample = (size_t)x * srcCh + ch;
+                    if (bitDepth == 16)
+                        dst[ch] = cur[sample * 2];
+                    else if (bitDepth == 8)
+                        dst[ch] = cur[sample];
+                    else {
+                        const size_t bit = sample * bitDepth;
+                        const int v = (cur[bit >> 3] >> (8 - bitDepth - (int)(bit & 7))) & ((1 << bitDepth) - 1);
+                        dst[ch] = (uint8_t)(v * greyScale);
+                    }
+                }
+            }
+            cur.swap(prev);
         }
     }
     /* channel count as stbi_info reports it; 1 stays 1, everything else is forced to RGBA
      * (Image<stbi_uc>::loadDiskImage) */
-    int infoCh = colorType == 3 ? (trns.empty() ? 3 : 4) : srcCh;
+    const int infoCh = colorType == 3 ? (trns.empty() ? 3 : 4) : srcCh;
     out.width = (int)w;
     out.height = (int)h;
     out.channels = infoCh == 1 ? 1 : 4;
     out.data.resize((size_t)w * h * out.channels);
     for (size_t p = 0; p < (size_t)w * h; p++) {
-        const uint8_t *s = &img[p * bpp];
+        const uint8_t *sp = &img[p * srcCh];
         uint8_t px[4] = {0, 0, 0, 255};
         switch (colorType) {
-            case 0: px[0] = px[1] = px[2] = s[0]; break;
-            case 2: px[0] = s[0]; px[1] = s[bps]; px[2] = s[2 * bps]; break;
+            case 0: px[0] = px[1] = px[2] = sp[0]; break;
+            case 2: px[0] = sp[0]; px[1] = sp[1]; px[2] = sp[2]; break;
             case 3: {
-                size_t k = s[0];
+                const size_t k = sp[0];
                 if (k * 3 + 2 < plte.size()) { px[0] = plte[k * 3]; px[1] = plte[k * 3 + 1]; px[2] = plte[k * 3 + 2]; }
                 if (k < trns.size()) px[3] = trns[k];
                 break;
             }
-            case 4: px[0] = px[1] = px[2] = s[0]; px[3] = s[bps]; break;
-            case 6: px[0] = s[0]; px[1] = s[bps]; px[2] = s[2 * bps]; px[3] = s[3 * bps]; break;
+            case 4: px[0] = px[1] = px[2] = sp[0]; px[3] = sp[1]; break;
+            case 6: px[0] = sp[0]; px[1] = sp[1]; px[2] = sp[2]; px[3] = sp[3]; break;
         }
         if (out.channels == 1)
             out.data[p] = px[0];
