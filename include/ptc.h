@@ -208,7 +208,7 @@ typedef struct ptc_stats {
     uint64_t upload_bytes;    /* host -> device bytes of the last ptc_upload_scene, per device (textures / the environment that stayed
                                  resident by uid are not copied and not counted) */
     double reduce_ms;         /* multi-GPU: the NCCL reduce of the accumulation buffers inside the last render */
-    double bin_ms;            /* time inside the ray-binning kernel (PTC_FLAG_TIME_KERNELS) */
+    double reserved_ms;       /* (was: time inside the ray-binning kernel of a rejected experiment) */
     uint64_t accel_levels;    /* 1 = one tree over world triangles, 2 = per-mesh trees under an instance tree */
     uint64_t traversal_bytes; /* nodes + triangles the traversal kernels read */
 } ptc_stats;

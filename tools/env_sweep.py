@@ -27,7 +27,7 @@ for flags in (0, 0, capi.PTC_FLAG_TIME_KERNELS):
     if flags == 0:
         out["Mseg_s"] = st["segments"] / st["render_ms"] / 1e3; out["ms_batch"] = st["render_ms"] / batches; out["mean"] = float(img[..., :3].mean())
     else:
-        out.update({"extend": st["trace_ms"] / batches, "shade": st["shade_ms"] / batches, "chains": st["shadow_ms"] / batches, "bin": st["bin_ms"] / batches,
+        out.update({"extend": st["trace_ms"] / batches, "shade": st["shade_ms"] / batches, "chains": st["shadow_ms"] / batches, "bin": 0.0,
                     "timed_total": st["render_ms"] / batches, "reserved": st["reserved"], "segments": st["segments"]})
 print(json.dumps(out))
 ''' % ROOT

@@ -81,7 +81,7 @@ class ptc_stats(C.Structure):
                 ("probe_hops", u64), ("render_ms", C.c_double), ("trace_ms", C.c_double), ("shade_ms", C.c_double),
                 ("shadow_ms", C.c_double), ("build_ms", C.c_double), ("trace_launches", u64), ("kernel_launches", u64),
                 ("n_triangles", u64), ("n_bvh_nodes", u64), ("scene_bytes", u64), ("reserved", u64 * 4),
-                ("upload_bytes", u64), ("reduce_ms", C.c_double), ("bin_ms", C.c_double), ("accel_levels", u64), ("traversal_bytes", u64)]
+                ("upload_bytes", u64), ("reduce_ms", C.c_double), ("reserved_ms", C.c_double), ("accel_levels", u64), ("traversal_bytes", u64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -82,7 +82,6 @@ struct Dev {
     struct WaveBufs {
         DBuf<float4> orgRng, dirFlags, beta, radiance, hit, aovA, aovN, shOrg, shDir, shContrib, prBeta;
         DBuf<uint32_t> queue0, queue1, qShadow, qProbe, counters, hitInst;
-        DBuf<uint16_t> qKey;
         DBuf<unsigned long long> stats;
         size_t capacity = 0;
     } wave[2];
@@ -100,7 +99,6 @@ struct Dev {
      * 2069 Mseg/s alone (profiles/r1_v4_kernel_experiments.log) - k_shade needs >= 3 blocks per SM to keep DRAM busy and k_extend
      * loses as much with 4 as the overlap wins.  PTC_OVERLAP=t,s / PTC_OVERLAP=0 for experiments. */
     int overlapTrace = 64, overlapShade = 64;
-    uint32_t binMode = 0;   /* PTC_BIN: ray binning between bounces (wf::k_bin_window) */
     uint32_t tileOrder = 0; /* PTC_TILE_ORDER: tile edge of the single-rank pixel walk, 0 = row major */
     float sceneLo[3] = {0, 0, 0}, sceneHi[3] = {0, 0, 0}; /* world box of the scene (from the build) */
 
@@ -392,7 +390,6 @@ void ensureWave(Dev *c, int k, size_t slots, uint32_t depth) {
         w.queue1.alloc(slots);
         w.qShadow.alloc(slots);
         w.qProbe.alloc(slots);
-        w.qKey.alloc(slots);
         if (c->twoLevel) w.hitInst.alloc(slots);
         w.capacity = slots;
     }
@@ -418,7 +415,6 @@ wf::Wave makeWave(Dev *c, int k) {
     w.queue[1] = b.queue1.p;
     w.qShadow = b.qShadow.p;
     w.qProbe = b.qProbe.p;
-    w.qKey = b.qKey.p;
     w.hitInst = b.hitInst.p;
     w.counters = b.counters.p;
     w.stats = b.stats.p;
@@ -537,12 +533,7 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
     rc.flags = rp->flags;
     rc.nPixLocal = nPixLocal;
     rc.pixmap = pixmapPtr;
-    rc.binMode = c->nWorldTris > 0 ? c->binMode : 0u;
-    for (int a = 0; a < 3; a++) {
-        rc.binLo[a] = c->sceneLo[a];
-        const float ext = c->sceneHi[a] - c->sceneLo[a];
-        rc.binScale[a] = ext > 0.0f ? 8.0f / ext : 0.0f;
-    }
+
     DScene sc = makeDScene(c);
 
     /* persistent kernels: exactly as many blocks as are resident at once (multiples of the SM count) */
@@ -573,15 +564,7 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
     const int gridShadow = residentGrid((const void *)shadowFn, TRV_BLOCK, capTrace);
     const int gridProbe = residentGrid((const void *)probeFn, TRV_BLOCK, capTrace);
     uint64_t launches = 0, traceLaunches = 0;
-    double traceMs = 0, shadeMs = 0, shadowMs = 0, binMs = 0;
-    const size_t binSmemBytes = ((size_t)(1u << BIN_KEY_BITS) + BIN_WINDOW) * 4 + (size_t)BIN_WINDOW * 2;
-    int gridBin = c->smCount;
-    if (rc.binMode != 0u) {
-        CUDA_TRY(cudaFuncSetAttribute((const void *)wf::k_bin_window, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)binSmemBytes));
-        int perSm = 1;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, (const void *)wf::k_bin_window, BIN_THREADS, binSmemBytes) != cudaSuccess || perSm < 1) perSm = 1;
-        gridBin = c->smCount * perSm;
-    }
+    double traceMs = 0, shadeMs = 0, shadowMs = 0;
     auto timed = [&](double &acc, cudaStream_t st, auto &&launch) {
         if (timeKernels) CUDA_TRY(cudaEventRecord(c->evA, st));
         launch();
@@ -644,12 +627,6 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
                         timed(shadowMs, st, [&] { probeFn<<<gridProbe, TRV_BLOCK, 0, st>>>(w, sc, rc, d, c->tune); });
                         launches++;
                     }
-                    if (rc.binMode != 0u && d + 1 < rp->depth) { /* regroup the survivors before they are traced */
-                        timed(binMs, st, [&] {
-                            wf::k_bin_window<<<gridBin, BIN_THREADS, binSmemBytes, st>>>(w.queue[(d + 1) & 1u], w.qKey, &w.counters[(d + 1) * wf::CNT_STRIDE + wf::CNT_ACTIVE]);
-                        });
-                        launches++;
-                    }
                 }
                 wf::k_collect_stats<<<1, 32, 0, st>>>(w, rp->depth);
                 /* accumulate in item order: item i adds after item i - 1 (which ran on the other stream) */
@@ -690,7 +667,6 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
     c->stats.trace_ms = traceMs;
     c->stats.shade_ms = shadeMs;
     c->stats.shadow_ms = shadowMs;
-    c->stats.bin_ms = binMs;
     c->stats.trace_launches = traceLaunches;
     c->stats.kernel_launches = launches;
     c->progress = 1.0f;
@@ -1086,7 +1062,6 @@ bool renderAll(ptc_ctx *ctx, const ptc_render_params *rp, void *const dOut[3], f
         st.probe_rays += x.probe_rays, st.probe_hops += x.probe_hops, st.trace_launches += x.trace_launches, st.kernel_launches += x.kernel_launches;
         st.render_ms = std::max(st.render_ms, x.render_ms), st.trace_ms = std::max(st.trace_ms, x.trace_ms);
         st.shade_ms = std::max(st.shade_ms, x.shade_ms), st.shadow_ms = std::max(st.shadow_ms, x.shadow_ms);
-        st.bin_ms = std::max(st.bin_ms, x.bin_ms);
         st.build_ms = std::max(st.build_ms, x.build_ms);
         for (int k = 0; k < 4; k++) st.reserved[k] += x.reserved[k];
     }
@@ -1157,7 +1132,6 @@ static void createDev(Dev *c, int device) {
         if (!strcmp(a, "flat")) c->accelMode = PTC_ACCEL_FLAT;
         if (!strcmp(a, "two")) c->accelMode = PTC_ACCEL_TWO_LEVEL;
     }
-    if (const char *b = getenv("PTC_BIN")) c->binMode = (uint32_t)std::min(2, std::max(0, atoi(b)));
     if (const char *t = getenv("PTC_TILE_ORDER")) c->tileOrder = (uint32_t)std::min(64, std::max(0, atoi(t)));
     if (const char *o = getenv("PTC_OVERLAP")) { /* "traceBlocksPerSM,shadeBlocksPerSM"; "0" = one wavefront at a time */
         int a = 0, b = 0;

@@ -200,13 +200,12 @@ struct Trav {
      * depth bound - shared + TRV_STACK entries against at most 63 + 32 binary levels collapsed eightfold, twice on two levels - makes
      * this unreachable for any tree the build produces) */
     PTC_D void push(const Stack &st, uint2 v) {
+        const bool fits = sp < TRV_SHARED_STACK + TRV_STACK;
         if (sp < TRV_SHARED_STACK)
             st.shared[sp * TRV_BLOCK] = v;
-        else if (sp - TRV_SHARED_STACK < TRV_STACK)
+        else if (fits)
             st.spill[sp - TRV_SHARED_STACK] = v;
-        else
-            return;
-        ++sp;
+        sp += fits ? 1 : 0;
     }
 
     /* Visits the nearest pending child node (8 quantised boxes at once): updates the node group and returns the

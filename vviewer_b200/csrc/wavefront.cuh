@@ -44,7 +44,6 @@ struct Wave {
     float4 *shContrib; /* unshadowed contribution rgb */
     float4 *prBetaPdf; /* probe request: beta before roulette .xyz, sampling pdf */
     uint32_t *queue[2];
-    uint16_t *qKey;    /* coherence key of every entry of the NEXT path queue (k_shade writes it, k_bin_window consumes it) */
     uint32_t *qShadow, *qProbe;
     uint32_t *counters; /* [depth + 1][CNT_STRIDE] */
     unsigned long long *stats;
@@ -59,8 +58,6 @@ struct RenderConst {
     uint32_t fuseProbe;      /* opaque, media-free scene: the probe ray of a path that goes on is its next path ray (see k_shade) */
     uint32_t envLight;       /* PTC_FLAG_ENV_IMPORTANCE and an HDRI environment: light index totalLights - 1 is the environment */
     uint32_t flags;
-    uint32_t binMode;        /* 0 = path queues stay in arrival order; 1 / 2 = k_bin_window regroups them (key layouts below) */
-    float binLo[3], binScale[3]; /* world box of the scene -> cell coordinate 0..8 per axis */
     uint32_t nPixLocal;      /* pixels rendered by this rank */
     const uint32_t *pixmap;  /* local pixel -> global pixel, or nullptr = identity */
 };
@@ -82,36 +79,6 @@ PTC_D void queuePush(uint32_t *__restrict__ queue, uint32_t *__restrict__ counte
     base = __shfl_sync(0xffffffffu, base, leader);
     if (pred) queue[base + __popc(m & ((1u << laneId()) - 1u))] = value;
 }
-/* same, and tells the caller where its value went (0xffffffff for lanes that pushed nothing) */
-PTC_D uint32_t queuePushPos(uint32_t *__restrict__ queue, uint32_t *__restrict__ counter, bool pred, uint32_t value) {
-    const unsigned m = __ballot_sync(0xffffffffu, pred);
-    if (m == 0u) return 0xffffffffu;
-    const int leader = __ffs(m) - 1;
-    uint32_t base = 0;
-    if ((int)laneId() == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (!pred) return 0xffffffffu;
-    const uint32_t pos = base + __popc(m & ((1u << laneId()) - 1u));
-    queue[pos] = value;
-    return pos;
-}
-
-/* Coherence key of a path ray (12 bits): the octant of its direction signs - the 8-wide BVH visits children in octant order, so rays of
- * one octant walk a node's children in the same order - and the cell of its origin in an 8 x 8 x 8 grid over the scene (3-bit Morton
- * interleave).  Layout 1: octant major (octant << 9 | cell); layout 2: cell major (cell << 3 | octant). */
-#define BIN_KEY_BITS 12
-PTC_D uint32_t spread3(uint32_t v) { /* 3 bits -> every third bit */
-    return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4);
-}
-PTC_D uint32_t binKey(const RenderConst &rc, float3 o, float3 d) {
-    const uint32_t oct = (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u);
-    const uint32_t cx = (uint32_t)fminf(fmaxf((o.x - rc.binLo[0]) * rc.binScale[0], 0.0f), 7.0f);
-    const uint32_t cy = (uint32_t)fminf(fmaxf((o.y - rc.binLo[1]) * rc.binScale[1], 0.0f), 7.0f);
-    const uint32_t cz = (uint32_t)fminf(fmaxf((o.z - rc.binLo[2]) * rc.binScale[2], 0.0f), 7.0f);
-    const uint32_t cell = (spread3(cx) << 2) | (spread3(cy) << 1) | spread3(cz);
-    return rc.binMode == 2u ? ((cell << 3) | oct) : ((oct << 9) | cell);
-}
-
 PTC_D void statAdd(unsigned long long *stat, uint32_t v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -647,7 +614,7 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
     const bool lastBounce = bounce + 1u >= rc.depth;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += stride) {
         const bool valid = i < count;
-        uint32_t slot = 0, binKeyOf = 0;
+        uint32_t slot = 0;
         bool alive = false;
         Requests rq;
         rq.shadow = rq.probe = false;
@@ -892,7 +859,6 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
                 stS(&w.dirFlags[slot], make_float4(dir.x, dir.y, dir.z, __uint_as_float(flags)));
             }
             if (alive) stS(&w.beta[slot], make_float4(beta.x, beta.y, beta.z, lastPdf));
-            if (alive && rc.binMode != 0u) binKeyOf = binKey(rc, origin, dir);
             if (VOLUMES && alive) {
                 /* how far the next segment has to be traced (ExtendPolicy): inside a medium its free-flight distance is already
                  * determined - the next event draws the same two numbers from the stored state (freeFlight) */
@@ -918,12 +884,7 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
             }
             if (rq.probe || deferProbe) stS(&w.prBetaPdf[slot], make_float4(rq.prBeta.x, rq.prBeta.y, rq.prBeta.z, rq.prPdf));
         }
-        if (rc.binMode != 0u) { /* warp-uniform */
-            const uint32_t pos = queuePushPos(qNext, cntNext, alive, slot);
-            if (alive) w.qKey[pos] = (uint16_t)binKeyOf;
-        } else {
-            queuePush(qNext, cntNext, alive, slot);
-        }
+        queuePush(qNext, cntNext, alive, slot);
         queuePush(w.qShadow, cntShadow, rq.shadow, slot);
         queuePush(w.qProbe, cntProbe, rq.probe, slot);
     }
@@ -1166,69 +1127,6 @@ __global__ void __launch_bounds__(TRV_BLOCK, TL ? TRV_TWO_LEVEL_MINBLOCKS : CHAI
     traceLoop(sc, pol, w.counters[bounce * CNT_STRIDE + CNT_PROBE], &w.counters[bounce * CNT_STRIDE + CNT_FETCH_PROBE], tune, stack,
               stashMem + threadIdx.x, cnt);
     statAdd(&w.stats[ST_PROBE_HOPS], pol.hops);
-}
-
-/* ------------------------------------------------------------------ k_bin_window: ray binning between bounces
- * After a diffuse bounce the 32 rays of a warp point anywhere: the traversal loop then runs at ~21 of 32 lanes per instruction and its
- * node fetches miss L1.  A GLOBAL sort of the queue would fix that and break something worse: the path state is addressed by slot, and
- * the queue's arrival order keeps the slots of neighbouring entries within a ~150 k-slot range that L2 absorbs; sorted globally, every
- * 16-byte state access becomes a random DRAM sector.  So the queue is regrouped INSIDE windows of BIN_WINDOW consecutive entries, one
- * block per window, with a counting sort in shared memory over the 12-bit key k_shade wrote next to each entry: a warp of the next
- * k_extend / k_shade then holds rays of one octant from one region of the scene, and the state traffic keeps its locality.  The order
- * inside a bin is arbitrary, which changes nothing: every result is per slot. */
-#define BIN_WINDOW 16384
-#define BIN_THREADS 1024
-__global__ void __launch_bounds__(BIN_THREADS) k_bin_window(uint32_t *__restrict__ queue, const uint16_t *__restrict__ keys, const uint32_t *__restrict__ countPtr) {
-    extern __shared__ uint32_t binSmem[];
-    uint32_t *hist = binSmem;                             /* 1 << BIN_KEY_BITS counters, then bin cursors */
-    uint32_t *slots = hist + (1u << BIN_KEY_BITS);        /* BIN_WINDOW */
-    uint16_t *ks = (uint16_t *)(slots + BIN_WINDOW);      /* BIN_WINDOW */
-    __shared__ uint32_t warpSums[BIN_THREADS / 32];
-    const uint32_t count = *countPtr;
-    const uint32_t nBins = 1u << BIN_KEY_BITS, perThread = nBins / BIN_THREADS;
-    for (uint32_t base = blockIdx.x * BIN_WINDOW; base < count; base += gridDim.x * BIN_WINDOW) {
-        const uint32_t n = min((uint32_t)BIN_WINDOW, count - base);
-        for (uint32_t b = threadIdx.x; b < nBins; b += BIN_THREADS) hist[b] = 0u;
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n; i += BIN_THREADS) {
-            const uint32_t k = keys[base + i];
-            ks[i] = (uint16_t)k;
-            slots[i] = queue[base + i];
-            atomicAdd(&hist[k], 1u);
-        }
-        __syncthreads();
-        /* exclusive scan of the histogram: perThread consecutive bins per thread, warp scan, scan of the warp sums */
-        uint32_t local[perThread], sum = 0;
-#pragma unroll
-        for (uint32_t j = 0; j < perThread; j++) {
-            local[j] = sum;
-            sum += hist[threadIdx.x * perThread + j];
-        }
-        uint32_t incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)laneId() >= o) incl += t;
-        }
-        if (laneId() == 31u) warpSums[threadIdx.x >> 5] = incl;
-        __syncthreads();
-        if (threadIdx.x < 32u) {
-            uint32_t v = warpSums[threadIdx.x], in2 = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, in2, o);
-                if ((int)threadIdx.x >= o) in2 += t;
-            }
-            warpSums[threadIdx.x] = in2 - v;
-        }
-        __syncthreads();
-        const uint32_t before = warpSums[threadIdx.x >> 5] + incl - sum;
-#pragma unroll
-        for (uint32_t j = 0; j < perThread; j++) hist[threadIdx.x * perThread + j] = before + local[j];
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n; i += BIN_THREADS) queue[base + atomicAdd(&hist[ks[i]], 1u)] = slots[i];
-        __syncthreads();
-    }
 }
 
 /* ------------------------------------------------------------------ k_accumulate (raygen.rgen.glsl:126-144) */
