@@ -98,8 +98,7 @@ PTC_D uint32_t permutationElement(uint32_t i, uint32_t l, uint32_t p) { /* rng_p
 PTC_D uint32_t pmjHash(uint32_t px, uint32_t py, uint32_t dimension) { /* rng_pmj.glsl:73-74, 92-94 */
     return (uint32_t)mixBits(((uint64_t)px << 48) ^ ((uint64_t)py << 32) ^ ((uint64_t)dimension << 16) ^ (uint64_t)PMJ_SEED);
 }
-/* (out of line: the default sampler's call sites stay small - inlining these into every rnd() of k_shade cost it 3 %) */
-__device__ __noinline__ float pmjRand1D(Rng &r) { /* rng_pmj.glsl:71-83 */
+PTC_D float pmjRand1D(Rng &r) { /* rng_pmj.glsl:71-83 */
     const uint32_t px = r.pixelSeed & 0xffffu, py = r.pixelSeed >> 16;
     const uint32_t idx = permutationElement(r.index, g_pmj.spp, pmjHash(px, py, r.s));
     /* include/rng/bluenoise.glsl:1-8: data[texture][pixel.x][pixel.y] */
@@ -107,7 +106,7 @@ __device__ __noinline__ float pmjRand1D(Rng &r) { /* rng_pmj.glsl:71-83 */
     r.s += 1u;
     return fminf(__fdiv_rn(__fadd_rn((float)idx, delta), (float)g_pmj.spp), ONEMINUSEPSILON);
 }
-__device__ __noinline__ float2 pmjRand2D(Rng &r) { /* rng_pmj.glsl:85-107 (BLUE_NOISE_2D is not defined) */
+PTC_D float2 pmjRand2D(Rng &r) { /* rng_pmj.glsl:85-107 (BLUE_NOISE_2D is not defined) */
     uint32_t idx = r.index;
     const uint32_t inst = r.s / 2u;
     if (inst >= PMJ_N_SEQUENCES) idx = permutationElement(r.index, g_pmj.spp, pmjHash(r.pixelSeed & 0xffffu, r.pixelSeed >> 16, r.s));

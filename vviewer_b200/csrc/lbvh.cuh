@@ -814,6 +814,12 @@ __global__ void k_gather_shading(uint32_t n, const uint32_t *__restrict__ wideOr
     r[8] = make_float4(c.tangent[0], c.tangent[1], c.tangent[2], 0.0f);
 }
 
+/* the traversal stack holds one postponed node group per level of the wide tree (traverse.cuh); its capacity is fixed */
+inline void checkStackDepth(uint32_t levels) {
+    const uint32_t capacity = 8u + 88u; /* TRV_SHARED_STACK + TRV_STACK */
+    if (levels + 4u > capacity) throw CudaError{"acceleration structure too deep for the traversal stack (" + std::to_string(levels) + " levels)"};
+}
+
 struct Build {
     DBuf<float4> trisUnsorted, triLo, triHi, nodeLo, nodeHi;
     DBuf<float4> shading;          /* 9 x float4 per triangle, traversal order (k_gather_shading) */
@@ -983,6 +989,7 @@ struct Build {
         if (wr.nTris != n) throw CudaError{"wide BVH collapse lost triangles"};
         nWide = wr.nWide;
         wideLevels = wr.levels;
+        checkStackDepth(wideLevels);
         return launches;
     }
 
@@ -1088,7 +1095,7 @@ struct TwoLevel {
         DBuf<float4> tris;      /* bottom level only */
         DBuf<float4> shading;   /* bottom level only */
         DBuf<uint32_t> order;   /* tree position -> primitive (triangle of the mesh / instance) */
-        uint32_t nNodes = 0, nPrims = 0, nodeBase = 0, triBase = 0;
+        uint32_t nNodes = 0, nPrims = 0, nodeBase = 0, triBase = 0, levels = 0;
         float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
     };
     Build work; /* scratch of every tree build */
@@ -1107,6 +1114,7 @@ struct TwoLevel {
     void keep(Tree &t, bool bottom, cudaStream_t s) {
         t.nNodes = work.nWide;
         t.nPrims = work.n;
+        t.levels = work.wideLevels;
         t.nodes.alloc(5 * (size_t)std::max(1u, t.nNodes));
         CUDA_TRY(cudaMemcpyAsync(t.nodes.p, work.wide.p, (size_t)t.nNodes * 80, cudaMemcpyDeviceToDevice, s));
         t.order.alloc(std::max(1u, t.nPrims));
@@ -1165,6 +1173,11 @@ struct TwoLevel {
             hostSyncs += work.hostSyncs + 1;
         } else {
             tlas.nNodes = tlas.nPrims = 0;
+        }
+        {
+            uint32_t deepest = 0;
+            for (auto &t : blas) deepest = std::max(deepest, t->levels);
+            checkStackDepth(tlas.levels + deepest + 2u); /* + the marker and the rest of the instance leaf */
         }
         /* ---- assembly */
         nNodes = tlas.nNodes + nodeTotal;

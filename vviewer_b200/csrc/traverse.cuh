@@ -196,16 +196,14 @@ struct Trav {
         --sp;
         return sp < TRV_SHARED_STACK ? st.shared[sp * TRV_BLOCK] : st.spill[sp - TRV_SHARED_STACK];
     }
-    /* (an entry beyond the spill array is dropped WITHOUT moving the stack pointer, so a later pop never reads past the array; the
-     * depth bound - shared + TRV_STACK entries against at most 63 + 32 binary levels collapsed eightfold, twice on two levels - makes
-     * this unreachable for any tree the build produces) */
+    /* (no bounds test here: ptc_build_accel refuses a tree whose depth - one postponed group per level, plus the marker and the leaf rest
+     * of the top level on two levels - does not fit TRV_SHARED_STACK + TRV_STACK entries; lbvh.cuh::checkStackDepth) */
     PTC_D void push(const Stack &st, uint2 v) {
-        const bool fits = sp < TRV_SHARED_STACK + TRV_STACK;
         if (sp < TRV_SHARED_STACK)
             st.shared[sp * TRV_BLOCK] = v;
-        else if (fits)
+        else
             st.spill[sp - TRV_SHARED_STACK] = v;
-        sp += fits ? 1 : 0;
+        ++sp;
     }
 
     /* Visits the nearest pending child node (8 quantised boxes at once): updates the node group and returns the

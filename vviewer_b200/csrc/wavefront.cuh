@@ -478,7 +478,7 @@ PTC_D void traceLoop(const DScene &sc, Policy &pol, uint32_t count, uint32_t *fe
                 } while (__popc(mT) >= tune.triLeave || (mT & ~mN) != 0u);
             }
             /* query complete: nothing left to visit, or an occlusion query that already has its answer */
-            const bool moreWork = tr.ng.y > 0x00ffffffu || hasTri || (Policy::TWO_LEVEL && (tr.sp > 0 || tr.ig.y != 0u));
+            const bool moreWork = Policy::TWO_LEVEL ? (tr.ng.y > 0x00ffffffu || hasTri || tr.sp > 0 || tr.ig.y != 0u) : (hasNode || hasTri);
             if (active && (!moreWork || (pol.anyHit() && tr.best.pos >= 0))) {
                 if constexpr (Policy::TWO_LEVEL) {
                     if (!tr.top) tr.leaveInstance(); /* an occlusion query may end inside an instance: the policy sees the world-space ray */
@@ -600,7 +600,10 @@ PTC_D bool roulette(Rng &rng, uint32_t depth, float3 &beta) {
 #ifndef SHADE_MINBLOCKS_LV
 #define SHADE_MINBLOCKS_LV 6 /* the instantiation with lights AND media (the largest): fog 5: 1291, 6: 1298, 7: 1273, 8: 1266 Mseg/s */
 #endif
-template <bool LIGHTS, bool VOLUMES>
+/* SAMPLER (0 default stream, 1 Sobol, 2 PMJ02BN) is a compile-time switch too: the generators are inlined at every rnd() of this
+ * kernel, and carrying the two table / hash based ones as run-time branches cost the default path 3-7 % (A/B against the round-1
+ * library on one box, profiles/r2_ab_vs_r1.log) */
+template <bool LIGHTS, bool VOLUMES, int SAMPLER>
 __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV : SHADE_MINBLOCKS) k_shade(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
                                                          uint32_t firstSample) {
     const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_ACTIVE];
@@ -626,9 +629,9 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
             uint32_t flags = __float_as_uint(d4.w);
             Rng rng;
             rng.s = __float_as_uint(o4.w);
-            rng.ld = samplerOfFlags(rc.flags);
+            rng.ld = (uint32_t)SAMPLER;
             rng.index = rng.pixelSeed = 0u;
-            if (rng.ld) { /* the sampler's key is a function of the slot: (pixel, global sample index) */
+            if (SAMPLER != 0) { /* the sampler's key is a function of the slot: (pixel, global sample index) */
                 const uint32_t p = slot % rc.nPixLocal, pixel = rc.pixmap ? rc.pixmap[p] : p;
                 rngRestore(rng, rng.ld, pixel % rc.width, pixel / rc.width, rc.width, firstSample + slot / rc.nPixLocal);
             }
