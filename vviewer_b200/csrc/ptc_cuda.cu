@@ -554,14 +554,13 @@ int renderImpl(Dev *c, const ptc_render_params *rp, float4 *dR, float4 *dA, floa
     const bool hasLights = rc.totalLights > 0, hasVolumes = c->anyVolumeChange || rp->scene.volumes[0] != -1.0f;
     rc.fuseProbe = (c->anyEmissive && hasLights && !c->anyTransparent && !hasVolumes && getenv("PTC_NO_PROBE_FUSION") == nullptr) ? 1u : 0u;
     using ShadeFn = void (*)(wf::Wave, const DScene, const wf::RenderConst, uint32_t, uint32_t);
-    /* k_shade<lights, media, sampler> */
-    static const ShadeFn shadeTable[2][2][3] = {
-        {{wf::k_shade<false, false, 0>, wf::k_shade<false, false, 1>, wf::k_shade<false, false, 2>},
-         {wf::k_shade<false, true, 0>, wf::k_shade<false, true, 1>, wf::k_shade<false, true, 2>}},
-        {{wf::k_shade<true, false, 0>, wf::k_shade<true, false, 1>, wf::k_shade<true, false, 2>},
-         {wf::k_shade<true, true, 0>, wf::k_shade<true, true, 1>, wf::k_shade<true, true, 2>}}};
+    /* k_shade<lights, media, sampler, environment light-sampled> (the environment as a light implies a non-empty light pick) */
+#define SHADE_ROW(L, V, E) {wf::k_shade<L, V, 0, E>, wf::k_shade<L, V, 1, E>, wf::k_shade<L, V, 2, E>}
+    static const ShadeFn shadeTable[2][2][2][3] = {{{SHADE_ROW(false, false, false), SHADE_ROW(false, false, false)}, {SHADE_ROW(false, true, false), SHADE_ROW(false, true, false)}},
+                                                   {{SHADE_ROW(true, false, false), SHADE_ROW(true, false, true)}, {SHADE_ROW(true, true, false), SHADE_ROW(true, true, true)}}};
+#undef SHADE_ROW
     const int samplerKind = (rp->flags & PTC_FLAG_SAMPLER_PMJ) ? 2 : ((rp->flags & PTC_FLAG_SAMPLER_SOBOL) ? 1 : 0);
-    const ShadeFn shadeFn = shadeTable[hasLights ? 1 : 0][hasVolumes ? 1 : 0][samplerKind];
+    const ShadeFn shadeFn = shadeTable[hasLights ? 1 : 0][hasVolumes ? 1 : 0][rc.envLight ? 1 : 0][samplerKind];
     const int gridShade = residentGrid((const void *)shadeFn, 128, capShade);
     using ChainFn = void (*)(wf::Wave, const DScene, const wf::RenderConst, uint32_t, wf::ExtendTune);
     const ChainFn shadowFn = c->anyTransparent ? (TL ? (ChainFn)wf::k_shadow<false, true> : (ChainFn)wf::k_shadow<false, false>)

@@ -181,6 +181,7 @@ struct LightSample {
     float pdf, tmax;
     bool delta;
 };
+template <bool ENV>
 PTC_D LightSample sampleLight(const DScene &sc, const RenderConst &rc, Rng &rng, float3 origin) {
     LightSample ls;
     ls.delta = true;
@@ -192,7 +193,7 @@ PTC_D LightSample sampleLight(const DScene &sc, const RenderConst &rc, Rng &rng,
     if (totalLights == 0u) return ls;
     const float pick = 1.0f / (float)totalLights;
     uint32_t li = min((uint32_t)(rnd(rng) * (float)totalLights), totalLights - 1u);
-    if (rc.envLight && li == totalLights - 1u) {
+    if (ENV && li == totalLights - 1u) {
         /* extension (trap T3, include/ptc.h PTC_FLAG_ENV_IMPORTANCE): the environment as the last light */
         const float2 u01 = rnd2(rng);
         const envd::DeviceTables et{sc.envCdfV, sc.envCdfU};
@@ -603,7 +604,9 @@ PTC_D bool roulette(Rng &rng, uint32_t depth, float3 &beta) {
 /* SAMPLER (0 default stream, 1 Sobol, 2 PMJ02BN) is a compile-time switch too: the generators are inlined at every rnd() of this
  * kernel, and carrying the two table / hash based ones as run-time branches cost the default path 3-7 % (A/B against the round-1
  * library on one box, profiles/r2_ab_vs_r1.log) */
-template <bool LIGHTS, bool VOLUMES, int SAMPLER>
+/* ENV: the environment is light-sampled (PTC_FLAG_ENV_IMPORTANCE, rc.envLight): the table inversion and the MIS of the miss are only
+ * compiled into the instantiations that use them */
+template <bool LIGHTS, bool VOLUMES, int SAMPLER, bool ENV>
 __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV : SHADE_MINBLOCKS) k_shade(Wave w, const __grid_constant__ DScene sc, const __grid_constant__ RenderConst rc, uint32_t bounce,
                                                          uint32_t firstSample) {
     const uint32_t count = w.counters[bounce * CNT_STRIDE + CNT_ACTIVE];
@@ -753,7 +756,7 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
                     stS(&w.aovNormal[slot], make_float4(0.0f, 0.0f, 0.0f, 0.0f));
                 }
                 /* environment found by a sampled direction while it is also light-sampled: power heuristic */
-                if (rc.envLight && lastPdf > 0.0f && (bg[3] == 1.0f || (bg[3] == 2.0f && !first))) {
+                if (ENV && lastPdf > 0.0f && (bg[3] == 1.0f || (bg[3] == 2.0f && !first))) {
                     const float2 uv = envd::equirectUV(normalize(rayDir));
                     const envd::DeviceTables et{sc.envCdfV, sc.envCdfU};
                     const float pl = (1.0f / (float)rc.totalLights) * envd::solidAnglePdf(envd::pdfUV(et, uv.x, uv.y), uv.y);
@@ -765,7 +768,7 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
             /* C. one light sample for every lane that scatters, in the medium or on a surface (lightSampling.glsl:1-106) */
             LightSample ls;
             ls.radiance = f3(0.0f);
-            if (LIGHTS && (sampledMedium || surfaceEvent)) ls = sampleLight(sc, rc, rng, lightPoint);
+            if (LIGHTS && (sampledMedium || surfaceEvent)) ls = sampleLight<ENV>(sc, rc, rng, lightPoint);
             /* D. its weight, the shadow request, and the next direction */
             if (VOLUMES && sampledMedium) { /* process_volume_hit.glsl:47-78 */
                 if (LIGHTS && !isBlack(ls.radiance)) {
