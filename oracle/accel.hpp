@@ -224,7 +224,15 @@ inline uint64_t expandBits10(uint64_t v) {
 }
 
 /* number of Morton bits per axis as a function of the triangle count (both sides must agree) */
-inline int mortonBitsPerAxis(uint64_t nTris) { return nTris <= 65536ull ? 10 : 21; }
+/* 30-bit codes up to 65 536 primitives, 48-bit (16 per axis: cells of 1 / 65 536 of the scene, six 8-bit sort passes) up to 2^26, the
+ * full 63 bits beyond */
+inline int mortonBitsPerAxis(uint64_t nTris) {
+    if (const char *e = getenv("PTC_MORTON_BITS")) { /* tests: force a tier (10, 16 or 21) on both sides */
+        const int b = atoi(e);
+        if (b == 10 || b == 16 || b == 21) return b;
+    }
+    return nTris <= 65536ull ? 10 : (nTris <= (1ull << 26) ? 16 : 21);
+}
 
 struct LBVH {
     uint64_t n = 0;

@@ -79,6 +79,27 @@ def test_wide_bvh_bit_exact(capi, engine, scene, kw, hierarchy):
     orc.close()
 
 
+@pytest.mark.parametrize("bits", [10, 16, 21])
+def test_every_morton_tier_bit_exact(capi, engine, bits):
+    """30-, 48- and 63-bit Morton codes (4, 6 and 8 passes of the hand-written radix sort): the tier is a function of the triangle
+    count, PTC_MORTON_BITS forces it on both sides so that a scene of modest size reaches the 63-bit path"""
+    engine.build_scene("Atrium", texture_size=4, scale=0.2)
+    os.environ["PTC_MORTON_BITS"] = str(bits)
+    try:
+        cu, orc = both(capi, engine.scene_desc())
+        a, b = cu.get_lbvh(), orc.get_lbvh()
+        wa, wb = cu.get_wide_bvh(), orc.get_wide_bvh()
+    finally:
+        del os.environ["PTC_MORTON_BITS"]
+    assert a["n"] == b["n"] > 20000
+    assert int(a["morton"].max()).bit_length() in range(3 * bits - 5, 3 * bits + 1)
+    for k in ("morton", "order", "parent", "left", "right", "aabb"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(wa["words"], wb["words"]) and np.array_equal(wa["tri_order"], wb["tri_order"])
+    cu.close()
+    orc.close()
+
+
 def test_lbvh_single_triangle_and_empty(capi):
     d, keep = make_quad_scene(capi)
     keep[2][0].tri_count = 1

@@ -7,7 +7,7 @@
  *
  *   k_flatten   instance x primitive -> world triangle (v0, e1, e2) + bounds      [__f*_rn: no FMA contraction]
  *   k_bounds    scene AABB (order-preserving uint atomics: exact, order independent)
- *   k_morton    30-bit (<= 65 536 triangles) or 63-bit Morton code of the bounds centre
+ *   k_morton    30-bit (<= 65 536 triangles), 48-bit (<= 2^26) or 63-bit Morton code of the bounds centre
  *   radix sort  stable LSD sort of (code, triangle id) pairs (radix.cuh: hand written, 8-bit digits)
  *   hierarchy   (a) PTC_HIERARCHY_LBVH: k_karras (Karras 2012, ties broken by sorted index) + k_fit (bottom-up AABB fit
  *               with per-node arrival counters);  (b) PTC_HIERARCHY_PLOC (default): parallel locally-ordered clustering
@@ -204,7 +204,15 @@ PTC_HD uint64_t expandBits10(uint64_t v) {
     v = (v * 0x00000005ull) & 0x49249249ull;
     return v;
 }
-inline int mortonBitsPerAxis(uint64_t nTris) { return nTris <= 65536ull ? 10 : 21; }
+/* 30-bit codes up to 65 536 primitives, 48-bit (16 per axis: cells of 1 / 65 536 of the scene, six 8-bit sort passes) up to 2^26, the
+ * full 63 bits beyond */
+inline int mortonBitsPerAxis(uint64_t nTris) {
+    if (const char *e = getenv("PTC_MORTON_BITS")) { /* tests: force a tier (10, 16 or 21) on both sides */
+        const int b = atoi(e);
+        if (b == 10 || b == 16 || b == 21) return b;
+    }
+    return nTris <= 65536ull ? 10 : (nTris <= (1ull << 26) ? 16 : 21);
+}
 
 __global__ void k_morton(const float4 *__restrict__ boundsLo, const float4 *__restrict__ boundsHi, const uint32_t *__restrict__ sceneBounds,
                          uint32_t nTris, int bits, uint64_t *__restrict__ keys, uint32_t *__restrict__ ids) {
