@@ -437,3 +437,26 @@ def test_accel_mode_auto(capi, engine):
     cu.build_accel()
     assert cu.stats()["accel_levels"] == 1
     cu.close()
+
+
+def test_packed_normal_roughness_tap_is_bit_identical(capi, engine):
+    """materials whose normal and roughness maps have the same size get ONE tap on the device (roughness in the alpha channel of a copy
+    of the normal map): the filter treats the four channels of a linear RGBA8 texture alike, so the image does not change by a bit"""
+    for scene, kw in (("Atrium", dict(scale=0.1, texture_size=64)), ("GLTF", {})):
+        engine.build_scene(scene, **kw)
+        engine.set_render_info(width=128, height=72, samples=8, batch_size=4)
+        desc, rp = engine.scene_desc(), engine.render_params()
+        out = {}
+        for packing in (True, False):
+            if not packing:
+                os.environ["PTC_NO_TEXTURE_PACKING"] = "1"
+            try:
+                cu = capi.Context(capi.load_cuda())
+                cu.upload_scene(desc)
+            finally:
+                os.environ.pop("PTC_NO_TEXTURE_PACKING", None)
+            cu.build_accel()
+            out[packing] = np.stack(cu.render(rp))
+            cu.close()
+        assert np.array_equal(out[True], out[False]), scene
+        assert out[True][0, ..., :3].mean() > 1e-3

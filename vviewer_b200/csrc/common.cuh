@@ -60,6 +60,9 @@ struct DInstance {
 
 #define PTC_MAX_EMISSIVE_BOXES 16
 #define TEX_WHITE 0xffffffffu /* texture whose every texel is (255, 255, 255, 255): reads as exactly 1 without a fetch */
+/* texture INDEX a material's roughness slot carries on the device when its roughness map was packed into the alpha channel of a copy of
+ * its normal map at upload (ptc_cuda.cu::createTextures): the normal-map tap already returned the roughness sample */
+#define TEX_IN_NORMAL_ALPHA 0xfffffffeu
 
 struct DScene {
     const ptc_vertex *vertices;

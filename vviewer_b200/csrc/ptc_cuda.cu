@@ -109,6 +109,9 @@ struct Dev {
     /* identity of what the texture arrays / the cubemap were built from (ptc_texture.uid, ptc_env.uid): an upload whose
      * textures are the same immutable objects keeps the device copies, like the reference, which uploads at import */
     std::vector<uint64_t> texSignature;
+    /* (normal map, roughness map) pairs that createTextures packed into one RGBA8 layer (normal.rgb, roughness.r): pair -> texture index */
+    std::map<std::pair<uint32_t, uint32_t>, uint32_t> packedPairs;
+    uint32_t nSceneTextures = 0; /* textures of the scene description (nTextures also counts the packed copies) */
     uint64_t envSignature[3] = {0, 0, 0};
 
     void freeTextureClasses() {
@@ -118,6 +121,7 @@ struct Dev {
         }
         texClasses.clear();
         texSignature.clear();
+        packedPairs.clear();
     }
     void freeCubemap() {
         if (cubeTex) cudaDestroyTextureObject(cubeTex);
@@ -216,10 +220,40 @@ DScene makeDScene(Dev *c) {
 /* Uploads the scene's 8-bit textures: every texture becomes RGBA8 (an R8 source reads back as (r, 0, 0, 1) like
  * VK_FORMAT_R8_UNORM), grouped into layered arrays by (width, height, sRGB).  Sampler = the reference's
  * (VulkanTexture.cpp:219-232): linear, REPEAT, normalised coordinates, sRGB decode before filtering. */
+/* Which (normal map, roughness map) pairs can share one tap: both linear (the alpha channel of an sRGB texture is not decoded either,
+ * but the normal map is linear anyway), the same size, neither all white.  Metallic-roughness assets sample exactly these two maps
+ * at the same coordinates on every surface event (rayPrimaryPBRStandard.rchit.glsl:100-110). */
+bool packablePair(const ptc_scene_desc *sd, const std::vector<uint32_t> &ref, uint32_t normalTex, uint32_t roughTex) {
+    if (normalTex >= sd->n_textures || roughTex >= sd->n_textures || normalTex == roughTex) return false;
+    if (ref[normalTex] == TEX_WHITE || ref[roughTex] == TEX_WHITE) return false;
+    const ptc_texture &a = sd->textures[normalTex], &b = sd->textures[roughTex];
+    return !a.srgb && !b.srgb && a.channels == 4 && a.width == b.width && a.height == b.height;
+}
+
 void createTextures(Dev *c, const ptc_scene_desc *sd) {
     const uint32_t n = sd->n_textures;
+    struct Source { /* a layer: a texture of the scene, or a packed (normal, roughness) pair */
+        uint32_t tex, rough;
+    };
     std::vector<uint32_t> ref(n, 0);
-    std::vector<std::vector<uint32_t>> members;
+    std::vector<std::vector<Source>> members;
+    auto classOf = [&](uint32_t width, uint32_t height, uint32_t srgb) {
+        uint32_t cls = 0;
+        for (; cls < c->texClasses.size(); cls++) {
+            const TextureClass &k = c->texClasses[cls];
+            if (k.width == width && k.height == height && k.srgb == srgb && members[cls].size() < 2048) break;
+        }
+        if (cls == c->texClasses.size()) {
+            TextureClass k;
+            k.width = width;
+            k.height = height;
+            k.srgb = srgb;
+            c->texClasses.push_back(k);
+            members.emplace_back();
+        }
+        if (cls > 0xfffeu) throw CudaError{"too many texture classes"};
+        return cls;
+    };
     for (uint32_t t = 0; t < n; t++) {
         const ptc_texture &in = sd->textures[t];
         const size_t texels = (size_t)in.width * in.height;
@@ -229,22 +263,20 @@ void createTextures(Dev *c, const ptc_scene_desc *sd) {
             ref[t] = TEX_WHITE;
             continue;
         }
-        uint32_t cls = 0;
-        for (; cls < c->texClasses.size(); cls++) {
-            const TextureClass &k = c->texClasses[cls];
-            if (k.width == in.width && k.height == in.height && k.srgb == (in.srgb ? 1u : 0u) && members[cls].size() < 2048) break;
-        }
-        if (cls == c->texClasses.size()) {
-            TextureClass k;
-            k.width = in.width;
-            k.height = in.height;
-            k.srgb = in.srgb ? 1u : 0u;
-            c->texClasses.push_back(k);
-            members.emplace_back();
-        }
-        if (cls > 0xfffeu) throw CudaError{"too many texture classes"};
+        const uint32_t cls = classOf(in.width, in.height, in.srgb ? 1u : 0u);
         ref[t] = (cls << 16) | (uint32_t)members[cls].size();
-        members[cls].push_back(t);
+        members[cls].push_back(Source{t, 0xffffffffu});
+    }
+    /* packed copies: one extra layer per distinct pair; the materials of the device table are pointed at it (patchMaterials) */
+    c->packedPairs.clear();
+    for (uint32_t m = 0; m < sd->n_materials; m++) {
+        const uint32_t nt = sd->materials[m].tex2[1], rt = sd->materials[m].tex1[2];
+        if (!packablePair(sd, ref, nt, rt) || c->packedPairs.count({nt, rt})) continue;
+        const ptc_texture &in = sd->textures[nt];
+        const uint32_t cls = classOf(in.width, in.height, 0u);
+        c->packedPairs[{nt, rt}] = (uint32_t)ref.size();
+        ref.push_back((cls << 16) | (uint32_t)members[cls].size());
+        members[cls].push_back(Source{nt, rt});
     }
     std::vector<cudaTextureObject_t> table(c->texClasses.size());
     for (size_t cls = 0; cls < c->texClasses.size(); cls++) {
@@ -253,9 +285,10 @@ void createTextures(Dev *c, const ptc_scene_desc *sd) {
         const size_t texels = (size_t)k.width * k.height;
         cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
         CUDA_TRY(cudaMalloc3DArray(&k.array, &fmt, make_cudaExtent(k.width, k.height, k.layers), cudaArrayLayered));
-        std::vector<uint8_t> rgba; /* staging only for R8 sources */
+        std::vector<uint8_t> rgba; /* staging for R8 sources and packed pairs */
         for (uint32_t l = 0; l < k.layers; l++) {
-            const ptc_texture &in = sd->textures[members[cls][l]];
+            const Source &srcId = members[cls][l];
+            const ptc_texture &in = sd->textures[srcId.tex];
             const uint8_t *src = in.data;
             if (in.channels != 4) {
                 rgba.resize(texels * 4);
@@ -263,6 +296,15 @@ void createTextures(Dev *c, const ptc_scene_desc *sd) {
                     uint8_t px[4] = {0, 0, 0, 255};
                     for (uint32_t ch = 0; ch < in.channels && ch < 4; ch++) px[ch] = in.data[p * in.channels + ch];
                     std::memcpy(rgba.data() + p * 4, px, 4);
+                }
+                src = rgba.data();
+            }
+            if (srcId.rough != 0xffffffffu) { /* (normal.r, normal.g, normal.b, roughness.r) */
+                const ptc_texture &ro = sd->textures[srcId.rough];
+                rgba.resize(texels * 4);
+                for (size_t p = 0; p < texels; p++) {
+                    std::memcpy(rgba.data() + p * 4, in.data + p * 4, 3);
+                    rgba[p * 4 + 3] = ro.data[p * ro.channels];
                 }
                 src = rgba.data();
             }
@@ -286,10 +328,25 @@ void createTextures(Dev *c, const ptc_scene_desc *sd) {
         CUDA_TRY(cudaCreateTextureObject(&k.tex, &rd, &td, nullptr));
         table[cls] = k.tex;
     }
-    c->nTextures = n;
+    c->nSceneTextures = n;
+    c->nTextures = (uint32_t)ref.size();
     c->texRef.upload(ref.data(), ref.size(), c->stream);
     c->texClassTable.upload(table.data(), table.size(), c->stream);
     CUDA_TRY(cudaStreamSynchronize(c->stream)); /* the host vectors die here */
+}
+
+/* the device copy of the material table: materials whose (normal, roughness) maps were packed fetch the packed layer once */
+void uploadMaterials(Dev *c, const ptc_scene_desc *sd) {
+    std::vector<ptc_material> mats(sd->materials, sd->materials + sd->n_materials);
+    if (getenv("PTC_NO_TEXTURE_PACKING") == nullptr)
+        for (ptc_material &m : mats) {
+            auto it = c->packedPairs.find({m.tex2[1], m.tex1[2]});
+            if (it == c->packedPairs.end()) continue;
+            m.tex2[1] = it->second;
+            m.tex1[2] = TEX_IN_NORMAL_ALPHA;
+        }
+    c->materials.upload(mats.data(), mats.size(), c->stream);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
 }
 
 void createCubemap(Dev *c, const ptc_env &env) {
@@ -832,7 +889,6 @@ void uploadSceneDev(Dev *c, const ptc_scene_desc *sd) {
     c->accelBuilt = false;
     c->vertices.upload(sd->vertices, sd->n_vertices, s);
     c->indices.upload(sd->indices, sd->n_indices, s);
-    c->materials.upload(sd->materials, sd->n_materials, s);
     c->lightData.upload(sd->light_data, sd->n_light_data, s);
     c->lightInstances.upload(sd->light_instances, sd->n_light_instances, s);
     c->nMaterials = sd->n_materials;
@@ -954,12 +1010,16 @@ void uploadSceneDev(Dev *c, const ptc_scene_desc *sd) {
     uint64_t uploadBytes = sd->n_vertices * sizeof(ptc_vertex) + sd->n_indices * 4ull + (uint64_t)sd->n_materials * sizeof(ptc_material) +
                            (uint64_t)sd->n_light_data * sizeof(ptc_light_data) + (uint64_t)sd->n_light_instances * sizeof(ptc_light_instance) +
                            (uint64_t)sd->n_instances * sizeof(DInstance);
-    if (!(allIdentified && sig == c->texSignature && c->nTextures == sd->n_textures)) {
+    /* (which maps are packed together depends on the materials: part of the identity of the device copies) */
+    sig.push_back(0x7061636b65647321ull);
+    for (uint32_t m = 0; m < sd->n_materials; m++) sig.push_back(((uint64_t)sd->materials[m].tex2[1] << 32) | sd->materials[m].tex1[2]);
+    if (!(allIdentified && sig == c->texSignature && c->nSceneTextures == sd->n_textures)) {
         c->freeTextureClasses();
         createTextures(c, sd);
         if (allIdentified) c->texSignature = sig;
         for (uint32_t t = 0; t < sd->n_textures; t++) uploadBytes += (uint64_t)sd->textures[t].width * sd->textures[t].height * sd->textures[t].channels;
     }
+    uploadMaterials(c, sd);
     const ptc_env &env = sd->env;
     const bool hasEnv = env.equirect_rgba && env.width && env.height;
     if (!(hasEnv && env.uid != 0 && c->cubeTex && c->envSignature[0] == env.uid && c->envSignature[1] == env.width && c->envSignature[2] == env.height)) {

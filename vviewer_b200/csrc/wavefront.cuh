@@ -686,7 +686,8 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
                     }
                 }
                 if (!passThrough) {
-                    applyNormal(fr, normalFromMap(f3(texFetch(sc, __ldg(&mat->tex2[1]), tu, tv))));
+                    const float4 normalTexel = texFetch(sc, __ldg(&mat->tex2[1]), tu, tv); /* .w: the roughness sample when the maps were packed */
+                    applyNormal(fr, normalFromMap(f3(normalTexel)));
                     albedo = ld3(mat->albedo) * f3(texFetch(sc, __ldg(&mat->tex1[0]), tu, tv));
                     const float3 emissive = ld3(mat->emissive) * __ldg(&mat->emissive[3]) * f3(texFetch(sc, __ldg(&mat->tex2[0]), tu, tv));
                     if (LIGHTS && !VOLUMES && (flags & PF_PROBE_DEFERRED)) {
@@ -717,7 +718,9 @@ __global__ void __launch_bounds__(128, (LIGHTS && VOLUMES) ? SHADE_MINBLOCKS_LV 
                     pbr.roughness = 1.0f;
                     if (!lambert) {
                         pbr.metallic = __ldg(&mat->metallic_roughness_ao[0]) * texFetch(sc, __ldg(&mat->tex1[1]), tu, tv).x;
-                        pbr.roughness = fmaxf(__ldg(&mat->metallic_roughness_ao[1]) * texFetch(sc, __ldg(&mat->tex1[2]), tu, tv).x, 0.035f);
+                        const uint32_t roughTex = __ldg(&mat->tex1[2]);
+                        const float roughTexel = roughTex == TEX_IN_NORMAL_ALPHA ? normalTexel.w : texFetch(sc, roughTex, tu, tv).x;
+                        pbr.roughness = fmaxf(__ldg(&mat->metallic_roughness_ao[1]) * roughTexel, 0.035f);
                     }
                     const bool first = !(flags & PF_SURFACE);
                     if (first) {
