@@ -307,9 +307,9 @@ def run_cuda(args, rank, world, local_rank):
             except Exception:
                 traffic = None
         # second kernel (k_shade, DRAM bound): algorithmic bytes per segment with the actual record sizes - queue id 4,
-        # hit + origin + direction + throughput read 64, new origin + direction + throughput written 48, shading record, three texture
-        # taps of 16 B (albedo, normal, roughness of the bench scene's materials)
-        shade_bytes = 4 + 64 + 48 + SHADING_RECORD_BYTES + 3 * 16
+        # hit + origin + direction + throughput read 64, new origin + direction + throughput written 48, shading record, two texture
+        # taps of 16 B (albedo; normal + roughness of the bench scene's materials share one packed tap)
+        shade_bytes = 4 + 64 + 48 + SHADING_RECORD_BYTES + 2 * 16
         shade_gbs = stp["segments"] * shade_bytes / (stp["shade_ms"] * 1e-3) / 1e9 if stp["shade_ms"] > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "bytes_per_ray": bytes_per_ray, "bvh_depth": bvh_depth,
