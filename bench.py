@@ -288,9 +288,20 @@ def run_cuda(args, rank, world, local_rank):
 
     value = segments / dev_ms / 1e3  # Msegments/s, whole job
     roofline, cpu = None, None
-    if world == 1:
-        # ---- roofline of the dominant kernel (k_extend), timed live with CUDA events on the launching stream
-        stp = render(2, flags=capi.PTC_FLAG_TIME_KERNELS)
+    if True:
+        # ---- roofline of the dominant kernel (k_extend), timed live with CUDA events on the launching stream.  With several ranks this
+        # is rank 0's GPU alone, on a context of its own without the communicator (the other ranks wait at the final barrier)
+        if world == 1:
+            stp = render(2, flags=capi.PTC_FLAG_TIME_KERNELS)
+        else:
+            rctx = capi.Context(cuda, device=local_rank)
+            rctx.upload_scene(desc)
+            rctx.build_accel()
+            rp1 = eng.render_params()
+            rp1.samples, rp1.batch_size, rp1.flags, rp1.split_mode = 2 * B, B, capi.PTC_FLAG_TIME_KERNELS, capi.PTC_SPLIT_NONE
+            rctx.render_device(rp1, None, None, None)
+            stp = rctx.stats()
+            rctx.close()
         bytes_per_ray, bvh_depth = algorithmic_bytes_per_ray(build_stats["n_triangles"])
         peak, peak_kind = measured_peak()
         rays = stp["segments"]
@@ -317,7 +328,7 @@ def run_cuda(args, rank, world, local_rank):
                     "k_shade": {"achieved": shade_gbs, "frac": shade_gbs / peak, "bytes_per_segment": shade_bytes, "traffic": shade_traffic}}
 
         # ---- CPU baseline: the oracle on the host cores, bounded sample of the same workload
-        if not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline:
             octx = capi.Context(oracle_loader.load_oracle())
             octx.upload_scene(desc)
             octx.build_accel()
