@@ -116,6 +116,27 @@ def test_deep_glossy_configs_match_oracle_statistically(capi, engine, scene, kw)
     assert np.median(rel) < 0.05 and np.percentile(rel, 95) < 0.2, (float(np.median(rel)), float(np.percentile(rel, 95)))
 
 
+@pytest.mark.parametrize("w,h", [(64, 40), (1056, 1000), (2048, 1031)])
+def test_host_readback_equals_device_targets(capi, engine, w, h):
+    """getRenderTargetData x3 (...PathTracing.cpp:890-893): the host images go through pinned staging chunks of 16 MB - one
+    chunk, one chunk plus a short tail, several chunks with a ragged end - and must be the device targets byte for byte"""
+    import torch
+    engine.build_scene("Cornell")
+    engine.set_render_info(width=w, height=h, samples=2, batch_size=1)
+    desc, rp = engine.scene_desc(), engine.render_params()
+    ctx = capi.Context(capi.load_cuda(), device=0)
+    ctx.upload_scene(desc)
+    ctx.build_accel()
+    host = ctx.render(rp)
+    dev = [torch.full((h, w, 4), -1.0, dtype=torch.float32, device="cuda:0") for _ in range(3)]
+    ctx.render_device(rp, *[t.data_ptr() for t in dev])
+    torch.cuda.synchronize()
+    ctx.close()
+    for a, b in zip(host, dev):
+        assert np.array_equal(np.asarray(a).reshape(h, w, 4), b.cpu().numpy())
+    assert np.all(np.asarray(host[0]).reshape(h, w, 4)[..., 3] == 1.0)
+
+
 def test_orthographic_rays_are_parallel(capi, engine):
     """trap T10 (parity unpinned in the reference): the build renders a TRUE orthographic view.  Property test: over a flat floor
     seen head-on, the first-hit normal AOV is constant and the albedo AOV of a checker of emissive spheres does not depend on
@@ -241,6 +262,28 @@ def test_multi_device_context_equals_single_device(capi, engine, mode):
     assert np.allclose(part[..., :3], full[..., :3], rtol=1e-5, atol=1e-6)
     assert np.all(part[..., 3] == 1.0)  # alpha after the multi-rank sum
     assert st["reduce_ms"] > 0.0
+
+
+def test_geometry_reaches_the_other_devices_over_the_communicator(capi, engine, monkeypatch):
+    """several devices in one process: the vertex / index pools are copied to the first device only and broadcast from there
+    (ncclBroadcast); the render is bit-identical to the one with a host copy per device"""
+    n = _gpu_count()
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    engine.build_scene("MeshLight")
+    engine.set_render_info(width=160, height=96, samples=16, batch_size=4)
+    desc, rp = engine.scene_desc(), engine.render_params()
+    rp.split_mode, rp.tile_size = capi.PTC_SPLIT_TILE, 16
+    images = {}
+    for label, min_bytes in (("broadcast", "0"), ("host copies", "-1")):
+        monkeypatch.setenv("PTC_SCENE_BROADCAST_MIN_BYTES", min_bytes)
+        multi = capi.Context(capi.load_cuda(), device=list(range(min(n, 4))))
+        multi.upload_scene(desc)
+        multi.build_accel()
+        images[label] = np.stack(multi.render(rp))
+        multi.close()
+    assert np.array_equal(images["broadcast"], images["host copies"])
+    assert np.isfinite(images["broadcast"]).all() and images["broadcast"][0, ..., :3].mean() > 0.01
 
 
 def test_engine_with_several_devices_renders_through_the_plugin(capi):

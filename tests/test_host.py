@@ -98,6 +98,35 @@ def test_flatten_mesh_light_and_order(engine):
     assert np.allclose(model[:3, 3], [0, 2, 0]) and np.isclose(np.linalg.norm(model[:3, 0]), 0.4, rtol=1e-5)
 
 
+def test_flatten_keeps_geometry_pools_while_the_meshes_stay(capi):
+    """Meshes are immutable after import (the reference uploads them once, VulkanMesh): flattening the same scene again - here
+    after a camera move of the render sequence - hands out the SAME vertex / index pools; another scene gets new ones with
+    its own content."""
+    eng = capi.HostEngine()
+    try:
+        eng.build_scene("BallOnPlane")
+        d = eng.scene_desc().contents
+        first = (C.addressof(d.vertices.contents), C.addressof(d.indices.contents), int(d.n_vertices), int(d.n_indices), d.n_meshes)
+        v0 = np.array(d.vertices[0].position, np.float32).copy()
+        view0 = np.array(eng.render_params().scene.view, np.float32).copy()
+        eng.set_sequence_frame(7)  # invalidates the flattened scene: only the camera differs
+        d = eng.scene_desc().contents
+        again = (C.addressof(d.vertices.contents), C.addressof(d.indices.contents), int(d.n_vertices), int(d.n_indices), d.n_meshes)
+        assert again == first
+        assert not np.array_equal(np.array(eng.render_params().scene.view, np.float32), view0)
+        assert np.array_equal(np.array(d.vertices[0].position, np.float32), v0)
+        eng.build_scene("Cornell")  # other meshes
+        d = eng.scene_desc().contents
+        assert (int(d.n_vertices), int(d.n_indices)) != first[2:4]
+        tri = sum(d.meshes[m].tri_count for m in range(d.n_meshes))
+        assert tri * 3 == d.n_indices
+        for m in range(d.n_meshes):
+            me = d.meshes[m]
+            assert me.first_vertex + me.vertex_count <= d.n_vertices and me.first_index + 3 * me.tri_count <= d.n_indices
+    finally:
+        eng.close()
+
+
 def test_flatten_directional_light_unnormalised(engine):
     """Trap T4: directional light direction = modelMatrix * (0,0,1,0), not normalised under scaled parents."""
     engine.build_scene("Hierarchy")

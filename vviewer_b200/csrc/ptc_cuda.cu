@@ -14,6 +14,7 @@
 
 #include <array>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -99,6 +100,10 @@ struct Dev {
      * 2069 Mseg/s alone (profiles/r1_v4_kernel_experiments.log) - k_shade needs >= 3 blocks per SM to keep DRAM busy and k_extend
      * loses as much with 4 as the overlap wins.  PTC_OVERLAP=t,s / PTC_OVERLAP=0 for experiments. */
     int overlapTrace = 64, overlapShade = 64;
+    /* readback of the images: two pinned staging buffers (allocated at the first host readback) and the event of each one's copy */
+    static constexpr size_t STAGE_BYTES = 16u << 20;
+    char *stage[2] = {nullptr, nullptr};
+    cudaEvent_t evStage[2] = {nullptr, nullptr};
     uint32_t tileOrder = 0; /* PTC_TILE_ORDER: tile edge of the single-rank pixel walk, 0 = row major */
     float sceneLo[3] = {0, 0, 0}, sceneHi[3] = {0, 0, 0}; /* world box of the scene (from the build) */
 
@@ -147,6 +152,10 @@ struct Dev {
             if (e) cudaEventDestroy(e);
         for (cudaEvent_t e : evItem)
             if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : evStage)
+            if (e) cudaEventDestroy(e);
+        for (char *p : stage)
+            if (p) cudaFreeHost(p);
         if (stream2) cudaStreamDestroy(stream2);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -746,6 +755,7 @@ struct NcclApi {
     ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -773,6 +783,7 @@ struct NcclApi {
         NCCL_SYM(CommInitAll, ncclCommInitAll)
         NCCL_SYM(CommDestroy, ncclCommDestroy)
         NCCL_SYM(Reduce, ncclReduce)
+        NCCL_SYM(Broadcast, ncclBroadcast)
         NCCL_SYM(GroupStart, ncclGroupStart)
         NCCL_SYM(GroupEnd, ncclGroupEnd)
         NCCL_SYM(GetErrorString, ncclGetErrorString)
@@ -881,14 +892,20 @@ void validateScene(const ptc_scene_desc *sd) {
     }
 }
 
-/* ptc_upload_scene on one device */
-void uploadSceneDev(Dev *c, const ptc_scene_desc *sd) {
+/* ptc_upload_scene on one device.  geometryFollows: the vertex / index pools are only allocated here and arrive from the first device
+ * of the context (broadcastGeometry) */
+void uploadSceneDev(Dev *c, const ptc_scene_desc *sd, bool geometryFollows) {
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
     c->sceneUploaded = false;
     c->accelBuilt = false;
-    c->vertices.upload(sd->vertices, sd->n_vertices, s);
-    c->indices.upload(sd->indices, sd->n_indices, s);
+    if (geometryFollows) {
+        c->vertices.alloc(sd->n_vertices);
+        c->indices.alloc(sd->n_indices);
+    } else {
+        c->vertices.upload(sd->vertices, sd->n_vertices, s);
+        c->indices.upload(sd->indices, sd->n_indices, s);
+    }
     c->lightData.upload(sd->light_data, sd->n_light_data, s);
     c->lightInstances.upload(sd->light_instances, sd->n_light_instances, s);
     c->nMaterials = sd->n_materials;
@@ -1038,6 +1055,26 @@ void uploadSceneDev(Dev *c, const ptc_scene_desc *sd) {
 }
 
 
+/* One process, several GPUs: the geometry pools cross PCIe ONCE, to the first device, and reach the others through the context's
+ * communicator (NVLink / NVSwitch) instead of N pageable host copies competing for the host's memory system (a 180 MB pool to 8 GPUs:
+ * 74 ms, profiles/r2_offlinerender_c4_8gpu.log).  The small per-render arrays (instances, materials, lights) stay plain copies. */
+void broadcastGeometry(ptc_ctx *ctx, const ptc_scene_desc *sd) {
+    const size_t nDev = ctx->devs.size();
+    NCCL_TRY(g_nccl.GroupStart());
+    for (size_t i = 0; i < nDev; i++) {
+        Dev *c = ctx->devs[i].get();
+        CUDA_TRY(cudaSetDevice(c->device));
+        if (sd->n_vertices)
+            NCCL_TRY(g_nccl.Broadcast(c->vertices.p, c->vertices.p, sd->n_vertices * sizeof(ptc_vertex), ncclUint8, 0, ctx->comms[i], c->stream));
+        if (sd->n_indices) NCCL_TRY(g_nccl.Broadcast(c->indices.p, c->indices.p, sd->n_indices * 4ull, ncclUint8, 0, ctx->comms[i], c->stream));
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
+    for (size_t i = 0; i < nDev; i++) {
+        CUDA_TRY(cudaSetDevice(ctx->devs[i]->device));
+        CUDA_TRY(cudaStreamSynchronize(ctx->devs[i]->stream));
+    }
+}
+
 __global__ void k_fill_alpha(float4 *a, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) a[i].w = 1.0f;
@@ -1057,12 +1094,66 @@ void checkRenderParams(ptc_ctx *ctx, const ptc_render_params *rp) {
     if (rp->split_mode != PTC_SPLIT_NONE && rp->world > 1 && rp->rank >= rp->world) throw CudaError{"rank must be below world"};
 }
 
+/* Device -> pageable host memory through the device's two pinned staging buffers: the DMA of chunk i runs while the host moves chunk
+ * i - 1 out of the other buffer (on up to four threads).  A plain cudaMemcpy into pageable memory does the same staging on one thread
+ * without the overlap: 400 MB of 4K images took 79 ms (5 GB/s, profiles/r2_offlinerender_c4_8gpu.log). */
+void hostCopyParallel(char *dst, const char *src, size_t n) {
+    const size_t ways = n >= (8u << 20) ? 4 : (n >= (2u << 20) ? 2 : 1);
+    if (ways == 1) {
+        std::memcpy(dst, src, n);
+        return;
+    }
+    const size_t part = (n / ways + 63) & ~(size_t)63;
+    std::vector<std::thread> th;
+    for (size_t w = 1; w < ways; w++) {
+        const size_t b = std::min(n, w * part), e = std::min(n, (w + 1) * part);
+        if (e > b) th.emplace_back([=] { std::memcpy(dst + b, src + b, e - b); });
+    }
+    std::memcpy(dst, src, std::min(n, part));
+    for (auto &t : th) t.join();
+}
+
+void readbackStaged(Dev *c, float *const hOut[3], float4 *const img[3], size_t bytesPerImage) {
+    struct Chunk {
+        char *dst;
+        const char *src;
+        size_t n;
+    };
+    std::vector<Chunk> chunks;
+    for (int k = 0; k < 3; k++)
+        if (hOut[k])
+            for (size_t off = 0; off < bytesPerImage; off += Dev::STAGE_BYTES)
+                chunks.push_back({(char *)hOut[k] + off, (const char *)img[k] + off, std::min(Dev::STAGE_BYTES, bytesPerImage - off)});
+    if (chunks.empty()) return;
+    for (int b = 0; b < 2; b++) {
+        if (!c->stage[b]) CUDA_TRY(cudaHostAlloc((void **)&c->stage[b], Dev::STAGE_BYTES, cudaHostAllocDefault));
+        if (!c->evStage[b]) CUDA_TRY(cudaEventCreateWithFlags(&c->evStage[b], cudaEventDisableTiming));
+    }
+    auto issue = [&](size_t i) {
+        CUDA_TRY(cudaMemcpyAsync(c->stage[i & 1u], chunks[i].src, chunks[i].n, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaEventRecord(c->evStage[i & 1u], c->stream));
+    };
+    issue(0);
+    for (size_t i = 0; i < chunks.size(); i++) {
+        if (i + 1 < chunks.size()) issue(i + 1); /* its buffer was emptied in the previous iteration */
+        CUDA_TRY(cudaEventSynchronize(c->evStage[i & 1u]));
+        hostCopyParallel(chunks[i].dst, c->stage[i & 1u], chunks[i].n);
+    }
+}
+
 /* The partitioned render of a context: every device renders its share into its own three targets (one allocation), the targets are
  * summed onto the root with ONE ncclReduce per device (tiles are disjoint and zero elsewhere, so the sum serves both split modes),
  * and the root writes alpha = 1 behind the reduce.  dOut (optional, device pointers on the root's device) / hOut (optional, host)
  * receive the three images.  Returns false on a non-root rank of a multi-process group (no image there). */
 bool renderAll(ptc_ctx *ctx, const ptc_render_params *rp, void *const dOut[3], float *const hOut[3]) {
     checkRenderParams(ctx, rp);
+    const bool verbose = getenv("PTC_VERBOSE") != nullptr;
+    auto tick = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) { /* host wall clock of the phases of one call */
+        const auto now = std::chrono::steady_clock::now();
+        if (verbose) fprintf(stderr, "[ptc]    %-12s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tick).count());
+        tick = now;
+    };
     const size_t nPix = (size_t)rp->width * rp->height;
     const uint32_t nDev = (uint32_t)ctx->devs.size();
     const bool group = nDev > 1, ranks = ctx->commWorld > 1;
@@ -1090,6 +1181,7 @@ bool renderAll(ptc_ctx *ctx, const ptc_render_params *rp, void *const dOut[3], f
         }
         renderImpl(c, &mine, r, a, n);
     });
+    lap("render");
     /* the exchange */
     ctx->reduceMs = 0.0;
     if (group || ranks) {
@@ -1114,6 +1206,7 @@ bool renderAll(ptc_ctx *ctx, const ptc_render_params *rp, void *const dOut[3], f
         CUDA_TRY(cudaEventElapsedTime(&ms, root->evA, root->evB));
         ctx->reduceMs = ms;
     }
+    lap("reduce");
     /* statistics of the whole context */
     ptc_stats st{};
     const ptc_stats &b0 = ctx->devs[0]->stats;
@@ -1146,10 +1239,9 @@ bool renderAll(ptc_ctx *ctx, const ptc_render_params *rp, void *const dOut[3], f
         for (int k = 0; k < 3; k++)
             if (dOut[k]) CUDA_TRY(cudaMemcpyAsync(dOut[k], img[k], nPix * 16, cudaMemcpyDeviceToDevice, root->stream));
     /* readback like getRenderTargetData x3 (…PathTracing.cpp:890-893) */
-    if (hOut)
-        for (int k = 0; k < 3; k++)
-            if (hOut[k]) CUDA_TRY(cudaMemcpyAsync(hOut[k], img[k], nPix * 16, cudaMemcpyDeviceToHost, root->stream));
+    if (hOut) readbackStaged(root, hOut, img, nPix * 16);
     CUDA_TRY(cudaStreamSynchronize(root->stream));
+    lap("readback");
     return true;
 }
 
@@ -1297,7 +1389,12 @@ PTC_API int ptc_upload_scene(ptc_ctx *ctx, const ptc_scene_desc *sd) {
     for (auto &d : ctx->devs) d->sceneUploaded = d->accelBuilt = false;
     validateScene(sd);
     /* the scene is replicated: every device gets its own copy */
-    forEachDev(ctx, [&](Dev *c, uint32_t) { uploadSceneDev(c, sd); });
+    const uint64_t geometryBytes = sd->n_vertices * sizeof(ptc_vertex) + sd->n_indices * 4ull;
+    const char *minEnv = getenv("PTC_SCENE_BROADCAST_MIN_BYTES"); /* negative = never */
+    const long long minBytes = minEnv ? atoll(minEnv) : (1ll << 20);
+    const bool viaLink = ctx->devs.size() > 1 && ctx->comms.size() == ctx->devs.size() && minBytes >= 0 && geometryBytes >= (uint64_t)minBytes;
+    forEachDev(ctx, [&](Dev *c, uint32_t i) { uploadSceneDev(c, sd, viaLink && i > 0); });
+    if (viaLink) broadcastGeometry(ctx, sd);
     ctx->stats.upload_bytes = ctx->devs[0]->stats.upload_bytes;
     return 0;
     PTC_GUARD_END(ctx)

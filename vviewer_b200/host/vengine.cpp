@@ -473,21 +473,15 @@ EnvironmentMap *Engine::importEnvironmentMap(const AssetInfo &info) {
 
 void Engine::flatten(FlatScene &out) {
     out = FlatScene();
-    /* geometry pools: only meshes that are instanced */
+    /* geometry pools: only meshes that are instanced, in the order the instances first name them */
     std::unordered_map<Mesh *, uint32_t> meshSlot;
+    std::vector<Mesh *> slotMesh;
     InstancesManager &im = m_scene->instancesManager();
     auto slotOf = [&](Mesh *mesh) -> uint32_t {
         auto it = meshSlot.find(mesh);
         if (it != meshSlot.end()) return it->second;
-        ptc_mesh pm{};
-        pm.first_index = (uint32_t)out.indices.size();
-        pm.tri_count = mesh->nTriangles();
-        pm.first_vertex = (uint32_t)out.vertices.size();
-        pm.vertex_count = (uint32_t)mesh->vertices.size();
-        out.vertices.insert(out.vertices.end(), mesh->vertices.begin(), mesh->vertices.end());
-        out.indices.insert(out.indices.end(), mesh->indices.begin(), mesh->indices.begin() + (size_t)pm.tri_count * 3);
-        uint32_t s = (uint32_t)out.meshes.size();
-        out.meshes.push_back(pm);
+        const uint32_t s = (uint32_t)slotMesh.size();
+        slotMesh.push_back(mesh);
         meshSlot[mesh] = s;
         return s;
     };
@@ -516,6 +510,38 @@ void Engine::flatten(FlatScene &out) {
         inst.num_triangles = mesh->nTriangles();
         instanceSlot[so] = (uint32_t)out.instances.size();
         out.instances.push_back(inst);
+    }
+    {
+        std::vector<uint64_t> key;
+        key.reserve(slotMesh.size() * 3);
+        for (Mesh *mesh : slotMesh) {
+            key.push_back(mesh->uid);
+            key.push_back((uint64_t)mesh->vertices.size());
+            key.push_back((uint64_t)mesh->indices.size());
+        }
+        if (!m_geometry || m_geometry->key != key) {
+            auto pools = std::make_shared<GeometryPools>();
+            size_t nv = 0, ni = 0;
+            for (Mesh *mesh : slotMesh) {
+                nv += mesh->vertices.size();
+                ni += (size_t)mesh->nTriangles() * 3;
+            }
+            pools->vertices.reserve(nv);
+            pools->indices.reserve(ni);
+            for (Mesh *mesh : slotMesh) {
+                ptc_mesh pm{};
+                pm.first_index = (uint32_t)pools->indices.size();
+                pm.tri_count = mesh->nTriangles();
+                pm.first_vertex = (uint32_t)pools->vertices.size();
+                pm.vertex_count = (uint32_t)mesh->vertices.size();
+                pools->vertices.insert(pools->vertices.end(), mesh->vertices.begin(), mesh->vertices.end());
+                pools->indices.insert(pools->indices.end(), mesh->indices.begin(), mesh->indices.begin() + (size_t)pm.tri_count * 3);
+                pools->meshes.push_back(pm);
+            }
+            pools->key = std::move(key);
+            m_geometry = std::move(pools);
+        }
+        out.geometry = m_geometry;
     }
     out.materials = m_materials->blocks();
     out.lightData = m_scene->lightData();
@@ -561,12 +587,12 @@ void Engine::flatten(FlatScene &out) {
         out.textures.push_back(pt);
     }
     ptc_scene_desc &d = out.desc;
-    d.vertices = out.vertices.data();
-    d.n_vertices = out.vertices.size();
-    d.indices = out.indices.data();
-    d.n_indices = out.indices.size();
-    d.meshes = out.meshes.data();
-    d.n_meshes = (uint32_t)out.meshes.size();
+    d.vertices = out.geometry->vertices.data();
+    d.n_vertices = out.geometry->vertices.size();
+    d.indices = out.geometry->indices.data();
+    d.n_indices = out.geometry->indices.size();
+    d.meshes = out.geometry->meshes.data();
+    d.n_meshes = (uint32_t)out.geometry->meshes.size();
     d.instances = out.instances.data();
     d.n_instances = (uint32_t)out.instances.size();
     d.materials = out.materials.data();

@@ -311,6 +311,7 @@ public:
     std::vector<uint32_t> indices;
     uint32_t nTriangles() const { return (uint32_t)(indices.size() / 3); }
     uint32_t poolIndex = 0; /* index into the engine's mesh list */
+    uint64_t uid = nextResourceUid(); /* identity of this mesh object for the flattened geometry pools (addresses can be reused) */
     Model3D *model = nullptr; /* Mesh::m_model */
 };
 class Model3D { /* core/Model3D.hpp */
@@ -611,10 +612,18 @@ class Scene;
 
 /* flattened, POD view of the scene = what crosses the C-ABI (core/Instances.cpp:145-181,
  * vulkan/VulkanInstances.cpp:66-130) */
-struct FlatScene {
+/* The geometry half of a flattened scene: vertex / index pools of the instanced meshes.  Meshes do not change once imported (the
+ * reference uploads them and builds their BLAS at import time, vulkan/resources/VulkanMesh.cpp), so the pools are rebuilt only when
+ * the LIST of instanced meshes changes (key), not on every render() */
+struct GeometryPools {
     std::vector<ptc_vertex> vertices;
     std::vector<uint32_t> indices;
     std::vector<ptc_mesh> meshes;
+    std::vector<uint64_t> key; /* per mesh slot: Mesh::uid, vertex count, index count */
+};
+
+struct FlatScene {
+    std::shared_ptr<const GeometryPools> geometry;
     std::vector<ptc_instance> instances;
     std::vector<ptc_material> materials;
     std::vector<ptc_light_data> lightData;
@@ -822,6 +831,7 @@ private:
     std::vector<std::unique_ptr<Model3D>> m_ownedModels;
     std::vector<std::unique_ptr<EnvironmentMap>> m_envMaps;
     std::vector<Mesh *> m_meshPool;
+    std::shared_ptr<const GeometryPools> m_geometry; /* of the last flatten() */
 };
 
 }  // namespace vengine
