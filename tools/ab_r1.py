@@ -1,5 +1,6 @@
 """A/B of the current library against the round-1 library (built from git 25bcd3b into _lib/libptc_cuda_r1.so) on the SAME box,
-alternating, through the part of the C-ABI both share.  usage: python tools/ab_r1.py Scene[:batches] ..."""
+alternating, through the part of the C-ABI both share.  usage: python tools/ab_r1.py Scene[:batches] ...
+AB_LIBS=label=path,label=path compares other builds of the library instead (experiment variants under _lib/)."""
 import ctypes as C
 import os
 import sys
@@ -44,6 +45,10 @@ def run(path, desc, rp, batches):
     return out, float(rad.reshape(-1, 4)[:, :3].mean())
 
 
+LIBS = [("r1", os.path.join(capi.LIB_DIR, "libptc_cuda_r1.so")), ("now", capi.CUDA_LIB)]
+if os.environ.get("AB_LIBS"):
+    LIBS = [(kv.split("=", 1)[0], os.path.join(ROOT, kv.split("=", 1)[1])) for kv in os.environ["AB_LIBS"].split(",")]
+
 for spec in sys.argv[1:] or ["Cornell:8", "Atrium:4"]:
     name, _, b = spec.partition(":")
     batches = int(b) if b else 4
@@ -51,10 +56,10 @@ for spec in sys.argv[1:] or ["Cornell:8", "Atrium:4"]:
     eng.build_scene(name, texture_size=1024 if name in ("Atrium", "Fog") else 512)
     desc = eng.scene_desc()
     for rnd in range(2):
-        for label, path in (("r1", os.path.join(capi.LIB_DIR, "libptc_cuda_r1.so")), ("now", capi.CUDA_LIB)):
+        for label, path in LIBS:
             res, mean = run(path, desc, eng.render_params(), batches)
             best = max(r[0] for r in res[:3])
             t = res[3]
-            print("%-12s %-4s best of 3: %8.1f Mseg/s (%.2f ms/batch) | timed: extend %.2f shade %.2f chains %.2f | mean %.6f" % (
+            print("%-12s %-5s best of 3: %8.1f Mseg/s (%.2f ms/batch) | timed: extend %.2f shade %.2f chains %.2f | mean %.6f" % (
                 name, label, best, min(r[1] for r in res[:3]), t[2], t[3], t[4], mean), flush=True)
     eng.close()
