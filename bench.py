@@ -203,6 +203,7 @@ def run_cuda(args, rank, world, local_rank):
         eng.comm_init_rank(share_id(eng.comm_unique_id), rank, world)  # plugin leg
         eng.set_render_options(split=args.split)
     ctx.upload_scene(desc)
+    ctx.build_accel()  # the first build of a process also loads the module and sizes its scratch buffers
     ctx.build_accel()
     build_stats = ctx.stats()
     split_mode = capi.PTC_SPLIT_TILE if args.split == "tile" else capi.PTC_SPLIT_SAMPLE
