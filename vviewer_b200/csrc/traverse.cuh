@@ -254,7 +254,8 @@ struct Trav {
                 /* Variants of this test that were measured and rejected (profiles/r1_v4_kernel_experiments.log; the code is in the
                  * history at "k_extend experiments recorded"): near / far plane of an axis in one packed FFMA2 (-4.5 % instructions, -0.7 %
                  * speed), bytes converted through fp16 halves on the FMA pipe (+-0), FMNMX3-only interval test with a sign-byte gather and
-                 * an unpredicated hit mask (+0.3 %), next-node prefetch (-11 %).  The kernel is bound by the dependency chain of its
+                 * an unpredicated hit mask (+0.3 %), next-node prefetch (-11 %); round 2 (profiles/r2_k_extend_cache_hints.log): triangle
+                 * fetches that bypass L1 (-2.4 %, C4 -8 %), evict-last node fetches (+-0).  The kernel is bound by the dependency chain of its
                  * L1-missing fetches at the occupancy the register file allows, not by the instruction count of either pipe. */
 #define TRV_CHILD(J)                                                                                                          \
     {                                                                                                                         \
