@@ -1,6 +1,7 @@
 """A/B of the current library against the round-1 library (built from git 25bcd3b into _lib/libptc_cuda_r1.so) on the SAME box,
 alternating, through the part of the C-ABI both share.  usage: python tools/ab_r1.py Scene[:batches] ...
-AB_LIBS=label=path,label=path compares other builds of the library instead (experiment variants under _lib/)."""
+AB_LIBS=label=path,label=path compares other builds of the library instead (experiment variants under _lib/); a path may carry
+@KEY=VALUE to run that entry with an environment variable set (run-time switches of one build)."""
 import ctypes as C
 import os
 import sys
@@ -17,6 +18,17 @@ class OldStats(C.Structure):  # ptc_stats of round 1
 
 
 def run(path, desc, rp, batches):
+    path, _, setting = path.partition("@")
+    if setting:
+        os.environ[setting.split("=", 1)[0]] = setting.split("=", 1)[1]
+    try:
+        return run_lib(path, desc, rp, batches)
+    finally:
+        if setting:
+            os.environ.pop(setting.split("=", 1)[0], None)
+
+
+def run_lib(path, desc, rp, batches):
     lib = C.CDLL(path, mode=C.RTLD_LOCAL)
     vp = C.c_void_p
     lib.ptc_create.argtypes = [C.POINTER(vp), vp, C.c_int]
