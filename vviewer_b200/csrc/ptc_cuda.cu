@@ -21,6 +21,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -1105,9 +1106,15 @@ void hostCopyParallel(char *dst, const char *src, size_t n) {
     }
     const size_t part = (n / ways + 63) & ~(size_t)63;
     std::vector<std::thread> th;
+    th.reserve(ways);
     for (size_t w = 1; w < ways; w++) {
-        const size_t b = std::min(n, w * part), e = std::min(n, (w + 1) * part);
-        if (e > b) th.emplace_back([=] { std::memcpy(dst + b, src + b, e - b); });
+        const size_t b = std::min(n, w * part), e = w + 1 == ways ? n : std::min(n, (w + 1) * part);
+        if (e <= b) continue;
+        try {
+            th.emplace_back([=] { std::memcpy(dst + b, src + b, e - b); });
+        } catch (const std::system_error &) { /* no thread to be had: this part is copied here */
+            std::memcpy(dst + b, src + b, e - b);
+        }
     }
     std::memcpy(dst, src, std::min(n, part));
     for (auto &t : th) t.join();
