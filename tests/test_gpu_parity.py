@@ -543,11 +543,14 @@ def test_texture_identity_cache(capi):
     cu.close()
 
 
-@pytest.mark.parametrize("mode", ["tile", "sample"])
-def test_partition_sums_to_full_render(capi, engine, mode):
+@pytest.mark.parametrize("mode,w,h,tile", [("tile", 160, 96, 32), ("sample", 160, 96, 32),
+                                             ("tile", 150, 90, 32),   # ragged tiles at the right and bottom edges
+                                             ("tile", 37, 29, 32),    # two tiles for three ranks: one rank owns no pixel
+                                             ("tile", 33, 17, 0)])    # tile_size 0 = the default edge of 32
+def test_partition_sums_to_full_render(capi, engine, mode, w, h, tile):
     import partition_util as parallel
     engine.build_scene("MeshLight")
-    engine.set_render_info(width=160, height=96, samples=16, batch_size=4)
+    engine.set_render_info(width=w, height=h, samples=16, batch_size=4)
     cu = capi.Context(capi.load_cuda())
     cu.upload_scene(engine.scene_desc())
     cu.build_accel()
@@ -557,7 +560,7 @@ def test_partition_sums_to_full_render(capi, engine, mode):
     total = np.zeros_like(full)
     seg = 0
     for r in range(world):
-        rp = parallel.partition(engine.render_params(), r, world, mode, tile_size=32)
+        rp = parallel.partition(engine.render_params(), r, world, mode, tile_size=tile)
         part = np.stack(cu.render(rp))
         total += part
         seg += cu.stats()["segments"]

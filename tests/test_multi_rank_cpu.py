@@ -78,3 +78,33 @@ def test_batches_of_rank():
     assert [parallel.batches_of_rank(1024, 16, r, 8, "sample") for r in range(8)] == [8] * 8
     assert [parallel.batches_of_rank(70, 16, r, 3, "sample") for r in range(3)] == [2, 1, 1]
     assert parallel.batches_of_rank(70, 16, 1, 3, "tile") == 4
+
+
+@pytest.mark.parametrize("w,h,tile,world", [(50, 37, 16, 3), (37, 29, 32, 3), (33, 17, 0, 2)])
+def test_ragged_tiles_and_ranks_without_pixels(capi, w, h, tile, world):
+    """tile split on image sizes that are no multiple of the tile edge, with more ranks than tiles (a rank that owns no pixel renders
+    nothing and returns zeros) and with tile_size 0 (= 32): the parts still sum to the full render, alpha included (oracle; the
+    CUDA core runs the same cases in test_gpu_parity.test_partition_sums_to_full_render)"""
+    import partition_util as parallel
+    from oracle import loader as oracle_loader
+    eng = capi.HostEngine()
+    eng.build_scene("MeshLight")
+    eng.set_render_info(width=w, height=h, samples=4, batch_size=2)
+    ctx = capi.Context(oracle_loader.load_oracle())
+    ctx.upload_scene(eng.scene_desc())
+    ctx.build_accel()
+    full = np.stack(ctx.render(eng.render_params()))
+    total = np.zeros_like(full)
+    owned = []
+    for r in range(world):
+        part = np.stack(ctx.render(parallel.partition(eng.render_params(), r, world, "tile", tile_size=tile)))
+        owned.append(int(np.count_nonzero(part[1].reshape(-1, 4)[:, :3].any(axis=1) | part[0].reshape(-1, 4)[:, :3].any(axis=1))))
+        total += part
+    assert np.allclose(total[..., :3], full[..., :3], rtol=1e-5, atol=1e-6)
+    assert np.all(total[..., 3] == 1.0)
+    edge = tile or 32
+    n_tiles = -(-w // edge) * -(-h // edge)
+    if n_tiles < world:
+        assert owned.count(0) >= world - n_tiles
+    ctx.close()
+    eng.close()
