@@ -849,7 +849,15 @@ void forEachDev(ptc_ctx *ctx, Fn &&fn) {
         body(0);
     } else {
         std::vector<std::thread> th;
-        for (size_t i = 0; i < n; i++) th.emplace_back(body, i);
+        th.reserve(n);
+        for (size_t i = 0; i < n; i++) {
+            try {
+                th.emplace_back(body, i);
+            } catch (const std::system_error &e) { /* joinable threads must not be destroyed: report and stop starting more */
+                errs[i] = std::string("cannot start the device thread: ") + e.what();
+                break;
+            }
+        }
         for (auto &t : th) t.join();
     }
     for (size_t i = 0; i < n; i++)
