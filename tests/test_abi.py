@@ -96,3 +96,19 @@ def test_product_does_not_reference_oracle():
     import inspect
     assert "backend" not in inspect.signature(capi.HostEngine.__init__).parameters
     assert "backend_lib" not in open(os.path.join(ROOT, "include", "vengine_host.h")).read()
+
+
+@pytest.mark.parametrize("header", ["ptc.h", "vengine_host.h"])
+def test_public_headers_are_plain_c(header, tmp_path):
+    """the drop-in boundary is a C ABI: the headers must compile as C11 (what a cgo / JNI / ctypes-generator binding consumes) and as
+    C++17 (the reference's language) without any other include"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "use.c"
+    src.write_text('#include "%s"\nint main(void) { return 0; }\n' % header)
+    for cc, std in (("gcc", "-std=c11"), ("g++", "-std=c++17")):
+        cmd = [cc, std, "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(root, "include")]
+        if cc == "g++":
+            cmd += ["-x", "c++"]
+        r = subprocess.run(cmd + [str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, "%s %s: %s" % (cc, header, r.stderr[:2000])
