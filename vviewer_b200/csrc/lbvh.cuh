@@ -61,11 +61,28 @@ PTC_D float xformRow(const float *r, float x, float y, float z) {
     return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[0], x), __fmul_rn(r[1], y)), __fmul_rn(r[2], z)), r[3]);
 }
 
-__global__ void k_flatten(const ptc_vertex *__restrict__ vertices, const uint32_t *__restrict__ indices,
+/* Fixed-size records (WORDS float4 each, one per thread) leave a block through shared memory: written record by record they would be
+ * 16-byte stores at a stride of WORDS * 16 bytes (32 partly written sectors per warp instruction); staged, the block writes its
+ * contiguous WORDS * 256 words with consecutive threads on consecutive words.  Every thread of the block must call this (barrier);
+ * valid = the number of leading threads of the block that hold a record. */
+#define RECORD_BLOCK 256
+template <int WORDS>
+PTC_D void storeRecords(float4 *__restrict__ out, uint32_t firstRecord, uint32_t valid, const float4 (&rec)[WORDS], float4 *stage) {
+#pragma unroll
+    for (int r = 0; r < WORDS; r++) stage[threadIdx.x * WORDS + r] = rec[r];
+    __syncthreads();
+    float4 *dst = out + (size_t)WORDS * firstRecord;
+    const uint32_t total = (uint32_t)WORDS * valid;
+    for (uint32_t j = threadIdx.x; j < total; j += RECORD_BLOCK) dst[j] = stage[j];
+}
+
+__global__ void __launch_bounds__(RECORD_BLOCK) k_flatten(const ptc_vertex *__restrict__ vertices, const uint32_t *__restrict__ indices,
                           const DInstance *__restrict__ instances, uint32_t nInstances, uint32_t nTris, float4 *__restrict__ triOut,
                           float4 *__restrict__ boundsLo, float4 *__restrict__ boundsHi, uint32_t *__restrict__ sceneBounds) {
+    __shared__ float4 stage[3 * RECORD_BLOCK];
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float3 lo = f3(3.4e38f), hi = f3(-3.4e38f);
+    float4 rec[3] = {};
     if (i < nTris) {
         /* binary search of the owning instance in the world-triangle prefix */
         uint32_t a = 0, b = nInstances;
@@ -85,9 +102,9 @@ __global__ void k_flatten(const ptc_vertex *__restrict__ vertices, const uint32_
         }
         float3 e1 = f3(__fsub_rn(p[1].x, p[0].x), __fsub_rn(p[1].y, p[0].y), __fsub_rn(p[1].z, p[0].z));
         float3 e2 = f3(__fsub_rn(p[2].x, p[0].x), __fsub_rn(p[2].y, p[0].y), __fsub_rn(p[2].z, p[0].z));
-        triOut[3 * (size_t)i + 0] = make_float4(p[0].x, p[0].y, p[0].z, __uint_as_float(a));
-        triOut[3 * (size_t)i + 1] = make_float4(e1.x, e1.y, e1.z, __uint_as_float(prim));
-        triOut[3 * (size_t)i + 2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
+        rec[0] = make_float4(p[0].x, p[0].y, p[0].z, __uint_as_float(a));
+        rec[1] = make_float4(e1.x, e1.y, e1.z, __uint_as_float(prim));
+        rec[2] = make_float4(e2.x, e2.y, e2.z, 0.0f);
         /* bounds over (v0, v0 + e1, v0 + e2), exactly what the oracle's triBounds does */
         float3 q1 = f3(__fadd_rn(p[0].x, e1.x), __fadd_rn(p[0].y, e1.y), __fadd_rn(p[0].z, e1.z));
         float3 q2 = f3(__fadd_rn(p[0].x, e2.x), __fadd_rn(p[0].y, e2.y), __fadd_rn(p[0].z, e2.z));
@@ -95,6 +112,10 @@ __global__ void k_flatten(const ptc_vertex *__restrict__ vertices, const uint32_
         hi = fmax3(p[0], fmax3(q1, q2));
         boundsLo[i] = make_float4(lo.x, lo.y, lo.z, 0.0f);
         boundsHi[i] = make_float4(hi.x, hi.y, hi.z, 0.0f);
+    }
+    {
+        const uint32_t first = blockIdx.x * RECORD_BLOCK;
+        storeRecords<3>(triOut, first, first < nTris ? min((uint32_t)RECORD_BLOCK, nTris - first) : 0u, rec, stage);
     }
     /* warp reduce then one atomic per warp and component */
 #pragma unroll
@@ -783,43 +804,49 @@ __global__ void __launch_bounds__(WIDE_BLOCK) k_wide_all(uint32_t n, int32_t bin
 }
 
 /* triangles in wide-node order: position k holds sorted triangle triMap[k] = world triangle order[triMap[k]] */
-__global__ void k_gather_tris(uint32_t n, const uint32_t *__restrict__ triMap, const uint32_t *__restrict__ order, const float4 *__restrict__ in,
-                              float4 *__restrict__ out, uint32_t *__restrict__ wideOrder) {
-    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    uint32_t t = order[triMap[k]];
-    float4 a = in[3 * (size_t)t + 0], b = in[3 * (size_t)t + 1], c = in[3 * (size_t)t + 2];
-    c.w = __uint_as_float(t); /* world triangle id: the tie-break key of the hit rule */
-    out[3 * (size_t)k + 0] = a;
-    out[3 * (size_t)k + 1] = b;
-    out[3 * (size_t)k + 2] = c;
-    wideOrder[k] = t;
+__global__ void __launch_bounds__(RECORD_BLOCK) k_gather_tris(uint32_t n, const uint32_t *__restrict__ triMap, const uint32_t *__restrict__ order,
+                                                              const float4 *__restrict__ in, float4 *__restrict__ out, uint32_t *__restrict__ wideOrder) {
+    __shared__ float4 stage[3 * RECORD_BLOCK];
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    float4 rec[3] = {};
+    if (k < n) {
+        const uint32_t t = order[triMap[k]];
+        rec[0] = in[3 * (size_t)t + 0], rec[1] = in[3 * (size_t)t + 1], rec[2] = in[3 * (size_t)t + 2];
+        rec[2].w = __uint_as_float(t); /* world triangle id: the tie-break key of the hit rule */
+        wideOrder[k] = t;
+    }
+    const uint32_t first = blockIdx.x * RECORD_BLOCK;
+    storeRecords<3>(out, first, first < n ? min((uint32_t)RECORD_BLOCK, n - first) : 0u, rec, stage);
 }
 
 /* Shading records, one per triangle in traversal order, 9 x float4 = 144 B, object space (same numbers the reference's
  * closest-hit shaders fetch through InstanceData -> index buffer -> 3 x Vertex, process_hit.glsl:1-17, in one contiguous read):
  *   r0 = (p0, uv0.x) r1 = (p1, uv0.y) r2 = (p2, uv1.x) r3 = (n0, uv1.y) r4 = (n1, uv2.x) r5 = (n2, uv2.y)
  *   r6 = (tangent0, bits(instance)) r7 = (tangent1, bits(primitive)) r8 = (tangent2, 0) */
-__global__ void k_gather_shading(uint32_t n, const uint32_t *__restrict__ wideOrder, const float4 *__restrict__ trisUnsorted,
-                                 const ptc_vertex *__restrict__ vertices, const uint32_t *__restrict__ indices,
-                                 const DInstance *__restrict__ instances, float4 *__restrict__ out) {
+__global__ void __launch_bounds__(RECORD_BLOCK) k_gather_shading(uint32_t n, const uint32_t *__restrict__ wideOrder, const float4 *__restrict__ trisUnsorted,
+                                                                 const ptc_vertex *__restrict__ vertices, const uint32_t *__restrict__ indices,
+                                                                 const DInstance *__restrict__ instances, float4 *__restrict__ out) {
+    __shared__ float4 stage[9 * RECORD_BLOCK];
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const uint32_t t = wideOrder[k];
-    const uint32_t inst = __float_as_uint(trisUnsorted[3 * (size_t)t + 0].w), prim = __float_as_uint(trisUnsorted[3 * (size_t)t + 1].w);
-    const DInstance &I = instances[inst];
-    const uint32_t *ind = indices + I.firstIndex + 3 * (size_t)prim;
-    const ptc_vertex &a = vertices[I.firstVertex + ind[0]], &b = vertices[I.firstVertex + ind[1]], &c = vertices[I.firstVertex + ind[2]];
-    float4 *r = out + 9 * (size_t)k;
-    r[0] = make_float4(a.position[0], a.position[1], a.position[2], a.uv[0]);
-    r[1] = make_float4(b.position[0], b.position[1], b.position[2], a.uv[1]);
-    r[2] = make_float4(c.position[0], c.position[1], c.position[2], b.uv[0]);
-    r[3] = make_float4(a.normal[0], a.normal[1], a.normal[2], b.uv[1]);
-    r[4] = make_float4(b.normal[0], b.normal[1], b.normal[2], c.uv[0]);
-    r[5] = make_float4(c.normal[0], c.normal[1], c.normal[2], c.uv[1]);
-    r[6] = make_float4(a.tangent[0], a.tangent[1], a.tangent[2], __uint_as_float(inst));
-    r[7] = make_float4(b.tangent[0], b.tangent[1], b.tangent[2], __uint_as_float(prim));
-    r[8] = make_float4(c.tangent[0], c.tangent[1], c.tangent[2], 0.0f);
+    float4 r[9] = {};
+    if (k < n) {
+        const uint32_t t = wideOrder[k];
+        const uint32_t inst = __float_as_uint(trisUnsorted[3 * (size_t)t + 0].w), prim = __float_as_uint(trisUnsorted[3 * (size_t)t + 1].w);
+        const DInstance &I = instances[inst];
+        const uint32_t *ind = indices + I.firstIndex + 3 * (size_t)prim;
+        const ptc_vertex &a = vertices[I.firstVertex + ind[0]], &b = vertices[I.firstVertex + ind[1]], &c = vertices[I.firstVertex + ind[2]];
+        r[0] = make_float4(a.position[0], a.position[1], a.position[2], a.uv[0]);
+        r[1] = make_float4(b.position[0], b.position[1], b.position[2], a.uv[1]);
+        r[2] = make_float4(c.position[0], c.position[1], c.position[2], b.uv[0]);
+        r[3] = make_float4(a.normal[0], a.normal[1], a.normal[2], b.uv[1]);
+        r[4] = make_float4(b.normal[0], b.normal[1], b.normal[2], c.uv[0]);
+        r[5] = make_float4(c.normal[0], c.normal[1], c.normal[2], c.uv[1]);
+        r[6] = make_float4(a.tangent[0], a.tangent[1], a.tangent[2], __uint_as_float(inst));
+        r[7] = make_float4(b.tangent[0], b.tangent[1], b.tangent[2], __uint_as_float(prim));
+        r[8] = make_float4(c.tangent[0], c.tangent[1], c.tangent[2], 0.0f);
+    }
+    const uint32_t first = blockIdx.x * RECORD_BLOCK;
+    storeRecords<9>(out, first, first < n ? min((uint32_t)RECORD_BLOCK, n - first) : 0u, r, stage);
 }
 
 /* the traversal stack holds one postponed node group per level of the wide tree (traverse.cuh); its capacity is fixed */
@@ -1018,16 +1045,16 @@ struct Build {
         const int B = 256;
         const uint32_t G = (n + B - 1) / B;
         int launches = 0;
-        k_flatten<<<G, B, 0, s>>>(vertices, indices, instances, nInstances, n, trisUnsorted.p, triLo.p, triHi.p, sceneBounds.p);
+        k_flatten<<<G, RECORD_BLOCK, 0, s>>>(vertices, indices, instances, nInstances, n, trisUnsorted.p, triLo.p, triHi.p, sceneBounds.p);
         launches++;
         launches += buildFromBounds(s);
         const auto tCollapsed = now();
         trav.alloc(5 * (size_t)nWide + 3 * (size_t)n);
         CUDA_TRY(cudaMemcpyAsync(trav.p, wide.p, (size_t)nWide * 80, cudaMemcpyDeviceToDevice, s));
-        k_gather_tris<<<G, B, 0, s>>>(n, triMap.p, order.p, trisUnsorted.p, trav.p + 5 * (size_t)nWide, wideOrder.p);
+        k_gather_tris<<<G, RECORD_BLOCK, 0, s>>>(n, triMap.p, order.p, trisUnsorted.p, trav.p + 5 * (size_t)nWide, wideOrder.p);
         launches++;
         shading.alloc(9 * (size_t)n);
-        k_gather_shading<<<G, B, 0, s>>>(n, wideOrder.p, trisUnsorted.p, vertices, indices, instances, shading.p);
+        k_gather_shading<<<G, RECORD_BLOCK, 0, s>>>(n, wideOrder.p, trisUnsorted.p, vertices, indices, instances, shading.p);
         launches++;
         CUDA_TRY(cudaGetLastError());
         if (verbose) {
