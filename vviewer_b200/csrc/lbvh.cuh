@@ -451,27 +451,29 @@ __global__ void __launch_bounds__(PLOC_BLOCK) k_ploc_all(uint32_t n, int radius,
         /* (A) */
         const uint32_t tiles = (c + PLOC_BLOCK - 1) / PLOC_BLOCK;
         for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const int64_t base = (int64_t)tile * PLOC_BLOCK - radius;
+            /* (positions are below 2^31 - the scene upload refuses more triangles - so 32-bit signed arithmetic is exact) */
+            const int32_t base = (int32_t)(tile * PLOC_BLOCK) - radius;
             for (int k = threadIdx.x; k < PLOC_BLOCK + 2 * radius; k += PLOC_BLOCK) {
-                const int64_t g = base + k;
-                if (g >= 0 && g < (int64_t)c) {
+                const int32_t g = base + k;
+                if (g >= 0 && g < (int32_t)c) {
                     sLo[k] = __ldcg(&cLo[g]);
                     sHi[k] = __ldcg(&cHi[g]);
                 }
             }
             __syncthreads();
-            const int64_t i = (int64_t)tile * PLOC_BLOCK + threadIdx.x;
-            if (i < (int64_t)c) {
+            const int32_t i = (int32_t)(tile * PLOC_BLOCK + threadIdx.x);
+            if (i < (int32_t)c) {
                 const float4 lo = sLo[threadIdx.x + radius], hi = sHi[threadIdx.x + radius];
                 float bestA = 0.0f;
-                int64_t best = -1;
-                for (int dj = -radius; dj <= radius; dj++) {
-                    const int64_t j = i + dj;
-                    if (dj == 0 || j < 0 || j >= (int64_t)c) continue;
+                int32_t best = -1;
+                /* the window clipped to the array once, instead of two range tests per candidate */
+                const int djLo = max(-radius, -i), djHi = min(radius, (int32_t)c - 1 - i);
+                for (int dj = djLo; dj <= djHi; dj++) {
+                    if (dj == 0) continue;
                     const float a = mergedHalfArea(lo, hi, sLo[threadIdx.x + radius + dj], sHi[threadIdx.x + radius + dj]);
                     if (best < 0 || a < bestA) { /* ascending j and strict <: the smallest position wins ties */
                         bestA = a;
-                        best = j;
+                        best = i + dj;
                     }
                 }
                 nn[i] = (uint32_t)best;
