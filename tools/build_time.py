@@ -1,12 +1,12 @@
 """Acceleration-structure build time per scene (CUDA events inside ptc_build_accel), first build (allocations) and rebuilds.
-usage: python tools/build_time.py Scene[:scale] ..."""
+usage: python tools/build_time.py Scene[:scale] ...   (BUILD_LIB=path times another build of the library, e.g. an experiment variant)"""
 import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vviewer_b200 import capi  # noqa: E402
 
-cuda = capi.load_cuda()
+cuda = capi.load_ptc(os.environ["BUILD_LIB"]) if os.environ.get("BUILD_LIB") else capi.load_cuda()
 for spec in sys.argv[1:] or ["Cornell", "Atrium", "Instanced:0.25"]:
     name, _, scale = spec.partition(":")
     eng = capi.HostEngine()

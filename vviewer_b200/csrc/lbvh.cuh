@@ -433,7 +433,10 @@ struct PlocResult {
  * is the larger position of a mutual pair; every block sums the flags of its contiguous chunk, (C) exclusive prefix over the blocks
  * + scan inside the chunk = node numbers (creation order = position order) and compacted positions; the pairs become nodes.  The
  * cluster count and the node counter live in registers of every thread (all blocks compute the same totals). */
-__global__ void __launch_bounds__(PLOC_BLOCK) k_ploc_all(uint32_t n, int radius, int32_t *cid0, int32_t *cid1, float4 *cLo0, float4 *cLo1, float4 *cHi0, float4 *cHi1,
+#ifndef PLOC_MINBLOCKS
+#define PLOC_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(PLOC_BLOCK, PLOC_MINBLOCKS) k_ploc_all(uint32_t n, int radius, int32_t *cid0, int32_t *cid1, float4 *cLo0, float4 *cLo1, float4 *cHi0, float4 *cHi1,
                                                          uint32_t *__restrict__ nn, int32_t *__restrict__ parent, int32_t *__restrict__ left, int32_t *__restrict__ right,
                                                          uint32_t *__restrict__ subCount, float4 *__restrict__ nodeLo, float4 *__restrict__ nodeHi, uint32_t *__restrict__ bigNodes,
                                                          uint2 *__restrict__ blockSums, PlocResult *__restrict__ result) {
@@ -747,7 +750,10 @@ struct WideResult {
  * (1) every wide node of the level chooses its children (wideSelect); blocks own contiguous chunks and sum their (internal
  * children, triangles); (2) prefix over the blocks + scan inside the chunk = first child index / first triangle position of every
  * node; wideEmit writes the nodes and the roots of the next level. */
-__global__ void __launch_bounds__(WIDE_BLOCK) k_wide_all(uint32_t n, int32_t binaryRoot, uint32_t maxWide, int32_t *__restrict__ rootOf, const int32_t *__restrict__ left,
+#ifndef WIDE_MINBLOCKS
+#define WIDE_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(WIDE_BLOCK, WIDE_MINBLOCKS) k_wide_all(uint32_t n, int32_t binaryRoot, uint32_t maxWide, int32_t *__restrict__ rootOf, const int32_t *__restrict__ left,
                                                          const int32_t *__restrict__ right, const uint32_t *__restrict__ subCount, const float4 *__restrict__ nodeLo,
                                                          const float4 *__restrict__ nodeHi, WideTmp *__restrict__ tmp, uint2 *__restrict__ counts, uint4 *__restrict__ wide,
                                                          uint32_t *__restrict__ triMap, uint2 *__restrict__ blockSums, WideResult *__restrict__ result) {
@@ -896,6 +902,7 @@ struct Build {
         CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, block, 0));
         if (perSm < 1) throw CudaError{"cooperative kernel does not fit on an SM"};
+        if (const char *e = getenv("PTC_COOP_BLOCKS")) capPerSm = std::max(1, atoi(e)); /* experiments: resident blocks per SM of the build's cooperative kernels */
         return sms * std::min(perSm, capPerSm);
     }
 

@@ -88,7 +88,10 @@ __global__ void __launch_bounds__(1024) k_radix_scan(uint32_t *__restrict__ tabl
     }
 }
 
-__global__ void __launch_bounds__(RADIX_THREADS) k_radix_scatter(const uint64_t *__restrict__ keysIn, const uint32_t *__restrict__ valsIn, uint32_t n, uint32_t chunk, int shift,
+#ifndef RADIX_MINBLOCKS
+#define RADIX_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(RADIX_THREADS, RADIX_MINBLOCKS) k_radix_scatter(const uint64_t *__restrict__ keysIn, const uint32_t *__restrict__ valsIn, uint32_t n, uint32_t chunk, int shift,
                                                                  const uint32_t *__restrict__ table, uint64_t *__restrict__ keysOut, uint32_t *__restrict__ valsOut) {
     constexpr int WARPS = RADIX_THREADS / 32;
     __shared__ uint32_t digitBase[256];          /* where the next key of each digit goes (global position) */
